@@ -1,0 +1,327 @@
+// Streaming (HBM-bound) stages and the small glue kernels between the solvers.
+//
+//  k_class_mean     condition averaging: mean over the trials of each class
+//                   (reference alignment/alignment_utils.py:42-61 cnd_avg, :12-39
+//                   extract_group_conditions).  Trials stay in their native
+//                   [trial][time][channel] layout; each thread owns a float4 of the
+//                   (time, channel) plane and walks the class's member list.
+//  k_center_rows    subtract a column-mean vector from a row block in place.
+//  k_copy_rows      strided batched 2-D copy.
+//  k_mcca_*         assemble / back-transform the MCCA generalised eigenproblem
+//                   (mvlearn _i_mcca 'gevp' form used through AlignMCCA.py:152-153).
+//  k_scores_*       PCA scores of train / test trials from the Gram eigen-pairs.
+#include "common.cuh"
+#include "descs.h"
+
+namespace {
+
+__global__ void __launch_bounds__(256)
+k_class_mean(const cpsd_class_mean_desc* __restrict__ descs) {
+  const cpsd_class_mean_desc d = descs[blockIdx.z];
+  const int slot = blockIdx.y;
+  if (slot >= d.nslot) return;
+  const int b = d.member_ptr[slot], e = d.member_ptr[slot + 1];
+  const float inv = (e > b) ? 1.f / (float)(e - b) : 0.f;
+  float* o = d.out + (long long)slot * d.TC;
+  if ((d.TC & 3) == 0 && ((((uintptr_t)d.X) | ((uintptr_t)d.out)) & 15) == 0) {
+    const int n4 = d.TC >> 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int m = b; m < e; ++m) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(d.X + (long long)d.members[m] * d.TC) + i);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+      reinterpret_cast<float4*>(o)[i] = acc;
+    }
+  } else {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.TC; i += gridDim.x * blockDim.x) {
+      float acc = 0.f;
+      for (int m = b; m < e; ++m) acc += d.X[(long long)d.members[m] * d.TC + i];
+      o[i] = acc * inv;
+    }
+  }
+}
+
+// Z[p][r][c] -= mu[p][c]   r < nrows[p]
+__global__ void __launch_bounds__(256)
+k_center_rows(float* __restrict__ Z, int ld, long long strideZ, const float* __restrict__ mu,
+              int ldmu, const int* __restrict__ nrows_dev, int nrows_fixed, int ncols) {
+  const int p = blockIdx.z;
+  const int nrows = nrows_dev ? nrows_dev[p] : nrows_fixed;
+  float* Zp = Z + (long long)p * strideZ;
+  const float* mp = mu + (long long)p * ldmu;
+  for (int r = blockIdx.y; r < nrows; r += gridDim.y) {
+    float* row = Zp + (long long)r * ld;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncols; c += gridDim.x * blockDim.x)
+      row[c] -= mp[c];
+  }
+}
+
+// dst[p][r][c] = src[p][r0[p] + r][c]
+__global__ void __launch_bounds__(256)
+k_copy_rows(const float* __restrict__ src, int lds, long long strideS, float* __restrict__ dst,
+            int ldd, long long strideD, const int* __restrict__ r0_dev, int r0_fixed, int nrows,
+            int ncols) {
+  const int p = blockIdx.z;
+  const int r0 = r0_dev ? r0_dev[p] : r0_fixed;
+  for (int r = blockIdx.y; r < nrows; r += gridDim.y) {
+    const float* s = src + (long long)p * strideS + (long long)(r0 + r) * lds;
+    float* d = dst + (long long)p * strideD + (long long)r * ldd;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncols; c += gridDim.x * blockDim.x)
+      d[c] = s[c];
+  }
+}
+
+// ------------------------------------------------------------------------------- MCCA
+// Per (fold, view): keep the leading r = min(R, rank, n_valid) principal directions of the
+// centred condition averages.  Vr (C x R, zero beyond r), d2 [R] squared singular values.
+__global__ void __launch_bounds__(128)
+k_mcca_mask(const float* __restrict__ evecs, int ldv, long long strideV,
+            const float* __restrict__ evals, int ld_e, const int* __restrict__ rank,
+            const int* __restrict__ cdim, int R, int Cmax, float* __restrict__ Vr,
+            float* __restrict__ d2, int* __restrict__ r_eff) {
+  const int p = blockIdx.x;  // fold * P + view
+  const int C = cdim[p];
+  int r = rank ? rank[p] : R;
+  if (r > R) r = R;
+  if (r > C) r = C;
+  if (r < 0) r = 0;
+  const float* V = evecs + (long long)p * strideV;
+  float* o = Vr + (long long)p * Cmax * R;
+  for (int e = threadIdx.x; e < Cmax * R; e += blockDim.x) {
+    const int c = e / R, j = e - c * R;
+    o[e] = (c < C && j < r) ? V[(long long)c * ldv + j] : 0.f;
+  }
+  for (int j = threadIdx.x; j < R; j += blockDim.x)
+    d2[(long long)p * R + j] = (j < r) ? fmaxf(evals[(long long)p * ld_e + j], 0.f) : 0.f;
+  if (threadIdx.x == 0) r_eff[p] = r;
+}
+
+// Per fold: compact the P*R reduced coordinates to the n = sum_v r_v valid ones and write
+// the whitened SUMCOR matrix  M = Dh^-1/2 LHS Dh^-1/2  (unit diagonal, zero inside a view,
+// scaled cross-scatter between views).  reg < 0 means regs=None.
+__global__ void __launch_bounds__(256)
+k_mcca_build(const float* __restrict__ G, int ldg, long long strideG, const int* __restrict__ r_eff,
+             int P, int R, float reg, float* __restrict__ M, int ldm, long long strideM,
+             int* __restrict__ n_out, int* __restrict__ cidx, float* __restrict__ dh, int n_comp,
+             int* __restrict__ status) {
+  extern __shared__ int sh[];
+  int* cmap = sh;                   // compact -> padded index
+  float* dhs = reinterpret_cast<float*>(sh + P * R);
+  __shared__ int n_s;
+  const int f = blockIdx.x;
+  const float* Gf = G + (long long)f * strideG;
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int v = 0; v < P; ++v) {
+      const int r = r_eff[f * P + v];
+      for (int j = 0; j < r; ++j) cmap[n++] = v * R + j;
+    }
+    n_s = n;
+    n_out[f] = n;
+    if (status && n < n_comp) status[f] = 1;
+  }
+  __syncthreads();
+  const int n = n_s;
+  for (int a = threadIdx.x; a < P * R; a += blockDim.x) {
+    float d = 0.f;
+    if (a < n) {
+      const int ia = cmap[a];
+      const float gaa = Gf[(long long)ia * ldg + ia];
+      d = (reg >= 0.f) ? (1.f - reg) * gaa + reg : gaa;
+      dhs[a] = d;
+    }
+    cidx[(long long)f * P * R + a] = (a < n) ? cmap[a] : -1;
+    dh[(long long)f * P * R + a] = d;
+  }
+  __syncthreads();
+  float* Mf = M + (long long)f * strideM;
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int a = e / n, b = e - a * n;
+    const int ia = cmap[a], ib = cmap[b];
+    float v;
+    if (a == b) v = 1.f;
+    else if (ia / R == ib / R) v = 0.f;
+    else v = Gf[(long long)ia * ldg + ib] * rsqrtf(dhs[a] * dhs[b]);
+    Mf[(long long)a * ldm + b] = v;
+  }
+}
+
+// loadings[f][v] (Cmax x n_comp) = Vr[f][v] (Cmax x R) @ ( Dh^-1/2 u )[rows of view v]
+// u: eigenvectors of M; column q is U[row][perm ? perm[q] : q].
+__global__ void __launch_bounds__(128)
+k_mcca_loadings(const float* __restrict__ Vr, const float* __restrict__ U, int ldu,
+                long long strideU, const int* __restrict__ perm, int ld_perm,
+                const int* __restrict__ r_eff, const float* __restrict__ dh, int P, int R,
+                int Cmax, int n_comp, float* __restrict__ L, int ldl) {
+  const int p = blockIdx.x;  // fold * P + view
+  const int f = p / P, v = p - f * P;
+  int off = 0;
+  for (int u = 0; u < v; ++u) off += r_eff[f * P + u];
+  const int r = r_eff[p];
+  const float* Uf = U + (long long)f * strideU;
+  const float* Vp = Vr + (long long)p * Cmax * R;
+  const float* dhf = dh + (long long)f * P * R;
+  float* Lp = L + (long long)p * Cmax * ldl;
+  for (int e = threadIdx.x; e < Cmax * n_comp; e += blockDim.x) {
+    const int c = e / n_comp, q = e - c * n_comp;
+    const int col = perm ? perm[(long long)f * ld_perm + q] : q;
+    float acc = 0.f;
+    for (int j = 0; j < r; ++j)
+      acc = fmaf(Vp[c * R + j], Uf[(long long)(off + j) * ldu + col] * rsqrtf(dhf[off + j]), acc);
+    Lp[(long long)c * ldl + q] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------- PCA scores
+// St[f][j][i] = V[f][i][perm[j]] * sqrt(max(lambda_j, 0))     j < k[f], i < n[f]
+__global__ void __launch_bounds__(256)
+k_scores_train(const float* __restrict__ V, int ldv, long long strideV,
+               const float* __restrict__ evals, const int* __restrict__ perm, int ld_e,
+               const int* __restrict__ k_dev, const int* __restrict__ n_dev, int n_fixed,
+               float* __restrict__ St, int lds, long long strideS, int kcap) {
+  const int f = blockIdx.z;
+  const int k = min(k_dev[f], kcap);
+  const int n = n_dev ? n_dev[f] : n_fixed;
+  const float* Vf = V + (long long)f * strideV;
+  float* Sf = St + (long long)f * strideS;
+  for (int j = blockIdx.y; j < k; j += gridDim.y) {
+    const float sc = sqrtf(fmaxf(evals[(long long)f * ld_e + j], 0.f));
+    const int col = perm ? perm[(long long)f * ld_e + j] : j;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+      Sf[(long long)j * lds + i] = Vf[(long long)i * ldv + col] * sc;
+  }
+}
+
+// Ste[f][j][t] = ( sum_i Kte[f][t][i] V[f][i][perm[j]] ) / sqrt(lambda_j)
+__global__ void __launch_bounds__(128)
+k_scores_test(const float* __restrict__ Kte, int ldk, long long strideK,
+              const float* __restrict__ V, int ldv, long long strideV,
+              const float* __restrict__ evals, const int* __restrict__ perm, int ld_e,
+              const int* __restrict__ k_dev, const int* __restrict__ n_dev, int n_fixed,
+              int n_te, float* __restrict__ Ste, int ldt, long long strideT, int kcap) {
+  const int f = blockIdx.z;
+  const int k = min(k_dev[f], kcap);
+  const int n = n_dev ? n_dev[f] : n_fixed;
+  const int t = blockIdx.y;
+  if (t >= n_te) return;
+  const float* Vf = V + (long long)f * strideV;
+  const float* kr = Kte + (long long)f * strideK + (long long)t * ldk;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < k; j += gridDim.x * blockDim.x) {
+    const int col = perm ? perm[(long long)f * ld_e + j] : j;
+    float acc = 0.f;
+    for (int i = 0; i < n; ++i) acc = fmaf(kr[i], Vf[(long long)i * ldv + col], acc);
+    const float lam = evals[(long long)f * ld_e + j];
+    Ste[(long long)f * strideT + (long long)j * ldt + t] = (lam > 0.f) ? acc * rsqrtf(lam) : 0.f;
+  }
+}
+
+}  // namespace
+
+extern "C" int cpsd_class_mean(const cpsd_class_mean_desc* descs_dev, int nprob, int nslot_max,
+                               int TC, cudaStream_t stream) {
+  CPSD_CHECK_ARG(nprob >= 0 && nslot_max >= 0 && TC > 0, "class_mean: bad dims");
+  if (nprob == 0 || nslot_max == 0) return CPSD_OK;
+  CPSD_CHECK_ARG(nslot_max <= 65535 && nprob <= 65535, "class_mean: grid too large");
+  int bx = (TC / 4 + 255) / 256;
+  if (bx > 32) bx = 32;
+  if (bx < 1) bx = 1;
+  k_class_mean<<<dim3(bx, nslot_max, nprob), 256, 0, stream>>>(descs_dev);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
+
+extern "C" int cpsd_center_rows(float* Z, int ld, long long strideZ, const float* mu, int ldmu,
+                                const int* nrows_dev, int nrows_fixed, int nrows_max, int ncols,
+                                int nprob, cudaStream_t stream) {
+  CPSD_CHECK_ARG(nprob >= 0 && ncols > 0 && nrows_max >= 0, "center_rows: bad dims");
+  if (nprob == 0 || nrows_max == 0) return CPSD_OK;
+  int bx = (ncols + 255) / 256;
+  if (bx > 8) bx = 8;
+  int by = nrows_max < 256 ? nrows_max : 256;
+  k_center_rows<<<dim3(bx, by, nprob), 256, 0, stream>>>(Z, ld, strideZ, mu, ldmu, nrows_dev,
+                                                        nrows_fixed, ncols);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
+
+extern "C" int cpsd_copy_rows(const float* src, int lds, long long strideS, float* dst, int ldd,
+                              long long strideD, const int* r0_dev, int r0_fixed, int nrows,
+                              int ncols, int nprob, cudaStream_t stream) {
+  CPSD_CHECK_ARG(nprob >= 0 && ncols > 0 && nrows >= 0, "copy_rows: bad dims");
+  if (nprob == 0 || nrows == 0) return CPSD_OK;
+  int bx = (ncols + 255) / 256;
+  if (bx > 8) bx = 8;
+  int by = nrows < 256 ? nrows : 256;
+  k_copy_rows<<<dim3(bx, by, nprob), 256, 0, stream>>>(src, lds, strideS, dst, ldd, strideD, r0_dev,
+                                                      r0_fixed, nrows, ncols);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
+
+extern "C" int cpsd_mcca_mask(const float* evecs, int ldv, long long strideV, const float* evals,
+                              int ld_e, const int* rank, const int* cdim, int R, int Cmax,
+                              float* Vr, float* d2, int* r_eff, int nprob, cudaStream_t stream) {
+  CPSD_CHECK_ARG(nprob >= 0 && R > 0 && Cmax > 0, "mcca_mask: bad dims");
+  if (nprob == 0) return CPSD_OK;
+  k_mcca_mask<<<nprob, 128, 0, stream>>>(evecs, ldv, strideV, evals, ld_e, rank, cdim, R, Cmax, Vr,
+                                         d2, r_eff);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
+
+extern "C" int cpsd_mcca_build(const float* G, int ldg, long long strideG, const int* r_eff, int P,
+                               int R, float reg, float* M, int ldm, long long strideM, int* n_out,
+                               int* cidx, float* dh, int n_comp, int* status, int nfold,
+                               cudaStream_t stream) {
+  CPSD_CHECK_ARG(nfold >= 0 && P > 0 && R > 0, "mcca_build: bad dims");
+  CPSD_CHECK_ARG(ldm >= P * R || ldm >= 1, "mcca_build: bad ldm");
+  if (nfold == 0) return CPSD_OK;
+  const size_t smem = (size_t)P * R * (sizeof(int) + sizeof(float));
+  k_mcca_build<<<nfold, 256, smem, stream>>>(G, ldg, strideG, r_eff, P, R, reg, M, ldm, strideM,
+                                             n_out, cidx, dh, n_comp, status);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
+
+extern "C" int cpsd_mcca_loadings(const float* Vr, const float* U, int ldu, long long strideU,
+                                  const int* perm, int ld_perm, const int* r_eff, const float* dh,
+                                  int P, int R, int Cmax, int n_comp, float* L, int ldl, int nfold,
+                                  cudaStream_t stream) {
+  CPSD_CHECK_ARG(nfold >= 0 && P > 0 && R > 0 && n_comp > 0, "mcca_loadings: bad dims");
+  if (nfold == 0) return CPSD_OK;
+  k_mcca_loadings<<<nfold * P, 128, 0, stream>>>(Vr, U, ldu, strideU, perm, ld_perm, r_eff, dh, P, R,
+                                                 Cmax, n_comp, L, ldl);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
+
+extern "C" int cpsd_scores_train(const float* V, int ldv, long long strideV, const float* evals,
+                                 const int* perm, int ld_e, const int* k_dev, const int* n_dev,
+                                 int n_fixed, int n_max, float* St, int lds, long long strideS,
+                                 int kcap, int nfold, cudaStream_t stream) {
+  CPSD_CHECK_ARG(nfold >= 0 && kcap > 0 && n_max > 0, "scores_train: bad dims");
+  if (nfold == 0) return CPSD_OK;
+  int by = kcap < 128 ? kcap : 128;
+  k_scores_train<<<dim3((n_max + 255) / 256, by, nfold), 256, 0, stream>>>(
+      V, ldv, strideV, evals, perm, ld_e, k_dev, n_dev, n_fixed, St, lds, strideS, kcap);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
+
+extern "C" int cpsd_scores_test(const float* Kte, int ldk, long long strideK, const float* V, int ldv,
+                                long long strideV, const float* evals, const int* perm, int ld_e,
+                                const int* k_dev, const int* n_dev, int n_fixed, int n_te,
+                                float* Ste, int ldt, long long strideT, int kcap, int nfold,
+                                cudaStream_t stream) {
+  CPSD_CHECK_ARG(nfold >= 0 && kcap > 0 && n_te >= 0, "scores_test: bad dims");
+  if (nfold == 0 || n_te == 0) return CPSD_OK;
+  int bx = (kcap + 127) / 128;
+  if (bx > 16) bx = 16;
+  k_scores_test<<<dim3(bx, n_te, nfold), 128, 0, stream>>>(Kte, ldk, strideK, V, ldv, strideV, evals,
+                                                           perm, ld_e, k_dev, n_dev, n_fixed, n_te,
+                                                           Ste, ldt, strideT, kcap);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
