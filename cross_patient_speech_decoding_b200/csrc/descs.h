@@ -71,6 +71,22 @@ typedef struct {
   int max_newton, dcd_epochs;
 } cpsd_svm_desc;
 
+typedef struct {
+  const float* Saa;      /* da x da scatter of the centred target latents, row stride lds */
+  const float* Sbb;      /* db x db */
+  const float* Sab;      /* da x db */
+  const int* da_dev;     /* optional device scalars overriding da / db */
+  const int* db_dev;
+  float* Ma;             /* dmax x dmax (row stride ldm): M_a in the leading da x d block */
+  float* Mb;             /* dmax x dmax: M_b in the leading db x d block */
+  float* G;              /* dmax x dmax (row stride ldg): b->a map M_b pinv(M_a), db x da */
+  float* rho;            /* [dmax] canonical correlations, descending, clamped to [0,1] */
+  int* info;             /* [4] d, rank warning, svd sweeps, reserved */
+  int da, db, lds, ldm, ldg, mode;
+  float rank_tol;
+  int pad_;
+} cpsd_cca_desc;
+
 #ifdef __cplusplus
 }
 #endif

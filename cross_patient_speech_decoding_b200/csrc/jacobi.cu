@@ -504,7 +504,7 @@ k_bj_extract(const float* __restrict__ K, int ld, long long stride, const int* _
 // clamped to [kmin, min(kmax, n)].
 __global__ void k_select_k(const float* __restrict__ evals, int ld_e, const int* __restrict__ n_dev,
                            int n_fixed, float thr, int mode, int kmin, int kmax,
-                           int* __restrict__ k_out, int nprob) {
+                           int* __restrict__ k_out, int k_stride, int nprob) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nprob) return;
   const int n = n_dev ? n_dev[p] : n_fixed;
@@ -536,7 +536,7 @@ __global__ void k_select_k(const float* __restrict__ evals, int ld_e, const int*
   const int hi = min(kmax, n);
   if (k > hi) k = hi;
   if (k < kmin) k = kmin;
-  k_out[p] = k;
+  k_out[(long long)p * k_stride] = k;
 }
 
 }  // namespace
@@ -632,12 +632,12 @@ extern "C" int cpsd_eig_sym_block(float* K, float* V, int ld, long long stride, 
 }
 
 extern "C" int cpsd_select_k(const float* evals, int ld_e, const int* n_dev, int n_fixed, float thr,
-                             int mode, int kmin, int kmax, int* k_out, int nprob,
+                             int mode, int kmin, int kmax, int* k_out, int k_stride, int nprob,
                              cudaStream_t stream) {
   CPSD_CHECK_ARG(mode >= 0 && mode <= 3, "select_k: bad mode");
   if (nprob == 0) return CPSD_OK;
   k_select_k<<<(nprob + 63) / 64, 64, 0, stream>>>(evals, ld_e, n_dev, n_fixed, thr, mode, kmin, kmax,
-                                                   k_out, nprob);
+                                                   k_out, k_stride, nprob);
   CPSD_LAUNCH_CHECK();
   return CPSD_OK;
 }

@@ -73,6 +73,20 @@ k_copy_rows(const float* __restrict__ src, int lds, long long strideS, float* __
   }
 }
 
+// dst[p][r][j] = src[p][r][perm[p][j]]   j < ncols, r < nrows
+__global__ void __launch_bounds__(256)
+k_permute_cols(const float* __restrict__ src, int lds, long long strideS,
+               const int* __restrict__ perm, int ld_perm, float* __restrict__ dst, int ldd,
+               long long strideD, int nrows, int ncols) {
+  const int p = blockIdx.z;
+  for (int r = blockIdx.y; r < nrows; r += gridDim.y) {
+    const float* s = src + (long long)p * strideS + (long long)r * lds;
+    float* d = dst + (long long)p * strideD + (long long)r * ldd;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < ncols; j += gridDim.x * blockDim.x)
+      d[j] = s[perm[(long long)p * ld_perm + j]];
+  }
+}
+
 // ------------------------------------------------------------------------------- MCCA
 // Per (fold, view): keep the leading r = min(R, rank, n_valid) principal directions of the
 // centred condition averages.  Vr (C x R, zero beyond r), d2 [R] squared singular values.
@@ -256,6 +270,20 @@ extern "C" int cpsd_copy_rows(const float* src, int lds, long long strideS, floa
   int by = nrows < 256 ? nrows : 256;
   k_copy_rows<<<dim3(bx, by, nprob), 256, 0, stream>>>(src, lds, strideS, dst, ldd, strideD, r0_dev,
                                                       r0_fixed, nrows, ncols);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
+
+extern "C" int cpsd_permute_cols(const float* src, int lds, long long strideS, const int* perm,
+                                 int ld_perm, float* dst, int ldd, long long strideD, int nrows,
+                                 int ncols, int nprob, cudaStream_t stream) {
+  CPSD_CHECK_ARG(nprob >= 0 && ncols > 0 && nrows >= 0, "permute_cols: bad dims");
+  if (nprob == 0 || nrows == 0) return CPSD_OK;
+  int bx = (ncols + 255) / 256;
+  if (bx > 8) bx = 8;
+  int by = nrows < 256 ? nrows : 256;
+  k_permute_cols<<<dim3(bx, by, nprob), 256, 0, stream>>>(src, lds, strideS, perm, ld_perm, dst, ldd,
+                                                         strideD, nrows, ncols);
   CPSD_LAUNCH_CHECK();
   return CPSD_OK;
 }

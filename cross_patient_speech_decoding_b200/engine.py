@@ -1,0 +1,617 @@
+"""Batched cross-validated align -> reduce -> decode engine.
+
+One call processes a whole list of CV folds ("units") for one target patient and a set
+of cross patients: every fold fits the alignment (MCCA / pairwise CCA / none), projects
+all trials into the shared latent space, pools them, runs the decoder-stage PCA on the
+pooled trials x (time*latent) matrix and trains + scores the one-vs-rest linear SVM.
+This is the loop body of the reference's scripts/aligned_decode_svm_ncv.py:344-442 with
+``crossPtDecoder_{mcca,sepAlign,sepDimRed}`` (decoders/cross_pt_decoders.py) and the
+``make_pipeline(DimRedReshape(PCA), <linear SVM>)`` decoder, executed for all folds at
+once by the kernels of libcpsd_b200.so.  Patient data stays resident in HBM; per batch
+the host only uploads fold index tables + descriptor records and downloads predictions.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .device import Context, HostPack, addr, ptr
+from .folds import class_ids
+
+F32 = torch.float32
+I32 = torch.int32
+
+
+def _ceil(a, b):
+    return (a + b - 1) // b * b
+
+
+class View:
+    """One patient resident on the device."""
+
+    def __init__(self, ctx, X, y, y_align, cls_ids):
+        X = np.asarray(X)
+        assert X.ndim == 3, 'features must be (trials, time, channels)'
+        self.N, self.T, self.C = X.shape
+        self.X = ctx.upload(X.reshape(self.N * self.T, self.C), np.float32)
+        self.y = np.asarray(y).astype(np.int64)
+        self.cls = np.asarray(cls_ids, dtype=np.int32)        # alignment class id per trial
+        self.h2d_bytes = X.size * 4
+
+
+class CVEngine:
+    """See module docstring.  ``method``: 'mcca' | 'cca' | 'none'."""
+
+    def __init__(self, target, cross, method='mcca', n_comp=None, regs=0.5, pca_var=0.8,
+                 decoder_var=0.8, C=1.0, tar_in_train=True, device=None, max_batch=24,
+                 dcd_epochs=2, max_newton=60, tol_newton=1e-9, tol_dcd=1e-4,
+                 eig_sweeps=12, eig_tol=3e-7, use_tensor_cores=False):
+        self.ctx = Context.get(device)
+        self.method = method
+        if n_comp is None:
+            n_comp = 30 if method == 'mcca' else 0.9
+        self.n_comp = n_comp
+        self.regs = regs
+        self.pca_var = pca_var
+        self.decoder_var = decoder_var
+        self.Csvm = float(C)
+        self.tar_in_train = tar_in_train
+        self.max_batch = max_batch
+        self.dcd_epochs = dcd_epochs
+        self.max_newton = max_newton
+        self.tol_newton = tol_newton
+        self.tol_dcd = tol_dcd
+        self.eig_sweeps = eig_sweeps
+        self.eig_tol = eig_tol
+        self.use_tc = use_tensor_cores
+        if method == 'mcca':
+            assert isinstance(n_comp, (int, np.integer)) and n_comp >= 1
+        views = [target] + list(cross)
+        ids, self.vocab = class_ids([v[2] if v[2] is not None else v[1] for v in views])
+        self.views = [View(self.ctx, v[0], v[1], v[2], i) for v, i in zip(views, ids)]
+        self.P = len(self.views)
+        self.T = self.views[0].T
+        assert all(v.T == self.T for v in self.views), 'all patients need the same time axis'
+        self.Cmax = max(v.C for v in self.views)
+        self.classes = np.unique(np.concatenate([v.y for v in self.views])).astype(np.int32)
+        self.classes_dev = self.ctx.upload(self.classes, np.int32)
+        self.packA = HostPack(self.ctx)
+        self.packB = HostPack(self.ctx)
+        self._ws = {}
+        self._sched = {}
+        self.stats = {}
+        self._prepare_cross()
+
+    # ------------------------------------------------------------------ workspace
+    def ws(self, name, shape, dtype=F32):
+        """Named persistent workspace tensor, grown on demand."""
+        n = int(np.prod(shape))
+        t = self._ws.get(name)
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = self.ctx.empty((max(n, 1),), dtype)
+            self._ws[name] = t
+        return t[:n].view(*shape) if n else t[:0]
+
+    def schedule(self, n_pad):
+        if n_pad not in self._sched:
+            nb = n_pad // 64
+            host = np.zeros((nb - 1) * (nb // 2) * 2, dtype=np.int32)
+            _lib.check(self.ctx.lib.cpsd_bj_schedule(n_pad, host.ctypes.data), 'bj_schedule')
+            self._sched[n_pad] = self.ctx.upload(host, np.int32)
+        return self._sched[n_pad]
+
+    # ------------------------------------------------------------------ eigen helpers
+    def eig_small(self, A, n_dev, n_fixed, nprob, lda, evals, evecs, ldv):
+        """A: (nprob, lda, lda) tensor, n <= 128.  Sorted descending."""
+        self.ctx.call('cpsd_eig_sym_small', ptr(A), lda, lda * lda, _p(n_dev), n_fixed, nprob,
+                      ptr(evals), evals.shape[-1], ptr(evecs), ldv, ldv * ldv if evecs is not None
+                      else 0, self.eig_sweeps + 3, self.eig_tol, ptr(None))
+
+    def eig_block(self, K, V, n_pad, n_dev, n_fixed, nprob, evals, perm, tag):
+        """K, V: (nprob, n_pad, n_pad).  K is destroyed; V columns perm[j] are eigenvectors."""
+        R = self.ws(tag + '_R', (nprob, n_pad // 128, 128 * 128))
+        fw = self.ws(tag + '_fw', (2 * nprob,))
+        iw = self.ws(tag + '_iw', (2 * nprob,), I32)
+        self.ctx.call('cpsd_eig_sym_block', ptr(K), ptr(V), n_pad, n_pad * n_pad, n_pad,
+                      _p(n_dev), n_fixed, nprob, ptr(self.schedule(n_pad)), ptr(R), ptr(fw),
+                      ptr(iw), ptr(evals), ptr(perm), evals.shape[-1], self.eig_sweeps,
+                      self.eig_tol)
+        return iw
+
+    def eig_any(self, A, n_pad, n_dev, n_fixed, nprob, tag, ncols=None):
+        """Sorted eigen-decomposition for any n_pad (A: (nprob, n_pad, n_pad), destroyed).
+        Returns (evals (nprob, n_pad), evecs (nprob, n_pad, n_pad) with sorted columns)."""
+        evals = self.ws(tag + '_ev', (nprob, n_pad))
+        evecs = self.ws(tag + '_evec', (nprob, n_pad, n_pad))
+        if n_pad <= 128:
+            self.eig_small(A, n_dev, n_fixed, nprob, n_pad, evals, evecs, n_pad)
+            return evals, evecs
+        V = self.ws(tag + '_V', (nprob, n_pad, n_pad))
+        perm = self.ws(tag + '_perm', (nprob, n_pad), I32)
+        self.eig_block(A, V, n_pad, n_dev, n_fixed, nprob, evals, perm, tag)
+        nc = n_pad if ncols is None else ncols
+        self.ctx.call('cpsd_permute_cols', ptr(V), n_pad, n_pad * n_pad, ptr(perm), n_pad,
+                      ptr(evecs), n_pad, n_pad * n_pad, n_pad, nc, nprob)
+        return evals, evecs
+
+    # ------------------------------------------------------------------ fold-invariant work
+    def _prepare_cross(self):
+        """Class means of every cross patient (all classes), and for MCCA their signal ranks,
+        for CCA / none their PCA bases -- none of it depends on the fold."""
+        ctx, T = self.ctx, self.T
+        pk = HostPack(ctx)
+        self.cm = [None] * self.P          # class-mean tensors (n_cls_v * T, C_v)
+        self.cm_row = [None] * self.P      # class id -> slot in cm (or -1)
+        recs = np.zeros(self.P - 1, dtype=_lib.CLASS_MEAN_DESC)
+        offs = []
+        for v in range(1, self.P):
+            vw = self.views[v]
+            present = np.unique(vw.cls)
+            row = -np.ones(len(self.vocab), dtype=np.int64)
+            row[present] = np.arange(len(present))
+            self.cm_row[v] = row
+            order = np.argsort(vw.cls, kind='stable')
+            counts = np.bincount(vw.cls, minlength=len(self.vocab))[present]
+            mptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+            offs.append((pk.add_ints(mptr), pk.add_ints(order.astype(np.int32)), len(present)))
+            self.cm[v] = ctx.empty((len(present) * T, vw.C))
+        if self.P > 1:
+            pk.reserve_ints()
+            for i, v in enumerate(range(1, self.P)):
+                vw = self.views[v]
+                o_ptr, o_mem, ns = offs[i]
+                recs[i] = (addr(vw.X), pk.iaddr(o_ptr), pk.iaddr(o_mem), addr(self.cm[v]), ns,
+                           T * vw.C, 0, 0)
+            d_off = pk.add_descs(recs)
+            pk.upload()
+            ns_max = max(o[2] for o in offs)
+            for i, v in enumerate(range(1, self.P)):
+                # one launch per view: TC differs between views
+                ctx.call('cpsd_class_mean',
+                         ctypes_off(pk.daddr(d_off), i * _lib.CLASS_MEAN_DESC.itemsize), 1,
+                         offs[i][2], T * self.views[v].C)
+        self.cross_classes = [set(np.unique(self.views[v].cls).tolist())
+                              for v in range(1, self.P)]
+        if self.method == 'mcca':
+            self.cross_rank = self._ranks_full(range(1, self.P))
+        elif self.P > 1:
+            self._cross_pca()
+        torch.cuda.synchronize(self.ctx.device)
+
+    def _ranks_full(self, vs):
+        """AlignMCCA.n_components_var on all trials of the given views (AlignMCCA.py:146-150)."""
+        vs = list(vs)
+        if not (0 < self.pca_var < 1) or not vs:
+            return np.full(len(vs), self.n_comp, dtype=np.int32)
+        ctx, T, Cm = self.ctx, self.T, self.Cmax
+        n_pad = _ceil(Cm, 128) if Cm > 128 else 128
+        pk = HostPack(ctx)
+        G = self.ws('rk_G', (len(vs), n_pad, n_pad))
+        G.zero_()
+        seg = [pk.add_ints(np.arange(self.views[v].N, dtype=np.int32) * T) for v in vs]
+        cdim = pk.add_ints([self.views[v].C for v in vs])
+        pk.reserve_ints()
+        recs = np.zeros(len(vs), dtype=_lib.GRAM_TN_DESC)
+        for i, v in enumerate(vs):
+            vw = self.views[v]
+            recs[i] = (addr(vw.X), addr(vw.X), pk.iaddr(seg[i]), pk.iaddr(seg[i]), 0, 0,
+                       addr(G, i * n_pad * n_pad), vw.N, T, vw.C, vw.C, vw.C, vw.C, n_pad, 1,
+                       1.0, 0)
+        d = pk.add_descs(recs)
+        pk.upload()
+        ctx.call('cpsd_gram_tn', pk.daddr(d), len(vs), Cm, Cm)
+        cd = ctypes_int_ptr(pk.iaddr(cdim))
+        evals, _ = self.eig_any(G, n_pad, cd, 0, len(vs), 'rk')
+        k = self.ws('rk_k', (len(vs),), I32)
+        ctx.call('cpsd_select_k', ptr(evals), n_pad, cd, 0, float(self.pca_var), 1, 0, 1 << 30,
+                 ptr(k), 1, len(vs))
+        return k.cpu().numpy().astype(np.int32)
+
+    def _cross_pca(self):
+        """sklearn PCA(n_comp) of every cross patient's (trials*time, channels) matrix
+        (cross_pt_decoders.py:234-235; fold-invariant)."""
+        ctx, T, Cm = self.ctx, self.T, self.Cmax
+        vs = list(range(1, self.P))
+        nv = len(vs)
+        n_pad = _ceil(Cm, 128) if Cm > 128 else 128
+        pk = HostPack(ctx)
+        self.cross_mu = self.ws('cp_mu', (nv, Cm))
+        cov = self.ws('cp_cov', (nv, n_pad, n_pad))
+        cov.zero_()
+        seg = [pk.add_ints(np.arange(self.views[v].N, dtype=np.int32) * T) for v in vs]
+        cdim = pk.add_ints([self.views[v].C for v in vs])
+        pk.reserve_ints()
+        r1 = np.zeros(nv, dtype=_lib.COLSUM_DESC)
+        r2 = np.zeros(nv, dtype=_lib.GRAM_TN_DESC)
+        for i, v in enumerate(vs):
+            vw = self.views[v]
+            r1[i] = (addr(vw.X), pk.iaddr(seg[i]), addr(self.cross_mu, i * Cm), vw.N, T, vw.C,
+                     vw.C, 1.0 / (vw.N * T), 0)
+            r2[i] = (addr(vw.X), addr(vw.X), pk.iaddr(seg[i]), pk.iaddr(seg[i]),
+                     addr(self.cross_mu, i * Cm), addr(self.cross_mu, i * Cm),
+                     addr(cov, i * n_pad * n_pad), vw.N, T, vw.C, vw.C, vw.C, vw.C, n_pad, 1,
+                     1.0 / (vw.N * T - 1), 0)
+        d1, d2 = pk.add_descs(r1), pk.add_descs(r2)
+        pk.upload()
+        ctx.call('cpsd_colsum', pk.daddr(d1), nv, Cm)
+        ctx.call('cpsd_gram_tn', pk.daddr(d2), nv, Cm, Cm)
+        cd = ctypes_int_ptr(pk.iaddr(cdim))
+        evals, evecs = self.eig_any(cov, n_pad, cd, 0, nv, 'cp')
+        self.cross_k_dev = self.ws('cp_k', (nv,), I32)
+        self._select_pca_k(evals, n_pad, cd, 0, self.cross_k_dev, 1, 0, nv, self.n_comp)
+        self.cross_k = self.cross_k_dev.cpu().numpy().astype(np.int32)
+        self.cross_evecs = evecs.clone()
+        self.cross_evals = evals.clone()
+        self.cross_npad = n_pad
+
+    def _select_pca_k(self, evals, ld_e, n_dev, n_fixed, k_out, stride, offset, nprob, n_comp):
+        if isinstance(n_comp, (float, np.floating)) and 0 < n_comp < 1:
+            mode, thr = 0, float(n_comp)
+        else:
+            mode, thr = 3, float(int(n_comp))
+        self.ctx.call('cpsd_select_k', ptr(evals), ld_e, _p(n_dev), n_fixed, thr, mode, 1, 1 << 30,
+                      ptr(k_out, offset), stride, nprob)
+
+    # ------------------------------------------------------------------ public API
+    def run(self, folds, return_details=False):
+        """folds: list of (train_idx, test_idx) into the target's trials.  Returns a dict with
+        ``y_pred`` (list of arrays, one per fold) and per-fold diagnostics."""
+        out = {'y_pred': [], 'k2': [], 'h2d_bytes': 0, 'd2h_bytes': 0}
+        details = []
+        for s in range(0, len(folds), self.max_batch):
+            batch = folds[s:s + self.max_batch]
+            if self.method == 'mcca':
+                res = self._batch_mcca(batch, return_details)
+            else:
+                res = self._batch_cca(batch, return_details)
+            out['y_pred'] += res['y_pred']
+            out['k2'] += res['k2']
+            out['h2d_bytes'] += res['h2d_bytes']
+            out['d2h_bytes'] += res['d2h_bytes']
+            if return_details:
+                details.append(res['details'])
+        if return_details:
+            out['details'] = details
+        return out
+
+    # ------------------------------------------------------------------ shared host prep
+    def _target_tables(self, pk, batch):
+        """Per fold: target class-mean CSR (classes present among the train trials)."""
+        tv = self.views[0]
+        tabs = []
+        for tr, te in batch:
+            tr = np.asarray(tr, dtype=np.int64)
+            cls = tv.cls[tr]
+            present = np.unique(cls)
+            order = np.argsort(cls, kind='stable')
+            counts = np.bincount(cls, minlength=len(self.vocab))[present]
+            mptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+            tabs.append(dict(tr=tr, te=np.asarray(te, dtype=np.int64), present=present,
+                             o_ptr=pk.add_ints(mptr), o_mem=pk.add_ints(tr[order]),
+                             o_tr=pk.add_ints(tr * self.T), o_te=pk.add_ints(np.asarray(te) * self.T)))
+        return tabs
+
+    def _class_means_target(self, pk, tabs, B, Kmax):
+        tv, T = self.views[0], self.T
+        cmT = self.ws('cmT', (B, Kmax * T, tv.C))
+        recs = np.zeros(B, dtype=_lib.CLASS_MEAN_DESC)
+        for f, tb in enumerate(tabs):
+            recs[f] = (addr(tv.X), pk.iaddr(tb['o_ptr']), pk.iaddr(tb['o_mem']),
+                       addr(cmT, f * Kmax * T * tv.C), len(tb['present']), T * tv.C, 0, 0)
+        return cmT, recs
+
+    # ------------------------------------------------------------------ pooled stage
+    def _pooled_stage(self, pk, B, Zall, n_pad, F, n_pool, n_te, o_npool, o_nall, o_ypool,
+                      ypool_ld, n_te_max, want_details):
+        """Decoder: PCA(decoder_var) on the pooled matrix + OvR linear SVM + prediction.
+        Zall (B, n_pad, F): rows [0,n_pool) pooled train, [n_pool, n_pool+n_te) test."""
+        ctx = self.ctx
+        n_all = [a + b for a, b in zip(n_pool, n_te)]
+        mu = self.ws('pool_mu', (B, F))
+        r1 = np.zeros(B, dtype=_lib.COLSUM_DESC)
+        zero_seg = pk.iaddr(self._o_zero)
+        r2 = np.zeros(B, dtype=_lib.GRAM_NT_DESC)
+        Kall = self.ws('pool_K', (B, n_pad, n_pad))
+        for f in range(B):
+            r1[f] = (addr(Zall, f * n_pad * F), zero_seg, addr(mu, f * F), 1, n_pool[f], F, F,
+                     1.0 / n_pool[f], 0)
+            r2[f] = (addr(Zall, f * n_pad * F), addr(Zall, f * n_pad * F),
+                     addr(Kall, f * n_pad * n_pad), n_all[f], n_all[f], F, F, F, n_pad, 1, 1.0)
+        return r1, r2, mu, Kall
+
+    def _pooled_stage_run(self, pk, d1, d2, B, Zall, mu, Kall, n_pad, F, n_pool, n_te, o_npool,
+                          o_nall, o_ypool, n_te_max, want_details):
+        ctx = self.ctx
+        npool_dev = ctypes_int_ptr(pk.iaddr(o_npool))
+        nall_dev = ctypes_int_ptr(pk.iaddr(o_nall))
+        ncls = len(self.classes)
+        ctx.call('cpsd_colsum', pk.daddr(d1), B, F)
+        ctx.call('cpsd_center_rows', ptr(Zall), F, n_pad * F, ptr(mu), F, nall_dev, 0,
+                 max(a + b for a, b in zip(n_pool, n_te)), F, B)
+        nmax = max(a + b for a, b in zip(n_pool, n_te))
+        if self.use_tc:
+            ctx.call('cpsd_gram_nt_tc', pk.daddr(d2), B, nmax, nmax)
+        else:
+            ctx.call('cpsd_gram_nt', pk.daddr(d2), B, nmax, nmax)
+        Kte = self.ws('pool_Kte', (B, n_te_max, n_pad))
+        ctx.call('cpsd_copy_rows', ptr(Kall), n_pad, n_pad * n_pad, ptr(Kte), n_pad,
+                 n_te_max * n_pad, npool_dev, 0, n_te_max, n_pad, B)
+        evals = self.ws('pool_ev', (B, n_pad))
+        k2 = self.ws('pool_k2', (B,), I32)
+        kcap = min(n_pad, F)
+        if n_pad <= 128:
+            V = self.ws('pool_V', (B, n_pad, n_pad))
+            # zero the test rows/cols: the tile solver reads only the leading n x n block
+            self.eig_small(Kall, npool_dev, 0, B, n_pad, evals, V, n_pad)
+            perm_p = ptr(None)
+            sweeps = None
+        else:
+            V = self.ws('pool_V', (B, n_pad, n_pad))
+            perm = self.ws('pool_perm', (B, n_pad), I32)
+            sweeps = self.eig_block(Kall, V, n_pad, npool_dev, 0, B, evals, perm, 'pool')
+            perm_p = ptr(perm)
+        if isinstance(self.decoder_var, (float, np.floating)) and 0 < self.decoder_var < 1:
+            mode, thr = 0, float(self.decoder_var)
+        else:
+            mode, thr = 3, float(int(self.decoder_var))
+        ctx.call('cpsd_select_k', ptr(evals), n_pad, npool_dev, 0, thr, mode, 1, kcap, ptr(k2), 1,
+                 B)
+        St = self.ws('pool_St', (B, kcap, n_pad))
+        Ste = self.ws('pool_Ste', (B, kcap, n_te_max))
+        ctx.call('cpsd_scores_train', ptr(V), n_pad, n_pad * n_pad, ptr(evals), perm_p, n_pad,
+                 ptr(k2), npool_dev, 0, max(n_pool), ptr(St), n_pad, kcap * n_pad, kcap, B)
+        ctx.call('cpsd_scores_test', ptr(Kte), n_pad, n_te_max * n_pad, ptr(V), n_pad,
+                 n_pad * n_pad, ptr(evals), perm_p, n_pad, ptr(k2), npool_dev, 0, n_te_max,
+                 ptr(Ste), n_te_max, kcap * n_te_max, kcap, B)
+        return evals, k2, St, Ste, V, sweeps, kcap
+
+    def _svm_stage(self, pk2, B, St, Ste, k2, kcap, n_pad, n_pool, n_te, o_ypool, ypool_ld,
+                   o_nte, n_te_max):
+        ctx = self.ctx
+        ncls = len(self.classes)
+        W = self.ws('svm_W', (B, ncls, kcap + 1), torch.float64)
+        info = self.ws('svm_info', (B, ncls, 4), I32)
+        recs = np.zeros(B * ncls, dtype=_lib.SVM_DESC)
+        for f in range(B):
+            for c in range(ncls):
+                recs[f * ncls + c] = (addr(St, f * kcap * n_pad), pk2.iaddr(o_ypool + f * ypool_ld),
+                                      addr(k2, f), addr(W, (f * ncls + c) * (kcap + 1)),
+                                      addr(info, (f * ncls + c) * 4), n_pool[f], 0, n_pad,
+                                      int(self.classes[c]), self.Csvm, self.tol_dcd,
+                                      self.tol_newton, self.max_newton, self.dcd_epochs)
+        return W, info, recs
+
+    # ------------------------------------------------------------------ MCCA batch
+    def _batch_mcca(self, batch, want_details):
+        ctx, T, P, Cm = self.ctx, self.T, self.P, self.Cmax
+        B = len(batch)
+        Q = int(self.n_comp)
+        use_rank = 0 < self.pca_var < 1
+        R = Q if use_rank else Cm      # pca_var == 1: no rank reduction (mvlearn _mcca_gevp)
+        tv = self.views[0]
+        launches0 = ctx.launches()
+        pk = self.packA
+        pk.reset()
+        self._o_zero = pk.add_ints([0])
+        tabs = self._target_tables(pk, batch)
+        cross_shared = set.intersection(*self.cross_classes) if P > 1 else None
+        shared = []
+        for tb in tabs:
+            s = set(tb['present'].tolist())
+            if cross_shared is not None:
+                s &= cross_shared
+            shared.append(np.array(sorted(s), dtype=np.int64))
+        Kmax = max(len(tb['present']) for tb in tabs)
+        Ks = [len(s) for s in shared]
+        KTmax = max(Ks) * T
+        if min(Ks) == 0:
+            raise ValueError('no alignment class is shared by all patients in some fold')
+        # segment tables: rows of the shared classes inside each view's class-mean array
+        o_seg = np.zeros((B, P), dtype=np.int64)
+        for f, tb in enumerate(tabs):
+            slot_t = -np.ones(len(self.vocab), dtype=np.int64)
+            slot_t[tb['present']] = np.arange(len(tb['present']))
+            o_seg[f, 0] = pk.add_ints(slot_t[shared[f]] * T)
+            for v in range(1, P):
+                o_seg[f, v] = pk.add_ints(self.cm_row[v][shared[f]] * T)
+        o_segdst = pk.add_ints(np.arange(max(Ks), dtype=np.int32) * T)
+        o_cdim = pk.add_ints(np.tile([vw.C for vw in self.views], B))
+        ranks = np.zeros((B, P), dtype=np.int32)
+        ranks[:, 1:] = self.cross_rank[None, :]
+        o_rank = pk.add_ints(ranks)
+        # pooled layout
+        n_tr = [len(tb['tr']) for tb in tabs]
+        n_te = [len(tb['te']) for tb in tabs]
+        cross_N = [self.views[v].N for v in range(1, P)]
+        n_pool = [(nt if self.tar_in_train else 0) + sum(cross_N) for nt in n_tr]
+        n_te_max = max(n_te)
+        n_pad = _ceil(max(a + b for a, b in zip(n_pool, n_te)), 128)
+        F = T * Q
+        ypool = np.zeros((B, n_pad), dtype=np.int32)
+        o_pooldst = np.zeros((B, P), dtype=np.int64)
+        o_allseg = [pk.add_ints(np.arange(self.views[v].N, dtype=np.int32) * T)
+                    for v in range(P)]
+        o_tedst = []
+        for f, tb in enumerate(tabs):
+            row = 0
+            ys = []
+            if self.tar_in_train:
+                o_pooldst[f, 0] = pk.add_ints((row + np.arange(n_tr[f])) * T)
+                ys.append(tv.y[tb['tr']])
+                row += n_tr[f]
+            for v in range(1, P):
+                o_pooldst[f, v] = pk.add_ints((row + np.arange(self.views[v].N)) * T)
+                ys.append(self.views[v].y)
+                row += self.views[v].N
+            ypool[f, :row] = np.concatenate(ys)
+            o_tedst.append(pk.add_ints((row + np.arange(n_te[f])) * T))
+        o_ypool = pk.add_ints(ypool)
+        o_npool = pk.add_ints(n_pool)
+        o_nall = pk.add_ints([a + b for a, b in zip(n_pool, n_te)])
+        o_nte = pk.add_ints(n_te)
+        pk.reserve_ints()
+
+        # ---- descriptors, stage A
+        cmT, r_cm = self._class_means_target(pk, tabs, B, Kmax)
+        cm_base = lambda f, v: (addr(cmT, f * Kmax * T * tv.C) if v == 0 else addr(self.cm[v]))
+        n_padC = 128 if Cm <= 128 else _ceil(Cm, 128)
+        Gt = self.ws('m_Gt', (B, n_padC, n_padC))
+        mu = self.ws('m_mu', (B * P, Cm))
+        cov = self.ws('m_cov', (B * P, n_padC, n_padC))
+        if Cm < n_padC:
+            cov.zero_()
+            Gt.zero_()
+        r_gt = np.zeros(B, dtype=_lib.GRAM_TN_DESC)
+        r_mu = np.zeros(B * P, dtype=_lib.COLSUM_DESC)
+        r_cov = np.zeros(B * P, dtype=_lib.GRAM_TN_DESC)
+        for f, tb in enumerate(tabs):
+            r_gt[f] = (addr(tv.X), addr(tv.X), pk.iaddr(tb['o_tr']), pk.iaddr(tb['o_tr']), 0, 0,
+                       addr(Gt, f * n_padC * n_padC), n_tr[f], T, tv.C, tv.C, tv.C, tv.C, n_padC,
+                       1, 1.0, 0)
+            for v in range(P):
+                C = self.views[v].C
+                i = f * P + v
+                sg = pk.iaddr(o_seg[f, v])
+                r_mu[i] = (cm_base(f, v), sg, addr(mu, i * Cm), Ks[f], T, C, C,
+                           1.0 / (Ks[f] * T), 0)
+                r_cov[i] = (cm_base(f, v), cm_base(f, v), sg, sg, addr(mu, i * Cm),
+                            addr(mu, i * Cm), addr(cov, i * n_padC * n_padC), Ks[f], T, C, C, C, C,
+                            n_padC, 1, 1.0, 0)
+        d_cm, d_gt = pk.add_descs(r_cm), pk.add_descs(r_gt)
+        d_mu, d_cov = pk.add_descs(r_mu), pk.add_descs(r_cov)
+        # reduced views
+        Vr = self.ws('m_Vr', (B * P, Cm, R))
+        d2 = self.ws('m_d2', (B * P, R))
+        r_eff = self.ws('m_reff', (B * P,), I32)
+        Zcat = self.ws('m_Zcat', (B, KTmax, P * R))
+        r_pz = np.zeros(B * P, dtype=_lib.PROJ_DESC)
+        r_g = np.zeros(B, dtype=_lib.GRAM_TN_DESC)
+        Gz = self.ws('m_Gz', (B, P * R, P * R))
+        for f in range(B):
+            for v in range(P):
+                C = self.views[v].C
+                i = f * P + v
+                r_pz[i] = (cm_base(f, v), pk.iaddr(o_seg[f, v]), pk.iaddr(o_segdst),
+                           addr(mu, i * Cm), addr(Vr, i * Cm * R),
+                           addr(Zcat, f * KTmax * P * R + v * R), Ks[f], T, C, R, C, R, P * R, 0)
+            r_g[f] = (addr(Zcat, f * KTmax * P * R), addr(Zcat, f * KTmax * P * R),
+                      pk.iaddr(self._o_zero), pk.iaddr(self._o_zero), 0, 0,
+                      addr(Gz, f * P * R * P * R), 1, Ks[f] * T, P * R, P * R, P * R, P * R, P * R,
+                      1, 1.0, 0)
+        d_pz, d_g = pk.add_descs(r_pz), pk.add_descs(r_g)
+        # pooled projection
+        n_padM = 128 if P * R <= 128 else _ceil(P * R, 128)
+        L = self.ws('m_L', (B * P, Cm, Q))
+        Zall = self.ws('pool_Z', (B, n_pad, F))
+        r_pp = np.zeros(B * P + B, dtype=_lib.PROJ_DESC)
+        for f, tb in enumerate(tabs):
+            for v in range(P):
+                vw = self.views[v]
+                i = f * P + v
+                if v == 0:
+                    nseg = n_tr[f] if self.tar_in_train else 0
+                    src = pk.iaddr(tb['o_tr'])
+                else:
+                    nseg, src = vw.N, pk.iaddr(o_allseg[v])
+                r_pp[i] = (addr(vw.X), src, pk.iaddr(o_pooldst[f, v]), addr(mu, i * Cm),
+                           addr(L, i * Cm * Q), addr(Zall, f * n_pad * F), nseg, T, vw.C, Q, vw.C,
+                           Q, Q, 0)
+            r_pp[B * P + f] = (addr(tv.X), pk.iaddr(tb['o_te']), pk.iaddr(o_tedst[f]),
+                               addr(mu, f * P * Cm), addr(L, f * P * Cm * Q),
+                               addr(Zall, f * n_pad * F), n_te[f], T, tv.C, Q, tv.C, Q, Q, 0)
+        d_pp = pk.add_descs(r_pp)
+        r1, r2, pmu, Kall = self._pooled_stage(pk, B, Zall, n_pad, F, n_pool, n_te, o_npool,
+                                               o_nall, o_ypool, n_pad, n_te_max, want_details)
+        d_p1, d_p2 = pk.add_descs(r1), pk.add_descs(r2)
+        kcap = min(n_pad, F)
+        # SVM descriptors need k2 / St addresses only (known now)
+        St = self.ws('pool_St', (B, kcap, n_pad))
+        k2 = self.ws('pool_k2', (B,), I32)
+        W, info, r_svm = self._svm_stage(pk, B, St, None, k2, kcap, n_pad, n_pool, n_te, o_ypool,
+                                         n_pad, o_nte, n_te_max)
+        d_svm = pk.add_descs(r_svm)
+        pk.upload()
+
+        # ---- launches
+        cdim_dev = ctypes_int_ptr(pk.iaddr(o_cdim))
+        rank_dev = self.ws('m_rank', (B * P,), I32)
+        # class means of the target's train trials
+        ctx.call('cpsd_class_mean', pk.daddr(d_cm), B, Kmax, T * tv.C)
+        # signal ranks (cross ranks are fold-invariant and come with the int table)
+        ctx.call('cpsd_copy_rows', ctypes_int_ptr(pk.iaddr(o_rank)), B * P, 0, ptr(rank_dev),
+                 B * P, 0, ptr(None), 0, 1, B * P, 1)
+        if use_rank:
+            ctx.call('cpsd_gram_tn', pk.daddr(d_gt), B, tv.C, tv.C)
+            ev_t, _ = self.eig_any(Gt, n_padC, ptr(None), tv.C, B, 'mrk')
+            ctx.call('cpsd_select_k', ptr(ev_t), n_padC, ptr(None), tv.C, float(self.pca_var), 1,
+                     0, 1 << 30, ptr(rank_dev), P, B)
+        # per-view centred scatter of the condition averages + eigen-decomposition
+        ctx.call('cpsd_colsum', pk.daddr(d_mu), B * P, Cm)
+        ctx.call('cpsd_gram_tn', pk.daddr(d_cov), B * P, Cm, Cm)
+        ev1, evec1 = self.eig_any(cov, n_padC, cdim_dev, 0, B * P, 'mv', ncols=min(n_padC, R))
+        ctx.call('cpsd_mcca_mask', ptr(evec1), n_padC, n_padC * n_padC, ptr(ev1), n_padC,
+                 ptr(rank_dev) if use_rank else ptr(None), cdim_dev, R, Cm, ptr(Vr), ptr(d2),
+                 ptr(r_eff), B * P)
+        ctx.call('cpsd_proj_nn', pk.daddr(d_pz), B * P, max(Ks), T, R)
+        ctx.call('cpsd_gram_tn', pk.daddr(d_g), B, P * R, P * R)
+        M = self.ws('m_M', (B, n_padM, n_padM))
+        M.zero_()
+        n_m = self.ws('m_nm', (B,), I32)
+        cidx = self.ws('m_cidx', (B, P * R), I32)
+        dh = self.ws('m_dh', (B, P * R))
+        status = self.ws('m_status', (B,), I32)
+        status.zero_()
+        reg = -1.0 if self.regs is None else float(self.regs)
+        ctx.call('cpsd_mcca_build', ptr(Gz), P * R, P * R * P * R, ptr(r_eff), P, R, reg, ptr(M),
+                 n_padM, n_padM * n_padM, ptr(n_m), ptr(cidx), ptr(dh), Q, ptr(status), B)
+        evm, U = self.eig_any(M, n_padM, ptr(n_m), 0, B, 'mm', ncols=Q)
+        ctx.call('cpsd_mcca_loadings', ptr(Vr), ptr(U), n_padM, n_padM * n_padM, ptr(None), 0,
+                 ptr(r_eff), ptr(dh), P, R, Cm, Q, ptr(L), Q, B)
+        # project every trial of every view into the pooled (trial x time*Q) matrix
+        ctx.call('cpsd_proj_nn', ctypes_off(pk.daddr(d_pp), 0), B * P + B,
+                 max(max(self.views[v].N for v in range(P)), n_te_max), T, Q)
+        evals, k2_, St_, Ste, V, sweeps, kcap = self._pooled_stage_run(
+            pk, d_p1, d_p2, B, Zall, pmu, Kall, n_pad, F, n_pool, n_te, o_npool, o_nall, o_ypool,
+            n_te_max, want_details)
+        ctx.call('cpsd_svm_fit_ovr', pk.daddr(d_svm), B * len(self.classes), kcap, n_pad)
+        yhat = self.ws('yhat', (B, n_te_max), I32)
+        ncls = len(self.classes)
+        ctx.call('cpsd_svm_predict_ovr', ptr(Ste), n_te_max, kcap * n_te_max, ptr(W), kcap + 1,
+                 ncls * (kcap + 1), ptr(k2), 0, ctypes_int_ptr(pk.iaddr(o_nte)), n_te_max,
+                 ptr(self.classes_dev), ncls, ptr(yhat), ptr(None), B)
+        yh = yhat.cpu().numpy()
+        k2h = k2.cpu().numpy()
+        st = status.cpu().numpy()
+        if st.any():
+            raise ValueError('MCCA: n_components=%d exceeds the total signal rank in fold(s) %s'
+                             % (Q, np.nonzero(st)[0].tolist()))
+        res = {'y_pred': [yh[f, :n_te[f]].copy() for f in range(B)], 'k2': k2h.tolist(),
+               'h2d_bytes': pk.h2d_bytes, 'd2h_bytes': yh.nbytes + k2h.nbytes + st.nbytes}
+        self.stats['launches_last_batch'] = ctx.launches() - launches0
+        if want_details:
+            res['details'] = dict(
+                loadings=L.view(B, P, Cm, Q).cpu().numpy(), mu=mu.view(B, P, Cm).cpu().numpy(),
+                evals_mcca=evm[:, :Q].cpu().numpy(), r_eff=r_eff.view(B, P).cpu().numpy(),
+                pool_evals=evals.cpu().numpy(), svm_info=info.cpu().numpy(),
+                W=W.cpu().numpy(), n_pool=list(n_pool), shared=[s.copy() for s in shared],
+                bj_sweeps=None if sweeps is None else sweeps.cpu().numpy()[B:2 * B])
+        return res
+
+    # ------------------------------------------------------------------ CCA / none batch
+    def _batch_cca(self, batch, want_details):
+        from .engine_cca import batch_cca
+        return batch_cca(self, batch, want_details)
+
+
+def ctypes_int_ptr(address):
+    return ctypes.c_void_p(address)
+
+
+def ctypes_off(p, nbytes):
+    return ctypes.c_void_p((p.value or 0) + nbytes)
+
+
+def _p(x):
+    """Tensor / None / c_void_p -> c_void_p."""
+    return x if isinstance(x, ctypes.c_void_p) else ptr(x)

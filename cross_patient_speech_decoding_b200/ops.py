@@ -1,0 +1,280 @@
+"""numpy-in / numpy-out entry points to the individual kernels (host buffers, copies
+included).  They back the sklearn-style classes (alignment/, decomposition/, svm.py) --
+which are the batch-of-one case of the engine -- and the kernel-level parity tests.
+Everything here runs on the GPU through libcpsd_b200.so; nothing is computed on the host
+beyond packing index tables.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .device import Context, HostPack, addr, ptr
+
+F32, I32, F64 = torch.float32, torch.int32, torch.float64
+
+
+def _ctx(device=None):
+    return Context.get(device)
+
+
+def _ceil(a, b):
+    return (a + b - 1) // b * b
+
+
+def _ivoid(address):
+    return ctypes.c_void_p(address)
+
+
+def eig_sym(A, n=None, max_sweeps=15, tol=3e-7, device=None, return_sweeps=False):
+    """Eigen-decomposition of a batch of symmetric matrices.  A: (nprob, n, n) or (n, n).
+    Returns (evals descending (nprob, n), evecs (nprob, n, n) columns)."""
+    ctx = _ctx(device)
+    A = np.asarray(A, dtype=np.float32)
+    single = A.ndim == 2
+    if single:
+        A = A[None]
+    nprob, nn, _ = A.shape
+    ns = np.full(nprob, nn, dtype=np.int32) if n is None else np.asarray(n, dtype=np.int32)
+    n_pad = 128 if nn <= 128 else _ceil(nn, 128)
+    Ap = np.zeros((nprob, n_pad, n_pad), dtype=np.float32)
+    Ap[:, :nn, :nn] = A
+    Ad = ctx.upload(Ap)
+    nd = ctx.upload(ns)
+    evals = ctx.empty((nprob, n_pad))
+    sw = ctx.zeros((max(2 * nprob, 2),), I32)
+    if n_pad <= 128:
+        evecs = ctx.zeros((nprob, n_pad, n_pad))
+        ctx.call('cpsd_eig_sym_small', ptr(Ad), n_pad, n_pad * n_pad, ptr(nd), 0, nprob, ptr(evals),
+                 n_pad, ptr(evecs), n_pad, n_pad * n_pad, max_sweeps, tol, ptr(sw))
+        ev, V = evals.cpu().numpy(), evecs.cpu().numpy()
+        sweeps = sw.cpu().numpy()[:nprob]
+    else:
+        nb = n_pad // 64
+        sched = np.zeros((nb - 1) * (nb // 2) * 2, dtype=np.int32)
+        _lib.check(ctx.lib.cpsd_bj_schedule(n_pad, sched.ctypes.data), 'bj_schedule')
+        sd = ctx.upload(sched)
+        V = ctx.empty((nprob, n_pad, n_pad))
+        R = ctx.empty((nprob, n_pad // 128, 128 * 128))
+        fw = ctx.empty((2 * nprob,))
+        perm = ctx.empty((nprob, n_pad), I32)
+        ctx.call('cpsd_eig_sym_block', ptr(Ad), ptr(V), n_pad, n_pad * n_pad, n_pad, ptr(nd), 0,
+                 nprob, ptr(sd), ptr(R), ptr(fw), ptr(sw), ptr(evals), ptr(perm), n_pad, max_sweeps,
+                 tol)
+        evecs = ctx.empty((nprob, n_pad, n_pad))
+        ctx.call('cpsd_permute_cols', ptr(V), n_pad, n_pad * n_pad, ptr(perm), n_pad, ptr(evecs),
+                 n_pad, n_pad * n_pad, n_pad, n_pad, nprob)
+        ev, V = evals.cpu().numpy(), evecs.cpu().numpy()
+        sweeps = sw.cpu().numpy()[nprob:2 * nprob]
+    ev, V = ev[:, :nn], V[:, :nn, :nn]
+    if single:
+        ev, V, sweeps = ev[0], V[0], sweeps[0]
+    return (ev, V, sweeps) if return_sweeps else (ev, V)
+
+
+def select_k(evals, thr, mode, n=None, kmin=0, kmax=1 << 30, device=None):
+    ctx = _ctx(device)
+    ev = np.atleast_2d(np.asarray(evals, dtype=np.float32))
+    nprob, ld = ev.shape
+    ns = np.full(nprob, ld, dtype=np.int32) if n is None else np.asarray(n, dtype=np.int32)
+    evd, nd = ctx.upload(ev), ctx.upload(ns)
+    k = ctx.empty((nprob,), I32)
+    ctx.call('cpsd_select_k', ptr(evd), ld, ptr(nd), 0, float(thr), int(mode), int(kmin), int(kmax),
+             ptr(k), 1, nprob)
+    return k.cpu().numpy()
+
+
+def gram_tn(A, B=None, seg_rows=None, seg_len=None, muA=None, muB=None, alpha=1.0, sym=None,
+            device=None):
+    """out = alpha * sum over the selected rows of (a - muA)^T (b - muB).
+    A: (rows, p); B: (rows, q) or None (= A).  seg_rows: first row of each segment."""
+    ctx = _ctx(device)
+    A = np.ascontiguousarray(A, dtype=np.float32)
+    same = B is None
+    Bm = A if same else np.ascontiguousarray(B, dtype=np.float32)
+    if seg_rows is None:
+        seg_rows, seg_len = np.zeros(1, dtype=np.int32), A.shape[0]
+    p, q = A.shape[1], Bm.shape[1]
+    Ad = ctx.upload(A)
+    Bd = Ad if same else ctx.upload(Bm)
+    pk = HostPack(ctx)
+    o = pk.add_ints(seg_rows)
+    pk.reserve_ints()
+    ma = ctx.upload(np.asarray(muA, dtype=np.float32)) if muA is not None else None
+    mb = ma if (same and muB is None) else (ctx.upload(np.asarray(muB, dtype=np.float32))
+                                            if muB is not None else None)
+    out = ctx.zeros((p, q))
+    if sym is None:
+        sym = same and (muB is None)
+    rec = np.zeros(1, dtype=_lib.GRAM_TN_DESC)
+    rec[0] = (addr(Ad), addr(Bd), pk.iaddr(o), pk.iaddr(o), addr(ma), addr(mb), addr(out),
+              len(seg_rows), int(seg_len), p, q, p, q, q, int(bool(sym)), float(alpha), 0)
+    d = pk.add_descs(rec)
+    pk.upload()
+    ctx.call('cpsd_gram_tn', pk.daddr(d), 1, p, q)
+    return out.cpu().numpy()
+
+
+def colmean(A, seg_rows=None, seg_len=None, device=None):
+    ctx = _ctx(device)
+    A = np.ascontiguousarray(A, dtype=np.float32)
+    if seg_rows is None:
+        seg_rows, seg_len = np.zeros(1, dtype=np.int32), A.shape[0]
+    Ad = ctx.upload(A)
+    pk = HostPack(ctx)
+    o = pk.add_ints(seg_rows)
+    pk.reserve_ints()
+    out = ctx.zeros((A.shape[1],))
+    rec = np.zeros(1, dtype=_lib.COLSUM_DESC)
+    rec[0] = (addr(Ad), pk.iaddr(o), addr(out), len(seg_rows), int(seg_len), A.shape[1],
+              A.shape[1], 1.0 / (len(seg_rows) * int(seg_len)), 0)
+    d = pk.add_descs(rec)
+    pk.upload()
+    ctx.call('cpsd_colsum', pk.daddr(d), 1, A.shape[1])
+    return out.cpu().numpy()
+
+
+def gram_nt(A, B=None, alpha=1.0, device=None, tensor_cores=False):
+    """out = alpha * A B^T  (A: (m, k), B: (n, k))."""
+    ctx = _ctx(device)
+    A = np.ascontiguousarray(A, dtype=np.float32)
+    same = B is None
+    Ad = ctx.upload(A)
+    Bd = Ad if same else ctx.upload(np.ascontiguousarray(B, dtype=np.float32))
+    m, k = A.shape
+    n = m if same else B.shape[0]
+    out = ctx.zeros((m, n))
+    rec = np.zeros(1, dtype=_lib.GRAM_NT_DESC)
+    rec[0] = (addr(Ad), addr(Bd), addr(out), m, n, k, k, k, n, int(same), float(alpha))
+    pk = HostPack(ctx)
+    pk.reserve_ints()
+    d = pk.add_descs(rec)
+    pk.upload()
+    ctx.call('cpsd_gram_nt_tc' if tensor_cores else 'cpsd_gram_nt', pk.daddr(d), 1, m, n)
+    return out.cpu().numpy()
+
+
+def project(X, W, mu=None, device=None):
+    """(X - mu) @ W for X (..., C), W (C, q), q <= 128."""
+    ctx = _ctx(device)
+    X = np.asarray(X, dtype=np.float32)
+    lead, C = X.shape[:-1], X.shape[-1]
+    X2 = np.ascontiguousarray(X.reshape(-1, C))
+    W = np.ascontiguousarray(W, dtype=np.float32)
+    q = W.shape[1]
+    outs = []
+    Xd, mud = ctx.upload(X2), (ctx.upload(np.asarray(mu, dtype=np.float32)) if mu is not None
+                               else None)
+    rows = X2.shape[0]
+    for j0 in range(0, q, 128):
+        Wd = ctx.upload(np.ascontiguousarray(W[:, j0:j0 + 128]))
+        qq = Wd.shape[1]
+        Y = ctx.empty((rows, qq))
+        pk = HostPack(ctx)
+        o = pk.add_ints([0])
+        pk.reserve_ints()
+        rec = np.zeros(1, dtype=_lib.PROJ_DESC)
+        rec[0] = (addr(Xd), pk.iaddr(o), pk.iaddr(o), addr(mud), addr(Wd), addr(Y), 1, rows, C, qq,
+                  C, qq, qq, 0)
+        d = pk.add_descs(rec)
+        pk.upload()
+        ctx.call('cpsd_proj_nn', pk.daddr(d), 1, 1, rows, qq)
+        outs.append(Y.cpu().numpy())
+    Y = outs[0] if len(outs) == 1 else np.concatenate(outs, axis=1)
+    return Y.reshape(lead + (q,))
+
+
+def class_mean(X, ids, device=None):
+    """Mean over trials of each class.  X: (N, ...) ; ids: (N,) ints.  Classes in sorted id
+    order.  Returns (classes, means (n_classes, ...))."""
+    ctx = _ctx(device)
+    X = np.asarray(X, dtype=np.float32)
+    N = X.shape[0]
+    TC = int(np.prod(X.shape[1:]))
+    ids = np.asarray(ids)
+    classes, inv = np.unique(ids, return_inverse=True)
+    order = np.argsort(inv, kind='stable').astype(np.int32)
+    mptr = np.concatenate([[0], np.cumsum(np.bincount(inv, minlength=len(classes)))])
+    Xd = ctx.upload(np.ascontiguousarray(X.reshape(N, TC)))
+    out = ctx.empty((len(classes), TC))
+    pk = HostPack(ctx)
+    o1, o2 = pk.add_ints(mptr), pk.add_ints(order)
+    pk.reserve_ints()
+    rec = np.zeros(1, dtype=_lib.CLASS_MEAN_DESC)
+    rec[0] = (addr(Xd), pk.iaddr(o1), pk.iaddr(o2), addr(out), len(classes), TC, 0, 0)
+    d = pk.add_descs(rec)
+    pk.upload()
+    ctx.call('cpsd_class_mean', pk.daddr(d), 1, len(classes), TC)
+    return classes, out.cpu().numpy().reshape((len(classes),) + X.shape[1:])
+
+
+def cca_solve(Saa, Sbb, Sab, device=None):
+    """CCA from scatter matrices.  Returns dict(Ma, Mb, G (db x da, b->a), rho, info)."""
+    ctx = _ctx(device)
+    da, db = Saa.shape[0], Sbb.shape[0]
+    dmax = _ceil(max(da, db), 4)
+    S = np.zeros((2 * dmax, 2 * dmax), dtype=np.float32)
+    S[:da, :da] = Saa
+    S[dmax:dmax + db, dmax:dmax + db] = Sbb
+    S[:da, dmax:dmax + db] = Sab
+    Sd = ctx.upload(S)
+    Ma, Mb, G = ctx.zeros((dmax, dmax)), ctx.zeros((dmax, dmax)), ctx.zeros((dmax, dmax))
+    rho, info = ctx.zeros((dmax,)), ctx.zeros((4,), I32)
+    rec = np.zeros(1, dtype=_lib.CCA_DESC)
+    base = addr(Sd)
+    rec[0] = (base, base + 4 * (dmax * 2 * dmax + dmax), base + 4 * dmax, 0, 0, addr(Ma), addr(Mb),
+              addr(G), addr(rho), addr(info), da, db, 2 * dmax, dmax, dmax, 0, 1e-10, 0)
+    pk = HostPack(ctx)
+    pk.reserve_ints()
+    d = pk.add_descs(rec)
+    pk.upload()
+    ctx.call('cpsd_cca_solve', pk.daddr(d), 1, dmax)
+    inf = info.cpu().numpy()
+    dd = int(inf[0])
+    return dict(Ma=Ma.cpu().numpy()[:da, :dd], Mb=Mb.cpu().numpy()[:db, :dd],
+                G=G.cpu().numpy()[:db, :da], rho=rho.cpu().numpy()[:dd], info=inf)
+
+
+def svm_fit_ovr(S, y, C=1.0, dcd_epochs=0, max_newton=60, tol_newton=1e-9, tol_dcd=1e-4,
+                device=None):
+    """One-vs-rest L2-regularised squared-hinge linear SVM.  S: (n, k) features, y: (n,) ints.
+    Returns (classes, W (n_classes, k+1) float64 with the bias last, info (n_classes, 4))."""
+    ctx = _ctx(device)
+    S = np.asarray(S, dtype=np.float32)
+    n, k = S.shape
+    y = np.asarray(y).astype(np.int32)
+    classes = np.unique(y).astype(np.int32)
+    lds = _ceil(n, 4)
+    St = np.zeros((max(k, 1), lds), dtype=np.float32)
+    St[:k, :n] = S.T
+    Sd, yd = ctx.upload(St), ctx.upload(y)
+    W = ctx.zeros((len(classes), k + 1), F64)
+    info = ctx.zeros((len(classes), 4), I32)
+    rec = np.zeros(len(classes), dtype=_lib.SVM_DESC)
+    for c, cv in enumerate(classes):
+        rec[c] = (addr(Sd), addr(yd), 0, addr(W, c * (k + 1)), addr(info, c * 4), n, k, lds,
+                  int(cv), float(C), float(tol_dcd), float(tol_newton), int(max_newton),
+                  int(dcd_epochs))
+    pk = HostPack(ctx)
+    pk.reserve_ints()
+    d = pk.add_descs(rec)
+    pk.upload()
+    ctx.call('cpsd_svm_fit_ovr', pk.daddr(d), len(classes), k, lds)
+    return classes, W.cpu().numpy(), info.cpu().numpy()
+
+
+def svm_predict_ovr(S, classes, W, device=None, return_decision=False):
+    ctx = _ctx(device)
+    S = np.asarray(S, dtype=np.float32)
+    n, k = S.shape
+    Xt = ctx.upload(np.ascontiguousarray(S.T) if k else np.zeros((1, n), dtype=np.float32))
+    Wd = ctx.upload(np.ascontiguousarray(W, dtype=np.float64))
+    cd = ctx.upload(np.asarray(classes, dtype=np.int32))
+    yh = ctx.empty((n,), I32)
+    dec = ctx.empty((n, len(classes)), F64)
+    ctx.call('cpsd_svm_predict_ovr', ptr(Xt), n, 0, ptr(Wd), k + 1, 0, ptr(None), k, ptr(None), n,
+             ptr(cd), len(classes), ptr(yh), ptr(dec), 1)
+    if return_decision:
+        return yh.cpu().numpy(), dec.cpu().numpy()
+    return yh.cpu().numpy()

@@ -1,0 +1,138 @@
+/* cpsd_b200 -- C ABI of the B200 (sm_100a) kernels behind the cross-validated
+ * align -> reduce -> decode loop of coganlab/cross_patient_speech_decoding.
+ *
+ * The reference is pure Python: its "interface" for this path is the sklearn-style class
+ * surface (AlignCCA / AlignMCCA / JointPCA / DimRedReshape / NoCenterPCA / crossPtDecoder_*),
+ * mirrored in Python by the package cross_patient_speech_decoding_b200.  Those classes and
+ * the batched engine call ONLY the functions below (through ctypes, see _lib.py); each
+ * entry cites the reference code whose arithmetic it replaces (paths relative to
+ * aligned_decoding/ in the reference tree).
+ *
+ * Conventions: plain C, device pointers unless named *_host, row-major fp32, explicit
+ * leading dimensions and batch strides (in elements), per-problem sizes optionally read
+ * from device int arrays (`*_dev`, may be NULL -> the `*_fixed` scalar applies), every
+ * function is asynchronous on `stream` and returns 0 on success (CPSD_OK) or a non-zero
+ * status with a message retrievable through cpsd_last_error().  No global state except
+ * the error string (thread local) and a launch counter.
+ */
+#ifndef CPSD_B200_H
+#define CPSD_B200_H
+
+#include <cuda_runtime_api.h>
+#include "../cross_patient_speech_decoding_b200/csrc/descs.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPSD_OK 0
+#define CPSD_ERR_INVALID 1
+#define CPSD_ERR_CUDA 2
+#define CPSD_ERR_UNSUPPORTED 3
+
+/* ---- library ------------------------------------------------------------------- */
+int cpsd_version(void);
+int cpsd_device_arch(void);                 /* major*10+minor of the current device */
+const char* cpsd_last_error(void);
+long long cpsd_launch_count(void);          /* kernels launched by this library so far */
+void cpsd_reset_launch_count(void);
+int cpsd_desc_sizes(int* out_host);         /* sizeof of the 7 descriptor records */
+
+/* ---- streaming stages ------------------------------------------------------------
+ * cnd_avg / extract_group_conditions (alignment/alignment_utils.py:42-61, 12-39): mean of
+ * the trials of each class, trials kept in [trial][time][channel] layout. */
+int cpsd_class_mean(const cpsd_class_mean_desc* descs, int nprob, int nslot_max, int TC,
+                    cudaStream_t stream);
+/* column means over selected row segments (centering of AlignCCA.py:259-260, PCA mean_,
+ * mvlearn MCCA means_) */
+int cpsd_colsum(const cpsd_colsum_desc* descs, int nprob, int p_max, cudaStream_t stream);
+int cpsd_center_rows(float* Z, int ld, long long strideZ, const float* mu, int ldmu,
+                     const int* nrows_dev, int nrows_fixed, int nrows_max, int ncols, int nprob,
+                     cudaStream_t stream);
+int cpsd_copy_rows(const float* src, int lds, long long strideS, float* dst, int ldd,
+                   long long strideD, const int* r0_dev, int r0_fixed, int nrows, int ncols,
+                   int nprob, cudaStream_t stream);
+int cpsd_permute_cols(const float* src, int lds, long long strideS, const int* perm, int ld_perm,
+                      float* dst, int ldd, long long strideD, int nrows, int ncols, int nprob,
+                      cudaStream_t stream);
+
+/* ---- covariance / projection GEMMs -------------------------------------------------
+ * X^T X, X^T Y over trial- or class-selected rows: sklearn PCA covariance_eigh reached from
+ * decoders/cross_pt_decoders.py:234-241; AlignMCCA.n_components_var (alignment/AlignMCCA.py:
+ * 156-174); scatter blocks of CCA_align (alignment/AlignCCA.py:235-285) and of the MCCA
+ * GEVP (AlignMCCA.py:140-154). */
+int cpsd_gram_tn(const cpsd_gram_tn_desc* descs, int nprob, int p_max, int q_max,
+                 cudaStream_t stream);
+/* (X - mu) W: PCA.transform, AlignCCA.transform (AlignCCA.py:93), MCCA transform_view
+ * (AlignMCCA.py:110,125), JointPCA.transform (JointPCA.py:132,149); output rows land
+ * directly in the pooled trials x (time*latent) matrix (cross_pt_decoders.py:260-270). */
+int cpsd_proj_nn(const cpsd_proj_desc* descs, int nprob, int nseg_max, int seg_len, int q_max,
+                 cudaStream_t stream);
+/* A B^T over the long feature axis: Gram of the pooled matrix for the decoder-stage PCA
+ * (decomposition/DimRedReshape.py:47-49 -> sklearn PCA full SVD). */
+int cpsd_gram_nt(const cpsd_gram_nt_desc* descs, int nprob, int m_max, int n_max,
+                 cudaStream_t stream);
+/* same contract, tcgen05 / TMEM tensor-core path (3xTF32 split, fp32 accumulate) */
+int cpsd_gram_nt_tc(const cpsd_gram_nt_desc* descs, int nprob, int m_max, int n_max,
+                    cudaStream_t stream);
+
+/* ---- small solvers ---------------------------------------------------------------
+ * symmetric eigen-decomposition, n <= 128, one CTA per problem, shared-memory Jacobi
+ * (replaces LAPACK syevd/gesdd behind PCA, n_components_var and the MCCA GEVP). */
+int cpsd_eig_sym_small(const float* A, int lda, long long strideA, const int* n_dev, int n_fixed,
+                       int nprob, float* evals, int ld_e, float* evecs, int ldv, long long strideV,
+                       int max_sweeps, float tol, int* sweeps_out, cudaStream_t stream);
+/* block Jacobi for n > 128 (n_pad multiple of 128): pooled-Gram PCA, large GEVPs */
+int cpsd_bj_schedule(int n_pad, int* pairs_host);
+int cpsd_eig_sym_block(float* K, float* V, int ld, long long stride, int n_pad, const int* n_dev,
+                       int n_fixed, int nprob, const int* pairs_dev, float* Rbuf, float* fwork,
+                       int* iwork, float* evals, int* perm, int ld_e, int max_sweeps, float tol,
+                       cudaStream_t stream);
+/* component counts: sklearn PCA float n_components (mode 0), AlignMCCA.n_components_var
+ * (mode 1, AlignMCCA.py:174), NoCenterPCA (mode 2, NoCenterPCA.py:101-103), integer (mode 3) */
+int cpsd_select_k(const float* evals, int ld_e, const int* n_dev, int n_fixed, float thr, int mode,
+                  int kmin, int kmax, int* k_out, int k_stride, int nprob, cudaStream_t stream);
+/* PCA components with sklearn's svd_flip sign convention, zero padded to dmax columns */
+int cpsd_pca_basis(const float* evecs, int ldv, long long strideV, const int* k_dev,
+                   const int* cdim, int c_fixed, int dmax, float* W, int ldw, int Cmax, int nprob,
+                   cudaStream_t stream);
+/* CCA_align in Gram form: Cholesky whitening + one-sided Jacobi SVD (AlignCCA.py:235-285),
+ * and the b->a map M_b pinv(M_a) of AlignCCA.transform (AlignCCA.py:93) */
+int cpsd_cca_solve(const cpsd_cca_desc* descs, int nprob, int dmax, cudaStream_t stream);
+
+/* ---- MCCA assembly (mvlearn.embed.MCCA as called at AlignMCCA.py:152-153) ---------- */
+int cpsd_mcca_mask(const float* evecs, int ldv, long long strideV, const float* evals, int ld_e,
+                   const int* rank, const int* cdim, int R, int Cmax, float* Vr, float* d2,
+                   int* r_eff, int nprob, cudaStream_t stream);
+int cpsd_mcca_build(const float* G, int ldg, long long strideG, const int* r_eff, int P, int R,
+                    float reg, float* M, int ldm, long long strideM, int* n_out, int* cidx,
+                    float* dh, int n_comp, int* status, int nfold, cudaStream_t stream);
+int cpsd_mcca_loadings(const float* Vr, const float* U, int ldu, long long strideU,
+                       const int* perm, int ld_perm, const int* r_eff, const float* dh, int P,
+                       int R, int Cmax, int n_comp, float* L, int ldl, int nfold,
+                       cudaStream_t stream);
+
+/* ---- decoder stage -----------------------------------------------------------------
+ * PCA scores of the pooled train / test trials from the Gram eigen-pairs */
+int cpsd_scores_train(const float* V, int ldv, long long strideV, const float* evals,
+                      const int* perm, int ld_e, const int* k_dev, const int* n_dev, int n_fixed,
+                      int n_max, float* St, int lds, long long strideS, int kcap, int nfold,
+                      cudaStream_t stream);
+int cpsd_scores_test(const float* Kte, int ldk, long long strideK, const float* V, int ldv,
+                     long long strideV, const float* evals, const int* perm, int ld_e,
+                     const int* k_dev, const int* n_dev, int n_fixed, int n_te, float* Ste,
+                     int ldt, long long strideT, int kcap, int nfold, cudaStream_t stream);
+/* one-vs-rest linear SVM: dual coordinate descent (liblinear solve_l2r_l1l2_svc, L2 loss)
+ * + Newton polish on the same objective; the decoder injected at
+ * decoders/cross_pt_decoders.py:46-59 */
+int cpsd_svm_fit_ovr(const cpsd_svm_desc* descs, int ntask, int k_max, int n_max,
+                     cudaStream_t stream);
+int cpsd_svm_predict_ovr(const float* Xt, int ldx, long long strideX, const double* W, int ldw,
+                         long long strideW, const int* k_dev, int k_fixed, const int* n_te,
+                         int n_te_max, const int* classes, int ncls, int* yhat, double* dec,
+                         int nfold, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPSD_B200_H */

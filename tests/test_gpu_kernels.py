@@ -1,0 +1,239 @@
+"""Kernel-level parity: every CUDA kernel (through the C-ABI, host buffers in/out) against
+a float64 numpy statement of the same operation on seeded inputs."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ops(lib_built):
+    from cross_patient_speech_decoding_b200 import ops
+    return ops
+
+
+def _rand_sym(rng, n, psd=True):
+    X = rng.standard_normal((n, max(n // 2, 3) if psd else n))
+    return X @ X.T if psd else X + X.T
+
+
+@pytest.mark.parametrize('n', [1, 2, 3, 13, 30, 69, 100, 127, 128])
+def test_eig_small(ops, n):
+    rng = np.random.default_rng(n)
+    A = np.stack([_rand_sym(rng, n, psd=(i % 2 == 0)) for i in range(5)])
+    ev, V = ops.eig_sym(A)
+    for i in range(5):
+        ref = np.linalg.eigvalsh(A[i])[::-1]
+        scale = np.abs(ref).max() + 1e-30
+        assert np.abs(ev[i] - ref).max() <= 2e-5 * scale
+        assert np.abs(V[i].T @ V[i] - np.eye(n)).max() < 5e-5
+        assert np.abs(A[i] @ V[i] - V[i] * ev[i]).max() <= 5e-5 * scale
+
+
+def test_eig_small_ragged_sizes(ops):
+    rng = np.random.default_rng(0)
+    ns = np.array([5, 40, 17, 64], dtype=np.int32)
+    A = np.zeros((4, 64, 64))
+    for i, n in enumerate(ns):
+        A[i, :n, :n] = _rand_sym(rng, n)
+    ev, V = ops.eig_sym(A, n=ns)
+    for i, n in enumerate(ns):
+        ref = np.linalg.eigvalsh(A[i, :n, :n])[::-1]
+        assert np.abs(ev[i, :n] - ref).max() <= 2e-5 * ref[0]
+
+
+@pytest.mark.parametrize('n', [129, 240, 300, 640])
+def test_eig_block(ops, n):
+    rng = np.random.default_rng(n)
+    A = np.stack([_rand_sym(rng, n, psd=(i == 0)) for i in range(2)])
+    ev, V, sw = ops.eig_sym(A, return_sweeps=True)
+    assert (sw <= 14).all(), sw
+    for i in range(2):
+        ref = np.linalg.eigvalsh(A[i])[::-1]
+        scale = np.abs(ref).max()
+        assert np.abs(ev[i] - ref).max() <= 3e-5 * scale
+        assert np.abs(V[i].T @ V[i] - np.eye(n)).max() < 1e-4
+        assert np.abs(A[i] @ V[i] - V[i] * ev[i]).max() <= 1e-4 * scale
+
+
+def test_eig_block_pooled_spectrum(ops):
+    """A spectrum like the pooled Gram: a few large, a flat bulk, exact rank deficiency."""
+    rng = np.random.default_rng(1)
+    n, F = 700, 900
+    Z = rng.standard_normal((n, F)) + 4 * rng.standard_normal((n, 6)) @ rng.standard_normal((6, F))
+    Z -= Z.mean(0)
+    K = Z @ Z.T
+    ev, V = ops.eig_sym(K)
+    ref_w, ref_v = np.linalg.eigh(K)
+    ref_w, ref_v = ref_w[::-1], ref_v[:, ::-1]
+    assert np.abs(ev - ref_w).max() <= 3e-5 * ref_w[0]
+    k = 50
+    s = np.linalg.svd(ref_v[:, :k].T @ V[:, :k], compute_uv=False)
+    assert s.min() > 1 - 1e-4
+
+
+def test_select_k_modes(ops):
+    ev = np.array([[5.0, 3.0, 1.0, 0.5, 0.5, 0.0]], dtype=np.float32)
+    r = np.cumsum(ev[0]) / ev[0].sum()
+    assert ops.select_k(ev, 0.8, 0)[0] == np.searchsorted(r, 0.8, side='right') + 1
+    assert ops.select_k(ev, 0.8, 1)[0] == np.argmax(r > 0.8)
+    assert ops.select_k(ev, 0.8, 2)[0] == np.argmax(r >= 0.8) + 1
+    assert ops.select_k(ev, 0.999999, 1)[0] == np.argmax(r > 0.999999)
+    assert ops.select_k(ev, 4, 3)[0] == 4
+
+
+@pytest.mark.parametrize('shape', [(1000, 128, 128), (333, 33, 70), (64, 201, 201), (5, 7, 3)])
+def test_gram_tn(ops, shape):
+    rows, p, q = shape
+    rng = np.random.default_rng(rows)
+    A = rng.standard_normal((rows, p)) + 0.5
+    B = rng.standard_normal((rows, q)) - 0.25
+    G = ops.gram_tn(A, B)
+    ref = A.T @ B
+    assert np.abs(G - ref).max() <= 2e-5 * np.abs(ref).max() + 1e-4
+    muA, muB = A.mean(0), B.mean(0)
+    Gc = ops.gram_tn(A, B, muA=muA, muB=muB, alpha=0.5)
+    refc = 0.5 * (A - muA).T @ (B - muB)
+    assert np.abs(Gc - refc).max() <= 2e-5 * np.abs(refc).max() + 1e-4
+    if p == q:
+        Gs = ops.gram_tn(A)
+        assert np.abs(Gs - A.T @ A).max() <= 2e-5 * np.abs(A.T @ A).max()
+        assert np.array_equal(Gs, Gs.T)
+
+
+def test_gram_tn_segments(ops):
+    rng = np.random.default_rng(3)
+    T, C = 50, 40
+    X = rng.standard_normal((12 * T, C))
+    sel = np.array([7, 0, 3, 11])
+    G = ops.gram_tn(X, seg_rows=sel * T, seg_len=T)
+    Xs = np.concatenate([X[s * T:(s + 1) * T] for s in sel])
+    assert np.abs(G - Xs.T @ Xs).max() <= 2e-5 * np.abs(Xs.T @ Xs).max()
+    m = ops.colmean(X, seg_rows=sel * T, seg_len=T)
+    assert np.abs(m - Xs.mean(0)).max() < 1e-5
+
+
+@pytest.mark.parametrize('shape', [(259, 259, 2600), (130, 130, 515), (8, 300, 1000), (1, 1, 5)])
+def test_gram_nt(ops, shape):
+    m, n, k = shape
+    rng = np.random.default_rng(m + k)
+    A = rng.standard_normal((m, k))
+    if m == n:
+        K = ops.gram_nt(A)
+        ref = A @ A.T
+        assert np.array_equal(K, K.T)
+    else:
+        B = rng.standard_normal((n, k))
+        K = ops.gram_nt(A, B)
+        ref = A @ B.T
+    assert np.abs(K - ref).max() <= 3e-5 * np.abs(ref).max() + 1e-5
+
+
+@pytest.mark.parametrize('C,q', [(128, 30), (33, 13), (201, 100), (64, 128), (10, 1)])
+def test_project(ops, C, q):
+    rng = np.random.default_rng(C + q)
+    X = rng.standard_normal((7, 53, C))
+    W = rng.standard_normal((C, q))
+    mu = rng.standard_normal(C)
+    Y = ops.project(X, W, mu)
+    ref = (X - mu) @ W
+    assert Y.shape == ref.shape
+    assert np.abs(Y - ref).max() <= 2e-5 * np.abs(ref).max()
+    Y0 = ops.project(X, W)
+    assert np.abs(Y0 - X @ W).max() <= 2e-5 * np.abs(X @ W).max()
+
+
+def test_class_mean(ops):
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((40, 20, 17))        # T*C = 340 (float4 path), odd C below
+    ids = rng.integers(0, 9, 40)
+    cls, M = ops.class_mean(X, ids)
+    assert np.array_equal(cls, np.unique(ids))
+    for i, c in enumerate(cls):
+        assert np.abs(M[i] - X[ids == c].mean(0)).max() < 1e-5
+    X2 = rng.standard_normal((15, 7, 3))         # T*C = 21: scalar path
+    ids2 = rng.integers(0, 4, 15)
+    cls2, M2 = ops.class_mean(X2, ids2)
+    for i, c in enumerate(cls2):
+        assert np.abs(M2[i] - X2[ids2 == c].mean(0)).max() < 1e-5
+
+
+def _cca_ref(La, Lb):
+    """Reference CCA_align in float64 (AlignCCA.py:235-285), written out for the test."""
+    La = La - La.mean(0)
+    Lb = Lb - Lb.mean(0)
+    Qa, Ra = np.linalg.qr(La)
+    Qb, Rb = np.linalg.qr(Lb)
+    U, S, Vt = np.linalg.svd(Qa.T @ Qb)
+    d = min(La.shape[1], Lb.shape[1])
+    Ma = np.linalg.pinv(Ra) @ U[:, :d]
+    Mb = np.linalg.pinv(Rb) @ Vt.T[:, :d]
+    return Ma, Mb, np.clip(S[:d], 0, 1), La, Lb
+
+
+@pytest.mark.parametrize('da,db', [(13, 13), (20, 14), (9, 26), (60, 60), (100, 97), (1, 1)])
+def test_cca_solve(ops, da, db):
+    rng = np.random.default_rng(da * 100 + db)
+    n = 900
+    Zs = rng.standard_normal((n, max(da, db)))
+    La = Zs[:, :da] @ rng.standard_normal((da, da)) + 0.3 * rng.standard_normal((n, da))
+    Lb = Zs[:, :db] @ rng.standard_normal((db, db)) + 0.3 * rng.standard_normal((n, db))
+    Ma, Mb, rho, Lac, Lbc = _cca_ref(La, Lb)
+    out = ops.cca_solve(Lac.T @ Lac, Lbc.T @ Lbc, Lac.T @ Lbc)
+    assert out['info'][0] == min(da, db)
+    assert np.abs(out['rho'] - rho).max() < 1e-4
+    # canonical variates: correlations of the projected data equal rho, variates are white
+    Pa, Pb = Lac @ out['Ma'], Lbc @ out['Mb']
+    assert np.abs(Pa.T @ Pa - np.eye(len(rho))).max() < 2e-3
+    assert np.abs(np.diag(Pa.T @ Pb) - rho).max() < 2e-4
+    # b -> a map equals M_b pinv(M_a) of the reference
+    Gref = Mb @ np.linalg.pinv(Ma)
+    num = np.abs(Lbc @ out['G'] - Lbc @ Gref).max()
+    assert num <= 2e-3 * np.abs(Lbc @ Gref).max()
+
+
+def test_svm_matches_liblinear_primal(ops):
+    from sklearn.svm import LinearSVC
+    rng = np.random.default_rng(0)
+    n, k = 300, 20
+    X = rng.standard_normal((n, k)) * np.linspace(60, 5, k)     # unscaled PCA-like scores
+    w = rng.standard_normal((k, 4))
+    y = np.argmax(X @ w + 30 * rng.standard_normal((n, 4)), 1) + 3
+    cls, W, info = ops.svm_fit_ovr(X, y, C=1.0, dcd_epochs=2)
+    assert (info[:, 3] == 0).all(), info
+    ref = LinearSVC(dual=False, C=1.0, tol=1e-12, max_iter=100000).fit(X, y)
+    Wref = np.hstack([ref.coef_, ref.intercept_[:, None]])
+    assert np.array_equal(cls, ref.classes_)
+    assert np.abs(W - Wref).max() <= 1e-6 * np.abs(Wref).max() + 1e-9
+    Xte = rng.standard_normal((50, k)) * np.linspace(60, 5, k)
+    yh, dec = ops.svm_predict_ovr(Xte, cls, W, return_decision=True)
+    assert np.array_equal(yh, ref.predict(Xte))
+    assert np.abs(dec - ref.decision_function(Xte)).max() < 1e-4
+
+
+def test_svm_dcd_alone_matches_liblinear_dual(ops):
+    """Phase 1 alone (no Newton) on a well-conditioned problem where liblinear's own dual CD
+    converges: same optimum as LinearSVC(dual=True)."""
+    from sklearn.svm import LinearSVC
+    rng = np.random.default_rng(1)
+    n, k = 200, 10
+    X = rng.standard_normal((n, k))
+    y = (X[:, 0] + 0.5 * X[:, 1] + 0.7 * rng.standard_normal(n) > 0).astype(int)
+    cls, W, info = ops.svm_fit_ovr(X, y, C=0.5, dcd_epochs=5000, max_newton=0, tol_dcd=1e-7)
+    assert (info[:, 3] == 0).all(), info
+    ref = LinearSVC(dual=True, C=0.5, tol=1e-8, max_iter=200000, random_state=0).fit(X, y)
+    wref = np.hstack([ref.coef_[0], ref.intercept_])
+    # binary sklearn keeps one row for the positive class (classes_[1])
+    assert np.abs(W[1] - wref).max() < 1e-4
+    assert np.abs(W[0] + wref).max() < 1e-4
+
+
+def test_svm_edge_cases(ops):
+    rng = np.random.default_rng(2)
+    X = rng.standard_normal((30, 1))
+    y = np.array([1] * 15 + [2] * 15)
+    cls, W, info = ops.svm_fit_ovr(X, y)
+    assert W.shape == (2, 2) and np.isfinite(W).all()
+    # k = 0 features: bias only
+    cls, W, info = ops.svm_fit_ovr(np.zeros((10, 0)), np.array([0, 1] * 5))
+    assert W.shape == (2, 1) and np.isfinite(W).all()

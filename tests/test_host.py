@@ -1,0 +1,122 @@
+"""CPU-side checks: fold-index generation is bit-exact against sklearn, golden fold indices
+are reproducible from seeds, and the C-ABI library loads and exports every symbol that
+include/cpsd_b200.h declares (no compute calls: there is no GPU here)."""
+import ctypes
+import os
+import re
+import sys
+import warnings
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, os.path.join(HERE, 'golden'))
+
+
+def test_stratified_kfold_bit_exact():
+    from sklearn.model_selection import KFold, StratifiedKFold
+    from cross_patient_speech_decoding_b200.folds import cv_splits, kfold, stratified_kfold
+    rng = np.random.default_rng(0)
+    warnings.simplefilter('ignore')
+    for trial in range(30):
+        n = int(rng.integers(30, 200))
+        y = rng.integers(1, 10, n)
+        ns = int(rng.integers(2, 21))
+        np.random.seed(trial)
+        try:
+            ref = list(StratifiedKFold(ns, shuffle=True).split(np.zeros(n), y))
+        except ValueError:
+            np.random.seed(trial)
+            ref = list(KFold(ns, shuffle=True).split(np.zeros(n)))
+        np.random.seed(trial)
+        got = cv_splits(y, ns)
+        assert len(ref) == len(got)
+        for (a, b), (c, d) in zip(ref, got):
+            assert np.array_equal(a, c) and np.array_equal(b, d)
+    # explicit RandomState and int seeds
+    y = rng.integers(0, 5, 100)
+    ref = list(StratifiedKFold(5, shuffle=True, random_state=3).split(np.zeros(100), y))
+    got = stratified_kfold(y, 5, random_state=3)
+    assert all(np.array_equal(a[1], b[1]) for a, b in zip(ref, got))
+    ref = list(KFold(7, shuffle=True, random_state=4).split(np.zeros(100)))
+    got = kfold(100, 7, random_state=4)
+    assert all(np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) for a, b in zip(ref, got))
+
+
+def test_label_strings_and_class_order():
+    from cross_patient_speech_decoding_b200.folds import class_ids, label2str
+    lab = np.array([[1, 2, 3], [10, 1, 1], [2, 9, 9]])
+    assert list(label2str(lab)) == ['123', '1011', '299']
+    assert list(label2str(np.array([3, 10, 2]))) == ['3', '10', '2']
+    ids, vocab = class_ids([np.array([10, 2, 3]), np.array([2, 2, 11])])
+    assert list(vocab) == ['10', '11', '2', '3']          # lexicographic, as np.unique of str
+    assert list(ids[0]) == [0, 2, 3] and list(ids[1]) == [2, 2, 1]
+
+
+def test_golden_fold_indices_reproducible():
+    import make_golden
+    for name, cfg in make_golden.CONFIGS.items():
+        path = os.path.join(HERE, 'golden', name + '.npz')
+        if not os.path.exists(path):
+            pytest.skip('golden file missing: ' + name)
+        g = np.load(path)
+        pts = [(None, None, None)]
+        # only labels are needed: regenerate patient 0 cheaply
+        from cross_patient_speech_decoding_b200 import synthetic
+        kw = dict(cfg['patients'][0])
+        kw.update(n_time=2, n_chan=2)
+        _, y, _ = synthetic.make_patient(**kw)
+        from cross_patient_speech_decoding_b200.folds import cv_splits
+        np.random.seed(cfg['seed'])
+        folds = cv_splits(y, cfg['n_splits'])
+        for f in range(int(g['n_folds'])):
+            assert np.array_equal(folds[f][0], g['train_%d' % f])
+            assert np.array_equal(folds[f][1], g['test_%d' % f])
+
+
+def test_synthetic_labels_do_not_depend_on_shape():
+    from cross_patient_speech_decoding_b200 import synthetic
+    _, y1, ya1 = synthetic.make_patient(0, n_time=2, n_chan=2)
+    _, y2, ya2 = synthetic.make_patient(0, n_time=5, n_chan=3)
+    assert np.array_equal(y1, y2) and np.array_equal(ya1, ya2)
+
+
+def test_library_exports_header_symbols(lib_built):
+    hdr = open(os.path.join(ROOT, 'include', 'cpsd_b200.h')).read()
+    names = sorted(set(re.findall(r'\b(cpsd_[a-z0-9_]+)\s*\(', hdr)))
+    assert len(names) >= 25
+    lib = ctypes.CDLL(lib_built)
+    for n in names:
+        assert hasattr(lib, n), 'missing export ' + n
+    from cross_patient_speech_decoding_b200 import _lib
+    assert set(names) == set(_lib.EXPORTED_SYMBOLS), set(names) ^ set(_lib.EXPORTED_SYMBOLS)
+    handle = _lib.load()      # also checks descriptor sizes against descs.h
+    assert handle.cpsd_version() >= 100
+
+
+def test_block_jacobi_schedule_is_a_tournament(lib_built):
+    lib = ctypes.CDLL(lib_built)
+    for n_pad in (256, 384, 1152):
+        nb = n_pad // 64
+        out = np.zeros((nb - 1) * (nb // 2) * 2, dtype=np.int32)
+        assert lib.cpsd_bj_schedule(n_pad, out.ctypes.data_as(ctypes.c_void_p)) == 0
+        pairs = out.reshape(nb - 1, nb // 2, 2)
+        seen = set()
+        for r in range(nb - 1):
+            assert sorted(pairs[r].ravel().tolist()) == list(range(nb))   # disjoint cover
+            for a, b in pairs[r]:
+                assert a < b
+                seen.add((int(a), int(b)))
+        assert len(seen) == nb * (nb - 1) // 2                            # every pair once
+
+
+def test_product_path_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from cross_patient_speech_decoding_b200 import _lib
+    from cross_patient_speech_decoding_b200.device import Context
+    with pytest.raises(_lib.CpsdError):
+        Context(None)
