@@ -89,7 +89,8 @@ _SIGS = {
                              _P, c_int, _P],
     'cpsd_cca_solve': [_P, c_int, c_int, _P],
     'cpsd_pca_basis': [_P, c_int, c_ll, _P, c_int, _P, _P, c_int, c_int, _P, c_int, c_int, _P],
-    'cpsd_gram_nt_tc': [_P, c_int, c_int, c_int, _P],
+    'cpsd_gram_nt_tc': [_P, c_int, c_int, c_int, _P, c_ll, _P, _P, _P],
+    'cpsd_gram_nt_tc_ws_bytes': [c_int],
 }
 _RESTYPES = {'cpsd_last_error': ctypes.c_char_p, 'cpsd_launch_count': c_ll,
              'cpsd_reset_launch_count': None}

@@ -45,7 +45,7 @@ __device__ __forceinline__ void mod_pair(int s, int k, int m, int& i, int& j) {
 //   As : m x m symmetric (row stride TS), Vs : vrows x m (row stride TS)
 //   npairs pairs (sb->pi[k], sb->pj[k]) must already be stored by the caller.
 // Returns (per calling thread) the largest |a_pq| it looked at.
-__device__ __forceinline__ float tile_rotations(float* As, StepBuf* sb, int npairs,
+__device__ __forceinline__ float tile_rotations(float* As, StepBuf* sb, int npairs, int nrot,
                                                 float skip_thr) {
   float seen = 0.f;
   const int k = threadIdx.x;
@@ -53,7 +53,7 @@ __device__ __forceinline__ float tile_rotations(float* As, StepBuf* sb, int npai
     const int i = sb->pi[k], j = sb->pj[k];
     const float app = As[i * TS + i], aqq = As[j * TS + j], apq = As[i * TS + j];
     float c = 1.f, s = 0.f, d = 0.f;
-    const float aa = fabsf(apq);
+    const float aa = (k < nrot) ? fabsf(apq) : 0.f;   // slots >= nrot only carry idle indices
     seen = aa;
     if (aa > skip_thr) {
       const float tau = (aqq - app) / (2.f * apq);
@@ -119,16 +119,24 @@ __device__ __forceinline__ void tile_apply(float* As, float* Vs, StepBuf* sb, in
 __device__ float tile_sweep_full(float* As, float* Vs, StepBuf* sb, int m, int vrows,
                                  float skip_thr, int* redmax) {
   float seen = 0.f;
+  const int npairs = m >> 1;
   for (int s = 0; s < m; ++s) {
-    const int npairs = (s & 1) ? (m >> 1) : (m >> 1) - 1;
+    // even steps leave two indices (s/2 and s/2 + m/2) unpaired: they ride along in the last
+    // slot with an identity rotation so that their rows / columns still get updated
+    const int nrot = (s & 1) ? npairs : npairs - 1;
     if ((int)threadIdx.x < npairs) {
       int i, j;
-      mod_pair(s, threadIdx.x, m, i, j);
+      if ((int)threadIdx.x < nrot) {
+        mod_pair(s, threadIdx.x, m, i, j);
+      } else {
+        i = s >> 1;
+        j = (i + npairs) % m;
+      }
       sb->pi[threadIdx.x] = i;
       sb->pj[threadIdx.x] = j;
     }
     __syncthreads();
-    seen = fmaxf(seen, tile_rotations(As, sb, npairs, skip_thr));
+    seen = fmaxf(seen, tile_rotations(As, sb, npairs, nrot, skip_thr));
     __syncthreads();
     tile_apply(As, Vs, sb, npairs, vrows);
     __syncthreads();
@@ -151,7 +159,7 @@ __device__ float tile_sweep_cross(float* As, float* Vs, StepBuf* sb, float skip_
       sb->pj[threadIdx.x] = BS + ((threadIdx.x + s) & (BS - 1));
     }
     __syncthreads();
-    seen = fmaxf(seen, tile_rotations(As, sb, BS, skip_thr));
+    seen = fmaxf(seen, tile_rotations(As, sb, BS, BS, skip_thr));
     __syncthreads();
     tile_apply(As, Vs, sb, BS, TS);
     __syncthreads();

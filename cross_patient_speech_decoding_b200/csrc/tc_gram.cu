@@ -1,10 +1,339 @@
-// tcgen05 / TMEM pooled-Gram kernel -- placeholder until the tensor-core path lands.
+// Pooled Gram  K = Z Z^T  on the 5th-generation tensor cores (sm_100a only).
+//
+// Replaces the fp32 SIMT k_gram_nt for the decoder-stage PCA (reference:
+// decomposition/DimRedReshape.py:47-49 -> sklearn PCA full SVD of the pooled
+// trials x (time*latent) matrix; here the n_pool x n_pool Gram over the long axis).
+//
+// Precision: 3xTF32.  Z is split once into hi = tf32(Z) (low 13 mantissa bits cleared) and
+// lo = Z - hi (exact in fp32); each 128x128 output tile accumulates
+//        hi_i hi_j^T + hi_i lo_j^T + lo_i hi_j^T
+// in fp32 in TMEM, i.e. every product term except lo*lo (relative 2^-20) -- the same error
+// class as an fp32 FMA chain, which is what the PCA variance threshold needs
+// (plain TF32 would perturb the spectrum at 1e-3 relative).
+//
+// Structure (one CTA per upper-triangular output tile, 192 threads):
+//   warp 0   : TMA producer   cp.async.bulk.tensor.2d -> 128B-swizzled smem ring (3 stages
+//              of {A_hi, A_lo, B_hi, B_lo}, 128 rows x 32 fp32 each)
+//   warp 1   : TMEM allocator + single-thread tcgen05.mma.kind::tf32 issuer (M=128, N=128,
+//              K=8), tcgen05.commit releases smem stages / signals the epilogue
+//   warps 2-5: epilogue  tcgen05.ld (32 lanes x 32 columns per warp) -> registers ->
+//              global, plus the mirrored tile (the transposed store is the coalesced one)
 #include "common.cuh"
 #include "descs.h"
+#include <cuda.h>
 
-extern "C" int cpsd_gram_nt_tc(const cpsd_gram_nt_desc* descs_dev, int nprob, int m_max, int n_max,
-                               cudaStream_t stream) {
-  (void)descs_dev; (void)nprob; (void)m_max; (void)n_max; (void)stream;
-  cpsd_set_error("gram_nt_tc: tensor-core path not built in this revision");
-  return CPSD_ERR_UNSUPPORTED;
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 32;      // BK fp32 = 128 bytes = one swizzle row
+constexpr int STAGES = 3;
+constexpr int TILE_BYTES = BM * BK * 4;          // 16 KB
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;      // A_hi, A_lo, B_hi, B_lo
+constexpr int TC_THREADS = 192;
+constexpr uint32_t TMEM_COLS = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+// Bounded wait: a lost arrival traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int c0, int c1,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+// K-major operand, 128-byte swizzle: 8-row groups are 1024 B apart (SBO), LBO unused.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address
+  d |= (uint64_t)1 << 16;                             // leading byte offset (ignored, 16 B)
+  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset
+  d |= (uint64_t)1 << 46;                             // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_c),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+struct TcProb {
+  float* out;
+  int n, ldo;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_gram_tc(const CUtensorMap* __restrict__ maps, const TcProb* __restrict__ probs, int k_total) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int prob = blockIdx.z;
+  const int tm = blockIdx.y, tn = blockIdx.x;
+  if (tm > tn) return;
+  const TcProb pr = probs[prob];
+  if (tm * BM >= pr.n || tn * BN >= pr.n) return;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool diag = (tm == tn);
+  const CUtensorMap* map_hi = maps + 2 * prob;
+  const CUtensorMap* map_lo = maps + 2 * prob + 1;
+  const int nkb = (k_total + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map_lo) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* st = smem + stage * STAGE_BYTES;
+        mbar_expect_tx(&full[stage], diag ? 2 * TILE_BYTES : 4 * TILE_BYTES);
+        tma_load_2d(st, map_hi, kb * BK, tm * BM, &full[stage]);
+        tma_load_2d(st + TILE_BYTES, map_lo, kb * BK, tm * BM, &full[stage]);
+        if (!diag) {
+          tma_load_2d(st + 2 * TILE_BYTES, map_hi, kb * BK, tn * BN, &full[stage]);
+          tma_load_2d(st + 3 * TILE_BYTES, map_lo, kb * BK, tn * BN, &full[stage]);
+        }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=tf32, both K-major, N=128, M=128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)(BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full[stage], phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+        const uint64_t a_hi = make_smem_desc(sa);
+        const uint64_t a_lo = make_smem_desc(sa + TILE_BYTES);
+        const uint64_t b_hi = diag ? a_hi : make_smem_desc(sa + 2 * TILE_BYTES);
+        const uint64_t b_lo = diag ? a_lo : make_smem_desc(sa + 3 * TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {
+          const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);   // 32 bytes per K=8 step
+          umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
+          umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
+          umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, 1u);
+        }
+        umma_commit(&empty[stage]);          // frees the smem stage when the MMAs retire
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tmem_full);                // accumulator complete
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue
+    mbar_wait(tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int quad = warp & 3;               // TMEM lane quadrant this warp may read
+    const int row = tm * BM + quad * 32 + lane;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+            "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+            "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
+            "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),
+            "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr)
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int col = tn * BN + c0 + j;
+        const float x = __uint_as_float(v[j]);
+        if (row < pr.n && col < pr.n) {
+          pr.out[(long long)row * pr.ldo + col] = x;
+          if (!diag) pr.out[(long long)col * pr.ldo + row] = x;
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// hi = x with the 13 low mantissa bits cleared (exactly representable in tf32), lo = x - hi
+__global__ void __launch_bounds__(256)
+k_split_tf32(const float* __restrict__ src, int ld_src, float* __restrict__ hi,
+             float* __restrict__ lo, int ld_dst, int nrows, int ncols) {
+  for (int r = blockIdx.y; r < nrows; r += gridDim.y) {
+    const float* s = src + (long long)r * ld_src;
+    float* h = hi + (long long)r * ld_dst;
+    float* l = lo + (long long)r * ld_dst;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncols; c += gridDim.x * blockDim.x) {
+      const float x = s[c];
+      const float xh = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+      h[c] = xh;
+      l[c] = x - xh;
+    }
+  }
+}
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                             const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                             CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                             CUtensorMapFloatOOBfill);
+
+EncodeFn get_encode() {
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeFn>(p);
+  }
+  return fn;
+}
+
+}  // namespace
+
+// Symmetric Gram of row-major fp32 matrices on the tensor cores.
+//   descs_host : HOST array of records (A == B, sym = 1, k % 4 == 0, lda % 4 == 0 required)
+//   split_ws   : device workspace, >= 2 * sum_p m_p * lda_p floats (hi / lo copies)
+//   map_ws     : device workspace, >= nprob * (2 * 128 + 16) bytes, 64-byte aligned
+//   stage_host : pinned host staging of the same size as map_ws
+extern "C" int cpsd_gram_nt_tc(const cpsd_gram_nt_desc* descs_host, int nprob, int m_max, int n_max,
+                               float* split_ws, long long split_ws_elems, void* map_ws,
+                               void* stage_host, cudaStream_t stream) {
+  CPSD_CHECK_ARG(nprob >= 0 && m_max > 0 && n_max == m_max, "gram_nt_tc: bad dims");
+  if (nprob == 0) return CPSD_OK;
+  CPSD_CHECK_ARG(nprob <= 65535, "gram_nt_tc: nprob > 65535");
+  EncodeFn enc = get_encode();
+  if (!enc) {
+    cpsd_set_error("gram_nt_tc: cuTensorMapEncodeTiled entry point unavailable");
+    return CPSD_ERR_CUDA;
+  }
+  CUtensorMap* maps_h = reinterpret_cast<CUtensorMap*>(stage_host);
+  TcProb* probs_h = reinterpret_cast<TcProb*>(reinterpret_cast<uint8_t*>(stage_host) +
+                                              (size_t)nprob * 2 * sizeof(CUtensorMap));
+  long long used = 0;
+  int k_total = descs_host[0].k;
+  for (int p = 0; p < nprob; ++p) {
+    const cpsd_gram_nt_desc& d = descs_host[p];
+    CPSD_CHECK_ARG(d.A == d.B && d.sym == 1 && d.m == d.n, "gram_nt_tc: symmetric problems only");
+    CPSD_CHECK_ARG((d.k & 3) == 0 && (d.lda & 3) == 0 && d.k == k_total,
+                   "gram_nt_tc: k and lda must be multiples of 4 and k uniform over the batch");
+    CPSD_CHECK_ARG(d.alpha == 1.0f, "gram_nt_tc: alpha must be 1");
+    const long long elems = (long long)d.m * d.lda;
+    CPSD_CHECK_ARG(used + 2 * elems <= split_ws_elems, "gram_nt_tc: split workspace too small");
+    float* hi = split_ws + used;
+    float* lo = hi + elems;
+    used += 2 * elems;
+    int bx = (d.k + 255) / 256;
+    if (bx > 8) bx = 8;
+    k_split_tf32<<<dim3(bx, d.m < 512 ? d.m : 512), 256, 0, stream>>>(d.A, d.lda, hi, lo, d.lda, d.m,
+                                                                      d.k);
+    CPSD_LAUNCH_CHECK();
+    const cuuint64_t gdim[2] = {(cuuint64_t)d.k, (cuuint64_t)d.m};
+    const cuuint64_t gstr[1] = {(cuuint64_t)d.lda * 4};
+    const cuuint32_t box[2] = {BK, BM};
+    const cuuint32_t estr[2] = {1, 1};
+    float* srcs[2] = {hi, lo};
+    for (int u = 0; u < 2; ++u) {
+      CUresult r = enc(&maps_h[2 * p + u], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, srcs[u], gdim, gstr,
+                       box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        cpsd_set_error("gram_nt_tc: cuTensorMapEncodeTiled failed");
+        return CPSD_ERR_CUDA;
+      }
+    }
+    probs_h[p].out = d.out;
+    probs_h[p].n = d.m;
+    probs_h[p].ldo = d.ldo;
+  }
+  const size_t bytes = (size_t)nprob * (2 * sizeof(CUtensorMap) + sizeof(TcProb));
+  CPSD_CUDA(cudaMemcpyAsync(map_ws, stage_host, bytes, cudaMemcpyHostToDevice, stream));
+  const CUtensorMap* maps_d = reinterpret_cast<const CUtensorMap*>(map_ws);
+  const TcProb* probs_d = reinterpret_cast<const TcProb*>(reinterpret_cast<uint8_t*>(map_ws) +
+                                                          (size_t)nprob * 2 * sizeof(CUtensorMap));
+  const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024 + 128;
+  CPSD_CUDA(cudaFuncSetAttribute(k_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int tiles = (m_max + BM - 1) / BM;
+  k_gram_tc<<<dim3(tiles, tiles, nprob), TC_THREADS, smem, stream>>>(maps_d, probs_d, k_total);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
+
+// bytes of map_ws / stage_host needed for nprob problems
+extern "C" int cpsd_gram_nt_tc_ws_bytes(int nprob) {
+  return nprob * (int)(2 * sizeof(CUtensorMap) + sizeof(TcProb)) + 64;
 }

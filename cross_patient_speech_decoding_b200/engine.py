@@ -318,7 +318,21 @@ class CVEngine:
                      1.0 / n_pool[f], 0)
             r2[f] = (addr(Zall, f * n_pad * F), addr(Zall, f * n_pad * F),
                      addr(Kall, f * n_pad * n_pad), n_all[f], n_all[f], F, F, F, n_pad, 1, 1.0)
+        self._r2_host = r2
         return r1, r2, mu, Kall
+
+    def gram_tc(self, recs_host, nprob, nmax, elems_per_prob):
+        """Tensor-core pooled Gram (tcgen05): needs the descriptor records on the host."""
+        ctx = self.ctx
+        nbytes = int(ctx.lib.cpsd_gram_nt_tc_ws_bytes(nprob))
+        split = self.ws('tc_split', (2 * nprob * elems_per_prob,))
+        maps = self.ws('tc_maps', (nbytes + 64,), torch.uint8)
+        if getattr(self, '_tc_stage', None) is None or self._tc_stage.numel() < nbytes:
+            self._tc_stage = torch.empty((nbytes + 64,), dtype=torch.uint8).pin_memory()
+        recs = np.ascontiguousarray(recs_host)
+        a = (maps.data_ptr() + 63) & ~63
+        ctx.call('cpsd_gram_nt_tc', ctypes.c_void_p(recs.ctypes.data), nprob, nmax, nmax, ptr(split),
+                 split.numel(), ctypes.c_void_p(a), ctypes.c_void_p(self._tc_stage.data_ptr()))
 
     def _pooled_stage_run(self, pk, d1, d2, B, Zall, mu, Kall, n_pad, F, n_pool, n_te, o_npool,
                           o_nall, o_ypool, n_te_max, want_details):
@@ -331,7 +345,7 @@ class CVEngine:
                  max(a + b for a, b in zip(n_pool, n_te)), F, B)
         nmax = max(a + b for a, b in zip(n_pool, n_te))
         if self.use_tc:
-            ctx.call('cpsd_gram_nt_tc', pk.daddr(d2), B, nmax, nmax)
+            self.gram_tc(self._r2_host, B, nmax, n_pad * F)
         else:
             ctx.call('cpsd_gram_nt', pk.daddr(d2), B, nmax, nmax)
         Kte = self.ws('pool_Kte', (B, n_te_max, n_pad))

@@ -151,7 +151,17 @@ def gram_nt(A, B=None, alpha=1.0, device=None, tensor_cores=False):
     pk.reserve_ints()
     d = pk.add_descs(rec)
     pk.upload()
-    ctx.call('cpsd_gram_nt_tc' if tensor_cores else 'cpsd_gram_nt', pk.daddr(d), 1, m, n)
+    if tensor_cores:
+        nbytes = int(ctx.lib.cpsd_gram_nt_tc_ws_bytes(1))
+        split = ctx.empty((2 * m * k,))
+        maps = ctx.empty((nbytes + 64,), torch.uint8)
+        stage = torch.empty((nbytes + 64,), dtype=torch.uint8).pin_memory()
+        a = (maps.data_ptr() + 63) & ~63
+        ctx.call('cpsd_gram_nt_tc', ctypes.c_void_p(rec.ctypes.data), 1, m, n, ptr(split),
+                 split.numel(), ctypes.c_void_p(a), ctypes.c_void_p(stage.data_ptr()))
+        torch.cuda.synchronize()
+    else:
+        ctx.call('cpsd_gram_nt', pk.daddr(d), 1, m, n)
     return out.cpu().numpy()
 
 

@@ -72,9 +72,15 @@ int cpsd_proj_nn(const cpsd_proj_desc* descs, int nprob, int nseg_max, int seg_l
  * (decomposition/DimRedReshape.py:47-49 -> sklearn PCA full SVD). */
 int cpsd_gram_nt(const cpsd_gram_nt_desc* descs, int nprob, int m_max, int n_max,
                  cudaStream_t stream);
-/* same contract, tcgen05 / TMEM tensor-core path (3xTF32 split, fp32 accumulate) */
-int cpsd_gram_nt_tc(const cpsd_gram_nt_desc* descs, int nprob, int m_max, int n_max,
+/* same product on the tensor cores: TMA -> 128B-swizzled smem -> tcgen05.mma.kind::tf32 with
+ * the accumulator in TMEM, 3xTF32 split (hi*hi + hi*lo + lo*hi), symmetric problems only.
+ * descs_host is a HOST array (tensor maps are encoded on the host); split_ws holds the
+ * hi/lo copies (2 * sum m*lda floats), map_ws / stage_host (pinned) hold the tensor maps,
+ * both cpsd_gram_nt_tc_ws_bytes(nprob) bytes. */
+int cpsd_gram_nt_tc(const cpsd_gram_nt_desc* descs_host, int nprob, int m_max, int n_max,
+                    float* split_ws, long long split_ws_elems, void* map_ws, void* stage_host,
                     cudaStream_t stream);
+int cpsd_gram_nt_tc_ws_bytes(int nprob);
 
 /* ---- small solvers ---------------------------------------------------------------
  * symmetric eigen-decomposition, n <= 128, one CTA per problem, shared-memory Jacobi

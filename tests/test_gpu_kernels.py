@@ -237,3 +237,18 @@ def test_svm_edge_cases(ops):
     # k = 0 features: bias only
     cls, W, info = ops.svm_fit_ovr(np.zeros((10, 0)), np.array([0, 1] * 5))
     assert W.shape == (2, 1) and np.isfinite(W).all()
+
+
+@pytest.mark.parametrize('shape', [(128, 64), (259, 2600), (700, 1000), (1152, 6000)])
+def test_gram_nt_tensor_core(ops, shape):
+    """tcgen05 3xTF32 Gram against float64, and against the fp32 SIMT kernel."""
+    m, k = shape
+    rng = np.random.default_rng(m + k)
+    A = rng.standard_normal((m, k)) * (1 + 5 * rng.random((m, 1)))
+    K = ops.gram_nt(A, tensor_cores=True)
+    ref = A @ A.T
+    assert np.array_equal(K, K.T)
+    err = np.abs(K - ref).max() / np.abs(ref).max()
+    assert err <= 2e-6, err
+    Ks = ops.gram_nt(A)
+    assert np.abs(K - Ks).max() / np.abs(ref).max() <= 1e-5
