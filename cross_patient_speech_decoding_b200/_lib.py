@@ -63,11 +63,14 @@ _SIGS = {
     'cpsd_desc_sizes': [_P],
     'cpsd_eig_sym_small': [_P, c_int, c_ll, _P, c_int, c_int, _P, c_int, _P, c_int, c_ll, c_int,
                            c_float, _P, _P],
+    'cpsd_eig_sym_small_f64': [_P, c_int, c_ll, _P, c_int, c_int, _P, c_int, _P, c_int, c_ll, c_int,
+                               c_float, _P, _P],
     'cpsd_bj_schedule': [c_int, _P],
     'cpsd_eig_sym_block': [_P, _P, c_int, c_ll, c_int, _P, c_int, c_int, _P, _P, _P, _P, _P, _P,
                            c_int, c_int, c_float, _P],
     'cpsd_select_k': [_P, c_int, _P, c_int, c_float, c_int, c_int, c_int, _P, c_int, c_int, _P],
     'cpsd_gram_tn': [_P, c_int, c_int, c_int, _P],
+    'cpsd_gram_tn_f64': [_P, c_int, c_int, c_int, _P],
     'cpsd_colsum': [_P, c_int, c_int, _P],
     'cpsd_proj_nn': [_P, c_int, c_int, c_int, c_int, _P],
     'cpsd_gram_nt': [_P, c_int, c_int, c_int, _P],
@@ -88,7 +91,7 @@ _SIGS = {
     'cpsd_svm_predict_ovr': [_P, c_int, c_ll, _P, c_int, c_ll, _P, c_int, _P, c_int, _P, c_int, _P,
                              _P, c_int, _P],
     'cpsd_cca_solve': [_P, c_int, c_int, _P],
-    'cpsd_pca_basis': [_P, c_int, c_ll, _P, c_int, _P, _P, c_int, c_int, _P, c_int, c_int, _P],
+    'cpsd_pca_basis': [_P, c_int, c_ll, _P, _P, c_int, c_int, _P, c_int, c_int, c_int, _P],
     'cpsd_gram_nt_tc': [_P, c_int, c_int, c_int, _P, c_ll, _P, _P, _P],
     'cpsd_gram_nt_tc_ws_bytes': [c_int],
 }

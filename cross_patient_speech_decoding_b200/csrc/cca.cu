@@ -116,9 +116,11 @@ __device__ int svd_onesided(float* W, float* V, int m, int n, int ld, int* flag)
         al = warp_sum(al); be = warp_sum(be); ga = warp_sum(ga);
         if (fabsf(ga) > 1e-7f * sqrtf(al * be) && fabsf(ga) > 1e-37f) {
           if (fabsf(ga) > 3e-7f * sqrtf(al * be) && lane == 0) *flag = 1;
-          const float zeta = (be - al) / (2.f * ga);
-          const float t = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(1.f + zeta * zeta));
-          const float c = rsqrtf(1.f + t * t), sn = t * c;
+          // fp64 evaluation, rounded once: keeps c^2 + s^2 = 1 unbiased (see jacobi.cu)
+          const double zeta = ((double)be - (double)al) / (2.0 * (double)ga);
+          const double td = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double cd = 1.0 / sqrt(1.0 + td * td);
+          const float c = (float)cd, sn = (float)(td * cd);
           for (int r = lane; r < m; r += 32) {
             const float x = W[r * ld + p], y = W[r * ld + q];
             W[r * ld + p] = c * x - sn * y;

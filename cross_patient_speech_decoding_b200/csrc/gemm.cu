@@ -21,20 +21,21 @@ namespace {
 // ------------------------------------------------------------------------------ gram_tn
 #define GT_TILE 64
 #define GT_RK 16
+template <typename AccT>
 __global__ void __launch_bounds__(256)
 k_gram_tn(const cpsd_gram_tn_desc* __restrict__ descs) {
   const cpsd_gram_tn_desc d = descs[blockIdx.z];
   const int i0 = blockIdx.y * GT_TILE, j0 = blockIdx.x * GT_TILE;
   if (i0 >= d.p || j0 >= d.q) return;
-  if (d.sym && blockIdx.y > blockIdx.x) return;
+  if ((d.sym & 1) && blockIdx.y > blockIdx.x) return;
   __shared__ __align__(16) float As[GT_RK][GT_TILE];
   __shared__ __align__(16) float Bs[GT_RK][GT_TILE];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  float acc[4][4];
+  AccT acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[i][j] = (AccT)0;
 
   // this thread's load slots: 4 elements of each operand per chunk
   const int lc = threadIdx.x & 63;   // column inside tile
@@ -62,16 +63,17 @@ k_gram_tn(const cpsd_gram_tn_desc* __restrict__ descs) {
       for (int kk = 0; kk < GT_RK; ++kk) {
         const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
         const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-        const float a[4] = {a4.x, a4.y, a4.z, a4.w};
-        const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+        const AccT a[4] = {(AccT)a4.x, (AccT)a4.y, (AccT)a4.z, (AccT)a4.w};
+        const AccT b[4] = {(AccT)b4.x, (AccT)b4.y, (AccT)b4.z, (AccT)b4.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+          for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
       }
       __syncthreads();
     }
   }
+  AccT* out = reinterpret_cast<AccT*>(d.out);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int gi = i0 + ty * 4 + i;
@@ -80,9 +82,9 @@ k_gram_tn(const cpsd_gram_tn_desc* __restrict__ descs) {
     for (int j = 0; j < 4; ++j) {
       const int gj = j0 + tx * 4 + j;
       if (gj >= d.q) continue;
-      const float v = d.alpha * acc[i][j];
-      d.out[(long long)gi * d.ldo + gj] = v;
-      if (d.sym && blockIdx.y != blockIdx.x) d.out[(long long)gj * d.ldo + gi] = v;
+      const AccT v = (AccT)d.alpha * acc[i][j];
+      out[(long long)gi * d.ldo + gj] = v;
+      if ((d.sym & 1) && blockIdx.y != blockIdx.x) out[(long long)gj * d.ldo + gi] = v;
     }
   }
 }
@@ -277,7 +279,21 @@ extern "C" int cpsd_gram_tn(const cpsd_gram_tn_desc* descs_dev, int nprob, int p
   if (nprob == 0) return CPSD_OK;
   CPSD_CHECK_ARG(nprob <= 65535, "gram_tn: nprob > 65535");
   dim3 grid((q_max + GT_TILE - 1) / GT_TILE, (p_max + GT_TILE - 1) / GT_TILE, nprob);
-  k_gram_tn<<<grid, 256, 0, stream>>>(descs_dev);
+  k_gram_tn<float><<<grid, 256, 0, stream>>>(descs_dev);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
+
+// Same contract with fp64 accumulation; every record's `out` points to DOUBLES (row stride
+// ldo in doubles).  Used for the scatter matrices that feed variance thresholds and the
+// eigen-solvers (noise-level PCA directions are gap-sensitive).
+extern "C" int cpsd_gram_tn_f64(const cpsd_gram_tn_desc* descs_dev, int nprob, int p_max,
+                                int q_max, cudaStream_t stream) {
+  CPSD_CHECK_ARG(nprob >= 0 && p_max > 0 && q_max > 0, "gram_tn_f64: bad dims");
+  if (nprob == 0) return CPSD_OK;
+  CPSD_CHECK_ARG(nprob <= 65535, "gram_tn_f64: nprob > 65535");
+  dim3 grid((q_max + GT_TILE - 1) / GT_TILE, (p_max + GT_TILE - 1) / GT_TILE, nprob);
+  k_gram_tn<double><<<grid, 256, 0, stream>>>(descs_dev);
   CPSD_LAUNCH_CHECK();
   return CPSD_OK;
 }

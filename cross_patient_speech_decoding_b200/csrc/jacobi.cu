@@ -25,9 +25,9 @@ namespace {
 struct StepBuf {
   int pi[TS / 2];
   int pj[TS / 2];
-  float c[TS / 2];
-  float s[TS / 2];
-  float d[TS / 2];   // t * a_pq (diagonal update)
+  double c[TS / 2];
+  double s[TS / 2];
+  double d[TS / 2];   // t * a_pq (diagonal update)
 };
 
 // pair (i, j) of slot k at step s, modulus ordering over m (even) indices:
@@ -41,25 +41,30 @@ __device__ __forceinline__ void mod_pair(int s, int k, int m, int& i, int& j) {
   if (j < 0) j += m;
 }
 
-// One Jacobi step on the tile held in shared memory.
-//   As : m x m symmetric (row stride TS), Vs : vrows x m (row stride TS)
-//   npairs pairs (sb->pi[k], sb->pj[k]) must already be stored by the caller.
+// Rotation parameters of every pair of the step.  They are always evaluated in fp64 and
+// rounded once: fp32 evaluation of c = 1/sqrt(1+t^2), s = t c has a systematic bias in
+// c^2 + s^2 (+5e-8 per rotation, measured) that accumulates over ~1e4 rotations per column
+// into 1e-4 norm drift of the eigenvectors.
+//   As : m x m symmetric (row stride TS), npairs pairs stored in sb by the caller; only the
+//   first nrot slots rotate (the rest carry idle indices with an identity).
 // Returns (per calling thread) the largest |a_pq| it looked at.
-__device__ __forceinline__ float tile_rotations(float* As, StepBuf* sb, int npairs, int nrot,
+template <typename T>
+__device__ __forceinline__ float tile_rotations(T* As, StepBuf* sb, int npairs, int nrot,
                                                 float skip_thr) {
   float seen = 0.f;
   const int k = threadIdx.x;
   if (k < npairs) {
     const int i = sb->pi[k], j = sb->pj[k];
-    const float app = As[i * TS + i], aqq = As[j * TS + j], apq = As[i * TS + j];
-    float c = 1.f, s = 0.f, d = 0.f;
-    const float aa = (k < nrot) ? fabsf(apq) : 0.f;   // slots >= nrot only carry idle indices
+    const double app = (double)As[i * TS + i], aqq = (double)As[j * TS + j];
+    const double apq = (double)As[i * TS + j];
+    double c = 1.0, s = 0.0, d = 0.0;
+    const float aa = (k < nrot) ? fabsf((float)apq) : 0.f;
     seen = aa;
     if (aa > skip_thr) {
-      const float tau = (aqq - app) / (2.f * apq);
-      const float t = copysignf(1.f, tau) / (fabsf(tau) + sqrtf(1.f + tau * tau));
-      if (t == t && fabsf(t) <= 1.f) {  // guards inf/nan
-        c = rsqrtf(1.f + t * t);
+      const double tau = (aqq - app) / (2.0 * apq);
+      const double t = copysign(1.0, tau) / (fabs(tau) + sqrt(1.0 + tau * tau));
+      if (t == t && fabs(t) <= 1.0) {  // guards inf/nan
+        c = 1.0 / sqrt(1.0 + t * t);
         s = t * c;
         d = t * apq;
       }
@@ -71,31 +76,31 @@ __device__ __forceinline__ float tile_rotations(float* As, StepBuf* sb, int npai
   return seen;
 }
 
-__device__ __forceinline__ void tile_apply(float* As, float* Vs, StepBuf* sb, int npairs,
-                                           int vrows) {
+template <typename T>
+__device__ __forceinline__ void tile_apply(T* As, float* Vs, StepBuf* sb, int npairs, int vrows) {
   const int nblk = npairs * npairs;
   for (int b = threadIdx.x; b < nblk; b += NT) {
     const int k = b / npairs, l = b - k * npairs;
     const int ik = sb->pi[k], jk = sb->pj[k];
-    const float ck = sb->c[k], sk = sb->s[k];
+    const T ck = (T)sb->c[k], sk = (T)sb->s[k];
     if (k == l) {
-      if (sk != 0.f) {
-        const float d = sb->d[k];
+      if (sk != (T)0) {
+        const T d = (T)sb->d[k];
         As[ik * TS + ik] -= d;
         As[jk * TS + jk] += d;
-        As[ik * TS + jk] = 0.f;
-        As[jk * TS + ik] = 0.f;
+        As[ik * TS + jk] = (T)0;
+        As[jk * TS + ik] = (T)0;
       }
       continue;
     }
     const int il = sb->pi[l], jl = sb->pj[l];
-    const float cl = sb->c[l], sl = sb->s[l];
-    if (sk == 0.f && sl == 0.f) continue;
-    const float app = As[ik * TS + il], apq = As[ik * TS + jl];
-    const float aqp = As[jk * TS + il], aqq = As[jk * TS + jl];
+    const T cl = (T)sb->c[l], sl = (T)sb->s[l];
+    if (sk == (T)0 && sl == (T)0) continue;
+    const T app = As[ik * TS + il], apq = As[ik * TS + jl];
+    const T aqp = As[jk * TS + il], aqq = As[jk * TS + jl];
     // columns (il, jl) rotated by (cl, sl)
-    const float tpp = cl * app - sl * apq, tpq = sl * app + cl * apq;
-    const float tqp = cl * aqp - sl * aqq, tqq = sl * aqp + cl * aqq;
+    const T tpp = cl * app - sl * apq, tpq = sl * app + cl * apq;
+    const T tqp = cl * aqp - sl * aqq, tqq = sl * aqp + cl * aqq;
     // rows (ik, jk) rotated by (ck, sk)
     As[ik * TS + il] = ck * tpp - sk * tqp;
     As[jk * TS + il] = sk * tpp + ck * tqp;
@@ -105,7 +110,7 @@ __device__ __forceinline__ void tile_apply(float* As, float* Vs, StepBuf* sb, in
   const int nv = vrows * npairs;
   for (int b = threadIdx.x; b < nv; b += NT) {
     const int r = b / npairs, l = b - r * npairs;
-    const float cl = sb->c[l], sl = sb->s[l];
+    const float cl = (float)sb->c[l], sl = (float)sb->s[l];
     if (sl == 0.f) continue;
     const int il = sb->pi[l], jl = sb->pj[l];
     const float vp = Vs[r * TS + il], vq = Vs[r * TS + jl];
@@ -116,8 +121,9 @@ __device__ __forceinline__ void tile_apply(float* As, float* Vs, StepBuf* sb, in
 
 // Full sweep (all m(m-1)/2 pairs, modulus ordering).  Returns block-wide max |a_pq| seen
 // (valid in all threads).  `redmax` is one shared int.
-__device__ float tile_sweep_full(float* As, float* Vs, StepBuf* sb, int m, int vrows,
-                                 float skip_thr, int* redmax) {
+template <typename T>
+__device__ float tile_sweep_full(T* As, float* Vs, StepBuf* sb, int m, int vrows, float skip_thr,
+                                 int* redmax) {
   float seen = 0.f;
   const int npairs = m >> 1;
   for (int s = 0; s < m; ++s) {
@@ -136,9 +142,9 @@ __device__ float tile_sweep_full(float* As, float* Vs, StepBuf* sb, int m, int v
       sb->pj[threadIdx.x] = j;
     }
     __syncthreads();
-    seen = fmaxf(seen, tile_rotations(As, sb, npairs, nrot, skip_thr));
+    seen = fmaxf(seen, tile_rotations<T>(As, sb, npairs, nrot, skip_thr));
     __syncthreads();
-    tile_apply(As, Vs, sb, npairs, vrows);
+    tile_apply<T>(As, Vs, sb, npairs, vrows);
     __syncthreads();
   }
   if (threadIdx.x == 0) *redmax = 0;
@@ -159,9 +165,9 @@ __device__ float tile_sweep_cross(float* As, float* Vs, StepBuf* sb, float skip_
       sb->pj[threadIdx.x] = BS + ((threadIdx.x + s) & (BS - 1));
     }
     __syncthreads();
-    seen = fmaxf(seen, tile_rotations(As, sb, BS, BS, skip_thr));
+    seen = fmaxf(seen, tile_rotations<float>(As, sb, BS, BS, skip_thr));
     __syncthreads();
-    tile_apply(As, Vs, sb, BS, TS);
+    tile_apply<float>(As, Vs, sb, BS, TS);
     __syncthreads();
   }
   if (threadIdx.x == 0) *redmax = 0;
@@ -172,11 +178,12 @@ __device__ float tile_sweep_cross(float* As, float* Vs, StepBuf* sb, float skip_
   return __int_as_float(*redmax);
 }
 
-__device__ float tile_diag_absmax(const float* As, int m, int* redmax) {
+template <typename T>
+__device__ float tile_diag_absmax(const T* As, int m, int* redmax) {
   if (threadIdx.x == 0) *redmax = 0;
   __syncthreads();
   float v = 0.f;
-  for (int i = threadIdx.x; i < m; i += NT) v = fmaxf(v, fabsf(As[i * TS + i]));
+  for (int i = threadIdx.x; i < m; i += NT) v = fmaxf(v, fabsf((float)As[i * TS + i]));
   v = warp_max(v);
   if ((threadIdx.x & 31) == 0) atomicMax(redmax, __float_as_int(v));
   __syncthreads();
@@ -186,15 +193,19 @@ __device__ float tile_diag_absmax(const float* As, int m, int* redmax) {
 }
 
 // ---------------------------------------------------------------------------------------
-// n <= 128 eigen-decomposition, one CTA per problem.
+// n <= 128 eigen-decomposition, one CTA per problem.  T = float: everything fp32.
+// T = double: the matrix iterates in fp64 (so rotation angles are accurate independently of
+// eigenvalue gaps) while the eigenvectors accumulate in fp32 -- their rounding noise is a
+// gap-independent ~1e-6 perturbation of the basis.
 // ---------------------------------------------------------------------------------------
+template <typename T>
 __global__ void __launch_bounds__(NT)
-k_eig_tile(const float* __restrict__ A, int lda, long long strideA, const int* __restrict__ n_dev,
+k_eig_tile(const T* __restrict__ A, int lda, long long strideA, const int* __restrict__ n_dev,
            int n_fixed, float* __restrict__ evals, int ld_e, float* __restrict__ evecs, int ldv,
            long long strideV, int max_sweeps, float tol, int* __restrict__ sweeps_out) {
-  extern __shared__ float smem[];
-  float* As = smem;
-  float* Vs = smem + TS * TS;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* As = reinterpret_cast<T*>(smem_raw);
+  float* Vs = reinterpret_cast<float*>(As + TS * TS);
   StepBuf* sb = reinterpret_cast<StepBuf*>(Vs + TS * TS);
   int* redmax = reinterpret_cast<int*>(sb + 1);
   int* rank = redmax + 1;  // TS ints
@@ -204,11 +215,11 @@ k_eig_tile(const float* __restrict__ A, int lda, long long strideA, const int* _
   if (n > TS) n = TS;
   if (n < 0) n = 0;
   const int m = (n + 1) & ~1;
-  const float* Ag = A + (long long)prob * strideA;
+  const T* Ag = A + (long long)prob * strideA;
 
   for (int e = threadIdx.x; e < TS * TS; e += NT) {
     const int r = e >> 7, c = e & (TS - 1);
-    float v = 0.f;
+    T v = (T)0;
     if (r < n && c < n) v = Ag[(long long)r * lda + c];
     As[e] = v;
     Vs[e] = (r == c) ? 1.f : 0.f;
@@ -218,7 +229,7 @@ k_eig_tile(const float* __restrict__ A, int lda, long long strideA, const int* _
   for (int e = threadIdx.x; e < TS * TS; e += NT) {
     const int r = e >> 7, c = e & (TS - 1);
     if (r < c) {
-      const float v = 0.5f * (As[r * TS + c] + As[c * TS + r]);
+      const T v = (T)0.5 * (As[r * TS + c] + As[c * TS + r]);
       As[r * TS + c] = v;
       As[c * TS + r] = v;
     }
@@ -228,8 +239,9 @@ k_eig_tile(const float* __restrict__ A, int lda, long long strideA, const int* _
   int sw = 0;
   if (m >= 2) {
     for (; sw < max_sweeps; ++sw) {
-      const float dmax = tile_diag_absmax(As, m, redmax);
-      const float off = tile_sweep_full(As, Vs, sb, m, m, 1e-9f * dmax + 1e-37f, redmax);
+      const float dmax = tile_diag_absmax<T>(As, m, redmax);
+      const float skip = (sizeof(T) == 8 ? 1e-15f : 1e-9f) * dmax + 1e-37f;
+      const float off = tile_sweep_full<T>(As, Vs, sb, m, m, skip, redmax);
       if (off <= tol * dmax) { ++sw; break; }
     }
   }
@@ -237,10 +249,10 @@ k_eig_tile(const float* __restrict__ A, int lda, long long strideA, const int* _
 
   // sort descending by counting
   for (int i = threadIdx.x; i < n; i += NT) {
-    const float li = As[i * TS + i];
+    const T li = As[i * TS + i];
     int r = 0;
     for (int j = 0; j < n; ++j) {
-      const float lj = As[j * TS + j];
+      const T lj = As[j * TS + j];
       r += (lj > li) || (lj == li && j < i);
     }
     rank[i] = r;
@@ -250,7 +262,7 @@ k_eig_tile(const float* __restrict__ A, int lda, long long strideA, const int* _
   for (int i = threadIdx.x; i < ld_e; i += NT) {
     if (i >= n) ev[i] = 0.f;
   }
-  for (int i = threadIdx.x; i < n; i += NT) ev[rank[i]] = As[i * TS + i];
+  for (int i = threadIdx.x; i < n; i += NT) ev[rank[i]] = (float)As[i * TS + i];
   if (evecs) {
     float* Vg = evecs + (long long)prob * strideV;
     for (int e = threadIdx.x; e < n * n; e += NT) {
@@ -292,7 +304,7 @@ k_bj_inner(float* __restrict__ K, int ldk, long long strideK, const int* __restr
   const float skip = 1e-9f * sc + 1e-37f;
   float off;
   if (full_mode)
-    off = tile_sweep_full(As, Vs, sb, TS, TS, skip, redmax);
+    off = tile_sweep_full<float>(As, Vs, sb, TS, TS, skip, redmax);
   else
     off = tile_sweep_cross(As, Vs, sb, skip, redmax);
   if (threadIdx.x == 0 && sc > 0.f)
@@ -552,8 +564,8 @@ __global__ void k_select_k(const float* __restrict__ evals, int ld_e, const int*
 // =======================================================================================
 // C ABI
 // =======================================================================================
-static size_t tile_smem_bytes() {
-  return 2 * TS * TS * sizeof(float) + sizeof(StepBuf) + (1 + TS) * sizeof(int) + 16;
+static size_t tile_smem_bytes(size_t elem = sizeof(float)) {
+  return TS * TS * (elem + sizeof(float)) + sizeof(StepBuf) + (1 + TS) * sizeof(int) + 16;
 }
 
 extern "C" int cpsd_eig_sym_small(const float* A, int lda, long long strideA, const int* n_dev,
@@ -564,9 +576,27 @@ extern "C" int cpsd_eig_sym_small(const float* A, int lda, long long strideA, co
   CPSD_CHECK_ARG(n_fixed <= TS, "eig_sym_small: n > 128 (use cpsd_eig_sym_block)");
   if (nprob == 0) return CPSD_OK;
   const size_t smem = tile_smem_bytes();
-  CPSD_CUDA(cudaFuncSetAttribute(k_eig_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_eig_tile<<<nprob, NT, smem, stream>>>(A, lda, strideA, n_dev, n_fixed, evals, ld_e, evecs, ldv,
-                                          strideV, max_sweeps, tol, sweeps_out);
+  CPSD_CUDA(cudaFuncSetAttribute(k_eig_tile<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+  k_eig_tile<float><<<nprob, NT, smem, stream>>>(A, lda, strideA, n_dev, n_fixed, evals, ld_e, evecs,
+                                                 ldv, strideV, max_sweeps, tol, sweeps_out);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
+
+// fp64 matrix / fp32 eigenvectors variant (A holds doubles, lda / strideA in doubles)
+extern "C" int cpsd_eig_sym_small_f64(const double* A, int lda, long long strideA, const int* n_dev,
+                                      int n_fixed, int nprob, float* evals, int ld_e, float* evecs,
+                                      int ldv, long long strideV, int max_sweeps, float tol,
+                                      int* sweeps_out, cudaStream_t stream) {
+  CPSD_CHECK_ARG(nprob >= 0 && lda >= 0 && ld_e >= 0, "eig_sym_small_f64: bad dims");
+  CPSD_CHECK_ARG(n_fixed <= TS, "eig_sym_small_f64: n > 128");
+  if (nprob == 0) return CPSD_OK;
+  const size_t smem = tile_smem_bytes(sizeof(double));
+  CPSD_CUDA(cudaFuncSetAttribute(k_eig_tile<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+  k_eig_tile<double><<<nprob, NT, smem, stream>>>(A, lda, strideA, n_dev, n_fixed, evals, ld_e,
+                                                  evecs, ldv, strideV, max_sweeps, tol, sweeps_out);
   CPSD_LAUNCH_CHECK();
   return CPSD_OK;
 }
@@ -630,7 +660,7 @@ extern "C" int cpsd_eig_sym_block(float* K, float* V, int ld, long long stride, 
           K, V, ld, stride, n_pad, pr, npairs, Rbuf, done);
       CPSD_LAUNCH_CHECK();
     }
-    k_bj_check<<<(nprob + 127) / 128, 128, 0, stream>>>(conv, done, sweeps, tol, nprob);
+    k_bj_check<<<(nprob + 127) / 128, 128, 0, stream>>>(conv, done, sweeps, fmaxf(tol, 2e-6f), nprob);
     CPSD_LAUNCH_CHECK();
   }
   k_bj_extract<<<nprob, NT, n_pad * sizeof(float), stream>>>(K, ld, stride, n_dev, n_fixed, evals,

@@ -16,8 +16,8 @@
 //              of {A_hi, A_lo, B_hi, B_lo}, 128 rows x 32 fp32 each)
 //   warp 1   : TMEM allocator + single-thread tcgen05.mma.kind::tf32 issuer (M=128, N=128,
 //              K=8), tcgen05.commit releases smem stages / signals the epilogue
-//   warps 2-5: epilogue  tcgen05.ld (32 lanes x 32 columns per warp) -> registers ->
-//              global, plus the mirrored tile (the transposed store is the coalesced one)
+//   warps 2-5: epilogue  tcgen05.ld (32 lanes x 32 columns per warp) of each partial
+//              accumulator -> fp32 register accumulators -> global, plus the mirrored tile
 #include "common.cuh"
 #include "descs.h"
 #include <cuda.h>
@@ -29,7 +29,7 @@ constexpr int STAGES = 3;
 constexpr int TILE_BYTES = BM * BK * 4;          // 16 KB
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;      // A_hi, A_lo, B_hi, B_lo
 constexpr int TC_THREADS = 192;
-constexpr uint32_t TMEM_COLS = 128;
+constexpr uint32_t TMEM_COLS = 256;          // two 128-column accumulator stages
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -96,6 +96,17 @@ struct TcProb {
   int n, ldo;
 };
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// The tensor core's fp32 accumulator truncates on every accumulate (measured: relative error
+// growing linearly with K, 1e-4 at K=6000).  So TMEM only accumulates CHUNK k-blocks
+// (48 MMAs); the epilogue warps drain each partial tile into round-to-nearest fp32 register
+// accumulators while the MMA warp fills the other TMEM stage.
+constexpr int CHUNK = 4;
+constexpr int ACC_STAGES = 2;
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gram_tc(const CUtensorMap* __restrict__ maps, const TcProb* __restrict__ probs, int k_total) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -109,14 +120,16 @@ k_gram_tc(const CUtensorMap* __restrict__ maps, const TcProb* __restrict__ probs
                                              ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty = full + STAGES;
-  uint64_t* tmem_full = empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_full = empty + STAGES;            // [ACC_STAGES]
+  uint64_t* tmem_empty = tmem_full + ACC_STAGES;   // [ACC_STAGES]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool diag = (tm == tn);
   const CUtensorMap* map_hi = maps + 2 * prob;
   const CUtensorMap* map_lo = maps + 2 * prob + 1;
   const int nkb = (k_total + BK - 1) / BK;
+  const int nchunk = (nkb + CHUNK - 1) / CHUNK;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map_hi) : "memory");
@@ -125,7 +138,10 @@ k_gram_tc(const CUtensorMap* __restrict__ maps, const TcProb* __restrict__ probs
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(tmem_full, 1);
+    for (int s = 0; s < ACC_STAGES; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);              // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -166,60 +182,83 @@ k_gram_tc(const CUtensorMap* __restrict__ maps, const TcProb* __restrict__ probs
                              ((uint32_t)(BM >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(&full[stage], phase);
+      for (int c = 0; c < nchunk; ++c) {
+        const int as = c & 1;
+        const uint32_t aphase = (uint32_t)(c >> 1) & 1u;
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-        const uint64_t a_hi = make_smem_desc(sa);
-        const uint64_t a_lo = make_smem_desc(sa + TILE_BYTES);
-        const uint64_t b_hi = diag ? a_hi : make_smem_desc(sa + 2 * TILE_BYTES);
-        const uint64_t b_lo = diag ? a_lo : make_smem_desc(sa + 3 * TILE_BYTES);
+        const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
+        const int kb_end = min(nkb, (c + 1) * CHUNK);
+        for (int kb = c * CHUNK; kb < kb_end; ++kb) {
+          mbar_wait(&full[stage], phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t a_hi = make_smem_desc(sa);
+          const uint64_t a_lo = make_smem_desc(sa + TILE_BYTES);
+          const uint64_t b_hi = diag ? a_hi : make_smem_desc(sa + 2 * TILE_BYTES);
+          const uint64_t b_lo = diag ? a_lo : make_smem_desc(sa + 3 * TILE_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / 8; ++k) {
-          const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);   // 32 bytes per K=8 step
-          umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
-          umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
-          umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, 1u);
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);   // 32 bytes per K=8 step
+            umma_tf32(tacc, a_lo + adv, b_hi + adv, idesc, (kb != c * CHUNK || k != 0) ? 1u : 0u);
+            umma_tf32(tacc, a_hi + adv, b_lo + adv, idesc, 1u);
+            umma_tf32(tacc, a_hi + adv, b_hi + adv, idesc, 1u);
+          }
+          umma_commit(&empty[stage]);        // frees the smem stage when the MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&empty[stage]);          // frees the smem stage when the MMAs retire
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        umma_commit(&tmem_full[as]);         // partial accumulator complete
       }
-      umma_commit(tmem_full);                // accumulator complete
     }
   } else {
     // ------------------------------------------------------------------ epilogue
-    mbar_wait(tmem_full, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int quad = warp & 3;               // TMEM lane quadrant this warp may read
     const int row = tm * BM + quad * 32 + lane;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t v[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
-            "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
-            "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
-            "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),
-            "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-          : "r"(taddr)
-          : "memory");
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    float acc[BN];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int col = tn * BN + c0 + j;
-        const float x = __uint_as_float(v[j]);
-        if (row < pr.n && col < pr.n) {
-          pr.out[(long long)row * pr.ldo + col] = x;
-          if (!diag) pr.out[(long long)col * pr.ldo + row] = x;
-        }
+    for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+    for (int c = 0; c < nchunk; ++c) {
+      const int as = c & 1;
+      const uint32_t aphase = (uint32_t)(c >> 1) & 1u;
+      mbar_wait(&tmem_full[as], aphase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + c0);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, "
+            "[%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+              "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]),
+              "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+              "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+              "=r"(v[31])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(v[j]);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+    }
+#pragma unroll
+    for (int j = 0; j < BN; ++j) {
+      const int col = tn * BN + j;
+      // diagonal tiles keep their upper triangle and mirror it, so the result is exactly
+      // symmetric (the two triangles accumulate the hi/lo cross terms in a different order)
+      if (row < pr.n && col < pr.n && (!diag || col >= row)) {
+        pr.out[(long long)row * pr.ldo + col] = acc[j];
+        if (col != row) pr.out[(long long)col * pr.ldo + row] = acc[j];
       }
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");

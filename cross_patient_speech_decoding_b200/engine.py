@@ -121,9 +121,16 @@ class CVEngine:
 
     def eig_any(self, A, n_pad, n_dev, n_fixed, nprob, tag, ncols=None):
         """Sorted eigen-decomposition for any n_pad (A: (nprob, n_pad, n_pad), destroyed).
+        A float64 tensor (n_pad <= 128 only) selects the fp64-matrix solver.
         Returns (evals (nprob, n_pad), evecs (nprob, n_pad, n_pad) with sorted columns)."""
         evals = self.ws(tag + '_ev', (nprob, n_pad))
         evecs = self.ws(tag + '_evec', (nprob, n_pad, n_pad))
+        if A.dtype == torch.float64:
+            assert n_pad <= 128
+            self.ctx.call('cpsd_eig_sym_small_f64', ptr(A), n_pad, n_pad * n_pad, _p(n_dev),
+                          n_fixed, nprob, ptr(evals), n_pad, ptr(evecs), n_pad, n_pad * n_pad,
+                          self.eig_sweeps + 6, 1e-10, ptr(None))
+            return evals, evecs
         if n_pad <= 128:
             self.eig_small(A, n_dev, n_fixed, nprob, n_pad, evals, evecs, n_pad)
             return evals, evecs
@@ -134,6 +141,13 @@ class CVEngine:
         self.ctx.call('cpsd_permute_cols', ptr(V), n_pad, n_pad * n_pad, ptr(perm), n_pad,
                       ptr(evecs), n_pad, n_pad * n_pad, n_pad, nc, nprob)
         return evals, evecs
+
+    def scatter(self, name, nprob, n_pad):
+        """Workspace + kernel name for a batch of scatter matrices that feed an eigen-solver:
+        fp64 accumulation and the fp64-matrix solver whenever the tile solver applies."""
+        if n_pad <= 128:
+            return self.ws(name, (nprob, n_pad, n_pad), torch.float64), 'cpsd_gram_tn_f64'
+        return self.ws(name, (nprob, n_pad, n_pad)), 'cpsd_gram_tn'
 
     # ------------------------------------------------------------------ fold-invariant work
     def _prepare_cross(self):
@@ -187,7 +201,7 @@ class CVEngine:
         ctx, T, Cm = self.ctx, self.T, self.Cmax
         n_pad = _ceil(Cm, 128) if Cm > 128 else 128
         pk = HostPack(ctx)
-        G = self.ws('rk_G', (len(vs), n_pad, n_pad))
+        G, gram = self.scatter('rk_G', len(vs), n_pad)
         G.zero_()
         seg = [pk.add_ints(np.arange(self.views[v].N, dtype=np.int32) * T) for v in vs]
         cdim = pk.add_ints([self.views[v].C for v in vs])
@@ -200,7 +214,7 @@ class CVEngine:
                        1.0, 0)
         d = pk.add_descs(recs)
         pk.upload()
-        ctx.call('cpsd_gram_tn', pk.daddr(d), len(vs), Cm, Cm)
+        ctx.call(gram, pk.daddr(d), len(vs), Cm, Cm)
         cd = ctypes_int_ptr(pk.iaddr(cdim))
         evals, _ = self.eig_any(G, n_pad, cd, 0, len(vs), 'rk')
         k = self.ws('rk_k', (len(vs),), I32)
@@ -217,7 +231,7 @@ class CVEngine:
         n_pad = _ceil(Cm, 128) if Cm > 128 else 128
         pk = HostPack(ctx)
         self.cross_mu = self.ws('cp_mu', (nv, Cm))
-        cov = self.ws('cp_cov', (nv, n_pad, n_pad))
+        cov, gram = self.scatter('cp_cov', nv, n_pad)
         cov.zero_()
         seg = [pk.add_ints(np.arange(self.views[v].N, dtype=np.int32) * T) for v in vs]
         cdim = pk.add_ints([self.views[v].C for v in vs])
@@ -235,7 +249,7 @@ class CVEngine:
         d1, d2 = pk.add_descs(r1), pk.add_descs(r2)
         pk.upload()
         ctx.call('cpsd_colsum', pk.daddr(d1), nv, Cm)
-        ctx.call('cpsd_gram_tn', pk.daddr(d2), nv, Cm, Cm)
+        ctx.call(gram, pk.daddr(d2), nv, Cm, Cm)
         cd = ctypes_int_ptr(pk.iaddr(cdim))
         evals, evecs = self.eig_any(cov, n_pad, cd, 0, nv, 'cp')
         self.cross_k_dev = self.ws('cp_k', (nv,), I32)
@@ -470,9 +484,9 @@ class CVEngine:
         cmT, r_cm = self._class_means_target(pk, tabs, B, Kmax)
         cm_base = lambda f, v: (addr(cmT, f * Kmax * T * tv.C) if v == 0 else addr(self.cm[v]))
         n_padC = 128 if Cm <= 128 else _ceil(Cm, 128)
-        Gt = self.ws('m_Gt', (B, n_padC, n_padC))
+        Gt, gram_c = self.scatter('m_Gt', B, n_padC)
         mu = self.ws('m_mu', (B * P, Cm))
-        cov = self.ws('m_cov', (B * P, n_padC, n_padC))
+        cov, _ = self.scatter('m_cov', B * P, n_padC)
         if Cm < n_padC:
             cov.zero_()
             Gt.zero_()
@@ -556,13 +570,13 @@ class CVEngine:
         ctx.call('cpsd_copy_rows', ctypes_int_ptr(pk.iaddr(o_rank)), B * P, 0, ptr(rank_dev),
                  B * P, 0, ptr(None), 0, 1, B * P, 1)
         if use_rank:
-            ctx.call('cpsd_gram_tn', pk.daddr(d_gt), B, tv.C, tv.C)
+            ctx.call(gram_c, pk.daddr(d_gt), B, tv.C, tv.C)
             ev_t, _ = self.eig_any(Gt, n_padC, ptr(None), tv.C, B, 'mrk')
             ctx.call('cpsd_select_k', ptr(ev_t), n_padC, ptr(None), tv.C, float(self.pca_var), 1,
                      0, 1 << 30, ptr(rank_dev), P, B)
         # per-view centred scatter of the condition averages + eigen-decomposition
         ctx.call('cpsd_colsum', pk.daddr(d_mu), B * P, Cm)
-        ctx.call('cpsd_gram_tn', pk.daddr(d_cov), B * P, Cm, Cm)
+        ctx.call(gram_c, pk.daddr(d_cov), B * P, Cm, Cm)
         ev1, evec1 = self.eig_any(cov, n_padC, cdim_dev, 0, B * P, 'mv', ncols=min(n_padC, R))
         ctx.call('cpsd_mcca_mask', ptr(evec1), n_padC, n_padC * n_padC, ptr(ev1), n_padC,
                  ptr(rank_dev) if use_rank else ptr(None), cdim_dev, R, Cm, ptr(Vr), ptr(d2),

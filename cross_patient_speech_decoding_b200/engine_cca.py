@@ -35,7 +35,7 @@ def batch_cca(eng, batch, want_details):
     Kmax = max(len(tb['present']) for tb in tabs)
     pk.reserve_ints()
     mu_t = eng.ws('c_mu_t', (B, Cm))
-    cov = eng.ws('c_cov', (B, n_padC, n_padC))
+    cov, gram_c = eng.scatter('c_cov', B, n_padC)
     if Cm < n_padC:
         cov.zero_()
     r_mu = np.zeros(B, dtype=_lib.COLSUM_DESC)
@@ -53,7 +53,7 @@ def batch_cca(eng, batch, want_details):
         d_cm = pk.add_descs(r_cm)
     pk.upload()
     ctx.call('cpsd_colsum', pk.daddr(d_mu), B, tv.C)
-    ctx.call('cpsd_gram_tn', pk.daddr(d_cov), B, tv.C, tv.C)
+    ctx.call(gram_c, pk.daddr(d_cov), B, tv.C, tv.C)
     if aligned:
         ctx.call('cpsd_class_mean', pk.daddr(d_cm), B, Kmax, T * tv.C)
     ev_t, evec_t = eng.eig_any(cov, n_padC, ptr(None), tv.C, B, 'ct')
@@ -126,8 +126,6 @@ def batch_cca(eng, batch, want_details):
     # PCA bases (sklearn sign convention, zero-padded to dmax columns)
     Wt = eng.ws('c_Wt', (B, Cm, dmax))
     Wx = eng.ws('c_Wx', (max(nv, 1), Cm, dmax))
-    ctx.call('cpsd_pca_basis', ptr(evec_t), n_padC, n_padC * n_padC, ptr(k_t),
-             ctypes_int_ptr(pk.iaddr(o_cdim_t)), 0, dmax, ptr(Wt), dmax, Cm, B)
     npair = len(pairs)
     Zall = eng.ws('pool_Z', (B, n_pad, F))
     Zall.zero_()
@@ -210,6 +208,8 @@ def batch_cca(eng, batch, want_details):
     pk.upload()
 
     # ------------------------------------------------------------- launches, stage B
+    ctx.call('cpsd_pca_basis', ptr(evec_t), n_padC, n_padC * n_padC, ptr(k_t),
+             ctypes_int_ptr(pk.iaddr(o_cdim_t)), 0, dmax, ptr(Wt), dmax, Cm, B)
     if nv:
         ctx.call('cpsd_pca_basis', ptr(eng.cross_evecs), eng.cross_npad,
                  eng.cross_npad * eng.cross_npad, ptr(eng.cross_k_dev),

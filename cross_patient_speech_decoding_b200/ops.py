@@ -27,18 +27,19 @@ def _ivoid(address):
     return ctypes.c_void_p(address)
 
 
-def eig_sym(A, n=None, max_sweeps=15, tol=3e-7, device=None, return_sweeps=False):
+def eig_sym(A, n=None, max_sweeps=15, tol=3e-7, device=None, return_sweeps=False, f64=False):
     """Eigen-decomposition of a batch of symmetric matrices.  A: (nprob, n, n) or (n, n).
+    ``f64`` (n <= 128): iterate the matrix in fp64, eigenvectors in fp32.
     Returns (evals descending (nprob, n), evecs (nprob, n, n) columns)."""
     ctx = _ctx(device)
-    A = np.asarray(A, dtype=np.float32)
+    A = np.asarray(A, dtype=np.float64 if f64 else np.float32)
     single = A.ndim == 2
     if single:
         A = A[None]
     nprob, nn, _ = A.shape
     ns = np.full(nprob, nn, dtype=np.int32) if n is None else np.asarray(n, dtype=np.int32)
     n_pad = 128 if nn <= 128 else _ceil(nn, 128)
-    Ap = np.zeros((nprob, n_pad, n_pad), dtype=np.float32)
+    Ap = np.zeros((nprob, n_pad, n_pad), dtype=A.dtype)
     Ap[:, :nn, :nn] = A
     Ad = ctx.upload(Ap)
     nd = ctx.upload(ns)
@@ -46,8 +47,9 @@ def eig_sym(A, n=None, max_sweeps=15, tol=3e-7, device=None, return_sweeps=False
     sw = ctx.zeros((max(2 * nprob, 2),), I32)
     if n_pad <= 128:
         evecs = ctx.zeros((nprob, n_pad, n_pad))
-        ctx.call('cpsd_eig_sym_small', ptr(Ad), n_pad, n_pad * n_pad, ptr(nd), 0, nprob, ptr(evals),
-                 n_pad, ptr(evecs), n_pad, n_pad * n_pad, max_sweeps, tol, ptr(sw))
+        ctx.call('cpsd_eig_sym_small_f64' if f64 else 'cpsd_eig_sym_small', ptr(Ad), n_pad,
+                 n_pad * n_pad, ptr(nd), 0, nprob, ptr(evals), n_pad, ptr(evecs), n_pad,
+                 n_pad * n_pad, max_sweeps, 1e-10 if f64 else tol, ptr(sw))
         ev, V = evals.cpu().numpy(), evecs.cpu().numpy()
         sweeps = sw.cpu().numpy()[:nprob]
     else:

@@ -63,6 +63,10 @@ int cpsd_permute_cols(const float* src, int lds, long long strideS, const int* p
  * GEVP (AlignMCCA.py:140-154). */
 int cpsd_gram_tn(const cpsd_gram_tn_desc* descs, int nprob, int p_max, int q_max,
                  cudaStream_t stream);
+/* same with fp64 accumulation; every record's `out` points to doubles (ldo in doubles).  Feeds
+ * the variance thresholds and eigen-solvers of the PCA stages. */
+int cpsd_gram_tn_f64(const cpsd_gram_tn_desc* descs, int nprob, int p_max, int q_max,
+                     cudaStream_t stream);
 /* (X - mu) W: PCA.transform, AlignCCA.transform (AlignCCA.py:93), MCCA transform_view
  * (AlignMCCA.py:110,125), JointPCA.transform (JointPCA.py:132,149); output rows land
  * directly in the pooled trials x (time*latent) matrix (cross_pt_decoders.py:260-270). */
@@ -88,6 +92,12 @@ int cpsd_gram_nt_tc_ws_bytes(int nprob);
 int cpsd_eig_sym_small(const float* A, int lda, long long strideA, const int* n_dev, int n_fixed,
                        int nprob, float* evals, int ld_e, float* evecs, int ldv, long long strideV,
                        int max_sweeps, float tol, int* sweeps_out, cudaStream_t stream);
+/* same solver iterating the matrix in fp64 (A holds doubles) with fp32 eigenvectors: rotation
+ * angles stay accurate for near-degenerate (noise-level) eigenvalues */
+int cpsd_eig_sym_small_f64(const double* A, int lda, long long strideA, const int* n_dev,
+                           int n_fixed, int nprob, float* evals, int ld_e, float* evecs, int ldv,
+                           long long strideV, int max_sweeps, float tol, int* sweeps_out,
+                           cudaStream_t stream);
 /* block Jacobi for n > 128 (n_pad multiple of 128): pooled-Gram PCA, large GEVPs */
 int cpsd_bj_schedule(int n_pad, int* pairs_host);
 int cpsd_eig_sym_block(float* K, float* V, int ld, long long stride, int n_pad, const int* n_dev,
