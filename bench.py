@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""Headline benchmark: CV align+decode folds/sec (MCCA -> PCA -> linear SVM).
+
+Workload (BASELINE.json configs[1]): MCCA alignment of 8 synthetic uECoG patients
+(144 trials x 200 time bins x 128 channels each) into a shared latent space, 20-fold CV
+cross-patient decode for one target patient.  One "step" = one CV iteration = 20 folds
+(20 units), exactly the inner loop of the reference's scripts/aligned_decode_svm_ncv.py:
+336-442.  Multi-GPU: every rank runs its own CV iterations (weak scaling, no data-path
+collective); per-fold accuracies are all-gathered with NCCL at the end of the timed region.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Prints ONE JSON line (rank 0).  `value` = folds/s with the patient data resident in HBM;
+`e2e` = the same through the public host-buffer call (cv_align_decode), uploads included.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_PATIENTS = 8
+N_FOLDS = 20
+METRIC = 'CV align+decode folds/sec (MCCA->PCA->SVM)'
+WORKLOAD = ('mcca_8patients_144x200x128_20fold: MCCA(n_comp=30, regs=0.5, pca_var=0.8) -> '
+            'PCA(0.8) -> OvR linear SVM, 20 folds per step')
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))), 'measured'
+    except Exception:
+        return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], False
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names)
+                   if any(len(r) > 2 + i and r[2 + i].lower().startswith('active') for r in self.rows)]
+        return {'sm_mhz': float(np.median(sm)) if sm else None,
+                'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'samples': len(self.rows)}
+
+
+def make_data():
+    from cross_patient_speech_decoding_b200 import synthetic
+    return synthetic.make_patients(N_PATIENTS)
+
+
+def step_folds(y, step_id):
+    from cross_patient_speech_decoding_b200.folds import cv_splits
+    import warnings
+    np.random.seed(step_id)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        return cv_splits(y, N_FOLDS)
+
+
+# ------------------------------------------------------------------------------ reference
+def cpu_sample(pts, n_folds_sample, step_id=0):
+    """Times the CPU port of the reference path (oracle/pipeline_port.py) on a bounded sample
+    of the same workload.  Returns (folds/s, seconds, accuracy)."""
+    from oracle import pipeline_port
+    folds = step_folds(pts[0][1], step_id)[:n_folds_sample]
+    t0 = time.perf_counter()
+    ok = tot = 0
+    for tr, te in folds:
+        yp, _ = pipeline_port.run_fold(pts[0], pts[1:], tr, te, method='mcca', n_comp=30, regs=0.5,
+                                       pca_var=0.8)
+        ok += int((yp == pts[0][1][te]).sum())
+        tot += len(te)
+    dt = time.perf_counter() - t0
+    return len(folds) / dt, dt, ok / max(tot, 1)
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([i.get('num_threads', 1) for i in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    pts = make_data()
+    for w in range(args.warmup):
+        cpu_sample(pts, 1, 1000 + w)
+    t0 = time.perf_counter()
+    n = 0
+    for s in range(args.steps):
+        _, _, _ = cpu_sample(pts, 1, s)
+        n += 1
+    dt = time.perf_counter() - t0
+    val = n / dt
+    cores = blas_threads()
+    line = {'metric': METRIC, 'value': val, 'unit': 'folds/s', 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / max(n, 1),
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic', 'impl': 'reference',
+            'config': {'workload': WORKLOAD, 'step': '1 fold of the 20-fold workload (bounded '
+                       'sample)', 'host': 'numpy/scipy/scikit-learn float64'},
+            'cpu_baseline': {'value': val, 'unit': 'folds/s', 'cores': cores, 'kind': 'port',
+                             'sample': '%d single-fold steps of the 8-patient 20-fold MCCA workload '
+                                       '(oracle/pipeline_port.py; /root/reference is absent on the '
+                                       'GPU box)' % n},
+            'e2e': {'value': val, 'unit': 'folds/s', 'h2d_bytes_per_step': 0,
+                    'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ ours
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours')
+    ap.add_argument('--no-tc', action='store_true', help='fp32 SIMT pooled Gram instead of tcgen05')
+    ap.add_argument('--cpu-folds', type=int, default=2, help='folds in the cpu_baseline sample')
+    ap.add_argument('--e2e-steps', type=int, default=None)
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__
+    if rank == 0:
+        __graft_entry__.build()
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        dist.barrier()
+    from cross_patient_speech_decoding_b200 import cv_align_decode
+    from cross_patient_speech_decoding_b200.engine import CVEngine
+
+    pts = make_data()
+    y0 = pts[0][1]
+    kw = dict(method='mcca', n_comp=30, regs=0.5, pca_var=0.8, decoder_var=0.8,
+              use_tensor_cores=not args.no_tc, max_batch=N_FOLDS)
+    eng = CVEngine(pts[0], pts[1:], device='cuda:%d' % local, **kw)
+    dev = eng.ctx.device
+
+    def one_step(sid):
+        folds = step_folds(y0, sid)
+        res = eng.run(folds)
+        ok = sum(int((p == y0[te]).sum()) for p, (_, te) in zip(res['y_pred'], folds))
+        tot = sum(len(te) for _, te in folds)
+        return res, ok, tot
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for w in range(args.warmup):
+        one_step(10_000 + rank * 1000 + w)
+    sync_all()
+    eng.ctx.lib.cpsd_reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    accs, h2d, d2h = [], 0, 0
+    with ClockSampler(local) as clk:
+        sync_all()
+        e0.record(torch.cuda.current_stream(dev))
+        for s in range(args.steps):
+            res, ok, tot = one_step(rank * 100_000 + s)
+            accs.append(ok / tot)
+            h2d += res['h2d_bytes']
+            d2h += res['d2h_bytes']
+        acc_t = torch.tensor(accs, dtype=torch.float32, device=dev)
+        if world > 1:   # the one collective of the path: gather per-iteration accuracies
+            gathered = [torch.empty_like(acc_t) for _ in range(world)]
+            dist.all_gather(gathered, acc_t)
+            acc_all = torch.cat(gathered).cpu().numpy()
+        else:
+            acc_all = acc_t.cpu().numpy()
+        e1.record(torch.cuda.current_stream(dev))
+        sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = int(eng.ctx.lib.cpsd_launch_count())
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max = float(t_ms.item())
+    folds_total = world * args.steps * N_FOLDS
+    value = folds_total / (ms_max * 1e-3)
+
+    # ---- end to end through the public host-buffer API (uploads + fold-invariant work inside)
+    e2e_steps = args.e2e_steps or min(args.steps, 3)
+    host_pts = [(torch.from_numpy(np.ascontiguousarray(X)).pin_memory(), y, ya)
+                for X, y, ya in pts]
+    cv_align_decode(host_pts[0], host_pts[1:], step_folds(y0, 77), device='cuda:%d' % local, **kw)
+    sync_all()
+    t0 = time.perf_counter()
+    e2e_h2d = e2e_d2h = 0
+    for s in range(e2e_steps):
+        r = cv_align_decode(host_pts[0], host_pts[1:], step_folds(y0, 500 + rank * 1000 + s),
+                            device='cuda:%d' % local, **kw)
+        e2e_h2d += r['h2d_bytes']
+        e2e_d2h += r['d2h_bytes']
+    sync_all()
+    e2e_dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
+    e2e_val = world * e2e_steps * N_FOLDS / float(e2e_dt.item())
+
+    # ---- stage breakdown + roofline of the dominant tensor / HBM kernels (profiling pass)
+    eng.profile = True
+    one_step(424242)
+    stages = eng.collect_marks()
+    eng.profile = False
+    pk, pk_kind = peaks()
+    n_all = 1152
+    F = 200 * 30
+    stage_total = sum(stages.values()) or 1.0
+    gram_ms = stages.get('pool_gram', float('nan'))
+    gram_flops = 2.0 * n_all * n_all * F * N_FOLDS            # algorithmic, per launch (20 folds)
+    gram_tf = gram_flops / (gram_ms * 1e-3) / 1e12
+    peak_tf = pk.get('bf16_tflops_sustained', pk.get('bf16_tflops'))
+    proj_ms = stages.get('project_pool', float('nan'))
+    proj_bytes = N_FOLDS * (sum(p[0].size for p in pts) * 4 + n_all * F * 4)   # read X once, write pooled
+    roofline = {'kernel': 'k_gram_tc (pooled Gram, tcgen05 kind::tf32, 3xTF32)' if not args.no_tc
+                else 'k_gram_nt (pooled Gram, fp32 SIMT)',
+                'bound': 'tensor', 'achieved': gram_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
+                'frac': gram_tf / peak_tf, 'traffic': None,
+                'peak_source': '%s bf16_tflops_sustained (TF32 dense is nominally half of it; '
+                               '3xTF32 issues 3 MMAs per algorithmic product)' % pk_kind,
+                'algorithmic_flops_per_launch': gram_flops, 'launch_ms': gram_ms,
+                'share_of_step': gram_ms / stage_total}
+    roofline_hbm = {'kernel': 'k_proj_nn (project all trials into the pooled matrix)',
+                    'bound': 'hbm', 'achieved': proj_bytes / (proj_ms * 1e-3) / 1e9,
+                    'peak': pk['hbm_gbs'], 'unit': 'GB/s',
+                    'frac': proj_bytes / (proj_ms * 1e-3) / 1e9 / pk['hbm_gbs'],
+                    'algorithmic_bytes_per_launch': proj_bytes, 'launch_ms': proj_ms,
+                    'share_of_step': proj_ms / stage_total}
+
+    if rank == 0:
+        cpu_sample(pts, 1, 12345)            # warm-up (imports, BLAS threads)
+        cpu_val, cpu_dt, cpu_acc = cpu_sample(pts, args.cpu_folds, 0)
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'folds/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_max / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'folds_per_step_per_gpu': N_FOLDS,
+                       'parallelism': 'folds sharded over %d GPU(s), one NCCL all_gather of '
+                                      'accuracies' % world,
+                       'precision': 'fp32 storage; fp64 scatter+eigen for PCA stages; 3xTF32 '
+                                    'tcgen05 pooled Gram; fp64 SVM',
+                       'l2': 'working set per step ~2 GB (20 pooled 1152x6000 matrices + Grams) '
+                             '>> 126 MB L2, no explicit flush'},
+            'e2e': {'value': e2e_val, 'unit': 'folds/s',
+                    'h2d_bytes_per_step': e2e_h2d // max(e2e_steps, 1),
+                    'd2h_bytes_per_step': e2e_d2h // max(e2e_steps, 1), 'steps': e2e_steps,
+                    'api': 'cross_patient_speech_decoding_b200.cv_align_decode (host float64 '
+                           'arrays in pinned memory -> predictions)'},
+            'gpu_launches': launches,
+            'h2d_bytes_per_step': h2d // args.steps, 'd2h_bytes_per_step': d2h // args.steps,
+            'clocks': clk.summary(),
+            'roofline': roofline, 'roofline_hbm': roofline_hbm,
+            'stages_ms_per_step': {k: round(v, 3) for k, v in stages.items()},
+            'accuracy_mean': float(np.mean(acc_all)),
+            'cpu_baseline': {'value': cpu_val, 'unit': 'folds/s', 'cores': blas_threads(),
+                             'kind': 'port', 'accuracy': cpu_acc,
+                             'sample': '%d folds of the same 8-patient 20-fold workload, '
+                                       'oracle/pipeline_port.py (numpy/scipy/sklearn float64), '
+                                       '%.1f s' % (args.cpu_folds, cpu_dt)},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -73,6 +73,14 @@ k_copy_rows(const float* __restrict__ src, int lds, long long strideS, float* __
   }
 }
 
+// fp64 host data (the reference's native dtype) -> fp32 device layout
+__global__ void __launch_bounds__(256)
+k_cast_f64_f32(const double* __restrict__ src, float* __restrict__ dst, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = (float)src[i];
+}
+
 // dst[p][r][j] = src[p][r][perm[p][j]]   j < ncols, r < nrows
 __global__ void __launch_bounds__(256)
 k_permute_cols(const float* __restrict__ src, int lds, long long strideS,
@@ -270,6 +278,16 @@ extern "C" int cpsd_copy_rows(const float* src, int lds, long long strideS, floa
   int by = nrows < 256 ? nrows : 256;
   k_copy_rows<<<dim3(bx, by, nprob), 256, 0, stream>>>(src, lds, strideS, dst, ldd, strideD, r0_dev,
                                                       r0_fixed, nrows, ncols);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
+
+extern "C" int cpsd_cast_f64_f32(const double* src, float* dst, long long n, cudaStream_t stream) {
+  CPSD_CHECK_ARG(n >= 0, "cast_f64_f32: bad size");
+  if (n == 0) return CPSD_OK;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_cast_f64_f32<<<(int)blocks, 256, 0, stream>>>(src, dst, n);
   CPSD_LAUNCH_CHECK();
   return CPSD_OK;
 }

@@ -31,13 +31,29 @@ class View:
     """One patient resident on the device."""
 
     def __init__(self, ctx, X, y, y_align, cls_ids):
-        X = np.asarray(X)
-        assert X.ndim == 3, 'features must be (trials, time, channels)'
-        self.N, self.T, self.C = X.shape
-        self.X = ctx.upload(X.reshape(self.N * self.T, self.C), np.float32)
+        # X: numpy array or (pinned) CPU torch tensor, float64 (the reference's dtype) or
+        # float32.  float64 is copied as is and cast on the device, so the host never touches
+        # the 29 M samples per patient.
+        if isinstance(X, torch.Tensor):
+            host = X if X.is_contiguous() else X.contiguous()
+        else:
+            host = torch.from_numpy(np.ascontiguousarray(X))
+        assert host.dim() == 3, 'features must be (trials, time, channels)'
+        if host.dtype not in (torch.float32, torch.float64):
+            host = host.to(torch.float64)
+        self.N, self.T, self.C = (int(v) for v in host.shape)
+        if not host.is_pinned():
+            host = host.pin_memory()
+        raw = host.to(ctx.device, non_blocking=True)
+        if raw.dtype == torch.float64:
+            self.X = ctx.empty((self.N * self.T, self.C))
+            ctx.call('cpsd_cast_f64_f32', ptr(raw), ptr(self.X), raw.numel())
+        else:
+            self.X = raw.view(self.N * self.T, self.C)
+        self._host = host                                     # keep staging alive until done
         self.y = np.asarray(y).astype(np.int64)
         self.cls = np.asarray(cls_ids, dtype=np.int32)        # alignment class id per trial
-        self.h2d_bytes = X.size * 4
+        self.h2d_bytes = host.numel() * host.element_size()
 
 
 class CVEngine:
@@ -81,7 +97,30 @@ class CVEngine:
         self._ws = {}
         self._sched = {}
         self.stats = {}
+        self.profile = False
+        self._marks = []
         self._prepare_cross()
+
+    # ------------------------------------------------------------------ stage timing
+    def mark(self, stage):
+        """Records a CUDA event on the launching stream when profiling is on; the time between
+        consecutive marks is attributed to the earlier mark's stage name."""
+        if getattr(self, 'profile', False):
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(torch.cuda.current_stream(self.ctx.device))
+            self._marks.append((stage, ev))
+
+    def collect_marks(self):
+        """Returns {stage: milliseconds} accumulated since the last call (synchronises)."""
+        out = {}
+        marks = getattr(self, '_marks', [])
+        if marks:
+            torch.cuda.synchronize(self.ctx.device)
+            for (name, e0), (_, e1) in zip(marks[:-1], marks[1:]):
+                if name != 'end':
+                    out[name] = out.get(name, 0.0) + e0.elapsed_time(e1)
+        self._marks = []
+        return out
 
     # ------------------------------------------------------------------ workspace
     def ws(self, name, shape, dtype=F32):
@@ -354,14 +393,17 @@ class CVEngine:
         npool_dev = ctypes_int_ptr(pk.iaddr(o_npool))
         nall_dev = ctypes_int_ptr(pk.iaddr(o_nall))
         ncls = len(self.classes)
+        self.mark('pool_center')
         ctx.call('cpsd_colsum', pk.daddr(d1), B, F)
         ctx.call('cpsd_center_rows', ptr(Zall), F, n_pad * F, ptr(mu), F, nall_dev, 0,
                  max(a + b for a, b in zip(n_pool, n_te)), F, B)
         nmax = max(a + b for a, b in zip(n_pool, n_te))
+        self.mark('pool_gram')
         if self.use_tc:
             self.gram_tc(self._r2_host, B, nmax, n_pad * F)
         else:
             ctx.call('cpsd_gram_nt', pk.daddr(d2), B, nmax, nmax)
+        self.mark('pool_eig')
         Kte = self.ws('pool_Kte', (B, n_te_max, n_pad))
         ctx.call('cpsd_copy_rows', ptr(Kall), n_pad, n_pad * n_pad, ptr(Kte), n_pad,
                  n_te_max * n_pad, npool_dev, 0, n_te_max, n_pad, B)
@@ -383,6 +425,7 @@ class CVEngine:
             mode, thr = 0, float(self.decoder_var)
         else:
             mode, thr = 3, float(int(self.decoder_var))
+        self.mark('pool_scores')
         ctx.call('cpsd_select_k', ptr(evals), n_pad, npool_dev, 0, thr, mode, 1, kcap, ptr(k2), 1,
                  B)
         St = self.ws('pool_St', (B, kcap, n_pad))
@@ -565,10 +608,12 @@ class CVEngine:
         cdim_dev = ctypes_int_ptr(pk.iaddr(o_cdim))
         rank_dev = self.ws('m_rank', (B * P,), I32)
         # class means of the target's train trials
+        self.mark('class_mean')
         ctx.call('cpsd_class_mean', pk.daddr(d_cm), B, Kmax, T * tv.C)
         # signal ranks (cross ranks are fold-invariant and come with the int table)
         ctx.call('cpsd_copy_rows', ctypes_int_ptr(pk.iaddr(o_rank)), B * P, 0, ptr(rank_dev),
                  B * P, 0, ptr(None), 0, 1, B * P, 1)
+        self.mark('align_scatter_eig')
         if use_rank:
             ctx.call(gram_c, pk.daddr(d_gt), B, tv.C, tv.C)
             ev_t, _ = self.eig_any(Gt, n_padC, ptr(None), tv.C, B, 'mrk')
@@ -593,21 +638,25 @@ class CVEngine:
         reg = -1.0 if self.regs is None else float(self.regs)
         ctx.call('cpsd_mcca_build', ptr(Gz), P * R, P * R * P * R, ptr(r_eff), P, R, reg, ptr(M),
                  n_padM, n_padM * n_padM, ptr(n_m), ptr(cidx), ptr(dh), Q, ptr(status), B)
+        self.mark('mcca_gevp')
         evm, U = self.eig_any(M, n_padM, ptr(n_m), 0, B, 'mm', ncols=Q)
         ctx.call('cpsd_mcca_loadings', ptr(Vr), ptr(U), n_padM, n_padM * n_padM, ptr(None), 0,
                  ptr(r_eff), ptr(dh), P, R, Cm, Q, ptr(L), Q, B)
         # project every trial of every view into the pooled (trial x time*Q) matrix
+        self.mark('project_pool')
         ctx.call('cpsd_proj_nn', ctypes_off(pk.daddr(d_pp), 0), B * P + B,
                  max(max(self.views[v].N for v in range(P)), n_te_max), T, Q)
         evals, k2_, St_, Ste, V, sweeps, kcap = self._pooled_stage_run(
             pk, d_p1, d_p2, B, Zall, pmu, Kall, n_pad, F, n_pool, n_te, o_npool, o_nall, o_ypool,
             n_te_max, want_details)
+        self.mark('svm')
         ctx.call('cpsd_svm_fit_ovr', pk.daddr(d_svm), B * len(self.classes), kcap, n_pad)
         yhat = self.ws('yhat', (B, n_te_max), I32)
         ncls = len(self.classes)
         ctx.call('cpsd_svm_predict_ovr', ptr(Ste), n_te_max, kcap * n_te_max, ptr(W), kcap + 1,
                  ncls * (kcap + 1), ptr(k2), 0, ctypes_int_ptr(pk.iaddr(o_nte)), n_te_max,
                  ptr(self.classes_dev), ncls, ptr(yhat), ptr(None), B)
+        self.mark('end')
         yh = yhat.cpu().numpy()
         k2h = k2.cpu().numpy()
         st = status.cpu().numpy()

@@ -52,6 +52,7 @@ def batch_cca(eng, batch, want_details):
         cmT, r_cm = eng._class_means_target(pk, tabs, B, Kmax)
         d_cm = pk.add_descs(r_cm)
     pk.upload()
+    eng.mark('align_scatter_eig')
     ctx.call('cpsd_colsum', pk.daddr(d_mu), B, tv.C)
     ctx.call(gram_c, pk.daddr(d_cov), B, tv.C, tv.C)
     if aligned:
@@ -208,6 +209,7 @@ def batch_cca(eng, batch, want_details):
     pk.upload()
 
     # ------------------------------------------------------------- launches, stage B
+    eng.mark('cca_solve')
     ctx.call('cpsd_pca_basis', ptr(evec_t), n_padC, n_padC * n_padC, ptr(k_t),
              ctypes_int_ptr(pk.iaddr(o_cdim_t)), 0, dmax, ptr(Wt), dmax, Cm, B)
     if nv:
@@ -220,17 +222,20 @@ def batch_cca(eng, batch, want_details):
         ctx.call('cpsd_gram_tn', pk.daddr(d_s), npair, 2 * dmax, 2 * dmax)
         ctx.call('cpsd_cca_solve', pk.daddr(d_c), npair, dmax)
         ctx.call('cpsd_proj_nn', pk.daddr(d_w), npair, 1, Cm, dmax)
+    eng.mark('project_pool')
     ctx.call('cpsd_proj_nn', pk.daddr(d_pp), len(r_pp),
              max(max(eng.views[v].N for v in range(P)), n_te_max), T, dq)
     evals, k2_, St_, Ste, V, sweeps, kcap = eng._pooled_stage_run(
         pk, d_p1, d_p2, B, Zall, pmu, Kall, n_pad, F, n_pool, n_te, o_npool, o_nall, o_ypool,
         n_te_max, want_details)
     ncls = len(eng.classes)
+    eng.mark('svm')
     ctx.call('cpsd_svm_fit_ovr', pk.daddr(d_svm), B * ncls, kcap, n_pad)
     yhat = eng.ws('yhat', (B, n_te_max), I32)
     ctx.call('cpsd_svm_predict_ovr', ptr(Ste), n_te_max, kcap * n_te_max, ptr(W), kcap + 1,
              ncls * (kcap + 1), ptr(k2), 0, ctypes_int_ptr(pk.iaddr(o_nte)), n_te_max,
              ptr(eng.classes_dev), ncls, ptr(yhat), ptr(None), B)
+    eng.mark('end')
     yh = yhat.cpu().numpy()
     k2h = k2.cpu().numpy()
     res = {'y_pred': [yh[f, :n_te[f]].copy() for f in range(B)], 'k2': k2h.tolist(),
