@@ -66,8 +66,11 @@ _SIGS = {
     'cpsd_eig_sym_small_f64': [_P, c_int, c_ll, _P, c_int, c_int, _P, c_int, _P, c_int, c_ll, c_int,
                                c_float, _P, _P],
     'cpsd_bj_schedule': [c_int, _P],
-    'cpsd_eig_sym_block': [_P, _P, c_int, c_ll, c_int, _P, c_int, c_int, _P, _P, _P, _P, _P, _P,
+    'cpsd_eig_sym_block': [_P, c_int, c_ll, c_int, _P, c_int, c_int, _P, _P, _P, _P, _P, _P,
                            c_int, c_int, c_float, _P],
+    'cpsd_bj_rlog_elems': [c_int, c_int, c_int],
+    'cpsd_bj_eigvecs': [_P, c_int, c_int, _P, _P, _P, c_int, _P, c_int, c_int, _P, c_int, c_ll,
+                        c_int, _P],
     'cpsd_select_k': [_P, c_int, _P, c_int, c_float, c_int, c_int, c_int, _P, c_int, c_int, _P],
     'cpsd_gram_tn': [_P, c_int, c_int, c_int, _P],
     'cpsd_gram_tn_f64': [_P, c_int, c_int, c_int, _P],
@@ -97,6 +100,7 @@ _SIGS = {
     'cpsd_gram_nt_tc_ws_bytes': [c_int],
 }
 _RESTYPES = {'cpsd_last_error': ctypes.c_char_p, 'cpsd_launch_count': c_ll,
+             'cpsd_bj_rlog_elems': c_ll,
              'cpsd_reset_launch_count': None}
 
 EXPORTED_SYMBOLS = sorted(_SIGS)

@@ -28,6 +28,21 @@ struct StepBuf {
   double c[TS / 2];
   double s[TS / 2];
   double d[TS / 2];   // t * a_pq (diagonal update)
+  float cf[TS / 2];   // fp32 copies (eigenvector update, fp32 matrix update): converting per
+  float sf[TS / 2];   // use would put an F2F on every element update
+  float df[TS / 2];
+};
+
+template <typename T> struct RotView;
+template <> struct RotView<double> {
+  static __device__ __forceinline__ double c(const StepBuf* sb, int k) { return sb->c[k]; }
+  static __device__ __forceinline__ double s(const StepBuf* sb, int k) { return sb->s[k]; }
+  static __device__ __forceinline__ double d(const StepBuf* sb, int k) { return sb->d[k]; }
+};
+template <> struct RotView<float> {
+  static __device__ __forceinline__ float c(const StepBuf* sb, int k) { return sb->cf[k]; }
+  static __device__ __forceinline__ float s(const StepBuf* sb, int k) { return sb->sf[k]; }
+  static __device__ __forceinline__ float d(const StepBuf* sb, int k) { return sb->df[k]; }
 };
 
 // pair (i, j) of slot k at step s, modulus ordering over m (even) indices:
@@ -72,20 +87,26 @@ __device__ __forceinline__ float tile_rotations(T* As, StepBuf* sb, int npairs, 
     sb->c[k] = c;
     sb->s[k] = s;
     sb->d[k] = d;
+    sb->cf[k] = (float)c;
+    sb->sf[k] = (float)s;
+    sb->df[k] = (float)d;
   }
   return seen;
 }
 
-template <typename T>
-__device__ __forceinline__ void tile_apply(T* As, float* Vs, StepBuf* sb, int npairs, int vrows) {
+// NP > 0: compile-time pair count (power of two) -- the block-Jacobi tiles; NP == 0: runtime.
+template <typename T, int NP>
+__device__ __forceinline__ void tile_apply(T* As, float* Vs, StepBuf* sb, int npairs_rt, int vrows) {
+  const int npairs = NP > 0 ? NP : npairs_rt;
   const int nblk = npairs * npairs;
   for (int b = threadIdx.x; b < nblk; b += NT) {
-    const int k = b / npairs, l = b - k * npairs;
+    const int k = NP > 0 ? b / NP : b / npairs;
+    const int l = b - k * npairs;
     const int ik = sb->pi[k], jk = sb->pj[k];
-    const T ck = (T)sb->c[k], sk = (T)sb->s[k];
+    const T ck = RotView<T>::c(sb, k), sk = RotView<T>::s(sb, k);
     if (k == l) {
       if (sk != (T)0) {
-        const T d = (T)sb->d[k];
+        const T d = RotView<T>::d(sb, k);
         As[ik * TS + ik] -= d;
         As[jk * TS + jk] += d;
         As[ik * TS + jk] = (T)0;
@@ -94,7 +115,7 @@ __device__ __forceinline__ void tile_apply(T* As, float* Vs, StepBuf* sb, int np
       continue;
     }
     const int il = sb->pi[l], jl = sb->pj[l];
-    const T cl = (T)sb->c[l], sl = (T)sb->s[l];
+    const T cl = RotView<T>::c(sb, l), sl = RotView<T>::s(sb, l);
     if (sk == (T)0 && sl == (T)0) continue;
     const T app = As[ik * TS + il], apq = As[ik * TS + jl];
     const T aqp = As[jk * TS + il], aqq = As[jk * TS + jl];
@@ -109,8 +130,9 @@ __device__ __forceinline__ void tile_apply(T* As, float* Vs, StepBuf* sb, int np
   }
   const int nv = vrows * npairs;
   for (int b = threadIdx.x; b < nv; b += NT) {
-    const int r = b / npairs, l = b - r * npairs;
-    const float cl = (float)sb->c[l], sl = (float)sb->s[l];
+    const int r = NP > 0 ? b / NP : b / npairs;
+    const int l = b - r * npairs;
+    const float cl = sb->cf[l], sl = sb->sf[l];
     if (sl == 0.f) continue;
     const int il = sb->pi[l], jl = sb->pj[l];
     const float vp = Vs[r * TS + il], vq = Vs[r * TS + jl];
@@ -144,7 +166,8 @@ __device__ float tile_sweep_full(T* As, float* Vs, StepBuf* sb, int m, int vrows
     __syncthreads();
     seen = fmaxf(seen, tile_rotations<T>(As, sb, npairs, nrot, skip_thr));
     __syncthreads();
-    tile_apply<T>(As, Vs, sb, npairs, vrows);
+    if (m == TS) tile_apply<T, TS / 2>(As, Vs, sb, npairs, vrows);
+    else tile_apply<T, 0>(As, Vs, sb, npairs, vrows);
     __syncthreads();
   }
   if (threadIdx.x == 0) *redmax = 0;
@@ -167,7 +190,7 @@ __device__ float tile_sweep_cross(float* As, float* Vs, StepBuf* sb, float skip_
     __syncthreads();
     seen = fmaxf(seen, tile_rotations<float>(As, sb, BS, BS, skip_thr));
     __syncthreads();
-    tile_apply<float>(As, Vs, sb, BS, TS);
+    tile_apply<float, BS>(As, Vs, sb, BS, TS);
     __syncthreads();
   }
   if (threadIdx.x == 0) *redmax = 0;
@@ -241,7 +264,7 @@ k_eig_tile(const T* __restrict__ A, int lda, long long strideA, const int* __res
     for (; sw < max_sweeps; ++sw) {
       const float dmax = tile_diag_absmax<T>(As, m, redmax);
       const float skip = (sizeof(T) == 8 ? 1e-15f : 1e-9f) * dmax + 1e-37f;
-      const float off = tile_sweep_full<T>(As, Vs, sb, m, m, skip, redmax);
+      const float off = tile_sweep_full<T>(As, Vs, sb, m, evecs ? m : 0, skip, redmax);
       if (off <= tol * dmax) { ++sw; break; }
     }
   }
@@ -274,7 +297,9 @@ k_eig_tile(const T* __restrict__ A, int lda, long long strideA, const int* __res
 
 // ---------------------------------------------------------------------------------------
 // Block Jacobi: inner rotation of one pair's diagonal tile.
-// grid (npairs, nprob).  pairs: [npairs][2] block indices of this round.
+// grid (npairs, nprob).  pairs: [npairs][2] block indices of this round.  The accumulated
+// 128x128 rotation of the tile goes into the rotation log:
+//   Rlog[((prob * total_rounds + round_idx) * npairs + pair)][128*128]
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ int tile_gidx(int r, int I, int J) {
   return (r < BS) ? (I * BS + r) : (J * BS + r - BS);
@@ -282,11 +307,12 @@ __device__ __forceinline__ int tile_gidx(int r, int I, int J) {
 
 __global__ void __launch_bounds__(NT)
 k_bj_inner(float* __restrict__ K, int ldk, long long strideK, const int* __restrict__ pairs,
-           float* __restrict__ Rbuf, const float* __restrict__ scale, float* __restrict__ conv,
+           float* __restrict__ Rlog, int total_rounds, int round_idx,
+           const float* __restrict__ scale, float* __restrict__ conv,
            const int* __restrict__ done, int full_mode) {
-  extern __shared__ float smem[];
-  float* As = smem;
-  float* Vs = smem + TS * TS;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* As = reinterpret_cast<float*>(smem_raw);
+  float* Vs = As + TS * TS;
   StepBuf* sb = reinterpret_cast<StepBuf*>(Vs + TS * TS);
   int* redmax = reinterpret_cast<int*>(sb + 1);
 
@@ -313,138 +339,333 @@ k_bj_inner(float* __restrict__ K, int ldk, long long strideK, const int* __restr
     const int r = e >> 7, c = e & (TS - 1);
     Kg[(long long)tile_gidx(r, I, J) * ldk + tile_gidx(c, I, J)] = As[e];
   }
-  float* Rg = Rbuf + ((long long)prob * npairs + pr) * (TS * TS);
+  float* Rg = Rlog + (((long long)prob * total_rounds + round_idx) * npairs + pr) * (TS * TS);
   for (int e = threadIdx.x; e < TS * TS; e += NT) Rg[e] = Vs[e];
 }
 
 // ---------------------------------------------------------------------------------------
+// Cross-sweep variant of the inner kernel (16 of every 17 rounds): only the 64x64 pairs
+// (i in block I, j in block J) rotate, in 64 steps of 64 disjoint pairs
+// (l, 64 + (l+s)%64).  The tile stays in shared memory (64 KB -> 2 CTAs/SM at 128 registers), but the
+// accumulated rotation R lives in REGISTERS: warp w owns rows 16w..16w+15, lane x holds
+// R[r][x], R[r][x+32] and the two J-block columns currently paired with them; the J columns
+// ride a 64-slot ring that advances one lane per step (2 shuffles), so the partner of
+// column l is always in the same lane.  Rotation parameters are evaluated in fp32 here; the
+// resulting O(1e-6) column-norm drift of R is removed by normalising R's columns before
+// they are logged.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT, 2)
+k_bj_inner_cross(float* __restrict__ K, int ldk, long long strideK, const int* __restrict__ pairs,
+                 float* __restrict__ Rlog, int total_rounds, int round_idx,
+                 const float* __restrict__ scale, float* __restrict__ conv,
+                 const int* __restrict__ done) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* As = reinterpret_cast<float*>(smem_raw);          // [128][128]
+  float2* cs = reinterpret_cast<float2*>(As + TS * TS);    // [64] (c, s) of the step
+  float* dd = reinterpret_cast<float*>(cs + BS);           // [64] t * a_pq
+  float* nrm = dd + BS;                                    // [128] column norms^2 of R
+  int* redmax = reinterpret_cast<int*>(nrm + TS);
+
+  const int pr = blockIdx.x, prob = blockIdx.y, npairs = gridDim.x;
+  if (done && done[prob]) return;
+  const int I = pairs[2 * pr], J = pairs[2 * pr + 1];
+  float* Kg = K + (long long)prob * strideK;
+  for (int e = threadIdx.x; e < TS * TS; e += NT) {
+    const int r = e >> 7, c = e & (TS - 1);
+    As[e] = Kg[(long long)tile_gidx(r, I, J) * ldk + tile_gidx(c, I, J)];
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float vI0[16], vI1[16], vJ0[16], vJ1[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int r = warp * 16 + i;
+    vI0[i] = (r == lane) ? 1.f : 0.f;
+    vI1[i] = (r == lane + 32) ? 1.f : 0.f;
+    vJ0[i] = (r == lane + 64) ? 1.f : 0.f;
+    vJ1[i] = (r == lane + 96) ? 1.f : 0.f;
+  }
+  const float sc = scale[prob];
+  const float skip = 1e-9f * sc + 1e-37f;
+  float seen = 0.f;
+  const int l = threadIdx.x & 63, kq = threadIdx.x >> 6;
+  __syncthreads();
+
+  for (int s = 0; s < BS; ++s) {
+    if (threadIdx.x < BS) {
+      const int i = threadIdx.x, j = BS + ((i + s) & (BS - 1));
+      const float app = As[i * TS + i], aqq = As[j * TS + j], apq = As[i * TS + j];
+      float c = 1.f, sn = 0.f, d = 0.f;
+      const float aa = fabsf(apq);
+      seen = fmaxf(seen, aa);
+      if (aa > skip) {
+        const float tau = (aqq - app) / (2.f * apq);
+        const float t = copysignf(1.f, tau) / (fabsf(tau) + sqrtf(1.f + tau * tau));
+        if (t == t && fabsf(t) <= 1.f) {
+          c = 1.f / sqrtf(1.f + t * t);
+          sn = t * c;
+          d = t * apq;
+        }
+      }
+      cs[i] = make_float2(c, sn);
+      dd[i] = d;
+    }
+    __syncthreads();
+    // ---- tile update: thread owns column pair l, walks row pairs k = kq, kq+4, ...
+    {
+      const float2 csl = cs[l];
+      const int jl = BS + ((l + s) & (BS - 1));
+#pragma unroll 4
+      for (int i = 0; i < 16; ++i) {
+        const int k = kq + 4 * i;
+        const float2 csk = cs[k];
+        const int jk = BS + ((k + s) & (BS - 1));
+        if (k == l) {
+          if (csk.y != 0.f) {
+            const float d = dd[k];
+            As[k * TS + k] -= d;
+            As[jk * TS + jk] += d;
+            As[k * TS + jk] = 0.f;
+            As[jk * TS + k] = 0.f;
+          }
+        } else if (csk.y != 0.f || csl.y != 0.f) {
+          const float app = As[k * TS + l], apq = As[k * TS + jl];
+          const float aqp = As[jk * TS + l], aqq = As[jk * TS + jl];
+          const float tpp = csl.x * app - csl.y * apq, tpq = csl.y * app + csl.x * apq;
+          const float tqp = csl.x * aqp - csl.y * aqq, tqq = csl.y * aqp + csl.x * aqq;
+          As[k * TS + l] = csk.x * tpp - csk.y * tqp;
+          As[jk * TS + l] = csk.y * tpp + csk.x * tqp;
+          As[k * TS + jl] = csk.x * tpq - csk.y * tqq;
+          As[jk * TS + jl] = csk.y * tpq + csk.x * tqq;
+        }
+      }
+    }
+    // ---- R update in registers: column lane (+32) pairs with ring slot lane (+32)
+    {
+      const float2 c0 = cs[lane], c1 = cs[lane + 32];
+      const int src = (lane + 1) & 31;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float p0 = vI0[i], q0 = vJ0[i], p1 = vI1[i], q1 = vJ1[i];
+        vI0[i] = c0.x * p0 - c0.y * q0;
+        const float nq0 = c0.y * p0 + c0.x * q0;
+        vI1[i] = c1.x * p1 - c1.y * q1;
+        const float nq1 = c1.y * p1 + c1.x * q1;
+        const float a = __shfl_sync(0xffffffffu, nq0, src);
+        const float b = __shfl_sync(0xffffffffu, nq1, src);
+        vJ0[i] = (lane == 31) ? b : a;
+        vJ1[i] = (lane == 31) ? a : b;
+      }
+    }
+    __syncthreads();
+  }
+  // convergence measure
+  if (threadIdx.x == 0) *redmax = 0;
+  __syncthreads();
+  seen = warp_max(seen);
+  if (lane == 0) atomicMax(redmax, __float_as_int(seen));
+  // column norms of R (rows are spread over the 8 warps)
+  for (int c = threadIdx.x; c < TS; c += NT) nrm[c] = 0.f;
+  __syncthreads();
+  {
+    float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      n0 = fmaf(vI0[i], vI0[i], n0);
+      n1 = fmaf(vI1[i], vI1[i], n1);
+      n2 = fmaf(vJ0[i], vJ0[i], n2);
+      n3 = fmaf(vJ1[i], vJ1[i], n3);
+    }
+    atomicAdd(&nrm[lane], n0);
+    atomicAdd(&nrm[lane + 32], n1);
+    atomicAdd(&nrm[lane + 64], n2);
+    atomicAdd(&nrm[lane + 96], n3);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && sc > 0.f)
+    atomicMax(reinterpret_cast<int*>(conv + prob), __float_as_int(__int_as_float(*redmax) / sc));
+  for (int e = threadIdx.x; e < TS * TS; e += NT) {
+    const int r = e >> 7, c = e & (TS - 1);
+    Kg[(long long)tile_gidx(r, I, J) * ldk + tile_gidx(c, I, J)] = As[e];
+  }
+  float* Rg = Rlog + (((long long)prob * total_rounds + round_idx) * npairs + pr) * (TS * TS);
+  const float s0 = rsqrtf(nrm[lane]), s1 = rsqrtf(nrm[lane + 32]);
+  const float s2 = rsqrtf(nrm[lane + 64]), s3 = rsqrtf(nrm[lane + 96]);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float* row = Rg + (warp * 16 + i) * TS;
+    row[lane] = vI0[i] * s0;
+    row[lane + 32] = vI1[i] * s1;
+    row[lane + 64] = vJ0[i] * s2;
+    row[lane + 96] = vJ1[i] * s3;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Block Jacobi: apply the round's rotations to the off-diagonal tiles of K (p < q, both
-// mirror images written) and to the column panels of the eigenvector matrix V.
-// grid (n_ktasks + n_vtasks, nprob)
+// mirror images written):  K[p,q] <- R_p^T K[p,q] R_q.   grid (npairs(npairs-1)/2, nprob)
+// The eigenvector matrix is NOT touched here: rotations are replayed on the wanted columns
+// afterwards (k_bj_backapply), which costs k/n of the classical accumulate-every-round.
 // ---------------------------------------------------------------------------------------
 #define LDX 129
 __global__ void __launch_bounds__(NT)
-k_bj_update(float* __restrict__ K, float* __restrict__ V, int ld, long long stride, int n_pad,
-            const int* __restrict__ pairs, int npairs, const float* __restrict__ Rbuf,
+k_bj_update(float* __restrict__ K, int ld, long long stride, const int* __restrict__ pairs,
+            int npairs, const float* __restrict__ Rlog, int total_rounds, int round_idx,
             const int* __restrict__ done) {
   extern __shared__ float smem[];
   float* Xs = smem;                 // [128][129]
   float* Rs = smem + TS * LDX;      // [128][128]
   const int prob = blockIdx.y;
   if (done && done[prob]) return;
-  const int n_ktasks = npairs * (npairs - 1) / 2;
-  int task = blockIdx.x;
+  const int task = blockIdx.x;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   float* Kg = K + (long long)prob * stride;
-  float* Vg = V + (long long)prob * stride;
-  const float* Rp_all = Rbuf + (long long)prob * npairs * (TS * TS);
+  const float* Rp_all = Rlog + ((long long)prob * total_rounds + round_idx) * npairs * (TS * TS);
 
-  if (task < n_ktasks) {
-    // decode (p, q), p < q
-    int p = 0, rem = task;
-    while (rem >= npairs - 1 - p) { rem -= npairs - 1 - p; ++p; }
-    const int q = p + 1 + rem;
-    const int Ip = pairs[2 * p], Jp = pairs[2 * p + 1];
-    const int Iq = pairs[2 * q], Jq = pairs[2 * q + 1];
-    const float* Rq = Rp_all + (long long)q * (TS * TS);
-    const float* Rp = Rp_all + (long long)p * (TS * TS);
-    for (int e = threadIdx.x; e < TS * TS; e += NT) {
-      const int r = e >> 7, c = e & (TS - 1);
-      Xs[r * LDX + c] = Kg[(long long)tile_gidx(r, Ip, Jp) * ld + tile_gidx(c, Iq, Jq)];
-      Rs[e] = Rq[e];
-    }
-    __syncthreads();
-    float acc[8][8];
+  // decode (p, q), p < q
+  int p = 0, rem = task;
+  while (rem >= npairs - 1 - p) { rem -= npairs - 1 - p; ++p; }
+  const int q = p + 1 + rem;
+  const int Ip = pairs[2 * p], Jp = pairs[2 * p + 1];
+  const int Iq = pairs[2 * q], Jq = pairs[2 * q + 1];
+  const float* Rq = Rp_all + (long long)q * (TS * TS);
+  const float* Rp = Rp_all + (long long)p * (TS * TS);
+  for (int e = threadIdx.x; e < TS * TS; e += NT) {
+    const int r = e >> 7, c = e & (TS - 1);
+    Xs[r * LDX + c] = Kg[(long long)tile_gidx(r, Ip, Jp) * ld + tile_gidx(c, Iq, Jq)];
+    Rs[e] = Rq[e];
+  }
+  __syncthreads();
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  for (int kk = 0; kk < TS; ++kk) {
+    float a[8], b[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = Xs[(ty + 16 * i) * LDX + kk];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b[j] = Rs[kk * TS + tx + 16 * j];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-    for (int kk = 0; kk < TS; ++kk) {
-      float a[8], b[8];
+      for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+  }
+  __syncthreads();
 #pragma unroll
-      for (int i = 0; i < 8; ++i) a[i] = Xs[(ty + 16 * i) * LDX + kk];
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) b[j] = Rs[kk * TS + tx + 16 * j];
+    for (int j = 0; j < 8; ++j) Xs[(ty + 16 * i) * LDX + tx + 16 * j] = acc[i][j];
+  for (int e = threadIdx.x; e < TS * TS; e += NT) Rs[e] = Rp[e];
+  __syncthreads();
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-    }
-    __syncthreads();
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  for (int kk = 0; kk < TS; ++kk) {
+    float a[8], b[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 8; ++i) a[i] = Rs[kk * TS + ty + 16 * i];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) Xs[(ty + 16 * i) * LDX + tx + 16 * j] = acc[i][j];
-    for (int e = threadIdx.x; e < TS * TS; e += NT) Rs[e] = Rp[e];
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-    for (int kk = 0; kk < TS; ++kk) {
-      float a[8], b[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) a[i] = Rs[kk * TS + ty + 16 * i];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) b[j] = Xs[kk * LDX + tx + 16 * j];
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int gr = tile_gidx(ty + 16 * i, Ip, Jp);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int gc = tile_gidx(tx + 16 * j, Iq, Jq);
-        Kg[(long long)gr * ld + gc] = acc[i][j];
-        Kg[(long long)gc * ld + gr] = acc[i][j];
-      }
-    }
-  } else {
-    task -= n_ktasks;
-    const int rb = task / npairs, q = task - rb * npairs;
-    const int Iq = pairs[2 * q], Jq = pairs[2 * q + 1];
-    const float* Rq = Rp_all + (long long)q * (TS * TS);
-    const int row0 = rb * TS;
-    for (int e = threadIdx.x; e < TS * TS; e += NT) {
-      const int r = e >> 7, c = e & (TS - 1);
-      Xs[r * LDX + c] = Vg[(long long)(row0 + r) * ld + tile_gidx(c, Iq, Jq)];
-      Rs[e] = Rq[e];
-    }
-    __syncthreads();
-    float acc[8][8];
+    for (int j = 0; j < 8; ++j) b[j] = Xs[kk * LDX + tx + 16 * j];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-    for (int kk = 0; kk < TS; ++kk) {
-      float a[8], b[8];
+      for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+  }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) a[i] = Xs[(ty + 16 * i) * LDX + kk];
+  for (int i = 0; i < 8; ++i) {
+    const int gr = tile_gidx(ty + 16 * i, Ip, Jp);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) b[j] = Rs[kk * TS + tx + 16 * j];
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    for (int j = 0; j < 8; ++j) {
+      const int gc = tile_gidx(tx + 16 * j, Iq, Jq);
+      Kg[(long long)gr * ld + gc] = acc[i][j];
+      Kg[(long long)gc * ld + gr] = acc[i][j];
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Eigenvectors on demand.  V = R_1 R_2 ... R_L (one block-diagonal rotation per round), so
+// the wanted columns are  E = R_1 ( R_2 ( ... ( R_L  I[:, sel] ))).
+// k_bj_einit writes I[:, sel] (sel = perm[0..k)), k_bj_backapply applies one round:
+//   E[rows of pair p, 64-column chunk] <- R_p E[rows of pair p, chunk]
+// grid (npairs * nchunks, nprob); chunks beyond k[prob] and rounds beyond the problem's own
+// sweep count exit immediately.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT)
+k_bj_einit(float* __restrict__ E, int lde, long long strideE, int n_pad,
+           const int* __restrict__ perm, int ld_perm, const int* __restrict__ k_dev, int k_fixed) {
+  const int prob = blockIdx.y;
+  int k = k_dev ? k_dev[prob] : k_fixed;
+  if (k > lde) k = lde;
+  float* Ep = E + (long long)prob * strideE;
+  const int* pp = perm + (long long)prob * ld_perm;
+  for (int r = blockIdx.x; r < n_pad; r += gridDim.x)
+    for (int j = threadIdx.x; j < k; j += NT) Ep[(long long)r * lde + j] = (pp[j] == r) ? 1.f : 0.f;
+}
+
+#define EC 64
+__global__ void __launch_bounds__(NT)
+k_bj_backapply(float* __restrict__ E, int lde, long long strideE, const int* __restrict__ pairs,
+               int npairs, const float* __restrict__ Rlog, int total_rounds, int round_idx,
+               int nrounds, const int* __restrict__ sweeps, const int* __restrict__ k_dev,
+               int k_fixed) {
+  extern __shared__ float smem[];
+  float* Rs = smem;               // [128][129]
+  float* Es = smem + TS * LDX;    // [128][EC]
+  const int prob = blockIdx.y;
+  if (round_idx >= sweeps[prob] * nrounds) return;
+  int k = k_dev ? k_dev[prob] : k_fixed;
+  if (k > lde) k = lde;
+  const int pr = blockIdx.x % npairs, chunk = blockIdx.x / npairs;
+  const int c0 = chunk * EC;
+  if (c0 >= k) return;
+  const int I = pairs[2 * pr], J = pairs[2 * pr + 1];
+  float* Ep = E + (long long)prob * strideE;
+  const float* Rg = Rlog + (((long long)prob * total_rounds + round_idx) * npairs + pr) * (TS * TS);
+  for (int e = threadIdx.x; e < TS * TS; e += NT) Rs[(e >> 7) * LDX + (e & (TS - 1))] = Rg[e];
+  for (int e = threadIdx.x; e < TS * EC; e += NT) {
+    const int r = e / EC, c = e - r * EC;
+    Es[e] = (c0 + c < k) ? Ep[(long long)tile_gidx(r, I, J) * lde + c0 + c] : 0.f;
+  }
+  __syncthreads();
+  // 128 x 64 outputs, 256 threads: thread -> rows ty + 16 i (i < 8), cols tx + 16 j (j < 4)
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[8][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int gr = row0 + ty + 16 * i;
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        Vg[(long long)gr * ld + tile_gidx(tx + 16 * j, Iq, Jq)] = acc[i][j];
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int kk = 0; kk < TS; ++kk) {
+    float a[8], b[4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = Rs[(ty + 16 * i) * LDX + kk];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = Es[kk * EC + tx + 16 * j];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int gr = tile_gidx(ty + 16 * i, I, J);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = c0 + tx + 16 * j;
+      if (c < k) Ep[(long long)gr * lde + c] = acc[i][j];
     }
   }
 }
 
 // per-sweep convergence bookkeeping: done[p] |= conv[p] <= tol ; conv[p] = 0
-__global__ void k_bj_check(float* conv, int* done, int* sweeps, float tol, int nprob) {
+__global__ void k_bj_check(float* conv, int* done, int* sweeps, float* hist, int hist_len,
+                           float tol, int nprob) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nprob) return;
   if (!done[p]) {
+    if (hist && sweeps[p] < hist_len) hist[(long long)p * hist_len + sweeps[p]] = conv[p];
     sweeps[p] += 1;
     if (conv[p] <= tol) done[p] = 1;
   }
@@ -453,20 +674,18 @@ __global__ void k_bj_check(float* conv, int* done, int* sweeps, float tol, int n
 
 // prepare: V = I, scale = max |diag|, flags reset; also symmetrise K and zero the padding
 __global__ void __launch_bounds__(NT)
-k_bj_prepare(float* __restrict__ K, float* __restrict__ V, int ld, long long stride, int n_pad,
+k_bj_prepare(float* __restrict__ K, int ld, long long stride, int n_pad,
              const int* __restrict__ n_dev, int n_fixed, float* __restrict__ scale,
              float* __restrict__ conv, int* __restrict__ done, int* __restrict__ sweeps) {
   __shared__ int redmax;
   const int prob = blockIdx.y;
   const int n = n_dev ? n_dev[prob] : n_fixed;
   float* Kg = K + (long long)prob * stride;
-  float* Vg = V + (long long)prob * stride;
   // each CTA of grid.x handles a slab of rows
   const int rows_per = (n_pad + gridDim.x - 1) / gridDim.x;
   const int r0 = blockIdx.x * rows_per, r1 = min(n_pad, r0 + rows_per);
   for (int r = r0; r < r1; ++r) {
     for (int c = threadIdx.x; c < n_pad; c += NT) {
-      Vg[(long long)r * ld + c] = (r == c) ? 1.f : 0.f;
       if (r >= n || c >= n) Kg[(long long)r * ld + c] = 0.f;
     }
   }
@@ -601,12 +820,14 @@ extern "C" int cpsd_eig_sym_small_f64(const double* A, int lda, long long stride
   return CPSD_OK;
 }
 
+// Block Jacobi eigen-solver for n_pad = multiple of 128 (> 128).  K is destroyed.
 // Workspace (device, caller-allocated):
-//   Rbuf  : nprob * (n_pad/128) * 128*128 floats
-//   fwork : 2 * nprob floats (scale, conv)
+//   Rlog  : nprob * max_sweeps * (nb-1) * (nb/2) * 128*128 floats, nb = n_pad/64 (rotation log)
+//   fwork : (2 + 16) * nprob floats (scale, conv, per-sweep convergence history)
 //   iwork : 2 * nprob ints (done, sweeps)
-//   pairs : (nb-1) * (nb/2) * 2 ints, round-robin schedule for nb = n_pad/64 blocks, as
-//           written by cpsd_bj_schedule().
+//   pairs : (nb-1) * (nb/2) * 2 ints, round-robin schedule as written by cpsd_bj_schedule().
+// Outputs: evals (descending) and perm (position of each eigenvalue on the diagonal); the
+// eigenvectors of any leading subset follow from cpsd_bj_eigvecs().
 extern "C" int cpsd_bj_schedule(int n_pad, int* pairs_host) {
   CPSD_CHECK_ARG(n_pad > 0 && n_pad % TS == 0, "bj_schedule: n_pad must be a multiple of 128");
   const int nb = n_pad / BS;
@@ -629,43 +850,91 @@ extern "C" int cpsd_bj_schedule(int n_pad, int* pairs_host) {
   return CPSD_OK;
 }
 
-extern "C" int cpsd_eig_sym_block(float* K, float* V, int ld, long long stride, int n_pad,
-                                  const int* n_dev, int n_fixed, int nprob, const int* pairs_dev,
-                                  float* Rbuf, float* fwork, int* iwork, float* evals, int* perm,
-                                  int ld_e, int max_sweeps, float tol, cudaStream_t stream) {
+#define BJ_HIST 16
+
+extern "C" long long cpsd_bj_rlog_elems(int n_pad, int nprob, int max_sweeps) {
+  const long long nb = n_pad / BS;
+  return (long long)nprob * max_sweeps * (nb - 1) * (nb / 2) * (TS * TS);
+}
+
+extern "C" int cpsd_eig_sym_block(float* K, int ld, long long stride, int n_pad, const int* n_dev,
+                                  int n_fixed, int nprob, const int* pairs_dev, float* Rlog,
+                                  float* fwork, int* iwork, float* evals, int* perm, int ld_e,
+                                  int max_sweeps, float tol, cudaStream_t stream) {
   CPSD_CHECK_ARG(n_pad > 0 && n_pad % TS == 0, "eig_sym_block: n_pad must be a multiple of 128");
   CPSD_CHECK_ARG(ld >= n_pad && ld_e >= n_pad, "eig_sym_block: ld < n_pad");
   if (nprob == 0) return CPSD_OK;
   const int nb = n_pad / BS, npairs = nb / 2, nrounds = nb - 1;
+  const int total_rounds = max_sweeps * nrounds;
   float* scale = fwork;
   float* conv = fwork + nprob;
+  float* hist = fwork + 2 * nprob;
   int* done = iwork;
   int* sweeps = iwork + nprob;
   const size_t smem_in = tile_smem_bytes();
   const size_t smem_up = (TS * LDX + TS * TS) * sizeof(float);
+  const size_t smem_cross = TS * TS * sizeof(float) + BS * 12 + TS * 4 + 16;
+  CPSD_CUDA(cudaFuncSetAttribute(k_bj_inner_cross, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem_cross));
   CPSD_CUDA(cudaFuncSetAttribute(k_bj_inner, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_in));
   CPSD_CUDA(cudaFuncSetAttribute(k_bj_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_up));
-  k_bj_prepare<<<dim3(16, nprob), NT, 0, stream>>>(K, V, ld, stride, n_pad, n_dev, n_fixed, scale,
-                                                   conv, done, sweeps);
+  k_bj_prepare<<<dim3(16, nprob), NT, 0, stream>>>(K, ld, stride, n_pad, n_dev, n_fixed, scale, conv,
+                                                   done, sweeps);
   CPSD_LAUNCH_CHECK();
   const int n_ktasks = npairs * (npairs - 1) / 2;
-  const int n_vtasks = (n_pad / TS) * npairs;
   for (int sw = 0; sw < max_sweeps; ++sw) {
     for (int r = 0; r < nrounds; ++r) {
       const int* pr = pairs_dev + (size_t)r * npairs * 2;
-      k_bj_inner<<<dim3(npairs, nprob), NT, smem_in, stream>>>(K, ld, stride, pr, Rbuf, scale, conv,
-                                                               done, r == 0 ? 1 : 0);
+      const int ridx = sw * nrounds + r;
+      if (r == 0)
+        k_bj_inner<<<dim3(npairs, nprob), NT, smem_in, stream>>>(K, ld, stride, pr, Rlog,
+                                                                 total_rounds, ridx, scale, conv,
+                                                                 done, 1);
+      else
+        k_bj_inner_cross<<<dim3(npairs, nprob), NT, smem_cross, stream>>>(
+            K, ld, stride, pr, Rlog, total_rounds, ridx, scale, conv, done);
       CPSD_LAUNCH_CHECK();
-      k_bj_update<<<dim3(n_ktasks + n_vtasks, nprob), NT, smem_up, stream>>>(
-          K, V, ld, stride, n_pad, pr, npairs, Rbuf, done);
-      CPSD_LAUNCH_CHECK();
+      if (n_ktasks > 0) {
+        k_bj_update<<<dim3(n_ktasks, nprob), NT, smem_up, stream>>>(K, ld, stride, pr, npairs, Rlog,
+                                                                    total_rounds, ridx, done);
+        CPSD_LAUNCH_CHECK();
+      }
     }
-    k_bj_check<<<(nprob + 127) / 128, 128, 0, stream>>>(conv, done, sweeps, fmaxf(tol, 2e-6f), nprob);
+    k_bj_check<<<(nprob + 127) / 128, 128, 0, stream>>>(conv, done, sweeps, hist, BJ_HIST,
+                                                        fmaxf(tol, 2e-6f), nprob);
     CPSD_LAUNCH_CHECK();
   }
   k_bj_extract<<<nprob, NT, n_pad * sizeof(float), stream>>>(K, ld, stride, n_dev, n_fixed, evals,
                                                              perm, ld_e);
   CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
+
+// Leading k eigenvectors (columns sorted like evals) from the rotation log of
+// cpsd_eig_sym_block: E (n_pad x lde, only the first k[prob] columns are written).
+// k_launch bounds the columns the grid covers (>= every k[prob]).
+extern "C" int cpsd_bj_eigvecs(const float* Rlog, int n_pad, int nprob, const int* pairs_dev,
+                               const int* iwork, const int* perm, int ld_perm, const int* k_dev,
+                               int k_fixed, int k_launch, float* E, int lde, long long strideE,
+                               int max_sweeps, cudaStream_t stream) {
+  CPSD_CHECK_ARG(n_pad > 0 && n_pad % TS == 0, "bj_eigvecs: n_pad must be a multiple of 128");
+  CPSD_CHECK_ARG(k_launch > 0 && k_launch <= lde, "bj_eigvecs: bad k_launch");
+  if (nprob == 0) return CPSD_OK;
+  const int nb = n_pad / BS, npairs = nb / 2, nrounds = nb - 1;
+  const int total_rounds = max_sweeps * nrounds;
+  const int* sweeps = iwork + nprob;
+  k_bj_einit<<<dim3(n_pad < 256 ? n_pad : 256, nprob), NT, 0, stream>>>(E, lde, strideE, n_pad, perm,
+                                                                        ld_perm, k_dev, k_fixed);
+  CPSD_LAUNCH_CHECK();
+  const size_t smem = (TS * LDX + TS * EC) * sizeof(float);
+  CPSD_CUDA(cudaFuncSetAttribute(k_bj_backapply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int nchunks = (k_launch + EC - 1) / EC;
+  for (int ridx = total_rounds - 1; ridx >= 0; --ridx) {
+    const int* pr = pairs_dev + (size_t)(ridx % nrounds) * npairs * 2;
+    k_bj_backapply<<<dim3(npairs * nchunks, nprob), NT, smem, stream>>>(
+        E, lde, strideE, pr, npairs, Rlog, total_rounds, ridx, nrounds, sweeps, k_dev, k_fixed);
+    CPSD_LAUNCH_CHECK();
+  }
   return CPSD_OK;
 }
 

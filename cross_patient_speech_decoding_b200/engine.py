@@ -147,21 +147,32 @@ class CVEngine:
                       ptr(evals), evals.shape[-1], ptr(evecs), ldv, ldv * ldv if evecs is not None
                       else 0, self.eig_sweeps + 3, self.eig_tol, ptr(None))
 
-    def eig_block(self, K, V, n_pad, n_dev, n_fixed, nprob, evals, perm, tag):
-        """K, V: (nprob, n_pad, n_pad).  K is destroyed; V columns perm[j] are eigenvectors."""
-        R = self.ws(tag + '_R', (nprob, n_pad // 128, 128 * 128))
-        fw = self.ws(tag + '_fw', (2 * nprob,))
+    def eig_block(self, K, n_pad, n_dev, n_fixed, nprob, evals, perm, tag):
+        """K: (nprob, n_pad, n_pad), destroyed.  Eigenvalues (descending) + diagonal positions;
+        eigenvectors come from eig_vecs() (rotation-log replay)."""
+        nlog = int(self.ctx.lib.cpsd_bj_rlog_elems(n_pad, nprob, self.eig_sweeps))
+        R = self.ws(tag + '_Rlog', (nlog,))
+        fw = self.ws(tag + '_fw', (18 * nprob,))
         iw = self.ws(tag + '_iw', (2 * nprob,), I32)
-        self.ctx.call('cpsd_eig_sym_block', ptr(K), ptr(V), n_pad, n_pad * n_pad, n_pad,
-                      _p(n_dev), n_fixed, nprob, ptr(self.schedule(n_pad)), ptr(R), ptr(fw),
-                      ptr(iw), ptr(evals), ptr(perm), evals.shape[-1], self.eig_sweeps,
-                      self.eig_tol)
+        self.ctx.call('cpsd_eig_sym_block', ptr(K), n_pad, n_pad * n_pad, n_pad, _p(n_dev),
+                      n_fixed, nprob, ptr(self.schedule(n_pad)), ptr(R), ptr(fw), ptr(iw),
+                      ptr(evals), ptr(perm), evals.shape[-1], self.eig_sweeps, self.eig_tol)
         return iw
+
+    def eig_vecs(self, tag, n_pad, nprob, perm, k_dev, k_fixed, k_launch, E):
+        """Leading eigenvectors (sorted columns) of the last eig_block(tag) call into E
+        (nprob, n_pad, n_pad)."""
+        R = self._ws[tag + '_Rlog']
+        iw = self._ws[tag + '_iw']
+        self.ctx.call('cpsd_bj_eigvecs', ptr(R), n_pad, nprob, ptr(self.schedule(n_pad)), ptr(iw),
+                      ptr(perm), n_pad, _p(k_dev), k_fixed, k_launch, ptr(E), n_pad, n_pad * n_pad,
+                      self.eig_sweeps)
 
     def eig_any(self, A, n_pad, n_dev, n_fixed, nprob, tag, ncols=None):
         """Sorted eigen-decomposition for any n_pad (A: (nprob, n_pad, n_pad), destroyed).
         A float64 tensor (n_pad <= 128 only) selects the fp64-matrix solver.
-        Returns (evals (nprob, n_pad), evecs (nprob, n_pad, n_pad) with sorted columns)."""
+        Returns (evals (nprob, n_pad), evecs (nprob, n_pad, n_pad) with sorted columns; for
+        n_pad > 128 only the leading ``ncols`` columns are computed)."""
         evals = self.ws(tag + '_ev', (nprob, n_pad))
         evecs = self.ws(tag + '_evec', (nprob, n_pad, n_pad))
         if A.dtype == torch.float64:
@@ -173,12 +184,10 @@ class CVEngine:
         if n_pad <= 128:
             self.eig_small(A, n_dev, n_fixed, nprob, n_pad, evals, evecs, n_pad)
             return evals, evecs
-        V = self.ws(tag + '_V', (nprob, n_pad, n_pad))
         perm = self.ws(tag + '_perm', (nprob, n_pad), I32)
-        self.eig_block(A, V, n_pad, n_dev, n_fixed, nprob, evals, perm, tag)
+        self.eig_block(A, n_pad, n_dev, n_fixed, nprob, evals, perm, tag)
         nc = n_pad if ncols is None else ncols
-        self.ctx.call('cpsd_permute_cols', ptr(V), n_pad, n_pad * n_pad, ptr(perm), n_pad,
-                      ptr(evecs), n_pad, n_pad * n_pad, n_pad, nc, nprob)
+        self.eig_vecs(tag, n_pad, nprob, perm, ptr(None), nc, nc, evecs)
         return evals, evecs
 
     def scatter(self, name, nprob, n_pad):
@@ -410,24 +419,25 @@ class CVEngine:
         evals = self.ws('pool_ev', (B, n_pad))
         k2 = self.ws('pool_k2', (B,), I32)
         kcap = min(n_pad, F)
-        if n_pad <= 128:
-            V = self.ws('pool_V', (B, n_pad, n_pad))
-            # zero the test rows/cols: the tile solver reads only the leading n x n block
-            self.eig_small(Kall, npool_dev, 0, B, n_pad, evals, V, n_pad)
-            perm_p = ptr(None)
-            sweeps = None
-        else:
-            V = self.ws('pool_V', (B, n_pad, n_pad))
-            perm = self.ws('pool_perm', (B, n_pad), I32)
-            sweeps = self.eig_block(Kall, V, n_pad, npool_dev, 0, B, evals, perm, 'pool')
-            perm_p = ptr(perm)
         if isinstance(self.decoder_var, (float, np.floating)) and 0 < self.decoder_var < 1:
             mode, thr = 0, float(self.decoder_var)
         else:
             mode, thr = 3, float(int(self.decoder_var))
-        self.mark('pool_scores')
+        V = self.ws('pool_V', (B, n_pad, n_pad))
+        if n_pad <= 128:
+            self.eig_small(Kall, npool_dev, 0, B, n_pad, evals, V, n_pad)
+            sweeps = None
+        else:
+            perm = self.ws('pool_perm', (B, n_pad), I32)
+            sweeps = self.eig_block(Kall, n_pad, npool_dev, 0, B, evals, perm, 'pool')
+        self.mark('pool_eigvecs')
         ctx.call('cpsd_select_k', ptr(evals), n_pad, npool_dev, 0, thr, mode, 1, kcap, ptr(k2), 1,
                  B)
+        if n_pad > 128:
+            # eigenvectors of the k2 retained components only (rotation-log replay)
+            self.eig_vecs('pool', n_pad, B, perm, k2, 0, kcap, V)
+        self.mark('pool_scores')
+        perm_p = ptr(None)
         St = self.ws('pool_St', (B, kcap, n_pad))
         Ste = self.ws('pool_Ste', (B, kcap, n_te_max))
         ctx.call('cpsd_scores_train', ptr(V), n_pad, n_pad * n_pad, ptr(evals), perm_p, n_pad,

@@ -57,18 +57,17 @@ def eig_sym(A, n=None, max_sweeps=15, tol=3e-7, device=None, return_sweeps=False
         sched = np.zeros((nb - 1) * (nb // 2) * 2, dtype=np.int32)
         _lib.check(ctx.lib.cpsd_bj_schedule(n_pad, sched.ctypes.data), 'bj_schedule')
         sd = ctx.upload(sched)
-        V = ctx.empty((nprob, n_pad, n_pad))
-        R = ctx.empty((nprob, n_pad // 128, 128 * 128))
-        fw = ctx.empty((2 * nprob,))
+        R = ctx.empty((int(ctx.lib.cpsd_bj_rlog_elems(n_pad, nprob, max_sweeps)),))
+        fw = ctx.zeros((18 * nprob,))
         perm = ctx.empty((nprob, n_pad), I32)
-        ctx.call('cpsd_eig_sym_block', ptr(Ad), ptr(V), n_pad, n_pad * n_pad, n_pad, ptr(nd), 0,
-                 nprob, ptr(sd), ptr(R), ptr(fw), ptr(sw), ptr(evals), ptr(perm), n_pad, max_sweeps,
-                 tol)
-        evecs = ctx.empty((nprob, n_pad, n_pad))
-        ctx.call('cpsd_permute_cols', ptr(V), n_pad, n_pad * n_pad, ptr(perm), n_pad, ptr(evecs),
-                 n_pad, n_pad * n_pad, n_pad, n_pad, nprob)
+        ctx.call('cpsd_eig_sym_block', ptr(Ad), n_pad, n_pad * n_pad, n_pad, ptr(nd), 0, nprob,
+                 ptr(sd), ptr(R), ptr(fw), ptr(sw), ptr(evals), ptr(perm), n_pad, max_sweeps, tol)
+        evecs = ctx.zeros((nprob, n_pad, n_pad))
+        ctx.call('cpsd_bj_eigvecs', ptr(R), n_pad, nprob, ptr(sd), ptr(sw), ptr(perm), n_pad,
+                 ptr(None), n_pad, n_pad, ptr(evecs), n_pad, n_pad * n_pad, max_sweeps)
         ev, V = evals.cpu().numpy(), evecs.cpu().numpy()
         sweeps = sw.cpu().numpy()[nprob:2 * nprob]
+        eig_sym.last_history = fw.cpu().numpy()[2 * nprob:].reshape(nprob, 16)
     ev, V = ev[:, :nn], V[:, :nn, :nn]
     if single:
         ev, V, sweeps = ev[0], V[0], sweeps[0]

@@ -100,12 +100,20 @@ int cpsd_eig_sym_small_f64(const double* A, int lda, long long strideA, const in
                            int n_fixed, int nprob, float* evals, int ld_e, float* evecs, int ldv,
                            long long strideV, int max_sweeps, float tol, int* sweeps_out,
                            cudaStream_t stream);
-/* block Jacobi for n > 128 (n_pad multiple of 128): pooled-Gram PCA, large GEVPs */
+/* block two-sided Jacobi for n > 128 (n_pad multiple of 128): pooled-Gram PCA, large GEVPs.
+ * Every round's 128x128 tile rotations are kept in a rotation log (Rlog,
+ * cpsd_bj_rlog_elems() floats); cpsd_bj_eigvecs replays them on the identity columns of the
+ * leading k eigenvalues only, instead of accumulating all n eigenvectors every round. */
 int cpsd_bj_schedule(int n_pad, int* pairs_host);
-int cpsd_eig_sym_block(float* K, float* V, int ld, long long stride, int n_pad, const int* n_dev,
-                       int n_fixed, int nprob, const int* pairs_dev, float* Rbuf, float* fwork,
+long long cpsd_bj_rlog_elems(int n_pad, int nprob, int max_sweeps);
+int cpsd_eig_sym_block(float* K, int ld, long long stride, int n_pad, const int* n_dev,
+                       int n_fixed, int nprob, const int* pairs_dev, float* Rlog, float* fwork,
                        int* iwork, float* evals, int* perm, int ld_e, int max_sweeps, float tol,
                        cudaStream_t stream);
+int cpsd_bj_eigvecs(const float* Rlog, int n_pad, int nprob, const int* pairs_dev,
+                    const int* iwork, const int* perm, int ld_perm, const int* k_dev, int k_fixed,
+                    int k_launch, float* E, int lde, long long strideE, int max_sweeps,
+                    cudaStream_t stream);
 /* component counts: sklearn PCA float n_components (mode 0), AlignMCCA.n_components_var
  * (mode 1, AlignMCCA.py:174), NoCenterPCA (mode 2, NoCenterPCA.py:101-103), integer (mode 3) */
 int cpsd_select_k(const float* evals, int ld_e, const int* n_dev, int n_fixed, float thr, int mode,

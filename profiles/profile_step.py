@@ -1,0 +1,32 @@
+"""One warm-up step + N measured steps of the headline workload (bench.py's step), for ncu.
+Usage: python profiles/profile_step.py [--steps N] [--no-tc] [--folds F]"""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument('--steps', type=int, default=1)
+ap.add_argument('--folds', type=int, default=20)
+ap.add_argument('--no-tc', action='store_true')
+ap.add_argument('--stages', action='store_true')
+a = ap.parse_args()
+from cross_patient_speech_decoding_b200.engine import CVEngine  # noqa: E402
+pts = bench.make_data()
+eng = CVEngine(pts[0], pts[1:], method='mcca', n_comp=30, regs=0.5, pca_var=0.8,
+               use_tensor_cores=not a.no_tc, max_batch=a.folds)
+folds = bench.step_folds(pts[0][1], 1)[:a.folds]
+eng.run(folds)
+for s in range(a.steps):
+    eng.profile = a.stages
+    res = eng.run(bench.step_folds(pts[0][1], 2 + s)[:a.folds], return_details=True)
+    if a.stages:
+        print('stages_ms', {k: round(v, 3) for k, v in eng.collect_marks().items()})
+    print('k2', res['k2'][:4], 'bj_sweeps', res['details'][0]['bj_sweeps'],
+          'svm_newton_max', int(res['details'][0]['svm_info'][..., 0].max()),
+          'launches', eng.stats['launches_last_batch'])
+    B = len(res['k2'])
+    print('conv_history fold0', eng._ws['pool_fw'][2 * B:2 * B + 16].cpu().numpy())

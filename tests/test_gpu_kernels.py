@@ -69,7 +69,7 @@ def test_eig_block_pooled_spectrum(ops):
     assert np.abs(ev - ref_w).max() <= 3e-5 * ref_w[0]
     k = 6                              # the well-separated signal subspace
     s = np.linalg.svd(ref_v[:, :k].T @ V[:, :k], compute_uv=False)
-    assert s.min() > 1 - 1e-6
+    assert s.min() > 1 - 5e-6
     assert np.abs(K @ V - V * ev).max() <= 1e-4 * ref_w[0]   # residual of every eigen-pair
     assert np.abs(V.T @ V - np.eye(n)).max() < 1e-4
 
