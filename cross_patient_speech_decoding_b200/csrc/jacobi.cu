@@ -605,7 +605,7 @@ k_bj_einit(float* __restrict__ E, int lde, long long strideE, int n_pad,
     for (int j = threadIdx.x; j < k; j += NT) Ep[(long long)r * lde + j] = (pp[j] == r) ? 1.f : 0.f;
 }
 
-#define EC 64
+#define EC 32
 __global__ void __launch_bounds__(NT)
 k_bj_backapply(float* __restrict__ E, int lde, long long strideE, const int* __restrict__ pairs,
                int npairs, const float* __restrict__ Rlog, int total_rounds, int round_idx,
@@ -618,43 +618,40 @@ k_bj_backapply(float* __restrict__ E, int lde, long long strideE, const int* __r
   if (round_idx >= sweeps[prob] * nrounds) return;
   int k = k_dev ? k_dev[prob] : k_fixed;
   if (k > lde) k = lde;
-  const int pr = blockIdx.x % npairs, chunk = blockIdx.x / npairs;
-  const int c0 = chunk * EC;
-  if (c0 >= k) return;
+  const int pr = blockIdx.x;
   const int I = pairs[2 * pr], J = pairs[2 * pr + 1];
   float* Ep = E + (long long)prob * strideE;
   const float* Rg = Rlog + (((long long)prob * total_rounds + round_idx) * npairs + pr) * (TS * TS);
   for (int e = threadIdx.x; e < TS * TS; e += NT) Rs[(e >> 7) * LDX + (e & (TS - 1))] = Rg[e];
-  for (int e = threadIdx.x; e < TS * EC; e += NT) {
-    const int r = e / EC, c = e - r * EC;
-    Es[e] = (c0 + c < k) ? Ep[(long long)tile_gidx(r, I, J) * lde + c0 + c] : 0.f;
-  }
-  __syncthreads();
-  // 128 x 64 outputs, 256 threads: thread -> rows ty + 16 i (i < 8), cols tx + 16 j (j < 4)
+  // 128 x 32 outputs per chunk, 256 threads: rows ty + 16 i (i < 8), cols tx + 16 j (j < 2)
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  float acc[8][4];
+  for (int c0 = 0; c0 < k; c0 += EC) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < TS * EC; e += NT) {
+      const int r = e / EC, c = e - r * EC;
+      Es[e] = (c0 + c < k) ? Ep[(long long)tile_gidx(r, I, J) * lde + c0 + c] : 0.f;
+    }
+    __syncthreads();
+    float acc[8][2];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 8; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; }
+#pragma unroll 4
+    for (int kk = 0; kk < TS; ++kk) {
+      float a[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int kk = 0; kk < TS; ++kk) {
-    float a[8], b[4];
+      for (int i = 0; i < 8; ++i) a[i] = Rs[(ty + 16 * i) * LDX + kk];
+      const float b0 = Es[kk * EC + tx], b1 = Es[kk * EC + tx + 16];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = Rs[(ty + 16 * i) * LDX + kk];
+      for (int i = 0; i < 8; ++i) {
+        acc[i][0] = fmaf(a[i], b0, acc[i][0]);
+        acc[i][1] = fmaf(a[i], b1, acc[i][1]);
+      }
+    }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) b[j] = Es[kk * EC + tx + 16 * j];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int gr = tile_gidx(ty + 16 * i, I, J);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = c0 + tx + 16 * j;
-      if (c < k) Ep[(long long)gr * lde + c] = acc[i][j];
+    for (int i = 0; i < 8; ++i) {
+      const int gr = tile_gidx(ty + 16 * i, I, J);
+      if (c0 + tx < k) Ep[(long long)gr * lde + c0 + tx] = acc[i][0];
+      if (c0 + tx + 16 < k) Ep[(long long)gr * lde + c0 + tx + 16] = acc[i][1];
     }
   }
 }
@@ -928,10 +925,9 @@ extern "C" int cpsd_bj_eigvecs(const float* Rlog, int n_pad, int nprob, const in
   CPSD_LAUNCH_CHECK();
   const size_t smem = (TS * LDX + TS * EC) * sizeof(float);
   CPSD_CUDA(cudaFuncSetAttribute(k_bj_backapply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int nchunks = (k_launch + EC - 1) / EC;
   for (int ridx = total_rounds - 1; ridx >= 0; --ridx) {
     const int* pr = pairs_dev + (size_t)(ridx % nrounds) * npairs * 2;
-    k_bj_backapply<<<dim3(npairs * nchunks, nprob), NT, smem, stream>>>(
+    k_bj_backapply<<<dim3(npairs, nprob), NT, smem, stream>>>(
         E, lde, strideE, pr, npairs, Rlog, total_rounds, ridx, nrounds, sweeps, k_dev, k_fixed);
     CPSD_LAUNCH_CHECK();
   }

@@ -168,7 +168,7 @@ class CVEngine:
                       ptr(perm), n_pad, _p(k_dev), k_fixed, k_launch, ptr(E), n_pad, n_pad * n_pad,
                       self.eig_sweeps)
 
-    def eig_any(self, A, n_pad, n_dev, n_fixed, nprob, tag, ncols=None):
+    def eig_any(self, A, n_pad, n_dev, n_fixed, nprob, tag, ncols=None, vecs=True):
         """Sorted eigen-decomposition for any n_pad (A: (nprob, n_pad, n_pad), destroyed).
         A float64 tensor (n_pad <= 128 only) selects the fp64-matrix solver.
         Returns (evals (nprob, n_pad), evecs (nprob, n_pad, n_pad) with sorted columns; for
@@ -178,8 +178,8 @@ class CVEngine:
         if A.dtype == torch.float64:
             assert n_pad <= 128
             self.ctx.call('cpsd_eig_sym_small_f64', ptr(A), n_pad, n_pad * n_pad, _p(n_dev),
-                          n_fixed, nprob, ptr(evals), n_pad, ptr(evecs), n_pad, n_pad * n_pad,
-                          self.eig_sweeps + 6, 1e-10, ptr(None))
+                          n_fixed, nprob, ptr(evals), n_pad, ptr(evecs if vecs else None), n_pad,
+                          n_pad * n_pad, self.eig_sweeps + 6, 1e-10, ptr(None))
             return evals, evecs
         if n_pad <= 128:
             self.eig_small(A, n_dev, n_fixed, nprob, n_pad, evals, evecs, n_pad)
@@ -264,7 +264,7 @@ class CVEngine:
         pk.upload()
         ctx.call(gram, pk.daddr(d), len(vs), Cm, Cm)
         cd = ctypes_int_ptr(pk.iaddr(cdim))
-        evals, _ = self.eig_any(G, n_pad, cd, 0, len(vs), 'rk')
+        evals, _ = self.eig_any(G, n_pad, cd, 0, len(vs), 'rk', vecs=False)
         k = self.ws('rk_k', (len(vs),), I32)
         ctx.call('cpsd_select_k', ptr(evals), n_pad, cd, 0, float(self.pca_var), 1, 0, 1 << 30,
                  ptr(k), 1, len(vs))
@@ -434,8 +434,10 @@ class CVEngine:
         ctx.call('cpsd_select_k', ptr(evals), n_pad, npool_dev, 0, thr, mode, 1, kcap, ptr(k2), 1,
                  B)
         if n_pad > 128:
-            # eigenvectors of the k2 retained components only (rotation-log replay)
-            self.eig_vecs('pool', n_pad, B, perm, k2, 0, kcap, V)
+            # eigenvectors of the k2 retained components only (rotation-log replay); one small
+            # read-back sizes the replay grid to the columns actually kept
+            k_launch = min(kcap, _ceil(max(int(k2.cpu().numpy().max()), 1), 64))
+            self.eig_vecs('pool', n_pad, B, perm, k2, 0, k_launch, V)
         self.mark('pool_scores')
         perm_p = ptr(None)
         St = self.ws('pool_St', (B, kcap, n_pad))
@@ -582,7 +584,13 @@ class CVEngine:
                       1, 1.0, 0)
         d_pz, d_g = pk.add_descs(r_pz), pk.add_descs(r_g)
         # pooled projection
-        n_padM = 128 if P * R <= 128 else _ceil(P * R, 128)
+        # size of the reduced GEVP: the target's rank is only known on the device (<= R), the
+        # cross patients' ranks are fold-invariant and known here
+        if use_rank:
+            n_m_max = R + int(np.minimum(self.cross_rank, R).sum())
+        else:
+            n_m_max = sum(min(R, vw.C) for vw in self.views)
+        n_padM = 128 if n_m_max <= 128 else _ceil(n_m_max, 128)
         L = self.ws('m_L', (B * P, Cm, Q))
         Zall = self.ws('pool_Z', (B, n_pad, F))
         r_pp = np.zeros(B * P + B, dtype=_lib.PROJ_DESC)
@@ -626,7 +634,7 @@ class CVEngine:
         self.mark('align_scatter_eig')
         if use_rank:
             ctx.call(gram_c, pk.daddr(d_gt), B, tv.C, tv.C)
-            ev_t, _ = self.eig_any(Gt, n_padC, ptr(None), tv.C, B, 'mrk')
+            ev_t, _ = self.eig_any(Gt, n_padC, ptr(None), tv.C, B, 'mrk', vecs=False)
             ctx.call('cpsd_select_k', ptr(ev_t), n_padC, ptr(None), tv.C, float(self.pca_var), 1,
                      0, 1 << 30, ptr(rank_dev), P, B)
         # per-view centred scatter of the condition averages + eigen-decomposition
