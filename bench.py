@@ -155,12 +155,13 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=8)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours')
     ap.add_argument('--no-tc', action='store_true', help='fp32 SIMT pooled Gram instead of tcgen05')
     ap.add_argument('--cpu-folds', type=int, default=2, help='folds in the cpu_baseline sample')
     ap.add_argument('--e2e-steps', type=int, default=None)
+    ap.add_argument('--batch', type=int, default=32, help='folds per engine batch')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -184,16 +185,24 @@ def main():
     pts = make_data()
     y0 = pts[0][1]
     kw = dict(method='mcca', n_comp=30, regs=0.5, pca_var=0.8, decoder_var=0.8,
-              use_tensor_cores=not args.no_tc, max_batch=N_FOLDS)
+              use_tensor_cores=not args.no_tc, max_batch=args.batch)
     eng = CVEngine(pts[0], pts[1:], device='cuda:%d' % local, **kw)
     dev = eng.ctx.device
 
-    def one_step(sid):
-        folds = step_folds(y0, sid)
+    def run_steps(sids):
+        """K steps = K CV iterations of 20 folds; the iterations are independent units, so all
+        their folds go to the engine in one call and are batched `--batch` at a time."""
+        folds = []
+        for sid in sids:
+            folds += step_folds(y0, sid)
         res = eng.run(folds)
-        ok = sum(int((p == y0[te]).sum()) for p, (_, te) in zip(res['y_pred'], folds))
-        tot = sum(len(te) for _, te in folds)
-        return res, ok, tot
+        accs = []
+        for i in range(len(sids)):
+            fs = folds[i * N_FOLDS:(i + 1) * N_FOLDS]
+            ps = res['y_pred'][i * N_FOLDS:(i + 1) * N_FOLDS]
+            ok = sum(int((p == y0[te]).sum()) for p, (_, te) in zip(ps, fs))
+            accs.append(ok / sum(len(te) for _, te in fs))
+        return res, accs
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -201,8 +210,8 @@ def main():
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    for w in range(args.warmup):
-        one_step(10_000 + rank * 1000 + w)
+    if args.warmup:
+        run_steps([10_000 + rank * 1000 + w for w in range(args.warmup)])
     sync_all()
     eng.ctx.lib.cpsd_reset_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -210,18 +219,15 @@ def main():
     with ClockSampler(local) as clk:
         sync_all()
         e0.record(torch.cuda.current_stream(dev))
-        for s in range(args.steps):
-            res, ok, tot = one_step(rank * 100_000 + s)
-            accs.append(ok / tot)
-            h2d += res['h2d_bytes']
-            d2h += res['d2h_bytes']
-        acc_t = torch.tensor(accs, dtype=torch.float32, device=dev)
-        if world > 1:   # the one collective of the path: gather per-iteration accuracies
-            gathered = [torch.empty_like(acc_t) for _ in range(world)]
-            dist.all_gather(gathered, acc_t)
-            acc_all = torch.cat(gathered).cpu().numpy()
-        else:
-            acc_all = acc_t.cpu().numpy()
+        res, accs = run_steps([rank * 100_000 + s for s in range(args.steps)])
+        h2d += res['h2d_bytes']
+        d2h += res['d2h_bytes']
+        # the one collective of the path: gather fixed-size per-iteration records
+        from cross_patient_speech_decoding_b200.sharding import gather_records
+        rec = np.array([[rank * args.steps + i, int(round(a * 1e6))] for i, a in enumerate(accs)],
+                       dtype=np.int32).reshape(-1, 2)
+        allrec = gather_records(rec, device=dev)
+        acc_all = allrec[:, 1] / 1e6
         e1.record(torch.cuda.current_stream(dev))
         sync_all()
     ms = e0.elapsed_time(e1)
@@ -254,7 +260,7 @@ def main():
 
     # ---- stage breakdown + roofline of the dominant tensor / HBM kernels (profiling pass)
     eng.profile = True
-    one_step(424242)
+    eng.run(step_folds(y0, 424242))
     stages = eng.collect_marks()
     eng.profile = False
     pk, pk_kind = peaks()
@@ -291,6 +297,7 @@ def main():
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'folds_per_step_per_gpu': N_FOLDS,
+                       'engine_batch_folds': args.batch,
                        'parallelism': 'folds sharded over %d GPU(s), one NCCL all_gather of '
                                       'accuracies' % world,
                        'precision': 'fp32 storage; fp64 scatter+eigen for PCA stages; 3xTF32 '

@@ -60,7 +60,7 @@ class CVEngine:
     """See module docstring.  ``method``: 'mcca' | 'cca' | 'none'."""
 
     def __init__(self, target, cross, method='mcca', n_comp=None, regs=0.5, pca_var=0.8,
-                 decoder_var=0.8, C=1.0, tar_in_train=True, device=None, max_batch=24,
+                 decoder_var=0.8, C=1.0, tar_in_train=True, device=None, max_batch=32,
                  dcd_epochs=2, max_newton=60, tol_newton=1e-9, tol_dcd=1e-4,
                  eig_sweeps=12, eig_tol=3e-7, use_tensor_cores=False):
         self.ctx = Context.get(device)
@@ -321,8 +321,10 @@ class CVEngine:
         ``y_pred`` (list of arrays, one per fold) and per-fold diagnostics."""
         out = {'y_pred': [], 'k2': [], 'h2d_bytes': 0, 'd2h_bytes': 0}
         details = []
-        for s in range(0, len(folds), self.max_batch):
-            batch = folds[s:s + self.max_batch]
+        nb = max(1, -(-len(folds) // self.max_batch))
+        size = -(-len(folds) // nb)          # balanced batches (a short tail batch costs as much
+        for s in range(0, len(folds), size):  # as a full one: the solvers are latency-bound)
+            batch = folds[s:s + size]
             if self.method == 'mcca':
                 res = self._batch_mcca(batch, return_details)
             else:
@@ -336,6 +338,12 @@ class CVEngine:
         if return_details:
             out['details'] = details
         return out
+
+    def align_mcca(self, train_idx=None):
+        """MCCA fit only (AlignMCCA.fit): loadings, view means and generalised eigenvalues for
+        the target's ``train_idx`` trials (default: all) pooled with the cross patients."""
+        tr = np.arange(self.views[0].N) if train_idx is None else np.asarray(train_idx)
+        return self._batch_mcca([(tr, np.zeros(0, dtype=np.int64))], False, align_only=True)
 
     # ------------------------------------------------------------------ shared host prep
     def _target_tables(self, pk, batch):
@@ -466,7 +474,7 @@ class CVEngine:
         return W, info, recs
 
     # ------------------------------------------------------------------ MCCA batch
-    def _batch_mcca(self, batch, want_details):
+    def _batch_mcca(self, batch, want_details, align_only=False):
         ctx, T, P, Cm = self.ctx, self.T, self.P, self.Cmax
         B = len(batch)
         Q = int(self.n_comp)
@@ -592,34 +600,35 @@ class CVEngine:
             n_m_max = sum(min(R, vw.C) for vw in self.views)
         n_padM = 128 if n_m_max <= 128 else _ceil(n_m_max, 128)
         L = self.ws('m_L', (B * P, Cm, Q))
-        Zall = self.ws('pool_Z', (B, n_pad, F))
-        r_pp = np.zeros(B * P + B, dtype=_lib.PROJ_DESC)
-        for f, tb in enumerate(tabs):
-            for v in range(P):
-                vw = self.views[v]
-                i = f * P + v
-                if v == 0:
-                    nseg = n_tr[f] if self.tar_in_train else 0
-                    src = pk.iaddr(tb['o_tr'])
-                else:
-                    nseg, src = vw.N, pk.iaddr(o_allseg[v])
-                r_pp[i] = (addr(vw.X), src, pk.iaddr(o_pooldst[f, v]), addr(mu, i * Cm),
-                           addr(L, i * Cm * Q), addr(Zall, f * n_pad * F), nseg, T, vw.C, Q, vw.C,
-                           Q, Q, 0)
-            r_pp[B * P + f] = (addr(tv.X), pk.iaddr(tb['o_te']), pk.iaddr(o_tedst[f]),
-                               addr(mu, f * P * Cm), addr(L, f * P * Cm * Q),
-                               addr(Zall, f * n_pad * F), n_te[f], T, tv.C, Q, tv.C, Q, Q, 0)
-        d_pp = pk.add_descs(r_pp)
-        r1, r2, pmu, Kall = self._pooled_stage(pk, B, Zall, n_pad, F, n_pool, n_te, o_npool,
-                                               o_nall, o_ypool, n_pad, n_te_max, want_details)
-        d_p1, d_p2 = pk.add_descs(r1), pk.add_descs(r2)
-        kcap = min(n_pad, F)
-        # SVM descriptors need k2 / St addresses only (known now)
-        St = self.ws('pool_St', (B, kcap, n_pad))
-        k2 = self.ws('pool_k2', (B,), I32)
-        W, info, r_svm = self._svm_stage(pk, B, St, None, k2, kcap, n_pad, n_pool, n_te, o_ypool,
-                                         n_pad, o_nte, n_te_max)
-        d_svm = pk.add_descs(r_svm)
+        if not align_only:
+            Zall = self.ws('pool_Z', (B, n_pad, F))
+            r_pp = np.zeros(B * P + B, dtype=_lib.PROJ_DESC)
+            for f, tb in enumerate(tabs):
+                for v in range(P):
+                    vw = self.views[v]
+                    i = f * P + v
+                    if v == 0:
+                        nseg = n_tr[f] if self.tar_in_train else 0
+                        src = pk.iaddr(tb['o_tr'])
+                    else:
+                        nseg, src = vw.N, pk.iaddr(o_allseg[v])
+                    r_pp[i] = (addr(vw.X), src, pk.iaddr(o_pooldst[f, v]), addr(mu, i * Cm),
+                               addr(L, i * Cm * Q), addr(Zall, f * n_pad * F), nseg, T, vw.C, Q, vw.C,
+                               Q, Q, 0)
+                r_pp[B * P + f] = (addr(tv.X), pk.iaddr(tb['o_te']), pk.iaddr(o_tedst[f]),
+                                   addr(mu, f * P * Cm), addr(L, f * P * Cm * Q),
+                                   addr(Zall, f * n_pad * F), n_te[f], T, tv.C, Q, tv.C, Q, Q, 0)
+            d_pp = pk.add_descs(r_pp)
+            r1, r2, pmu, Kall = self._pooled_stage(pk, B, Zall, n_pad, F, n_pool, n_te, o_npool,
+                                                   o_nall, o_ypool, n_pad, n_te_max, want_details)
+            d_p1, d_p2 = pk.add_descs(r1), pk.add_descs(r2)
+            kcap = min(n_pad, F)
+            # SVM descriptors need k2 / St addresses only (known now)
+            St = self.ws('pool_St', (B, kcap, n_pad))
+            k2 = self.ws('pool_k2', (B,), I32)
+            W, info, r_svm = self._svm_stage(pk, B, St, None, k2, kcap, n_pad, n_pool, n_te, o_ypool,
+                                             n_pad, o_nte, n_te_max)
+            d_svm = pk.add_descs(r_svm)
         pk.upload()
 
         # ---- launches
@@ -660,6 +669,14 @@ class CVEngine:
         evm, U = self.eig_any(M, n_padM, ptr(n_m), 0, B, 'mm', ncols=Q)
         ctx.call('cpsd_mcca_loadings', ptr(Vr), ptr(U), n_padM, n_padM * n_padM, ptr(None), 0,
                  ptr(r_eff), ptr(dh), P, R, Cm, Q, ptr(L), Q, B)
+        if align_only:
+            torch.cuda.synchronize(self.ctx.device)
+            st = status.cpu().numpy()
+            if st.any():
+                raise ValueError('MCCA: n_components=%d exceeds the total signal rank' % Q)
+            return dict(loadings=L.view(B, P, Cm, Q).cpu().numpy(),
+                        mu=mu.view(B, P, Cm).cpu().numpy(), evals_mcca=evm[:, :Q].cpu().numpy(),
+                        r_eff=r_eff.view(B, P).cpu().numpy(), shared=[s_.copy() for s_ in shared])
         # project every trial of every view into the pooled (trial x time*Q) matrix
         self.mark('project_pool')
         ctx.call('cpsd_proj_nn', ctypes_off(pk.daddr(d_pp), 0), B * P + B,

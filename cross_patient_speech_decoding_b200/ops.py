@@ -87,7 +87,7 @@ def select_k(evals, thr, mode, n=None, kmin=0, kmax=1 << 30, device=None):
 
 
 def gram_tn(A, B=None, seg_rows=None, seg_len=None, muA=None, muB=None, alpha=1.0, sym=None,
-            device=None):
+            device=None, f64=False):
     """out = alpha * sum over the selected rows of (a - muA)^T (b - muB).
     A: (rows, p); B: (rows, q) or None (= A).  seg_rows: first row of each segment."""
     ctx = _ctx(device)
@@ -105,7 +105,7 @@ def gram_tn(A, B=None, seg_rows=None, seg_len=None, muA=None, muB=None, alpha=1.
     ma = ctx.upload(np.asarray(muA, dtype=np.float32)) if muA is not None else None
     mb = ma if (same and muB is None) else (ctx.upload(np.asarray(muB, dtype=np.float32))
                                             if muB is not None else None)
-    out = ctx.zeros((p, q))
+    out = ctx.zeros((p, q), F64 if f64 else F32)
     if sym is None:
         sym = same and (muB is None)
     rec = np.zeros(1, dtype=_lib.GRAM_TN_DESC)
@@ -113,7 +113,7 @@ def gram_tn(A, B=None, seg_rows=None, seg_len=None, muA=None, muB=None, alpha=1.
               len(seg_rows), int(seg_len), p, q, p, q, q, int(bool(sym)), float(alpha), 0)
     d = pk.add_descs(rec)
     pk.upload()
-    ctx.call('cpsd_gram_tn', pk.daddr(d), 1, p, q)
+    ctx.call('cpsd_gram_tn_f64' if f64 else 'cpsd_gram_tn', pk.daddr(d), 1, p, q)
     return out.cpu().numpy()
 
 
