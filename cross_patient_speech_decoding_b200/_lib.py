@@ -67,7 +67,7 @@ _SIGS = {
                                c_float, _P, _P],
     'cpsd_bj_schedule': [c_int, _P],
     'cpsd_eig_sym_block': [_P, c_int, c_ll, c_int, _P, c_int, c_int, _P, _P, _P, _P, _P, _P,
-                           c_int, c_int, c_float, _P],
+                           c_int, c_int, c_float, _P, _P],
     'cpsd_bj_rlog_elems': [c_int, c_int, c_int],
     'cpsd_bj_eigvecs': [_P, c_int, c_int, _P, _P, _P, c_int, _P, c_int, c_int, _P, c_int, c_ll,
                         c_int, _P],

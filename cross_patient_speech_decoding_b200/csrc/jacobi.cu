@@ -15,6 +15,7 @@
 //                   is applied to the rest of the matrix and to the eigenvector matrix by
 //                   tile GEMMs.
 #include "common.cuh"
+#include "bj_tc.cuh"
 
 #define TS 128          // tile size
 #define BS 64           // block size of the block-Jacobi
@@ -309,7 +310,7 @@ __global__ void __launch_bounds__(NT)
 k_bj_inner(float* __restrict__ K, int ldk, long long strideK, const int* __restrict__ pairs,
            float* __restrict__ Rlog, int total_rounds, int round_idx,
            const float* __restrict__ scale, float* __restrict__ conv,
-           const int* __restrict__ done, int full_mode) {
+           const int* __restrict__ done, int full_mode, float* __restrict__ RTbuf) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* As = reinterpret_cast<float*>(smem_raw);
   float* Vs = As + TS * TS;
@@ -341,6 +342,10 @@ k_bj_inner(float* __restrict__ K, int ldk, long long strideK, const int* __restr
   }
   float* Rg = Rlog + (((long long)prob * total_rounds + round_idx) * npairs + pr) * (TS * TS);
   for (int e = threadIdx.x; e < TS * TS; e += NT) Rg[e] = Vs[e];
+  if (RTbuf) {   // transposed copy for the tensor-core update (K-major operand)
+    float* RTg = RTbuf + ((long long)prob * npairs + pr) * (TS * TS);
+    for (int e = threadIdx.x; e < TS * TS; e += NT) RTg[e] = Vs[(e & (TS - 1)) * TS + (e >> 7)];
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -358,7 +363,7 @@ __global__ void __launch_bounds__(NT, 2)
 k_bj_inner_cross(float* __restrict__ K, int ldk, long long strideK, const int* __restrict__ pairs,
                  float* __restrict__ Rlog, int total_rounds, int round_idx,
                  const float* __restrict__ scale, float* __restrict__ conv,
-                 const int* __restrict__ done) {
+                 const int* __restrict__ done, float* __restrict__ RTbuf) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* As = reinterpret_cast<float*>(smem_raw);          // [128][128]
   float2* cs = reinterpret_cast<float2*>(As + TS * TS);    // [64] (c, s) of the step
@@ -498,6 +503,25 @@ k_bj_inner_cross(float* __restrict__ K, int ldk, long long strideK, const int* _
     row[lane + 64] = vJ0[i] * s2;
     row[lane + 96] = vJ1[i] * s3;
   }
+  if (RTbuf) {
+    // transposed copy through the (now free) tile buffer, XOR-swizzled so that both the row
+    // writes and the column reads are bank-conflict free
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int r = warp * 16 + i, x = r & 31;
+      As[r * TS + (lane ^ x)] = vI0[i] * s0;
+      As[r * TS + 32 + (lane ^ x)] = vI1[i] * s1;
+      As[r * TS + 64 + (lane ^ x)] = vJ0[i] * s2;
+      As[r * TS + 96 + (lane ^ x)] = vJ1[i] * s3;
+    }
+    __syncthreads();
+    float* RTg = RTbuf + ((long long)prob * npairs + pr) * (TS * TS);
+    for (int e = threadIdx.x; e < TS * TS; e += NT) {
+      const int c = e >> 7, r = e & (TS - 1);
+      RTg[e] = As[r * TS + (c & ~31) + ((c & 31) ^ (r & 31))];
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -583,6 +607,24 @@ k_bj_update(float* __restrict__ K, int ld, long long stride, const int* __restri
       Kg[(long long)gc * ld + gr] = acc[i][j];
     }
   }
+}
+
+// tensor-core version of k_bj_update (see bj_tc.cuh); RTbuf holds this round's transposed
+// rotations, one 128x128 block per (problem, pair)
+__global__ void __launch_bounds__(NT, 1)
+k_bj_update_tc(float* __restrict__ K, int ld, long long stride, const int* __restrict__ pairs,
+               int npairs, const float* __restrict__ RTbuf, const int* __restrict__ done) {
+  extern __shared__ __align__(1024) unsigned char smem_tc[];
+  const int prob = blockIdx.y;
+  if (done && done[prob]) return;
+  int p = 0, rem = blockIdx.x;
+  while (rem >= npairs - 1 - p) { rem -= npairs - 1 - p; ++p; }
+  const int q = p + 1 + rem;
+  const float* RT = RTbuf + (long long)prob * npairs * (TS * TS);
+  bjtc::update_tile_tc(K + (long long)prob * stride, ld, RT + (long long)p * (TS * TS),
+                       RT + (long long)q * (TS * TS), pairs[2 * p], pairs[2 * p + 1],
+                       pairs[2 * q], pairs[2 * q + 1], smem_tc,
+                       [](int r, int I, int J) { return tile_gidx(r, I, J); });
 }
 
 // ---------------------------------------------------------------------------------------
@@ -857,7 +899,7 @@ extern "C" long long cpsd_bj_rlog_elems(int n_pad, int nprob, int max_sweeps) {
 extern "C" int cpsd_eig_sym_block(float* K, int ld, long long stride, int n_pad, const int* n_dev,
                                   int n_fixed, int nprob, const int* pairs_dev, float* Rlog,
                                   float* fwork, int* iwork, float* evals, int* perm, int ld_e,
-                                  int max_sweeps, float tol, cudaStream_t stream) {
+                                  int max_sweeps, float tol, float* RTbuf, cudaStream_t stream) {
   CPSD_CHECK_ARG(n_pad > 0 && n_pad % TS == 0, "eig_sym_block: n_pad must be a multiple of 128");
   CPSD_CHECK_ARG(ld >= n_pad && ld_e >= n_pad, "eig_sym_block: ld < n_pad");
   if (nprob == 0) return CPSD_OK;
@@ -875,6 +917,8 @@ extern "C" int cpsd_eig_sym_block(float* K, int ld, long long stride, int n_pad,
                                  (int)smem_cross));
   CPSD_CUDA(cudaFuncSetAttribute(k_bj_inner, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_in));
   CPSD_CUDA(cudaFuncSetAttribute(k_bj_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_up));
+  CPSD_CUDA(cudaFuncSetAttribute(k_bj_update_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 bjtc::SMEM_BYTES));
   k_bj_prepare<<<dim3(16, nprob), NT, 0, stream>>>(K, ld, stride, n_pad, n_dev, n_fixed, scale, conv,
                                                    done, sweeps);
   CPSD_LAUNCH_CHECK();
@@ -886,12 +930,16 @@ extern "C" int cpsd_eig_sym_block(float* K, int ld, long long stride, int n_pad,
       if (r == 0)
         k_bj_inner<<<dim3(npairs, nprob), NT, smem_in, stream>>>(K, ld, stride, pr, Rlog,
                                                                  total_rounds, ridx, scale, conv,
-                                                                 done, 1);
+                                                                 done, 1, RTbuf);
       else
         k_bj_inner_cross<<<dim3(npairs, nprob), NT, smem_cross, stream>>>(
-            K, ld, stride, pr, Rlog, total_rounds, ridx, scale, conv, done);
+            K, ld, stride, pr, Rlog, total_rounds, ridx, scale, conv, done, RTbuf);
       CPSD_LAUNCH_CHECK();
-      if (n_ktasks > 0) {
+      if (n_ktasks > 0 && RTbuf) {
+        k_bj_update_tc<<<dim3(n_ktasks, nprob), NT, bjtc::SMEM_BYTES, stream>>>(K, ld, stride, pr,
+                                                                               npairs, RTbuf, done);
+        CPSD_LAUNCH_CHECK();
+      } else if (n_ktasks > 0) {
         k_bj_update<<<dim3(n_ktasks, nprob), NT, smem_up, stream>>>(K, ld, stride, pr, npairs, Rlog,
                                                                     total_rounds, ridx, done);
         CPSD_LAUNCH_CHECK();

@@ -18,11 +18,12 @@
 //              K=8), tcgen05.commit releases smem stages / signals the epilogue
 //   warps 2-5: epilogue  tcgen05.ld (32 lanes x 32 columns per warp) of each partial
 //              accumulator -> fp32 register accumulators -> global, plus the mirrored tile
-#include "common.cuh"
+#include "tc_common.cuh"
 #include "descs.h"
 #include <cuda.h>
 
 namespace {
+using namespace tc;
 
 constexpr int BM = 128, BN = 128, BK = 32;      // BK fp32 = 128 bytes = one swizzle row
 constexpr int STAGES = 3;
@@ -31,74 +32,10 @@ constexpr int STAGE_BYTES = 4 * TILE_BYTES;      // A_hi, A_lo, B_hi, B_lo
 constexpr int TC_THREADS = 192;
 constexpr uint32_t TMEM_COLS = 256;          // two 128-column accumulator stages
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(bytes)
-               : "memory");
-}
-// Bounded wait: a lost arrival traps instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t a = smem_u32(bar);
-  uint32_t done = 0;
-  for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(a), "r"(parity)
-        : "memory");
-    if (done) return;
-  }
-  __trap();
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int c0, int c1,
-                                            uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
-      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                   smem_u32(bar))
-               : "memory");
-}
-// K-major operand, 128-byte swizzle: 8-row groups are 1024 B apart (SBO), LBO unused.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address
-  d |= (uint64_t)1 << 16;                             // leading byte offset (ignored, 16 B)
-  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset
-  d |= (uint64_t)1 << 46;                             // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
-  return d;
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_c),
-      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
 struct TcProb {
   float* out;
   int n, ldo;
 };
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 // The tensor core's fp32 accumulator truncates on every accumulate (measured: relative error
 // growing linearly with K, 1e-4 at K=6000).  So TMEM only accumulates CHUNK k-blocks

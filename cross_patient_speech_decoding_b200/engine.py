@@ -154,9 +154,11 @@ class CVEngine:
         R = self.ws(tag + '_Rlog', (nlog,))
         fw = self.ws(tag + '_fw', (18 * nprob,))
         iw = self.ws(tag + '_iw', (2 * nprob,), I32)
+        RT = self.ws(tag + '_RT', (nprob * (n_pad // 128) * 128 * 128,)) if self.use_tc else None
         self.ctx.call('cpsd_eig_sym_block', ptr(K), n_pad, n_pad * n_pad, n_pad, _p(n_dev),
                       n_fixed, nprob, ptr(self.schedule(n_pad)), ptr(R), ptr(fw), ptr(iw),
-                      ptr(evals), ptr(perm), evals.shape[-1], self.eig_sweeps, self.eig_tol)
+                      ptr(evals), ptr(perm), evals.shape[-1], self.eig_sweeps, self.eig_tol,
+                      ptr(RT))
         return iw
 
     def eig_vecs(self, tag, n_pad, nprob, perm, k_dev, k_fixed, k_launch, E):

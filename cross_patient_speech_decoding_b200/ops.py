@@ -27,7 +27,8 @@ def _ivoid(address):
     return ctypes.c_void_p(address)
 
 
-def eig_sym(A, n=None, max_sweeps=15, tol=3e-7, device=None, return_sweeps=False, f64=False):
+def eig_sym(A, n=None, max_sweeps=15, tol=3e-7, device=None, return_sweeps=False, f64=False,
+            tensor_cores=False):
     """Eigen-decomposition of a batch of symmetric matrices.  A: (nprob, n, n) or (n, n).
     ``f64`` (n <= 128): iterate the matrix in fp64, eigenvectors in fp32.
     Returns (evals descending (nprob, n), evecs (nprob, n, n) columns)."""
@@ -60,8 +61,10 @@ def eig_sym(A, n=None, max_sweeps=15, tol=3e-7, device=None, return_sweeps=False
         R = ctx.empty((int(ctx.lib.cpsd_bj_rlog_elems(n_pad, nprob, max_sweeps)),))
         fw = ctx.zeros((18 * nprob,))
         perm = ctx.empty((nprob, n_pad), I32)
+        RT = ctx.empty((nprob * (n_pad // 128) * 128 * 128,)) if tensor_cores else None
         ctx.call('cpsd_eig_sym_block', ptr(Ad), n_pad, n_pad * n_pad, n_pad, ptr(nd), 0, nprob,
-                 ptr(sd), ptr(R), ptr(fw), ptr(sw), ptr(evals), ptr(perm), n_pad, max_sweeps, tol)
+                 ptr(sd), ptr(R), ptr(fw), ptr(sw), ptr(evals), ptr(perm), n_pad, max_sweeps, tol,
+                 ptr(RT))
         evecs = ctx.zeros((nprob, n_pad, n_pad))
         ctx.call('cpsd_bj_eigvecs', ptr(R), n_pad, nprob, ptr(sd), ptr(sw), ptr(perm), n_pad,
                  ptr(None), n_pad, n_pad, ptr(evecs), n_pad, n_pad * n_pad, max_sweeps)

@@ -109,6 +109,8 @@ long long cpsd_bj_rlog_elems(int n_pad, int nprob, int max_sweeps);
 int cpsd_eig_sym_block(float* K, int ld, long long stride, int n_pad, const int* n_dev,
                        int n_fixed, int nprob, const int* pairs_dev, float* Rlog, float* fwork,
                        int* iwork, float* evals, int* perm, int ld_e, int max_sweeps, float tol,
+                       float* RTbuf /* nprob*(n_pad/128)*128*128 floats: tcgen05 tile update;
+                                       NULL: fp32 SIMT update */,
                        cudaStream_t stream);
 int cpsd_bj_eigvecs(const float* Rlog, int n_pad, int nprob, const int* pairs_dev,
                     const int* iwork, const int* perm, int ld_perm, const int* k_dev, int k_fixed,

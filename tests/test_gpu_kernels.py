@@ -42,11 +42,12 @@ def test_eig_small_ragged_sizes(ops):
         assert np.abs(ev[i, :n] - ref).max() <= 2e-5 * ref[0]
 
 
+@pytest.mark.parametrize('tc', [False, True])
 @pytest.mark.parametrize('n', [129, 240, 300, 640])
-def test_eig_block(ops, n):
+def test_eig_block(ops, n, tc):
     rng = np.random.default_rng(n)
     A = np.stack([_rand_sym(rng, n, psd=(i == 0)) for i in range(2)])
-    ev, V, sw = ops.eig_sym(A, return_sweeps=True)
+    ev, V, sw = ops.eig_sym(A, return_sweeps=True, tensor_cores=tc)
     assert (sw <= 15).all(), sw
     for i in range(2):
         ref = np.linalg.eigvalsh(A[i])[::-1]
@@ -63,7 +64,7 @@ def test_eig_block_pooled_spectrum(ops):
     Z = rng.standard_normal((n, F)) + 4 * rng.standard_normal((n, 6)) @ rng.standard_normal((6, F))
     Z -= Z.mean(0)
     K = Z @ Z.T
-    ev, V = ops.eig_sym(K)
+    ev, V = ops.eig_sym(K, tensor_cores=True)
     ref_w, ref_v = np.linalg.eigh(K)
     ref_w, ref_v = ref_w[::-1], ref_v[:, ::-1]
     assert np.abs(ev - ref_w).max() <= 3e-5 * ref_w[0]
