@@ -56,7 +56,8 @@ template <typename GIDX>
 __device__ __forceinline__ void update_tile_tc(float* __restrict__ Kg, int ld,
                                                const float* __restrict__ RTp,
                                                const float* __restrict__ RTq, int Ip, int Jp,
-                                               int Iq, int Jq, uint8_t* smem_raw, GIDX gidx) {
+                                               int Iq, int Jq, bool mirror, uint8_t* smem_raw,
+                                               GIDX gidx) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
   uint8_t* regA = smem;                      // 128 KB: GEMM1 stages, later Y^T hi | lo
@@ -174,8 +175,10 @@ __device__ __forceinline__ void update_tile_tc(float* __restrict__ Kg, int ld,
         *reinterpret_cast<float4*>(Kg + (long long)gr * ld + gc0 + j) =
             make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
                         __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+      if (mirror) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) Kg[(long long)(gc0 + j) * ld + gr] = __uint_as_float(v[j]);
+        for (int j = 0; j < 32; ++j) Kg[(long long)(gc0 + j) * ld + gr] = __uint_as_float(v[j]);
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -349,6 +349,53 @@ k_bj_inner(float* __restrict__ K, int ldk, long long strideK, const int* __restr
 }
 
 // ---------------------------------------------------------------------------------------
+// Within-block sweep ("W" round, once per sweep): one CTA per 64-block rotates all pairs
+// inside its 64x64 diagonal block (64 steps x 32 pairs, 64 KB of shared memory -> 3 CTAs/SM)
+// and logs the rotation as the block-diagonal 128x128 matrix diag(R_I, R_J) of the round-0
+// pair (I, J) the block belongs to.  K itself is updated by the tile-update kernel, which
+// in W rounds also covers the diagonal pair tiles.  grid (nb, nprob).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT)
+k_bj_within(const float* __restrict__ K, int ldk, long long strideK, const int* __restrict__ pairs,
+            int npairs, float* __restrict__ Rlog, int total_rounds, int round_idx,
+            const float* __restrict__ scale, float* __restrict__ conv,
+            const int* __restrict__ done, float* __restrict__ RTbuf) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* As = reinterpret_cast<float*>(smem_raw);     // [64][TS]
+  float* Vs = As + BS * TS;                           // [64][TS]
+  StepBuf* sb = reinterpret_cast<StepBuf*>(Vs + BS * TS);
+  int* redmax = reinterpret_cast<int*>(sb + 1);
+  const int blk = blockIdx.x, prob = blockIdx.y;
+  if (done && done[prob]) return;
+  int pr = 0, half = 0;
+  for (int u = 0; u < npairs; ++u) {
+    if (pairs[2 * u] == blk) { pr = u; half = 0; }
+    if (pairs[2 * u + 1] == blk) { pr = u; half = 1; }
+  }
+  const float* Kg = K + (long long)prob * strideK;
+  for (int e = threadIdx.x; e < BS * BS; e += NT) {
+    const int r = e >> 6, c = e & (BS - 1);
+    As[r * TS + c] = Kg[(long long)(blk * BS + r) * ldk + blk * BS + c];
+    Vs[r * TS + c] = (r == c) ? 1.f : 0.f;
+  }
+  __syncthreads();
+  const float sc = scale[prob];
+  const float off = tile_sweep_full<float>(As, Vs, sb, BS, BS, 1e-9f * sc + 1e-37f, redmax);
+  if (threadIdx.x == 0 && sc > 0.f)
+    atomicMax(reinterpret_cast<int*>(conv + prob), __float_as_int(off / sc));
+  // rows [half*64, half*64+64) of the pair's block-diagonal rotation (and of its transpose)
+  float* Rg = Rlog + (((long long)prob * total_rounds + round_idx) * npairs + pr) * (TS * TS);
+  float* RTg = RTbuf ? RTbuf + ((long long)prob * npairs + pr) * (TS * TS) : nullptr;
+  for (int e = threadIdx.x; e < BS * TS; e += NT) {
+    const int r = e >> 7, c = e & (TS - 1);
+    const bool in = (c >> 6) == half;
+    const int cc = c & (BS - 1);
+    Rg[(half * BS + r) * TS + c] = in ? Vs[r * TS + cc] : 0.f;
+    if (RTg) RTg[(half * BS + r) * TS + c] = in ? Vs[cc * TS + r] : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Cross-sweep variant of the inner kernel (16 of every 17 rounds): only the 64x64 pairs
 // (i in block I, j in block J) rotate, in 64 steps of 64 disjoint pairs
 // (l, 64 + (l+s)%64).  The tile stays in shared memory (64 KB -> 2 CTAs/SM at 128 registers), but the
@@ -545,10 +592,16 @@ k_bj_update(float* __restrict__ K, int ld, long long stride, const int* __restri
   float* Kg = K + (long long)prob * stride;
   const float* Rp_all = Rlog + ((long long)prob * total_rounds + round_idx) * npairs * (TS * TS);
 
-  // decode (p, q), p < q
-  int p = 0, rem = task;
-  while (rem >= npairs - 1 - p) { rem -= npairs - 1 - p; ++p; }
-  const int q = p + 1 + rem;
+  // decode (p, q), p < q; tasks beyond the strict upper triangle are the diagonal tiles (W rounds)
+  const int n_off = npairs * (npairs - 1) / 2;
+  int p = 0, q;
+  if (task < n_off) {
+    int rem = task;
+    while (rem >= npairs - 1 - p) { rem -= npairs - 1 - p; ++p; }
+    q = p + 1 + rem;
+  } else {
+    p = q = task - n_off;
+  }
   const int Ip = pairs[2 * p], Jp = pairs[2 * p + 1];
   const int Iq = pairs[2 * q], Jq = pairs[2 * q + 1];
   const float* Rq = Rp_all + (long long)q * (TS * TS);
@@ -604,7 +657,7 @@ k_bj_update(float* __restrict__ K, int ld, long long stride, const int* __restri
     for (int j = 0; j < 8; ++j) {
       const int gc = tile_gidx(tx + 16 * j, Iq, Jq);
       Kg[(long long)gr * ld + gc] = acc[i][j];
-      Kg[(long long)gc * ld + gr] = acc[i][j];
+      if (p != q) Kg[(long long)gc * ld + gr] = acc[i][j];
     }
   }
 }
@@ -617,13 +670,19 @@ k_bj_update_tc(float* __restrict__ K, int ld, long long stride, const int* __res
   extern __shared__ __align__(1024) unsigned char smem_tc[];
   const int prob = blockIdx.y;
   if (done && done[prob]) return;
-  int p = 0, rem = blockIdx.x;
-  while (rem >= npairs - 1 - p) { rem -= npairs - 1 - p; ++p; }
-  const int q = p + 1 + rem;
+  const int n_off = npairs * (npairs - 1) / 2;
+  int p = 0, q;
+  if ((int)blockIdx.x < n_off) {
+    int rem = blockIdx.x;
+    while (rem >= npairs - 1 - p) { rem -= npairs - 1 - p; ++p; }
+    q = p + 1 + rem;
+  } else {
+    p = q = blockIdx.x - n_off;          // diagonal pair tile (W rounds only)
+  }
   const float* RT = RTbuf + (long long)prob * npairs * (TS * TS);
   bjtc::update_tile_tc(K + (long long)prob * stride, ld, RT + (long long)p * (TS * TS),
                        RT + (long long)q * (TS * TS), pairs[2 * p], pairs[2 * p + 1],
-                       pairs[2 * q], pairs[2 * q + 1], smem_tc,
+                       pairs[2 * q], pairs[2 * q + 1], p != q, smem_tc,
                        [](int r, int I, int J) { return tile_gidx(r, I, J); });
 }
 
@@ -861,7 +920,8 @@ extern "C" int cpsd_eig_sym_small_f64(const double* A, int lda, long long stride
 
 // Block Jacobi eigen-solver for n_pad = multiple of 128 (> 128).  K is destroyed.
 // Workspace (device, caller-allocated):
-//   Rlog  : nprob * max_sweeps * (nb-1) * (nb/2) * 128*128 floats, nb = n_pad/64 (rotation log)
+//   Rlog  : nprob * max_sweeps * nb * (nb/2) * 128*128 floats, nb = n_pad/64 (rotation log:
+//           per sweep one within-block round + nb-1 cross rounds)
 //   fwork : (2 + 16) * nprob floats (scale, conv, per-sweep convergence history)
 //   iwork : 2 * nprob ints (done, sweeps)
 //   pairs : (nb-1) * (nb/2) * 2 ints, round-robin schedule as written by cpsd_bj_schedule().
@@ -893,7 +953,7 @@ extern "C" int cpsd_bj_schedule(int n_pad, int* pairs_host) {
 
 extern "C" long long cpsd_bj_rlog_elems(int n_pad, int nprob, int max_sweeps) {
   const long long nb = n_pad / BS;
-  return (long long)nprob * max_sweeps * (nb - 1) * (nb / 2) * (TS * TS);
+  return (long long)nprob * max_sweeps * nb * (nb / 2) * (TS * TS);
 }
 
 extern "C" int cpsd_eig_sym_block(float* K, int ld, long long stride, int n_pad, const int* n_dev,
@@ -904,44 +964,47 @@ extern "C" int cpsd_eig_sym_block(float* K, int ld, long long stride, int n_pad,
   CPSD_CHECK_ARG(ld >= n_pad && ld_e >= n_pad, "eig_sym_block: ld < n_pad");
   if (nprob == 0) return CPSD_OK;
   const int nb = n_pad / BS, npairs = nb / 2, nrounds = nb - 1;
-  const int total_rounds = max_sweeps * nrounds;
+  const int rps = nrounds + 1;                 // rounds per sweep: 1 within-block + nrounds cross
+  const int total_rounds = max_sweeps * rps;
   float* scale = fwork;
   float* conv = fwork + nprob;
   float* hist = fwork + 2 * nprob;
   int* done = iwork;
   int* sweeps = iwork + nprob;
-  const size_t smem_in = tile_smem_bytes();
+  const size_t smem_w = 2 * BS * TS * sizeof(float) + sizeof(StepBuf) + 32;
   const size_t smem_up = (TS * LDX + TS * TS) * sizeof(float);
   const size_t smem_cross = TS * TS * sizeof(float) + BS * 12 + TS * 4 + 16;
   CPSD_CUDA(cudaFuncSetAttribute(k_bj_inner_cross, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem_cross));
-  CPSD_CUDA(cudaFuncSetAttribute(k_bj_inner, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_in));
+  CPSD_CUDA(cudaFuncSetAttribute(k_bj_within, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
   CPSD_CUDA(cudaFuncSetAttribute(k_bj_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_up));
   CPSD_CUDA(cudaFuncSetAttribute(k_bj_update_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  bjtc::SMEM_BYTES));
   k_bj_prepare<<<dim3(16, nprob), NT, 0, stream>>>(K, ld, stride, n_pad, n_dev, n_fixed, scale, conv,
                                                    done, sweeps);
   CPSD_LAUNCH_CHECK();
-  const int n_ktasks = npairs * (npairs - 1) / 2;
+  const int n_off = npairs * (npairs - 1) / 2;
   for (int sw = 0; sw < max_sweeps; ++sw) {
-    for (int r = 0; r < nrounds; ++r) {
-      const int* pr = pairs_dev + (size_t)r * npairs * 2;
-      const int ridx = sw * nrounds + r;
-      if (r == 0)
-        k_bj_inner<<<dim3(npairs, nprob), NT, smem_in, stream>>>(K, ld, stride, pr, Rlog,
-                                                                 total_rounds, ridx, scale, conv,
-                                                                 done, 1, RTbuf);
+    for (int rr = 0; rr < rps; ++rr) {
+      // rr == 0: within-block round on the pairing of cross round 0; rr >= 1: cross round rr-1
+      const int* pr = pairs_dev + (size_t)(rr == 0 ? 0 : rr - 1) * npairs * 2;
+      const int ridx = sw * rps + rr;
+      if (rr == 0)
+        k_bj_within<<<dim3(nb, nprob), NT, smem_w, stream>>>(K, ld, stride, pr, npairs, Rlog,
+                                                             total_rounds, ridx, scale, conv, done,
+                                                             RTbuf);
       else
         k_bj_inner_cross<<<dim3(npairs, nprob), NT, smem_cross, stream>>>(
             K, ld, stride, pr, Rlog, total_rounds, ridx, scale, conv, done, RTbuf);
       CPSD_LAUNCH_CHECK();
-      if (n_ktasks > 0 && RTbuf) {
-        k_bj_update_tc<<<dim3(n_ktasks, nprob), NT, bjtc::SMEM_BYTES, stream>>>(K, ld, stride, pr,
-                                                                               npairs, RTbuf, done);
+      const int ntask = n_off + (rr == 0 ? npairs : 0);   // W rounds also rotate the diagonal tiles
+      if (ntask > 0 && RTbuf) {
+        k_bj_update_tc<<<dim3(ntask, nprob), NT, bjtc::SMEM_BYTES, stream>>>(K, ld, stride, pr,
+                                                                            npairs, RTbuf, done);
         CPSD_LAUNCH_CHECK();
-      } else if (n_ktasks > 0) {
-        k_bj_update<<<dim3(n_ktasks, nprob), NT, smem_up, stream>>>(K, ld, stride, pr, npairs, Rlog,
-                                                                    total_rounds, ridx, done);
+      } else if (ntask > 0) {
+        k_bj_update<<<dim3(ntask, nprob), NT, smem_up, stream>>>(K, ld, stride, pr, npairs, Rlog,
+                                                                 total_rounds, ridx, done);
         CPSD_LAUNCH_CHECK();
       }
     }
@@ -966,7 +1029,8 @@ extern "C" int cpsd_bj_eigvecs(const float* Rlog, int n_pad, int nprob, const in
   CPSD_CHECK_ARG(k_launch > 0 && k_launch <= lde, "bj_eigvecs: bad k_launch");
   if (nprob == 0) return CPSD_OK;
   const int nb = n_pad / BS, npairs = nb / 2, nrounds = nb - 1;
-  const int total_rounds = max_sweeps * nrounds;
+  const int rps = nrounds + 1;
+  const int total_rounds = max_sweeps * rps;
   const int* sweeps = iwork + nprob;
   k_bj_einit<<<dim3(n_pad < 256 ? n_pad : 256, nprob), NT, 0, stream>>>(E, lde, strideE, n_pad, perm,
                                                                         ld_perm, k_dev, k_fixed);
@@ -974,9 +1038,10 @@ extern "C" int cpsd_bj_eigvecs(const float* Rlog, int n_pad, int nprob, const in
   const size_t smem = (TS * LDX + TS * EC) * sizeof(float);
   CPSD_CUDA(cudaFuncSetAttribute(k_bj_backapply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   for (int ridx = total_rounds - 1; ridx >= 0; --ridx) {
-    const int* pr = pairs_dev + (size_t)(ridx % nrounds) * npairs * 2;
+    const int rr = ridx % rps;
+    const int* pr = pairs_dev + (size_t)(rr == 0 ? 0 : rr - 1) * npairs * 2;
     k_bj_backapply<<<dim3(npairs, nprob), NT, smem, stream>>>(
-        E, lde, strideE, pr, npairs, Rlog, total_rounds, ridx, nrounds, sweeps, k_dev, k_fixed);
+        E, lde, strideE, pr, npairs, Rlog, total_rounds, ridx, rps, sweeps, k_dev, k_fixed);
     CPSD_LAUNCH_CHECK();
   }
   return CPSD_OK;

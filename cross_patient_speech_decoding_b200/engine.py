@@ -446,8 +446,11 @@ class CVEngine:
         if n_pad > 128:
             # eigenvectors of the k2 retained components only (rotation-log replay); one small
             # read-back sizes the replay grid to the columns actually kept
-            k_launch = min(kcap, _ceil(max(int(k2.cpu().numpy().max()), 1), 64))
+            self._k2_max = max(int(k2.cpu().numpy().max()), 1)
+            k_launch = min(kcap, _ceil(self._k2_max, 64))
             self.eig_vecs('pool', n_pad, B, perm, k2, 0, k_launch, V)
+        else:
+            self._k2_max = kcap
         self.mark('pool_scores')
         perm_p = ptr(None)
         St = self.ws('pool_St', (B, kcap, n_pad))
@@ -687,7 +690,9 @@ class CVEngine:
             pk, d_p1, d_p2, B, Zall, pmu, Kall, n_pad, F, n_pool, n_te, o_npool, o_nall, o_ypool,
             n_te_max, want_details)
         self.mark('svm')
-        ctx.call('cpsd_svm_fit_ovr', pk.daddr(d_svm), B * len(self.classes), kcap, n_pad)
+        # shared memory of the solver is sized by the largest k2 of the batch, not by its cap
+        ctx.call('cpsd_svm_fit_ovr', pk.daddr(d_svm), B * len(self.classes),
+                 min(kcap, self._k2_max), n_pad)
         yhat = self.ws('yhat', (B, n_te_max), I32)
         ncls = len(self.classes)
         ctx.call('cpsd_svm_predict_ovr', ptr(Ste), n_te_max, kcap * n_te_max, ptr(W), kcap + 1,

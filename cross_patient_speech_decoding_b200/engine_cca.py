@@ -230,7 +230,7 @@ def batch_cca(eng, batch, want_details):
         n_te_max, want_details)
     ncls = len(eng.classes)
     eng.mark('svm')
-    ctx.call('cpsd_svm_fit_ovr', pk.daddr(d_svm), B * ncls, kcap, n_pad)
+    ctx.call('cpsd_svm_fit_ovr', pk.daddr(d_svm), B * ncls, min(kcap, eng._k2_max), n_pad)
     yhat = eng.ws('yhat', (B, n_te_max), I32)
     ctx.call('cpsd_svm_predict_ovr', ptr(Ste), n_te_max, kcap * n_te_max, ptr(W), kcap + 1,
              ncls * (kcap + 1), ptr(k2), 0, ctypes_int_ptr(pk.iaddr(o_nte)), n_te_max,
