@@ -79,7 +79,7 @@ _SIGS = {
     'cpsd_gram_nt': [_P, c_int, c_int, c_int, _P],
     'cpsd_class_mean': [_P, c_int, c_int, c_int, _P],
     'cpsd_center_rows': [_P, c_int, c_ll, _P, c_int, _P, c_int, c_int, c_int, c_int, _P],
-    'cpsd_copy_rows': [_P, c_int, c_ll, _P, c_int, c_ll, _P, c_int, c_int, c_int, c_int, _P],
+    'cpsd_copy_rows': [_P, c_int, c_ll, _P, c_int, c_ll, _P, c_int, c_int, c_int, c_int, c_int, _P],
     'cpsd_cast_f64_f32': [_P, _P, c_ll, _P],
     'cpsd_permute_cols': [_P, c_int, c_ll, _P, c_int, _P, c_int, c_ll, c_int, c_int, c_int, _P],
     'cpsd_mcca_mask': [_P, c_int, c_ll, _P, c_int, _P, _P, c_int, c_int, _P, _P, _P, c_int, _P],

@@ -62,14 +62,15 @@ k_center_rows(float* __restrict__ Z, int ld, long long strideZ, const float* __r
 __global__ void __launch_bounds__(256)
 k_copy_rows(const float* __restrict__ src, int lds, long long strideS, float* __restrict__ dst,
             int ldd, long long strideD, const int* __restrict__ r0_dev, int r0_fixed, int nrows,
-            int ncols) {
+            int ncols, int src_rows) {
   const int p = blockIdx.z;
   const int r0 = r0_dev ? r0_dev[p] : r0_fixed;
   for (int r = blockIdx.y; r < nrows; r += gridDim.y) {
+    const bool in = (r0 + r) < src_rows;       // rows past the source block read as zero
     const float* s = src + (long long)p * strideS + (long long)(r0 + r) * lds;
     float* d = dst + (long long)p * strideD + (long long)r * ldd;
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncols; c += gridDim.x * blockDim.x)
-      d[c] = s[c];
+      d[c] = in ? s[c] : 0.f;
   }
 }
 
@@ -270,14 +271,14 @@ extern "C" int cpsd_center_rows(float* Z, int ld, long long strideZ, const float
 
 extern "C" int cpsd_copy_rows(const float* src, int lds, long long strideS, float* dst, int ldd,
                               long long strideD, const int* r0_dev, int r0_fixed, int nrows,
-                              int ncols, int nprob, cudaStream_t stream) {
+                              int ncols, int src_rows, int nprob, cudaStream_t stream) {
   CPSD_CHECK_ARG(nprob >= 0 && ncols > 0 && nrows >= 0, "copy_rows: bad dims");
   if (nprob == 0 || nrows == 0) return CPSD_OK;
   int bx = (ncols + 255) / 256;
   if (bx > 8) bx = 8;
   int by = nrows < 256 ? nrows : 256;
   k_copy_rows<<<dim3(bx, by, nprob), 256, 0, stream>>>(src, lds, strideS, dst, ldd, strideD, r0_dev,
-                                                      r0_fixed, nrows, ncols);
+                                                      r0_fixed, nrows, ncols, src_rows);
   CPSD_LAUNCH_CHECK();
   return CPSD_OK;
 }

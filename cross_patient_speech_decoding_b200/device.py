@@ -8,7 +8,11 @@ import ctypes
 import numpy as np
 import torch
 
+import os
+
 from . import _lib
+
+_SYNC_DEBUG = os.environ.get('CPSD_SYNC', '0') == '1'
 
 
 class Context:
@@ -60,6 +64,11 @@ class Context:
     def call(self, name, *args):
         fn = getattr(self.lib, name)
         _lib.check(fn(*args, self.stream), name)
+        if _SYNC_DEBUG:      # CPSD_SYNC=1: localise an asynchronous fault to the call that made it
+            try:
+                torch.cuda.synchronize(self.device)
+            except Exception as e:
+                raise _lib.CpsdError('%s faulted: %s' % (name, str(e).splitlines()[0]))
 
 
 def ptr(t, offset_elems=0):

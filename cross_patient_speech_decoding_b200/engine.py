@@ -425,7 +425,7 @@ class CVEngine:
         self.mark('pool_eig')
         Kte = self.ws('pool_Kte', (B, n_te_max, n_pad))
         ctx.call('cpsd_copy_rows', ptr(Kall), n_pad, n_pad * n_pad, ptr(Kte), n_pad,
-                 n_te_max * n_pad, npool_dev, 0, n_te_max, n_pad, B)
+                 n_te_max * n_pad, npool_dev, 0, n_te_max, n_pad, n_pad, B)
         evals = self.ws('pool_ev', (B, n_pad))
         k2 = self.ws('pool_k2', (B,), I32)
         kcap = min(n_pad, F)
@@ -644,7 +644,7 @@ class CVEngine:
         ctx.call('cpsd_class_mean', pk.daddr(d_cm), B, Kmax, T * tv.C)
         # signal ranks (cross ranks are fold-invariant and come with the int table)
         ctx.call('cpsd_copy_rows', ctypes_int_ptr(pk.iaddr(o_rank)), B * P, 0, ptr(rank_dev),
-                 B * P, 0, ptr(None), 0, 1, B * P, 1)
+                 B * P, 0, ptr(None), 0, 1, B * P, 1, 1)
         self.mark('align_scatter_eig')
         if use_rank:
             ctx.call(gram_c, pk.daddr(d_gt), B, tv.C, tv.C)

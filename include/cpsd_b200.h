@@ -51,7 +51,7 @@ int cpsd_center_rows(float* Z, int ld, long long strideZ, const float* mu, int l
                      cudaStream_t stream);
 int cpsd_copy_rows(const float* src, int lds, long long strideS, float* dst, int ldd,
                    long long strideD, const int* r0_dev, int r0_fixed, int nrows, int ncols,
-                   int nprob, cudaStream_t stream);
+                   int src_rows, int nprob, cudaStream_t stream);
 /* ingest: the reference keeps trials as float64 (pickled numpy); cast once on the device */
 int cpsd_cast_f64_f32(const double* src, float* dst, long long n, cudaStream_t stream);
 int cpsd_permute_cols(const float* src, int lds, long long strideS, const int* perm, int ld_perm,

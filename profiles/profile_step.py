@@ -18,11 +18,17 @@ from cross_patient_speech_decoding_b200.engine import CVEngine  # noqa: E402
 pts = bench.make_data()
 eng = CVEngine(pts[0], pts[1:], method='mcca', n_comp=30, regs=0.5, pca_var=0.8,
                use_tensor_cores=not a.no_tc, max_batch=a.folds)
-folds = bench.step_folds(pts[0][1], 1)[:a.folds]
-eng.run(folds)
+def mk(seed):
+    out = []
+    while len(out) < a.folds:
+        out += bench.step_folds(pts[0][1], seed + len(out))
+    return out[:a.folds]
+
+
+eng.run(mk(1000))
 for s in range(a.steps):
     eng.profile = a.stages
-    res = eng.run(bench.step_folds(pts[0][1], 2 + s)[:a.folds], return_details=True)
+    res = eng.run(mk(2000 + 100 * s), return_details=True)
     if a.stages:
         print('stages_ms', {k: round(v, 3) for k, v in eng.collect_marks().items()})
     print('k2', res['k2'][:4], 'bj_sweeps', res['details'][0]['bj_sweeps'],
