@@ -72,6 +72,15 @@ _SIGS = {
     'cpsd_bj_eigvecs': [_P, c_int, c_int, _P, _P, _P, c_int, _P, c_int, c_int, _P, c_int, c_ll,
                         c_int, _P],
     'cpsd_select_k': [_P, c_int, _P, c_int, c_float, c_int, c_int, c_int, _P, c_int, c_int, _P],
+    'cpsd_select_k_total': [_P, c_int, _P, c_int, _P, c_float, c_int, c_int, c_int, _P, c_int,
+                            c_int, _P],
+    'cpsd_eig_topk_ws_elems': [c_int, c_int, c_int],
+    'cpsd_eig_topk_voff': [c_int, c_int, c_int],
+    'cpsd_eig_sym_topk': [_P, c_int, c_ll, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P,
+                          c_int, _P, _P, _P, c_int, c_float, _P],
+    'cpsd_sgemm_batched': [c_int, c_int, c_int, c_int, c_float, _P, c_int, c_ll, _P, c_int, c_ll,
+                           _P, c_int, c_ll, c_int, _P],
+    'cpsd_chol_inv': [_P, c_int, c_ll, c_int, _P, c_int, c_ll, _P, c_int, _P],
     'cpsd_gram_tn': [_P, c_int, c_int, c_int, _P],
     'cpsd_gram_tn_f64': [_P, c_int, c_int, c_int, _P],
     'cpsd_colsum': [_P, c_int, c_int, _P],
@@ -100,7 +109,8 @@ _SIGS = {
     'cpsd_gram_nt_tc_ws_bytes': [c_int],
 }
 _RESTYPES = {'cpsd_last_error': ctypes.c_char_p, 'cpsd_launch_count': c_ll,
-             'cpsd_bj_rlog_elems': c_ll,
+             'cpsd_bj_rlog_elems': c_ll, 'cpsd_eig_topk_ws_elems': c_ll,
+             'cpsd_eig_topk_voff': c_ll,
              'cpsd_reset_launch_count': None}
 
 EXPORTED_SYMBOLS = sorted(_SIGS)

@@ -840,8 +840,8 @@ k_bj_extract(const float* __restrict__ K, int ld, long long stride, const int* _
 // Negative eigenvalues are clipped to 0 (sklearn covariance_eigh does the same); result is
 // clamped to [kmin, min(kmax, n)].
 __global__ void k_select_k(const float* __restrict__ evals, int ld_e, const int* __restrict__ n_dev,
-                           int n_fixed, float thr, int mode, int kmin, int kmax,
-                           int* __restrict__ k_out, int k_stride, int nprob) {
+                           int n_fixed, const float* __restrict__ tot_dev, float thr, int mode,
+                           int kmin, int kmax, int* __restrict__ k_out, int k_stride, int nprob) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nprob) return;
   const int n = n_dev ? n_dev[p] : n_fixed;
@@ -851,7 +851,8 @@ __global__ void k_select_k(const float* __restrict__ evals, int ld_e, const int*
     k = (int)thr;
   } else {
     double tot = 0.0;
-    for (int i = 0; i < n; ++i) tot += fmax((double)ev[i], 0.0);
+    if (tot_dev) tot = (double)tot_dev[p];   // only the leading n values are known: total given
+    else for (int i = 0; i < n; ++i) tot += fmax((double)ev[i], 0.0);
     double cum = 0.0;
     k = -1;
     int cnt_le = 0;
@@ -1052,8 +1053,22 @@ extern "C" int cpsd_select_k(const float* evals, int ld_e, const int* n_dev, int
                              cudaStream_t stream) {
   CPSD_CHECK_ARG(mode >= 0 && mode <= 3, "select_k: bad mode");
   if (nprob == 0) return CPSD_OK;
-  k_select_k<<<(nprob + 63) / 64, 64, 0, stream>>>(evals, ld_e, n_dev, n_fixed, thr, mode, kmin, kmax,
-                                                   k_out, k_stride, nprob);
+  k_select_k<<<(nprob + 63) / 64, 64, 0, stream>>>(evals, ld_e, n_dev, n_fixed, nullptr, thr, mode,
+                                                   kmin, kmax, k_out, k_stride, nprob);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
+
+// Same selection when only the leading n eigenvalues are known and the total variance (the
+// trace) is given per problem (cpsd_eig_sym_topk).
+extern "C" int cpsd_select_k_total(const float* evals, int ld_e, const int* n_dev, int n_fixed,
+                                   const float* total_dev, float thr, int mode, int kmin, int kmax,
+                                   int* k_out, int k_stride, int nprob, cudaStream_t stream) {
+  CPSD_CHECK_ARG(mode >= 0 && mode <= 3, "select_k_total: bad mode");
+  CPSD_CHECK_ARG(total_dev != nullptr, "select_k_total: total_dev is NULL");
+  if (nprob == 0) return CPSD_OK;
+  k_select_k<<<(nprob + 63) / 64, 64, 0, stream>>>(evals, ld_e, n_dev, n_fixed, total_dev, thr, mode,
+                                                   kmin, kmax, k_out, k_stride, nprob);
   CPSD_LAUNCH_CHECK();
   return CPSD_OK;
 }

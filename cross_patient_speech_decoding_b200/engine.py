@@ -62,7 +62,8 @@ class CVEngine:
     def __init__(self, target, cross, method='mcca', n_comp=None, regs=0.5, pca_var=0.8,
                  decoder_var=0.8, C=1.0, tar_in_train=True, device=None, max_batch=32,
                  dcd_epochs=2, max_newton=60, tol_newton=1e-9, tol_dcd=1e-4,
-                 eig_sweeps=12, eig_tol=3e-7, use_tensor_cores=False):
+                 eig_sweeps=12, eig_tol=3e-7, use_tensor_cores=False, pool_solver='auto',
+                 topk_block=128, topk_iters=8, topk_tol=2e-5, topk_rounds=3):
         self.ctx = Context.get(device)
         self.method = method
         if n_comp is None:
@@ -81,6 +82,16 @@ class CVEngine:
         self.eig_sweeps = eig_sweeps
         self.eig_tol = eig_tol
         self.use_tc = use_tensor_cores
+        # decoder-stage PCA eigen-solver: 'topk' = block subspace iteration for the leading
+        # components (falls back to the full solver when the requested variance is not reached
+        # inside the block), 'full' = block Jacobi of the whole Gram, 'auto' = topk when the
+        # pooled matrix is large enough for it to pay
+        assert pool_solver in ('auto', 'topk', 'full')
+        self.pool_solver = pool_solver
+        self.topk_block = int(topk_block)
+        self.topk_iters = int(topk_iters)
+        self.topk_tol = float(topk_tol)
+        self.topk_rounds = int(topk_rounds)
         if method == 'mcca':
             assert isinstance(n_comp, (int, np.integer)) and n_comp >= 1
         views = [target] + list(cross)
@@ -191,6 +202,45 @@ class CVEngine:
         nc = n_pad if ncols is None else ncols
         self.eig_vecs(tag, n_pad, nprob, perm, ptr(None), nc, nc, evecs)
         return evals, evecs
+
+    def eig_topk(self, K, n_pad, n_dev, nprob, m, evals, tag, thr, mode, kcap, k2):
+        """Leading eigen-pairs of K (nprob, n_pad, n_pad) by subspace iteration; K keeps its
+        leading block.  Fills evals / k2 and returns (V tensor view, ldv, strideV) when every
+        problem reached its component count inside the block with converged Ritz pairs, else
+        None (the caller falls back to the full solver)."""
+        ctx = self.ctx
+        nws = int(ctx.lib.cpsd_eig_topk_ws_elems(n_pad, m, nprob))
+        ws = self.ws(tag + '_tkws', (nws,))
+        tot = self.ws(tag + '_tktot', (nprob,))
+        resid = self.ws(tag + '_tkres', (nprob, m))
+        status = self.ws(tag + '_tkst', (nprob,), I32)
+        voff = int(ctx.lib.cpsd_eig_topk_voff(n_pad, m, nprob))
+        V = ws[voff:voff + nprob * 2 * n_pad * m]
+        info = {'rounds': 0, 'ok': False}
+        self.stats['topk'] = info
+        for rnd in range(self.topk_rounds):
+            ctx.call('cpsd_eig_sym_topk', ptr(K), n_pad, n_pad * n_pad, n_pad, _p(n_dev), 0, nprob,
+                     m, self.topk_iters, 1 if rnd == 0 else 0, ptr(ws), ptr(evals),
+                     evals.shape[-1], ptr(tot), ptr(resid), ptr(status), self.eig_sweeps + 3,
+                     self.eig_tol)
+            ctx.call('cpsd_select_k_total', ptr(evals), evals.shape[-1], ptr(None), m, ptr(tot),
+                     thr, mode, 1, min(kcap, m), ptr(k2), 1, nprob)
+            k2h = k2.cpu().numpy()
+            rh = resid.cpu().numpy()
+            ev0 = evals[:, 0].cpu().numpy()
+            info['rounds'] = rnd + 1
+            if status.cpu().numpy().any():
+                return None                       # rank-deficient block
+            if mode == 0 and (k2h >= m - 8).any():
+                return None                       # variance threshold not crossed inside the block
+            worst = max(float(rh[f, :k2h[f]].max()) / max(float(ev0[f]), 1e-30)
+                        for f in range(nprob))
+            info['resid'] = worst
+            if worst <= self.topk_tol:
+                info['ok'] = True
+                self._k2_max = max(int(k2h.max()), 1)
+                return V, m, 2 * n_pad * m
+        return None
 
     def scatter(self, name, nprob, n_pad):
         """Workspace + kernel name for a batch of scatter matrices that feed an eigen-solver:
@@ -433,32 +483,45 @@ class CVEngine:
             mode, thr = 0, float(self.decoder_var)
         else:
             mode, thr = 3, float(int(self.decoder_var))
-        V = self.ws('pool_V', (B, n_pad, n_pad))
-        if n_pad <= 128:
-            self.eig_small(Kall, npool_dev, 0, B, n_pad, evals, V, n_pad)
-            sweeps = None
-        else:
-            perm = self.ws('pool_perm', (B, n_pad), I32)
-            sweeps = self.eig_block(Kall, n_pad, npool_dev, 0, B, evals, perm, 'pool')
-        self.mark('pool_eigvecs')
-        ctx.call('cpsd_select_k', ptr(evals), n_pad, npool_dev, 0, thr, mode, 1, kcap, ptr(k2), 1,
-                 B)
-        if n_pad > 128:
-            # eigenvectors of the k2 retained components only (rotation-log replay); one small
-            # read-back sizes the replay grid to the columns actually kept
-            self._k2_max = max(int(k2.cpu().numpy().max()), 1)
-            k_launch = min(kcap, _ceil(self._k2_max, 64))
-            self.eig_vecs('pool', n_pad, B, perm, k2, 0, k_launch, V)
-        else:
-            self._k2_max = kcap
-        self.mark('pool_scores')
+        ldv, sV = n_pad, n_pad * n_pad
+        sweeps = None
+        V = None
+        m = self.topk_block
+        use_topk = (self.pool_solver != 'full' and n_pad > 128 and mode in (0, 3)
+                    and (mode == 0 or int(thr) <= m - 8)
+                    and (self.pool_solver == 'topk'
+                         or (min(n_pool) - 1 >= 2 * m and F >= 2 * m)))
         perm_p = ptr(None)
+        if use_topk:
+            got = self.eig_topk(Kall, n_pad, npool_dev, B, m, evals, 'pool', thr, mode, kcap, k2)
+            if got is not None:
+                V, ldv, sV = got
+            self.mark('pool_eigvecs')
+        if V is None:
+            V = self.ws('pool_V', (B, n_pad, n_pad))
+            if n_pad <= 128:
+                self.eig_small(Kall, npool_dev, 0, B, n_pad, evals, V, n_pad)
+            else:
+                perm = self.ws('pool_perm', (B, n_pad), I32)
+                sweeps = self.eig_block(Kall, n_pad, npool_dev, 0, B, evals, perm, 'pool')
+            self.mark('pool_eigvecs')
+            ctx.call('cpsd_select_k', ptr(evals), n_pad, npool_dev, 0, thr, mode, 1, kcap, ptr(k2),
+                     1, B)
+            if n_pad > 128:
+                # eigenvectors of the k2 retained components only (rotation-log replay); one
+                # small read-back sizes the replay grid to the columns actually kept
+                self._k2_max = max(int(k2.cpu().numpy().max()), 1)
+                k_launch = min(kcap, _ceil(self._k2_max, 64))
+                self.eig_vecs('pool', n_pad, B, perm, k2, 0, k_launch, V)
+            else:
+                self._k2_max = kcap
+        self.mark('pool_scores')
         St = self.ws('pool_St', (B, kcap, n_pad))
         Ste = self.ws('pool_Ste', (B, kcap, n_te_max))
-        ctx.call('cpsd_scores_train', ptr(V), n_pad, n_pad * n_pad, ptr(evals), perm_p, n_pad,
+        ctx.call('cpsd_scores_train', ptr(V), ldv, sV, ptr(evals), perm_p, n_pad,
                  ptr(k2), npool_dev, 0, max(n_pool), ptr(St), n_pad, kcap * n_pad, kcap, B)
-        ctx.call('cpsd_scores_test', ptr(Kte), n_pad, n_te_max * n_pad, ptr(V), n_pad,
-                 n_pad * n_pad, ptr(evals), perm_p, n_pad, ptr(k2), npool_dev, 0, n_te_max,
+        ctx.call('cpsd_scores_test', ptr(Kte), n_pad, n_te_max * n_pad, ptr(V), ldv,
+                 sV, ptr(evals), perm_p, n_pad, ptr(k2), npool_dev, 0, n_te_max,
                  ptr(Ste), n_te_max, kcap * n_te_max, kcap, B)
         return evals, k2, St, Ste, V, sweeps, kcap
 

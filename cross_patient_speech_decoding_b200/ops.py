@@ -77,15 +77,75 @@ def eig_sym(A, n=None, max_sweeps=15, tol=3e-7, device=None, return_sweeps=False
     return (ev, V, sweeps) if return_sweeps else (ev, V)
 
 
-def select_k(evals, thr, mode, n=None, kmin=0, kmax=1 << 30, device=None):
+def sgemm_batched(A, B, trans_a=False, alpha=1.0, device=None):
+    """C[b] = alpha * op(A[b]) @ B[b] (fp32).  trans_a: A[b] is stored (K, M)."""
+    ctx = _ctx(device)
+    A = np.ascontiguousarray(A, dtype=np.float32)
+    B = np.ascontiguousarray(B, dtype=np.float32)
+    nprob = A.shape[0]
+    Kd, M = (A.shape[1], A.shape[2]) if trans_a else (A.shape[2], A.shape[1])
+    N = B.shape[2]
+    assert B.shape[1] == Kd
+    Ad, Bd = ctx.upload(A), ctx.upload(B)
+    C = ctx.empty((nprob, M, N))
+    ctx.call('cpsd_sgemm_batched', int(bool(trans_a)), M, N, Kd, float(alpha), ptr(Ad), A.shape[2],
+             A.shape[1] * A.shape[2], ptr(Bd), N, Kd * N, ptr(C), N, M * N, nprob)
+    return C.cpu().numpy()
+
+
+def chol_inv(S, device=None):
+    """Inverse of the upper Cholesky factor: S[b] = R^T R -> (R^{-1} (nprob, m, m), status)."""
+    ctx = _ctx(device)
+    S = np.ascontiguousarray(S, dtype=np.float32)
+    nprob, m, _ = S.shape
+    Sd = ctx.upload(S)
+    Rinv = ctx.empty((nprob, m, m))
+    st = ctx.zeros((nprob,), I32)
+    ctx.call('cpsd_chol_inv', ptr(Sd), m, m * m, m, ptr(Rinv), m, m * m, ptr(st), nprob)
+    return Rinv.cpu().numpy(), st.cpu().numpy()
+
+
+def eig_topk(A, m=128, iters=8, rounds=1, n=None, max_sweeps=15, tol=3e-7, device=None):
+    """Leading m eigen-pairs of symmetric PSD matrices A (nprob, n, n) by subspace iteration.
+    Returns dict(evals (nprob, m), V (nprob, n, m), total, resid (nprob, m), status)."""
+    ctx = _ctx(device)
+    A = np.asarray(A, dtype=np.float32)
+    nprob, nn, _ = A.shape
+    n_pad = _ceil(nn, 128)
+    ns = np.full(nprob, nn, dtype=np.int32) if n is None else np.asarray(n, dtype=np.int32)
+    Ap = np.zeros((nprob, n_pad, n_pad), dtype=np.float32)
+    Ap[:, :nn, :nn] = A
+    Ad, nd = ctx.upload(Ap), ctx.upload(ns)
+    ws = ctx.empty((int(ctx.lib.cpsd_eig_topk_ws_elems(n_pad, m, nprob)),))
+    evals = ctx.empty((nprob, n_pad))
+    tot, resid = ctx.empty((nprob,)), ctx.empty((nprob, m))
+    st = ctx.zeros((nprob,), I32)
+    for r in range(rounds):
+        ctx.call('cpsd_eig_sym_topk', ptr(Ad), n_pad, n_pad * n_pad, n_pad, ptr(nd), 0, nprob, m,
+                 iters, 1 if r == 0 else 0, ptr(ws), ptr(evals), n_pad, ptr(tot), ptr(resid),
+                 ptr(st), max_sweeps, tol)
+    voff = int(ctx.lib.cpsd_eig_topk_voff(n_pad, m, nprob))
+    V = ws[voff:voff + nprob * 2 * n_pad * m].view(nprob, 2 * n_pad, m)[:, :nn, :]
+    return dict(evals=evals.cpu().numpy()[:, :m], V=V.cpu().numpy(), total=tot.cpu().numpy(),
+                resid=resid.cpu().numpy(), status=st.cpu().numpy())
+
+
+def select_k(evals, thr, mode, n=None, kmin=0, kmax=1 << 30, device=None, total=None):
+    """Component count from descending spectra; ``total``: per-problem total variance when only
+    the leading eigenvalues are given."""
     ctx = _ctx(device)
     ev = np.atleast_2d(np.asarray(evals, dtype=np.float32))
     nprob, ld = ev.shape
     ns = np.full(nprob, ld, dtype=np.int32) if n is None else np.asarray(n, dtype=np.int32)
     evd, nd = ctx.upload(ev), ctx.upload(ns)
     k = ctx.empty((nprob,), I32)
-    ctx.call('cpsd_select_k', ptr(evd), ld, ptr(nd), 0, float(thr), int(mode), int(kmin), int(kmax),
-             ptr(k), 1, nprob)
+    if total is not None:
+        td = ctx.upload(np.asarray(total, dtype=np.float32))
+        ctx.call('cpsd_select_k_total', ptr(evd), ld, ptr(nd), 0, ptr(td), float(thr), int(mode),
+                 int(kmin), int(kmax), ptr(k), 1, nprob)
+    else:
+        ctx.call('cpsd_select_k', ptr(evd), ld, ptr(nd), 0, float(thr), int(mode), int(kmin),
+                 int(kmax), ptr(k), 1, nprob)
     return k.cpu().numpy()
 
 

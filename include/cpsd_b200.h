@@ -120,6 +120,32 @@ int cpsd_bj_eigvecs(const float* Rlog, int n_pad, int nprob, const int* pairs_de
  * (mode 1, AlignMCCA.py:174), NoCenterPCA (mode 2, NoCenterPCA.py:101-103), integer (mode 3) */
 int cpsd_select_k(const float* evals, int ld_e, const int* n_dev, int n_fixed, float thr, int mode,
                   int kmin, int kmax, int* k_out, int k_stride, int nprob, cudaStream_t stream);
+/* same selection from the leading n eigenvalues only, total variance (trace) given */
+int cpsd_select_k_total(const float* evals, int ld_e, const int* n_dev, int n_fixed,
+                        const float* total_dev, float thr, int mode, int kmin, int kmax, int* k_out,
+                        int k_stride, int nprob, cudaStream_t stream);
+/* Leading m (<= 128) eigen-pairs of symmetric PSD matrices by block subspace iteration
+ * (Y = K Q, Cholesky QR) + Rayleigh-Ritz: the decoder-stage PCA with a float n_components
+ * (decomposition/DimRedReshape.py:47-49 -> sklearn PCA) keeps only the components that explain
+ * the requested variance, and the total variance is the trace.  K's padding (rows / columns
+ * >= n) is zeroed, K is otherwise preserved.  ws: cpsd_eig_topk_ws_elems() floats; the
+ * eigenvectors land at ws + cpsd_eig_topk_voff() as (n_pad x m) per problem, row stride m,
+ * problem stride 2*n_pad*m.  resid[prob][j] = ||K v_j - theta_j v_j||; status bit 0 = the
+ * block lost rank.  init = 0 continues from the Ritz vectors of the previous call. */
+long long cpsd_eig_topk_ws_elems(int n_pad, int m, int nprob);
+long long cpsd_eig_topk_voff(int n_pad, int m, int nprob);
+int cpsd_eig_sym_topk(float* K, int ld, long long stride, int n_pad, const int* n_dev, int n_fixed,
+                      int nprob, int m, int iters, int init, float* ws, float* evals, int ld_e,
+                      float* total, float* resid, int* status, int eig_sweeps, float eig_tol,
+                      cudaStream_t stream);
+/* building blocks of the above, exported for the kernel-level parity tests:
+ * C = alpha op(A) B (batched, element strides; trans_a: A stored K x M), and the inverse of
+ * the upper Cholesky factor of an m x m (m <= 128) Gram (fp64 in shared memory). */
+int cpsd_sgemm_batched(int trans_a, int M, int N, int K, float alpha, const float* A, int lda,
+                       long long strideA, const float* B, int ldb, long long strideB, float* C,
+                       int ldc, long long strideC, int nprob, cudaStream_t stream);
+int cpsd_chol_inv(const float* S, int lds, long long strideS, int m, float* Rinv, int ldr,
+                  long long strideR, int* status, int nprob, cudaStream_t stream);
 /* PCA components with sklearn's svd_flip sign convention, zero padded to dmax columns */
 int cpsd_pca_basis(const float* evecs, int ldv, long long strideV, const int* k_dev,
                    const int* cdim, int c_fixed, int dmax, float* W, int ldw, int Cmax, int nprob,

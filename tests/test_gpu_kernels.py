@@ -297,3 +297,88 @@ def test_gram_tn_f64_accumulation(ops):
     G = out.cpu().numpy()
     ref = A.astype(np.float64).T @ A.astype(np.float64)
     assert np.abs(G - ref).max() <= 1e-12 * np.abs(ref).max()
+
+
+# ------------------------------------------------------------------ subspace (top-k) solver
+@pytest.mark.parametrize('trans_a', [False, True])
+@pytest.mark.parametrize('shape', [(128, 64, 16), (1152, 128, 1152), (130, 70, 37), (5, 3, 2),
+                                   (256, 128, 128)])
+def test_sgemm_batched(ops, shape, trans_a):
+    M, N, K = shape
+    rng = np.random.default_rng(M + N + K)
+    A = rng.standard_normal((3, K, M) if trans_a else (3, M, K))
+    B = rng.standard_normal((3, K, N))
+    C = ops.sgemm_batched(A, B, trans_a=trans_a, alpha=0.5)
+    ref = 0.5 * np.einsum('bkm,bkn->bmn' if trans_a else 'bmk,bkn->bmn', A, B)
+    assert np.abs(C - ref).max() <= 2e-6 * np.sqrt(K) * np.abs(ref).max() + 1e-6
+
+
+@pytest.mark.parametrize('m', [4, 33, 128])
+def test_chol_inv(ops, m):
+    rng = np.random.default_rng(m)
+    Y = rng.standard_normal((4, 3 * m + 5, m)) * np.linspace(1.0, 30.0, m)
+    S = np.einsum('bkm,bkn->bmn', Y, Y)
+    Rinv, st = ops.chol_inv(S)
+    assert not st.any()
+    for b in range(4):
+        R = np.linalg.cholesky(S[b]).T
+        ref = np.linalg.inv(R)
+        assert np.abs(Rinv[b] - ref).max() <= 1e-5 * np.abs(ref).max()
+        assert np.abs(np.tril(Rinv[b], -1)).max() == 0.0
+    # rank-deficient Gram is flagged, output stays finite
+    S[1] = np.outer(np.ones(m), np.ones(m))
+    Rinv, st = ops.chol_inv(S)
+    assert st[1] == 1 and st[0] == 0 and np.isfinite(Rinv).all()
+
+
+def _pooled_like(rng, n, F, decay):
+    X = rng.standard_normal((n, F)) * decay[None, :F]
+    X -= X.mean(axis=0)
+    return X @ X.T
+
+
+@pytest.mark.parametrize('n', [300, 1144])
+def test_eig_topk_leading_pairs(ops, n):
+    rng = np.random.default_rng(n)
+    decay = 1.0 / (1.0 + np.arange(4000) / 20.0)
+    A = np.stack([_pooled_like(rng, n, 4000, decay) for _ in range(3)])
+    out = ops.eig_topk(A, m=128, iters=8)
+    assert not out['status'].any()
+    for b in range(3):
+        w, U = np.linalg.eigh(A[b])
+        w, U = w[::-1], U[:, ::-1]
+        assert abs(out['total'][b] - np.trace(A[b])) <= 1e-5 * np.trace(A[b])
+        k = 64
+        assert np.abs(out['evals'][b, :k] - w[:k]).max() <= 2e-5 * w[0]
+        V = out['V'][b][:, :k]
+        assert np.abs(V.T @ V - np.eye(k)).max() < 1e-4
+        assert out['resid'][b, :k].max() <= 2e-5 * w[0]
+        # same invariant subspace as LAPACK: principal angles ~ 0
+        sv = np.linalg.svd(U[:, :k].T @ V, compute_uv=False)
+        assert sv.min() > 1 - 1e-6
+
+
+def test_eig_topk_resume_and_ragged(ops):
+    rng = np.random.default_rng(5)
+    ns = np.array([260, 300], dtype=np.int32)
+    decay = 1.0 / (1.0 + np.arange(2000) / 60.0)      # slow decay: one round is not enough
+    A = np.zeros((2, 300, 300))
+    for b, n in enumerate(ns):
+        A[b, :n, :n] = _pooled_like(rng, n, 2000, decay)
+        A[b, n:, :] = 7.0                              # garbage in the padding must be ignored
+        A[b, :, n:] = 7.0
+    one = ops.eig_topk(A, m=64, iters=2, rounds=1, n=ns)
+    more = ops.eig_topk(A, m=64, iters=2, rounds=6, n=ns)
+    for b, n in enumerate(ns):
+        w = np.linalg.eigvalsh(A[b, :n, :n])[::-1]
+        assert more['resid'][b, :20].max() < one['resid'][b, :20].max()
+        assert np.abs(more['evals'][b, :20] - w[:20]).max() <= 2e-5 * w[0]
+        if n < A.shape[1]:
+            assert np.abs(more['V'][b][n:, :]).max() == 0.0
+
+
+def test_select_k_total(ops):
+    ev = np.array([[5.0, 3.0, 1.0, 0.5]], dtype=np.float32)
+    # mode 0: k = #{cumulative ratio <= thr} + 1
+    assert ops.select_k(ev, 0.82, 0, total=[10.0])[0] == 3    # ratios .5 .8 .9 .95 of the given total
+    assert ops.select_k(ev, 0.82, 0)[0] == 2                  # ratios .526 .842 ... of their own sum
