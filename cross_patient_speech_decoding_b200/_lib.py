@@ -83,6 +83,7 @@ _SIGS = {
     'cpsd_chol_inv': [_P, c_int, c_ll, c_int, _P, c_int, c_ll, _P, c_int, _P],
     'cpsd_gram_tn': [_P, c_int, c_int, c_int, _P],
     'cpsd_gram_tn_f64': [_P, c_int, c_int, c_int, _P],
+    'cpsd_gram_tn_f64_split': [_P, c_int, c_int, c_int, c_int, _P],
     'cpsd_colsum': [_P, c_int, c_int, _P],
     'cpsd_proj_nn': [_P, c_int, c_int, c_int, c_int, _P],
     'cpsd_gram_nt': [_P, c_int, c_int, c_int, _P],
@@ -92,6 +93,8 @@ _SIGS = {
     'cpsd_cast_f64_f32': [_P, _P, c_ll, _P],
     'cpsd_permute_cols': [_P, c_int, c_ll, _P, c_int, _P, c_int, c_ll, c_int, c_int, c_int, _P],
     'cpsd_mcca_mask': [_P, c_int, c_ll, _P, c_int, _P, _P, c_int, c_int, _P, _P, _P, c_int, _P],
+    'cpsd_mcca_mask_idx': [_P, c_int, c_ll, _P, c_int, _P, _P, _P, c_int, c_int, _P, _P, _P, c_int,
+                           _P],
     'cpsd_mcca_build': [_P, c_int, c_ll, _P, c_int, c_int, c_float, _P, c_int, c_ll, _P, _P, _P,
                         c_int, _P, c_int, _P],
     'cpsd_mcca_loadings': [_P, _P, c_int, c_ll, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, _P,

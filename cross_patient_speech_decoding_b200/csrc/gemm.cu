@@ -21,13 +21,17 @@ namespace {
 // ------------------------------------------------------------------------------ gram_tn
 #define GT_TILE 64
 #define GT_RK 16
+// nsplit > 1: the segments are dealt round-robin to nsplit CTAs per output tile (blockIdx.x =
+// tile + tiles_x * split) which accumulate into a ZEROED output with atomics -- for batches
+// with few problems and many rows (the per-fold target scatter: 4 tiles x 27 400 rows).
 template <typename AccT>
 __global__ void __launch_bounds__(256)
-k_gram_tn(const cpsd_gram_tn_desc* __restrict__ descs) {
+k_gram_tn(const cpsd_gram_tn_desc* __restrict__ descs, int tiles_x, int nsplit) {
   const cpsd_gram_tn_desc d = descs[blockIdx.z];
-  const int i0 = blockIdx.y * GT_TILE, j0 = blockIdx.x * GT_TILE;
+  const int bx = blockIdx.x % tiles_x, split = blockIdx.x / tiles_x;
+  const int i0 = blockIdx.y * GT_TILE, j0 = bx * GT_TILE;
   if (i0 >= d.p || j0 >= d.q) return;
-  if ((d.sym & 1) && blockIdx.y > blockIdx.x) return;
+  if ((d.sym & 1) && blockIdx.y > bx) return;
   __shared__ __align__(16) float As[GT_RK][GT_TILE];
   __shared__ __align__(16) float Bs[GT_RK][GT_TILE];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -45,7 +49,7 @@ k_gram_tn(const cpsd_gram_tn_desc* __restrict__ descs) {
   const float ma = (va && d.muA) ? d.muA[ca] : 0.f;
   const float mb = (vb && d.muB) ? d.muB[cb] : 0.f;
 
-  for (int s = 0; s < d.nseg; ++s) {
+  for (int s = split; s < d.nseg; s += nsplit) {
     const long long ra = d.segA[s], rb = d.segB ? d.segB[s] : ra;
     for (int r0 = 0; r0 < d.seg_len; r0 += GT_RK) {
 #pragma unroll
@@ -83,8 +87,13 @@ k_gram_tn(const cpsd_gram_tn_desc* __restrict__ descs) {
       const int gj = j0 + tx * 4 + j;
       if (gj >= d.q) continue;
       const AccT v = (AccT)d.alpha * acc[i][j];
-      out[(long long)gi * d.ldo + gj] = v;
-      if ((d.sym & 1) && blockIdx.y != blockIdx.x) out[(long long)gj * d.ldo + gi] = v;
+      if (nsplit > 1) {
+        atomicAdd(&out[(long long)gi * d.ldo + gj], v);
+        if ((d.sym & 1) && blockIdx.y != bx) atomicAdd(&out[(long long)gj * d.ldo + gi], v);
+      } else {
+        out[(long long)gi * d.ldo + gj] = v;
+        if ((d.sym & 1) && blockIdx.y != bx) out[(long long)gj * d.ldo + gi] = v;
+      }
     }
   }
 }
@@ -279,7 +288,7 @@ extern "C" int cpsd_gram_tn(const cpsd_gram_tn_desc* descs_dev, int nprob, int p
   if (nprob == 0) return CPSD_OK;
   CPSD_CHECK_ARG(nprob <= 65535, "gram_tn: nprob > 65535");
   dim3 grid((q_max + GT_TILE - 1) / GT_TILE, (p_max + GT_TILE - 1) / GT_TILE, nprob);
-  k_gram_tn<float><<<grid, 256, 0, stream>>>(descs_dev);
+  k_gram_tn<float><<<grid, 256, 0, stream>>>(descs_dev, grid.x, 1);
   CPSD_LAUNCH_CHECK();
   return CPSD_OK;
 }
@@ -293,7 +302,22 @@ extern "C" int cpsd_gram_tn_f64(const cpsd_gram_tn_desc* descs_dev, int nprob, i
   if (nprob == 0) return CPSD_OK;
   CPSD_CHECK_ARG(nprob <= 65535, "gram_tn_f64: nprob > 65535");
   dim3 grid((q_max + GT_TILE - 1) / GT_TILE, (p_max + GT_TILE - 1) / GT_TILE, nprob);
-  k_gram_tn<double><<<grid, 256, 0, stream>>>(descs_dev);
+  k_gram_tn<double><<<grid, 256, 0, stream>>>(descs_dev, grid.x, 1);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
+
+// fp64 accumulation with the segments of every problem split over nsplit CTAs per tile; the
+// outputs must be ZERO on entry (partial sums are added with fp64 atomics).
+extern "C" int cpsd_gram_tn_f64_split(const cpsd_gram_tn_desc* descs_dev, int nprob, int p_max,
+                                      int q_max, int nsplit, cudaStream_t stream) {
+  CPSD_CHECK_ARG(nprob >= 0 && p_max > 0 && q_max > 0, "gram_tn_f64_split: bad dims");
+  CPSD_CHECK_ARG(nsplit >= 1 && nsplit <= 64, "gram_tn_f64_split: nsplit must be in 1..64");
+  if (nprob == 0) return CPSD_OK;
+  CPSD_CHECK_ARG(nprob <= 65535, "gram_tn_f64_split: nprob > 65535");
+  const int tx = (q_max + GT_TILE - 1) / GT_TILE;
+  dim3 grid(tx * nsplit, (p_max + GT_TILE - 1) / GT_TILE, nprob);
+  k_gram_tn<double><<<grid, 256, 0, stream>>>(descs_dev, tx, nsplit);
   CPSD_LAUNCH_CHECK();
   return CPSD_OK;
 }

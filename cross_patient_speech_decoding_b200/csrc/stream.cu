@@ -102,22 +102,23 @@ k_permute_cols(const float* __restrict__ src, int lds, long long strideS,
 __global__ void __launch_bounds__(128)
 k_mcca_mask(const float* __restrict__ evecs, int ldv, long long strideV,
             const float* __restrict__ evals, int ld_e, const int* __restrict__ rank,
-            const int* __restrict__ cdim, int R, int Cmax, float* __restrict__ Vr,
-            float* __restrict__ d2, int* __restrict__ r_eff) {
+            const int* __restrict__ cdim, const int* __restrict__ src_idx, int R, int Cmax,
+            float* __restrict__ Vr, float* __restrict__ d2, int* __restrict__ r_eff) {
   const int p = blockIdx.x;  // fold * P + view
+  const int sp = src_idx ? src_idx[p] : p;   // where this problem's eigen-pairs live
   const int C = cdim[p];
   int r = rank ? rank[p] : R;
   if (r > R) r = R;
   if (r > C) r = C;
   if (r < 0) r = 0;
-  const float* V = evecs + (long long)p * strideV;
+  const float* V = evecs + (long long)sp * strideV;
   float* o = Vr + (long long)p * Cmax * R;
   for (int e = threadIdx.x; e < Cmax * R; e += blockDim.x) {
     const int c = e / R, j = e - c * R;
     o[e] = (c < C && j < r) ? V[(long long)c * ldv + j] : 0.f;
   }
   for (int j = threadIdx.x; j < R; j += blockDim.x)
-    d2[(long long)p * R + j] = (j < r) ? fmaxf(evals[(long long)p * ld_e + j], 0.f) : 0.f;
+    d2[(long long)p * R + j] = (j < r) ? fmaxf(evals[(long long)sp * ld_e + j], 0.f) : 0.f;
   if (threadIdx.x == 0) r_eff[p] = r;
 }
 
@@ -312,8 +313,23 @@ extern "C" int cpsd_mcca_mask(const float* evecs, int ldv, long long strideV, co
                               float* Vr, float* d2, int* r_eff, int nprob, cudaStream_t stream) {
   CPSD_CHECK_ARG(nprob >= 0 && R > 0 && Cmax > 0, "mcca_mask: bad dims");
   if (nprob == 0) return CPSD_OK;
-  k_mcca_mask<<<nprob, 128, 0, stream>>>(evecs, ldv, strideV, evals, ld_e, rank, cdim, R, Cmax, Vr,
-                                         d2, r_eff);
+  k_mcca_mask<<<nprob, 128, 0, stream>>>(evecs, ldv, strideV, evals, ld_e, rank, cdim, nullptr, R,
+                                         Cmax, Vr, d2, r_eff);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
+
+// Same, with the eigen-pairs of problem p read from slot src_idx[p] of evecs / evals: the
+// view statistics of the cross patients do not depend on the fold, so many (fold, view)
+// problems share one solved slot.
+extern "C" int cpsd_mcca_mask_idx(const float* evecs, int ldv, long long strideV, const float* evals,
+                                  int ld_e, const int* rank, const int* cdim, const int* src_idx,
+                                  int R, int Cmax, float* Vr, float* d2, int* r_eff, int nprob,
+                                  cudaStream_t stream) {
+  CPSD_CHECK_ARG(nprob >= 0 && R > 0 && Cmax > 0, "mcca_mask_idx: bad dims");
+  if (nprob == 0) return CPSD_OK;
+  k_mcca_mask<<<nprob, 128, 0, stream>>>(evecs, ldv, strideV, evals, ld_e, rank, cdim, src_idx, R,
+                                         Cmax, Vr, d2, r_eff);
   CPSD_LAUNCH_CHECK();
   return CPSD_OK;
 }

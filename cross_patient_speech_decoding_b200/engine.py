@@ -181,13 +181,18 @@ class CVEngine:
                       ptr(perm), n_pad, _p(k_dev), k_fixed, k_launch, ptr(E), n_pad, n_pad * n_pad,
                       self.eig_sweeps)
 
-    def eig_any(self, A, n_pad, n_dev, n_fixed, nprob, tag, ncols=None, vecs=True):
+    def eig_any(self, A, n_pad, n_dev, n_fixed, nprob, tag, ncols=None, vecs=True, out=None):
         """Sorted eigen-decomposition for any n_pad (A: (nprob, n_pad, n_pad), destroyed).
         A float64 tensor (n_pad <= 128 only) selects the fp64-matrix solver.
         Returns (evals (nprob, n_pad), evecs (nprob, n_pad, n_pad) with sorted columns; for
         n_pad > 128 only the leading ``ncols`` columns are computed)."""
-        evals = self.ws(tag + '_ev', (nprob, n_pad))
-        evecs = self.ws(tag + '_evec', (nprob, n_pad, n_pad))
+        if out is not None:      # caller-owned (nprob, n_pad) / (nprob, n_pad, n_pad) outputs
+            evals, evecs = out
+        else:
+            evals = self.ws(tag + '_ev', (nprob, n_pad))
+            evecs = self.ws(tag + '_evec', (nprob, n_pad, n_pad))
+        if nprob == 0:
+            return evals, evecs
         if A.dtype == torch.float64:
             assert n_pad <= 128
             self.ctx.call('cpsd_eig_sym_small_f64', ptr(A), n_pad, n_pad * n_pad, _p(n_dev),
@@ -241,6 +246,37 @@ class CVEngine:
                 self._k2_max = max(int(k2h.max()), 1)
                 return V, m, 2 * n_pad * m
         return None
+
+    def _view_slots(self, B, n_pad, Cm):
+        """Per-view statistics of the MCCA fit (mean, spectrum and eigenvectors of the centred
+        condition-average scatter) live in slots: [0, res) are the per-fold target problems of
+        the current batch, the rest caches the cross patients' problems keyed by (view, shared
+        class set) -- they do not depend on the fold (AlignMCCA.py:140-154 recomputes them for
+        every fold; here they are solved once and reused)."""
+        vs = getattr(self, '_vs', None)
+        if vs is None or vs['res'] < B or vs['npad'] != n_pad:
+            res = max(B, self.max_batch)
+            cap = res + max(512, res * max(self.P - 1, 1))
+            vs = dict(res=res, cap=cap, npad=n_pad, keys={}, next=res,
+                      mu=self.ctx.zeros((cap, Cm)), ev=self.ctx.zeros((cap, n_pad)),
+                      evec=self.ctx.zeros((cap, n_pad, n_pad)))
+            self._vs = vs
+        return vs
+
+    def _slot_means(self, mu, slot, Cm):
+        idx = torch.from_numpy(slot.ravel()).to(mu.device)
+        return mu[idx].view(slot.shape[0], slot.shape[1], Cm).cpu().numpy()
+
+    def gram_scatter(self, kernel, descs, nprob, p, q, out, tiles):
+        """Launches a scatter-matrix Gram; the fp64 variant splits the row segments over
+        several CTAs per tile when the batch alone cannot fill the GPU."""
+        if kernel == 'cpsd_gram_tn_f64':
+            nsplit = min(16, max(1, 592 // max(nprob * tiles, 1)))
+            if nsplit > 1:
+                out.zero_()
+                self.ctx.call('cpsd_gram_tn_f64_split', descs, nprob, p, q, nsplit)
+                return
+        self.ctx.call(kernel, descs, nprob, p, q)
 
     def scatter(self, name, nprob, n_pad):
         """Workspace + kernel name for a batch of scatter matrices that feed an eigen-solver:
@@ -579,6 +615,30 @@ class CVEngine:
         ranks = np.zeros((B, P), dtype=np.int32)
         ranks[:, 1:] = self.cross_rank[None, :]
         o_rank = pk.add_ints(ranks)
+        # slot of every (fold, view) problem; solve list = targets + cache misses
+        n_padC = 128 if Cm <= 128 else _ceil(Cm, 128)
+        vs = self._view_slots(B, n_padC, Cm)
+        if vs['next'] + B * (P - 1) > vs['cap']:
+            vs['keys'].clear()
+            vs['next'] = vs['res']
+        slot = np.zeros((B, P), dtype=np.int64)
+        slot[:, 0] = np.arange(B)
+        solve = [(f, 0, f) for f in range(B)]
+        pending = {}
+        for f in range(B):
+            kb = shared[f].tobytes()
+            for v in range(1, P):
+                key = (v, kb)
+                sl = vs['keys'].get(key)
+                if sl is None:
+                    sl = pending.get(key)
+                    if sl is None:
+                        sl = vs['next'] + len(pending)
+                        pending[key] = sl
+                        solve.append((f, v, sl))
+                slot[f, v] = sl
+        o_slot = pk.add_ints(slot)
+        o_cds = pk.add_ints([self.views[v].C for _, v, _ in solve])
         # pooled layout
         n_tr = [len(tb['tr']) for tb in tabs]
         n_te = [len(tb['te']) for tb in tabs]
@@ -616,27 +676,27 @@ class CVEngine:
         cm_base = lambda f, v: (addr(cmT, f * Kmax * T * tv.C) if v == 0 else addr(self.cm[v]))
         n_padC = 128 if Cm <= 128 else _ceil(Cm, 128)
         Gt, gram_c = self.scatter('m_Gt', B, n_padC)
-        mu = self.ws('m_mu', (B * P, Cm))
-        cov, _ = self.scatter('m_cov', B * P, n_padC)
+        nS = len(solve)
+        mu = vs['mu']
+        mu_of = lambda f, v: addr(mu, int(slot[f, v]) * Cm)
+        cov, _ = self.scatter('m_cov', nS, n_padC)
         if Cm < n_padC:
             cov.zero_()
             Gt.zero_()
         r_gt = np.zeros(B, dtype=_lib.GRAM_TN_DESC)
-        r_mu = np.zeros(B * P, dtype=_lib.COLSUM_DESC)
-        r_cov = np.zeros(B * P, dtype=_lib.GRAM_TN_DESC)
+        r_mu = np.zeros(nS, dtype=_lib.COLSUM_DESC)
+        r_cov = np.zeros(nS, dtype=_lib.GRAM_TN_DESC)
         for f, tb in enumerate(tabs):
             r_gt[f] = (addr(tv.X), addr(tv.X), pk.iaddr(tb['o_tr']), pk.iaddr(tb['o_tr']), 0, 0,
                        addr(Gt, f * n_padC * n_padC), n_tr[f], T, tv.C, tv.C, tv.C, tv.C, n_padC,
                        1, 1.0, 0)
-            for v in range(P):
-                C = self.views[v].C
-                i = f * P + v
-                sg = pk.iaddr(o_seg[f, v])
-                r_mu[i] = (cm_base(f, v), sg, addr(mu, i * Cm), Ks[f], T, C, C,
-                           1.0 / (Ks[f] * T), 0)
-                r_cov[i] = (cm_base(f, v), cm_base(f, v), sg, sg, addr(mu, i * Cm),
-                            addr(mu, i * Cm), addr(cov, i * n_padC * n_padC), Ks[f], T, C, C, C, C,
-                            n_padC, 1, 1.0, 0)
+        for j, (f, v, sl) in enumerate(solve):
+            C = self.views[v].C
+            sg = pk.iaddr(o_seg[f, v])
+            r_mu[j] = (cm_base(f, v), sg, addr(mu, sl * Cm), Ks[f], T, C, C, 1.0 / (Ks[f] * T), 0)
+            r_cov[j] = (cm_base(f, v), cm_base(f, v), sg, sg, addr(mu, sl * Cm),
+                        addr(mu, sl * Cm), addr(cov, j * n_padC * n_padC), Ks[f], T, C, C, C, C,
+                        n_padC, 1, 1.0, 0)
         d_cm, d_gt = pk.add_descs(r_cm), pk.add_descs(r_gt)
         d_mu, d_cov = pk.add_descs(r_mu), pk.add_descs(r_cov)
         # reduced views
@@ -652,7 +712,7 @@ class CVEngine:
                 C = self.views[v].C
                 i = f * P + v
                 r_pz[i] = (cm_base(f, v), pk.iaddr(o_seg[f, v]), pk.iaddr(o_segdst),
-                           addr(mu, i * Cm), addr(Vr, i * Cm * R),
+                           mu_of(f, v), addr(Vr, i * Cm * R),
                            addr(Zcat, f * KTmax * P * R + v * R), Ks[f], T, C, R, C, R, P * R, 0)
             r_g[f] = (addr(Zcat, f * KTmax * P * R), addr(Zcat, f * KTmax * P * R),
                       pk.iaddr(self._o_zero), pk.iaddr(self._o_zero), 0, 0,
@@ -680,11 +740,11 @@ class CVEngine:
                         src = pk.iaddr(tb['o_tr'])
                     else:
                         nseg, src = vw.N, pk.iaddr(o_allseg[v])
-                    r_pp[i] = (addr(vw.X), src, pk.iaddr(o_pooldst[f, v]), addr(mu, i * Cm),
+                    r_pp[i] = (addr(vw.X), src, pk.iaddr(o_pooldst[f, v]), mu_of(f, v),
                                addr(L, i * Cm * Q), addr(Zall, f * n_pad * F), nseg, T, vw.C, Q, vw.C,
                                Q, Q, 0)
                 r_pp[B * P + f] = (addr(tv.X), pk.iaddr(tb['o_te']), pk.iaddr(o_tedst[f]),
-                                   addr(mu, f * P * Cm), addr(L, f * P * Cm * Q),
+                                   mu_of(f, 0), addr(L, f * P * Cm * Q),
                                    addr(Zall, f * n_pad * F), n_te[f], T, tv.C, Q, tv.C, Q, Q, 0)
             d_pp = pk.add_descs(r_pp)
             r1, r2, pmu, Kall = self._pooled_stage(pk, B, Zall, n_pad, F, n_pool, n_te, o_npool,
@@ -710,17 +770,28 @@ class CVEngine:
                  B * P, 0, ptr(None), 0, 1, B * P, 1, 1)
         self.mark('align_scatter_eig')
         if use_rank:
-            ctx.call(gram_c, pk.daddr(d_gt), B, tv.C, tv.C)
+            self.gram_scatter(gram_c, pk.daddr(d_gt), B, tv.C, tv.C, Gt, 3)
             ev_t, _ = self.eig_any(Gt, n_padC, ptr(None), tv.C, B, 'mrk', vecs=False)
             ctx.call('cpsd_select_k', ptr(ev_t), n_padC, ptr(None), tv.C, float(self.pca_var), 1,
                      0, 1 << 30, ptr(rank_dev), P, B)
-        # per-view centred scatter of the condition averages + eigen-decomposition
-        ctx.call('cpsd_colsum', pk.daddr(d_mu), B * P, Cm)
-        ctx.call(gram_c, pk.daddr(d_cov), B * P, Cm, Cm)
-        ev1, evec1 = self.eig_any(cov, n_padC, cdim_dev, 0, B * P, 'mv', ncols=min(n_padC, R))
-        ctx.call('cpsd_mcca_mask', ptr(evec1), n_padC, n_padC * n_padC, ptr(ev1), n_padC,
-                 ptr(rank_dev) if use_rank else ptr(None), cdim_dev, R, Cm, ptr(Vr), ptr(d2),
-                 ptr(r_eff), B * P)
+        # per-view centred scatter of the condition averages + eigen-decomposition, for the
+        # target of every fold and for the cross-patient problems not solved before
+        ctx.call('cpsd_colsum', pk.daddr(d_mu), nS, Cm)
+        self.gram_scatter(gram_c, pk.daddr(d_cov), nS, Cm, Cm, cov, 3)
+        nM, s0 = nS - B, vs['next']
+        ncol = min(n_padC, R)
+        self.eig_any(cov[:B], n_padC, ctypes_int_ptr(pk.iaddr(o_cds)), 0, B, 'mv', ncols=ncol,
+                     out=(vs['ev'][:B], vs['evec'][:B]))
+        if nM:
+            self.eig_any(cov[B:], n_padC, ctypes_int_ptr(pk.iaddr(o_cds + B)), 0, nM, 'mvx',
+                         ncols=ncol, out=(vs['ev'][s0:s0 + nM], vs['evec'][s0:s0 + nM]))
+        vs['keys'].update(pending)
+        vs['next'] += nM
+        self.stats['view_solves'] = self.stats.get('view_solves', 0) + nS
+        self.stats['view_problems'] = self.stats.get('view_problems', 0) + B * P
+        ctx.call('cpsd_mcca_mask_idx', ptr(vs['evec']), n_padC, n_padC * n_padC, ptr(vs['ev']),
+                 n_padC, ptr(rank_dev) if use_rank else ptr(None), cdim_dev,
+                 ctypes_int_ptr(pk.iaddr(o_slot)), R, Cm, ptr(Vr), ptr(d2), ptr(r_eff), B * P)
         ctx.call('cpsd_proj_nn', pk.daddr(d_pz), B * P, max(Ks), T, R)
         ctx.call('cpsd_gram_tn', pk.daddr(d_g), B, P * R, P * R)
         M = self.ws('m_M', (B, n_padM, n_padM))
@@ -743,7 +814,7 @@ class CVEngine:
             if st.any():
                 raise ValueError('MCCA: n_components=%d exceeds the total signal rank' % Q)
             return dict(loadings=L.view(B, P, Cm, Q).cpu().numpy(),
-                        mu=mu.view(B, P, Cm).cpu().numpy(), evals_mcca=evm[:, :Q].cpu().numpy(),
+                        mu=self._slot_means(mu, slot, Cm), evals_mcca=evm[:, :Q].cpu().numpy(),
                         r_eff=r_eff.view(B, P).cpu().numpy(), shared=[s_.copy() for s_ in shared])
         # project every trial of every view into the pooled (trial x time*Q) matrix
         self.mark('project_pool')
@@ -773,7 +844,7 @@ class CVEngine:
         self.stats['launches_last_batch'] = ctx.launches() - launches0
         if want_details:
             res['details'] = dict(
-                loadings=L.view(B, P, Cm, Q).cpu().numpy(), mu=mu.view(B, P, Cm).cpu().numpy(),
+                loadings=L.view(B, P, Cm, Q).cpu().numpy(), mu=self._slot_means(mu, slot, Cm),
                 evals_mcca=evm[:, :Q].cpu().numpy(), r_eff=r_eff.view(B, P).cpu().numpy(),
                 pool_evals=evals.cpu().numpy(), svm_info=info.cpu().numpy(),
                 W=W.cpu().numpy(), n_pool=list(n_pool), shared=[s.copy() for s in shared],

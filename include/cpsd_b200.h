@@ -69,6 +69,10 @@ int cpsd_gram_tn(const cpsd_gram_tn_desc* descs, int nprob, int p_max, int q_max
  * the variance thresholds and eigen-solvers of the PCA stages. */
 int cpsd_gram_tn_f64(const cpsd_gram_tn_desc* descs, int nprob, int p_max, int q_max,
                      cudaStream_t stream);
+/* fp64 accumulation, every problem's row segments dealt to nsplit CTAs per output tile (few
+ * problems x many rows); outputs must be zero on entry (fp64 atomics). */
+int cpsd_gram_tn_f64_split(const cpsd_gram_tn_desc* descs, int nprob, int p_max, int q_max,
+                           int nsplit, cudaStream_t stream);
 /* (X - mu) W: PCA.transform, AlignCCA.transform (AlignCCA.py:93), MCCA transform_view
  * (AlignMCCA.py:110,125), JointPCA.transform (JointPCA.py:132,149); output rows land
  * directly in the pooled trials x (time*latent) matrix (cross_pt_decoders.py:260-270). */
@@ -158,6 +162,11 @@ int cpsd_cca_solve(const cpsd_cca_desc* descs, int nprob, int dmax, cudaStream_t
 int cpsd_mcca_mask(const float* evecs, int ldv, long long strideV, const float* evals, int ld_e,
                    const int* rank, const int* cdim, int R, int Cmax, float* Vr, float* d2,
                    int* r_eff, int nprob, cudaStream_t stream);
+/* same with an indirection: problem p reads the eigen-pairs of slot src_idx[p] (fold-invariant
+ * view statistics of the cross patients are solved once and shared by the folds) */
+int cpsd_mcca_mask_idx(const float* evecs, int ldv, long long strideV, const float* evals, int ld_e,
+                       const int* rank, const int* cdim, const int* src_idx, int R, int Cmax,
+                       float* Vr, float* d2, int* r_eff, int nprob, cudaStream_t stream);
 int cpsd_mcca_build(const float* G, int ldg, long long strideG, const int* r_eff, int P, int R,
                     float reg, float* M, int ldm, long long strideM, int* n_out, int* cidx,
                     float* dh, int n_comp, int* status, int nfold, cudaStream_t stream);
