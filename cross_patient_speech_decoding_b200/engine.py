@@ -247,6 +247,50 @@ class CVEngine:
                 return V, m, 2 * n_pad * m
         return None
 
+    # ------------------------------------------------------------------ tensor-core projection
+    def _tc_proj_ready(self, Q):
+        """Tensor-core pooled projection (csrc/tc_proj.cu): available for <= 32 latent columns,
+        <= 128 channels (multiples of 4) and <= 16 patients.  Splits every patient into tf32
+        hi / lo once and encodes the TMA tensor maps."""
+        if not self.use_tc or Q > 32 or self.P > 16:
+            return False
+        if any(v.C > 128 or v.C % 4 for v in self.views):
+            return False
+        if getattr(self, '_tcp', None) is None:
+            ctx = self.ctx
+            maps_h = torch.zeros((2 * self.P, 128), dtype=torch.uint8).pin_memory()
+            keep = []
+            for i, vw in enumerate(self.views):
+                hi, lo = ctx.empty(vw.X.shape), ctx.empty(vw.X.shape)
+                ctx.call('cpsd_split_tf32', ptr(vw.X), ptr(hi), ptr(lo), vw.X.numel())
+                for u, t in enumerate((hi, lo)):
+                    _lib.check(ctx.lib.cpsd_tmap_encode_f32(
+                        ctypes.c_void_p(maps_h[2 * i + u].data_ptr()), ptr(t), vw.N * vw.T, vw.C,
+                        vw.C, 128), 'tmap_encode')
+                keep += [hi, lo]
+            self._tcp = dict(xmaps=maps_h.to(ctx.device), split=keep, cap=0,
+                             ntr=np.array([v.N for v in self.views], dtype=np.int32),
+                             nch=np.array([v.C for v in self.views], dtype=np.int32),
+                             sms=torch.cuda.get_device_properties(ctx.device).multi_processor_count)
+        return True
+
+    def _tc_proj_ws(self, nprob):
+        """L^T hi / lo (nprob, 32, 128), mu L (nprob, 32) and their tensor maps."""
+        tcp = self._tcp
+        if tcp['cap'] < nprob:
+            ctx = self.ctx
+            cap = max(nprob, self.max_batch * self.P)
+            tcp['lthi'] = ctx.zeros((cap, 32, 128))
+            tcp['ltlo'] = ctx.zeros((cap, 32, 128))
+            tcp['mul'] = ctx.zeros((cap, 32))
+            mh = torch.zeros((2, 128), dtype=torch.uint8).pin_memory()
+            for u, t in enumerate((tcp['lthi'], tcp['ltlo'])):
+                _lib.check(ctx.lib.cpsd_tmap_encode_f32(ctypes.c_void_p(mh[u].data_ptr()), ptr(t),
+                                                        cap * 32, 128, 128, 32), 'tmap_encode')
+            tcp['ltmaps'] = mh.to(ctx.device)
+            tcp['cap'] = cap
+        return tcp
+
     def _view_slots(self, B, n_pad, Cm):
         """Per-view statistics of the MCCA fit (mean, spectrum and eigenvectors of the centred
         condition-average scatter) live in slots: [0, res) are the per-fold target problems of
@@ -669,6 +713,21 @@ class CVEngine:
         o_npool = pk.add_ints(n_pool)
         o_nall = pk.add_ints([a + b for a, b in zip(n_pool, n_te)])
         o_nte = pk.add_ints(n_te)
+        tc_proj = (not align_only) and self._tc_proj_ready(Q)
+        if tc_proj:
+            # destination trial row of every (fold, view, trial) in the fold's pooled matrix
+            Nmax = max(vw.N for vw in self.views)
+            dst = -np.ones((B, P, Nmax), dtype=np.int32)
+            for f, tb in enumerate(tabs):
+                row = 0
+                if self.tar_in_train:
+                    dst[f, 0, tb['tr']] = np.arange(n_tr[f])
+                    row = n_tr[f]
+                for v in range(1, P):
+                    dst[f, v, :self.views[v].N] = row + np.arange(self.views[v].N)
+                    row += self.views[v].N
+                dst[f, 0, tb['te']] = row + np.arange(n_te[f])
+            o_dst = pk.add_ints(dst)
         pk.reserve_ints()
 
         # ---- descriptors, stage A
@@ -818,8 +877,17 @@ class CVEngine:
                         r_eff=r_eff.view(B, P).cpu().numpy(), shared=[s_.copy() for s_ in shared])
         # project every trial of every view into the pooled (trial x time*Q) matrix
         self.mark('project_pool')
-        ctx.call('cpsd_proj_nn', ctypes_off(pk.daddr(d_pp), 0), B * P + B,
-                 max(max(self.views[v].N for v in range(P)), n_te_max), T, Q)
+        if tc_proj:
+            tcp = self._tc_proj_ws(B * P)
+            ctx.call('cpsd_proj_tc_prep', ptr(L), Q, Cm * Q, ptr(mu), ctypes_int_ptr(pk.iaddr(o_slot)),
+                     Cm, cdim_dev, Q, ptr(tcp['lthi']), ptr(tcp['ltlo']), ptr(tcp['mul']), B * P)
+            ctx.call('cpsd_proj_tc', ptr(tcp['xmaps']), ptr(tcp['ltmaps']), P, B, T, Q,
+                     ctypes.c_void_p(tcp['ntr'].ctypes.data), ctypes.c_void_p(tcp['nch'].ctypes.data),
+                     Nmax, ctypes_int_ptr(pk.iaddr(o_dst)), ptr(tcp['mul']), ptr(Zall), n_pad * F,
+                     tcp['sms'])
+        else:
+            ctx.call('cpsd_proj_nn', ctypes_off(pk.daddr(d_pp), 0), B * P + B,
+                     max(max(self.views[v].N for v in range(P)), n_te_max), T, Q)
         evals, k2_, St_, Ste, V, sweeps, kcap = self._pooled_stage_run(
             pk, d_p1, d_p2, B, Zall, pmu, Kall, n_pad, F, n_pool, n_te, o_npool, o_nall, o_ypool,
             n_te_max, want_details)

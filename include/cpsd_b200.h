@@ -78,6 +78,22 @@ int cpsd_gram_tn_f64_split(const cpsd_gram_tn_desc* descs, int nprob, int p_max,
  * directly in the pooled trials x (time*latent) matrix (cross_pt_decoders.py:260-270). */
 int cpsd_proj_nn(const cpsd_proj_desc* descs, int nprob, int nseg_max, int seg_len, int q_max,
                  cudaStream_t stream);
+/* the same projection for all folds of a batch on the tensor cores (tcgen05 kind::tf32,
+ * 3xTF32, TMA): a persistent CTA keeps one 128-row tile of a patient in shared memory and
+ * streams the loadings of every fold past it.  Needs the tf32 hi/lo split of every patient
+ * (cpsd_split_tf32, once), tensor maps (cpsd_tmap_encode_f32: host-encoded, copied to the
+ * device by the caller; X maps with box_rows = 128, L^T maps with box_rows = 32) and the
+ * per-problem L^T hi/lo + mu L prepared by cpsd_proj_tc_prep.  Channels <= 128 (multiple of
+ * 4), latent size <= 32. */
+int cpsd_split_tf32(const float* src, float* hi, float* lo, long long n, cudaStream_t stream);
+int cpsd_tmap_encode_f32(void* map_out_host, const float* base, long long rows, int cols,
+                         long long ld, int box_rows);
+int cpsd_proj_tc_prep(const float* L, int ldl, long long strideL, const float* mu_base,
+                      const int* slot, int ld_mu, const int* cdim, int Q, float* LtHi, float* LtLo,
+                      float* muL, int nprob, cudaStream_t stream);
+int cpsd_proj_tc(const void* xmaps_dev, const void* ltmaps_dev, int P, int B, int T, int Q,
+                 const int* n_trials_host, const int* n_chan_host, int n_max, const int* dst_row,
+                 const float* muL, float* Y, long long strideY, int num_sms, cudaStream_t stream);
 /* A B^T over the long feature axis: Gram of the pooled matrix for the decoder-stage PCA
  * (decomposition/DimRedReshape.py:47-49 -> sklearn PCA full SVD). */
 int cpsd_gram_nt(const cpsd_gram_nt_desc* descs, int nprob, int m_max, int n_max,

@@ -10,7 +10,7 @@ import bench  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument('--steps', type=int, default=1)
-ap.add_argument('--folds', type=int, default=20)
+ap.add_argument('--folds', type=int, default=107)
 ap.add_argument('--no-tc', action='store_true')
 ap.add_argument('--stages', action='store_true')
 a = ap.parse_args()
@@ -31,8 +31,7 @@ for s in range(a.steps):
     res = eng.run(mk(2000 + 100 * s), return_details=True)
     if a.stages:
         print('stages_ms', {k: round(v, 3) for k, v in eng.collect_marks().items()})
-    print('k2', res['k2'][:4], 'bj_sweeps', res['details'][0]['bj_sweeps'],
+    sw = res['details'][0]['bj_sweeps']
+    print('k2', res['k2'][:4], 'topk', eng.stats.get('topk'), 'bj_sweeps', None if sw is None else sw[:4],
           'svm_newton_max', int(res['details'][0]['svm_info'][..., 0].max()),
           'launches', eng.stats['launches_last_batch'])
-    B = len(res['k2'])
-    print('conv_history fold0', eng._ws['pool_fw'][2 * B:2 * B + 16].cpu().numpy())
