@@ -333,6 +333,7 @@ def main():
             'across folds: %d of %d (fold, view) eigen-problems solved'
             % (eng.stats.get('view_solves', 0), eng.stats.get('view_problems', 0)),
             'accuracy_mean': float(np.mean(acc_all)),
+            'host_pack_ms_total': round(eng.stats.get('host_pack_ms', 0.0), 1),
             'cpu_baseline': {'value': cpu_val, 'unit': 'folds/s', 'cores': blas_threads(),
                              'kind': 'port', 'accuracy': cpu_acc,
                              'sample': '%d folds of the same 8-patient 20-fold workload, '

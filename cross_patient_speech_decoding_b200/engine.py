@@ -11,6 +11,7 @@ once by the kernels of libcpsd_b200.so.  Patient data stays resident in HBM; per
 the host only uploads fold index tables + descriptor records and downloads predictions.
 """
 import ctypes
+import time
 
 import numpy as np
 import torch
@@ -105,6 +106,9 @@ class CVEngine:
         self.classes_dev = self.ctx.upload(self.classes, np.int32)
         self.packA = HostPack(self.ctx)
         self.packB = HostPack(self.ctx)
+        self.packM = [HostPack(self.ctx), HostPack(self.ctx)]   # MCCA batches alternate
+        self._pack_i = 0
+        self._before_sync = None
         self._ws = {}
         self._sched = {}
         self.stats = {}
@@ -230,6 +234,7 @@ class CVEngine:
                      self.eig_tol)
             ctx.call('cpsd_select_k_total', ptr(evals), evals.shape[-1], ptr(None), m, ptr(tot),
                      thr, mode, 1, min(kcap, m), ptr(k2), 1, nprob)
+            self._sync_hook()
             k2h = k2.cpu().numpy()
             rh = resid.cpu().numpy()
             ev0 = evals[:, 0].cpu().numpy()
@@ -448,6 +453,13 @@ class CVEngine:
                       ptr(k_out, offset), stride, nprob)
 
     # ------------------------------------------------------------------ public API
+    def _sync_hook(self):
+        """Called right before the first blocking read-back of a batch: the host uses the wait
+        to pack the next batch's index tables and descriptors."""
+        h, self._before_sync = self._before_sync, None
+        if h is not None:
+            h()
+
     def run(self, folds, return_details=False):
         """folds: list of (train_idx, test_idx) into the target's trials.  Returns a dict with
         ``y_pred`` (list of arrays, one per fold) and per-fold diagnostics."""
@@ -455,21 +467,57 @@ class CVEngine:
         details = []
         nb = max(1, -(-len(folds) // self.max_batch))
         size = -(-len(folds) // nb)          # balanced batches (a short tail batch costs as much
-        for s in range(0, len(folds), size):  # as a full one: the solvers are latency-bound)
-            batch = folds[s:s + size]
-            if self.method == 'mcca':
-                res = self._batch_mcca(batch, return_details)
-            else:
-                res = self._batch_cca(batch, return_details)
+        batches = [folds[s:s + size] for s in range(0, len(folds), size)]   # as a full one)
+
+        def take(res):
             out['y_pred'] += res['y_pred']
             out['k2'] += res['k2']
             out['h2d_bytes'] += res['h2d_bytes']
             out['d2h_bytes'] += res['d2h_bytes']
             if return_details:
                 details.append(res['details'])
+
+        if self.method == 'mcca':
+            # software pipeline: batch i+1 is packed on the host (and its tables uploaded) while
+            # the GPU works on batch i
+            nxt = [self._mcca_start(batches[0], return_details)] if batches else []
+            for i in range(len(batches)):
+                cur = nxt.pop()
+
+                def prefetch(i=i):
+                    if i + 1 < len(batches):
+                        nxt.append(self._mcca_start(batches[i + 1], return_details))
+                self._before_sync = prefetch
+                res = self._mcca_finish(cur)
+                self._sync_hook()            # in case the batch never blocked
+                take(res)
+        else:
+            for batch in batches:
+                take(self._batch_cca(batch, return_details))
         if return_details:
             out['details'] = details
         return out
+
+    def _mcca_start(self, batch, want_details, align_only=False):
+        t0 = time.perf_counter()
+        pk = self.packM[self._pack_i]
+        self._pack_i ^= 1
+        g = self._batch_mcca_gen(batch, want_details, align_only, pk)
+        next(g)                              # host packing + table upload
+        self.stats['host_pack_ms'] = self.stats.get('host_pack_ms', 0.0) + \
+            1e3 * (time.perf_counter() - t0)
+        return g
+
+    @staticmethod
+    def _mcca_finish(g):
+        try:
+            next(g)
+        except StopIteration as e:
+            return e.value
+        raise RuntimeError('batch generator did not finish')
+
+    def _batch_mcca(self, batch, want_details, align_only=False):
+        return self._mcca_finish(self._mcca_start(batch, want_details, align_only))
 
     def align_mcca(self, train_idx=None):
         """MCCA fit only (AlignMCCA.fit): loadings, view means and generalised eigenvalues for
@@ -498,9 +546,13 @@ class CVEngine:
         tv, T = self.views[0], self.T
         cmT = self.ws('cmT', (B, Kmax * T, tv.C))
         recs = np.zeros(B, dtype=_lib.CLASS_MEAN_DESC)
-        for f, tb in enumerate(tabs):
-            recs[f] = (addr(tv.X), pk.iaddr(tb['o_ptr']), pk.iaddr(tb['o_mem']),
-                       addr(cmT, f * Kmax * T * tv.C), len(tb['present']), T * tv.C, 0, 0)
+        ib = pk.iaddr(0)
+        recs['X'] = addr(tv.X)
+        recs['member_ptr'] = ib + 4 * np.array([tb['o_ptr'] for tb in tabs], dtype=np.int64)
+        recs['members'] = ib + 4 * np.array([tb['o_mem'] for tb in tabs], dtype=np.int64)
+        recs['out'] = addr(cmT) + 4 * Kmax * T * tv.C * np.arange(B, dtype=np.int64)
+        recs['nslot'] = [len(tb['present']) for tb in tabs]
+        recs['TC'] = T * tv.C
         return cmT, recs
 
     # ------------------------------------------------------------------ pooled stage
@@ -512,15 +564,18 @@ class CVEngine:
         n_all = [a + b for a, b in zip(n_pool, n_te)]
         mu = self.ws('pool_mu', (B, F))
         r1 = np.zeros(B, dtype=_lib.COLSUM_DESC)
-        zero_seg = pk.iaddr(self._o_zero)
         r2 = np.zeros(B, dtype=_lib.GRAM_NT_DESC)
         Kall = self.ws('pool_K', (B, n_pad, n_pad))
-        for f in range(B):
-            r1[f] = (addr(Zall, f * n_pad * F), zero_seg, addr(mu, f * F), 1, n_pool[f], F, F,
-                     1.0 / n_pool[f], 0)
-            r2[f] = (addr(Zall, f * n_pad * F), addr(Zall, f * n_pad * F),
-                     addr(Kall, f * n_pad * n_pad), n_all[f], n_all[f], F, F, F, n_pad, 1, 1.0)
-        self._r2_host = r2
+        fi = np.arange(B, dtype=np.int64)
+        zb = addr(Zall) + 4 * n_pad * F * fi
+        npool = np.asarray(n_pool, dtype=np.int64)
+        r1['A'], r1['segA'], r1['out'] = zb, pk.iaddr(pk.o_zero), addr(mu) + 4 * F * fi
+        r1['nseg'], r1['seg_len'], r1['p'], r1['lda'] = 1, npool, F, F
+        r1['alpha'] = 1.0 / npool
+        r2['A'], r2['B'], r2['out'] = zb, zb, addr(Kall) + 4 * n_pad * n_pad * fi
+        r2['m'] = r2['n'] = np.asarray(n_all, dtype=np.int64)
+        r2['k'], r2['lda'], r2['ldb'], r2['ldo'], r2['sym'], r2['alpha'] = F, F, F, n_pad, 1, 1.0
+        pk.r2_host = r2
         return r1, r2, mu, Kall
 
     def gram_tc(self, recs_host, nprob, nmax, elems_per_prob):
@@ -549,7 +604,7 @@ class CVEngine:
         nmax = max(a + b for a, b in zip(n_pool, n_te))
         self.mark('pool_gram')
         if self.use_tc:
-            self.gram_tc(self._r2_host, B, nmax, n_pad * F)
+            self.gram_tc(pk.r2_host, B, nmax, n_pad * F)
         else:
             ctx.call('cpsd_gram_nt', pk.daddr(d2), B, nmax, nmax)
         self.mark('pool_eig')
@@ -566,6 +621,11 @@ class CVEngine:
         ldv, sV = n_pad, n_pad * n_pad
         sweeps = None
         V = None
+        # every workspace used after the first read-back is fetched before it: the host packs
+        # the next batch during that wait and may grow same-named workspaces
+        St = self.ws('pool_St', (B, kcap, n_pad))
+        Ste = self.ws('pool_Ste', (B, kcap, n_te_max))
+        yhat = self.ws('yhat', (B, n_te_max), I32)
         m = self.topk_block
         use_topk = (self.pool_solver != 'full' and n_pad > 128 and mode in (0, 3)
                     and (mode == 0 or int(thr) <= m - 8)
@@ -590,14 +650,13 @@ class CVEngine:
             if n_pad > 128:
                 # eigenvectors of the k2 retained components only (rotation-log replay); one
                 # small read-back sizes the replay grid to the columns actually kept
+                self._sync_hook()
                 self._k2_max = max(int(k2.cpu().numpy().max()), 1)
                 k_launch = min(kcap, _ceil(self._k2_max, 64))
                 self.eig_vecs('pool', n_pad, B, perm, k2, 0, k_launch, V)
             else:
                 self._k2_max = kcap
         self.mark('pool_scores')
-        St = self.ws('pool_St', (B, kcap, n_pad))
-        Ste = self.ws('pool_Ste', (B, kcap, n_te_max))
         ctx.call('cpsd_scores_train', ptr(V), ldv, sV, ptr(evals), perm_p, n_pad,
                  ptr(k2), npool_dev, 0, max(n_pool), ptr(St), n_pad, kcap * n_pad, kcap, B)
         ctx.call('cpsd_scores_test', ptr(Kte), n_pad, n_te_max * n_pad, ptr(V), ldv,
@@ -612,17 +671,23 @@ class CVEngine:
         W = self.ws('svm_W', (B, ncls, kcap + 1), torch.float64)
         info = self.ws('svm_info', (B, ncls, 4), I32)
         recs = np.zeros(B * ncls, dtype=_lib.SVM_DESC)
-        for f in range(B):
-            for c in range(ncls):
-                recs[f * ncls + c] = (addr(St, f * kcap * n_pad), pk2.iaddr(o_ypool + f * ypool_ld),
-                                      addr(k2, f), addr(W, (f * ncls + c) * (kcap + 1)),
-                                      addr(info, (f * ncls + c) * 4), n_pool[f], 0, n_pad,
-                                      int(self.classes[c]), self.Csvm, self.tol_dcd,
-                                      self.tol_newton, self.max_newton, self.dcd_epochs)
+        fi = np.repeat(np.arange(B, dtype=np.int64), ncls)
+        ti = np.arange(B * ncls, dtype=np.int64)
+        recs['St'] = addr(St) + 4 * kcap * n_pad * fi
+        recs['y'] = pk2.iaddr(o_ypool) + 4 * ypool_ld * fi
+        recs['k_dev'] = addr(k2) + 4 * fi
+        recs['w'] = addr(W) + 8 * (kcap + 1) * ti
+        recs['info'] = addr(info) + 16 * ti
+        recs['n'] = np.repeat(np.asarray(n_pool, dtype=np.int64), ncls)
+        recs['lds'] = n_pad
+        recs['cls'] = np.tile(self.classes.astype(np.int64), B)
+        recs['C'], recs['tol_dcd'], recs['tol_newton'] = self.Csvm, self.tol_dcd, self.tol_newton
+        recs['max_newton'], recs['dcd_epochs'] = self.max_newton, self.dcd_epochs
         return W, info, recs
 
     # ------------------------------------------------------------------ MCCA batch
-    def _batch_mcca(self, batch, want_details, align_only=False):
+    def _batch_mcca_gen(self, batch, want_details, align_only, pk):
+        """Generator: runs the host packing + table upload, yields once, then launches."""
         ctx, T, P, Cm = self.ctx, self.T, self.P, self.Cmax
         B = len(batch)
         Q = int(self.n_comp)
@@ -630,9 +695,8 @@ class CVEngine:
         R = Q if use_rank else Cm      # pca_var == 1: no rank reduction (mvlearn _mcca_gevp)
         tv = self.views[0]
         launches0 = ctx.launches()
-        pk = self.packA
         pk.reset()
-        self._o_zero = pk.add_ints([0])
+        pk.o_zero = pk.add_ints([0])
         tabs = self._target_tables(pk, batch)
         cross_shared = set.intersection(*self.cross_classes) if P > 1 else None
         shared = []
@@ -646,16 +710,23 @@ class CVEngine:
         KTmax = max(Ks) * T
         if min(Ks) == 0:
             raise ValueError('no alignment class is shared by all patients in some fold')
-        # segment tables: rows of the shared classes inside each view's class-mean array
+        # segment tables: rows of the shared classes inside each view's class-mean array (the
+        # cross patients' tables depend on the shared class set only)
         o_seg = np.zeros((B, P), dtype=np.int64)
+        seg_cache = {}
+        keys = [sh.tobytes() for sh in shared]
         for f, tb in enumerate(tabs):
             slot_t = -np.ones(len(self.vocab), dtype=np.int64)
             slot_t[tb['present']] = np.arange(len(tb['present']))
             o_seg[f, 0] = pk.add_ints(slot_t[shared[f]] * T)
-            for v in range(1, P):
-                o_seg[f, v] = pk.add_ints(self.cm_row[v][shared[f]] * T)
+            row = seg_cache.get(keys[f])
+            if row is None:
+                row = [pk.add_ints(self.cm_row[v][shared[f]] * T) for v in range(1, P)]
+                seg_cache[keys[f]] = row
+            o_seg[f, 1:] = row
         o_segdst = pk.add_ints(np.arange(max(Ks), dtype=np.int32) * T)
-        o_cdim = pk.add_ints(np.tile([vw.C for vw in self.views], B))
+        cdims = np.array([vw.C for vw in self.views], dtype=np.int64)
+        o_cdim = pk.add_ints(np.tile(cdims, B))
         ranks = np.zeros((B, P), dtype=np.int32)
         ranks[:, 1:] = self.cross_rank[None, :]
         o_rank = pk.add_ints(ranks)
@@ -669,18 +740,21 @@ class CVEngine:
         slot[:, 0] = np.arange(B)
         solve = [(f, 0, f) for f in range(B)]
         pending = {}
+        row_cache = {}
         for f in range(B):
-            kb = shared[f].tobytes()
-            for v in range(1, P):
-                key = (v, kb)
-                sl = vs['keys'].get(key)
-                if sl is None:
-                    sl = pending.get(key)
+            row = row_cache.get(keys[f])
+            if row is None:
+                row = []
+                for v in range(1, P):
+                    key = (v, keys[f])
+                    sl = vs['keys'].get(key)
                     if sl is None:
                         sl = vs['next'] + len(pending)
                         pending[key] = sl
                         solve.append((f, v, sl))
-                slot[f, v] = sl
+                    row.append(sl)
+                row_cache[keys[f]] = row
+            slot[f, 1:] = row
         o_slot = pk.add_ints(slot)
         o_cds = pk.add_ints([self.views[v].C for _, v, _ in solve])
         # pooled layout
@@ -691,71 +765,92 @@ class CVEngine:
         n_te_max = max(n_te)
         n_pad = _ceil(max(a + b for a, b in zip(n_pool, n_te)), 128)
         F = T * Q
+        tc_proj = (not align_only) and self._tc_proj_ready(Q)
+        ycross = getattr(self, '_ycross', None)
+        if ycross is None:
+            ycross = self._ycross = (np.concatenate([self.views[v].y for v in range(1, P)])
+                                     if P > 1 else np.zeros(0, dtype=np.int64)).astype(np.int32)
         ypool = np.zeros((B, n_pad), dtype=np.int32)
-        o_pooldst = np.zeros((B, P), dtype=np.int64)
-        o_allseg = [pk.add_ints(np.arange(self.views[v].N, dtype=np.int32) * T)
-                    for v in range(P)]
-        o_tedst = []
+        row0 = np.array([nt if self.tar_in_train else 0 for nt in n_tr], dtype=np.int64)
         for f, tb in enumerate(tabs):
-            row = 0
-            ys = []
             if self.tar_in_train:
-                o_pooldst[f, 0] = pk.add_ints((row + np.arange(n_tr[f])) * T)
-                ys.append(tv.y[tb['tr']])
-                row += n_tr[f]
+                ypool[f, :n_tr[f]] = tv.y[tb['tr']]
+            ypool[f, row0[f]:row0[f] + len(ycross)] = ycross
+        if not tc_proj:
+            o_pooldst = np.zeros((B, P), dtype=np.int64)
+            o_allseg = [pk.add_ints(np.arange(self.views[v].N, dtype=np.int32) * T)
+                        for v in range(P)]
+            o_tedst = []
+            for f, tb in enumerate(tabs):
+                row = 0
+                if self.tar_in_train:
+                    o_pooldst[f, 0] = pk.add_ints((row + np.arange(n_tr[f])) * T)
+                    row += n_tr[f]
+                for v in range(1, P):
+                    o_pooldst[f, v] = pk.add_ints((row + np.arange(self.views[v].N)) * T)
+                    row += self.views[v].N
+                o_tedst.append(pk.add_ints((row + np.arange(n_te[f])) * T))
+        else:
+            # destination trial row of every (fold, view, trial) in the fold's pooled matrix
+            Nmax = max(vw.N for vw in self.views)
+            cbase = -np.ones((P, Nmax), dtype=np.int64)
+            off = 0
             for v in range(1, P):
-                o_pooldst[f, v] = pk.add_ints((row + np.arange(self.views[v].N)) * T)
-                ys.append(self.views[v].y)
-                row += self.views[v].N
-            ypool[f, :row] = np.concatenate(ys)
-            o_tedst.append(pk.add_ints((row + np.arange(n_te[f])) * T))
+                cbase[v, :self.views[v].N] = off + np.arange(self.views[v].N)
+                off += self.views[v].N
+            dst = np.where(cbase[None] >= 0, cbase[None] + row0[:, None, None], -1).astype(np.int32)
+            for f, tb in enumerate(tabs):
+                if self.tar_in_train:
+                    dst[f, 0, tb['tr']] = np.arange(n_tr[f])
+                dst[f, 0, tb['te']] = n_pool[f] + np.arange(n_te[f])
+            o_dst = pk.add_ints(dst)
         o_ypool = pk.add_ints(ypool)
         o_npool = pk.add_ints(n_pool)
         o_nall = pk.add_ints([a + b for a, b in zip(n_pool, n_te)])
         o_nte = pk.add_ints(n_te)
-        tc_proj = (not align_only) and self._tc_proj_ready(Q)
-        if tc_proj:
-            # destination trial row of every (fold, view, trial) in the fold's pooled matrix
-            Nmax = max(vw.N for vw in self.views)
-            dst = -np.ones((B, P, Nmax), dtype=np.int32)
-            for f, tb in enumerate(tabs):
-                row = 0
-                if self.tar_in_train:
-                    dst[f, 0, tb['tr']] = np.arange(n_tr[f])
-                    row = n_tr[f]
-                for v in range(1, P):
-                    dst[f, v, :self.views[v].N] = row + np.arange(self.views[v].N)
-                    row += self.views[v].N
-                dst[f, 0, tb['te']] = row + np.arange(n_te[f])
-            o_dst = pk.add_ints(dst)
         pk.reserve_ints()
+        ib = pk.iaddr(0)
 
-        # ---- descriptors, stage A
+        # ---- descriptors, stage A (filled column-wise: one numpy op per field)
         cmT, r_cm = self._class_means_target(pk, tabs, B, Kmax)
-        cm_base = lambda f, v: (addr(cmT, f * Kmax * T * tv.C) if v == 0 else addr(self.cm[v]))
-        n_padC = 128 if Cm <= 128 else _ceil(Cm, 128)
         Gt, gram_c = self.scatter('m_Gt', B, n_padC)
         nS = len(solve)
         mu = vs['mu']
-        mu_of = lambda f, v: addr(mu, int(slot[f, v]) * Cm)
         cov, _ = self.scatter('m_cov', nS, n_padC)
-        if Cm < n_padC:
-            cov.zero_()
-            Gt.zero_()
+        esz = cov.element_size()
+        fi = np.arange(B, dtype=np.int64)
+        # base address of the class-mean array of every (fold, view)
+        cmb = np.empty((B, P), dtype=np.int64)
+        cmb[:, 0] = addr(cmT) + 4 * Kmax * T * tv.C * fi
+        for v in range(1, P):
+            cmb[:, v] = addr(self.cm[v])
+        segb = ib + 4 * o_seg                       # (B, P) segment-table addresses
+        mub = addr(mu) + 4 * Cm * slot               # (B, P) mean vectors (slots)
+        Ksa = np.asarray(Ks, dtype=np.int64)
+        o_tr = ib + 4 * np.array([tb['o_tr'] for tb in tabs], dtype=np.int64)
         r_gt = np.zeros(B, dtype=_lib.GRAM_TN_DESC)
+        r_gt['A'] = r_gt['B'] = addr(tv.X)
+        r_gt['segA'] = r_gt['segB'] = o_tr
+        r_gt['out'] = addr(Gt) + Gt.element_size() * n_padC * n_padC * fi
+        r_gt['nseg'], r_gt['seg_len'] = n_tr, T
+        r_gt['p'] = r_gt['q'] = r_gt['lda'] = r_gt['ldb'] = tv.C
+        r_gt['ldo'], r_gt['sym'], r_gt['alpha'] = n_padC, 1, 1.0
+        sf = np.array([t[0] for t in solve], dtype=np.int64)
+        sv = np.array([t[1] for t in solve], dtype=np.int64)
+        ssl = np.array([t[2] for t in solve], dtype=np.int64)
+        sC = cdims[sv]
         r_mu = np.zeros(nS, dtype=_lib.COLSUM_DESC)
+        r_mu['A'], r_mu['segA'], r_mu['out'] = cmb[sf, sv], segb[sf, sv], addr(mu) + 4 * Cm * ssl
+        r_mu['nseg'], r_mu['seg_len'], r_mu['p'], r_mu['lda'] = Ksa[sf], T, sC, sC
+        r_mu['alpha'] = 1.0 / (Ksa[sf] * T)
         r_cov = np.zeros(nS, dtype=_lib.GRAM_TN_DESC)
-        for f, tb in enumerate(tabs):
-            r_gt[f] = (addr(tv.X), addr(tv.X), pk.iaddr(tb['o_tr']), pk.iaddr(tb['o_tr']), 0, 0,
-                       addr(Gt, f * n_padC * n_padC), n_tr[f], T, tv.C, tv.C, tv.C, tv.C, n_padC,
-                       1, 1.0, 0)
-        for j, (f, v, sl) in enumerate(solve):
-            C = self.views[v].C
-            sg = pk.iaddr(o_seg[f, v])
-            r_mu[j] = (cm_base(f, v), sg, addr(mu, sl * Cm), Ks[f], T, C, C, 1.0 / (Ks[f] * T), 0)
-            r_cov[j] = (cm_base(f, v), cm_base(f, v), sg, sg, addr(mu, sl * Cm),
-                        addr(mu, sl * Cm), addr(cov, j * n_padC * n_padC), Ks[f], T, C, C, C, C,
-                        n_padC, 1, 1.0, 0)
+        r_cov['A'] = r_cov['B'] = cmb[sf, sv]
+        r_cov['segA'] = r_cov['segB'] = segb[sf, sv]
+        r_cov['muA'] = r_cov['muB'] = addr(mu) + 4 * Cm * ssl
+        r_cov['out'] = addr(cov) + esz * n_padC * n_padC * np.arange(nS, dtype=np.int64)
+        r_cov['nseg'], r_cov['seg_len'] = Ksa[sf], T
+        r_cov['p'] = r_cov['q'] = r_cov['lda'] = r_cov['ldb'] = sC
+        r_cov['ldo'], r_cov['sym'], r_cov['alpha'] = n_padC, 1, 1.0
         d_cm, d_gt = pk.add_descs(r_cm), pk.add_descs(r_gt)
         d_mu, d_cov = pk.add_descs(r_mu), pk.add_descs(r_cov)
         # reduced views
@@ -763,20 +858,22 @@ class CVEngine:
         d2 = self.ws('m_d2', (B * P, R))
         r_eff = self.ws('m_reff', (B * P,), I32)
         Zcat = self.ws('m_Zcat', (B, KTmax, P * R))
-        r_pz = np.zeros(B * P, dtype=_lib.PROJ_DESC)
-        r_g = np.zeros(B, dtype=_lib.GRAM_TN_DESC)
         Gz = self.ws('m_Gz', (B, P * R, P * R))
-        for f in range(B):
-            for v in range(P):
-                C = self.views[v].C
-                i = f * P + v
-                r_pz[i] = (cm_base(f, v), pk.iaddr(o_seg[f, v]), pk.iaddr(o_segdst),
-                           mu_of(f, v), addr(Vr, i * Cm * R),
-                           addr(Zcat, f * KTmax * P * R + v * R), Ks[f], T, C, R, C, R, P * R, 0)
-            r_g[f] = (addr(Zcat, f * KTmax * P * R), addr(Zcat, f * KTmax * P * R),
-                      pk.iaddr(self._o_zero), pk.iaddr(self._o_zero), 0, 0,
-                      addr(Gz, f * P * R * P * R), 1, Ks[f] * T, P * R, P * R, P * R, P * R, P * R,
-                      1, 1.0, 0)
+        pi = np.arange(B * P, dtype=np.int64)
+        pf, pv = pi // P, pi % P
+        r_pz = np.zeros(B * P, dtype=_lib.PROJ_DESC)
+        r_pz['X'], r_pz['seg_src'], r_pz['seg_dst'] = cmb.ravel(), segb.ravel(), ib + 4 * o_segdst
+        r_pz['mu'], r_pz['W'] = mub.ravel(), addr(Vr) + 4 * Cm * R * pi
+        r_pz['Y'] = addr(Zcat) + 4 * (KTmax * P * R * pf + R * pv)
+        r_pz['nseg'], r_pz['seg_len'], r_pz['C'], r_pz['q'] = Ksa[pf], T, cdims[pv], R
+        r_pz['ldx'], r_pz['ldw'], r_pz['ldy'] = cdims[pv], R, P * R
+        r_g = np.zeros(B, dtype=_lib.GRAM_TN_DESC)
+        r_g['A'] = r_g['B'] = addr(Zcat) + 4 * KTmax * P * R * fi
+        r_g['segA'] = r_g['segB'] = pk.iaddr(pk.o_zero)
+        r_g['out'] = addr(Gz) + 4 * P * R * P * R * fi
+        r_g['nseg'], r_g['seg_len'] = 1, Ksa * T
+        r_g['p'] = r_g['q'] = r_g['lda'] = r_g['ldb'] = r_g['ldo'] = P * R
+        r_g['sym'], r_g['alpha'] = 1, 1.0
         d_pz, d_g = pk.add_descs(r_pz), pk.add_descs(r_g)
         # pooled projection
         # size of the reduced GEVP: the target's rank is only known on the device (<= R), the
@@ -789,23 +886,24 @@ class CVEngine:
         L = self.ws('m_L', (B * P, Cm, Q))
         if not align_only:
             Zall = self.ws('pool_Z', (B, n_pad, F))
-            r_pp = np.zeros(B * P + B, dtype=_lib.PROJ_DESC)
-            for f, tb in enumerate(tabs):
-                for v in range(P):
-                    vw = self.views[v]
-                    i = f * P + v
-                    if v == 0:
-                        nseg = n_tr[f] if self.tar_in_train else 0
-                        src = pk.iaddr(tb['o_tr'])
-                    else:
-                        nseg, src = vw.N, pk.iaddr(o_allseg[v])
-                    r_pp[i] = (addr(vw.X), src, pk.iaddr(o_pooldst[f, v]), mu_of(f, v),
-                               addr(L, i * Cm * Q), addr(Zall, f * n_pad * F), nseg, T, vw.C, Q, vw.C,
-                               Q, Q, 0)
-                r_pp[B * P + f] = (addr(tv.X), pk.iaddr(tb['o_te']), pk.iaddr(o_tedst[f]),
-                                   mu_of(f, 0), addr(L, f * P * Cm * Q),
-                                   addr(Zall, f * n_pad * F), n_te[f], T, tv.C, Q, tv.C, Q, Q, 0)
-            d_pp = pk.add_descs(r_pp)
+            if not tc_proj:
+                r_pp = np.zeros(B * P + B, dtype=_lib.PROJ_DESC)
+                for f, tb in enumerate(tabs):
+                    for v in range(P):
+                        vw = self.views[v]
+                        i = f * P + v
+                        if v == 0:
+                            nseg = n_tr[f] if self.tar_in_train else 0
+                            src = pk.iaddr(tb['o_tr'])
+                        else:
+                            nseg, src = vw.N, pk.iaddr(o_allseg[v])
+                        r_pp[i] = (addr(vw.X), src, pk.iaddr(o_pooldst[f, v]), int(mub[f, v]),
+                                   addr(L, i * Cm * Q), addr(Zall, f * n_pad * F), nseg, T, vw.C, Q,
+                                   vw.C, Q, Q, 0)
+                    r_pp[B * P + f] = (addr(tv.X), pk.iaddr(tb['o_te']), pk.iaddr(o_tedst[f]),
+                                       int(mub[f, 0]), addr(L, f * P * Cm * Q),
+                                       addr(Zall, f * n_pad * F), n_te[f], T, tv.C, Q, tv.C, Q, Q, 0)
+                d_pp = pk.add_descs(r_pp)
             r1, r2, pmu, Kall = self._pooled_stage(pk, B, Zall, n_pad, F, n_pool, n_te, o_npool,
                                                    o_nall, o_ypool, n_pad, n_te_max, want_details)
             d_p1, d_p2 = pk.add_descs(r1), pk.add_descs(r2)
@@ -817,6 +915,7 @@ class CVEngine:
                                              n_pad, o_nte, n_te_max)
             d_svm = pk.add_descs(r_svm)
         pk.upload()
+        yield 'packed'
 
         # ---- launches
         cdim_dev = ctypes_int_ptr(pk.iaddr(o_cdim))
@@ -828,6 +927,9 @@ class CVEngine:
         ctx.call('cpsd_copy_rows', ctypes_int_ptr(pk.iaddr(o_rank)), B * P, 0, ptr(rank_dev),
                  B * P, 0, ptr(None), 0, 1, B * P, 1, 1)
         self.mark('align_scatter_eig')
+        if Cm < n_padC:
+            cov.zero_()
+            Gt.zero_()
         if use_rank:
             self.gram_scatter(gram_c, pk.daddr(d_gt), B, tv.C, tv.C, Gt, 3)
             ev_t, _ = self.eig_any(Gt, n_padC, ptr(None), tv.C, B, 'mrk', vecs=False)

@@ -28,7 +28,7 @@ def batch_cca(eng, batch, want_details):
     # ------------------------------------------------------------- stage A: target PCA
     pk = eng.packA
     pk.reset()
-    eng._o_zero = pk.add_ints([0])
+    eng._o_zero = pk.o_zero = pk.add_ints([0])
     tabs = eng._target_tables(pk, batch)
     n_tr = [len(tb['tr']) for tb in tabs]
     n_te = [len(tb['te']) for tb in tabs]
@@ -74,7 +74,7 @@ def batch_cca(eng, batch, want_details):
     # ------------------------------------------------------------- stage B
     pk = eng.packB
     pk.reset()
-    eng._o_zero = pk.add_ints([0])
+    eng._o_zero = pk.o_zero = pk.add_ints([0])
     o_tr = [pk.add_ints(tb['tr'] * T) for tb in tabs]
     o_te = [pk.add_ints(tb['te'] * T) for tb in tabs]
     o_allseg = [pk.add_ints(np.arange(eng.views[v].N, dtype=np.int32) * T) for v in range(P)]
