@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libcpsd_b200.so')
+LIB_PATH = os.environ.get('CPSD_LIB') or os.path.join(_HERE, 'libcpsd_b200.so')
 
 c_int = ctypes.c_int
 c_ll = ctypes.c_longlong

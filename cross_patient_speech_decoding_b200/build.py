@@ -8,6 +8,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libcpsd_b200.so')
 SOURCES = ['api.cu', 'jacobi.cu', 'gemm.cu', 'stream.cu', 'svm.cu', 'cca.cu', 'tc_gram.cu', 'subspace.cu', 'tc_proj.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+EXTRA = os.environ.get('CPSD_NVCC_FLAGS', '').split()
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
          '-Xcompiler', '-fPIC', '--use_fast_math=false' if False else '-Xptxas', '-v']
 
@@ -29,7 +30,7 @@ def build(force=False, verbose=False):
     procs = []
     for s in srcs:
         o = os.path.join(CSRC, s.replace('.cu', '.o'))
-        cmd = [NVCC] + FLAGS + ['-I', CSRC, '-c', os.path.join(CSRC, s), '-o', o]
+        cmd = [NVCC] + FLAGS + EXTRA + ['-I', CSRC, '-c', os.path.join(CSRC, s), '-o', o]
         procs.append((s, o, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                                              text=True)))
     log = []

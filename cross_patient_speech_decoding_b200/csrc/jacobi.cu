@@ -19,7 +19,12 @@
 
 #define TS 128          // tile size
 #define BS 64           // block size of the block-Jacobi
-#define NT 256          // threads per CTA
+#define NT 256          // threads per CTA (block-Jacobi kernels)
+// threads per CTA of the n <= 128 tile solver: one problem per SM and the Jacobi step is bound
+// by shared-memory latency, so it wants every warp slot of the SM
+#ifndef ET_NT
+#define ET_NT 1024
+#endif
 
 namespace {
 
@@ -100,7 +105,7 @@ template <typename T, int NP>
 __device__ __forceinline__ void tile_apply(T* As, float* Vs, StepBuf* sb, int npairs_rt, int vrows) {
   const int npairs = NP > 0 ? NP : npairs_rt;
   const int nblk = npairs * npairs;
-  for (int b = threadIdx.x; b < nblk; b += NT) {
+  for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
     const int k = NP > 0 ? b / NP : b / npairs;
     const int l = b - k * npairs;
     const int ik = sb->pi[k], jk = sb->pj[k];
@@ -130,7 +135,7 @@ __device__ __forceinline__ void tile_apply(T* As, float* Vs, StepBuf* sb, int np
     As[jk * TS + jl] = sk * tpq + ck * tqq;
   }
   const int nv = vrows * npairs;
-  for (int b = threadIdx.x; b < nv; b += NT) {
+  for (int b = threadIdx.x; b < nv; b += blockDim.x) {
     const int r = NP > 0 ? b / NP : b / npairs;
     const int l = b - r * npairs;
     const float cl = sb->cf[l], sl = sb->sf[l];
@@ -207,7 +212,7 @@ __device__ float tile_diag_absmax(const T* As, int m, int* redmax) {
   if (threadIdx.x == 0) *redmax = 0;
   __syncthreads();
   float v = 0.f;
-  for (int i = threadIdx.x; i < m; i += NT) v = fmaxf(v, fabsf((float)As[i * TS + i]));
+  for (int i = threadIdx.x; i < m; i += blockDim.x) v = fmaxf(v, fabsf((float)As[i * TS + i]));
   v = warp_max(v);
   if ((threadIdx.x & 31) == 0) atomicMax(redmax, __float_as_int(v));
   __syncthreads();
@@ -223,7 +228,7 @@ __device__ float tile_diag_absmax(const T* As, int m, int* redmax) {
 // gap-independent ~1e-6 perturbation of the basis.
 // ---------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(ET_NT)
 k_eig_tile(const T* __restrict__ A, int lda, long long strideA, const int* __restrict__ n_dev,
            int n_fixed, float* __restrict__ evals, int ld_e, float* __restrict__ evecs, int ldv,
            long long strideV, int max_sweeps, float tol, int* __restrict__ sweeps_out) {
@@ -241,7 +246,7 @@ k_eig_tile(const T* __restrict__ A, int lda, long long strideA, const int* __res
   const int m = (n + 1) & ~1;
   const T* Ag = A + (long long)prob * strideA;
 
-  for (int e = threadIdx.x; e < TS * TS; e += NT) {
+  for (int e = threadIdx.x; e < TS * TS; e += ET_NT) {
     const int r = e >> 7, c = e & (TS - 1);
     T v = (T)0;
     if (r < n && c < n) v = Ag[(long long)r * lda + c];
@@ -250,7 +255,7 @@ k_eig_tile(const T* __restrict__ A, int lda, long long strideA, const int* __res
   }
   __syncthreads();
   // symmetrise (inputs are Grams computed tile-wise; removes last-ulp asymmetry)
-  for (int e = threadIdx.x; e < TS * TS; e += NT) {
+  for (int e = threadIdx.x; e < TS * TS; e += ET_NT) {
     const int r = e >> 7, c = e & (TS - 1);
     if (r < c) {
       const T v = (T)0.5 * (As[r * TS + c] + As[c * TS + r]);
@@ -272,7 +277,7 @@ k_eig_tile(const T* __restrict__ A, int lda, long long strideA, const int* __res
   if (sweeps_out && threadIdx.x == 0) sweeps_out[prob] = sw;
 
   // sort descending by counting
-  for (int i = threadIdx.x; i < n; i += NT) {
+  for (int i = threadIdx.x; i < n; i += ET_NT) {
     const T li = As[i * TS + i];
     int r = 0;
     for (int j = 0; j < n; ++j) {
@@ -283,13 +288,13 @@ k_eig_tile(const T* __restrict__ A, int lda, long long strideA, const int* __res
   }
   __syncthreads();
   float* ev = evals + (long long)prob * ld_e;
-  for (int i = threadIdx.x; i < ld_e; i += NT) {
+  for (int i = threadIdx.x; i < ld_e; i += ET_NT) {
     if (i >= n) ev[i] = 0.f;
   }
-  for (int i = threadIdx.x; i < n; i += NT) ev[rank[i]] = (float)As[i * TS + i];
+  for (int i = threadIdx.x; i < n; i += ET_NT) ev[rank[i]] = (float)As[i * TS + i];
   if (evecs) {
     float* Vg = evecs + (long long)prob * strideV;
-    for (int e = threadIdx.x; e < n * n; e += NT) {
+    for (int e = threadIdx.x; e < n * n; e += ET_NT) {
       const int r = e / n, c = e - r * n;
       Vg[(long long)r * ldv + rank[c]] = Vs[r * TS + c];
     }
@@ -896,7 +901,7 @@ extern "C" int cpsd_eig_sym_small(const float* A, int lda, long long strideA, co
   const size_t smem = tile_smem_bytes();
   CPSD_CUDA(cudaFuncSetAttribute(k_eig_tile<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
-  k_eig_tile<float><<<nprob, NT, smem, stream>>>(A, lda, strideA, n_dev, n_fixed, evals, ld_e, evecs,
+  k_eig_tile<float><<<nprob, ET_NT, smem, stream>>>(A, lda, strideA, n_dev, n_fixed, evals, ld_e, evecs,
                                                  ldv, strideV, max_sweeps, tol, sweeps_out);
   CPSD_LAUNCH_CHECK();
   return CPSD_OK;
@@ -913,7 +918,7 @@ extern "C" int cpsd_eig_sym_small_f64(const double* A, int lda, long long stride
   const size_t smem = tile_smem_bytes(sizeof(double));
   CPSD_CUDA(cudaFuncSetAttribute(k_eig_tile<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
-  k_eig_tile<double><<<nprob, NT, smem, stream>>>(A, lda, strideA, n_dev, n_fixed, evals, ld_e,
+  k_eig_tile<double><<<nprob, ET_NT, smem, stream>>>(A, lda, strideA, n_dev, n_fixed, evals, ld_e,
                                                   evecs, ldv, strideV, max_sweeps, tol, sweeps_out);
   CPSD_LAUNCH_CHECK();
   return CPSD_OK;

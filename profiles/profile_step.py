@@ -35,3 +35,6 @@ for s in range(a.steps):
     print('k2', res['k2'][:4], 'topk', eng.stats.get('topk'), 'bj_sweeps', None if sw is None else sw[:4],
           'svm_newton_max', int(res['details'][0]['svm_info'][..., 0].max()),
           'launches', eng.stats['launches_last_batch'])
+    si = res['details'][0]['svm_info']
+    print('svm newton its mean %.2f max %d; cg iterations per task mean %.1f max %d; dcd epochs %d' % (
+        si[..., 0].mean(), si[..., 0].max(), si[..., 1].mean(), si[..., 1].max(), si[..., 2].max()))
