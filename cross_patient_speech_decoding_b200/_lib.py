@@ -90,6 +90,7 @@ _SIGS = {
     'cpsd_class_mean': [_P, c_int, c_int, c_int, _P],
     'cpsd_center_rows': [_P, c_int, c_ll, _P, c_int, _P, c_int, c_int, c_int, c_int, _P],
     'cpsd_copy_rows': [_P, c_int, c_ll, _P, c_int, c_ll, _P, c_int, c_int, c_int, c_int, c_int, _P],
+    'cpsd_sum_mats_f64': [_P, _P, c_ll, _P, _P, ctypes.c_double, _P, c_ll, c_int, c_int, _P],
     'cpsd_cast_f64_f32': [_P, _P, c_ll, _P],
     'cpsd_permute_cols': [_P, c_int, c_ll, _P, c_int, _P, c_int, c_ll, c_int, c_int, c_int, _P],
     'cpsd_mcca_mask': [_P, c_int, c_ll, _P, c_int, _P, _P, c_int, c_int, _P, _P, _P, c_int, _P],
@@ -114,6 +115,7 @@ _SIGS = {
     'cpsd_proj_tc': [_P, _P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P, _P, c_ll, c_int,
                      _P],
     'cpsd_gram_nt_tc': [_P, c_int, c_int, c_int, _P, c_ll, _P, _P, _P],
+    'cpsd_gram_nt_tc_centered': [_P, c_int, c_int, c_int, _P, c_ll, _P, _P, _P, c_int, _P],
     'cpsd_gram_nt_tc_ws_bytes': [c_int],
 }
 _RESTYPES = {'cpsd_last_error': ctypes.c_char_p, 'cpsd_launch_count': c_ll,

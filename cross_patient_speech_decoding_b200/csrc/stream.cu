@@ -241,7 +241,38 @@ k_scores_test(const float* __restrict__ Kte, int ldk, long long strideK,
   }
 }
 
+// out[p] = base + sign * sum_{j in list[list_ptr[p] .. list_ptr[p+1])} mats[list[j]]   (fp64)
+__global__ void __launch_bounds__(256)
+k_sum_mats_f64(const double* __restrict__ base, const double* __restrict__ mats, long long mat_stride,
+               const int* __restrict__ list_ptr, const int* __restrict__ list, double sign,
+               double* __restrict__ out, long long out_stride, int elems) {
+  const int p = blockIdx.y;
+  const int j0 = list_ptr[p], j1 = list_ptr[p + 1];
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < elems; e += gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    for (int j = j0; j < j1; ++j) acc += mats[(long long)list[j] * mat_stride + e];
+    out[(long long)p * out_stride + e] = (base ? base[e] : 0.0) + sign * acc;
+  }
+}
+
 }  // namespace
+
+// Scatter matrix of a trial subset from per-trial scatter matrices: the uncentred Gram of the
+// target's train trials (AlignMCCA.n_components_var, AlignMCCA.py:156-174) is the all-trials
+// Gram minus the Grams of the few held-out trials.
+extern "C" int cpsd_sum_mats_f64(const double* base, const double* mats, long long mat_stride,
+                                 const int* list_ptr, const int* list, double sign, double* out,
+                                 long long out_stride, int elems, int nprob, cudaStream_t stream) {
+  CPSD_CHECK_ARG(nprob >= 0 && elems > 0, "sum_mats_f64: bad dims");
+  if (nprob == 0) return CPSD_OK;
+  CPSD_CHECK_ARG(nprob <= 65535, "sum_mats_f64: nprob > 65535");
+  int bx = (elems + 255) / 256;
+  if (bx > 16) bx = 16;
+  k_sum_mats_f64<<<dim3(bx, nprob), 256, 0, stream>>>(base, mats, mat_stride, list_ptr, list, sign, out,
+                                                      out_stride, elems);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
 
 extern "C" int cpsd_class_mean(const cpsd_class_mean_desc* descs_dev, int nprob, int nslot_max,
                                int TC, cudaStream_t stream) {

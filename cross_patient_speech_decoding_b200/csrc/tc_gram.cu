@@ -34,7 +34,11 @@ constexpr uint32_t TMEM_COLS = 256;          // two 128-column accumulator stage
 
 struct TcProb {
   float* out;
-  int n, ldo;
+  const float* src;     // row-major source (n rows, lda floats apart)
+  const float* mu;      // optional [k] vector subtracted from every row before the split
+  float* hi;
+  float* lo;
+  int n, ldo, lda, pad_;
 };
 
 // The tensor core's fp32 accumulator truncates on every accumulate (measured: relative error
@@ -205,19 +209,30 @@ k_gram_tc(const CUtensorMap* __restrict__ maps, const TcProb* __restrict__ probs
   }
 }
 
-// hi = x with the 13 low mantissa bits cleared (exactly representable in tf32), lo = x - hi
+// all problems in one launch: grid (column chunks, row phases, problem); optional centring
+// (x - mu[col]) fused into the split, so the centred matrix is never written in fp32
 __global__ void __launch_bounds__(256)
-k_split_tf32(const float* __restrict__ src, int ld_src, float* __restrict__ hi,
-             float* __restrict__ lo, int ld_dst, int nrows, int ncols) {
-  for (int r = blockIdx.y; r < nrows; r += gridDim.y) {
-    const float* s = src + (long long)r * ld_src;
-    float* h = hi + (long long)r * ld_dst;
-    float* l = lo + (long long)r * ld_dst;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncols; c += gridDim.x * blockDim.x) {
-      const float x = s[c];
-      const float xh = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+k_split_tf32_batched(const TcProb* __restrict__ probs, int ncols) {
+  const TcProb pr = probs[blockIdx.z];
+  const int nvec = ncols >> 2;
+  for (int r = blockIdx.y; r < pr.n; r += gridDim.y) {
+    const float4* s = reinterpret_cast<const float4*>(pr.src + (long long)r * pr.lda);
+    float4* h = reinterpret_cast<float4*>(pr.hi + (long long)r * pr.lda);
+    float4* l = reinterpret_cast<float4*>(pr.lo + (long long)r * pr.lda);
+    const float4* m = reinterpret_cast<const float4*>(pr.mu);
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nvec; c += gridDim.x * blockDim.x) {
+      float4 x = s[c];
+      if (m) {
+        const float4 mm = m[c];
+        x.x -= mm.x; x.y -= mm.y; x.z -= mm.z; x.w -= mm.w;
+      }
+      float4 xh, xl;
+      split_tf32(x.x, xh.x, xl.x);
+      split_tf32(x.y, xh.y, xl.y);
+      split_tf32(x.z, xh.z, xl.z);
+      split_tf32(x.w, xh.w, xl.w);
       h[c] = xh;
-      l[c] = x - xh;
+      l[c] = xl;
     }
   }
 }
@@ -246,9 +261,9 @@ EncodeFn get_encode() {
 //   split_ws   : device workspace, >= 2 * sum_p m_p * lda_p floats (hi / lo copies)
 //   map_ws     : device workspace, >= nprob * (2 * 128 + 16) bytes, 64-byte aligned
 //   stage_host : pinned host staging of the same size as map_ws
-extern "C" int cpsd_gram_nt_tc(const cpsd_gram_nt_desc* descs_host, int nprob, int m_max, int n_max,
-                               float* split_ws, long long split_ws_elems, void* map_ws,
-                               void* stage_host, cudaStream_t stream) {
+static int gram_nt_tc_impl(const cpsd_gram_nt_desc* descs_host, int nprob, int m_max, int n_max,
+                           float* split_ws, long long split_ws_elems, void* map_ws,
+                           void* stage_host, const float* mu, int ldmu, cudaStream_t stream) {
   CPSD_CHECK_ARG(nprob >= 0 && m_max > 0 && n_max == m_max, "gram_nt_tc: bad dims");
   if (nprob == 0) return CPSD_OK;
   CPSD_CHECK_ARG(nprob <= 65535, "gram_nt_tc: nprob > 65535");
@@ -262,22 +277,19 @@ extern "C" int cpsd_gram_nt_tc(const cpsd_gram_nt_desc* descs_host, int nprob, i
                                               (size_t)nprob * 2 * sizeof(CUtensorMap));
   long long used = 0;
   int k_total = descs_host[0].k;
+  int rows_max = 0;
   for (int p = 0; p < nprob; ++p) {
     const cpsd_gram_nt_desc& d = descs_host[p];
     CPSD_CHECK_ARG(d.A == d.B && d.sym == 1 && d.m == d.n, "gram_nt_tc: symmetric problems only");
     CPSD_CHECK_ARG((d.k & 3) == 0 && (d.lda & 3) == 0 && d.k == k_total,
                    "gram_nt_tc: k and lda must be multiples of 4 and k uniform over the batch");
+    CPSD_CHECK_ARG((((uintptr_t)d.A) & 15) == 0, "gram_nt_tc: operand must be 16-byte aligned");
     CPSD_CHECK_ARG(d.alpha == 1.0f, "gram_nt_tc: alpha must be 1");
     const long long elems = (long long)d.m * d.lda;
     CPSD_CHECK_ARG(used + 2 * elems <= split_ws_elems, "gram_nt_tc: split workspace too small");
     float* hi = split_ws + used;
     float* lo = hi + elems;
     used += 2 * elems;
-    int bx = (d.k + 255) / 256;
-    if (bx > 8) bx = 8;
-    k_split_tf32<<<dim3(bx, d.m < 512 ? d.m : 512), 256, 0, stream>>>(d.A, d.lda, hi, lo, d.lda, d.m,
-                                                                      d.k);
-    CPSD_LAUNCH_CHECK();
     const cuuint64_t gdim[2] = {(cuuint64_t)d.k, (cuuint64_t)d.m};
     const cuuint64_t gstr[1] = {(cuuint64_t)d.lda * 4};
     const cuuint32_t box[2] = {BK, BM};
@@ -293,20 +305,54 @@ extern "C" int cpsd_gram_nt_tc(const cpsd_gram_nt_desc* descs_host, int nprob, i
       }
     }
     probs_h[p].out = d.out;
+    probs_h[p].src = d.A;
+    probs_h[p].mu = mu ? mu + (long long)p * ldmu : nullptr;
+    probs_h[p].hi = hi;
+    probs_h[p].lo = lo;
     probs_h[p].n = d.m;
     probs_h[p].ldo = d.ldo;
+    probs_h[p].lda = d.lda;
+    probs_h[p].pad_ = 0;
+    if (d.m > rows_max) rows_max = d.m;
   }
   const size_t bytes = (size_t)nprob * (2 * sizeof(CUtensorMap) + sizeof(TcProb));
   CPSD_CUDA(cudaMemcpyAsync(map_ws, stage_host, bytes, cudaMemcpyHostToDevice, stream));
   const CUtensorMap* maps_d = reinterpret_cast<const CUtensorMap*>(map_ws);
   const TcProb* probs_d = reinterpret_cast<const TcProb*>(reinterpret_cast<uint8_t*>(map_ws) +
                                                           (size_t)nprob * 2 * sizeof(CUtensorMap));
+  {
+    int bx = (k_total / 4 + 255) / 256;
+    if (bx > 4) bx = 4;
+    int by = rows_max < 64 ? rows_max : 64;
+    k_split_tf32_batched<<<dim3(bx, by, nprob), 256, 0, stream>>>(probs_d, k_total);
+    CPSD_LAUNCH_CHECK();
+  }
   const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024 + 128;
   CPSD_CUDA(cudaFuncSetAttribute(k_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int tiles = (m_max + BM - 1) / BM;
   k_gram_tc<<<dim3(tiles, tiles, nprob), TC_THREADS, smem, stream>>>(maps_d, probs_d, k_total);
   CPSD_LAUNCH_CHECK();
   return CPSD_OK;
+}
+
+extern "C" int cpsd_gram_nt_tc(const cpsd_gram_nt_desc* descs_host, int nprob, int m_max, int n_max,
+                               float* split_ws, long long split_ws_elems, void* map_ws,
+                               void* stage_host, cudaStream_t stream) {
+  return gram_nt_tc_impl(descs_host, nprob, m_max, n_max, split_ws, split_ws_elems, map_ws, stage_host,
+                         nullptr, 0, stream);
+}
+
+// Gram of the CENTRED rows: mu (nprob x ldmu) row p is subtracted from every row of problem p
+// inside the hi/lo split (sklearn PCA centring, _pca.py, fused: the centred matrix is never
+// written in fp32).
+extern "C" int cpsd_gram_nt_tc_centered(const cpsd_gram_nt_desc* descs_host, int nprob, int m_max,
+                                        int n_max, float* split_ws, long long split_ws_elems,
+                                        void* map_ws, void* stage_host, const float* mu, int ldmu,
+                                        cudaStream_t stream) {
+  CPSD_CHECK_ARG(mu != nullptr && (ldmu & 3) == 0 && (((uintptr_t)mu) & 15) == 0,
+                 "gram_nt_tc_centered: mu must be 16-byte aligned with ldmu % 4 == 0");
+  return gram_nt_tc_impl(descs_host, nprob, m_max, n_max, split_ws, split_ws_elems, map_ws, stage_host,
+                         mu, ldmu, stream);
 }
 
 // bytes of map_ws / stage_host needed for nprob problems

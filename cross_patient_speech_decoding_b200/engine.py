@@ -62,7 +62,7 @@ class CVEngine:
 
     def __init__(self, target, cross, method='mcca', n_comp=None, regs=0.5, pca_var=0.8,
                  decoder_var=0.8, C=1.0, tar_in_train=True, device=None, max_batch=32,
-                 dcd_epochs=2, max_newton=60, tol_newton=1e-9, tol_dcd=1e-4,
+                 dcd_epochs=0, max_newton=60, tol_newton=1e-9, tol_dcd=1e-4,
                  eig_sweeps=12, eig_tol=3e-7, use_tensor_cores=False, pool_solver='auto',
                  topk_block=128, topk_iters=8, topk_tol=2e-5, topk_rounds=3):
         self.ctx = Context.get(device)
@@ -374,6 +374,7 @@ class CVEngine:
                               for v in range(1, self.P)]
         if self.method == 'mcca':
             self.cross_rank = self._ranks_full(range(1, self.P))
+            self._target_trial_grams()
         elif self.P > 1:
             self._cross_pca()
         torch.cuda.synchronize(self.ctx.device)
@@ -406,6 +407,35 @@ class CVEngine:
         ctx.call('cpsd_select_k', ptr(evals), n_pad, cd, 0, float(self.pca_var), 1, 0, 1 << 30,
                  ptr(k), 1, len(vs))
         return k.cpu().numpy().astype(np.int32)
+
+    def _target_trial_grams(self):
+        """Uncentred per-trial scatter matrices X_t^T X_t of the target (fp64) and their sum:
+        the train-set Gram of every fold follows by subtracting the held-out trials."""
+        self.tg = None
+        tv = self.views[0]
+        if not (0 < self.pca_var < 1) or tv.C > 128:
+            return
+        ctx, T = self.ctx, self.T
+        pk = HostPack(ctx)
+        seg = pk.add_ints(np.arange(tv.N, dtype=np.int32) * T)
+        pk.reserve_ints()
+        G = ctx.zeros((tv.N, 128, 128), torch.float64)
+        recs = np.zeros(tv.N, dtype=_lib.GRAM_TN_DESC)
+        recs['A'] = recs['B'] = addr(tv.X)
+        recs['segA'] = recs['segB'] = pk.iaddr(seg) + 4 * np.arange(tv.N, dtype=np.int64)
+        recs['out'] = addr(G) + 8 * 128 * 128 * np.arange(tv.N, dtype=np.int64)
+        recs['nseg'], recs['seg_len'] = 1, T
+        recs['p'] = recs['q'] = recs['lda'] = recs['ldb'] = tv.C
+        recs['ldo'], recs['sym'], recs['alpha'] = 128, 1, 1.0
+        d = pk.add_descs(recs)
+        pk.upload()
+        ctx.call('cpsd_gram_tn_f64', pk.daddr(d), tv.N, tv.C, tv.C)
+        allp = ctx.upload(np.array([0, tv.N], dtype=np.int32))
+        alll = ctx.upload(np.arange(tv.N, dtype=np.int32))
+        Gall = ctx.zeros((128, 128), torch.float64)
+        ctx.call('cpsd_sum_mats_f64', ptr(None), ptr(G), 128 * 128, ptr(allp), ptr(alll), 1.0,
+                 ptr(Gall), 128 * 128, 128 * 128, 1)
+        self.tg = dict(trial=G, all=Gall)
 
     def _cross_pca(self):
         """sklearn PCA(n_comp) of every cross patient's (trials*time, channels) matrix
@@ -578,8 +608,9 @@ class CVEngine:
         pk.r2_host = r2
         return r1, r2, mu, Kall
 
-    def gram_tc(self, recs_host, nprob, nmax, elems_per_prob):
-        """Tensor-core pooled Gram (tcgen05): needs the descriptor records on the host."""
+    def gram_tc(self, recs_host, nprob, nmax, elems_per_prob, mu=None, ldmu=0):
+        """Tensor-core pooled Gram (tcgen05): needs the descriptor records on the host.  With
+        ``mu`` the rows are centred inside the hi/lo split."""
         ctx = self.ctx
         nbytes = int(ctx.lib.cpsd_gram_nt_tc_ws_bytes(nprob))
         split = self.ws('tc_split', (2 * nprob * elems_per_prob,))
@@ -588,6 +619,11 @@ class CVEngine:
             self._tc_stage = torch.empty((nbytes + 64,), dtype=torch.uint8).pin_memory()
         recs = np.ascontiguousarray(recs_host)
         a = (maps.data_ptr() + 63) & ~63
+        if mu is not None:
+            ctx.call('cpsd_gram_nt_tc_centered', ctypes.c_void_p(recs.ctypes.data), nprob, nmax, nmax,
+                     ptr(split), split.numel(), ctypes.c_void_p(a),
+                     ctypes.c_void_p(self._tc_stage.data_ptr()), ptr(mu), ldmu)
+            return
         ctx.call('cpsd_gram_nt_tc', ctypes.c_void_p(recs.ctypes.data), nprob, nmax, nmax, ptr(split),
                  split.numel(), ctypes.c_void_p(a), ctypes.c_void_p(self._tc_stage.data_ptr()))
 
@@ -599,12 +635,13 @@ class CVEngine:
         ncls = len(self.classes)
         self.mark('pool_center')
         ctx.call('cpsd_colsum', pk.daddr(d1), B, F)
-        ctx.call('cpsd_center_rows', ptr(Zall), F, n_pad * F, ptr(mu), F, nall_dev, 0,
-                 max(a + b for a, b in zip(n_pool, n_te)), F, B)
         nmax = max(a + b for a, b in zip(n_pool, n_te))
+        tc_gram = self.use_tc and F % 4 == 0
+        if not tc_gram:
+            ctx.call('cpsd_center_rows', ptr(Zall), F, n_pad * F, ptr(mu), F, nall_dev, 0, nmax, F, B)
         self.mark('pool_gram')
-        if self.use_tc:
-            self.gram_tc(pk.r2_host, B, nmax, n_pad * F)
+        if tc_gram:       # centring fused into the tf32 split of the tensor-core Gram
+            self.gram_tc(pk.r2_host, B, nmax, n_pad * F, mu=mu, ldmu=F)
         else:
             ctx.call('cpsd_gram_nt', pk.daddr(d2), B, nmax, nmax)
         self.mark('pool_eig')
@@ -757,6 +794,12 @@ class CVEngine:
             slot[f, 1:] = row
         o_slot = pk.add_ints(slot)
         o_cds = pk.add_ints([self.views[v].C for _, v, _ in solve])
+        downdate = use_rank and getattr(self, 'tg', None) is not None and n_padC == 128
+        if downdate:
+            use_te = sum(len(tb['te']) for tb in tabs) <= sum(len(tb['tr']) for tb in tabs)
+            lists = [tb['te'] if use_te else tb['tr'] for tb in tabs]
+            o_lptr = pk.add_ints(np.concatenate([[0], np.cumsum([len(x) for x in lists])]))
+            o_list = pk.add_ints(np.concatenate(lists) if lists else [])
         # pooled layout
         n_tr = [len(tb['tr']) for tb in tabs]
         n_te = [len(tb['te']) for tb in tabs]
@@ -931,7 +974,13 @@ class CVEngine:
             cov.zero_()
             Gt.zero_()
         if use_rank:
-            self.gram_scatter(gram_c, pk.daddr(d_gt), B, tv.C, tv.C, Gt, 3)
+            if downdate:     # train-set Gram = all-trials Gram - held-out trials (or sum of train)
+                ctx.call('cpsd_sum_mats_f64', ptr(self.tg['all']) if use_te else ptr(None),
+                         ptr(self.tg['trial']), 128 * 128, ctypes_int_ptr(pk.iaddr(o_lptr)),
+                         ctypes_int_ptr(pk.iaddr(o_list)), -1.0 if use_te else 1.0, ptr(Gt),
+                         128 * 128, 128 * 128, B)
+            else:
+                self.gram_scatter(gram_c, pk.daddr(d_gt), B, tv.C, tv.C, Gt, 3)
             ev_t, _ = self.eig_any(Gt, n_padC, ptr(None), tv.C, B, 'mrk', vecs=False)
             ctx.call('cpsd_select_k', ptr(ev_t), n_padC, ptr(None), tv.C, float(self.pca_var), 1,
                      0, 1 << 30, ptr(rank_dev), P, B)

@@ -52,6 +52,12 @@ int cpsd_center_rows(float* Z, int ld, long long strideZ, const float* mu, int l
 int cpsd_copy_rows(const float* src, int lds, long long strideS, float* dst, int ldd,
                    long long strideD, const int* r0_dev, int r0_fixed, int nrows, int ncols,
                    int src_rows, int nprob, cudaStream_t stream);
+/* out[p] = base + sign * sum of the listed per-trial scatter matrices (fp64): the train-set
+ * Gram of AlignMCCA.n_components_var (AlignMCCA.py:156-174) as all-trials Gram minus the
+ * held-out trials' Grams */
+int cpsd_sum_mats_f64(const double* base, const double* mats, long long mat_stride,
+                      const int* list_ptr, const int* list, double sign, double* out,
+                      long long out_stride, int elems, int nprob, cudaStream_t stream);
 /* ingest: the reference keeps trials as float64 (pickled numpy); cast once on the device */
 int cpsd_cast_f64_f32(const double* src, float* dst, long long n, cudaStream_t stream);
 int cpsd_permute_cols(const float* src, int lds, long long strideS, const int* perm, int ld_perm,
@@ -106,6 +112,10 @@ int cpsd_gram_nt(const cpsd_gram_nt_desc* descs, int nprob, int m_max, int n_max
 int cpsd_gram_nt_tc(const cpsd_gram_nt_desc* descs_host, int nprob, int m_max, int n_max,
                     float* split_ws, long long split_ws_elems, void* map_ws, void* stage_host,
                     cudaStream_t stream);
+/* Gram of the centred rows (row p of mu subtracted inside the hi/lo split) */
+int cpsd_gram_nt_tc_centered(const cpsd_gram_nt_desc* descs_host, int nprob, int m_max, int n_max,
+                             float* split_ws, long long split_ws_elems, void* map_ws,
+                             void* stage_host, const float* mu, int ldmu, cudaStream_t stream);
 int cpsd_gram_nt_tc_ws_bytes(int nprob);
 
 /* ---- small solvers ---------------------------------------------------------------

@@ -13,11 +13,12 @@ ap.add_argument('--steps', type=int, default=1)
 ap.add_argument('--folds', type=int, default=107)
 ap.add_argument('--no-tc', action='store_true')
 ap.add_argument('--stages', action='store_true')
+ap.add_argument('--dcd', type=int, default=2)
 a = ap.parse_args()
 from cross_patient_speech_decoding_b200.engine import CVEngine  # noqa: E402
 pts = bench.make_data()
 eng = CVEngine(pts[0], pts[1:], method='mcca', n_comp=30, regs=0.5, pca_var=0.8,
-               use_tensor_cores=not a.no_tc, max_batch=a.folds)
+               use_tensor_cores=not a.no_tc, max_batch=a.folds, dcd_epochs=a.dcd)
 def mk(seed):
     out = []
     while len(out) < a.folds:
@@ -28,10 +29,12 @@ def mk(seed):
 eng.run(mk(1000))
 for s in range(a.steps):
     eng.profile = a.stages
-    res = eng.run(mk(2000 + 100 * s), return_details=True)
+    fl = mk(2000 + 100 * s)
+    res = eng.run(fl, return_details=True)
     if a.stages:
         print('stages_ms', {k: round(v, 3) for k, v in eng.collect_marks().items()})
     sw = res['details'][0]['bj_sweeps']
+    print('acc', sum(int((p == pts[0][1][te]).sum()) for p, (_, te) in zip(res['y_pred'], fl)) / sum(len(te) for _, te in fl))
     print('k2', res['k2'][:4], 'topk', eng.stats.get('topk'), 'bj_sweeps', None if sw is None else sw[:4],
           'svm_newton_max', int(res['details'][0]['svm_info'][..., 0].max()),
           'launches', eng.stats['launches_last_batch'])
