@@ -211,10 +211,11 @@ def main():
             torch.cuda.synchronize(dev)
 
     # size every workspace for a full engine batch before anything is timed
+    # (two full batches: both execution lanes allocate their workspaces)
     big = []
-    while len(big) < args.batch:
+    while len(big) < 2 * args.batch:
         big += step_folds(y0, 20_000 + len(big))
-    eng.run(big[:args.batch])
+    eng.run(big[:2 * args.batch])
     if args.warmup:
         run_steps([10_000 + rank * 1000 + w for w in range(args.warmup)])
     sync_all()

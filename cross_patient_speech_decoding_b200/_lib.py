@@ -98,6 +98,8 @@ _SIGS = {
                            _P],
     'cpsd_mcca_build': [_P, c_int, c_ll, _P, c_int, c_int, c_float, _P, c_int, c_ll, _P, _P, _P,
                         c_int, _P, c_int, _P],
+    'cpsd_mcca_build_split': [_P, c_int, c_ll, _P, c_int, c_ll, _P, _P, c_int, c_int, c_float, _P,
+                              c_int, c_ll, _P, _P, _P, c_int, _P, c_int, _P],
     'cpsd_mcca_loadings': [_P, _P, c_int, c_ll, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, _P,
                            c_int, c_int, _P],
     'cpsd_scores_train': [_P, c_int, c_ll, _P, _P, c_int, _P, _P, c_int, c_int, _P, c_int, c_ll,

@@ -125,17 +125,35 @@ k_mcca_mask(const float* __restrict__ evecs, int ldv, long long strideV,
 // Per fold: compact the P*R reduced coordinates to the n = sum_v r_v valid ones and write
 // the whitened SUMCOR matrix  M = Dh^-1/2 LHS Dh^-1/2  (unit diagonal, zero inside a view,
 // scaled cross-scatter between views).  reg < 0 means regs=None.
+// Split source (Gx != NULL): G holds only the target's R rows [G_tt | G_tx] per fold and the
+// cross x cross block comes from slot xslot[f] of Gx (fold-invariant, cached).
+struct GzView {
+  const float* Gf;
+  const float* Gx;
+  int ldg, ldx, R;
+  __device__ __forceinline__ float at(int ia, int ib) const {
+    if (!Gx) return Gf[(long long)ia * ldg + ib];
+    if (ia < R) return Gf[(long long)ia * ldg + ib];
+    if (ib < R) return Gf[(long long)ib * ldg + ia];
+    return Gx[(long long)(ia - R) * ldx + (ib - R)];
+  }
+};
+
 __global__ void __launch_bounds__(256)
-k_mcca_build(const float* __restrict__ G, int ldg, long long strideG, const int* __restrict__ r_eff,
-             int P, int R, float reg, float* __restrict__ M, int ldm, long long strideM,
-             int* __restrict__ n_out, int* __restrict__ cidx, float* __restrict__ dh, int n_comp,
-             int* __restrict__ status) {
+k_mcca_build(const float* __restrict__ G, int ldg, long long strideG, const float* __restrict__ Gxx,
+             int ldx, long long strideX, const int* __restrict__ xslot,
+             const int* __restrict__ r_eff, int P, int R, float reg, float* __restrict__ M, int ldm,
+             long long strideM, int* __restrict__ n_out, int* __restrict__ cidx,
+             float* __restrict__ dh, int n_comp, int* __restrict__ status) {
   extern __shared__ int sh[];
   int* cmap = sh;                   // compact -> padded index
   float* dhs = reinterpret_cast<float*>(sh + P * R);
   __shared__ int n_s;
   const int f = blockIdx.x;
-  const float* Gf = G + (long long)f * strideG;
+  GzView Gv;
+  Gv.Gf = G + (long long)f * strideG;
+  Gv.Gx = Gxx ? Gxx + (long long)xslot[f] * strideX : nullptr;
+  Gv.ldg = ldg; Gv.ldx = ldx; Gv.R = R;
   if (threadIdx.x == 0) {
     int n = 0;
     for (int v = 0; v < P; ++v) {
@@ -152,7 +170,7 @@ k_mcca_build(const float* __restrict__ G, int ldg, long long strideG, const int*
     float d = 0.f;
     if (a < n) {
       const int ia = cmap[a];
-      const float gaa = Gf[(long long)ia * ldg + ia];
+      const float gaa = Gv.at(ia, ia);
       d = (reg >= 0.f) ? (1.f - reg) * gaa + reg : gaa;
       dhs[a] = d;
     }
@@ -167,7 +185,7 @@ k_mcca_build(const float* __restrict__ G, int ldg, long long strideG, const int*
     float v;
     if (a == b) v = 1.f;
     else if (ia / R == ib / R) v = 0.f;
-    else v = Gf[(long long)ia * ldg + ib] * rsqrtf(dhs[a] * dhs[b]);
+    else v = Gv.at(ia, ib) * rsqrtf(dhs[a] * dhs[b]);
     Mf[(long long)a * ldm + b] = v;
   }
 }
@@ -373,8 +391,26 @@ extern "C" int cpsd_mcca_build(const float* G, int ldg, long long strideG, const
   CPSD_CHECK_ARG(ldm >= P * R || ldm >= 1, "mcca_build: bad ldm");
   if (nfold == 0) return CPSD_OK;
   const size_t smem = (size_t)P * R * (sizeof(int) + sizeof(float));
-  k_mcca_build<<<nfold, 256, smem, stream>>>(G, ldg, strideG, r_eff, P, R, reg, M, ldm, strideM,
-                                             n_out, cidx, dh, n_comp, status);
+  k_mcca_build<<<nfold, 256, smem, stream>>>(G, ldg, strideG, nullptr, 0, 0, nullptr, r_eff, P, R, reg,
+                                             M, ldm, strideM, n_out, cidx, dh, n_comp, status);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
+
+// Same with the cross-scatter in two parts: Gt (per fold, R x P*R: the target's rows
+// [G_tt | G_tx]) and Gxx (slot xslot[f], (P-1)R x (P-1)R: the cross patients' block, which does
+// not depend on the fold and is computed once per shared class set).
+extern "C" int cpsd_mcca_build_split(const float* Gt, int ldg, long long strideG, const float* Gxx,
+                                     int ldx, long long strideX, const int* xslot, const int* r_eff,
+                                     int P, int R, float reg, float* M, int ldm, long long strideM,
+                                     int* n_out, int* cidx, float* dh, int n_comp, int* status,
+                                     int nfold, cudaStream_t stream) {
+  CPSD_CHECK_ARG(nfold >= 0 && P > 0 && R > 0, "mcca_build_split: bad dims");
+  CPSD_CHECK_ARG(Gxx != nullptr && xslot != nullptr, "mcca_build_split: Gxx / xslot is NULL");
+  if (nfold == 0) return CPSD_OK;
+  const size_t smem = (size_t)P * R * (sizeof(int) + sizeof(float));
+  k_mcca_build<<<nfold, 256, smem, stream>>>(Gt, ldg, strideG, Gxx, ldx, strideX, xslot, r_eff, P, R,
+                                             reg, M, ldm, strideM, n_out, cidx, dh, n_comp, status);
   CPSD_LAUNCH_CHECK();
   return CPSD_OK;
 }

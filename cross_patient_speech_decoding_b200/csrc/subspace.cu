@@ -184,7 +184,8 @@ k_sgemm(const float* __restrict__ A, int lda, long long strideA, const float* __
 // positive (rank-deficient block); the pivot is then replaced so the factor stays finite.
 // ---------------------------------------------------------------------------------------
 #define CH_LD 129
-__global__ void __launch_bounds__(256)
+#define CH_NT 1024
+__global__ void __launch_bounds__(CH_NT)
 k_chol_inv(const float* __restrict__ S, int lds, long long strideS, int m,
            float* __restrict__ Rinv, int ldr, long long strideR, int* __restrict__ status) {
   // P: strict lower triangle + diagonal = Cholesky factor L; afterwards the strict upper
@@ -197,9 +198,9 @@ k_chol_inv(const float* __restrict__ S, int lds, long long strideS, int m,
   const int prob = blockIdx.x;
   const float* Sg = S + (long long)prob * strideS;
   const int tid = threadIdx.x;
-  const int tx = tid & 15, ty = tid >> 4;
+  const int tx = tid & 31, ty = tid >> 5;
   if (tid == 0) s_bad = 0;
-  for (int e = tid; e < m * m; e += 256) {
+  for (int e = tid; e < m * m; e += CH_NT) {
     const int r = e / m, c = e - r * m;
     P[r * CH_LD + c] = (c <= r) ? 0.5 * ((double)Sg[(long long)r * lds + c] +
                                          (double)Sg[(long long)c * lds + r])
@@ -222,12 +223,12 @@ k_chol_inv(const float* __restrict__ S, int lds, long long strideS, int m,
     __syncthreads();
     const double ljj = s_piv;
     const double inv = 1.0 / ljj;
-    for (int i = j + tid; i < m; i += 256) P[i * CH_LD + j] = (i == j) ? ljj : P[i * CH_LD + j] * inv;
+    for (int i = j + tid; i < m; i += CH_NT) P[i * CH_LD + j] = (i == j) ? ljj : P[i * CH_LD + j] * inv;
     __syncthreads();
     // trailing update of the lower triangle: L[i][k] -= L[i][j] L[k][j], j < k <= i < m
-    for (int i = j + 1 + ty; i < m; i += 16) {
+    for (int i = j + 1 + ty; i < m; i += 32) {
       const double lij = P[i * CH_LD + j];
-      for (int k = j + 1 + tx; k <= i; k += 16) P[i * CH_LD + k] -= lij * P[k * CH_LD + j];
+      for (int k = j + 1 + tx; k <= i; k += 32) P[i * CH_LD + k] -= lij * P[k * CH_LD + j];
     }
     __syncthreads();
   }
@@ -235,12 +236,12 @@ k_chol_inv(const float* __restrict__ S, int lds, long long strideS, int m,
   // eliminated from every row below.  X[i][c] (c < i) lives at P[c][i].
   for (int k = 0; k < m; ++k) {
     const double inv = 1.0 / P[k * CH_LD + k];
-    for (int c = tid; c < k; c += 256) P[c * CH_LD + k] *= inv;
+    for (int c = tid; c < k; c += CH_NT) P[c * CH_LD + k] *= inv;
     if (tid == 0) xd[k] = inv;
     __syncthreads();
-    for (int i = k + 1 + ty; i < m; i += 16) {
+    for (int i = k + 1 + ty; i < m; i += 32) {
       const double lik = P[i * CH_LD + k];
-      for (int c = tx; c <= k; c += 16) {
+      for (int c = tx; c <= k; c += 32) {
         const double xkc = (c == k) ? inv : P[c * CH_LD + k];
         P[c * CH_LD + i] -= lik * xkc;
       }
@@ -249,7 +250,7 @@ k_chol_inv(const float* __restrict__ S, int lds, long long strideS, int m,
   }
   // Rinv = (L^T)^{-1} = X^T (upper)
   float* Rg = Rinv + (long long)prob * strideR;
-  for (int e = tid; e < m * m; e += 256) {
+  for (int e = tid; e < m * m; e += CH_NT) {
     const int r = e / m, c = e - r * m;
     Rg[(long long)r * ldr + c] = (r < c) ? (float)P[r * CH_LD + c] : (r == c ? (float)xd[r] : 0.f);
   }
@@ -380,7 +381,7 @@ extern "C" int cpsd_chol_inv(const float* S, int lds, long long strideS, int m, 
   if (nprob == 0) return CPSD_OK;
   const size_t smem = 128 * CH_LD * sizeof(double);
   CPSD_CUDA(cudaFuncSetAttribute(k_chol_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_chol_inv<<<nprob, 256, smem, stream>>>(S, lds, strideS, m, Rinv, ldr, strideR, status);
+  k_chol_inv<<<nprob, CH_NT, smem, stream>>>(S, lds, strideS, m, Rinv, ldr, strideR, status);
   CPSD_LAUNCH_CHECK();
   return CPSD_OK;
 }

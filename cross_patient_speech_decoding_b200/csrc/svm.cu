@@ -238,6 +238,9 @@ k_svm_fit(const cpsd_svm_desc* __restrict__ descs, int kp_max, int n_max) {
     double rz = bdot(s.r, s.zz, kp, s.red);
     const double r0 = sqrt(bdot(s.r, s.r, kp, s.red));
     const int cg_max = 4 * kp + 20;
+    // inexact Newton: the linear system is solved to a relative residual that tightens with
+    // the gradient (eta = min(0.1, |g| / |g0|), quadratic forcing), down to 1e-10
+    const double eta = fmax(1e-10, fmin(0.1, gmax / g0));
     for (int cg = 0; cg < cg_max; ++cg) {
       xmul(St, lds, n, k, s.p, s.q);
       __syncthreads();
@@ -256,7 +259,7 @@ k_svm_fit(const cpsd_svm_desc* __restrict__ descs, int kp_max, int n_max) {
       __syncthreads();
       ++cg_total;
       const double rn = sqrt(bdot(s.r, s.r, kp, s.red));
-      if (rn <= 1e-10 * r0) break;
+      if (rn <= eta * r0) break;
       for (int j = threadIdx.x; j < kp; j += SV_NT) s.zz[j] = s.r[j] / s.dg[j];
       __syncthreads();
       const double rzn = bdot(s.r, s.zz, kp, s.red);

@@ -200,12 +200,16 @@ k_proj_tc(const CUtensorMap* __restrict__ xmaps, const CUtensorMap* __restrict__
       }
       const int* drow = dst_row + ((long long)f0 * prm.P + v) * prm.n_max;
       int d_next = (my_tr >= 0) ? drow[my_tr] : -1;
+      // mu L of the fold: lane j keeps column j, broadcast by shuffle in the epilogue
+      float ml_next = muL[(long long)(f0 * prm.P + v) * PT_N + lane];
       for (int f = f0; f < f1; ++f, ++it_b) {
         const int s = it_b & 1;
         const int d = d_next;
-        if (f + 1 < f1) {        // destination of the next fold: in flight during this one
+        const float ml_mine = ml_next;
+        if (f + 1 < f1) {        // destination / mu L of the next fold: in flight during this one
           drow += (long long)prm.P * prm.n_max;
           d_next = (my_tr >= 0) ? drow[my_tr] : -1;
+          ml_next = muL[(long long)((f + 1) * prm.P + v) * PT_N + lane];
         }
         mbar_wait(&t_full[s], (it_b >> 1) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -214,9 +218,9 @@ k_proj_tc(const CUtensorMap* __restrict__ xmaps, const CUtensorMap* __restrict__
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_empty[s]);
-        const float* ml = muL + (long long)(f * prm.P + v) * PT_N;
 #pragma unroll
-        for (int j = 0; j < PT_N; ++j) stg[r_own * PT_LDS + j] = __uint_as_float(vv[j]) - ml[j];
+        for (int j = 0; j < PT_N; ++j)
+          stg[r_own * PT_LDS + j] = __uint_as_float(vv[j]) - __shfl_sync(0xffffffffu, ml_mine, j);
         row_off[et] = (d >= 0) ? (d * prm.T + my_t) * Q : -1;
         asm volatile("bar.sync 1, 128;" ::: "memory");
         float* Yf = Y + (long long)f * prm.strideY;

@@ -28,6 +28,18 @@ def _ceil(a, b):
     return (a + b - 1) // b * b
 
 
+_LANE_STREAMS = {}
+
+
+def _lane_stream(device, i):
+    """One CUDA stream per (device, lane index) for the whole process: torch's caching allocator
+    pools memory per stream, so engines created one after the other reuse the same blocks."""
+    key = (str(device), i)
+    if key not in _LANE_STREAMS:
+        _LANE_STREAMS[key] = torch.cuda.Stream(device)
+    return _LANE_STREAMS[key]
+
+
 class View:
     """One patient resident on the device."""
 
@@ -64,7 +76,7 @@ class CVEngine:
                  decoder_var=0.8, C=1.0, tar_in_train=True, device=None, max_batch=32,
                  dcd_epochs=0, max_newton=60, tol_newton=1e-9, tol_dcd=1e-4,
                  eig_sweeps=12, eig_tol=3e-7, use_tensor_cores=False, pool_solver='auto',
-                 topk_block=128, topk_iters=8, topk_tol=2e-5, topk_rounds=3):
+                 topk_block=128, topk_iters=8, topk_tol=2e-5, topk_rounds=3, n_lanes=2):
         self.ctx = Context.get(device)
         self.method = method
         if n_comp is None:
@@ -108,7 +120,7 @@ class CVEngine:
         self.packB = HostPack(self.ctx)
         self.packM = [HostPack(self.ctx), HostPack(self.ctx)]   # MCCA batches alternate
         self._pack_i = 0
-        self._before_sync = None
+        self.n_lanes = int(n_lanes)
         self._ws = {}
         self._sched = {}
         self.stats = {}
@@ -216,7 +228,8 @@ class CVEngine:
         """Leading eigen-pairs of K (nprob, n_pad, n_pad) by subspace iteration; K keeps its
         leading block.  Fills evals / k2 and returns (V tensor view, ldv, strideV) when every
         problem reached its component count inside the block with converged Ritz pairs, else
-        None (the caller falls back to the full solver)."""
+        None (the caller falls back to the full solver).  Generator: yields before every
+        blocking read-back so that another lane's work can be queued first."""
         ctx = self.ctx
         nws = int(ctx.lib.cpsd_eig_topk_ws_elems(n_pad, m, nprob))
         ws = self.ws(tag + '_tkws', (nws,))
@@ -234,7 +247,7 @@ class CVEngine:
                      self.eig_tol)
             ctx.call('cpsd_select_k_total', ptr(evals), evals.shape[-1], ptr(None), m, ptr(tot),
                      thr, mode, 1, min(kcap, m), ptr(k2), 1, nprob)
-            self._sync_hook()
+            yield 'sync'
             k2h = k2.cpu().numpy()
             rh = resid.cpu().numpy()
             ev0 = evals[:, 0].cpu().numpy()
@@ -311,6 +324,28 @@ class CVEngine:
                       evec=self.ctx.zeros((cap, n_pad, n_pad)))
             self._vs = vs
         return vs
+
+    def _xcache(self, R, XR):
+        """Reduced coordinates Zx (K*T x (P-1)R) of the cross patients' condition averages and
+        their cross-scatter Gxx, one slot per shared class set (fold-invariant)."""
+        xc = getattr(self, '_xc', None)
+        if xc is None or xc['R'] != R:
+            cap = max(16, 2 * self.max_batch)
+            ncls = len(set.intersection(*self.cross_classes)) if self.P > 1 else 1
+            KT = max(ncls, 1) * self.T
+            # slots are claimed lazily: memory is cap * KT * XR floats at most (~9 MB per slot at
+            # the headline shapes), allocated in chunks of 16
+            xc = dict(R=R, cap=cap, KT=KT, keys={}, Zx=None, Gxx=None, alloc=0)
+            self._xc = xc
+        need = min(xc['cap'], len(xc['keys']) + self.max_batch)
+        if xc['alloc'] < need or xc['Zx'] is None:
+            n = min(xc['cap'], max(need, 16))
+            Zx = self.ctx.zeros((n, xc['KT'], max(XR, 1)))
+            Gxx = self.ctx.zeros((n, max(XR, 1), max(XR, 1)))
+            if xc['Zx'] is not None:
+                xc['keys'].clear()       # slots moved: recompute on demand
+            xc['Zx'], xc['Gxx'], xc['alloc'] = Zx, Gxx, n
+        return xc
 
     def _slot_means(self, mu, slot, Cm):
         idx = torch.from_numpy(slot.ravel()).to(mu.device)
@@ -483,12 +518,30 @@ class CVEngine:
                       ptr(k_out, offset), stride, nprob)
 
     # ------------------------------------------------------------------ public API
-    def _sync_hook(self):
-        """Called right before the first blocking read-back of a batch: the host uses the wait
-        to pack the next batch's index tables and descriptors."""
-        h, self._before_sync = self._before_sync, None
-        if h is not None:
-            h()
+    def _lanes(self, n):
+        """Independent execution lanes: shallow copies of the engine that share the resident
+        patient data and fold-invariant tables but own their stream, workspaces, index packs and
+        view-statistics cache, so consecutive batches can be in flight at the same time."""
+        if getattr(self, 'stream', None) is None:
+            self.stream = _lane_stream(self.ctx.device, 0)
+        extra = getattr(self, '_extra_lanes', None)
+        if extra is None:
+            extra = self._extra_lanes = []
+        while 1 + len(extra) < n:
+            import copy
+            ln = copy.copy(self)
+            ln._extra_lanes = None                    # no reference cycles: engines must die by
+            ln._ws, ln._vs, ln._tc_stage, ln._marks = {}, None, None, []   # refcount
+            ln._xc = None
+            ln.packA, ln.packB = HostPack(self.ctx), HostPack(self.ctx)
+            ln.packM = [HostPack(self.ctx), HostPack(self.ctx)]
+            ln._pack_i = 0
+            if getattr(self, '_tcp', None) is not None:
+                ln._tcp = dict(self._tcp, cap=0)      # shares the X split + maps, own L^T buffers
+            ln.stream = _lane_stream(self.ctx.device, 1 + len(extra))
+            extra.append(ln)
+        lanes = [self] + extra
+        return lanes[:n]
 
     def run(self, folds, return_details=False):
         """folds: list of (train_idx, test_idx) into the target's trials.  Returns a dict with
@@ -498,32 +551,48 @@ class CVEngine:
         nb = max(1, -(-len(folds) // self.max_batch))
         size = -(-len(folds) // nb)          # balanced batches (a short tail batch costs as much
         batches = [folds[s:s + size] for s in range(0, len(folds), size)]   # as a full one)
-
-        def take(res):
+        results = [None] * len(batches)
+        if self.method == 'mcca':
+            # every batch is a generator that yields right before each blocking read-back; the
+            # lanes are advanced round-robin, so while one lane waits for its GPU results the
+            # host packs and queues the other lane's batch on its own stream
+            if self._tc_proj_ready(int(self.n_comp)):
+                pass                                   # split X / encode maps before the lanes fork
+            nl = 1 if (self.profile or len(batches) == 1) else min(self.n_lanes, len(batches))
+            lanes = self._lanes(nl)
+            todo = [list(range(li, len(batches), nl)) for li in range(nl)]
+            gens = [None] * nl
+            cur = [None] * nl
+            torch.cuda.current_stream(self.ctx.device).synchronize()
+            live = sum(len(t) for t in todo)
+            while live:
+                for li, ln in enumerate(lanes):
+                    if gens[li] is None:
+                        if not todo[li]:
+                            continue
+                        cur[li] = todo[li].pop(0)
+                        with torch.cuda.stream(ln.stream):
+                            gens[li] = ln._mcca_start(batches[cur[li]], return_details)
+                        continue
+                    with torch.cuda.stream(ln.stream):
+                        try:
+                            next(gens[li])
+                        except StopIteration as e:
+                            results[cur[li]] = e.value
+                            gens[li] = None
+                            live -= 1
+            for ln in lanes:
+                ln.stream.synchronize()
+        else:
+            for i, batch in enumerate(batches):
+                results[i] = self._batch_cca(batch, return_details)
+        for res in results:
             out['y_pred'] += res['y_pred']
             out['k2'] += res['k2']
             out['h2d_bytes'] += res['h2d_bytes']
             out['d2h_bytes'] += res['d2h_bytes']
             if return_details:
                 details.append(res['details'])
-
-        if self.method == 'mcca':
-            # software pipeline: batch i+1 is packed on the host (and its tables uploaded) while
-            # the GPU works on batch i
-            nxt = [self._mcca_start(batches[0], return_details)] if batches else []
-            for i in range(len(batches)):
-                cur = nxt.pop()
-
-                def prefetch(i=i):
-                    if i + 1 < len(batches):
-                        nxt.append(self._mcca_start(batches[i + 1], return_details))
-                self._before_sync = prefetch
-                res = self._mcca_finish(cur)
-                self._sync_hook()            # in case the batch never blocked
-                take(res)
-        else:
-            for batch in batches:
-                take(self._batch_cca(batch, return_details))
         if return_details:
             out['details'] = details
         return out
@@ -538,16 +607,8 @@ class CVEngine:
             1e3 * (time.perf_counter() - t0)
         return g
 
-    @staticmethod
-    def _mcca_finish(g):
-        try:
-            next(g)
-        except StopIteration as e:
-            return e.value
-        raise RuntimeError('batch generator did not finish')
-
     def _batch_mcca(self, batch, want_details, align_only=False):
-        return self._mcca_finish(self._mcca_start(batch, want_details, align_only))
+        return _drain(self._mcca_start(batch, want_details, align_only))
 
     def align_mcca(self, train_idx=None):
         """MCCA fit only (AlignMCCA.fit): loadings, view means and generalised eigenvalues for
@@ -627,8 +688,12 @@ class CVEngine:
         ctx.call('cpsd_gram_nt_tc', ctypes.c_void_p(recs.ctypes.data), nprob, nmax, nmax, ptr(split),
                  split.numel(), ctypes.c_void_p(a), ctypes.c_void_p(self._tc_stage.data_ptr()))
 
-    def _pooled_stage_run(self, pk, d1, d2, B, Zall, mu, Kall, n_pad, F, n_pool, n_te, o_npool,
-                          o_nall, o_ypool, n_te_max, want_details):
+    def _pooled_stage_run(self, *args):
+        """Blocking form of _pooled_stage_run_gen (CCA / none batches)."""
+        return _drain(self._pooled_stage_run_gen(*args))
+
+    def _pooled_stage_run_gen(self, pk, d1, d2, B, Zall, mu, Kall, n_pad, F, n_pool, n_te, o_npool,
+                              o_nall, o_ypool, n_te_max, want_details):
         ctx = self.ctx
         npool_dev = ctypes_int_ptr(pk.iaddr(o_npool))
         nall_dev = ctypes_int_ptr(pk.iaddr(o_nall))
@@ -670,7 +735,8 @@ class CVEngine:
                          or (min(n_pool) - 1 >= 2 * m and F >= 2 * m)))
         perm_p = ptr(None)
         if use_topk:
-            got = self.eig_topk(Kall, n_pad, npool_dev, B, m, evals, 'pool', thr, mode, kcap, k2)
+            got = yield from self.eig_topk(Kall, n_pad, npool_dev, B, m, evals, 'pool', thr, mode,
+                                           kcap, k2)
             if got is not None:
                 V, ldv, sV = got
             self.mark('pool_eigvecs')
@@ -687,7 +753,7 @@ class CVEngine:
             if n_pad > 128:
                 # eigenvectors of the k2 retained components only (rotation-log replay); one
                 # small read-back sizes the replay grid to the columns actually kept
-                self._sync_hook()
+                yield 'sync'
                 self._k2_max = max(int(k2.cpu().numpy().max()), 1)
                 k_launch = min(kcap, _ceil(self._k2_max, 64))
                 self.eig_vecs('pool', n_pad, B, perm, k2, 0, k_launch, V)
@@ -794,6 +860,24 @@ class CVEngine:
             slot[f, 1:] = row
         o_slot = pk.add_ints(slot)
         o_cds = pk.add_ints([self.views[v].C for _, v, _ in solve])
+        # cross-block cache slot of every fold (one slot per shared class set)
+        XR = (P - 1) * R
+        xc = self._xcache(R, XR)
+        newx = []                       # (cache slot, first fold with that class set)
+        xs_of = {}
+        xslot = np.zeros(B, dtype=np.int32)
+        if len(xc['keys']) + B > xc['cap']:
+            xc['keys'].clear()
+        for f in range(B):
+            xs = xc['keys'].get(keys[f])
+            if xs is None:
+                xs = xs_of.get(keys[f])
+                if xs is None:
+                    xs = len(xc['keys']) + len(xs_of)
+                    xs_of[keys[f]] = xs
+                    newx.append((xs, f))
+            xslot[f] = xs
+        o_xslot = pk.add_ints(xslot)
         downdate = use_rank and getattr(self, 'tg', None) is not None and n_padC == 128
         if downdate:
             use_te = sum(len(tb['te']) for tb in tabs) <= sum(len(tb['tr']) for tb in tabs)
@@ -900,23 +984,52 @@ class CVEngine:
         Vr = self.ws('m_Vr', (B * P, Cm, R))
         d2 = self.ws('m_d2', (B * P, R))
         r_eff = self.ws('m_reff', (B * P,), I32)
-        Zcat = self.ws('m_Zcat', (B, KTmax, P * R))
-        Gz = self.ws('m_Gz', (B, P * R, P * R))
-        pi = np.arange(B * P, dtype=np.int64)
-        pf, pv = pi // P, pi % P
-        r_pz = np.zeros(B * P, dtype=_lib.PROJ_DESC)
-        r_pz['X'], r_pz['seg_src'], r_pz['seg_dst'] = cmb.ravel(), segb.ravel(), ib + 4 * o_segdst
-        r_pz['mu'], r_pz['W'] = mub.ravel(), addr(Vr) + 4 * Cm * R * pi
-        r_pz['Y'] = addr(Zcat) + 4 * (KTmax * P * R * pf + R * pv)
-        r_pz['nseg'], r_pz['seg_len'], r_pz['C'], r_pz['q'] = Ksa[pf], T, cdims[pv], R
-        r_pz['ldx'], r_pz['ldw'], r_pz['ldy'] = cdims[pv], R, P * R
-        r_g = np.zeros(B, dtype=_lib.GRAM_TN_DESC)
-        r_g['A'] = r_g['B'] = addr(Zcat) + 4 * KTmax * P * R * fi
+        # reduced coordinates of the condition averages: the target's per fold (Zt), the cross
+        # patients' once per shared class set (Zx, cached with their cross-scatter block Gxx)
+        nX = len(newx)
+        KTc = xc['KT']
+        Zt = self.ws('m_Zt', (B, KTmax, R))
+        Gtx = self.ws('m_Gtx', (B, R, P * R))
+        Zx, Gxx = xc['Zx'], xc['Gxx']
+        npz = B + nX * (P - 1)
+        r_pz = np.zeros(npz, dtype=_lib.PROJ_DESC)
+        # targets
+        r_pz['X'][:B], r_pz['seg_src'][:B] = cmb[:, 0], segb[:, 0]
+        r_pz['mu'][:B], r_pz['W'][:B] = mub[:, 0], addr(Vr) + 4 * Cm * R * P * fi
+        r_pz['Y'][:B] = addr(Zt) + 4 * KTmax * R * fi
+        r_pz['nseg'][:B], r_pz['C'][:B], r_pz['ldx'][:B], r_pz['ldy'][:B] = Ksa, cdims[0], cdims[0], R
+        j = B
+        for xs, f in newx:
+            for v in range(1, P):
+                r_pz[j] = (cmb[f, v], segb[f, v], 0, mub[f, v], addr(Vr, (f * P + v) * Cm * R),
+                           addr(Zx, xs * KTc * XR + (v - 1) * R), Ks[f], T, cdims[v], R, cdims[v],
+                           R, XR, 0)
+                j += 1
+        r_pz['seg_dst'], r_pz['seg_len'], r_pz['q'], r_pz['ldw'] = ib + 4 * o_segdst, T, R, R
+        ng = (2 * B if XR else B) + nX
+        r_g = np.zeros(ng, dtype=_lib.GRAM_TN_DESC)
+        zt = addr(Zt) + 4 * KTmax * R * fi
+        r_g['A'][:B] = r_g['B'][:B] = zt
+        r_g['out'][:B] = addr(Gtx) + 4 * R * P * R * fi
+        r_g['seg_len'][:B] = Ksa * T
+        r_g['p'][:B] = r_g['q'][:B] = r_g['lda'][:B] = r_g['ldb'][:B] = R
+        r_g['sym'][:B] = 1
+        if XR:
+            r_g['A'][B:2 * B] = zt
+            r_g['B'][B:2 * B] = addr(Zx) + 4 * KTc * XR * xslot.astype(np.int64)
+            r_g['out'][B:2 * B] = addr(Gtx) + 4 * (R * P * R * fi + R)
+            r_g['seg_len'][B:2 * B] = Ksa * T
+            r_g['p'][B:2 * B] = r_g['lda'][B:2 * B] = R
+            r_g['q'][B:2 * B] = r_g['ldb'][B:2 * B] = XR
+            j = 2 * B
+            for xs, f in newx:
+                zx = addr(Zx, xs * KTc * XR)
+                r_g[j] = (zx, zx, 0, 0, 0, 0, addr(Gxx, xs * XR * XR), 1, Ks[f] * T, XR, XR, XR, XR,
+                          XR, 1, 1.0, 0)
+                j += 1
         r_g['segA'] = r_g['segB'] = pk.iaddr(pk.o_zero)
-        r_g['out'] = addr(Gz) + 4 * P * R * P * R * fi
-        r_g['nseg'], r_g['seg_len'] = 1, Ksa * T
-        r_g['p'] = r_g['q'] = r_g['lda'] = r_g['ldb'] = r_g['ldo'] = P * R
-        r_g['sym'], r_g['alpha'] = 1, 1.0
+        r_g['nseg'], r_g['alpha'] = 1, 1.0
+        r_g['ldo'][:2 * B if XR else B] = P * R
         d_pz, d_g = pk.add_descs(r_pz), pk.add_descs(r_g)
         # pooled projection
         # size of the reduced GEVP: the target's rank is only known on the device (<= R), the
@@ -1002,8 +1115,9 @@ class CVEngine:
         ctx.call('cpsd_mcca_mask_idx', ptr(vs['evec']), n_padC, n_padC * n_padC, ptr(vs['ev']),
                  n_padC, ptr(rank_dev) if use_rank else ptr(None), cdim_dev,
                  ctypes_int_ptr(pk.iaddr(o_slot)), R, Cm, ptr(Vr), ptr(d2), ptr(r_eff), B * P)
-        ctx.call('cpsd_proj_nn', pk.daddr(d_pz), B * P, max(Ks), T, R)
-        ctx.call('cpsd_gram_tn', pk.daddr(d_g), B, P * R, P * R)
+        ctx.call('cpsd_proj_nn', pk.daddr(d_pz), npz, max(Ks), T, R)
+        ctx.call('cpsd_gram_tn', pk.daddr(d_g), ng, max(R, XR), max(R, XR))
+        xc['keys'].update(xs_of)
         M = self.ws('m_M', (B, n_padM, n_padM))
         M.zero_()
         n_m = self.ws('m_nm', (B,), I32)
@@ -1012,8 +1126,13 @@ class CVEngine:
         status = self.ws('m_status', (B,), I32)
         status.zero_()
         reg = -1.0 if self.regs is None else float(self.regs)
-        ctx.call('cpsd_mcca_build', ptr(Gz), P * R, P * R * P * R, ptr(r_eff), P, R, reg, ptr(M),
-                 n_padM, n_padM * n_padM, ptr(n_m), ptr(cidx), ptr(dh), Q, ptr(status), B)
+        if XR:
+            ctx.call('cpsd_mcca_build_split', ptr(Gtx), P * R, R * P * R, ptr(Gxx), XR, XR * XR,
+                     ctypes_int_ptr(pk.iaddr(o_xslot)), ptr(r_eff), P, R, reg, ptr(M), n_padM,
+                     n_padM * n_padM, ptr(n_m), ptr(cidx), ptr(dh), Q, ptr(status), B)
+        else:
+            ctx.call('cpsd_mcca_build', ptr(Gtx), R, R * R, ptr(r_eff), P, R, reg, ptr(M), n_padM,
+                     n_padM * n_padM, ptr(n_m), ptr(cidx), ptr(dh), Q, ptr(status), B)
         self.mark('mcca_gevp')
         evm, U = self.eig_any(M, n_padM, ptr(n_m), 0, B, 'mm', ncols=Q)
         ctx.call('cpsd_mcca_loadings', ptr(Vr), ptr(U), n_padM, n_padM * n_padM, ptr(None), 0,
@@ -1039,7 +1158,7 @@ class CVEngine:
         else:
             ctx.call('cpsd_proj_nn', ctypes_off(pk.daddr(d_pp), 0), B * P + B,
                      max(max(self.views[v].N for v in range(P)), n_te_max), T, Q)
-        evals, k2_, St_, Ste, V, sweeps, kcap = self._pooled_stage_run(
+        evals, k2_, St_, Ste, V, sweeps, kcap = yield from self._pooled_stage_run_gen(
             pk, d_p1, d_p2, B, Zall, pmu, Kall, n_pad, F, n_pool, n_te, o_npool, o_nall, o_ypool,
             n_te_max, want_details)
         self.mark('svm')
@@ -1052,6 +1171,7 @@ class CVEngine:
                  ncls * (kcap + 1), ptr(k2), 0, ctypes_int_ptr(pk.iaddr(o_nte)), n_te_max,
                  ptr(self.classes_dev), ncls, ptr(yhat), ptr(None), B)
         self.mark('end')
+        yield 'sync'
         yh = yhat.cpu().numpy()
         k2h = k2.cpu().numpy()
         st = status.cpu().numpy()
@@ -1074,6 +1194,15 @@ class CVEngine:
     def _batch_cca(self, batch, want_details):
         from .engine_cca import batch_cca
         return batch_cca(self, batch, want_details)
+
+
+def _drain(g):
+    """Runs a generator to completion and returns its value."""
+    try:
+        while True:
+            next(g)
+    except StopIteration as e:
+        return e.value
 
 
 def ctypes_int_ptr(address):

@@ -196,6 +196,12 @@ int cpsd_mcca_mask_idx(const float* evecs, int ldv, long long strideV, const flo
 int cpsd_mcca_build(const float* G, int ldg, long long strideG, const int* r_eff, int P, int R,
                     float reg, float* M, int ldm, long long strideM, int* n_out, int* cidx,
                     float* dh, int n_comp, int* status, int nfold, cudaStream_t stream);
+/* the cross-scatter in two parts: per-fold target rows [G_tt | G_tx] (R x P*R) and the cached
+ * fold-invariant cross x cross block of slot xslot[f] */
+int cpsd_mcca_build_split(const float* Gt, int ldg, long long strideG, const float* Gxx, int ldx,
+                          long long strideX, const int* xslot, const int* r_eff, int P, int R,
+                          float reg, float* M, int ldm, long long strideM, int* n_out, int* cidx,
+                          float* dh, int n_comp, int* status, int nfold, cudaStream_t stream);
 int cpsd_mcca_loadings(const float* Vr, const float* U, int ldu, long long strideU,
                        const int* perm, int ld_perm, const int* r_eff, const float* dh, int P,
                        int R, int Cmax, int n_comp, float* L, int ldl, int nfold,

@@ -13,7 +13,7 @@ ap.add_argument('--steps', type=int, default=1)
 ap.add_argument('--folds', type=int, default=107)
 ap.add_argument('--no-tc', action='store_true')
 ap.add_argument('--stages', action='store_true')
-ap.add_argument('--dcd', type=int, default=2)
+ap.add_argument('--dcd', type=int, default=0)
 a = ap.parse_args()
 from cross_patient_speech_decoding_b200.engine import CVEngine  # noqa: E402
 pts = bench.make_data()
