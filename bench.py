@@ -41,27 +41,61 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """SM clocks / throttle reasons while the timed region runs.  Sampled in-process through
+    NVML (nvidia_ml_py): spawning nvidia-smi every 200 ms stalls kernel launches for tens of
+    milliseconds, which is visible in a sub-second timed region.  Falls back to nvidia-smi."""
 
     Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
+    NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
 
-    def __init__(self, index):
-        self.index, self.rows, self.stop = index, [], False
+    def __init__(self, index, period=0.1):
+        self.index, self.rows, self.stop, self.period = index, [], False, period
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = index
+            if vis:
+                ids = vis.split(',')
+                if index < len(ids) and ids[index].strip().isdigit():
+                    phys = int(ids[index])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
         self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        bits = [getattr(n, 'nvmlClocksThrottleReasonHwSlowdown', 0x8),
+                getattr(n, 'nvmlClocksThrottleReasonHwThermalSlowdown', 0x40),
+                getattr(n, 'nvmlClocksThrottleReasonSwThermalSlowdown', 0x20),
+                getattr(n, 'nvmlClocksThrottleReasonSwPowerCap', 0x4)]
+        return [str(sm), str(mx)] + ['Active' if (r & b) else 'Not Active' for b in bits]
 
     def _run(self):
         while not self.stop:
             try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                      '--format=csv,noheader,nounits'], capture_output=True,
-                                     text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(',')])
+                if self.nvml is not None:
+                    self.rows.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(['nvidia-smi', '-i', str(self.index),
+                                          '--query-gpu=' + self.Q, '--format=csv,noheader,nounits'],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([c.strip() for c in out.split(',')])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(self.period if self.nvml is not None else 0.5)
 
     def __enter__(self):
         self.t.start()
@@ -74,12 +108,11 @@ class ClockSampler:
     def summary(self):
         sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for i, n in enumerate(names)
+        reasons = [n for i, n in enumerate(self.NAMES)
                    if any(len(r) > 2 + i and r[2 + i].lower().startswith('active') for r in self.rows)]
         return {'sm_mhz': float(np.median(sm)) if sm else None,
                 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
-                'samples': len(self.rows)}
+                'samples': len(self.rows), 'source': 'nvml' if self.nvml is not None else 'nvidia-smi'}
 
 
 def make_data():
