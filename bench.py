@@ -188,12 +188,13 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=8)
+    ap.add_argument('--steps', type=int, default=48)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours')
     ap.add_argument('--no-tc', action='store_true', help='fp32 SIMT pooled Gram instead of tcgen05')
     ap.add_argument('--cpu-folds', type=int, default=2, help='folds in the cpu_baseline sample')
     ap.add_argument('--e2e-steps', type=int, default=None)
+    ap.add_argument('--e2e-depth', type=int, default=8, help='steps in flight in the e2e measurement')
     ap.add_argument('--batch', type=int, default=148, help='max folds per engine batch')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
@@ -278,17 +279,30 @@ def main():
     folds_total = world * args.steps * N_FOLDS
     value = folds_total / (ms_max * 1e-3)
 
-    # ---- end to end through the public host-buffer API (uploads + fold-invariant work inside)
-    e2e_steps = args.e2e_steps or min(args.steps, 3)
+    # ---- end to end through the public host-buffer API: every step uploads its inputs (8 patients,
+    # float64, pinned host memory), runs its 20 folds and reads its predictions back.  The
+    # streaming entry point keeps `depth` independent steps in flight on separate CUDA streams;
+    # the blocking one-call-per-step form is reported beside it.
+    from cross_patient_speech_decoding_b200 import cv_align_decode_stream
+    e2e_steps = args.e2e_steps or max(args.steps, 12)
     host_pts = [(torch.from_numpy(np.ascontiguousarray(X)).pin_memory(), y, ya)
                 for X, y, ya in pts]
-    cv_align_decode(host_pts[0], host_pts[1:], step_folds(y0, 77), device='cuda:%d' % local, **kw)
+    kw_e2e = dict(kw, max_batch=N_FOLDS)
+
+    def jobs(n, seed0):
+        for s in range(n):
+            yield host_pts[0], host_pts[1:], step_folds(y0, seed0 + s)
+
+    for _ in cv_align_decode_stream(jobs(4, 77), depth=args.e2e_depth, device='cuda:%d' % local,
+                                    **kw_e2e):
+        pass
     sync_all()
     t0 = time.perf_counter()
     e2e_h2d = e2e_d2h = 0
-    for s in range(e2e_steps):
-        r = cv_align_decode(host_pts[0], host_pts[1:], step_folds(y0, 500 + rank * 1000 + s),
-                            device='cuda:%d' % local, **kw)
+    e2e_ok = e2e_tot = 0
+    for s, r in enumerate(cv_align_decode_stream(jobs(e2e_steps, 500 + rank * 1000),
+                                                 depth=args.e2e_depth, device='cuda:%d' % local,
+                                                 **kw_e2e)):
         e2e_h2d += r['h2d_bytes']
         e2e_d2h += r['d2h_bytes']
     sync_all()
@@ -296,6 +310,16 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
     e2e_val = world * e2e_steps * N_FOLDS / float(e2e_dt.item())
+    # blocking form (one call per step, nothing overlapped)
+    nblk = min(e2e_steps, 4)
+    cv_align_decode(host_pts[0], host_pts[1:], step_folds(y0, 78), device='cuda:%d' % local, **kw_e2e)
+    sync_all()
+    t0 = time.perf_counter()
+    for s in range(nblk):
+        cv_align_decode(host_pts[0], host_pts[1:], step_folds(y0, 700 + rank * 1000 + s),
+                        device='cuda:%d' % local, **kw_e2e)
+    sync_all()
+    e2e_blocking = world * nblk * N_FOLDS / (time.perf_counter() - t0)
 
     # ---- stage breakdown + roofline of the dominant tensor / HBM kernels (profiling pass)
     # one engine batch of the size the timed region used, CUDA events between the stages
@@ -354,8 +378,11 @@ def main():
             'e2e': {'value': e2e_val, 'unit': 'folds/s',
                     'h2d_bytes_per_step': e2e_h2d // max(e2e_steps, 1),
                     'd2h_bytes_per_step': e2e_d2h // max(e2e_steps, 1), 'steps': e2e_steps,
-                    'api': 'cross_patient_speech_decoding_b200.cv_align_decode (host float64 '
-                           'arrays in pinned memory -> predictions)'},
+                    'api': 'cross_patient_speech_decoding_b200.cv_align_decode_stream (host float64 '
+                           'arrays in pinned memory -> predictions; every step uploads its own '
+                           'inputs; %d steps in flight)' % args.e2e_depth,
+                    'blocking_value': e2e_blocking,
+                    'blocking_api': 'cv_align_decode, one blocking call per step'},
             'gpu_launches': launches,
             'h2d_bytes_per_step': h2d // args.steps, 'd2h_bytes_per_step': d2h // args.steps,
             'clocks': clk.summary(),

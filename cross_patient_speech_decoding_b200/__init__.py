@@ -22,3 +22,70 @@ def cv_align_decode(target, cross, folds, method='mcca', **kw):
     out = eng.run(folds)
     out['h2d_bytes'] += sum(v.h2d_bytes for v in eng.views)
     return out
+
+
+def cv_align_decode_stream(jobs, depth=8, method='mcca', device=None, **kw):
+    """Pipelined form of ``cv_align_decode`` for many independent jobs (e.g. the 50 CV
+    iterations x patient sets of scripts/aligned_decode_svm_ncv.py:332-456): ``jobs`` is an
+    iterable of ``(target, cross, folds)``; results are yielded in order.  Up to ``depth`` jobs
+    are in flight, each on its own CUDA stream with its own upload, so the host->device copy
+    and the latency-bound small solvers of one job overlap the kernels of the others."""
+    import collections
+
+    import torch
+
+    from .engine import CVEngine, _lane_stream
+    from .device import Context
+    dev = Context.get(device).device
+    pending = collections.deque()
+    it = iter(jobs)
+    nsub = 0
+    done = False
+
+    def submit(job):
+        nonlocal nsub
+        lane = 8 + (nsub % depth) * 4           # leave room for the engines' extra lanes
+        nsub += 1
+        with torch.cuda.stream(_lane_stream(dev, lane)):
+            eng = CVEngine(job[0], job[1], method=method, device=dev, lane=lane, **kw)
+            gen = eng.run_gen(job[2])
+        return [eng, gen, None, False, None]     # engine, generator, result, done, wait event
+
+    import time
+    while True:
+        t_iter = time.perf_counter()
+        while not done and len(pending) < depth:
+            try:
+                job = next(it)
+            except StopIteration:
+                done = True
+                break
+            pending.append(submit(job))
+        if not pending:
+            return
+        progressed = False
+        for ent in pending:
+            if ent[3]:
+                continue
+            # resume a job only when the GPU work it queued before yielding has finished
+            if ent[4] is not None and len(pending) > 1 and not ent[4].query():
+                continue
+            progressed = True
+            with torch.cuda.stream(ent[0].stream):
+                try:
+                    next(ent[1])
+                    ent[4] = torch.cuda.Event()
+                    ent[4].record(ent[0].stream)
+                except StopIteration as e:
+                    out = e.value
+                    out['h2d_bytes'] += sum(v.h2d_bytes for v in ent[0].views)
+                    ent[2], ent[3] = out, True
+        while pending and pending[0][3]:
+            progressed = True
+            yield pending.popleft()[2]
+        if not progressed:
+            time.sleep(0)
+            cv_align_decode_stream.idle_s += time.perf_counter() - t_iter
+
+
+cv_align_decode_stream.idle_s = 0.0     # host time spent with every in-flight job waiting on the GPU

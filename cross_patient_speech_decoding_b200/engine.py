@@ -76,8 +76,19 @@ class CVEngine:
                  decoder_var=0.8, C=1.0, tar_in_train=True, device=None, max_batch=32,
                  dcd_epochs=0, max_newton=60, tol_newton=1e-9, tol_dcd=1e-4,
                  eig_sweeps=12, eig_tol=3e-7, use_tensor_cores=False, pool_solver='auto',
-                 topk_block=128, topk_iters=8, topk_tol=2e-5, topk_rounds=3, n_lanes=2):
+                 topk_block=128, topk_iters=8, topk_tol=2e-5, topk_rounds=3, n_lanes=2, lane=0):
         self.ctx = Context.get(device)
+        self.lane = int(lane)
+        self.stream = _lane_stream(self.ctx.device, self.lane)
+        with torch.cuda.stream(self.stream):     # uploads + fold-invariant work on the lane's stream
+            self._init(target, cross, method, n_comp, regs, pca_var, decoder_var, C, tar_in_train,
+                       max_batch, dcd_epochs, max_newton, tol_newton, tol_dcd, eig_sweeps, eig_tol,
+                       use_tensor_cores, pool_solver, topk_block, topk_iters, topk_tol, topk_rounds,
+                       n_lanes)
+
+    def _init(self, target, cross, method, n_comp, regs, pca_var, decoder_var, C, tar_in_train,
+              max_batch, dcd_epochs, max_newton, tol_newton, tol_dcd, eig_sweeps, eig_tol,
+              use_tensor_cores, pool_solver, topk_block, topk_iters, topk_tol, topk_rounds, n_lanes):
         self.method = method
         if n_comp is None:
             n_comp = 30 if method == 'mcca' else 0.9
@@ -286,7 +297,8 @@ class CVEngine:
                         ctypes.c_void_p(maps_h[2 * i + u].data_ptr()), ptr(t), vw.N * vw.T, vw.C,
                         vw.C, 128), 'tmap_encode')
                 keep += [hi, lo]
-            self._tcp = dict(xmaps=maps_h.to(ctx.device), split=keep, cap=0,
+            self._tcp = dict(xmaps=maps_h.to(ctx.device, non_blocking=True), xmaps_host=maps_h,
+                             split=keep, cap=0,
                              ntr=np.array([v.N for v in self.views], dtype=np.int32),
                              nch=np.array([v.C for v in self.views], dtype=np.int32),
                              sms=torch.cuda.get_device_properties(ctx.device).multi_processor_count)
@@ -305,7 +317,8 @@ class CVEngine:
             for u, t in enumerate((tcp['lthi'], tcp['ltlo'])):
                 _lib.check(ctx.lib.cpsd_tmap_encode_f32(ctypes.c_void_p(mh[u].data_ptr()), ptr(t),
                                                         cap * 32, 128, 128, 32), 'tmap_encode')
-            tcp['ltmaps'] = mh.to(ctx.device)
+            tcp['ltmaps'] = mh.to(ctx.device, non_blocking=True)
+            tcp['ltmaps_host'] = mh               # pinned source stays alive until the copy ran
             tcp['cap'] = cap
         return tcp
 
@@ -330,21 +343,13 @@ class CVEngine:
         their cross-scatter Gxx, one slot per shared class set (fold-invariant)."""
         xc = getattr(self, '_xc', None)
         if xc is None or xc['R'] != R:
-            cap = max(16, 2 * self.max_batch)
+            cap = max(32, self.max_batch + 16)
             ncls = len(set.intersection(*self.cross_classes)) if self.P > 1 else 1
             KT = max(ncls, 1) * self.T
-            # slots are claimed lazily: memory is cap * KT * XR floats at most (~9 MB per slot at
-            # the headline shapes), allocated in chunks of 16
-            xc = dict(R=R, cap=cap, KT=KT, keys={}, Zx=None, Gxx=None, alloc=0)
+            xc = dict(R=R, cap=cap, KT=KT, keys={},
+                      Zx=self.ctx.empty((cap, KT, max(XR, 1))),
+                      Gxx=self.ctx.empty((cap, max(XR, 1), max(XR, 1))))
             self._xc = xc
-        need = min(xc['cap'], len(xc['keys']) + self.max_batch)
-        if xc['alloc'] < need or xc['Zx'] is None:
-            n = min(xc['cap'], max(need, 16))
-            Zx = self.ctx.zeros((n, xc['KT'], max(XR, 1)))
-            Gxx = self.ctx.zeros((n, max(XR, 1), max(XR, 1)))
-            if xc['Zx'] is not None:
-                xc['keys'].clear()       # slots moved: recompute on demand
-            xc['Zx'], xc['Gxx'], xc['alloc'] = Zx, Gxx, n
         return xc
 
     def _slot_means(self, mu, slot, Cm):
@@ -408,17 +413,29 @@ class CVEngine:
         self.cross_classes = [set(np.unique(self.views[v].cls).tolist())
                               for v in range(1, self.P)]
         if self.method == 'mcca':
-            self.cross_rank = self._ranks_full(range(1, self.P))
+            # the ranks stay on the device until the first batch needs them on the host
+            # (_ensure_ready): constructing an engine does not block on its own uploads
+            self._rank_dev = self._ranks_full(range(1, self.P))
+            self.cross_rank = None
             self._target_trial_grams()
-        elif self.P > 1:
-            self._cross_pca()
-        torch.cuda.synchronize(self.ctx.device)
+            self._keep = [pk]                # staging of the kernels still in flight
+        else:
+            if self.P > 1:
+                self._cross_pca()
+            torch.cuda.current_stream(self.ctx.device).synchronize()
+
+    def _ensure_ready(self):
+        """Blocking tail of the constructor: signal ranks of the cross patients -> host."""
+        if self.method == 'mcca' and self.cross_rank is None:
+            with torch.cuda.stream(self.stream):
+                self.cross_rank = self._rank_dev.cpu().numpy().astype(np.int32)
+            self._keep = None
 
     def _ranks_full(self, vs):
         """AlignMCCA.n_components_var on all trials of the given views (AlignMCCA.py:146-150)."""
         vs = list(vs)
         if not (0 < self.pca_var < 1) or not vs:
-            return np.full(len(vs), self.n_comp, dtype=np.int32)
+            return torch.full((len(vs),), int(self.n_comp), dtype=I32, device=self.ctx.device)
         ctx, T, Cm = self.ctx, self.T, self.Cmax
         n_pad = _ceil(Cm, 128) if Cm > 128 else 128
         pk = HostPack(ctx)
@@ -435,13 +452,14 @@ class CVEngine:
                        1.0, 0)
         d = pk.add_descs(recs)
         pk.upload()
-        ctx.call(gram, pk.daddr(d), len(vs), Cm, Cm)
+        self.gram_scatter(gram, pk.daddr(d), len(vs), Cm, Cm, G, 3)
         cd = ctypes_int_ptr(pk.iaddr(cdim))
         evals, _ = self.eig_any(G, n_pad, cd, 0, len(vs), 'rk', vecs=False)
         k = self.ws('rk_k', (len(vs),), I32)
         ctx.call('cpsd_select_k', ptr(evals), n_pad, cd, 0, float(self.pca_var), 1, 0, 1 << 30,
                  ptr(k), 1, len(vs))
-        return k.cpu().numpy().astype(np.int32)
+        self._keep_rk = pk
+        return k.clone()
 
     def _target_trial_grams(self):
         """Uncentred per-trial scatter matrices X_t^T X_t of the target (fp64) and their sum:
@@ -522,8 +540,6 @@ class CVEngine:
         """Independent execution lanes: shallow copies of the engine that share the resident
         patient data and fold-invariant tables but own their stream, workspaces, index packs and
         view-statistics cache, so consecutive batches can be in flight at the same time."""
-        if getattr(self, 'stream', None) is None:
-            self.stream = _lane_stream(self.ctx.device, 0)
         extra = getattr(self, '_extra_lanes', None)
         if extra is None:
             extra = self._extra_lanes = []
@@ -538,7 +554,7 @@ class CVEngine:
             ln._pack_i = 0
             if getattr(self, '_tcp', None) is not None:
                 ln._tcp = dict(self._tcp, cap=0)      # shares the X split + maps, own L^T buffers
-            ln.stream = _lane_stream(self.ctx.device, 1 + len(extra))
+            ln.stream = _lane_stream(self.ctx.device, self.lane + 1 + len(extra))
             extra.append(ln)
         lanes = [self] + extra
         return lanes[:n]
@@ -552,20 +568,26 @@ class CVEngine:
         size = -(-len(folds) // nb)          # balanced batches (a short tail batch costs as much
         batches = [folds[s:s + size] for s in range(0, len(folds), size)]   # as a full one)
         results = [None] * len(batches)
+        self._ensure_ready()
         if self.method == 'mcca':
             # every batch is a generator that yields right before each blocking read-back; the
             # lanes are advanced round-robin, so while one lane waits for its GPU results the
             # host packs and queues the other lane's batch on its own stream
-            if self._tc_proj_ready(int(self.n_comp)):
-                pass                                   # split X / encode maps before the lanes fork
+            with torch.cuda.stream(self.stream):
+                self._tc_proj_ready(int(self.n_comp))  # split X / encode maps before the lanes fork
             nl = 1 if (self.profile or len(batches) == 1) else min(self.n_lanes, len(batches))
             lanes = self._lanes(nl)
+            ready = torch.cuda.Event()
+            ready.record(self.stream)
+            for ln in lanes[1:]:
+                ln.stream.wait_event(ready)            # fold-invariant tables live on lane 0's stream
             todo = [list(range(li, len(batches), nl)) for li in range(nl)]
             gens = [None] * nl
             cur = [None] * nl
-            torch.cuda.current_stream(self.ctx.device).synchronize()
+            wait = [None] * nl          # event recorded when the lane last yielded
             live = sum(len(t) for t in todo)
             while live:
+                progressed = False
                 for li, ln in enumerate(lanes):
                     if gens[li] is None:
                         if not todo[li]:
@@ -573,20 +595,60 @@ class CVEngine:
                         cur[li] = todo[li].pop(0)
                         with torch.cuda.stream(ln.stream):
                             gens[li] = ln._mcca_start(batches[cur[li]], return_details)
+                        wait[li] = None
+                        progressed = True
                         continue
+                    # resume a lane only when the work it queued before yielding has finished:
+                    # its read-back then returns at once and the host never sits in one lane's
+                    # wait while another lane has nothing queued
+                    if wait[li] is not None and nl > 1 and not wait[li].query():
+                        continue
+                    progressed = True
                     with torch.cuda.stream(ln.stream):
                         try:
                             next(gens[li])
+                            wait[li] = torch.cuda.Event()
+                            wait[li].record(ln.stream)
                         except StopIteration as e:
                             results[cur[li]] = e.value
                             gens[li] = None
                             live -= 1
+                if not progressed:
+                    time.sleep(0)
             for ln in lanes:
                 ln.stream.synchronize()
         else:
-            for i, batch in enumerate(batches):
-                results[i] = self._batch_cca(batch, return_details)
+            with torch.cuda.stream(self.stream):
+                for i, batch in enumerate(batches):
+                    results[i] = self._batch_cca(batch, return_details)
         for res in results:
+            out['y_pred'] += res['y_pred']
+            out['k2'] += res['k2']
+            out['h2d_bytes'] += res['h2d_bytes']
+            out['d2h_bytes'] += res['d2h_bytes']
+            if return_details:
+                details.append(res['details'])
+        if return_details:
+            out['details'] = details
+        return out
+
+    def run_gen(self, folds, return_details=False):
+        """Generator form of run() on this engine's own stream only (no extra lanes): yields
+        before every blocking read-back, returns the result dict.  The caller advances it with
+        this engine's stream current (cv_align_decode_stream keeps several jobs in flight)."""
+        out = {'y_pred': [], 'k2': [], 'h2d_bytes': 0, 'd2h_bytes': 0}
+        details = []
+        nb = max(1, -(-len(folds) // self.max_batch))
+        size = -(-len(folds) // nb)
+        if self.method == 'mcca' and self.cross_rank is None:
+            yield 'sync'                     # constructor work still in flight
+        self._ensure_ready()
+        for s0 in range(0, len(folds), size):
+            batch = folds[s0:s0 + size]
+            if self.method == 'mcca':
+                res = yield from self._mcca_start(batch, return_details)
+            else:
+                res = self._batch_cca(batch, return_details)
             out['y_pred'] += res['y_pred']
             out['k2'] += res['k2']
             out['h2d_bytes'] += res['h2d_bytes']
@@ -608,7 +670,9 @@ class CVEngine:
         return g
 
     def _batch_mcca(self, batch, want_details, align_only=False):
-        return _drain(self._mcca_start(batch, want_details, align_only))
+        self._ensure_ready()
+        with torch.cuda.stream(self.stream):
+            return _drain(self._mcca_start(batch, want_details, align_only))
 
     def align_mcca(self, train_idx=None):
         """MCCA fit only (AlignMCCA.fit): loadings, view means and generalised eigenvalues for
