@@ -80,6 +80,8 @@ _SIGS = {
                           c_int, _P, _P, _P, c_int, c_float, _P],
     'cpsd_sgemm_batched': [c_int, c_int, c_int, c_int, c_float, _P, c_int, c_ll, _P, c_int, c_ll,
                            _P, c_int, c_ll, c_int, _P],
+    'cpsd_chol_solve_f64': [_P, c_int, c_ll, c_int, _P, c_int, c_ll, c_int, _P, c_int, c_ll, _P, c_int,
+                            _P],
     'cpsd_chol_inv': [_P, c_int, c_ll, c_int, _P, c_int, c_ll, _P, c_int, _P],
     'cpsd_gram_tn': [_P, c_int, c_int, c_int, _P],
     'cpsd_gram_tn_f64': [_P, c_int, c_int, c_int, _P],

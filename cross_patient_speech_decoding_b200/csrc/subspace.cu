@@ -258,6 +258,72 @@ k_chol_inv(const float* __restrict__ S, int lds, long long strideS, int m,
 }
 
 // ---------------------------------------------------------------------------------------
+// SPD solve  S W = B  (S m x m fp64, B m x q fp64, both row-major) by Cholesky in shared
+// memory: W = S^{-1} B written as fp32 (ldw).  Least-squares read-in matrices of JointPCA
+// (alignment/JointPCA.py:203-206: pinv(X_p) @ latent = (X_p^T X_p)^{-1} X_p^T latent for a
+// full-column-rank X_p).  B is used as workspace.  status |= 1 on a non-positive pivot.
+__global__ void __launch_bounds__(CH_NT)
+k_chol_solve_f64(const double* __restrict__ S, int lds, long long strideS, int m,
+                 double* __restrict__ B, int ldb, long long strideB, int q,
+                 float* __restrict__ W, int ldw, long long strideW, int* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* P = reinterpret_cast<double*>(smem_raw);          // m x CH_LD, lower factor
+  __shared__ double s_piv;
+  __shared__ int s_bad;
+  const int prob = blockIdx.x;
+  const double* Sg = S + (long long)prob * strideS;
+  double* Bg = B + (long long)prob * strideB;
+  float* Wg = W + (long long)prob * strideW;
+  const int tid = threadIdx.x;
+  const int tx = tid & 31, ty = tid >> 5;
+  if (tid == 0) s_bad = 0;
+  for (int e = tid; e < m * m; e += CH_NT) {
+    const int r = e / m, c = e - r * m;
+    P[r * CH_LD + c] = (c <= r) ? 0.5 * (Sg[(long long)r * lds + c] + Sg[(long long)c * lds + r]) : 0.0;
+  }
+  __syncthreads();
+  double dmax = 0.0;
+  for (int i = 0; i < m; ++i) dmax = fmax(dmax, P[i * CH_LD + i]);
+  const double floor_piv = dmax * 1e-14 + 1e-290;
+  for (int j = 0; j < m; ++j) {
+    if (tid == 0) {
+      double d = P[j * CH_LD + j];
+      if (!(d > floor_piv)) {
+        s_bad = 1;
+        d = floor_piv;
+      }
+      s_piv = sqrt(d);
+    }
+    __syncthreads();
+    const double ljj = s_piv;
+    const double inv = 1.0 / ljj;
+    for (int i = j + tid; i < m; i += CH_NT) P[i * CH_LD + j] = (i == j) ? ljj : P[i * CH_LD + j] * inv;
+    __syncthreads();
+    for (int i = j + 1 + ty; i < m; i += 32) {
+      const double lij = P[i * CH_LD + j];
+      for (int k = j + 1 + tx; k <= i; k += 32) P[i * CH_LD + k] -= lij * P[k * CH_LD + j];
+    }
+    __syncthreads();
+  }
+  // one thread per right-hand side: forward then back substitution, in place in B
+  for (int c = tid; c < q; c += CH_NT) {
+    for (int i = 0; i < m; ++i) {
+      double acc = Bg[(long long)i * ldb + c];
+      for (int k = 0; k < i; ++k) acc -= P[i * CH_LD + k] * Bg[(long long)k * ldb + c];
+      Bg[(long long)i * ldb + c] = acc / P[i * CH_LD + i];
+    }
+    for (int i = m - 1; i >= 0; --i) {
+      double acc = Bg[(long long)i * ldb + c];
+      for (int k = i + 1; k < m; ++k) acc -= P[k * CH_LD + i] * Bg[(long long)k * ldb + c];
+      acc /= P[i * CH_LD + i];
+      Bg[(long long)i * ldb + c] = acc;
+      Wg[(long long)i * ldw + c] = (float)acc;
+    }
+  }
+  if (tid == 0 && s_bad && status) atomicOr(&status[prob], 1);
+}
+
+// ---------------------------------------------------------------------------------------
 __device__ __forceinline__ float hash_uniform(unsigned int x) {
   x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
   return (float)(x >> 8) * (1.0f / 8388608.0f) - 1.0f;    // [-1, 1)
@@ -382,6 +448,20 @@ extern "C" int cpsd_chol_inv(const float* S, int lds, long long strideS, int m, 
   const size_t smem = 128 * CH_LD * sizeof(double);
   CPSD_CUDA(cudaFuncSetAttribute(k_chol_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_chol_inv<<<nprob, CH_NT, smem, stream>>>(S, lds, strideS, m, Rinv, ldr, strideR, status);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
+
+extern "C" int cpsd_chol_solve_f64(const double* S, int lds, long long strideS, int m, double* B,
+                                   int ldb, long long strideB, int q, float* W, int ldw,
+                                   long long strideW, int* status, int nprob, cudaStream_t stream) {
+  CPSD_CHECK_ARG(m > 0 && m <= 128 && q > 0, "chol_solve_f64: m must be in 1..128");
+  if (nprob == 0) return CPSD_OK;
+  const size_t smem = 128 * CH_LD * sizeof(double);
+  CPSD_CUDA(cudaFuncSetAttribute(k_chol_solve_f64, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+  k_chol_solve_f64<<<nprob, CH_NT, smem, stream>>>(S, lds, strideS, m, B, ldb, strideB, q, W, ldw,
+                                                   strideW, status);
   CPSD_LAUNCH_CHECK();
   return CPSD_OK;
 }

@@ -105,6 +105,37 @@ def chol_inv(S, device=None):
     return Rinv.cpu().numpy(), st.cpu().numpy()
 
 
+def lstsq_gram(X, Y, device=None):
+    """Least-squares solution W = argmin |X W - Y| for a full-column-rank X (rows x C, C <= 128)
+    through the normal equations in fp64: X^T X and X^T Y are accumulated in fp64 on the GPU and
+    solved by a shared-memory Cholesky.  Returns (W (C, q) float64, status)."""
+    ctx = _ctx(device)
+    X = np.ascontiguousarray(X, dtype=np.float32)
+    Y = np.ascontiguousarray(Y, dtype=np.float32)
+    rows, C = X.shape
+    q = Y.shape[1]
+    assert Y.shape[0] == rows and C <= 128
+    Xd, Yd = ctx.upload(X), ctx.upload(Y)
+    pk = HostPack(ctx)
+    o = pk.add_ints([0])
+    pk.reserve_ints()
+    S = ctx.zeros((C, C), F64)
+    Bm = ctx.zeros((C, q), F64)
+    recs = np.zeros(2, dtype=_lib.GRAM_TN_DESC)
+    recs[0] = (addr(Xd), addr(Xd), pk.iaddr(o), pk.iaddr(o), 0, 0, addr(S), 1, rows, C, C, C, C, C,
+               1, 1.0, 0)
+    recs[1] = (addr(Xd), addr(Yd), pk.iaddr(o), pk.iaddr(o), 0, 0, addr(Bm), 1, rows, C, q, C, q, q,
+               0, 1.0, 0)
+    d = pk.add_descs(recs)
+    pk.upload()
+    ctx.call('cpsd_gram_tn_f64', pk.daddr(d), 2, C, max(C, q))
+    W = ctx.zeros((C, q))
+    st = ctx.zeros((1,), I32)
+    ctx.call('cpsd_chol_solve_f64', ptr(S), C, C * C, C, ptr(Bm), q, C * q, q, ptr(W), q, C * q,
+             ptr(st), 1)
+    return W.cpu().numpy().astype(np.float64), int(st.cpu().numpy()[0])
+
+
 def eig_topk(A, m=128, iters=8, rounds=1, n=None, max_sweeps=15, tol=3e-7, device=None):
     """Leading m eigen-pairs of symmetric PSD matrices A (nprob, n, n) by subspace iteration.
     Returns dict(evals (nprob, m), V (nprob, n, m), total, resid (nprob, m), status)."""

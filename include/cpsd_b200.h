@@ -176,6 +176,12 @@ int cpsd_sgemm_batched(int trans_a, int M, int N, int K, float alpha, const floa
                        int ldc, long long strideC, int nprob, cudaStream_t stream);
 int cpsd_chol_inv(const float* S, int lds, long long strideS, int m, float* Rinv, int ldr,
                   long long strideR, int* status, int nprob, cudaStream_t stream);
+/* SPD solve S W = B (fp64 Cholesky in shared memory, m <= 128; B is used as workspace): the
+ * least-squares read-in matrices pinv(X_p) @ latent of get_joint_PCA_transforms
+ * (alignment/JointPCA.py:203-206) from X_p^T X_p and X_p^T latent */
+int cpsd_chol_solve_f64(const double* S, int lds, long long strideS, int m, double* B, int ldb,
+                        long long strideB, int q, float* W, int ldw, long long strideW,
+                        int* status, int nprob, cudaStream_t stream);
 /* PCA components with sklearn's svd_flip sign convention, zero padded to dmax columns */
 int cpsd_pca_basis(const float* evecs, int ldv, long long strideV, const int* k_dev,
                    const int* cdim, int c_fixed, int dmax, float* W, int ldw, int Cmax, int nprob,

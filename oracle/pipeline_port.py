@@ -90,6 +90,20 @@ def cca_fit(Xa, Xb, ya, yb):
     return cca_directions(La.reshape(-1, La.shape[-1]), Lb.reshape(-1, Lb.shape[-1]))
 
 
+# ----------------------------------------------------------------------- JointPCA.py
+def joint_pca_fit(Xs, labs, n_components):
+    """JointPCA.py:165-211 (get_joint_PCA_transforms): PCA of the channel-concatenated class
+    averages, then per patient W_p = pinv(X_p) @ latent."""
+    views = [a.reshape(-1, a.shape[-1]) for a in shared_condition_averages(Xs, labs)]
+    latent = PCA(n_components=n_components, svd_solver='full').fit_transform(np.hstack(views))
+    return [np.linalg.pinv(v) @ latent for v in views]
+
+
+def joint_pca_transform(W, X):
+    """JointPCA.py:132,149 -- no centring."""
+    return (X.reshape(-1, X.shape[-1]) @ W).reshape(X.shape[:-1] + (-1,))
+
+
 # -------------------------------------------------------------- cross_pt_decoders.py
 def pool_mcca(Xtr, ytr, yal, cross, n_comp, regs, pca_var):
     """crossPtDecoder_mcca.preprocess_train (cross_pt_decoders.py:395-433)."""

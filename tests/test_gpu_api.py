@@ -46,7 +46,11 @@ def test_pca_matches_sklearn_tall_and_wide(pkg):
     rng = np.random.default_rng(0)
     tall = rng.standard_normal((3000, 40)) @ np.diag(np.linspace(3, 0.2, 40)) + 1.5
     wide = rng.standard_normal((150, 900)) * np.linspace(4, 0.5, 900) - 0.5
-    for X, nc in [(tall, 0.9), (tall, 7), (wide, 0.8), (wide, 12), (tall, None)]:
+    # > 256 on the eigen side: the top-k subspace solver path of the PCA class
+    wide2 = rng.standard_normal((400, 900)) * (1.0 / (1.0 + np.arange(900) / 15.0)) + 0.3
+    tall2 = rng.standard_normal((1500, 300)) * (1.0 / (1.0 + np.arange(300) / 10.0)) - 1.0
+    for X, nc in [(tall, 0.9), (tall, 7), (wide, 0.8), (wide, 12), (tall, None), (wide2, 0.8),
+                  (wide2, 12), (tall2, 10), (tall2, 0.9)]:
         # svd_solver='full': sklearn's 'auto' picks the randomized solver for the wide int case
         ours, ref = PCA(n_components=nc).fit(X), SkPCA(n_components=nc, svd_solver='full').fit(X)
         assert ours.n_components_ == ref.n_components_
@@ -183,3 +187,47 @@ def test_cv_align_decode_public_api(pkg):
     yr = np.concatenate([g['y_pred_%d' % f] for f in range(len(folds))])
     assert np.mean(yp == yr) >= 0.99
     assert out['h2d_bytes'] > 0 and out['d2h_bytes'] > 0
+
+
+def test_joint_pca_matches_reference_golden(pkg):
+    """alignment.JointPCA.JointPCA (GPU) against the reference class's stored output: read-in
+    matrices, transformed trials, API errors; and crossPtDecoder_jointDimRed end to end."""
+    import make_golden
+    from cross_patient_speech_decoding_b200.alignment.JointPCA import JointPCA
+    from cross_patient_speech_decoding_b200.decoders.cross_pt_decoders import crossPtDecoder_jointDimRed
+    from cross_patient_speech_decoding_b200.decomposition.DimRedReshape import DimRedReshape
+    from cross_patient_speech_decoding_b200.decomposition.PCA import PCA
+    from cross_patient_speech_decoding_b200.svm import LinearSVC
+    from sklearn.pipeline import make_pipeline
+    g = np.load(os.path.join(HERE, 'golden', 'jointpca_p3_ragged.npz'))
+    pts, folds = make_golden.build_inputs(make_golden.CONFIGS['mcca_p3_ragged'])
+    Xs, yal = [p[0] for p in pts], [p[2] for p in pts]
+    nc = int(g['n_comp'])
+    jp = JointPCA(n_components=nc)
+    with pytest.raises(RuntimeError):
+        jp.transform(Xs)
+    Z = jp.fit_transform(Xs, yal)
+    assert isinstance(Z, tuple) and len(Z) == 3 and len(jp.transforms) == 3
+    for v in range(3):
+        Wref, Zref = g['W_full_%d' % v], g['Z_full_%d' % v]
+        assert jp.transforms[v].shape == Wref.shape
+        # the transformed data is what downstream stages consume: compare it tightly, and the
+        # read-in matrices through the subspace they span
+        assert np.abs(Z[v][:4] - Zref).max() <= 2e-4 * np.abs(Zref).max()
+        assert np.abs(jp.transforms[v] - Wref).max() <= 5e-3 * np.abs(Wref).max()
+    zs = jp.transform(Xs[1][:3], idx=1)
+    assert np.abs(zs - g['Zsingle_full']).max() <= 2e-4 * np.abs(g['Zsingle_full']).max()
+    with pytest.raises(IndexError):
+        jp.transform(Xs[0], idx=3)
+    # decoder
+    Xt, yt, yat = pts[0]
+    agree = tot = 0
+    for f, (tr, te) in enumerate(folds):
+        clf = make_pipeline(DimRedReshape(PCA, n_components=0.8), LinearSVC())
+        model = crossPtDecoder_jointDimRed(pts[1:], clf, JointPCA, n_comp=nc)
+        model.fit(Xt[tr], yt[tr], y_align=yat[tr])
+        yp = model.predict(Xt[te])
+        assert clf.named_steps['dimredreshape'].transformer.n_components_ == int(g['k2_%d' % f])
+        agree += int((yp == g['y_pred_%d' % f]).sum())
+        tot += len(te)
+    assert agree / tot >= 0.99

@@ -142,3 +142,22 @@ def test_reference_classes_match_port_live():
     am.fit([Xa, Xb], [ya, yb])
     pm = pipeline_port.mcca_fit([Xa, Xb], [ya, yb], 6, 0.5, 0.8)
     assert np.abs(am.mcca.evals_ - pm.evals_).max() < 1e-10
+
+
+def test_joint_pca_port_matches_reference_golden():
+    """oracle/pipeline_port.joint_pca_* against the output of the reference's own JointPCA
+    (tests/golden/jointpca_p3_ragged.npz, made by make_golden_jointpca.py)."""
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, 'golden'))
+    import make_golden
+    from oracle import pipeline_port as port
+    g = np.load(os.path.join(here, 'golden', 'jointpca_p3_ragged.npz'))
+    pts, _ = make_golden.build_inputs(make_golden.CONFIGS['mcca_p3_ragged'])
+    W = port.joint_pca_fit([p[0] for p in pts], [p[2] for p in pts], int(g['n_comp']))
+    for v, p in enumerate(pts):
+        Wref = g['W_full_%d' % v]
+        assert np.abs(W[v] - Wref).max() <= 1e-8 * np.abs(Wref).max()
+        Z = port.joint_pca_transform(W[v], p[0][:4])
+        assert np.abs(Z - g['Z_full_%d' % v]).max() <= 1e-8 * np.abs(g['Z_full_%d' % v]).max()
