@@ -134,6 +134,7 @@ def cpu_sample(pts, n_folds_sample, step_id=0):
     """Times the CPU port of the reference path (oracle/pipeline_port.py) on a bounded sample
     of the same workload.  Returns (folds/s, seconds, accuracy)."""
     from oracle import pipeline_port
+    use_all_host_threads()
     folds = step_folds(pts[0][1], step_id)[:n_folds_sample]
     t0 = time.perf_counter()
     ok = tot = 0
@@ -144,6 +145,17 @@ def cpu_sample(pts, n_folds_sample, step_id=0):
         tot += len(te)
     dt = time.perf_counter() - t0
     return len(folds) / dt, dt, ok / max(tot, 1)
+
+
+def use_all_host_threads():
+    """The CPU arm uses every host core (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    n = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=n)
+    except Exception:
+        pass
+    return n
 
 
 def blas_threads():
