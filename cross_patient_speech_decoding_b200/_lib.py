@@ -78,6 +78,13 @@ _SIGS = {
     'cpsd_eig_topk_voff': [c_int, c_int, c_int],
     'cpsd_eig_sym_topk': [_P, c_int, c_ll, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P,
                           c_int, _P, _P, _P, c_int, c_float, _P],
+    'cpsd_topk_tc_ws_elems': [c_int, c_int],
+    'cpsd_topk_tc_map_bytes': [c_int],
+    'cpsd_topk_tc_encode': [_P, c_int, c_ll, c_int, c_int, _P, _P, _P, _P],
+    'cpsd_topk_tc_split_k': [_P, c_int, c_ll, c_int, c_int, _P, _P],
+    'cpsd_topk_tc_kq': [_P, c_ll, _P, c_ll, c_int, c_int, c_int, _P, _P, _P],
+    'cpsd_eig_sym_topk_tc': [_P, c_int, c_ll, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P,
+                             c_int, _P, _P, _P, c_int, c_float, _P, _P, c_int, _P],
     'cpsd_sgemm_batched': [c_int, c_int, c_int, c_int, c_float, _P, c_int, c_ll, _P, c_int, c_ll,
                            _P, c_int, c_ll, c_int, _P],
     'cpsd_chol_solve_f64': [_P, c_int, c_ll, c_int, _P, c_int, c_ll, c_int, _P, c_int, c_ll, _P, c_int,
@@ -124,7 +131,7 @@ _SIGS = {
 }
 _RESTYPES = {'cpsd_last_error': ctypes.c_char_p, 'cpsd_launch_count': c_ll,
              'cpsd_bj_rlog_elems': c_ll, 'cpsd_eig_topk_ws_elems': c_ll,
-             'cpsd_eig_topk_voff': c_ll,
+             'cpsd_eig_topk_voff': c_ll, 'cpsd_topk_tc_ws_elems': c_ll,
              'cpsd_reset_launch_count': None}
 
 EXPORTED_SYMBOLS = sorted(_SIGS)

@@ -483,10 +483,17 @@ extern "C" long long cpsd_eig_topk_voff(int n_pad, int m, int nprob) {
   return (long long)nprob * 2LL * n_pad * m;
 }
 
-extern "C" int cpsd_eig_sym_topk(float* K, int ld, long long stride, int n_pad, const int* n_dev,
-                                 int n_fixed, int nprob, int m, int iters, int init, float* ws,
-                                 float* evals, int ld_e, float* total, float* resid, int* status,
-                                 int eig_sweeps, float eig_tol, cudaStream_t stream) {
+extern "C" int cpsd_topk_tc_split_k(const float* K, int ld, long long stride, int n_pad, int nprob,
+                                    float* tc_ws, cudaStream_t stream);
+extern "C" int cpsd_topk_tc_kq(const float* Q, long long strideQ, float* Y, long long strideY, int n_pad,
+                               int nprob, int terms, float* tc_ws, const void* map_dev,
+                               cudaStream_t stream);
+
+static int eig_sym_topk_impl(float* K, int ld, long long stride, int n_pad, const int* n_dev,
+                             int n_fixed, int nprob, int m, int iters, int init, float* ws,
+                             float* evals, int ld_e, float* total, float* resid, int* status,
+                             int eig_sweeps, float eig_tol, float* tc_ws, const void* map_dev,
+                             int tf32_iters, cudaStream_t stream) {
   CPSD_CHECK_ARG(n_pad > 0 && ld >= n_pad, "eig_sym_topk: bad dims");
   CPSD_CHECK_ARG(m > 0 && m <= 128 && (m % 4) == 0 && m <= n_pad, "eig_sym_topk: m must be a multiple of 4 in 4..128");
   CPSD_CHECK_ARG(ld_e >= m && iters >= 0, "eig_sym_topk: bad ld_e / iters");
@@ -504,6 +511,18 @@ extern "C" int cpsd_eig_sym_topk(float* K, int ld, long long stride, int n_pad, 
   k_topk_init<<<dim3(16, nprob), 256, 0, stream>>>(K, ld, stride, n_pad, n_dev, n_fixed, Q, sQY, m,
                                                    total, status, init);
   CPSD_LAUNCH_CHECK();
+  const bool tc = tc_ws != nullptr;
+  if (tc) {
+    CPSD_CHECK_ARG(m == 128 && n_pad % 128 == 0 && ld == n_pad && stride == (long long)n_pad * n_pad,
+                   "eig_sym_topk_tc: needs m = 128 and densely packed K with n_pad % 128 == 0");
+    CPSD_TRY(cpsd_topk_tc_split_k(K, ld, stride, n_pad, nprob, tc_ws, stream));
+  }
+  // Y = K Q: tensor cores (single-pass TF32 while the block is still far from converged -- the
+  // iteration is self-correcting -- then 3xTF32) or the fp32 SIMT GEMM
+  auto kq = [&](int terms) -> int {
+    if (tc) return cpsd_topk_tc_kq(Q, sQY, Y, sQY, n_pad, nprob, terms, tc_ws, map_dev, stream);
+    return launch_sgemm<1>(K, ld, stride, Q, m, sQY, Y, m, sQY, n_pad, m, n_pad, 1.f, nprob, stream);
+  };
   if (!init) {
     // resume from the Ritz vectors (orthonormal up to rounding)
     CPSD_CUDA(cudaMemcpy2DAsync(Q, sQY * sizeof(float), VV, sQY * sizeof(float),
@@ -524,8 +543,7 @@ extern "C" int cpsd_eig_sym_topk(float* K, int ld, long long stride, int n_pad, 
     CPSD_TRY(launch_sgemm<0>(Y, m, sQY, Rinv, m, sMM, Q, m, sQY, n_pad, m, m, 1.f, nprob, stream));
   }
   for (int it = 0; it < iters; ++it) {
-    // Y = K Q  (K symmetric: read as K^T)
-    CPSD_TRY(launch_sgemm<1>(K, ld, stride, Q, m, sQY, Y, m, sQY, n_pad, m, n_pad, 1.f, nprob, stream));
+    CPSD_TRY(kq((init && it < tf32_iters) ? 1 : 3));
     CPSD_TRY(orth(Y));
     CPSD_TRY(launch_sgemm<0>(Y, m, sQY, Rinv, m, sMM, Q, m, sQY, n_pad, m, m, 1.f, nprob, stream));
   }
@@ -535,7 +553,7 @@ extern "C" int cpsd_eig_sym_topk(float* K, int ld, long long stride, int n_pad, 
                               stream));
   CPSD_TRY(orth(Y));
   CPSD_TRY(launch_sgemm<0>(Y, m, sQY, Rinv, m, sMM, Q, m, sQY, n_pad, m, m, 1.f, nprob, stream));
-  CPSD_TRY(launch_sgemm<1>(K, ld, stride, Q, m, sQY, Y, m, sQY, n_pad, m, n_pad, 1.f, nprob, stream));
+  CPSD_TRY(kq(3));
   CPSD_TRY(launch_sgemm<1>(Q, m, sQY, Y, m, sQY, H, m, sMM, m, m, n_pad, 1.f, nprob, stream));
   k_symmetrize<<<nprob, 256, 0, stream>>>(H, m, sMM);
   CPSD_LAUNCH_CHECK();
@@ -546,4 +564,25 @@ extern "C" int cpsd_eig_sym_topk(float* K, int ld, long long stride, int n_pad, 
   k_topk_resid<<<nprob, 256, 0, stream>>>(VV, sQY, n_pad, m, evals, ld_e, resid);
   CPSD_LAUNCH_CHECK();
   return CPSD_OK;
+}
+
+extern "C" int cpsd_eig_sym_topk(float* K, int ld, long long stride, int n_pad, const int* n_dev,
+                                 int n_fixed, int nprob, int m, int iters, int init, float* ws,
+                                 float* evals, int ld_e, float* total, float* resid, int* status,
+                                 int eig_sweeps, float eig_tol, cudaStream_t stream) {
+  return eig_sym_topk_impl(K, ld, stride, n_pad, n_dev, n_fixed, nprob, m, iters, init, ws, evals, ld_e,
+                           total, resid, status, eig_sweeps, eig_tol, nullptr, nullptr, 0, stream);
+}
+
+// Same solver with K Q on the tensor cores (tcgen05, tc_gram.cu): tc_ws = cpsd_topk_tc_ws_elems()
+// floats, map_dev = the tensor maps written by cpsd_topk_tc_encode for this K / tc_ws; the
+// first tf32_iters iterations of a fresh start use single-pass TF32, the rest 3xTF32.
+extern "C" int cpsd_eig_sym_topk_tc(float* K, int ld, long long stride, int n_pad, const int* n_dev,
+                                    int n_fixed, int nprob, int m, int iters, int init, float* ws,
+                                    float* evals, int ld_e, float* total, float* resid, int* status,
+                                    int eig_sweeps, float eig_tol, float* tc_ws, const void* map_dev,
+                                    int tf32_iters, cudaStream_t stream) {
+  CPSD_CHECK_ARG(tc_ws != nullptr && map_dev != nullptr, "eig_sym_topk_tc: tc_ws / map_dev is NULL");
+  return eig_sym_topk_impl(K, ld, stride, n_pad, n_dev, n_fixed, nprob, m, iters, init, ws, evals, ld_e,
+                           total, resid, status, eig_sweeps, eig_tol, tc_ws, map_dev, tf32_iters, stream);
 }

@@ -209,6 +209,209 @@ k_gram_tc(const CUtensorMap* __restrict__ maps, const TcProb* __restrict__ probs
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// General batched NT product on the tensor cores:  C_p (M x 128) = A_p (M x K) B_p^T,
+// B_p (128 x K), both operands K-major (row-major with K contiguous).  One CTA per 128-row
+// tile of A.  terms == 1: single-pass TF32 straight from the fp32 operands (the tensor core
+// drops the low 13 mantissa bits) -- used where the product only has to be directionally
+// right (early subspace iterations, which are self-correcting); terms == 3: 3xTF32 on
+// pre-split hi/lo operands, drained every `chunk` k-blocks into fp32 registers (fp32-class).
+// maps: per problem 5 tensor maps {A, A_hi, A_lo, B_hi (or B itself for terms == 1), B_lo}.
+// ---------------------------------------------------------------------------------------
+constexpr int GT_MAPS = 5;
+constexpr int GT_MAX_STAGES = 6;
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_gemm_tc_nt(const CUtensorMap* __restrict__ maps, float* __restrict__ C, int ldc, long long strideC,
+             int M, int k_total, int terms, int chunk) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int prob = blockIdx.z;
+  const int tm = blockIdx.x;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  const int stage_bytes = (terms == 1 ? 2 : 4) * TILE_BYTES;
+  const int nstages = terms == 1 ? GT_MAX_STAGES : 3;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + GT_MAX_STAGES * 2 * TILE_BYTES);
+  uint64_t* empty = full + GT_MAX_STAGES;
+  uint64_t* tmem_full = empty + GT_MAX_STAGES;     // [ACC_STAGES]
+  uint64_t* tmem_empty = tmem_full + ACC_STAGES;   // [ACC_STAGES]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const CUtensorMap* pm = maps + (long long)prob * GT_MAPS;
+  const int nkb = (k_total + BK - 1) / BK;
+  const int nchunk = (nkb + chunk - 1) / chunk;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < GT_MAX_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < ACC_STAGES; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* st = smem + stage * stage_bytes;
+        mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
+        if (terms == 1) {
+          tma_load_2d(st, pm + 0, kb * BK, tm * BM, &full[stage]);
+          tma_load_2d(st + TILE_BYTES, pm + 3, kb * BK, 0, &full[stage]);
+        } else {
+          tma_load_2d(st, pm + 1, kb * BK, tm * BM, &full[stage]);
+          tma_load_2d(st + TILE_BYTES, pm + 2, kb * BK, tm * BM, &full[stage]);
+          tma_load_2d(st + 2 * TILE_BYTES, pm + 3, kb * BK, 0, &full[stage]);
+          tma_load_2d(st + 3 * TILE_BYTES, pm + 4, kb * BK, 0, &full[stage]);
+        }
+        if (++stage == nstages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = idesc_tf32(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int c = 0; c < nchunk; ++c) {
+        const int as = c & 1;
+        const uint32_t aphase = (uint32_t)(c >> 1) & 1u;
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
+        const int kb_end = min(nkb, (c + 1) * chunk);
+        for (int kb = c * chunk; kb < kb_end; ++kb) {
+          mbar_wait(&full[stage], phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+          if (terms == 1) {
+            const uint64_t a = make_smem_desc(sa), b = make_smem_desc(sa + TILE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k) {
+              const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
+              umma_tf32(tacc, a + adv, b + adv, idesc, (kb != c * chunk || k != 0) ? 1u : 0u);
+            }
+          } else {
+            const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + TILE_BYTES);
+            const uint64_t b_hi = make_smem_desc(sa + 2 * TILE_BYTES);
+            const uint64_t b_lo = make_smem_desc(sa + 3 * TILE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k) {
+              const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
+              umma_tf32(tacc, a_lo + adv, b_hi + adv, idesc, (kb != c * chunk || k != 0) ? 1u : 0u);
+              umma_tf32(tacc, a_hi + adv, b_lo + adv, idesc, 1u);
+              umma_tf32(tacc, a_hi + adv, b_hi + adv, idesc, 1u);
+            }
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[as]);
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int row = tm * BM + quad * 32 + lane;
+    float acc[BN];
+#pragma unroll
+    for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+    for (int c = 0; c < nchunk; ++c) {
+      const int as = c & 1;
+      const uint32_t aphase = (uint32_t)(c >> 1) & 1u;
+      mbar_wait(&tmem_full[as], aphase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + c0), v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(v[j]);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+    }
+    if (row < M) {
+      float4* dst = reinterpret_cast<float4*>(C + (long long)prob * strideC + (long long)row * ldc);
+#pragma unroll
+      for (int j = 0; j < BN; j += 4) dst[j >> 2] = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// src (rows x cols, ld_src) -> dst_hi / dst_lo (cols x rows, ld_dst): transpose + tf32 split
+// (lo may be NULL: plain transpose).  grid (ceil(cols/32), ceil(rows/32), nprob), 32 x 8 threads
+__global__ void __launch_bounds__(256)
+k_transpose_split(const float* __restrict__ src, int ld_src, long long stride_src,
+                  float* __restrict__ hi, float* __restrict__ lo, int ld_dst, long long stride_dst,
+                  int rows, int cols) {
+  __shared__ float tile[32][33];
+  const float* s = src + (long long)blockIdx.z * stride_src;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < rows && c < cols) ? s[(long long)r * ld_src + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;       // output row = source column
+    if (c < cols && r < rows) {
+      const float x = tile[tx][i];
+      const long long o = (long long)blockIdx.z * stride_dst + (long long)c * ld_dst + r;
+      if (lo) {
+        float h, l;
+        split_tf32(x, h, l);
+        hi[o] = h;
+        lo[o] = l;
+      } else {
+        hi[o] = x;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_split_flat2(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo,
+              long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x * 4;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    const float4 x = *reinterpret_cast<const float4*>(src + i);
+    float4 h, l;
+    split_tf32(x.x, h.x, l.x);
+    split_tf32(x.y, h.y, l.y);
+    split_tf32(x.z, h.z, l.z);
+    split_tf32(x.w, h.w, l.w);
+    *reinterpret_cast<float4*>(hi + i) = h;
+    *reinterpret_cast<float4*>(lo + i) = l;
+  }
+}
+
 // all problems in one launch: grid (column chunks, row phases, problem); optional centring
 // (x - mu[col]) fused into the split, so the centred matrix is never written in fp32
 __global__ void __launch_bounds__(256)
@@ -353,6 +556,92 @@ extern "C" int cpsd_gram_nt_tc_centered(const cpsd_gram_nt_desc* descs_host, int
                  "gram_nt_tc_centered: mu must be 16-byte aligned with ldmu % 4 == 0");
   return gram_nt_tc_impl(descs_host, nprob, m_max, n_max, split_ws, split_ws_elems, map_ws, stage_host,
                          mu, ldmu, stream);
+}
+
+// ---- tensor-core K Q of the top-k subspace iteration (subspace.cu) -------------------------
+// Layout of tc_ws (floats): K_hi, K_lo (nprob * n_pad^2 each), Qt_hi, Qt_lo (nprob * 128 * n_pad
+// each).  maps: nprob * 5 tensor maps (device, 64-byte aligned), encoded on the host into
+// stage_host (pinned, same size) by cpsd_topk_tc_encode whenever K / tc_ws move.
+extern "C" long long cpsd_topk_tc_ws_elems(int n_pad, int nprob) {
+  return (long long)nprob * (2LL * n_pad * n_pad + 2LL * 128 * n_pad);
+}
+extern "C" int cpsd_topk_tc_map_bytes(int nprob) { return nprob * GT_MAPS * (int)sizeof(CUtensorMap) + 64; }
+
+extern "C" int cpsd_topk_tc_encode(const float* K, int ld, long long stride, int n_pad, int nprob,
+                                   float* tc_ws, void* map_dev, void* stage_host, cudaStream_t stream) {
+  CPSD_CHECK_ARG(n_pad > 0 && n_pad % 128 == 0 && ld % 4 == 0, "topk_tc_encode: bad dims");
+  EncodeFn enc = get_encode();
+  if (!enc) {
+    cpsd_set_error("topk_tc_encode: cuTensorMapEncodeTiled entry point unavailable");
+    return CPSD_ERR_CUDA;
+  }
+  CUtensorMap* mh = reinterpret_cast<CUtensorMap*>(stage_host);
+  const long long nn = (long long)n_pad * n_pad, qn = 128LL * n_pad;
+  float* Khi = tc_ws;
+  float* Klo = Khi + (long long)nprob * nn;
+  float* Qhi = Klo + (long long)nprob * nn;
+  float* Qlo = Qhi + (long long)nprob * qn;
+  const cuuint32_t box[2] = {BK, BM};
+  const cuuint32_t estr[2] = {1, 1};
+  for (int p = 0; p < nprob; ++p) {
+    float* bases[GT_MAPS] = {const_cast<float*>(K) + (long long)p * stride, Khi + p * nn, Klo + p * nn,
+                             Qhi + p * qn, Qlo + p * qn};
+    const cuuint64_t rows[GT_MAPS] = {(cuuint64_t)n_pad, (cuuint64_t)n_pad, (cuuint64_t)n_pad, 128, 128};
+    const cuuint64_t lds[GT_MAPS] = {(cuuint64_t)ld, (cuuint64_t)n_pad, (cuuint64_t)n_pad,
+                                     (cuuint64_t)n_pad, (cuuint64_t)n_pad};
+    for (int u = 0; u < GT_MAPS; ++u) {
+      const cuuint64_t gdim[2] = {(cuuint64_t)n_pad, rows[u]};
+      const cuuint64_t gstr[1] = {lds[u] * 4};
+      CUresult r = enc(&mh[p * GT_MAPS + u], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, bases[u], gdim, gstr,
+                       box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        cpsd_set_error("topk_tc_encode: cuTensorMapEncodeTiled failed");
+        return CPSD_ERR_CUDA;
+      }
+    }
+  }
+  CPSD_CUDA(cudaMemcpyAsync(map_dev, stage_host, (size_t)nprob * GT_MAPS * sizeof(CUtensorMap),
+                            cudaMemcpyHostToDevice, stream));
+  return CPSD_OK;
+}
+
+// K -> K_hi / K_lo (once per eigen-solve, after the padding has been zeroed)
+extern "C" int cpsd_topk_tc_split_k(const float* K, int ld, long long stride, int n_pad, int nprob,
+                                    float* tc_ws, cudaStream_t stream) {
+  CPSD_CHECK_ARG(ld == n_pad && stride == (long long)n_pad * n_pad,
+                 "topk_tc_split_k: K must be densely packed (ld = n_pad)");
+  const long long n = (long long)nprob * n_pad * n_pad;
+  float* Khi = tc_ws;
+  float* Klo = Khi + n;
+  long long nb = (n / 4 + 255) / 256;
+  if (nb > 148 * 16) nb = 148 * 16;
+  k_split_flat2<<<(int)nb, 256, 0, stream>>>(K, Khi, Klo, n);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
+
+// Y (n_pad x 128 per problem, row stride 128, problem stride strideY) = K Q with Q given as
+// (n_pad x 128, row stride 128, problem stride strideQ): transposes (and for terms == 3 splits)
+// Q into the workspace, then runs the tensor-core product.
+extern "C" int cpsd_topk_tc_kq(const float* Q, long long strideQ, float* Y, long long strideY, int n_pad,
+                               int nprob, int terms, float* tc_ws, const void* map_dev,
+                               cudaStream_t stream) {
+  CPSD_CHECK_ARG(terms == 1 || terms == 3, "topk_tc_kq: terms must be 1 or 3");
+  CPSD_CHECK_ARG(n_pad > 0 && n_pad % 128 == 0 && nprob > 0 && nprob <= 65535, "topk_tc_kq: bad dims");
+  const long long nn = (long long)n_pad * n_pad, qn = 128LL * n_pad;
+  float* Qhi = tc_ws + 2LL * nprob * nn;
+  float* Qlo = Qhi + (long long)nprob * qn;
+  k_transpose_split<<<dim3(4, n_pad / 32, nprob), 256, 0, stream>>>(
+      Q, 128, strideQ, Qhi, terms == 3 ? Qlo : nullptr, n_pad, qn, n_pad, 128);
+  CPSD_LAUNCH_CHECK();
+  const size_t smem = (size_t)GT_MAX_STAGES * 2 * TILE_BYTES + 1024 + 256;
+  CPSD_CUDA(cudaFuncSetAttribute(k_gemm_tc_nt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_gemm_tc_nt<<<dim3(n_pad / BM, 1, nprob), TC_THREADS, smem, stream>>>(
+      reinterpret_cast<const CUtensorMap*>(map_dev), Y, 128, strideY, n_pad, n_pad, terms,
+      terms == 1 ? (n_pad / BK) : CHUNK);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
 }
 
 // bytes of map_ws / stage_host needed for nprob problems

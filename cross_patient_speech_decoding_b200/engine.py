@@ -76,7 +76,8 @@ class CVEngine:
                  decoder_var=0.8, C=1.0, tar_in_train=True, device=None, max_batch=32,
                  dcd_epochs=0, max_newton=60, tol_newton=1e-9, tol_dcd=1e-4,
                  eig_sweeps=12, eig_tol=3e-7, use_tensor_cores=False, pool_solver='auto',
-                 topk_block=128, topk_iters=8, topk_tol=2e-5, topk_rounds=3, n_lanes=2, lane=0):
+                 topk_block=128, topk_iters=8, topk_tol=2e-5, topk_rounds=3, n_lanes=2, lane=0,
+                 topk_tf32_iters=5):
         self.ctx = Context.get(device)
         self.lane = int(lane)
         self.stream = _lane_stream(self.ctx.device, self.lane)
@@ -85,6 +86,7 @@ class CVEngine:
                        max_batch, dcd_epochs, max_newton, tol_newton, tol_dcd, eig_sweeps, eig_tol,
                        use_tensor_cores, pool_solver, topk_block, topk_iters, topk_tol, topk_rounds,
                        n_lanes)
+            self.topk_tf32_iters = int(topk_tf32_iters)
 
     def _init(self, target, cross, method, n_comp, regs, pca_var, decoder_var, C, tar_in_train,
               max_batch, dcd_epochs, max_newton, tol_newton, tol_dcd, eig_sweeps, eig_tol,
@@ -251,11 +253,31 @@ class CVEngine:
         V = ws[voff:voff + nprob * 2 * n_pad * m]
         info = {'rounds': 0, 'ok': False}
         self.stats['topk'] = info
+        tc = self.use_tc and m == 128 and n_pad % 128 == 0
+        if tc:
+            # K Q on the tensor cores: hi/lo workspace + tensor maps (re-encoded only when the
+            # Gram or the workspace moved)
+            tcw = self.ws(tag + '_tkc', (int(ctx.lib.cpsd_topk_tc_ws_elems(n_pad, nprob)),))
+            nb = int(ctx.lib.cpsd_topk_tc_map_bytes(nprob))
+            maps = self.ws(tag + '_tkm', (nb + 64,), torch.uint8)
+            mp = (maps.data_ptr() + 63) & ~63
+            key = (K.data_ptr(), tcw.data_ptr(), mp, n_pad, nprob)
+            if getattr(self, '_tkc_key', None) != key:
+                self._tkc_stage = torch.empty((nb + 64,), dtype=torch.uint8).pin_memory()
+                ctx.call('cpsd_topk_tc_encode', ptr(K), n_pad, n_pad * n_pad, n_pad, nprob, ptr(tcw),
+                         ctypes.c_void_p(mp), ctypes.c_void_p(self._tkc_stage.data_ptr()))
+                self._tkc_key = key
         for rnd in range(self.topk_rounds):
-            ctx.call('cpsd_eig_sym_topk', ptr(K), n_pad, n_pad * n_pad, n_pad, _p(n_dev), 0, nprob,
-                     m, self.topk_iters, 1 if rnd == 0 else 0, ptr(ws), ptr(evals),
-                     evals.shape[-1], ptr(tot), ptr(resid), ptr(status), self.eig_sweeps + 3,
-                     self.eig_tol)
+            if tc:
+                ctx.call('cpsd_eig_sym_topk_tc', ptr(K), n_pad, n_pad * n_pad, n_pad, _p(n_dev), 0,
+                         nprob, m, self.topk_iters, 1 if rnd == 0 else 0, ptr(ws), ptr(evals),
+                         evals.shape[-1], ptr(tot), ptr(resid), ptr(status), self.eig_sweeps + 3,
+                         self.eig_tol, ptr(tcw), ctypes.c_void_p(mp), self.topk_tf32_iters)
+            else:
+                ctx.call('cpsd_eig_sym_topk', ptr(K), n_pad, n_pad * n_pad, n_pad, _p(n_dev), 0,
+                         nprob, m, self.topk_iters, 1 if rnd == 0 else 0, ptr(ws), ptr(evals),
+                         evals.shape[-1], ptr(tot), ptr(resid), ptr(status), self.eig_sweeps + 3,
+                         self.eig_tol)
             ctx.call('cpsd_select_k_total', ptr(evals), evals.shape[-1], ptr(None), m, ptr(tot),
                      thr, mode, 1, min(kcap, m), ptr(k2), 1, nprob)
             yield 'sync'
@@ -549,6 +571,7 @@ class CVEngine:
             ln._extra_lanes = None                    # no reference cycles: engines must die by
             ln._ws, ln._vs, ln._tc_stage, ln._marks = {}, None, None, []   # refcount
             ln._xc = None
+            ln._tkc_key = None
             ln.packA, ln.packB = HostPack(self.ctx), HostPack(self.ctx)
             ln.packM = [HostPack(self.ctx), HostPack(self.ctx)]
             ln._pack_i = 0

@@ -136,7 +136,8 @@ def lstsq_gram(X, Y, device=None):
     return W.cpu().numpy().astype(np.float64), int(st.cpu().numpy()[0])
 
 
-def eig_topk(A, m=128, iters=8, rounds=1, n=None, max_sweeps=15, tol=3e-7, device=None):
+def eig_topk(A, m=128, iters=8, rounds=1, n=None, max_sweeps=15, tol=3e-7, device=None,
+             tensor_cores=False, tf32_iters=5):
     """Leading m eigen-pairs of symmetric PSD matrices A (nprob, n, n) by subspace iteration.
     Returns dict(evals (nprob, m), V (nprob, n, m), total, resid (nprob, m), status)."""
     ctx = _ctx(device)
@@ -151,10 +152,23 @@ def eig_topk(A, m=128, iters=8, rounds=1, n=None, max_sweeps=15, tol=3e-7, devic
     evals = ctx.empty((nprob, n_pad))
     tot, resid = ctx.empty((nprob,)), ctx.empty((nprob, m))
     st = ctx.zeros((nprob,), I32)
+    if tensor_cores:
+        tcw = ctx.empty((int(ctx.lib.cpsd_topk_tc_ws_elems(n_pad, nprob)),))
+        nb = int(ctx.lib.cpsd_topk_tc_map_bytes(nprob))
+        maps = ctx.empty((nb + 64,), torch.uint8)
+        mp = (maps.data_ptr() + 63) & ~63
+        stage = torch.empty((nb + 64,), dtype=torch.uint8).pin_memory()
+        ctx.call('cpsd_topk_tc_encode', ptr(Ad), n_pad, n_pad * n_pad, n_pad, nprob, ptr(tcw),
+                 ctypes.c_void_p(mp), ctypes.c_void_p(stage.data_ptr()))
     for r in range(rounds):
-        ctx.call('cpsd_eig_sym_topk', ptr(Ad), n_pad, n_pad * n_pad, n_pad, ptr(nd), 0, nprob, m,
-                 iters, 1 if r == 0 else 0, ptr(ws), ptr(evals), n_pad, ptr(tot), ptr(resid),
-                 ptr(st), max_sweeps, tol)
+        if tensor_cores:
+            ctx.call('cpsd_eig_sym_topk_tc', ptr(Ad), n_pad, n_pad * n_pad, n_pad, ptr(nd), 0, nprob,
+                     m, iters, 1 if r == 0 else 0, ptr(ws), ptr(evals), n_pad, ptr(tot), ptr(resid),
+                     ptr(st), max_sweeps, tol, ptr(tcw), ctypes.c_void_p(mp), tf32_iters)
+        else:
+            ctx.call('cpsd_eig_sym_topk', ptr(Ad), n_pad, n_pad * n_pad, n_pad, ptr(nd), 0, nprob,
+                     m, iters, 1 if r == 0 else 0, ptr(ws), ptr(evals), n_pad, ptr(tot),
+                     ptr(resid), ptr(st), max_sweeps, tol)
     voff = int(ctx.lib.cpsd_eig_topk_voff(n_pad, m, nprob))
     V = ws[voff:voff + nprob * 2 * n_pad * m].view(nprob, 2 * n_pad, m)[:, :nn, :]
     return dict(evals=evals.cpu().numpy()[:, :m], V=V.cpu().numpy(), total=tot.cpu().numpy(),

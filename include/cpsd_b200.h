@@ -168,6 +168,24 @@ int cpsd_eig_sym_topk(float* K, int ld, long long stride, int n_pad, const int* 
                       int nprob, int m, int iters, int init, float* ws, float* evals, int ld_e,
                       float* total, float* resid, int* status, int eig_sweeps, float eig_tol,
                       cudaStream_t stream);
+/* same solver with Y = K Q on the tensor cores (tcgen05 kind::tf32 + TMA): single-pass TF32
+ * for the first tf32_iters iterations of a fresh start (the iteration is self-correcting),
+ * 3xTF32 afterwards.  tc_ws: cpsd_topk_tc_ws_elems() floats; map_dev: cpsd_topk_tc_map_bytes()
+ * bytes (64-byte aligned) filled by cpsd_topk_tc_encode (host-encoded tensor maps, staged in
+ * pinned stage_host) whenever K or tc_ws move.  Needs m = 128 and densely packed K. */
+long long cpsd_topk_tc_ws_elems(int n_pad, int nprob);
+int cpsd_topk_tc_map_bytes(int nprob);
+int cpsd_topk_tc_encode(const float* K, int ld, long long stride, int n_pad, int nprob, float* tc_ws,
+                        void* map_dev, void* stage_host, cudaStream_t stream);
+int cpsd_topk_tc_split_k(const float* K, int ld, long long stride, int n_pad, int nprob,
+                         float* tc_ws, cudaStream_t stream);
+int cpsd_topk_tc_kq(const float* Q, long long strideQ, float* Y, long long strideY, int n_pad,
+                    int nprob, int terms, float* tc_ws, const void* map_dev, cudaStream_t stream);
+int cpsd_eig_sym_topk_tc(float* K, int ld, long long stride, int n_pad, const int* n_dev,
+                         int n_fixed, int nprob, int m, int iters, int init, float* ws, float* evals,
+                         int ld_e, float* total, float* resid, int* status, int eig_sweeps,
+                         float eig_tol, float* tc_ws, const void* map_dev, int tf32_iters,
+                         cudaStream_t stream);
 /* building blocks of the above, exported for the kernel-level parity tests:
  * C = alpha op(A) B (batched, element strides; trans_a: A stored K x M), and the inverse of
  * the upper Cholesky factor of an m x m (m <= 128) Gram (fp64 in shared memory). */

@@ -337,12 +337,13 @@ def _pooled_like(rng, n, F, decay):
     return X @ X.T
 
 
+@pytest.mark.parametrize('tc', [False, True])
 @pytest.mark.parametrize('n', [300, 1144])
-def test_eig_topk_leading_pairs(ops, n):
+def test_eig_topk_leading_pairs(ops, n, tc):
     rng = np.random.default_rng(n)
     decay = 1.0 / (1.0 + np.arange(4000) / 20.0)
     A = np.stack([_pooled_like(rng, n, 4000, decay) for _ in range(3)])
-    out = ops.eig_topk(A, m=128, iters=8)
+    out = ops.eig_topk(A, m=128, iters=8, tensor_cores=tc)
     assert not out['status'].any()
     for b in range(3):
         w, U = np.linalg.eigh(A[b])
