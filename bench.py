@@ -305,7 +305,7 @@ def main():
         for s in range(n):
             yield host_pts[0], host_pts[1:], step_folds(y0, seed0 + s)
 
-    for _ in cv_align_decode_stream(jobs(4, 77), depth=args.e2e_depth, device='cuda:%d' % local,
+    for _ in cv_align_decode_stream(jobs(args.e2e_depth + 2, 77), depth=args.e2e_depth, device='cuda:%d' % local,
                                     **kw_e2e):
         pass
     sync_all()

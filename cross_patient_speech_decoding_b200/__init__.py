@@ -73,9 +73,11 @@ def cv_align_decode_stream(jobs, depth=8, method='mcca', device=None, **kw):
             progressed = True
             with torch.cuda.stream(ent[0].stream):
                 try:
-                    next(ent[1])
-                    ent[4] = torch.cuda.Event()
-                    ent[4].record(ent[0].stream)
+                    if next(ent[1]) == 'host':
+                        ent[4] = None               # pure host step: resumable at once
+                    else:
+                        ent[4] = torch.cuda.Event()
+                        ent[4].record(ent[0].stream)
                 except StopIteration as e:
                     out = e.value
                     out['h2d_bytes'] += sum(v.h2d_bytes for v in ent[0].views)

@@ -629,9 +629,11 @@ class CVEngine:
                     progressed = True
                     with torch.cuda.stream(ln.stream):
                         try:
-                            next(gens[li])
-                            wait[li] = torch.cuda.Event()
-                            wait[li].record(ln.stream)
+                            if next(gens[li]) == 'host':
+                                wait[li] = None      # nothing queued: resumable at once
+                            else:
+                                wait[li] = torch.cuda.Event()
+                                wait[li].record(ln.stream)
                         except StopIteration as e:
                             results[cur[li]] = e.value
                             gens[li] = None
@@ -683,14 +685,10 @@ class CVEngine:
         return out
 
     def _mcca_start(self, batch, want_details, align_only=False):
-        t0 = time.perf_counter()
+        """Generator of one MCCA batch (nothing runs until it is advanced)."""
         pk = self.packM[self._pack_i]
         self._pack_i ^= 1
-        g = self._batch_mcca_gen(batch, want_details, align_only, pk)
-        next(g)                              # host packing + table upload
-        self.stats['host_pack_ms'] = self.stats.get('host_pack_ms', 0.0) + \
-            1e3 * (time.perf_counter() - t0)
-        return g
+        return self._batch_mcca_gen(batch, want_details, align_only, pk)
 
     def _batch_mcca(self, batch, want_details, align_only=False):
         self._ensure_ready()
@@ -885,9 +883,14 @@ class CVEngine:
         R = Q if use_rank else Cm      # pca_var == 1: no rank reduction (mvlearn _mcca_gevp)
         tv = self.views[0]
         launches0 = ctx.launches()
+        t_pack = time.perf_counter()
         pk.reset()
         pk.o_zero = pk.add_ints([0])
         tabs = self._target_tables(pk, batch)
+        self.stats['host_pack_ms'] = self.stats.get('host_pack_ms', 0.0) + \
+            1e3 * (time.perf_counter() - t_pack)
+        yield 'host'        # packing is pure host work: let the scheduler service other lanes
+        t_pack = time.perf_counter()
         cross_shared = set.intersection(*self.cross_classes) if P > 1 else None
         shared = []
         for tb in tabs:
@@ -965,6 +968,10 @@ class CVEngine:
                     newx.append((xs, f))
             xslot[f] = xs
         o_xslot = pk.add_ints(xslot)
+        self.stats['host_pack_ms'] = self.stats.get('host_pack_ms', 0.0) + \
+            1e3 * (time.perf_counter() - t_pack)
+        yield 'host'
+        t_pack = time.perf_counter()
         downdate = use_rank and getattr(self, 'tg', None) is not None and n_padC == 128
         if downdate:
             use_te = sum(len(tb['te']) for tb in tabs) <= sum(len(tb['tr']) for tb in tabs)
@@ -1022,6 +1029,10 @@ class CVEngine:
         o_npool = pk.add_ints(n_pool)
         o_nall = pk.add_ints([a + b for a, b in zip(n_pool, n_te)])
         o_nte = pk.add_ints(n_te)
+        self.stats['host_pack_ms'] = self.stats.get('host_pack_ms', 0.0) + \
+            1e3 * (time.perf_counter() - t_pack)
+        yield 'host'
+        t_pack = time.perf_counter()
         pk.reserve_ints()
         ib = pk.iaddr(0)
 
@@ -1071,6 +1082,10 @@ class CVEngine:
         Vr = self.ws('m_Vr', (B * P, Cm, R))
         d2 = self.ws('m_d2', (B * P, R))
         r_eff = self.ws('m_reff', (B * P,), I32)
+        self.stats['host_pack_ms'] = self.stats.get('host_pack_ms', 0.0) + \
+            1e3 * (time.perf_counter() - t_pack)
+        yield 'host'
+        t_pack = time.perf_counter()
         # reduced coordinates of the condition averages: the target's per fold (Zt), the cross
         # patients' once per shared class set (Zx, cached with their cross-scatter block Gxx)
         nX = len(newx)
@@ -1158,7 +1173,10 @@ class CVEngine:
                                              n_pad, o_nte, n_te_max)
             d_svm = pk.add_descs(r_svm)
         pk.upload()
-        yield 'packed'
+        self.stats['host_pack_ms'] = self.stats.get('host_pack_ms', 0.0) + \
+            1e3 * (time.perf_counter() - t_pack)
+        yield 'host'
+        t_pack = time.perf_counter()
 
         # ---- launches
         cdim_dev = ctypes_int_ptr(pk.iaddr(o_cdim))

@@ -22,7 +22,7 @@ def jobs(n, seed0):
         yield host[0], host[1:], bench.step_folds(pts[0][1], seed0 + s)
 
 
-for depth in (4, 6, 8, 12):
+for depth in (8, 8):
     for _ in cv_align_decode_stream(jobs(depth + 2, 10), depth=depth, **kw):
         pass
     torch.cuda.synchronize()
