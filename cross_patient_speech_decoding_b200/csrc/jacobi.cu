@@ -222,19 +222,182 @@ __device__ float tile_diag_absmax(const T* As, int m, int* redmax) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Symmetric-storage variants for the n <= 128 tile solver: only the upper triangle (with the
+// diagonal) of the matrix lives in shared memory, in rows of LDS = TS + 1 elements, so that
+// element (i, j) = As[min * LDS + max] sits in bank (i + j) mod 32 whichever way it is
+// addressed -- a warp whose lanes walk consecutive column indices never conflicts, row-wise
+// or column-wise.  A Jacobi step then touches every matrix element once (2x2 blocks with
+// k <= l only) instead of twice, which halves the shared-memory traffic that bounds the solver.
+// ---------------------------------------------------------------------------------------
+#define LDS_SYM (TS + 1)
+__device__ __forceinline__ int sym_idx(int i, int j) {
+  return (i < j) ? i * LDS_SYM + j : j * LDS_SYM + i;
+}
+
+// Pair indices of step s AND their rotations in one phase (one barrier less per step).
+// t = sign(x) y / (|x| + sqrt(x^2 + y^2)) with x = a_qq - a_pp, y = 2 a_pq is the smaller root
+// of t^2 + 2 tau t - 1 = 0 (tau = x / y) written without forming tau: one sqrt, one division
+// and one rsqrt per rotation, all in fp64 (see tile_rotations for why not fp32).
+template <typename T>
+__device__ __forceinline__ float tile_rotations_sym(T* As, StepBuf* sb, int s, int m, int npairs,
+                                                    int nrot, float skip_thr) {
+  float seen = 0.f;
+  const int k = threadIdx.x;
+  if (k < npairs) {
+    int i, j;
+    if (k < nrot) {
+      mod_pair(s, k, m, i, j);
+    } else {
+      // even steps leave two indices unpaired: they ride along with an identity rotation
+      i = s >> 1;
+      j = (i + npairs) % m;
+    }
+    sb->pi[k] = i;
+    sb->pj[k] = j;
+    const double app = (double)As[i * LDS_SYM + i], aqq = (double)As[j * LDS_SYM + j];
+    const double apq = (double)As[sym_idx(i, j)];
+    double c = 1.0, sn = 0.0, d = 0.0;
+    const float aa = (k < nrot) ? fabsf((float)apq) : 0.f;
+    seen = aa;
+    if (aa > skip_thr) {
+      const double x = aqq - app, y = 2.0 * apq;
+      const double t = (x >= 0.0 ? y : -y) / (fabs(x) + sqrt(fma(x, x, y * y)));
+      if (t == t && fabs(t) <= 1.0) {  // guards inf/nan
+        c = rsqrt(fma(t, t, 1.0));
+        sn = t * c;
+        d = t * apq;
+      }
+    }
+    sb->c[k] = c;
+    sb->s[k] = sn;
+    sb->d[k] = d;
+    sb->cf[k] = (float)c;
+    sb->sf[k] = (float)sn;
+    sb->df[k] = (float)d;
+  }
+  return seen;
+}
+
+// One 2x2 block: rows (ik, jk) x columns (il, jl), k < l.
+template <typename T>
+__device__ __forceinline__ void sym_block(T* As, const StepBuf* sb, int k, int l) {
+  const T sk = RotView<T>::s(sb, k), sl = RotView<T>::s(sb, l);
+  if (sk == (T)0 && sl == (T)0) return;
+  const T ck = RotView<T>::c(sb, k), cl = RotView<T>::c(sb, l);
+  const int ik = sb->pi[k], jk = sb->pj[k], il = sb->pi[l], jl = sb->pj[l];
+  const int xpp = sym_idx(ik, il), xpq = sym_idx(ik, jl);
+  const int xqp = sym_idx(jk, il), xqq = sym_idx(jk, jl);
+  const T app = As[xpp], apq = As[xpq], aqp = As[xqp], aqq = As[xqq];
+  // columns (il, jl) rotated by (cl, sl)
+  const T tpp = cl * app - sl * apq, tpq = sl * app + cl * apq;
+  const T tqp = cl * aqp - sl * aqq, tqq = sl * aqp + cl * aqq;
+  // rows (ik, jk) rotated by (ck, sk)
+  As[xpp] = ck * tpp - sk * tqp;
+  As[xqp] = sk * tpp + ck * tqp;
+  As[xpq] = ck * tpq - sk * tqq;
+  As[xqq] = sk * tpq + ck * tqq;
+}
+
+template <typename T, int NP>
+__device__ __forceinline__ void tile_apply_sym(T* As, float* Vs, StepBuf* sb, int npairs_rt,
+                                               int vrows) {
+  const int npairs = NP > 0 ? NP : npairs_rt;
+  // diagonal 2x2 blocks (the rotated pairs themselves)
+  for (int k = threadIdx.x; k < npairs; k += blockDim.x) {
+    if (RotView<T>::s(sb, k) != (T)0) {
+      const int ik = sb->pi[k], jk = sb->pj[k];
+      const T d = RotView<T>::d(sb, k);
+      As[ik * LDS_SYM + ik] -= d;
+      As[jk * LDS_SYM + jk] += d;
+      As[sym_idx(ik, jk)] = (T)0;
+    }
+  }
+  if (NP == 64) {
+    // strict upper triangle of the 64 x 64 block grid, folded so that every lane has work:
+    // slot (rp, c), c < 64, holds row rp (63 - rp entries) followed by row 62 - rp (rp + 1
+    // entries); row 31 (32 entries) has a slot line of its own.  32 x 64 = 2048 slots.
+    for (int b = threadIdx.x; b < 32 * 64; b += blockDim.x) {
+      const int rp = b >> 6, c = b & 63;
+      int k, l;
+      if (rp < 31) {
+        if (c < 63 - rp) { k = rp; l = rp + 1 + c; }
+        else { k = 62 - rp; l = c; }                 // (63 - rp) + (c - (63 - rp))
+      } else {
+        if (c >= 32) continue;
+        k = 31; l = 32 + c;
+      }
+      sym_block<T>(As, sb, k, l);
+    }
+  } else {
+    const int nblk = npairs * npairs;
+    for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
+      const int k = b / npairs;
+      const int l = b - k * npairs;
+      if (l > k) sym_block<T>(As, sb, k, l);
+    }
+  }
+  const int nv = vrows * npairs;
+  for (int b = threadIdx.x; b < nv; b += blockDim.x) {
+    const int r = NP > 0 ? b / NP : b / npairs;
+    const int l = b - r * npairs;
+    const float cl = sb->cf[l], sl = sb->sf[l];
+    if (sl == 0.f) continue;
+    const int il = sb->pi[l], jl = sb->pj[l];
+    const float vp = Vs[r * TS + il], vq = Vs[r * TS + jl];
+    Vs[r * TS + il] = cl * vp - sl * vq;
+    Vs[r * TS + jl] = sl * vp + cl * vq;
+  }
+}
+
+template <typename T>
+__device__ float tile_sweep_full_sym(T* As, float* Vs, StepBuf* sb, int m, int vrows, float skip_thr,
+                                     int* redmax) {
+  float seen = 0.f;
+  const int npairs = m >> 1;
+  for (int s = 0; s < m; ++s) {
+    const int nrot = (s & 1) ? npairs : npairs - 1;
+    seen = fmaxf(seen, tile_rotations_sym<T>(As, sb, s, m, npairs, nrot, skip_thr));
+    __syncthreads();
+    if (m == TS) tile_apply_sym<T, TS / 2>(As, Vs, sb, npairs, vrows);
+    else tile_apply_sym<T, 0>(As, Vs, sb, npairs, vrows);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *redmax = 0;
+  __syncthreads();
+  seen = warp_max(seen);
+  if ((threadIdx.x & 31) == 0) atomicMax(redmax, __float_as_int(seen));
+  __syncthreads();
+  return __int_as_float(*redmax);
+}
+
+template <typename T>
+__device__ float tile_diag_absmax_sym(const T* As, int m, int* redmax) {
+  if (threadIdx.x == 0) *redmax = 0;
+  __syncthreads();
+  float v = 0.f;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) v = fmaxf(v, fabsf((float)As[i * LDS_SYM + i]));
+  v = warp_max(v);
+  if ((threadIdx.x & 31) == 0) atomicMax(redmax, __float_as_int(v));
+  __syncthreads();
+  const float r = __int_as_float(*redmax);
+  __syncthreads();
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------
 // n <= 128 eigen-decomposition, one CTA per problem.  T = float: everything fp32.
 // T = double: the matrix iterates in fp64 (so rotation angles are accurate independently of
 // eigenvalue gaps) while the eigenvectors accumulate in fp32 -- their rounding noise is a
 // gap-independent ~1e-6 perturbation of the basis.
 // ---------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(ET_NT)
+__global__ void __launch_bounds__(ET_NT, 1)
 k_eig_tile(const T* __restrict__ A, int lda, long long strideA, const int* __restrict__ n_dev,
            int n_fixed, float* __restrict__ evals, int ld_e, float* __restrict__ evecs, int ldv,
            long long strideV, int max_sweeps, float tol, int* __restrict__ sweeps_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* As = reinterpret_cast<T*>(smem_raw);
-  float* Vs = reinterpret_cast<float*>(As + TS * TS);
+  T* As = reinterpret_cast<T*>(smem_raw);                  // upper triangle, rows of LDS_SYM
+  float* Vs = reinterpret_cast<float*>(As + TS * LDS_SYM);
   StepBuf* sb = reinterpret_cast<StepBuf*>(Vs + TS * TS);
   int* redmax = reinterpret_cast<int*>(sb + 1);
   int* rank = redmax + 1;  // TS ints
@@ -246,31 +409,25 @@ k_eig_tile(const T* __restrict__ A, int lda, long long strideA, const int* __res
   const int m = (n + 1) & ~1;
   const T* Ag = A + (long long)prob * strideA;
 
+  // upper triangle of the symmetrised input (inputs are Grams computed tile-wise; the average
+  // removes last-ulp asymmetry), identity eigenvectors
   for (int e = threadIdx.x; e < TS * TS; e += ET_NT) {
     const int r = e >> 7, c = e & (TS - 1);
-    T v = (T)0;
-    if (r < n && c < n) v = Ag[(long long)r * lda + c];
-    As[e] = v;
-    Vs[e] = (r == c) ? 1.f : 0.f;
-  }
-  __syncthreads();
-  // symmetrise (inputs are Grams computed tile-wise; removes last-ulp asymmetry)
-  for (int e = threadIdx.x; e < TS * TS; e += ET_NT) {
-    const int r = e >> 7, c = e & (TS - 1);
-    if (r < c) {
-      const T v = (T)0.5 * (As[r * TS + c] + As[c * TS + r]);
-      As[r * TS + c] = v;
-      As[c * TS + r] = v;
+    if (r <= c) {
+      T v = (T)0;
+      if (c < n) v = (T)0.5 * (Ag[(long long)r * lda + c] + Ag[(long long)c * lda + r]);
+      As[r * LDS_SYM + c] = v;
     }
+    Vs[e] = (r == c) ? 1.f : 0.f;
   }
   __syncthreads();
 
   int sw = 0;
   if (m >= 2) {
     for (; sw < max_sweeps; ++sw) {
-      const float dmax = tile_diag_absmax<T>(As, m, redmax);
+      const float dmax = tile_diag_absmax_sym<T>(As, m, redmax);
       const float skip = (sizeof(T) == 8 ? 1e-15f : 1e-9f) * dmax + 1e-37f;
-      const float off = tile_sweep_full<T>(As, Vs, sb, m, evecs ? m : 0, skip, redmax);
+      const float off = tile_sweep_full_sym<T>(As, Vs, sb, m, evecs ? m : 0, skip, redmax);
       if (off <= tol * dmax) { ++sw; break; }
     }
   }
@@ -278,10 +435,10 @@ k_eig_tile(const T* __restrict__ A, int lda, long long strideA, const int* __res
 
   // sort descending by counting
   for (int i = threadIdx.x; i < n; i += ET_NT) {
-    const T li = As[i * TS + i];
+    const T li = As[i * LDS_SYM + i];
     int r = 0;
     for (int j = 0; j < n; ++j) {
-      const T lj = As[j * TS + j];
+      const T lj = As[j * LDS_SYM + j];
       r += (lj > li) || (lj == li && j < i);
     }
     rank[i] = r;
@@ -291,7 +448,7 @@ k_eig_tile(const T* __restrict__ A, int lda, long long strideA, const int* __res
   for (int i = threadIdx.x; i < ld_e; i += ET_NT) {
     if (i >= n) ev[i] = 0.f;
   }
-  for (int i = threadIdx.x; i < n; i += ET_NT) ev[rank[i]] = (float)As[i * TS + i];
+  for (int i = threadIdx.x; i < n; i += ET_NT) ev[rank[i]] = (float)As[i * LDS_SYM + i];
   if (evecs) {
     float* Vg = evecs + (long long)prob * strideV;
     for (int e = threadIdx.x; e < n * n; e += ET_NT) {
@@ -888,7 +1045,7 @@ __global__ void k_select_k(const float* __restrict__ evals, int ld_e, const int*
 // C ABI
 // =======================================================================================
 static size_t tile_smem_bytes(size_t elem = sizeof(float)) {
-  return TS * TS * (elem + sizeof(float)) + sizeof(StepBuf) + (1 + TS) * sizeof(int) + 16;
+  return TS * LDS_SYM * elem + TS * TS * sizeof(float) + sizeof(StepBuf) + (1 + TS) * sizeof(int) + 16;
 }
 
 extern "C" int cpsd_eig_sym_small(const float* A, int lda, long long strideA, const int* n_dev,

@@ -40,7 +40,7 @@ def _eig_leading(A, n_components, kmax):
         else:
             k = int(ops.select_k(ev[None], float(n_components), 0, n=[128], kmin=1, kmax=128,
                                  total=[tot])[0])
-        if not out['status'][0] and k <= 112 and out['resid'][0, :k].max() <= 2e-5 * max(ev[0], 1e-30):
+        if not out['status'][0] and k <= 112 and out['resid'][0, :k].max() <= 5e-6 * max(ev[0], 1e-30):
             return ev, V, tot
     ev, V = ops.eig_sym(A, f64=n <= 128)
     return ev, V, None

@@ -13,6 +13,10 @@ import os
 from . import _lib
 
 _SYNC_DEBUG = os.environ.get('CPSD_SYNC', '0') == '1'
+# CPSD_POISON=1: every fresh device allocation is filled with NaN (0x7f.. for ints) so that a
+# kernel that reads memory nobody wrote shows up in the parity tests instead of depending on
+# whatever the caching allocator hands back
+_POISON = os.environ.get('CPSD_POISON', '0') == '1'
 
 
 class Context:
@@ -45,7 +49,15 @@ class Context:
 
     # ------------------------------------------------------------------ allocation
     def empty(self, shape, dtype=torch.float32):
-        return torch.empty(shape, dtype=dtype, device=self.device)
+        t = torch.empty(shape, dtype=dtype, device=self.device)
+        if _POISON:
+            if t.dtype.is_floating_point:
+                t.fill_(float('nan'))
+            elif t.dtype == torch.uint8:
+                t.fill_(0x7f)
+            else:
+                t.fill_(0x7f7f7f7f if t.dtype == torch.int32 else 0x7f)
+        return t
 
     def zeros(self, shape, dtype=torch.float32):
         return torch.zeros(shape, dtype=dtype, device=self.device)

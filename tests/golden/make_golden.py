@@ -27,7 +27,7 @@ CONFIGS = {
     'cca_p2_5fold': dict(method='cca', n_comp=0.9, n_splits=5, seed=0,
                          patients=[dict(p=0), dict(p=1)]),
     'cca_p2_fixed30': dict(method='cca', n_comp=30, n_splits=5, seed=1,
-                           patients=[dict(p=0), dict(p=1)], max_folds=2),
+                           patients=[dict(p=0), dict(p=1)]),
     'cca_p3_ragged': dict(method='cca', n_comp=0.9, n_splits=4, seed=2,
                           patients=[dict(p=0, n_trials=90, n_time=60, n_chan=48),
                                     dict(p=1, n_trials=110, n_time=60, n_chan=64),
@@ -43,7 +43,7 @@ CONFIGS = {
     'mcca_p8_20fold': dict(method='mcca', n_comp=30, regs=0.5, pca_var=0.8, n_splits=20, seed=5,
                            patients=[dict(p=i) for i in range(8)], max_folds=6),
     'cca_p2_noisy': dict(method='cca', n_comp=0.9, n_splits=5, seed=6,
-                         patients=[dict(p=0, noise=1.0), dict(p=1, noise=1.0)], max_folds=2),
+                         patients=[dict(p=0, noise=1.0), dict(p=1, noise=1.0)]),
 }
 
 
