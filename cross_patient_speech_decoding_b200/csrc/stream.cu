@@ -273,7 +273,64 @@ k_sum_mats_f64(const double* __restrict__ base, const double* __restrict__ mats,
   }
 }
 
+// dst[r][j] = src[r][idx[j]]   (electrode subsampling: keep a subset of the channels)
+__global__ void __launch_bounds__(256)
+k_gather_channels(const float* __restrict__ src, int lds, const int* __restrict__ idx, int nidx,
+                  float* __restrict__ dst, int ldd, long long nrows) {
+  const long long total = nrows * nidx;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / nidx;
+    const int j = (int)(e - r * nidx);
+    dst[r * ldd + j] = src[r * lds + idx[j]];
+  }
+}
+
+// out[trial][t][reg] = mean over the electrodes e of region reg of data[trial][e][t]
+// (data: trials x electrodes x time, time contiguous; fp64 like the reference's np.mean)
+__global__ void __launch_bounds__(128)
+k_region_mean_f64(const double* __restrict__ data, int nelec, int T, const int* __restrict__ reg_ptr,
+                  const int* __restrict__ reg_elec, int nreg, double* __restrict__ out) {
+  const int trial = blockIdx.y, reg = blockIdx.x;
+  const int e0 = reg_ptr[reg], e1 = reg_ptr[reg + 1];
+  const double* d = data + (long long)trial * nelec * T;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    double acc = 0.0;
+    for (int e = e0; e < e1; ++e) acc += d[(long long)reg_elec[e] * T + t];
+    out[((long long)trial * T + t) * nreg + reg] = (e1 > e0) ? acc / (double)(e1 - e0) : 0.0;
+  }
+}
+
 }  // namespace
+
+// Electrode subsampling on resident trials (scripts/aligned_decode_{grid,pitch}_subsample.py
+// index the channel axis with the lists made by processing_utils/{grid_subsampling,
+// poisson_disk_sampling}.py): dst (nrows x nidx) = src[:, idx].
+extern "C" int cpsd_gather_channels(const float* src, int lds, const int* idx, int nidx, float* dst,
+                                    int ldd, long long nrows, cudaStream_t stream) {
+  CPSD_CHECK_ARG(nidx > 0 && nrows >= 0 && lds > 0 && ldd >= nidx, "gather_channels: bad dims");
+  if (nrows == 0) return CPSD_OK;
+  long long nb = (nrows * nidx + 255) / 256;
+  if (nb > 148 * 32) nb = 148 * 32;
+  k_gather_channels<<<(int)nb, 256, 0, stream>>>(src, lds, idx, nidx, dst, ldd, nrows);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
+
+// spatial_avg_data (processing_utils/spatial_avg_subsampling.py:74-96): block means of the
+// electrode grid.  data (trials x nelec x T) fp64, regions as CSR (reg_ptr, reg_elec = flat
+// electrode index x * grid_y + y), out (trials x T x nreg) fp64.
+extern "C" int cpsd_region_mean_f64(const double* data, int ntrials, int nelec, int T,
+                                    const int* reg_ptr, const int* reg_elec, int nreg, double* out,
+                                    cudaStream_t stream) {
+  CPSD_CHECK_ARG(ntrials >= 0 && nelec > 0 && T > 0 && nreg > 0, "region_mean_f64: bad dims");
+  CPSD_CHECK_ARG(ntrials <= 65535, "region_mean_f64: too many trials");
+  if (ntrials == 0) return CPSD_OK;
+  k_region_mean_f64<<<dim3(nreg, ntrials), 128, 0, stream>>>(data, nelec, T, reg_ptr, reg_elec, nreg,
+                                                             out);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
 
 // Scatter matrix of a trial subset from per-trial scatter matrices: the uncentred Gram of the
 // target's train trials (AlignMCCA.n_components_var, AlignMCCA.py:156-174) is the all-trials

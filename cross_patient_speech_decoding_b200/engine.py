@@ -47,6 +47,22 @@ class View:
         # X: numpy array or (pinned) CPU torch tensor, float64 (the reference's dtype) or
         # float32.  float64 is copied as is and cast on the device, so the host never touches
         # the 29 M samples per patient.
+        if isinstance(X, torch.Tensor) and X.is_cuda:
+            # already resident (e.g. a channel subset gathered on the device by
+            # processing_utils.device_subsample): no upload
+            assert X.dim() == 3, 'features must be (trials, time, channels)'
+            self.N, self.T, self.C = (int(v) for v in X.shape)
+            Xc = X.contiguous()
+            if Xc.dtype == torch.float64:
+                self.X = ctx.empty((self.N * self.T, self.C))
+                ctx.call('cpsd_cast_f64_f32', ptr(Xc), ptr(self.X), Xc.numel())
+            else:
+                self.X = Xc.to(torch.float32).view(self.N * self.T, self.C)
+            self._host = Xc
+            self.y = np.asarray(y).astype(np.int64)
+            self.cls = np.asarray(cls_ids, dtype=np.int32)
+            self.h2d_bytes = 0
+            return
         if isinstance(X, torch.Tensor):
             host = X if X.is_contiguous() else X.contiguous()
         else:

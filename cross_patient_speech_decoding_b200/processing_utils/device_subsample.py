@@ -1,0 +1,54 @@
+"""GPU side of the electrode-subsampling analyses: the trials of every patient are uploaded
+once (``resident``), each subsample is a channel gather on the device (``gather_channels``)
+whose result goes straight into ``cv_align_decode`` / ``cv_align_decode_stream`` /
+``CVEngine`` -- no host copy of the 50 x sliced arrays the reference materialises
+(scripts/aligned_decode_grid_subsample.py:280-300)."""
+import numpy as np
+import torch
+
+from ..device import Context, ptr
+
+I32 = torch.int32
+
+
+def resident(X, device=None):
+    """Host (trials, time, channels) array -> fp32 CUDA tensor (uploaded once)."""
+    ctx = Context.get(device)
+    X = np.ascontiguousarray(X)
+    t = torch.from_numpy(X)
+    raw = t.pin_memory().to(ctx.device, non_blocking=True)
+    if raw.dtype == torch.float64:
+        out = ctx.empty(tuple(X.shape))
+        ctx.call('cpsd_cast_f64_f32', ptr(raw), ptr(out), raw.numel())
+        return out
+    return raw.to(torch.float32)
+
+
+def gather_channels(X_dev, idx, device=None):
+    """X_dev (trials, time, channels) fp32 CUDA tensor -> X_dev[:, :, idx] (new CUDA tensor)."""
+    ctx = Context.get(device if device is not None else X_dev.device)
+    assert X_dev.is_cuda and X_dev.dtype == torch.float32 and X_dev.dim() == 3
+    X_dev = X_dev.contiguous()
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    assert idx.ndim == 1 and idx.size > 0 and idx.min() >= 0 and idx.max() < X_dev.shape[2]
+    idx_d = ctx.upload(idx, np.int32)
+    N, T, C = (int(v) for v in X_dev.shape)
+    out = ctx.empty((N, T, idx.size))
+    ctx.call('cpsd_gather_channels', ptr(X_dev), C, ptr(idx_d), int(idx.size), ptr(out), int(idx.size),
+             N * T)
+    return out
+
+
+def spatial_average(data, avgIdxs, device=None):
+    """spatial_avg_data: data (trials, grid_x, grid_y, time) host float array, avgIdxs list of
+    (n_i, 2) grid index arrays -> (trials, time, regions) float64 numpy array."""
+    ctx = Context.get(device)
+    data = np.ascontiguousarray(data, dtype=np.float64)
+    ntr, gx, gy, T = data.shape
+    reg_ptr = np.concatenate([[0], np.cumsum([len(ix) for ix in avgIdxs])]).astype(np.int32)
+    flat = np.concatenate([np.asarray(ix)[:, 0] * gy + np.asarray(ix)[:, 1] for ix in avgIdxs])
+    d = ctx.upload(data.reshape(ntr, gx * gy, T))
+    rp, re = ctx.upload(reg_ptr, np.int32), ctx.upload(flat, np.int32)
+    out = ctx.empty((ntr, T, len(avgIdxs)), torch.float64)
+    ctx.call('cpsd_region_mean_f64', ptr(d), ntr, gx * gy, T, ptr(rp), ptr(re), len(avgIdxs), ptr(out))
+    return out.cpu().numpy()

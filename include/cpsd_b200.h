@@ -58,6 +58,13 @@ int cpsd_copy_rows(const float* src, int lds, long long strideS, float* dst, int
 int cpsd_sum_mats_f64(const double* base, const double* mats, long long mat_stride,
                       const int* list_ptr, const int* list, double sign, double* out,
                       long long out_stride, int elems, int nprob, cudaStream_t stream);
+/* electrode subsampling of resident trials: dst = src[:, idx] (the channel lists of
+ * processing_utils/grid_subsampling.py:8-61 and poisson_disk_sampling.py:9-77) and the block
+ * means of spatial_avg_data (processing_utils/spatial_avg_subsampling.py:74-96) */
+int cpsd_gather_channels(const float* src, int lds, const int* idx, int nidx, float* dst, int ldd,
+                         long long nrows, cudaStream_t stream);
+int cpsd_region_mean_f64(const double* data, int ntrials, int nelec, int T, const int* reg_ptr,
+                         const int* reg_elec, int nreg, double* out, cudaStream_t stream);
 /* ingest: the reference keeps trials as float64 (pickled numpy); cast once on the device */
 int cpsd_cast_f64_f32(const double* src, float* dst, long long n, cudaStream_t stream);
 int cpsd_permute_cols(const float* src, int lds, long long strideS, const int* perm, int ld_perm,
