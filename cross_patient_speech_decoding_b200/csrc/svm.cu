@@ -24,6 +24,9 @@
 namespace {
 
 #define SV_NT 256
+#ifndef SV_MINB
+#define SV_MINB 3
+#endif
 
 struct SvmSmem {
   double* w; double* g; double* d; double* r; double* zz; double* p; double* hp; double* dg;
@@ -76,7 +79,7 @@ __device__ __forceinline__ double bdot(const double* a, const double* b, int n, 
   return block_sum(s, red);
 }
 
-__global__ void __launch_bounds__(SV_NT)
+__global__ void __launch_bounds__(SV_NT, SV_MINB)
 k_svm_fit(const cpsd_svm_desc* __restrict__ descs, int kp_max, int n_max) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const cpsd_svm_desc t = descs[blockIdx.x];
