@@ -162,9 +162,13 @@ k_proj_tc(const CUtensorMap* __restrict__ xmaps, const CUtensorMap* __restrict__
 #pragma unroll
             for (int k = 0; k < PT_BK / 8; ++k) {
               const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
+#ifdef PT_EXPERIMENT_1TERM
+              umma_tf32(tacc, a_hi + adv, b_hi + adv, idesc, (kb != 0 || k != 0) ? 1u : 0u);
+#else
               umma_tf32(tacc, a_lo + adv, b_hi + adv, idesc, (kb != 0 || k != 0) ? 1u : 0u);
               umma_tf32(tacc, a_hi + adv, b_lo + adv, idesc, 1u);
               umma_tf32(tacc, a_hi + adv, b_hi + adv, idesc, 1u);
+#endif
             }
           }
           umma_commit(&b_empty[s]);
@@ -176,23 +180,23 @@ k_proj_tc(const CUtensorMap* __restrict__ xmaps, const CUtensorMap* __restrict__
   } else {
     // ------------------------------------------------------------------ epilogue
     const int quad = warp & 3;
-    const int et = threadIdx.x - 64;           // 0..127
     const int r_own = quad * 32 + lane;        // TMEM lane = tile row owned by this thread
     const int Q = prm.Q;
-    // copy-out pattern of this thread: element e = et + 128 i of the (128 x Q) tile
+    // every epilogue warp stages and writes its own 32 rows (no cross-warp barrier): copy-out
+    // pattern of this lane = element e = lane + 32 i of the warp's (32 x Q) block
     uint32_t rj[PT_N];
 #pragma unroll
     for (int i = 0; i < PT_N; ++i) {
-      const int e = et + 128 * i;
+      const int e = lane + 32 * i;
       const int r = e / Q, j = e - r * Q;
-      rj[i] = (uint32_t)(r << 8) | (uint32_t)j;
+      rj[i] = (uint32_t)((quad * 32 + r) << 8) | (uint32_t)j;
     }
     uint32_t it_b = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
       int v, tile, f0, f1;
       decode(item, v, tile, f0, f1);
       // this thread's row of the tile: trial and time bin (item-invariant)
-      const int R = tile * PT_BM + et;
+      const int R = tile * PT_BM + r_own;
       int my_tr = -1, my_t = 0;
       if (R < prm.nrows[v]) {
         my_tr = R / prm.T;
@@ -221,18 +225,23 @@ k_proj_tc(const CUtensorMap* __restrict__ xmaps, const CUtensorMap* __restrict__
 #pragma unroll
         for (int j = 0; j < PT_N; ++j)
           stg[r_own * PT_LDS + j] = __uint_as_float(vv[j]) - __shfl_sync(0xffffffffu, ml_mine, j);
-        row_off[et] = (d >= 0) ? (d * prm.T + my_t) * Q : -1;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        row_off[r_own] = (d >= 0) ? (d * prm.T + my_t) * Q : -1;
+        __syncwarp();
         float* Yf = Y + (long long)f * prm.strideY;
+        // all shared-memory reads first (independent), then the predicated global stores
+        int offs[PT_N];
+        float vals[PT_N];
 #pragma unroll
         for (int i = 0; i < PT_N; ++i) {
-          if (i < Q) {
-            const int r = (int)(rj[i] >> 8), j = (int)(rj[i] & 255u);
-            const int off = row_off[r];
-            if (off >= 0) Yf[off + j] = stg[r * PT_LDS + j];
-          }
+          const int r = (int)(rj[i] >> 8), j = (int)(rj[i] & 255u);
+          const int off = (i < Q) ? row_off[r] : -1;
+          offs[i] = (off >= 0) ? off + j : -1;
+          vals[i] = stg[r * PT_LDS + j];
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < PT_N; ++i)
+          if (offs[i] >= 0) Yf[offs[i]] = vals[i];
+        __syncwarp();
       }
     }
   }
