@@ -356,15 +356,25 @@ def main():
     peak_tf = pk.get('bf16_tflops_sustained', pk.get('bf16_tflops'))
     proj_ms = stages_batch.get('project_pool', float('nan'))
     proj_bytes = nprof * (sum(p[0].size for p in pts) * 4 + n_all * F * 4)   # read X once, write pooled
-    roofline = {'kernel': 'k_gram_tc (pooled Gram, tcgen05 kind::tf32, 3xTF32)' if not args.no_tc
+    roofline = {'kernel': 'k_split_tf32_batched + k_gram_tc (pooled Gram of the centred matrix, tcgen05 '
+                          'kind::tf32, 3xTF32)' if not args.no_tc
                 else 'k_gram_nt (pooled Gram, fp32 SIMT)',
                 'bound': 'tensor', 'achieved': gram_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                'frac': gram_tf / peak_tf, 'traffic': None,
+                'frac': gram_tf / peak_tf,
+                # dram__bytes_read + write of one `ncu --set full` capture (profiles/
+                # ncu_r1_k_gram_tc.txt: 7.48 GB per 107-fold launch), scaled to this launch
+                'traffic': 7.478e9 / 107 * nprof,
                 'peak_source': '%s bf16_tflops_sustained (TF32 dense is nominally half of it; '
                                '3xTF32 issues 3 MMAs per algorithmic product)' % pk_kind,
                 'algorithmic_flops_per_launch': gram_flops, 'launch_ms': gram_ms,
                 'share_of_step': gram_ms / stage_total}
-    roofline_hbm = {'kernel': 'k_proj_nn (project all trials into the pooled matrix)',
+    roofline_hbm = {'kernel': 'k_proj_tc_prep + k_proj_tc (project all trials of all patients into the '
+                              'pooled matrices, tcgen05 3xTF32 + TMA)',
+                    'traffic': 3.209e9 / 107 * nprof,
+                    'note': 'achieved counts SURVEY 8(d) algorithmic bytes (every fold reads every '
+                            'patient once and writes its pooled matrix); the kernel shares each X '
+                            'tile between all folds of the batch, so its real DRAM traffic '
+                            '(`traffic`, ncu) is ~5x lower',
                     'bound': 'hbm', 'achieved': proj_bytes / (proj_ms * 1e-3) / 1e9,
                     'peak': pk['hbm_gbs'], 'unit': 'GB/s',
                     'frac': proj_bytes / (proj_ms * 1e-3) / 1e9 / pk['hbm_gbs'],
@@ -383,8 +393,11 @@ def main():
                        'engine_batch_folds': args.batch,
                        'parallelism': 'folds sharded over %d GPU(s), one NCCL all_gather of '
                                       'accuracies' % world,
-                       'precision': 'fp32 storage; fp64 scatter+eigen for PCA stages; 3xTF32 '
-                                    'tcgen05 pooled Gram; fp64 SVM',
+                       'precision': 'fp32 storage; fp64 scatter + eigen-solver for the alignment PCA '
+                                    'stages; 3xTF32 tcgen05 projection and pooled Gram; top-k '
+                                    'subspace iteration (TF32 then 3xTF32 tcgen05) for the decoder '
+                                    'PCA; fp64 Newton SVM',
+                       'lanes': 2,
                        'l2': 'working set per step ~2 GB (20 pooled 1152x6000 matrices + Grams) '
                              '>> 126 MB L2, no explicit flush'},
             'e2e': {'value': e2e_val, 'unit': 'folds/s',

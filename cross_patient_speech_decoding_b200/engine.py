@@ -722,10 +722,13 @@ class CVEngine:
 
     # ------------------------------------------------------------------ shared host prep
     def _target_tables(self, pk, batch):
-        """Per fold: target class-mean CSR (classes present among the train trials)."""
+        """Per fold: target class-mean CSR (classes present among the train trials).  Generator
+        (yields 'host' every few folds so the scheduler can service other lanes)."""
         tv = self.views[0]
         tabs = []
-        for tr, te in batch:
+        for bi, (tr, te) in enumerate(batch):
+            if bi and bi % 24 == 0:
+                yield 'host'
             tr = np.asarray(tr, dtype=np.int64)
             cls = tv.cls[tr]
             present = np.unique(cls)
@@ -905,7 +908,7 @@ class CVEngine:
         t_pack = time.perf_counter()
         pk.reset()
         pk.o_zero = pk.add_ints([0])
-        tabs = self._target_tables(pk, batch)
+        tabs = yield from self._target_tables(pk, batch)
         self.stats['host_pack_ms'] = self.stats.get('host_pack_ms', 0.0) + \
             1e3 * (time.perf_counter() - t_pack)
         yield 'host'        # packing is pure host work: let the scheduler service other lanes

@@ -16,6 +16,14 @@ from .device import addr, ptr
 from .engine import F32, I32, _ceil, ctypes_int_ptr
 
 
+def _drain(g):
+    try:
+        while True:
+            next(g)
+    except StopIteration as e:
+        return e.value
+
+
 def batch_cca(eng, batch, want_details):
     ctx, T, P, Cm = eng.ctx, eng.T, eng.P, eng.Cmax
     B = len(batch)
@@ -29,7 +37,7 @@ def batch_cca(eng, batch, want_details):
     pk = eng.packA
     pk.reset()
     eng._o_zero = pk.o_zero = pk.add_ints([0])
-    tabs = eng._target_tables(pk, batch)
+    tabs = _drain(eng._target_tables(pk, batch))
     n_tr = [len(tb['tr']) for tb in tabs]
     n_te = [len(tb['te']) for tb in tabs]
     Kmax = max(len(tb['present']) for tb in tabs)
