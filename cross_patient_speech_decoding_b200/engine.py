@@ -746,10 +746,13 @@ class CVEngine:
         recs = np.zeros(B, dtype=_lib.CLASS_MEAN_DESC)
         ib = pk.iaddr(0)
         recs['X'] = addr(tv.X)
-        recs['member_ptr'] = ib + 4 * np.array([tb['o_ptr'] for tb in tabs], dtype=np.int64)
-        recs['members'] = ib + 4 * np.array([tb['o_mem'] for tb in tabs], dtype=np.int64)
+        if not isinstance(tabs, dict):       # list of per-fold tables (CCA / none batches)
+            tabs = dict(o_ptr=[tb['o_ptr'] for tb in tabs], o_mem=[tb['o_mem'] for tb in tabs],
+                        Kp=[len(tb['present']) for tb in tabs])
+        recs['member_ptr'] = ib + 4 * np.asarray(tabs['o_ptr'], dtype=np.int64)
+        recs['members'] = ib + 4 * np.asarray(tabs['o_mem'], dtype=np.int64)
         recs['out'] = addr(cmT) + 4 * Kmax * T * tv.C * np.arange(B, dtype=np.int64)
-        recs['nslot'] = [len(tb['present']) for tb in tabs]
+        recs['nslot'] = tabs['Kp']
         recs['TC'] = T * tv.C
         return cmT, recs
 
@@ -908,38 +911,65 @@ class CVEngine:
         t_pack = time.perf_counter()
         pk.reset()
         pk.o_zero = pk.add_ints([0])
-        tabs = yield from self._target_tables(pk, batch)
+        # ---- index tables, built for all folds at once (2-D numpy ops over (fold, trial) /
+        # (fold, class) instead of per-fold Python loops)
+        V = len(self.vocab)
+        n_tr_a = np.array([len(tr) for tr, _ in batch], dtype=np.int64)
+        n_te_a = np.array([len(te) for _, te in batch], dtype=np.int64)
+        ntr_max, nte_max = int(n_tr_a.max()), max(int(n_te_a.max()), 1)
+        TR = np.full((B, ntr_max), -1, dtype=np.int64)
+        TE = np.full((B, nte_max), -1, dtype=np.int64)
+        for f, (tr, te) in enumerate(batch):
+            TR[f, :n_tr_a[f]] = tr
+            TE[f, :n_te_a[f]] = te
+        mtr, mte = TR >= 0, TE >= 0
+        fold_of = np.arange(B, dtype=np.int64)
+        cls2d = np.where(mtr, tv.cls[np.where(mtr, TR, 0)], V)          # padding sorts last
+        members = np.take_along_axis(TR, np.argsort(cls2d, axis=1, kind='stable'), axis=1)
+        counts = np.bincount((fold_of[:, None] * (V + 1) + cls2d).ravel(),
+                             minlength=B * (V + 1)).reshape(B, V + 1)[:, :V]
+        present = counts > 0                                             # (fold, class)
+        Kp = present.sum(axis=1)
+        # class-mean CSR pointers of every fold: [0, cumulative counts of its present classes]
+        p_start = np.concatenate([[0], np.cumsum(Kp + 1)])[:-1]
+        mptr = np.zeros(int((Kp + 1).sum()), dtype=np.int32)
+        mptr[np.arange(int(Kp.sum())) + 1 + np.repeat(fold_of, Kp)] = np.cumsum(counts, axis=1)[present]
+        o_ptr = pk.add_ints(mptr) + p_start
+        o_mem = pk.add_ints(np.where(members >= 0, members, 0)) + fold_of * ntr_max
+        o_trv = pk.add_ints(np.where(mtr, TR, 0) * T) + fold_of * ntr_max
+        o_tev = pk.add_ints(np.where(mte, TE, 0) * T) + fold_of * nte_max
+        tabs = dict(o_ptr=o_ptr, o_mem=o_mem, Kp=Kp)
         self.stats['host_pack_ms'] = self.stats.get('host_pack_ms', 0.0) + \
             1e3 * (time.perf_counter() - t_pack)
         yield 'host'        # packing is pure host work: let the scheduler service other lanes
         t_pack = time.perf_counter()
-        cross_shared = set.intersection(*self.cross_classes) if P > 1 else None
-        shared = []
-        for tb in tabs:
-            s = set(tb['present'].tolist())
-            if cross_shared is not None:
-                s &= cross_shared
-            shared.append(np.array(sorted(s), dtype=np.int64))
-        Kmax = max(len(tb['present']) for tb in tabs)
-        Ks = [len(s) for s in shared]
-        KTmax = max(Ks) * T
-        if min(Ks) == 0:
+        # shared class sets (alignment classes present in the fold's train trials AND in every
+        # cross patient); folds with the same set share everything that depends on it
+        cmask = np.ones(V, dtype=bool)
+        if P > 1:
+            cmask[:] = False
+            cmask[sorted(set.intersection(*self.cross_classes))] = True
+        shared2d = present & cmask[None, :]
+        Ksa = shared2d.sum(axis=1).astype(np.int64)
+        if Ksa.min() == 0:
             raise ValueError('no alignment class is shared by all patients in some fold')
-        # segment tables: rows of the shared classes inside each view's class-mean array (the
-        # cross patients' tables depend on the shared class set only)
+        uniq, first, inv = np.unique(shared2d, axis=0, return_index=True, return_inverse=True)
+        inv = np.asarray(inv).ravel()
+        shared_u = [np.nonzero(u)[0].astype(np.int64) for u in uniq]
+        keys_u = [sh.tobytes() for sh in shared_u]
+        shared = [shared_u[u] for u in inv]
+        Kmax, Ks = int(Kp.max()), Ksa.tolist()
+        KTmax = int(Ksa.max()) * T
+        # segment tables: rows of the shared classes inside each view's class-mean array
         o_seg = np.zeros((B, P), dtype=np.int64)
-        seg_cache = {}
-        keys = [sh.tobytes() for sh in shared]
-        for f, tb in enumerate(tabs):
-            slot_t = -np.ones(len(self.vocab), dtype=np.int64)
-            slot_t[tb['present']] = np.arange(len(tb['present']))
-            o_seg[f, 0] = pk.add_ints(slot_t[shared[f]] * T)
-            row = seg_cache.get(keys[f])
-            if row is None:
-                row = [pk.add_ints(self.cm_row[v][shared[f]] * T) for v in range(1, P)]
-                seg_cache[keys[f]] = row
-            o_seg[f, 1:] = row
-        o_segdst = pk.add_ints(np.arange(max(Ks), dtype=np.int32) * T)
+        slot_in_fold = np.cumsum(present, axis=1) - 1                    # class -> row of the fold's means
+        o_seg[:, 0] = pk.add_ints(slot_in_fold[shared2d] * T) + \
+            np.concatenate([[0], np.cumsum(Ksa)])[:-1]
+        if P > 1:
+            seg_u = np.array([[pk.add_ints(self.cm_row[v][sh] * T) for v in range(1, P)]
+                              for sh in shared_u], dtype=np.int64)
+            o_seg[:, 1:] = seg_u[inv]
+        o_segdst = pk.add_ints(np.arange(int(Ksa.max()), dtype=np.int32) * T)
         cdims = np.array([vw.C for vw in self.views], dtype=np.int64)
         o_cdim = pk.add_ints(np.tile(cdims, B))
         ranks = np.zeros((B, P), dtype=np.int32)
@@ -952,24 +982,21 @@ class CVEngine:
             vs['keys'].clear()
             vs['next'] = vs['res']
         slot = np.zeros((B, P), dtype=np.int64)
-        slot[:, 0] = np.arange(B)
+        slot[:, 0] = fold_of
         solve = [(f, 0, f) for f in range(B)]
         pending = {}
-        row_cache = {}
-        for f in range(B):
-            row = row_cache.get(keys[f])
-            if row is None:
-                row = []
+        if P > 1:
+            rows_u = np.zeros((len(shared_u), P - 1), dtype=np.int64)
+            for u, ku in enumerate(keys_u):
                 for v in range(1, P):
-                    key = (v, keys[f])
+                    key = (v, ku)
                     sl = vs['keys'].get(key)
                     if sl is None:
                         sl = vs['next'] + len(pending)
                         pending[key] = sl
-                        solve.append((f, v, sl))
-                    row.append(sl)
-                row_cache[keys[f]] = row
-            slot[f, 1:] = row
+                        solve.append((int(first[u]), v, sl))
+                    rows_u[u, v - 1] = sl
+            slot[:, 1:] = rows_u[inv]
         o_slot = pk.add_ints(slot)
         o_cds = pk.add_ints([self.views[v].C for _, v, _ in solve])
         # cross-block cache slot of every fold (one slot per shared class set)
@@ -977,18 +1004,18 @@ class CVEngine:
         xc = self._xcache(R, XR)
         newx = []                       # (cache slot, first fold with that class set)
         xs_of = {}
-        xslot = np.zeros(B, dtype=np.int32)
         if len(xc['keys']) + B > xc['cap']:
             xc['keys'].clear()
-        for f in range(B):
-            xs = xc['keys'].get(keys[f])
+        xs_u = np.zeros(len(shared_u), dtype=np.int32)
+        for u, ku in enumerate(keys_u):
+            xs = xc['keys'].get(ku)
             if xs is None:
-                xs = xs_of.get(keys[f])
-                if xs is None:
-                    xs = len(xc['keys']) + len(xs_of)
-                    xs_of[keys[f]] = xs
-                    newx.append((xs, f))
-            xslot[f] = xs
+                xs = len(xc['keys']) + len(xs_of)
+                xs_of[ku] = xs
+                newx.append((xs, int(first[u])))
+            xs_u[u] = xs
+        xslot = xs_u[inv]
+        keys = [keys_u[u] for u in inv]
         o_xslot = pk.add_ints(xslot)
         self.stats['host_pack_ms'] = self.stats.get('host_pack_ms', 0.0) + \
             1e3 * (time.perf_counter() - t_pack)
@@ -996,13 +1023,12 @@ class CVEngine:
         t_pack = time.perf_counter()
         downdate = use_rank and getattr(self, 'tg', None) is not None and n_padC == 128
         if downdate:
-            use_te = sum(len(tb['te']) for tb in tabs) <= sum(len(tb['tr']) for tb in tabs)
-            lists = [tb['te'] if use_te else tb['tr'] for tb in tabs]
-            o_lptr = pk.add_ints(np.concatenate([[0], np.cumsum([len(x) for x in lists])]))
-            o_list = pk.add_ints(np.concatenate(lists) if lists else [])
+            use_te = int(n_te_a.sum()) <= int(n_tr_a.sum())
+            La, Lm = (TE, mte) if use_te else (TR, mtr)
+            o_lptr = pk.add_ints(np.concatenate([[0], np.cumsum(Lm.sum(axis=1))]))
+            o_list = pk.add_ints(La[Lm])
         # pooled layout
-        n_tr = [len(tb['tr']) for tb in tabs]
-        n_te = [len(tb['te']) for tb in tabs]
+        n_tr, n_te = n_tr_a.tolist(), n_te_a.tolist()
         cross_N = [self.views[v].N for v in range(1, P)]
         n_pool = [(nt if self.tar_in_train else 0) + sum(cross_N) for nt in n_tr]
         n_te_max = max(n_te)
@@ -1014,17 +1040,18 @@ class CVEngine:
             ycross = self._ycross = (np.concatenate([self.views[v].y for v in range(1, P)])
                                      if P > 1 else np.zeros(0, dtype=np.int64)).astype(np.int32)
         ypool = np.zeros((B, n_pad), dtype=np.int32)
-        row0 = np.array([nt if self.tar_in_train else 0 for nt in n_tr], dtype=np.int64)
-        for f, tb in enumerate(tabs):
-            if self.tar_in_train:
-                ypool[f, :n_tr[f]] = tv.y[tb['tr']]
-            ypool[f, row0[f]:row0[f] + len(ycross)] = ycross
+        row0 = n_tr_a.copy() if self.tar_in_train else np.zeros(B, dtype=np.int64)
+        fr, fc = np.nonzero(mtr)                    # (fold, rank inside the fold's train list)
+        if self.tar_in_train:
+            ypool[fr, fc] = tv.y[TR[mtr]]
+        if len(ycross):
+            ypool[fold_of[:, None], row0[:, None] + np.arange(len(ycross))[None, :]] = ycross[None, :]
         if not tc_proj:
             o_pooldst = np.zeros((B, P), dtype=np.int64)
             o_allseg = [pk.add_ints(np.arange(self.views[v].N, dtype=np.int32) * T)
                         for v in range(P)]
             o_tedst = []
-            for f, tb in enumerate(tabs):
+            for f in range(B):
                 row = 0
                 if self.tar_in_train:
                     o_pooldst[f, 0] = pk.add_ints((row + np.arange(n_tr[f])) * T)
@@ -1042,10 +1069,10 @@ class CVEngine:
                 cbase[v, :self.views[v].N] = off + np.arange(self.views[v].N)
                 off += self.views[v].N
             dst = np.where(cbase[None] >= 0, cbase[None] + row0[:, None, None], -1).astype(np.int32)
-            for f, tb in enumerate(tabs):
-                if self.tar_in_train:
-                    dst[f, 0, tb['tr']] = np.arange(n_tr[f])
-                dst[f, 0, tb['te']] = n_pool[f] + np.arange(n_te[f])
+            if self.tar_in_train:
+                dst[fr, 0, TR[mtr]] = fc
+            er, ec = np.nonzero(mte)
+            dst[er, 0, TE[mte]] = np.asarray(n_pool, dtype=np.int64)[er] + ec
             o_dst = pk.add_ints(dst)
         o_ypool = pk.add_ints(ypool)
         o_npool = pk.add_ints(n_pool)
@@ -1074,7 +1101,7 @@ class CVEngine:
         segb = ib + 4 * o_seg                       # (B, P) segment-table addresses
         mub = addr(mu) + 4 * Cm * slot               # (B, P) mean vectors (slots)
         Ksa = np.asarray(Ks, dtype=np.int64)
-        o_tr = ib + 4 * np.array([tb['o_tr'] for tb in tabs], dtype=np.int64)
+        o_tr = ib + 4 * o_trv
         r_gt = np.zeros(B, dtype=_lib.GRAM_TN_DESC)
         r_gt['A'] = r_gt['B'] = addr(tv.X)
         r_gt['segA'] = r_gt['segB'] = o_tr
@@ -1168,19 +1195,19 @@ class CVEngine:
             Zall = self.ws('pool_Z', (B, n_pad, F))
             if not tc_proj:
                 r_pp = np.zeros(B * P + B, dtype=_lib.PROJ_DESC)
-                for f, tb in enumerate(tabs):
+                for f in range(B):
                     for v in range(P):
                         vw = self.views[v]
                         i = f * P + v
                         if v == 0:
                             nseg = n_tr[f] if self.tar_in_train else 0
-                            src = pk.iaddr(tb['o_tr'])
+                            src = pk.iaddr(int(o_trv[f]))
                         else:
                             nseg, src = vw.N, pk.iaddr(o_allseg[v])
                         r_pp[i] = (addr(vw.X), src, pk.iaddr(o_pooldst[f, v]), int(mub[f, v]),
                                    addr(L, i * Cm * Q), addr(Zall, f * n_pad * F), nseg, T, vw.C, Q,
                                    vw.C, Q, Q, 0)
-                    r_pp[B * P + f] = (addr(tv.X), pk.iaddr(tb['o_te']), pk.iaddr(o_tedst[f]),
+                    r_pp[B * P + f] = (addr(tv.X), pk.iaddr(int(o_tev[f])), pk.iaddr(o_tedst[f]),
                                        int(mub[f, 0]), addr(L, f * P * Cm * Q),
                                        addr(Zall, f * n_pad * F), n_te[f], T, tv.C, Q, tv.C, Q, Q, 0)
                 d_pp = pk.add_descs(r_pp)
