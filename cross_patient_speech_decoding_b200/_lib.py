@@ -92,7 +92,8 @@ _SIGS = {
     'cpsd_chol_inv': [_P, c_int, c_ll, c_int, _P, c_int, c_ll, _P, c_int, _P],
     'cpsd_gram_tn': [_P, c_int, c_int, c_int, _P],
     'cpsd_gram_tn_f64': [_P, c_int, c_int, c_int, _P],
-    'cpsd_gram_tn_f64_split': [_P, c_int, c_int, c_int, c_int, _P],
+    'cpsd_gram_tn_f64_split': [_P, c_int, c_int, c_int, c_int, c_int, _P, _P],
+    'cpsd_gram_tn_split_ws_elems': [c_int, c_int, c_int, c_int],
     'cpsd_colsum': [_P, c_int, c_int, _P],
     'cpsd_proj_nn': [_P, c_int, c_int, c_int, c_int, _P],
     'cpsd_gram_nt': [_P, c_int, c_int, c_int, _P],
@@ -134,6 +135,7 @@ _SIGS = {
 _RESTYPES = {'cpsd_last_error': ctypes.c_char_p, 'cpsd_launch_count': c_ll,
              'cpsd_bj_rlog_elems': c_ll, 'cpsd_eig_topk_ws_elems': c_ll,
              'cpsd_eig_topk_voff': c_ll, 'cpsd_topk_tc_ws_elems': c_ll,
+             'cpsd_gram_tn_split_ws_elems': c_ll,
              'cpsd_reset_launch_count': None}
 
 EXPORTED_SYMBOLS = sorted(_SIGS)

@@ -22,11 +22,13 @@ namespace {
 #define GT_TILE 64
 #define GT_RK 16
 // nsplit > 1: the segments are dealt round-robin to nsplit CTAs per output tile (blockIdx.x =
-// tile + tiles_x * split) which accumulate into a ZEROED output with atomics -- for batches
-// with few problems and many rows (the per-fold target scatter: 4 tiles x 27 400 rows).
+// tile + tiles_x * split); every CTA writes its partial tile to part[split][prob] and
+// k_gram_tn_reduce adds the partials in a fixed order (deterministic, no atomics) -- for
+// batches with few problems and many rows (the per-fold scatters: 3 tiles x 10 400 rows).
 template <typename AccT>
 __global__ void __launch_bounds__(256)
-k_gram_tn(const cpsd_gram_tn_desc* __restrict__ descs, int tiles_x, int nsplit) {
+k_gram_tn(const cpsd_gram_tn_desc* __restrict__ descs, int tiles_x, int nsplit, AccT* __restrict__ part,
+          long long part_stride) {
   const cpsd_gram_tn_desc d = descs[blockIdx.z];
   const int bx = blockIdx.x % tiles_x, split = blockIdx.x / tiles_x;
   const int i0 = blockIdx.y * GT_TILE, j0 = bx * GT_TILE;
@@ -88,13 +90,30 @@ k_gram_tn(const cpsd_gram_tn_desc* __restrict__ descs, int tiles_x, int nsplit) 
       if (gj >= d.q) continue;
       const AccT v = (AccT)d.alpha * acc[i][j];
       if (nsplit > 1) {
-        atomicAdd(&out[(long long)gi * d.ldo + gj], v);
-        if ((d.sym & 1) && blockIdx.y != bx) atomicAdd(&out[(long long)gj * d.ldo + gi], v);
+        AccT* po = part + ((long long)split * gridDim.z + blockIdx.z) * part_stride;
+        po[(long long)gi * d.ldo + gj] = v;
+        if ((d.sym & 1) && blockIdx.y != bx) po[(long long)gj * d.ldo + gi] = v;
       } else {
         out[(long long)gi * d.ldo + gj] = v;
         if ((d.sym & 1) && blockIdx.y != bx) out[(long long)gj * d.ldo + gi] = v;
       }
     }
+  }
+}
+
+// out[prob] = sum over splits (ascending) of part[split][prob]
+__global__ void __launch_bounds__(256)
+k_gram_tn_reduce(const cpsd_gram_tn_desc* __restrict__ descs, const double* __restrict__ part,
+                 long long part_stride, int nsplit) {
+  const cpsd_gram_tn_desc d = descs[blockIdx.y];
+  double* out = reinterpret_cast<double*>(d.out);
+  const int total = d.p * d.q;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int i = e / d.q, j = e - i * d.q;
+    double acc = 0.0;
+    for (int s = 0; s < nsplit; ++s)
+      acc += part[((long long)s * gridDim.y + blockIdx.y) * part_stride + (long long)i * d.ldo + j];
+    out[(long long)i * d.ldo + j] = acc;
   }
 }
 
@@ -288,7 +307,7 @@ extern "C" int cpsd_gram_tn(const cpsd_gram_tn_desc* descs_dev, int nprob, int p
   if (nprob == 0) return CPSD_OK;
   CPSD_CHECK_ARG(nprob <= 65535, "gram_tn: nprob > 65535");
   dim3 grid((q_max + GT_TILE - 1) / GT_TILE, (p_max + GT_TILE - 1) / GT_TILE, nprob);
-  k_gram_tn<float><<<grid, 256, 0, stream>>>(descs_dev, grid.x, 1);
+  k_gram_tn<float><<<grid, 256, 0, stream>>>(descs_dev, grid.x, 1, nullptr, 0);
   CPSD_LAUNCH_CHECK();
   return CPSD_OK;
 }
@@ -302,23 +321,37 @@ extern "C" int cpsd_gram_tn_f64(const cpsd_gram_tn_desc* descs_dev, int nprob, i
   if (nprob == 0) return CPSD_OK;
   CPSD_CHECK_ARG(nprob <= 65535, "gram_tn_f64: nprob > 65535");
   dim3 grid((q_max + GT_TILE - 1) / GT_TILE, (p_max + GT_TILE - 1) / GT_TILE, nprob);
-  k_gram_tn<double><<<grid, 256, 0, stream>>>(descs_dev, grid.x, 1);
+  k_gram_tn<double><<<grid, 256, 0, stream>>>(descs_dev, grid.x, 1, nullptr, 0);
   CPSD_LAUNCH_CHECK();
   return CPSD_OK;
 }
 
-// fp64 accumulation with the segments of every problem split over nsplit CTAs per tile; the
-// outputs must be ZERO on entry (partial sums are added with fp64 atomics).
+// fp64 accumulation with the segments of every problem split over nsplit CTAs per tile.  The
+// partial tiles go to part_ws (nsplit * nprob * ldo_max * p_max doubles, see
+// cpsd_gram_tn_split_ws_elems) and are added in a fixed order: bit-reproducible.
+extern "C" long long cpsd_gram_tn_split_ws_elems(int nprob, int p_max, int ldo_max, int nsplit) {
+  return (long long)nsplit * nprob * ldo_max * p_max;
+}
+
 extern "C" int cpsd_gram_tn_f64_split(const cpsd_gram_tn_desc* descs_dev, int nprob, int p_max,
-                                      int q_max, int nsplit, cudaStream_t stream) {
-  CPSD_CHECK_ARG(nprob >= 0 && p_max > 0 && q_max > 0, "gram_tn_f64_split: bad dims");
+                                      int q_max, int ldo_max, int nsplit, double* part_ws,
+                                      cudaStream_t stream) {
+  CPSD_CHECK_ARG(nprob >= 0 && p_max > 0 && q_max > 0 && ldo_max >= q_max, "gram_tn_f64_split: bad dims");
   CPSD_CHECK_ARG(nsplit >= 1 && nsplit <= 64, "gram_tn_f64_split: nsplit must be in 1..64");
+  CPSD_CHECK_ARG(part_ws != nullptr || nsplit == 1, "gram_tn_f64_split: part_ws is NULL");
   if (nprob == 0) return CPSD_OK;
   CPSD_CHECK_ARG(nprob <= 65535, "gram_tn_f64_split: nprob > 65535");
   const int tx = (q_max + GT_TILE - 1) / GT_TILE;
   dim3 grid(tx * nsplit, (p_max + GT_TILE - 1) / GT_TILE, nprob);
-  k_gram_tn<double><<<grid, 256, 0, stream>>>(descs_dev, tx, nsplit);
+  const long long pstride = (long long)ldo_max * p_max;
+  k_gram_tn<double><<<grid, 256, 0, stream>>>(descs_dev, tx, nsplit, part_ws, pstride);
   CPSD_LAUNCH_CHECK();
+  if (nsplit > 1) {
+    int bx = (p_max * q_max + 255) / 256;
+    if (bx > 32) bx = 32;
+    k_gram_tn_reduce<<<dim3(bx, nprob), 256, 0, stream>>>(descs_dev, part_ws, pstride, nsplit);
+    CPSD_LAUNCH_CHECK();
+  }
   return CPSD_OK;
 }
 

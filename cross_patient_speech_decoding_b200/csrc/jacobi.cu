@@ -578,7 +578,8 @@ k_bj_inner_cross(float* __restrict__ K, int ldk, long long strideK, const int* _
   float2* cs = reinterpret_cast<float2*>(As + TS * TS);    // [64] (c, s) of the step
   float* dd = reinterpret_cast<float*>(cs + BS);           // [64] t * a_pq
   float* nrm = dd + BS;                                    // [128] column norms^2 of R
-  int* redmax = reinterpret_cast<int*>(nrm + TS);
+  float* nrm_part = nrm + TS;                              // [8][128] per-warp partial norms
+  int* redmax = reinterpret_cast<int*>(nrm_part + (NT / 32) * TS);
 
   const int pr = blockIdx.x, prob = blockIdx.y, npairs = gridDim.x;
   if (done && done[prob]) return;
@@ -677,8 +678,8 @@ k_bj_inner_cross(float* __restrict__ K, int ldk, long long strideK, const int* _
   __syncthreads();
   seen = warp_max(seen);
   if (lane == 0) atomicMax(redmax, __float_as_int(seen));
-  // column norms of R (rows are spread over the 8 warps)
-  for (int c = threadIdx.x; c < TS; c += NT) nrm[c] = 0.f;
+  // column norms of R (rows are spread over the 8 warps): per-warp partials, summed in a fixed
+  // order (shared-memory float atomics would make the last bit depend on the warp schedule)
   __syncthreads();
   {
     float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
@@ -689,10 +690,18 @@ k_bj_inner_cross(float* __restrict__ K, int ldk, long long strideK, const int* _
       n2 = fmaf(vJ0[i], vJ0[i], n2);
       n3 = fmaf(vJ1[i], vJ1[i], n3);
     }
-    atomicAdd(&nrm[lane], n0);
-    atomicAdd(&nrm[lane + 32], n1);
-    atomicAdd(&nrm[lane + 64], n2);
-    atomicAdd(&nrm[lane + 96], n3);
+    float* pw = nrm_part + warp * TS;
+    pw[lane] = n0;
+    pw[lane + 32] = n1;
+    pw[lane + 64] = n2;
+    pw[lane + 96] = n3;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < TS; c += NT) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) t += nrm_part[w * TS + c];
+    nrm[c] = t;
   }
   __syncthreads();
   if (threadIdx.x == 0 && sc > 0.f)
@@ -1136,7 +1145,7 @@ extern "C" int cpsd_eig_sym_block(float* K, int ld, long long stride, int n_pad,
   int* sweeps = iwork + nprob;
   const size_t smem_w = 2 * BS * TS * sizeof(float) + sizeof(StepBuf) + 32;
   const size_t smem_up = (TS * LDX + TS * TS) * sizeof(float);
-  const size_t smem_cross = TS * TS * sizeof(float) + BS * 12 + TS * 4 + 16;
+  const size_t smem_cross = TS * TS * sizeof(float) + BS * 12 + TS * 4 + (NT / 32) * TS * 4 + 16;
   CPSD_CUDA(cudaFuncSetAttribute(k_bj_inner_cross, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem_cross));
   CPSD_CUDA(cudaFuncSetAttribute(k_bj_within, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));

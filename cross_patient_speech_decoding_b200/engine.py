@@ -403,8 +403,10 @@ class CVEngine:
         if kernel == 'cpsd_gram_tn_f64':
             nsplit = min(16, max(1, 592 // max(nprob * tiles, 1)))
             if nsplit > 1:
-                out.zero_()
-                self.ctx.call('cpsd_gram_tn_f64_split', descs, nprob, p, q, nsplit)
+                ldo = out.shape[-1]
+                part = self.ws('gram_part', (int(self.ctx.lib.cpsd_gram_tn_split_ws_elems(
+                    nprob, p, ldo, nsplit)),), torch.float64)
+                self.ctx.call('cpsd_gram_tn_f64_split', descs, nprob, p, q, ldo, nsplit, ptr(part))
                 return
         self.ctx.call(kernel, descs, nprob, p, q)
 

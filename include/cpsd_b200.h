@@ -83,9 +83,11 @@ int cpsd_gram_tn(const cpsd_gram_tn_desc* descs, int nprob, int p_max, int q_max
 int cpsd_gram_tn_f64(const cpsd_gram_tn_desc* descs, int nprob, int p_max, int q_max,
                      cudaStream_t stream);
 /* fp64 accumulation, every problem's row segments dealt to nsplit CTAs per output tile (few
- * problems x many rows); outputs must be zero on entry (fp64 atomics). */
+ * problems x many rows); the partial tiles are staged in part_ws
+ * (cpsd_gram_tn_split_ws_elems doubles) and added in a fixed order (bit-reproducible). */
+long long cpsd_gram_tn_split_ws_elems(int nprob, int p_max, int ldo_max, int nsplit);
 int cpsd_gram_tn_f64_split(const cpsd_gram_tn_desc* descs, int nprob, int p_max, int q_max,
-                           int nsplit, cudaStream_t stream);
+                           int ldo_max, int nsplit, double* part_ws, cudaStream_t stream);
 /* (X - mu) W: PCA.transform, AlignCCA.transform (AlignCCA.py:93), MCCA transform_view
  * (AlignMCCA.py:110,125), JointPCA.transform (JointPCA.py:132,149); output rows land
  * directly in the pooled trials x (time*latent) matrix (cross_pt_decoders.py:260-270). */

@@ -2,7 +2,7 @@ import sys, os, numpy as np
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests/golden'); sys.path.insert(0, 'tests')
 import make_golden
 from cross_patient_speech_decoding_b200.engine import CVEngine
-for name in ['cca_p2_5fold', 'cca_p2_noisy', 'cca_p2_noisy', 'cca_p2_noisy']:
+for name in ['cca_p2_noisy', 'cca_p2_noisy', 'cca_p2_noisy']:
     cfg = make_golden.CONFIGS[name]
     pts, folds = make_golden.build_inputs(cfg)
     g = np.load('tests/golden/%s.npz' % name)
