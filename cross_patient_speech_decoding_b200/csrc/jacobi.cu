@@ -299,8 +299,7 @@ __device__ __forceinline__ void sym_block(T* As, const StepBuf* sb, int k, int l
 }
 
 template <typename T, int NP>
-__device__ __forceinline__ void tile_apply_sym(T* As, float* Vs, StepBuf* sb, int npairs_rt,
-                                               int vrows) {
+__device__ __forceinline__ void tile_apply_sym_A(T* As, StepBuf* sb, int npairs_rt) {
   const int npairs = NP > 0 ? NP : npairs_rt;
   // diagonal 2x2 blocks (the rotated pairs themselves)
   for (int k = threadIdx.x; k < npairs; k += blockDim.x) {
@@ -336,8 +335,17 @@ __device__ __forceinline__ void tile_apply_sym(T* As, float* Vs, StepBuf* sb, in
       if (l > k) sym_block<T>(As, sb, k, l);
     }
   }
+}
+
+// Eigenvector update of one step by the threads t0 .. blockDim.x-1 (the first t0 threads are
+// busy with the next step's rotations, see tile_sweep_full_sym).
+template <int NP>
+__device__ __forceinline__ void tile_apply_sym_V(float* Vs, const StepBuf* sb, int npairs_rt,
+                                                 int vrows, int t0) {
+  const int npairs = NP > 0 ? NP : npairs_rt;
   const int nv = vrows * npairs;
-  for (int b = threadIdx.x; b < nv; b += blockDim.x) {
+  if ((int)threadIdx.x < t0) return;
+  for (int b = threadIdx.x - t0; b < nv; b += blockDim.x - t0) {
     const int r = NP > 0 ? b / NP : b / npairs;
     const int l = b - r * npairs;
     const float cl = sb->cf[l], sl = sb->sf[l];
@@ -349,18 +357,33 @@ __device__ __forceinline__ void tile_apply_sym(T* As, float* Vs, StepBuf* sb, in
   }
 }
 
+// One sweep.  Per step: [matrix update with rot(s)] | barrier | [rot(s+1) on the first 64
+// threads  ||  eigenvector update with rot(s) on the others] | barrier -- the fp64
+// sqrt / division / rsqrt chain of the next step's rotations hides behind the eigenvector
+// update of the current one (two StepBufs alternate).
 template <typename T>
-__device__ float tile_sweep_full_sym(T* As, float* Vs, StepBuf* sb, int m, int vrows, float skip_thr,
+__device__ float tile_sweep_full_sym(T* As, float* Vs, StepBuf* sb2, int m, int vrows, float skip_thr,
                                      int* redmax) {
-  float seen = 0.f;
   const int npairs = m >> 1;
+  const int t0 = (vrows > 0 && (int)blockDim.x >= 4 * BS) ? BS : 0;   // threads reserved for rot(s+1)
+  int cur = 0;
+  float seen = tile_rotations_sym<T>(As, sb2, 0, m, npairs, npairs - 1, skip_thr);
+  __syncthreads();
   for (int s = 0; s < m; ++s) {
-    const int nrot = (s & 1) ? npairs : npairs - 1;
-    seen = fmaxf(seen, tile_rotations_sym<T>(As, sb, s, m, npairs, nrot, skip_thr));
+    StepBuf* sb = sb2 + cur;
+    if (m == TS) tile_apply_sym_A<T, TS / 2>(As, sb, npairs);
+    else tile_apply_sym_A<T, 0>(As, sb, npairs);
     __syncthreads();
-    if (m == TS) tile_apply_sym<T, TS / 2>(As, Vs, sb, npairs, vrows);
-    else tile_apply_sym<T, 0>(As, Vs, sb, npairs, vrows);
+    if (s + 1 < m) {
+      const int nrot = ((s + 1) & 1) ? npairs : npairs - 1;
+      seen = fmaxf(seen, tile_rotations_sym<T>(As, sb2 + (cur ^ 1), s + 1, m, npairs, nrot, skip_thr));
+    }
+    if (vrows > 0) {
+      if (m == TS) tile_apply_sym_V<TS / 2>(Vs, sb, npairs, vrows, t0);
+      else tile_apply_sym_V<0>(Vs, sb, npairs, vrows, t0);
+    }
     __syncthreads();
+    cur ^= 1;
   }
   if (threadIdx.x == 0) *redmax = 0;
   __syncthreads();
@@ -398,8 +421,8 @@ k_eig_tile(const T* __restrict__ A, int lda, long long strideA, const int* __res
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* As = reinterpret_cast<T*>(smem_raw);                  // upper triangle, rows of LDS_SYM
   float* Vs = reinterpret_cast<float*>(As + TS * LDS_SYM);
-  StepBuf* sb = reinterpret_cast<StepBuf*>(Vs + TS * TS);
-  int* redmax = reinterpret_cast<int*>(sb + 1);
+  StepBuf* sb = reinterpret_cast<StepBuf*>(Vs + TS * TS);   // two of them (alternating steps)
+  int* redmax = reinterpret_cast<int*>(sb + 2);
   int* rank = redmax + 1;  // TS ints
 
   const int prob = blockIdx.x;
@@ -1054,7 +1077,7 @@ __global__ void k_select_k(const float* __restrict__ evals, int ld_e, const int*
 // C ABI
 // =======================================================================================
 static size_t tile_smem_bytes(size_t elem = sizeof(float)) {
-  return TS * LDS_SYM * elem + TS * TS * sizeof(float) + sizeof(StepBuf) + (1 + TS) * sizeof(int) + 16;
+  return TS * LDS_SYM * elem + TS * TS * sizeof(float) + 2 * sizeof(StepBuf) + (1 + TS) * sizeof(int) + 16;
 }
 
 extern "C" int cpsd_eig_sym_small(const float* A, int lda, long long strideA, const int* n_dev,
