@@ -14,8 +14,8 @@ def cv_align_decode(target, cross, folds, method='mcca', **kw):
     the ``(D, lab, lab_full)`` triples of the reference's ``decoding_data_from_dict``
     (alignment/alignment_utils.py:127-157).  Returns a dict with ``y_pred`` (one array per
     fold), ``k2`` and the bytes moved host<->device.  ``method``: 'mcca'
-    (crossPtDecoder_mcca), 'cca' (crossPtDecoder_sepAlign + AlignCCA) or 'none'
-    (crossPtDecoder_sepDimRed); the decoder is PCA(decoder_var) -> one-vs-rest linear SVM.
+    (crossPtDecoder_mcca), 'jointpca' (crossPtDecoder_jointDimRed + JointPCA), 'cca'
+    (crossPtDecoder_sepAlign + AlignCCA) or 'none' (crossPtDecoder_sepDimRed); the decoder is PCA(decoder_var) -> one-vs-rest linear SVM.
     """
     from .engine import CVEngine
     eng = CVEngine(target, cross, method=method, **kw)

@@ -108,6 +108,9 @@ _SIGS = {
     'cpsd_mcca_mask': [_P, c_int, c_ll, _P, c_int, _P, _P, c_int, c_int, _P, _P, _P, c_int, _P],
     'cpsd_mcca_mask_idx': [_P, c_int, c_ll, _P, c_int, _P, _P, _P, c_int, c_int, _P, _P, _P, c_int,
                            _P],
+    'cpsd_joint_cov': [_P, _P, _P, c_int, _P, c_int, c_int, _P],
+    'cpsd_joint_rhs': [_P, _P, _P, c_int, _P, c_int, c_ll, _P, c_int, c_int, c_int, _P, c_int, c_ll,
+                       c_int, _P],
     'cpsd_mcca_build': [_P, c_int, c_ll, _P, c_int, c_int, c_float, _P, c_int, c_ll, _P, _P, _P,
                         c_int, _P, c_int, _P],
     'cpsd_mcca_build_split': [_P, c_int, c_ll, _P, c_int, c_ll, _P, _P, c_int, c_int, c_float, _P,

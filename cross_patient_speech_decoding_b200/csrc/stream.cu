@@ -301,7 +301,77 @@ k_region_mean_f64(const double* __restrict__ data, int nelec, int T, const int* 
   }
 }
 
+// ---- JointPCA (alignment/JointPCA.py:165-211) --------------------------------------------
+// G (n x n fp64): Gram of the channel-concatenated class averages, only the blocks u <= v are
+// stored (diagonal blocks completely); s (n, fp32): column sums; nrows: rows of the matrix.
+__device__ __forceinline__ double gsym(const double* G, int n, int i, int j) {
+  return (i <= j) ? G[(long long)i * n + j] : G[(long long)j * n + i];
+}
+
+// cov[i][j] = (G_ij - nrows m_i m_j) / (nrows - 1), m = s / nrows: sklearn PCA's covariance of
+// the concatenated matrix, written as fp32 (n_pad x n_pad, zero padded)
+__global__ void __launch_bounds__(256)
+k_joint_cov(const double* __restrict__ G, const float* __restrict__ s, const int* __restrict__ nrows,
+            int n, float* __restrict__ cov, int n_pad) {
+  const int f = blockIdx.y;
+  const double* Gf = G + (long long)f * n * n;
+  const float* sf = s + (long long)f * n;
+  float* cf = cov + (long long)f * n_pad * n_pad;
+  const double nr = (double)nrows[f];
+  const long long total = (long long)n_pad * n_pad;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e / n_pad), j = (int)(e - (long long)i * n_pad);
+    float v = 0.f;
+    if (i < n && j < n)
+      v = (float)((gsym(Gf, n, i, j) - (double)sf[i] * (double)sf[j] / nr) / (nr - 1.0));
+    cf[e] = v;
+  }
+}
+
+// rhs[f][view] (C x k, fp64, row stride ldr) = X_p^T (M - 1 mean^T) V_k
+//   = sum_c (G[off + r][c] - s[off + r] s[c] / nrows) V[c][j]       grid (C_max, B * P)
+__global__ void __launch_bounds__(128)
+k_joint_rhs(const double* __restrict__ G, const float* __restrict__ s, const int* __restrict__ nrows,
+            int n, const float* __restrict__ V, int ldv, long long strideV, const int* __restrict__ coff,
+            int P, int k, double* __restrict__ rhs, int ldr, long long strideR) {
+  const int fp = blockIdx.y, f = fp / P, p = fp - f * P;
+  const int C = coff[p + 1] - coff[p], r = blockIdx.x;
+  if (r >= C) return;
+  const int j = threadIdx.x;
+  const int gi = coff[p] + r;
+  const double* Gf = G + (long long)f * n * n;
+  const float* sf = s + (long long)f * n;
+  const float* Vf = V + (long long)f * strideV;
+  const double si = (double)sf[gi] / (double)nrows[f];
+  double acc = 0.0;
+  if (j < k)
+    for (int c = 0; c < n; ++c)
+      acc = fma(gsym(Gf, n, gi, c) - si * (double)sf[c], (double)Vf[(long long)c * ldv + j], acc);
+  if (j < k) rhs[(long long)fp * strideR + (long long)r * ldr + j] = acc;
+}
+
 }  // namespace
+
+extern "C" int cpsd_joint_cov(const double* G, const float* s, const int* nrows, int n, float* cov,
+                              int n_pad, int nfold, cudaStream_t stream) {
+  CPSD_CHECK_ARG(n > 0 && n_pad >= n && nfold >= 0, "joint_cov: bad dims");
+  if (nfold == 0) return CPSD_OK;
+  k_joint_cov<<<dim3(148, nfold), 256, 0, stream>>>(G, s, nrows, n, cov, n_pad);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
+
+extern "C" int cpsd_joint_rhs(const double* G, const float* s, const int* nrows, int n, const float* V,
+                              int ldv, long long strideV, const int* coff, int P, int C_max, int k,
+                              double* rhs, int ldr, long long strideR, int nfold, cudaStream_t stream) {
+  CPSD_CHECK_ARG(n > 0 && P > 0 && k > 0 && k <= 128 && C_max > 0, "joint_rhs: k must be in 1..128");
+  if (nfold == 0) return CPSD_OK;
+  k_joint_rhs<<<dim3(C_max, nfold * P), 128, 0, stream>>>(G, s, nrows, n, V, ldv, strideV, coff, P, k, rhs,
+                                                         ldr, strideR);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
 
 // Electrode subsampling on resident trials (scripts/aligned_decode_{grid,pitch}_subsample.py
 // index the channel axis with the lists made by processing_utils/{grid_subsampling,

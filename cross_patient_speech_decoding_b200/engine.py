@@ -109,7 +109,7 @@ class CVEngine:
               use_tensor_cores, pool_solver, topk_block, topk_iters, topk_tol, topk_rounds, n_lanes):
         self.method = method
         if n_comp is None:
-            n_comp = 30 if method == 'mcca' else 0.9
+            n_comp = 30 if method == 'mcca' else (40 if method == 'jointpca' else 0.9)
         self.n_comp = n_comp
         self.regs = regs
         self.pca_var = pca_var
@@ -137,7 +137,7 @@ class CVEngine:
         self.topk_iters = int(topk_iters)
         self.topk_tol = float(topk_tol)
         self.topk_rounds = int(topk_rounds)
-        if method == 'mcca':
+        if method in ('mcca', 'jointpca'):
             assert isinstance(n_comp, (int, np.integer)) and n_comp >= 1
         views = [target] + list(cross)
         ids, self.vocab = class_ids([v[2] if v[2] is not None else v[1] for v in views])
@@ -281,11 +281,14 @@ class CVEngine:
             maps = self.ws(tag + '_tkm', (nb + 64,), torch.uint8)
             mp = (maps.data_ptr() + 63) & ~63
             key = (K.data_ptr(), tcw.data_ptr(), mp, n_pad, nprob)
-            if getattr(self, '_tkc_key', None) != key:
-                self._tkc_stage = torch.empty((nb + 64,), dtype=torch.uint8).pin_memory()
+            cache = getattr(self, '_tkc_key', None)
+            if not isinstance(cache, dict):
+                cache = self._tkc_key = {}
+            if cache.get(tag, (None, None))[0] != key:
+                stage = torch.empty((nb + 64,), dtype=torch.uint8).pin_memory()
                 ctx.call('cpsd_topk_tc_encode', ptr(K), n_pad, n_pad * n_pad, n_pad, nprob, ptr(tcw),
-                         ctypes.c_void_p(mp), ctypes.c_void_p(self._tkc_stage.data_ptr()))
-                self._tkc_key = key
+                         ctypes.c_void_p(mp), ctypes.c_void_p(stage.data_ptr()))
+                cache[tag] = (key, stage)
         for rnd in range(self.topk_rounds):
             if tc:
                 ctx.call('cpsd_eig_sym_topk_tc', ptr(K), n_pad, n_pad * n_pad, n_pad, _p(n_dev), 0,
@@ -463,7 +466,7 @@ class CVEngine:
             self._target_trial_grams()
             self._keep = [pk]                # staging of the kernels still in flight
         else:
-            if self.P > 1:
+            if self.P > 1 and self.method != 'jointpca':
                 self._cross_pca()
             torch.cuda.current_stream(self.ctx.device).synchronize()
 
@@ -613,7 +616,7 @@ class CVEngine:
         batches = [folds[s:s + size] for s in range(0, len(folds), size)]   # as a full one)
         results = [None] * len(batches)
         self._ensure_ready()
-        if self.method == 'mcca':
+        if self.method in ('mcca', 'jointpca'):
             # every batch is a generator that yields right before each blocking read-back; the
             # lanes are advanced round-robin, so while one lane waits for its GPU results the
             # host packs and queues the other lane's batch on its own stream
@@ -691,7 +694,7 @@ class CVEngine:
         self._ensure_ready()
         for s0 in range(0, len(folds), size):
             batch = folds[s0:s0 + size]
-            if self.method == 'mcca':
+            if self.method in ('mcca', 'jointpca'):
                 res = yield from self._mcca_start(batch, return_details)
             else:
                 res = self._batch_cca(batch, return_details)
@@ -906,7 +909,8 @@ class CVEngine:
         ctx, T, P, Cm = self.ctx, self.T, self.P, self.Cmax
         B = len(batch)
         Q = int(self.n_comp)
-        use_rank = 0 < self.pca_var < 1
+        joint = self.method == 'jointpca'
+        use_rank = (0 < self.pca_var < 1) and not joint
         R = Q if use_rank else Cm      # pca_var == 1: no rank reduction (mvlearn _mcca_gevp)
         tv = self.views[0]
         launches0 = ctx.launches()
@@ -974,56 +978,64 @@ class CVEngine:
         o_segdst = pk.add_ints(np.arange(int(Ksa.max()), dtype=np.int32) * T)
         cdims = np.array([vw.C for vw in self.views], dtype=np.int64)
         o_cdim = pk.add_ints(np.tile(cdims, B))
-        ranks = np.zeros((B, P), dtype=np.int32)
-        ranks[:, 1:] = self.cross_rank[None, :]
-        o_rank = pk.add_ints(ranks)
-        # slot of every (fold, view) problem; solve list = targets + cache misses
         n_padC = 128 if Cm <= 128 else _ceil(Cm, 128)
-        vs = self._view_slots(B, n_padC, Cm)
-        if vs['next'] + B * (P - 1) > vs['cap']:
-            vs['keys'].clear()
-            vs['next'] = vs['res']
         slot = np.zeros((B, P), dtype=np.int64)
-        slot[:, 0] = fold_of
-        solve = [(f, 0, f) for f in range(B)]
-        pending = {}
-        if P > 1:
-            rows_u = np.zeros((len(shared_u), P - 1), dtype=np.int64)
+        if joint:
+            coff = np.concatenate([[0], np.cumsum(cdims)]).astype(np.int64)   # channel offsets
+            nJ = int(coff[-1])
+            nJ_pad = _ceil(nJ, 128)
+            o_nj = pk.add_ints(np.full(B, nJ, dtype=np.int32))
+        else:
+            ranks = np.zeros((B, P), dtype=np.int32)
+            ranks[:, 1:] = self.cross_rank[None, :]
+            o_rank = pk.add_ints(ranks)
+            # slot of every (fold, view) problem; solve list = targets + cache misses
+            n_padC = 128 if Cm <= 128 else _ceil(Cm, 128)
+            vs = self._view_slots(B, n_padC, Cm)
+            if vs['next'] + B * (P - 1) > vs['cap']:
+                vs['keys'].clear()
+                vs['next'] = vs['res']
+            slot = np.zeros((B, P), dtype=np.int64)
+            slot[:, 0] = fold_of
+            solve = [(f, 0, f) for f in range(B)]
+            pending = {}
+            if P > 1:
+                rows_u = np.zeros((len(shared_u), P - 1), dtype=np.int64)
+                for u, ku in enumerate(keys_u):
+                    for v in range(1, P):
+                        key = (v, ku)
+                        sl = vs['keys'].get(key)
+                        if sl is None:
+                            sl = vs['next'] + len(pending)
+                            pending[key] = sl
+                            solve.append((int(first[u]), v, sl))
+                        rows_u[u, v - 1] = sl
+                slot[:, 1:] = rows_u[inv]
+            o_slot = pk.add_ints(slot)
+            o_cds = pk.add_ints([self.views[v].C for _, v, _ in solve])
+            # cross-block cache slot of every fold (one slot per shared class set)
+            XR = (P - 1) * R
+            xc = self._xcache(R, XR)
+            newx = []                       # (cache slot, first fold with that class set)
+            xs_of = {}
+            if len(xc['keys']) + B > xc['cap']:
+                xc['keys'].clear()
+            xs_u = np.zeros(len(shared_u), dtype=np.int32)
             for u, ku in enumerate(keys_u):
-                for v in range(1, P):
-                    key = (v, ku)
-                    sl = vs['keys'].get(key)
-                    if sl is None:
-                        sl = vs['next'] + len(pending)
-                        pending[key] = sl
-                        solve.append((int(first[u]), v, sl))
-                    rows_u[u, v - 1] = sl
-            slot[:, 1:] = rows_u[inv]
-        o_slot = pk.add_ints(slot)
-        o_cds = pk.add_ints([self.views[v].C for _, v, _ in solve])
-        # cross-block cache slot of every fold (one slot per shared class set)
-        XR = (P - 1) * R
-        xc = self._xcache(R, XR)
-        newx = []                       # (cache slot, first fold with that class set)
-        xs_of = {}
-        if len(xc['keys']) + B > xc['cap']:
-            xc['keys'].clear()
-        xs_u = np.zeros(len(shared_u), dtype=np.int32)
-        for u, ku in enumerate(keys_u):
-            xs = xc['keys'].get(ku)
-            if xs is None:
-                xs = len(xc['keys']) + len(xs_of)
-                xs_of[ku] = xs
-                newx.append((xs, int(first[u])))
-            xs_u[u] = xs
-        xslot = xs_u[inv]
-        keys = [keys_u[u] for u in inv]
-        o_xslot = pk.add_ints(xslot)
+                xs = xc['keys'].get(ku)
+                if xs is None:
+                    xs = len(xc['keys']) + len(xs_of)
+                    xs_of[ku] = xs
+                    newx.append((xs, int(first[u])))
+                xs_u[u] = xs
+            xslot = xs_u[inv]
+            keys = [keys_u[u] for u in inv]
+            o_xslot = pk.add_ints(xslot)
         self.stats['host_pack_ms'] = self.stats.get('host_pack_ms', 0.0) + \
             1e3 * (time.perf_counter() - t_pack)
         yield 'host'
         t_pack = time.perf_counter()
-        downdate = use_rank and getattr(self, 'tg', None) is not None and n_padC == 128
+        downdate = (not joint) and use_rank and getattr(self, 'tg', None) is not None and n_padC == 128
         if downdate:
             use_te = int(n_te_a.sum()) <= int(n_tr_a.sum())
             La, Lm = (TE, mte) if use_te else (TR, mtr)
@@ -1089,11 +1101,6 @@ class CVEngine:
 
         # ---- descriptors, stage A (filled column-wise: one numpy op per field)
         cmT, r_cm = self._class_means_target(pk, tabs, B, Kmax)
-        Gt, gram_c = self.scatter('m_Gt', B, n_padC)
-        nS = len(solve)
-        mu = vs['mu']
-        cov, _ = self.scatter('m_cov', nS, n_padC)
-        esz = cov.element_size()
         fi = np.arange(B, dtype=np.int64)
         # base address of the class-mean array of every (fold, view)
         cmb = np.empty((B, P), dtype=np.int64)
@@ -1101,97 +1108,132 @@ class CVEngine:
         for v in range(1, P):
             cmb[:, v] = addr(self.cm[v])
         segb = ib + 4 * o_seg                       # (B, P) segment-table addresses
-        mub = addr(mu) + 4 * Cm * slot               # (B, P) mean vectors (slots)
         Ksa = np.asarray(Ks, dtype=np.int64)
         o_tr = ib + 4 * o_trv
-        r_gt = np.zeros(B, dtype=_lib.GRAM_TN_DESC)
-        r_gt['A'] = r_gt['B'] = addr(tv.X)
-        r_gt['segA'] = r_gt['segB'] = o_tr
-        r_gt['out'] = addr(Gt) + Gt.element_size() * n_padC * n_padC * fi
-        r_gt['nseg'], r_gt['seg_len'] = n_tr, T
-        r_gt['p'] = r_gt['q'] = r_gt['lda'] = r_gt['ldb'] = tv.C
-        r_gt['ldo'], r_gt['sym'], r_gt['alpha'] = n_padC, 1, 1.0
-        sf = np.array([t[0] for t in solve], dtype=np.int64)
-        sv = np.array([t[1] for t in solve], dtype=np.int64)
-        ssl = np.array([t[2] for t in solve], dtype=np.int64)
-        sC = cdims[sv]
-        r_mu = np.zeros(nS, dtype=_lib.COLSUM_DESC)
-        r_mu['A'], r_mu['segA'], r_mu['out'] = cmb[sf, sv], segb[sf, sv], addr(mu) + 4 * Cm * ssl
-        r_mu['nseg'], r_mu['seg_len'], r_mu['p'], r_mu['lda'] = Ksa[sf], T, sC, sC
-        r_mu['alpha'] = 1.0 / (Ksa[sf] * T)
-        r_cov = np.zeros(nS, dtype=_lib.GRAM_TN_DESC)
-        r_cov['A'] = r_cov['B'] = cmb[sf, sv]
-        r_cov['segA'] = r_cov['segB'] = segb[sf, sv]
-        r_cov['muA'] = r_cov['muB'] = addr(mu) + 4 * Cm * ssl
-        r_cov['out'] = addr(cov) + esz * n_padC * n_padC * np.arange(nS, dtype=np.int64)
-        r_cov['nseg'], r_cov['seg_len'] = Ksa[sf], T
-        r_cov['p'] = r_cov['q'] = r_cov['lda'] = r_cov['ldb'] = sC
-        r_cov['ldo'], r_cov['sym'], r_cov['alpha'] = n_padC, 1, 1.0
-        d_cm, d_gt = pk.add_descs(r_cm), pk.add_descs(r_gt)
-        d_mu, d_cov = pk.add_descs(r_mu), pk.add_descs(r_cov)
-        # reduced views
-        Vr = self.ws('m_Vr', (B * P, Cm, R))
-        d2 = self.ws('m_d2', (B * P, R))
-        r_eff = self.ws('m_reff', (B * P,), I32)
-        self.stats['host_pack_ms'] = self.stats.get('host_pack_ms', 0.0) + \
-            1e3 * (time.perf_counter() - t_pack)
-        yield 'host'
-        t_pack = time.perf_counter()
-        # reduced coordinates of the condition averages: the target's per fold (Zt), the cross
-        # patients' once per shared class set (Zx, cached with their cross-scatter block Gxx)
-        nX = len(newx)
-        KTc = xc['KT']
-        Zt = self.ws('m_Zt', (B, KTmax, R))
-        Gtx = self.ws('m_Gtx', (B, R, P * R))
-        Zx, Gxx = xc['Zx'], xc['Gxx']
-        npz = B + nX * (P - 1)
-        r_pz = np.zeros(npz, dtype=_lib.PROJ_DESC)
-        # targets
-        r_pz['X'][:B], r_pz['seg_src'][:B] = cmb[:, 0], segb[:, 0]
-        r_pz['mu'][:B], r_pz['W'][:B] = mub[:, 0], addr(Vr) + 4 * Cm * R * P * fi
-        r_pz['Y'][:B] = addr(Zt) + 4 * KTmax * R * fi
-        r_pz['nseg'][:B], r_pz['C'][:B], r_pz['ldx'][:B], r_pz['ldy'][:B] = Ksa, cdims[0], cdims[0], R
-        j = B
-        for xs, f in newx:
-            for v in range(1, P):
-                r_pz[j] = (cmb[f, v], segb[f, v], 0, mub[f, v], addr(Vr, (f * P + v) * Cm * R),
-                           addr(Zx, xs * KTc * XR + (v - 1) * R), Ks[f], T, cdims[v], R, cdims[v],
-                           R, XR, 0)
-                j += 1
-        r_pz['seg_dst'], r_pz['seg_len'], r_pz['q'], r_pz['ldw'] = ib + 4 * o_segdst, T, R, R
-        ng = (2 * B if XR else B) + nX
-        r_g = np.zeros(ng, dtype=_lib.GRAM_TN_DESC)
-        zt = addr(Zt) + 4 * KTmax * R * fi
-        r_g['A'][:B] = r_g['B'][:B] = zt
-        r_g['out'][:B] = addr(Gtx) + 4 * R * P * R * fi
-        r_g['seg_len'][:B] = Ksa * T
-        r_g['p'][:B] = r_g['q'][:B] = r_g['lda'][:B] = r_g['ldb'][:B] = R
-        r_g['sym'][:B] = 1
-        if XR:
-            r_g['A'][B:2 * B] = zt
-            r_g['B'][B:2 * B] = addr(Zx) + 4 * KTc * XR * xslot.astype(np.int64)
-            r_g['out'][B:2 * B] = addr(Gtx) + 4 * (R * P * R * fi + R)
-            r_g['seg_len'][B:2 * B] = Ksa * T
-            r_g['p'][B:2 * B] = r_g['lda'][B:2 * B] = R
-            r_g['q'][B:2 * B] = r_g['ldb'][B:2 * B] = XR
-            j = 2 * B
-            for xs, f in newx:
-                zx = addr(Zx, xs * KTc * XR)
-                r_g[j] = (zx, zx, 0, 0, 0, 0, addr(Gxx, xs * XR * XR), 1, Ks[f] * T, XR, XR, XR, XR,
-                          XR, 1, 1.0, 0)
-                j += 1
-        r_g['segA'] = r_g['segB'] = pk.iaddr(pk.o_zero)
-        r_g['nseg'], r_g['alpha'] = 1, 1.0
-        r_g['ldo'][:2 * B if XR else B] = P * R
-        d_pz, d_g = pk.add_descs(r_pz), pk.add_descs(r_g)
-        # pooled projection
-        # size of the reduced GEVP: the target's rank is only known on the device (<= R), the
-        # cross patients' ranks are fold-invariant and known here
-        if use_rank:
-            n_m_max = R + int(np.minimum(self.cross_rank, R).sum())
+        if joint:
+            # ---- JointPCA (alignment/JointPCA.py:165-211): per fold the Gram of the channel-
+            # concatenated class averages (fp64, upper blocks), its column sums, the PCA of the
+            # concatenation and one least-squares read-in matrix per patient
+            mub = np.zeros((B, P), dtype=np.int64)             # no centring at transform time
+            Gj = self.ws('j_G', (B, nJ, nJ), torch.float64)
+            sj = self.ws('j_s', (B, nJ))
+            pairs = [(u, v) for u in range(P) for v in range(u, P)]
+            npair = len(pairs)
+            pu = np.array([p_[0] for p_ in pairs], dtype=np.int64)
+            pv = np.array([p_[1] for p_ in pairs], dtype=np.int64)
+            r_jg = np.zeros(B * npair, dtype=_lib.GRAM_TN_DESC)
+            ff = np.repeat(fi, npair)
+            uu, vv = np.tile(pu, B), np.tile(pv, B)
+            r_jg['A'], r_jg['B'] = cmb[ff, uu], cmb[ff, vv]
+            r_jg['segA'], r_jg['segB'] = segb[ff, uu], segb[ff, vv]
+            r_jg['out'] = addr(Gj) + 8 * (nJ * nJ * ff + coff[uu] * nJ + coff[vv])
+            r_jg['nseg'], r_jg['seg_len'] = Ksa[ff], T
+            r_jg['p'] = r_jg['lda'] = cdims[uu]
+            r_jg['q'] = r_jg['ldb'] = cdims[vv]
+            r_jg['ldo'], r_jg['sym'], r_jg['alpha'] = nJ, (uu == vv).astype(np.int32), 1.0
+            r_js = np.zeros(B * P, dtype=_lib.COLSUM_DESC)
+            pf_, pv_ = np.repeat(fi, P), np.tile(np.arange(P, dtype=np.int64), B)
+            r_js['A'], r_js['segA'] = cmb.ravel(), segb.ravel()
+            r_js['out'] = addr(sj) + 4 * (nJ * pf_ + coff[pv_])
+            r_js['nseg'], r_js['seg_len'], r_js['p'], r_js['lda'] = Ksa[pf_], T, cdims[pv_], cdims[pv_]
+            r_js['alpha'] = 1.0
+            d_cm = pk.add_descs(r_cm)
+            d_jg, d_js = pk.add_descs(r_jg), pk.add_descs(r_js)
         else:
-            n_m_max = sum(min(R, vw.C) for vw in self.views)
-        n_padM = 128 if n_m_max <= 128 else _ceil(n_m_max, 128)
+            Gt, gram_c = self.scatter('m_Gt', B, n_padC)
+            nS = len(solve)
+            mu = vs['mu']
+            cov, _ = self.scatter('m_cov', nS, n_padC)
+            esz = cov.element_size()
+            mub = addr(mu) + 4 * Cm * slot               # (B, P) mean vectors (slots)
+            r_gt = np.zeros(B, dtype=_lib.GRAM_TN_DESC)
+            r_gt['A'] = r_gt['B'] = addr(tv.X)
+            r_gt['segA'] = r_gt['segB'] = o_tr
+            r_gt['out'] = addr(Gt) + Gt.element_size() * n_padC * n_padC * fi
+            r_gt['nseg'], r_gt['seg_len'] = n_tr, T
+            r_gt['p'] = r_gt['q'] = r_gt['lda'] = r_gt['ldb'] = tv.C
+            r_gt['ldo'], r_gt['sym'], r_gt['alpha'] = n_padC, 1, 1.0
+            sf = np.array([t[0] for t in solve], dtype=np.int64)
+            sv = np.array([t[1] for t in solve], dtype=np.int64)
+            ssl = np.array([t[2] for t in solve], dtype=np.int64)
+            sC = cdims[sv]
+            r_mu = np.zeros(nS, dtype=_lib.COLSUM_DESC)
+            r_mu['A'], r_mu['segA'], r_mu['out'] = cmb[sf, sv], segb[sf, sv], addr(mu) + 4 * Cm * ssl
+            r_mu['nseg'], r_mu['seg_len'], r_mu['p'], r_mu['lda'] = Ksa[sf], T, sC, sC
+            r_mu['alpha'] = 1.0 / (Ksa[sf] * T)
+            r_cov = np.zeros(nS, dtype=_lib.GRAM_TN_DESC)
+            r_cov['A'] = r_cov['B'] = cmb[sf, sv]
+            r_cov['segA'] = r_cov['segB'] = segb[sf, sv]
+            r_cov['muA'] = r_cov['muB'] = addr(mu) + 4 * Cm * ssl
+            r_cov['out'] = addr(cov) + esz * n_padC * n_padC * np.arange(nS, dtype=np.int64)
+            r_cov['nseg'], r_cov['seg_len'] = Ksa[sf], T
+            r_cov['p'] = r_cov['q'] = r_cov['lda'] = r_cov['ldb'] = sC
+            r_cov['ldo'], r_cov['sym'], r_cov['alpha'] = n_padC, 1, 1.0
+            d_cm, d_gt = pk.add_descs(r_cm), pk.add_descs(r_gt)
+            d_mu, d_cov = pk.add_descs(r_mu), pk.add_descs(r_cov)
+            # reduced views
+            Vr = self.ws('m_Vr', (B * P, Cm, R))
+            d2 = self.ws('m_d2', (B * P, R))
+            r_eff = self.ws('m_reff', (B * P,), I32)
+            self.stats['host_pack_ms'] = self.stats.get('host_pack_ms', 0.0) + \
+                1e3 * (time.perf_counter() - t_pack)
+            yield 'host'
+            t_pack = time.perf_counter()
+            # reduced coordinates of the condition averages: the target's per fold (Zt), the cross
+            # patients' once per shared class set (Zx, cached with their cross-scatter block Gxx)
+            nX = len(newx)
+            KTc = xc['KT']
+            Zt = self.ws('m_Zt', (B, KTmax, R))
+            Gtx = self.ws('m_Gtx', (B, R, P * R))
+            Zx, Gxx = xc['Zx'], xc['Gxx']
+            npz = B + nX * (P - 1)
+            r_pz = np.zeros(npz, dtype=_lib.PROJ_DESC)
+            # targets
+            r_pz['X'][:B], r_pz['seg_src'][:B] = cmb[:, 0], segb[:, 0]
+            r_pz['mu'][:B], r_pz['W'][:B] = mub[:, 0], addr(Vr) + 4 * Cm * R * P * fi
+            r_pz['Y'][:B] = addr(Zt) + 4 * KTmax * R * fi
+            r_pz['nseg'][:B], r_pz['C'][:B], r_pz['ldx'][:B], r_pz['ldy'][:B] = Ksa, cdims[0], cdims[0], R
+            j = B
+            for xs, f in newx:
+                for v in range(1, P):
+                    r_pz[j] = (cmb[f, v], segb[f, v], 0, mub[f, v], addr(Vr, (f * P + v) * Cm * R),
+                               addr(Zx, xs * KTc * XR + (v - 1) * R), Ks[f], T, cdims[v], R, cdims[v],
+                               R, XR, 0)
+                    j += 1
+            r_pz['seg_dst'], r_pz['seg_len'], r_pz['q'], r_pz['ldw'] = ib + 4 * o_segdst, T, R, R
+            ng = (2 * B if XR else B) + nX
+            r_g = np.zeros(ng, dtype=_lib.GRAM_TN_DESC)
+            zt = addr(Zt) + 4 * KTmax * R * fi
+            r_g['A'][:B] = r_g['B'][:B] = zt
+            r_g['out'][:B] = addr(Gtx) + 4 * R * P * R * fi
+            r_g['seg_len'][:B] = Ksa * T
+            r_g['p'][:B] = r_g['q'][:B] = r_g['lda'][:B] = r_g['ldb'][:B] = R
+            r_g['sym'][:B] = 1
+            if XR:
+                r_g['A'][B:2 * B] = zt
+                r_g['B'][B:2 * B] = addr(Zx) + 4 * KTc * XR * xslot.astype(np.int64)
+                r_g['out'][B:2 * B] = addr(Gtx) + 4 * (R * P * R * fi + R)
+                r_g['seg_len'][B:2 * B] = Ksa * T
+                r_g['p'][B:2 * B] = r_g['lda'][B:2 * B] = R
+                r_g['q'][B:2 * B] = r_g['ldb'][B:2 * B] = XR
+                j = 2 * B
+                for xs, f in newx:
+                    zx = addr(Zx, xs * KTc * XR)
+                    r_g[j] = (zx, zx, 0, 0, 0, 0, addr(Gxx, xs * XR * XR), 1, Ks[f] * T, XR, XR, XR, XR,
+                              XR, 1, 1.0, 0)
+                    j += 1
+            r_g['segA'] = r_g['segB'] = pk.iaddr(pk.o_zero)
+            r_g['nseg'], r_g['alpha'] = 1, 1.0
+            r_g['ldo'][:2 * B if XR else B] = P * R
+            d_pz, d_g = pk.add_descs(r_pz), pk.add_descs(r_g)
+            # pooled projection
+            # size of the reduced GEVP: the target's rank is only known on the device (<= R), the
+            # cross patients' ranks are fold-invariant and known here
+            if use_rank:
+                n_m_max = R + int(np.minimum(self.cross_rank, R).sum())
+            else:
+                n_m_max = sum(min(R, vw.C) for vw in self.views)
+            n_padM = 128 if n_m_max <= 128 else _ceil(n_m_max, 128)
         L = self.ws('m_L', (B * P, Cm, Q))
         if not align_only:
             Zall = self.ws('pool_Z', (B, n_pad, F))
@@ -1235,77 +1277,121 @@ class CVEngine:
         # class means of the target's train trials
         self.mark('class_mean')
         ctx.call('cpsd_class_mean', pk.daddr(d_cm), B, Kmax, T * tv.C)
-        # signal ranks (cross ranks are fold-invariant and come with the int table)
-        ctx.call('cpsd_copy_rows', ctypes_int_ptr(pk.iaddr(o_rank)), B * P, 0, ptr(rank_dev),
-                 B * P, 0, ptr(None), 0, 1, B * P, 1, 1)
-        self.mark('align_scatter_eig')
-        if Cm < n_padC:
-            cov.zero_()
-            Gt.zero_()
-        if use_rank:
-            if downdate:     # train-set Gram = all-trials Gram - held-out trials (or sum of train)
-                ctx.call('cpsd_sum_mats_f64', ptr(self.tg['all']) if use_te else ptr(None),
-                         ptr(self.tg['trial']), 128 * 128, ctypes_int_ptr(pk.iaddr(o_lptr)),
-                         ctypes_int_ptr(pk.iaddr(o_list)), -1.0 if use_te else 1.0, ptr(Gt),
-                         128 * 128, 128 * 128, B)
-            else:
-                self.gram_scatter(gram_c, pk.daddr(d_gt), B, tv.C, tv.C, Gt, 3)
-            ev_t, _ = self.eig_any(Gt, n_padC, ptr(None), tv.C, B, 'mrk', vecs=False)
-            ctx.call('cpsd_select_k', ptr(ev_t), n_padC, ptr(None), tv.C, float(self.pca_var), 1,
-                     0, 1 << 30, ptr(rank_dev), P, B)
-        # per-view centred scatter of the condition averages + eigen-decomposition, for the
-        # target of every fold and for the cross-patient problems not solved before
-        ctx.call('cpsd_colsum', pk.daddr(d_mu), nS, Cm)
-        self.gram_scatter(gram_c, pk.daddr(d_cov), nS, Cm, Cm, cov, 3)
-        nM, s0 = nS - B, vs['next']
-        ncol = min(n_padC, R)
-        self.eig_any(cov[:B], n_padC, ctypes_int_ptr(pk.iaddr(o_cds)), 0, B, 'mv', ncols=ncol,
-                     out=(vs['ev'][:B], vs['evec'][:B]))
-        if nM:
-            self.eig_any(cov[B:], n_padC, ctypes_int_ptr(pk.iaddr(o_cds + B)), 0, nM, 'mvx',
-                         ncols=ncol, out=(vs['ev'][s0:s0 + nM], vs['evec'][s0:s0 + nM]))
-        vs['keys'].update(pending)
-        vs['next'] += nM
-        self.stats['view_solves'] = self.stats.get('view_solves', 0) + nS
-        self.stats['view_problems'] = self.stats.get('view_problems', 0) + B * P
-        ctx.call('cpsd_mcca_mask_idx', ptr(vs['evec']), n_padC, n_padC * n_padC, ptr(vs['ev']),
-                 n_padC, ptr(rank_dev) if use_rank else ptr(None), cdim_dev,
-                 ctypes_int_ptr(pk.iaddr(o_slot)), R, Cm, ptr(Vr), ptr(d2), ptr(r_eff), B * P)
-        ctx.call('cpsd_proj_nn', pk.daddr(d_pz), npz, max(Ks), T, R)
-        ctx.call('cpsd_gram_tn', pk.daddr(d_g), ng, max(R, XR), max(R, XR))
-        xc['keys'].update(xs_of)
-        M = self.ws('m_M', (B, n_padM, n_padM))
-        M.zero_()
-        n_m = self.ws('m_nm', (B,), I32)
-        cidx = self.ws('m_cidx', (B, P * R), I32)
-        dh = self.ws('m_dh', (B, P * R))
         status = self.ws('m_status', (B,), I32)
-        status.zero_()
-        reg = -1.0 if self.regs is None else float(self.regs)
-        if XR:
-            ctx.call('cpsd_mcca_build_split', ptr(Gtx), P * R, R * P * R, ptr(Gxx), XR, XR * XR,
-                     ctypes_int_ptr(pk.iaddr(o_xslot)), ptr(r_eff), P, R, reg, ptr(M), n_padM,
-                     n_padM * n_padM, ptr(n_m), ptr(cidx), ptr(dh), Q, ptr(status), B)
+        if joint:
+            # ---- JointPCA fit of every fold
+            self.mark('align_scatter_eig')
+            ctx.call('cpsd_colsum', pk.daddr(d_js), B * P, Cm)
+            ctx.call('cpsd_gram_tn_f64', pk.daddr(d_jg), B * npair, Cm, Cm)
+            nrows_dev = self.ws('j_nrows', (B,), I32)
+            nrows_dev.copy_(torch.from_numpy((Ksa * T).astype(np.int32)).pin_memory(), non_blocking=True)
+            covj = self.ws('j_cov', (B, nJ_pad, nJ_pad))
+            ctx.call('cpsd_joint_cov', ptr(Gj), ptr(sj), ptr(nrows_dev), nJ, ptr(covj), nJ_pad, B)
+            self.mark('mcca_gevp')
+            nj_dev = ctypes_int_ptr(pk.iaddr(o_nj))
+            evj = self.ws('j_ev', (B, nJ_pad))
+            kj = self.ws('j_k', (B,), I32)
+            Vj = None
+            mj = self.topk_block
+            if nJ_pad > 128 and Q <= mj - 8 and self.pool_solver != 'full':
+                got = yield from self.eig_topk(covj, nJ_pad, nj_dev, B, mj, evj, 'joint', float(Q), 3,
+                                               nJ_pad, kj)
+                if got is not None:
+                    Vj, ldvj, sVj = got
+            if Vj is None:
+                evj, Vj = self.eig_any(covj, nJ_pad, nj_dev, 0, B, 'jointf', ncols=_ceil(Q, 64))
+                ldvj, sVj = nJ_pad, nJ_pad * nJ_pad
+            rhs = self.ws('j_rhs', (B * P, Cm, Q), torch.float64)
+            coff_dev = self.ws('j_coff', (P + 1,), I32)
+            coff_dev.copy_(torch.from_numpy(coff.astype(np.int32)).pin_memory(), non_blocking=True)
+            ctx.call('cpsd_joint_rhs', ptr(Gj), ptr(sj), ptr(nrows_dev), nJ, ptr(Vj), ldvj, sVj,
+                     ptr(coff_dev), P, Cm, Q, ptr(rhs), Q, Cm * Q, B)
+            status.zero_()
+            L.zero_()
+            stj = self.ws('j_status', (B * P,), I32)
+            stj.zero_()
+            for v in range(P):           # S_p W_p = rhs_p with S_p = G's diagonal block of patient p
+                C = int(cdims[v])
+                ctx.call('cpsd_chol_solve_f64', ptr(Gj, int(coff[v]) * nJ + int(coff[v])), nJ, nJ * nJ, C,
+                         ptr(rhs, v * Cm * Q), Q, P * Cm * Q, Q, ptr(L, v * Cm * Q), Q, P * Cm * Q,
+                         ptr(stj, v), B)
+            if align_only:
+                torch.cuda.synchronize(self.ctx.device)
+                return dict(loadings=L.view(B, P, Cm, Q).cpu().numpy(), shared=[s_.copy() for s_ in shared],
+                            evals=evj[:, :Q].cpu().numpy(), status=stj.cpu().numpy())
         else:
-            ctx.call('cpsd_mcca_build', ptr(Gtx), R, R * R, ptr(r_eff), P, R, reg, ptr(M), n_padM,
-                     n_padM * n_padM, ptr(n_m), ptr(cidx), ptr(dh), Q, ptr(status), B)
-        self.mark('mcca_gevp')
-        evm, U = self.eig_any(M, n_padM, ptr(n_m), 0, B, 'mm', ncols=Q)
-        ctx.call('cpsd_mcca_loadings', ptr(Vr), ptr(U), n_padM, n_padM * n_padM, ptr(None), 0,
-                 ptr(r_eff), ptr(dh), P, R, Cm, Q, ptr(L), Q, B)
-        if align_only:
-            torch.cuda.synchronize(self.ctx.device)
-            st = status.cpu().numpy()
-            if st.any():
-                raise ValueError('MCCA: n_components=%d exceeds the total signal rank' % Q)
-            return dict(loadings=L.view(B, P, Cm, Q).cpu().numpy(),
-                        mu=self._slot_means(mu, slot, Cm), evals_mcca=evm[:, :Q].cpu().numpy(),
-                        r_eff=r_eff.view(B, P).cpu().numpy(), shared=[s_.copy() for s_ in shared])
+            # signal ranks (cross ranks are fold-invariant and come with the int table)
+            ctx.call('cpsd_copy_rows', ctypes_int_ptr(pk.iaddr(o_rank)), B * P, 0, ptr(rank_dev),
+                     B * P, 0, ptr(None), 0, 1, B * P, 1, 1)
+            self.mark('align_scatter_eig')
+            if Cm < n_padC:
+                cov.zero_()
+                Gt.zero_()
+            if use_rank:
+                if downdate:     # train-set Gram = all-trials Gram - held-out trials (or sum of train)
+                    ctx.call('cpsd_sum_mats_f64', ptr(self.tg['all']) if use_te else ptr(None),
+                             ptr(self.tg['trial']), 128 * 128, ctypes_int_ptr(pk.iaddr(o_lptr)),
+                             ctypes_int_ptr(pk.iaddr(o_list)), -1.0 if use_te else 1.0, ptr(Gt),
+                             128 * 128, 128 * 128, B)
+                else:
+                    self.gram_scatter(gram_c, pk.daddr(d_gt), B, tv.C, tv.C, Gt, 3)
+                ev_t, _ = self.eig_any(Gt, n_padC, ptr(None), tv.C, B, 'mrk', vecs=False)
+                ctx.call('cpsd_select_k', ptr(ev_t), n_padC, ptr(None), tv.C, float(self.pca_var), 1,
+                         0, 1 << 30, ptr(rank_dev), P, B)
+            # per-view centred scatter of the condition averages + eigen-decomposition, for the
+            # target of every fold and for the cross-patient problems not solved before
+            ctx.call('cpsd_colsum', pk.daddr(d_mu), nS, Cm)
+            self.gram_scatter(gram_c, pk.daddr(d_cov), nS, Cm, Cm, cov, 3)
+            nM, s0 = nS - B, vs['next']
+            ncol = min(n_padC, R)
+            self.eig_any(cov[:B], n_padC, ctypes_int_ptr(pk.iaddr(o_cds)), 0, B, 'mv', ncols=ncol,
+                         out=(vs['ev'][:B], vs['evec'][:B]))
+            if nM:
+                self.eig_any(cov[B:], n_padC, ctypes_int_ptr(pk.iaddr(o_cds + B)), 0, nM, 'mvx',
+                             ncols=ncol, out=(vs['ev'][s0:s0 + nM], vs['evec'][s0:s0 + nM]))
+            vs['keys'].update(pending)
+            vs['next'] += nM
+            self.stats['view_solves'] = self.stats.get('view_solves', 0) + nS
+            self.stats['view_problems'] = self.stats.get('view_problems', 0) + B * P
+            ctx.call('cpsd_mcca_mask_idx', ptr(vs['evec']), n_padC, n_padC * n_padC, ptr(vs['ev']),
+                     n_padC, ptr(rank_dev) if use_rank else ptr(None), cdim_dev,
+                     ctypes_int_ptr(pk.iaddr(o_slot)), R, Cm, ptr(Vr), ptr(d2), ptr(r_eff), B * P)
+            ctx.call('cpsd_proj_nn', pk.daddr(d_pz), npz, max(Ks), T, R)
+            ctx.call('cpsd_gram_tn', pk.daddr(d_g), ng, max(R, XR), max(R, XR))
+            xc['keys'].update(xs_of)
+            M = self.ws('m_M', (B, n_padM, n_padM))
+            M.zero_()
+            n_m = self.ws('m_nm', (B,), I32)
+            cidx = self.ws('m_cidx', (B, P * R), I32)
+            dh = self.ws('m_dh', (B, P * R))
+            status = self.ws('m_status', (B,), I32)
+            status.zero_()
+            reg = -1.0 if self.regs is None else float(self.regs)
+            if XR:
+                ctx.call('cpsd_mcca_build_split', ptr(Gtx), P * R, R * P * R, ptr(Gxx), XR, XR * XR,
+                         ctypes_int_ptr(pk.iaddr(o_xslot)), ptr(r_eff), P, R, reg, ptr(M), n_padM,
+                         n_padM * n_padM, ptr(n_m), ptr(cidx), ptr(dh), Q, ptr(status), B)
+            else:
+                ctx.call('cpsd_mcca_build', ptr(Gtx), R, R * R, ptr(r_eff), P, R, reg, ptr(M), n_padM,
+                         n_padM * n_padM, ptr(n_m), ptr(cidx), ptr(dh), Q, ptr(status), B)
+            self.mark('mcca_gevp')
+            evm, U = self.eig_any(M, n_padM, ptr(n_m), 0, B, 'mm', ncols=Q)
+            ctx.call('cpsd_mcca_loadings', ptr(Vr), ptr(U), n_padM, n_padM * n_padM, ptr(None), 0,
+                     ptr(r_eff), ptr(dh), P, R, Cm, Q, ptr(L), Q, B)
+            if align_only:
+                torch.cuda.synchronize(self.ctx.device)
+                st = status.cpu().numpy()
+                if st.any():
+                    raise ValueError('MCCA: n_components=%d exceeds the total signal rank' % Q)
+                return dict(loadings=L.view(B, P, Cm, Q).cpu().numpy(),
+                            mu=self._slot_means(mu, slot, Cm), evals_mcca=evm[:, :Q].cpu().numpy(),
+                            r_eff=r_eff.view(B, P).cpu().numpy(), shared=[s_.copy() for s_ in shared])
         # project every trial of every view into the pooled (trial x time*Q) matrix
         self.mark('project_pool')
         if tc_proj:
             tcp = self._tc_proj_ws(B * P)
-            ctx.call('cpsd_proj_tc_prep', ptr(L), Q, Cm * Q, ptr(mu), ctypes_int_ptr(pk.iaddr(o_slot)),
+            ctx.call('cpsd_proj_tc_prep', ptr(L), Q, Cm * Q, ptr(None) if joint else ptr(mu),
+                     ptr(None) if joint else ctypes_int_ptr(pk.iaddr(o_slot)),
                      Cm, cdim_dev, Q, ptr(tcp['lthi']), ptr(tcp['ltlo']), ptr(tcp['mul']), B * P)
             ctx.call('cpsd_proj_tc', ptr(tcp['xmaps']), ptr(tcp['ltmaps']), P, B, T, Q,
                      ctypes.c_void_p(tcp['ntr'].ctypes.data), ctypes.c_void_p(tcp['nch'].ctypes.data),
@@ -1337,7 +1423,13 @@ class CVEngine:
         res = {'y_pred': [yh[f, :n_te[f]].copy() for f in range(B)], 'k2': k2h.tolist(),
                'h2d_bytes': pk.h2d_bytes, 'd2h_bytes': yh.nbytes + k2h.nbytes + st.nbytes}
         self.stats['launches_last_batch'] = ctx.launches() - launches0
-        if want_details:
+        if want_details and joint:
+            res['details'] = dict(
+                loadings=L.view(B, P, Cm, Q).cpu().numpy(), evals_joint=evj[:, :Q].cpu().numpy(),
+                pool_evals=evals.cpu().numpy(), svm_info=info.cpu().numpy(), W=W.cpu().numpy(),
+                n_pool=list(n_pool), shared=[s.copy() for s in shared], lsq_status=stj.cpu().numpy(),
+                bj_sweeps=None if sweeps is None else sweeps.cpu().numpy()[B:2 * B])
+        elif want_details:
             res['details'] = dict(
                 loadings=L.view(B, P, Cm, Q).cpu().numpy(), mu=self._slot_means(mu, slot, Cm),
                 evals_mcca=evm[:, :Q].cpu().numpy(), r_eff=r_eff.view(B, P).cpu().numpy(),

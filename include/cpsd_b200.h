@@ -240,6 +240,17 @@ int cpsd_mcca_loadings(const float* Vr, const float* U, int ldu, long long strid
                        int R, int Cmax, int n_comp, float* L, int ldl, int nfold,
                        cudaStream_t stream);
 
+/* ---- JointPCA assembly (alignment/JointPCA.py:165-211), batched over folds ----------------
+ * G: fp64 Gram of the channel-concatenated class averages (blocks u <= v), s: its column sums.
+ * joint_cov: sklearn-PCA covariance of the concatenation (fp32, zero padded);  joint_rhs:
+ * X_p^T (M - 1 mean^T) V_k per (fold, patient), the right-hand sides of the least-squares
+ * read-in matrices pinv(X_p) @ latent (solved by cpsd_chol_solve_f64 on G's diagonal blocks). */
+int cpsd_joint_cov(const double* G, const float* s, const int* nrows, int n, float* cov, int n_pad,
+                   int nfold, cudaStream_t stream);
+int cpsd_joint_rhs(const double* G, const float* s, const int* nrows, int n, const float* V, int ldv,
+                   long long strideV, const int* coff, int P, int C_max, int k, double* rhs, int ldr,
+                   long long strideR, int nfold, cudaStream_t stream);
+
 /* ---- decoder stage -----------------------------------------------------------------
  * PCA scores of the pooled train / test trials from the Gram eigen-pairs */
 int cpsd_scores_train(const float* V, int ldv, long long strideV, const float* evals,
