@@ -375,7 +375,7 @@ class CVEngine:
         vs = getattr(self, '_vs', None)
         if vs is None or vs['res'] < B or vs['npad'] != n_pad:
             res = max(B, self.max_batch)
-            cap = res + max(512, res * max(self.P - 1, 1))
+            cap = res + max(1024, 2 * res * max(self.P - 1, 1))
             vs = dict(res=res, cap=cap, npad=n_pad, keys={}, next=res,
                       mu=self.ctx.zeros((cap, Cm)), ev=self.ctx.zeros((cap, n_pad)),
                       evec=self.ctx.zeros((cap, n_pad, n_pad)))
@@ -992,25 +992,27 @@ class CVEngine:
             # slot of every (fold, view) problem; solve list = targets + cache misses
             n_padC = 128 if Cm <= 128 else _ceil(Cm, 128)
             vs = self._view_slots(B, n_padC, Cm)
-            if vs['next'] + B * (P - 1) > vs['cap']:
-                vs['keys'].clear()
-                vs['next'] = vs['res']
             slot = np.zeros((B, P), dtype=np.int64)
             slot[:, 0] = fold_of
-            solve = [(f, 0, f) for f in range(B)]
-            pending = {}
-            if P > 1:
-                rows_u = np.zeros((len(shared_u), P - 1), dtype=np.int64)
-                for u, ku in enumerate(keys_u):
-                    for v in range(1, P):
-                        key = (v, ku)
-                        sl = vs['keys'].get(key)
-                        if sl is None:
-                            sl = vs['next'] + len(pending)
-                            pending[key] = sl
-                            solve.append((int(first[u]), v, sl))
-                        rows_u[u, v - 1] = sl
-                slot[:, 1:] = rows_u[inv]
+            for attempt in range(2):
+                solve = [(f, 0, f) for f in range(B)]
+                pending = {}
+                if P > 1:
+                    rows_u = np.zeros((len(shared_u), P - 1), dtype=np.int64)
+                    for u, ku in enumerate(keys_u):
+                        for v in range(1, P):
+                            key = (v, ku)
+                            sl = vs['keys'].get(key)
+                            if sl is None:
+                                sl = vs['next'] + len(pending)
+                                pending[key] = sl
+                                solve.append((int(first[u]), v, sl))
+                            rows_u[u, v - 1] = sl
+                    slot[:, 1:] = rows_u[inv]
+                if vs['next'] + len(pending) <= vs['cap']:
+                    break
+                vs['keys'].clear()           # cache full: start over (everything misses once)
+                vs['next'] = vs['res']
             o_slot = pk.add_ints(slot)
             o_cds = pk.add_ints([self.views[v].C for _, v, _ in solve])
             # cross-block cache slot of every fold (one slot per shared class set)
@@ -1018,8 +1020,8 @@ class CVEngine:
             xc = self._xcache(R, XR)
             newx = []                       # (cache slot, first fold with that class set)
             xs_of = {}
-            if len(xc['keys']) + B > xc['cap']:
-                xc['keys'].clear()
+            if len(xc['keys']) + sum(ku not in xc['keys'] for ku in keys_u) > xc['cap']:
+                xc['keys'].clear()           # cache full: start over
             xs_u = np.zeros(len(shared_u), dtype=np.int32)
             for u, ku in enumerate(keys_u):
                 xs = xc['keys'].get(ku)

@@ -10,6 +10,7 @@ import bench  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument('--steps', type=int, default=1)
+ap.add_argument('--same', action='store_true', help='repeat the same folds (warm caches)')
 ap.add_argument('--folds', type=int, default=107)
 ap.add_argument('--no-tc', action='store_true')
 ap.add_argument('--stages', action='store_true')
@@ -29,7 +30,7 @@ def mk(seed):
 eng.run(mk(1000))
 for s in range(a.steps):
     eng.profile = a.stages
-    fl = mk(2000 + 100 * s)
+    fl = mk(2000 if a.same else 2000 + 100 * s)
     res = eng.run(fl, return_details=True)
     if a.stages:
         print('stages_ms', {k: round(v, 3) for k, v in eng.collect_marks().items()})
