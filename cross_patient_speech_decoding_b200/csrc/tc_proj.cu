@@ -236,7 +236,7 @@ k_proj_tc(const CUtensorMap* __restrict__ xmaps, const CUtensorMap* __restrict__
           const int r = (int)(rj[i] >> 8), j = (int)(rj[i] & 255u);
           const int off = (i < Q) ? row_off[r] : -1;
           offs[i] = (off >= 0) ? off + j : -1;
-          vals[i] = stg[r * PT_LDS + j];
+          vals[i] = (i < Q) ? stg[r * PT_LDS + j] : 0.f;
         }
 #pragma unroll
         for (int i = 0; i < PT_N; ++i)
