@@ -1,0 +1,435 @@
+// Kernel C-SVC with one-vs-one voting: the reference scripts' literal decoder
+// `SVC(kernel='rbf', class_weight='balanced')` (aligned_decoding/scripts/aligned_decode_svm_ncv.py:313-317,
+// aligned_decode_grid_subsample.py:261) and the `SVC(kernel='linear')` inside its
+// `BaggingClassifier` (aligned_decode_svm.py:262-263).  sklearn hands both to libsvm; this file
+// restates libsvm's published algorithm (Fan, Chen, Lin 2005: SMO with second-order working-set
+// selection, float kernel values, double gradients, eps = tol stopping rule, first-maximum vote)
+// as batched kernels:
+//   k_svc_gamma      gamma='scale' = 1 / (n_features * var(X)) per fold
+//   k_svc_kmat       (n x n) kernel matrix per fold (fp64 accumulation, stored as float like
+//                    libsvm's Qfloat cache)
+//   k_svc_smo        one WARP per (fold, class pair) dual problem: members, alpha and the
+//                    gradient live in shared memory, no block barrier inside the SMO loop
+//   k_svc_predict    one CTA per (fold, held-out trial): kernel row, all pair decisions, vote
+// No shrinking (it changes the iteration path, not the optimum the eps rule accepts).
+#include "common.cuh"
+
+namespace {
+
+constexpr int SVC_WARPS = 2;       // tasks per CTA of k_svc_smo
+constexpr double SVC_TAU = 1e-12;
+constexpr double SVC_INF = 1.0e300;
+
+__global__ void k_svc_gamma(const float* __restrict__ St, int lds, long long strideS,
+                            const int* __restrict__ k_dev, int k_fixed,
+                            const int* __restrict__ n_dev, int n_fixed, int kernel, double gamma_in,
+                            double* __restrict__ gamma_out) {
+  __shared__ double red[40];
+  const int f = blockIdx.x;
+  const int k = k_dev ? k_dev[f] : k_fixed;
+  const int n = n_dev ? n_dev[f] : n_fixed;
+  double g = gamma_in;
+  if (kernel == 1 && gamma_in <= 0.0) {       // 'scale'
+    const float* X = St + (long long)f * strideS;
+    double s = 0.0;
+    for (int j = 0; j < k; ++j)
+      for (int t = threadIdx.x; t < n; t += blockDim.x) s += (double)X[(long long)j * lds + t];
+    const double cnt = (double)k * (double)n;
+    const double mean = block_sum(s, red) / fmax(cnt, 1.0);
+    double v = 0.0;
+    for (int j = 0; j < k; ++j)
+      for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        const double d = (double)X[(long long)j * lds + t] - mean;
+        v += d * d;
+      }
+    const double var = block_sum(v, red) / fmax(cnt, 1.0);
+    g = (var > 0.0 && k > 0) ? 1.0 / ((double)k * var) : 1.0;
+  }
+  if (threadIdx.x == 0) gamma_out[f] = g;
+}
+
+// 32x32 output tile per CTA, 256 threads x 4 entries; features staged 32 at a time.
+__global__ void k_svc_kmat(const float* __restrict__ St, int lds, long long strideS,
+                           const int* __restrict__ k_dev, int k_fixed,
+                           const int* __restrict__ n_dev, int n_fixed, int kernel,
+                           const double* __restrict__ gamma, float* __restrict__ K, int ldk,
+                           long long strideK) {
+  __shared__ float a[32][33], b[32][33];
+  const int f = blockIdx.z;
+  const int k = k_dev ? k_dev[f] : k_fixed;
+  const int n = n_dev ? n_dev[f] : n_fixed;
+  const int i0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
+  if (i0 >= n || t0 >= n) return;
+  const float* X = St + (long long)f * strideS;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // ty 0..7
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int j0 = 0; j0 < k; j0 += 32) {
+    for (int r = ty; r < 32; r += 8) {
+      const int j = j0 + r;
+      a[r][tx] = (j < k && i0 + tx < n) ? X[(long long)j * lds + i0 + tx] : 0.f;
+      b[r][tx] = (j < k && t0 + tx < n) ? X[(long long)j * lds + t0 + tx] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) {
+      const double bv = (double)b[r][tx];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const double av = (double)a[r][ty + 8 * e];
+        if (kernel == 1) { const double d = av - bv; acc[e] = fma(d, d, acc[e]); }
+        else acc[e] = fma(av, bv, acc[e]);
+      }
+    }
+    __syncthreads();
+  }
+  const double g = gamma[f];
+  float* Kf = K + (long long)f * strideK;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int i = i0 + ty + 8 * e, t = t0 + tx;
+    if (i < n && t < n) Kf[(long long)i * ldk + t] = (float)(kernel == 1 ? exp(-g * acc[e]) : acc[e]);
+  }
+}
+
+struct Pick { double v; int i; };
+// larger value wins, ties go to the larger index (libsvm scans upwards with >=)
+__device__ __forceinline__ Pick warp_argmax_last(Pick p) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double v = __shfl_xor_sync(0xffffffffu, p.v, o);
+    const int i = __shfl_xor_sync(0xffffffffu, p.i, o);
+    if (v > p.v || (v == p.v && i > p.i)) { p.v = v; p.i = i; }
+  }
+  return p;
+}
+__device__ __forceinline__ double warp_maxd(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_mind(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// pair p -> (a, b), a < b, in libsvm's order (a outer, b inner)
+__device__ __forceinline__ void pair_of(int p, int ncls, int& a, int& b) {
+  a = 0;
+  int rem = p;
+  while (rem >= ncls - 1 - a) { rem -= ncls - 1 - a; ++a; }
+  b = a + 1 + rem;
+}
+
+// Dual problem of one class pair.  Members of class a (y=+1) first, then class b (y=-1), both in
+// pool order.  Shared memory per warp: alpha[m_max], G[m_max] (double), idx[m_max] (int),
+// qd[m_max] (float), ys[m_max] (signed char).
+__global__ void __launch_bounds__(32 * SVC_WARPS)
+k_svc_smo(const float* __restrict__ K, int ldk, long long strideK, const int* __restrict__ y, int ldy,
+          const int* __restrict__ n_dev, int n_fixed, const int* __restrict__ classes, int ncls,
+          double Cpar, int balanced, double eps, int max_iter, double* __restrict__ coef, int ldc,
+          double* __restrict__ rho, int* __restrict__ info, int m_max, int ntask) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int task = blockIdx.x * SVC_WARPS + w;
+  if (task >= ntask) return;
+  const int npair = ncls * (ncls - 1) / 2;
+  const int f = task / npair, p = task - f * npair;
+  int ca, cb;
+  pair_of(p, ncls, ca, cb);
+  const size_t per_warp = (size_t)m_max * (8 + 8 + 4 + 4 + 1) + 16;
+  unsigned char* base = smem_raw + (size_t)w * ((per_warp + 15) & ~(size_t)15);
+  double* alpha = (double*)base;
+  double* G = alpha + m_max;
+  int* idx = (int*)(G + m_max);
+  float* qd = (float*)(idx + m_max);
+  signed char* ys = (signed char*)(qd + m_max);
+
+  const int n = n_dev ? n_dev[f] : n_fixed;
+  const int* yf = y + (long long)f * ldy;
+  const float* Kf = K + (long long)f * strideK;
+  const int la = classes[ca], lb = classes[cb];
+  // members (ordered compaction, 32 at a time) and the class statistics of the whole pool
+  int ma = 0, mb = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    const int want = pass == 0 ? la : lb;
+    for (int t0 = 0; t0 < n; t0 += 32) {
+      const int t = t0 + lane;
+      const bool hit = t < n && yf[t] == want;
+      const unsigned msk = __ballot_sync(0xffffffffu, hit);
+      const int pos = (pass == 0 ? ma : ma + mb) + __popc(msk & ((1u << lane) - 1u));
+      if (hit && pos < m_max) { idx[pos] = t; ys[pos] = pass == 0 ? 1 : -1; }
+      if (pass == 0) ma += __popc(msk); else mb += __popc(msk);
+    }
+  }
+  const int m = ma + mb;
+  int* inf = info + 2 * (long long)task;
+  if (ma == 0 || mb == 0) {            // class absent from this pool: no such pair in libsvm
+    if (lane == 0) { rho[task] = 0.0; inf[0] = 0; inf[1] = 2; }
+    return;
+  }
+  if (m > m_max) {
+    if (lane == 0) { rho[task] = 0.0; inf[0] = 0; inf[1] = 3; }
+    return;
+  }
+  double Cp = Cpar, Cn = Cpar;
+  if (balanced) {                       // n_samples / (n_classes_present * count_c), sklearn
+    int present = 0;
+    for (int c = 0; c < ncls; ++c) {
+      int cnt = 0;
+      for (int t = lane; t < n; t += 32) cnt += yf[t] == classes[c];
+      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      present += cnt > 0;
+    }
+    Cp = Cpar * ((double)n / ((double)present * (double)ma));
+    Cn = Cpar * ((double)n / ((double)present * (double)mb));
+  }
+  for (int t = lane; t < m; t += 32) {
+    alpha[t] = 0.0;
+    G[t] = -1.0;
+    qd[t] = Kf[(long long)idx[t] * ldk + idx[t]];
+  }
+  __syncwarp();
+
+  int it = 0, status = 1;
+  while (it < max_iter) {
+    // --- i: maximal violator of the "up" set
+    Pick pi{-SVC_INF, -1};
+    for (int t = lane; t < m; t += 32) {
+      const double a = alpha[t], g = G[t];
+      if (ys[t] > 0) { if (a < Cp && -g >= pi.v) { pi.v = -g; pi.i = t; } }
+      else           { if (a > 0.0 && g >= pi.v) { pi.v = g; pi.i = t; } }
+    }
+    pi = warp_argmax_last(pi);
+    const int i = pi.i;
+    const double Gmax = pi.v;
+    if (i < 0) { status = 0; break; }
+    const float* Ki = Kf + (long long)idx[i] * ldk;
+    const int yi = ys[i];
+    const double qdi = (double)qd[i];
+    // --- j: second-order choice in the "low" set
+    Pick pj{-SVC_INF, -1};               // maximise -obj  (obj <= min, ties to the larger index)
+    double Gmax2 = -SVC_INF;
+    for (int t = lane; t < m; t += 32) {
+      const double a = alpha[t], g = G[t];
+      const int yt = ys[t];
+      double gd;
+      bool ok;
+      if (yt > 0) { ok = a > 0.0; gd = Gmax + g; if (ok) Gmax2 = fmax(Gmax2, g); }
+      else        { ok = a < Cn;  gd = Gmax - g; if (ok) Gmax2 = fmax(Gmax2, -g); }
+      if (ok && gd > 0.0) {
+        // QD_i + QD_t - 2 y_i y_t Q_it with Q_it = y_i y_t K_it
+        double quad = qdi + (double)qd[t] - 2.0 * (double)Ki[idx[t]];
+        if (!(quad > 0.0)) quad = SVC_TAU;
+        const double nobj = (gd * gd) / quad;
+        if (nobj >= pj.v) { pj.v = nobj; pj.i = t; }
+      }
+    }
+    pj = warp_argmax_last(pj);
+    Gmax2 = warp_maxd(Gmax2);
+    const int j = pj.i;
+    if (Gmax + Gmax2 < eps || j < 0) { status = 0; break; }
+    ++it;
+    const float* Kj = Kf + (long long)idx[j] * ldk;
+    const int yj = ys[j];
+    const double Ci = yi > 0 ? Cp : Cn, Cj = yj > 0 ? Cp : Cn;
+    const double ai0 = alpha[i], aj0 = alpha[j], Gi = G[i], Gj = G[j];
+    const double Qij = (double)((float)(yi * yj) * Ki[idx[j]]);
+    double ai = ai0, aj = aj0;
+    if (yi != yj) {
+      double quad = qdi + (double)qd[j] + 2.0 * Qij;
+      if (!(quad > 0.0)) quad = SVC_TAU;
+      const double delta = (-Gi - Gj) / quad;
+      const double diff = ai - aj;
+      ai += delta;
+      aj += delta;
+      if (diff > 0.0) { if (aj < 0.0) { aj = 0.0; ai = diff; } }
+      else            { if (ai < 0.0) { ai = 0.0; aj = -diff; } }
+      if (diff > Ci - Cj) { if (ai > Ci) { ai = Ci; aj = Ci - diff; } }
+      else                { if (aj > Cj) { aj = Cj; ai = Cj + diff; } }
+    } else {
+      double quad = qdi + (double)qd[j] - 2.0 * Qij;
+      if (!(quad > 0.0)) quad = SVC_TAU;
+      const double delta = (Gi - Gj) / quad;
+      const double sum = ai + aj;
+      ai -= delta;
+      aj += delta;
+      if (sum > Ci) { if (ai > Ci) { ai = Ci; aj = sum - Ci; } }
+      else          { if (aj < 0.0) { aj = 0.0; ai = sum; } }
+      if (sum > Cj) { if (aj > Cj) { aj = Cj; ai = sum - Cj; } }
+      else          { if (ai < 0.0) { ai = 0.0; aj = sum; } }
+    }
+    const double dai = ai - ai0, daj = aj - aj0;
+    __syncwarp();                        // every lane has read alpha/G of i and j
+    for (int t = lane; t < m; t += 32) {
+      const int yt = ys[t];
+      const float qit = (float)(yi * yt) * Ki[idx[t]];
+      const float qjt = (float)(yj * yt) * Kj[idx[t]];
+      G[t] += (double)qit * dai + (double)qjt * daj;
+    }
+    if (lane == 0) { alpha[i] = ai; alpha[j] = aj; }
+    __syncwarp();
+  }
+  // rho: mean of y G over the free variables, else the midpoint of the bounds
+  double ub = SVC_INF, lbv = -SVC_INF, sum_free = 0.0;
+  int nfree = 0;
+  for (int t = lane; t < m; t += 32) {
+    const double a = alpha[t];
+    const int yt = ys[t];
+    const double yG = (double)yt * G[t];
+    const double Ct = yt > 0 ? Cp : Cn;
+    if (a >= Ct)      { if (yt < 0) ub = fmin(ub, yG); else lbv = fmax(lbv, yG); }
+    else if (a <= 0.0) { if (yt > 0) ub = fmin(ub, yG); else lbv = fmax(lbv, yG); }
+    else { ++nfree; sum_free += yG; }
+  }
+  nfree = __reduce_add_sync(0xffffffffu, nfree);
+  sum_free = warp_sum(sum_free);
+  ub = warp_mind(ub);
+  lbv = warp_maxd(lbv);
+  const double r = nfree > 0 ? sum_free / (double)nfree : 0.5 * (ub + lbv);
+  // coefficients in libsvm's sv_coef layout: a class-a member stores the pair under slot b-1,
+  // a class-b member under slot a
+  double* cf = coef + (long long)f * (ncls - 1) * ldc;
+  for (int t = lane; t < m; t += 32) {
+    const int slot = ys[t] > 0 ? cb - 1 : ca;
+    cf[(long long)slot * ldc + idx[t]] = alpha[t] * (double)ys[t];
+  }
+  if (lane == 0) { rho[task] = r; inf[0] = it; inf[1] = status; }
+}
+
+// One CTA per (fold, held-out trial).  dec (optional): [fold][n_te_max][npair] pair decisions.
+__global__ void k_svc_predict(const float* __restrict__ St, int lds, long long strideS,
+                              const float* __restrict__ Ste, int ldt, long long strideT,
+                              const int* __restrict__ k_dev, int k_fixed,
+                              const int* __restrict__ n_dev, int n_fixed,
+                              const int* __restrict__ n_te, int n_te_max, const int* __restrict__ y,
+                              int ldy, const int* __restrict__ classes, int ncls, int kernel,
+                              const double* __restrict__ gamma, const double* __restrict__ coef,
+                              int ldc, const double* __restrict__ rho, int* __restrict__ yhat,
+                              double* __restrict__ dec) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int votes[64], counts[64];
+  __shared__ float z[1024];
+  const int f = blockIdx.y, s = blockIdx.x;
+  const int nt = n_te ? n_te[f] : n_te_max;
+  if (s >= nt) {
+    if (threadIdx.x == 0) yhat[(long long)f * n_te_max + s] = -1;
+    return;
+  }
+  const int k = k_dev ? k_dev[f] : k_fixed;
+  const int n = n_dev ? n_dev[f] : n_fixed;
+  double* kv = (double*)smem_raw;
+  const float* X = St + (long long)f * strideS;
+  const float* Z = Ste + (long long)f * strideT;
+  const int* yf = y + (long long)f * ldy;
+  for (int j = threadIdx.x; j < k; j += blockDim.x) z[j] = Z[(long long)j * ldt + s];
+  if (threadIdx.x < 64) { votes[threadIdx.x] = 0; counts[threadIdx.x] = 0; }
+  __syncthreads();
+  const double g = gamma[f];
+  for (int t = threadIdx.x; t < n; t += blockDim.x) {
+    double acc = 0.0;
+    for (int j = 0; j < k; ++j) {
+      const double xv = (double)X[(long long)j * lds + t], zv = (double)z[j];
+      if (kernel == 1) { const double d = xv - zv; acc = fma(d, d, acc); }
+      else acc = fma(xv, zv, acc);
+    }
+    kv[t] = kernel == 1 ? exp(-g * acc) : acc;
+    const int lab = yf[t];
+    for (int c = 0; c < ncls; ++c)
+      if (classes[c] == lab) atomicAdd(&counts[c], 1);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int npair = ncls * (ncls - 1) / 2;
+  const double* cf = coef + (long long)f * (ncls - 1) * ldc;
+  for (int p = w; p < npair; p += nw) {
+    int ca, cb;
+    pair_of(p, ncls, ca, cb);
+    if (counts[ca] == 0 || counts[cb] == 0) {
+      if (dec && lane == 0) dec[((long long)f * n_te_max + s) * npair + p] = 0.0;
+      continue;
+    }
+    const int la = classes[ca], lb = classes[cb];
+    double sum = 0.0;
+    for (int t = lane; t < n; t += 32) {
+      const int lab = yf[t];
+      if (lab == la) sum = fma(cf[(long long)(cb - 1) * ldc + t], kv[t], sum);
+      else if (lab == lb) sum = fma(cf[(long long)ca * ldc + t], kv[t], sum);
+    }
+    sum = warp_sum(sum) - rho[(long long)f * npair + p];
+    if (lane == 0) {
+      if (dec) dec[((long long)f * n_te_max + s) * npair + p] = sum;
+      atomicAdd(&votes[sum > 0.0 ? ca : cb], 1);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int best = -1, bv = -1;
+    for (int c = 0; c < ncls; ++c)
+      if (counts[c] > 0 && votes[c] > bv) { bv = votes[c]; best = c; }
+    yhat[(long long)f * n_te_max + s] = best >= 0 ? classes[best] : -1;
+  }
+}
+
+static size_t smo_smem(int m_max) {
+  const size_t per_warp = (size_t)m_max * (8 + 8 + 4 + 4 + 1) + 16;
+  return SVC_WARPS * ((per_warp + 15) & ~(size_t)15);
+}
+
+}  // namespace
+
+extern "C" int cpsd_svc_kernel_matrix(const float* St, int lds, long long strideS, const int* k_dev,
+                                      int k_fixed, const int* n_dev, int n_fixed, int n_max, int kernel,
+                                      double gamma, double* gamma_out, float* K, int ldk,
+                                      long long strideK, int nfold, cudaStream_t stream) {
+  CPSD_CHECK_ARG(nfold >= 0 && n_max > 0 && ldk >= n_max && (kernel == 0 || kernel == 1),
+                 "svc_kernel_matrix: bad dims");
+  if (nfold == 0) return CPSD_OK;
+  k_svc_gamma<<<nfold, 256, 0, stream>>>(St, lds, strideS, k_dev, k_fixed, n_dev, n_fixed, kernel, gamma,
+                                         gamma_out);
+  CPSD_LAUNCH_CHECK();
+  const int tiles = (n_max + 31) / 32;
+  k_svc_kmat<<<dim3(tiles, tiles, nfold), 256, 0, stream>>>(St, lds, strideS, k_dev, k_fixed, n_dev, n_fixed,
+                                                             kernel, gamma_out, K, ldk, strideK);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
+
+extern "C" int cpsd_svc_fit_ovo(const float* K, int ldk, long long strideK, const int* y, int ldy,
+                                const int* n_dev, int n_fixed, const int* classes, int ncls, double C,
+                                int balanced, double eps, int max_iter, double* coef, int ldc,
+                                double* rho, int* info, int m_max, int nfold, cudaStream_t stream) {
+  CPSD_CHECK_ARG(nfold >= 0 && ncls >= 2 && ncls <= 64 && m_max > 0 && C > 0 && eps > 0 && max_iter > 0,
+                 "svc_fit_ovo: bad arguments");
+  if (nfold == 0) return CPSD_OK;
+  const size_t smem = smo_smem(m_max);
+  CPSD_CHECK_ARG(smem <= 227 * 1024, "svc_fit_ovo: pair size exceeds the shared-memory budget");
+  CPSD_CUDA(cudaFuncSetAttribute(k_svc_smo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CPSD_CUDA(cudaMemsetAsync(coef, 0, sizeof(double) * (size_t)nfold * (ncls - 1) * ldc, stream));
+  const int ntask = nfold * (ncls * (ncls - 1) / 2);
+  k_svc_smo<<<(ntask + SVC_WARPS - 1) / SVC_WARPS, 32 * SVC_WARPS, smem, stream>>>(
+      K, ldk, strideK, y, ldy, n_dev, n_fixed, classes, ncls, C, balanced, eps, max_iter, coef, ldc, rho,
+      info, m_max, ntask);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
+
+extern "C" int cpsd_svc_predict_ovo(const float* St, int lds, long long strideS, const float* Ste, int ldt,
+                                    long long strideT, const int* k_dev, int k_fixed, const int* n_dev,
+                                    int n_fixed, int n_max, const int* n_te, int n_te_max, const int* y,
+                                    int ldy, const int* classes, int ncls, int kernel,
+                                    const double* gamma, const double* coef, int ldc, const double* rho,
+                                    int* yhat, double* dec, int k_max, int nfold, cudaStream_t stream) {
+  CPSD_CHECK_ARG(nfold >= 0 && ncls >= 2 && ncls <= 64 && n_te_max > 0 && n_max > 0 && k_max <= 1024,
+                 "svc_predict_ovo: bad arguments (at most 64 classes, 1024 features)");
+  if (nfold == 0) return CPSD_OK;
+  const size_t smem = sizeof(double) * (size_t)n_max;
+  CPSD_CHECK_ARG(smem <= 200 * 1024, "svc_predict_ovo: pool too large");
+  CPSD_CUDA(cudaFuncSetAttribute(k_svc_predict, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_svc_predict<<<dim3(n_te_max, nfold), 256, smem, stream>>>(St, lds, strideS, Ste, ldt, strideT, k_dev,
+                                                              k_fixed, n_dev, n_fixed, n_te, n_te_max, y,
+                                                              ldy, classes, ncls, kernel, gamma, coef, ldc,
+                                                              rho, yhat, dec);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}

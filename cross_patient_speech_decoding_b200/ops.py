@@ -397,3 +397,76 @@ def svm_predict_ovr(S, classes, W, device=None, return_decision=False):
     if return_decision:
         return yh.cpu().numpy(), dec.cpu().numpy()
     return yh.cpu().numpy()
+
+
+_SVC_KERNELS = {'linear': 0, 'rbf': 1}
+
+
+def svc_fit_ovo(S, y, C=1.0, kernel='rbf', gamma='scale', balanced=False, tol=1e-3,
+                max_iter=1000000, device=None):
+    """libsvm-style C-SVC, one-vs-one (sklearn.svm.SVC as the reference scripts build it,
+    scripts/aligned_decode_svm_ncv.py:313-317).  S: (n, k) features, y: (n,) ints.  Returns a
+    dict holding the device state ``predict`` needs plus host copies of the fitted quantities
+    (coef in libsvm's sv_coef layout (n_classes-1, n), rho per pair, gamma, info)."""
+    ctx = _ctx(device)
+    S = np.asarray(S, dtype=np.float32)
+    n, k = S.shape
+    y = np.asarray(y).astype(np.int32)
+    classes, counts = np.unique(y, return_counts=True)
+    classes = classes.astype(np.int32)
+    ncls = len(classes)
+    if ncls < 2:
+        raise ValueError('The number of classes has to be greater than one; got %d class' % ncls)
+    if kernel not in _SVC_KERNELS:
+        raise ValueError("kernel must be 'linear' or 'rbf'")
+    if isinstance(gamma, str):
+        if gamma == 'scale':
+            g = -1.0
+        elif gamma == 'auto':
+            g = 1.0 / max(k, 1)
+        else:
+            raise ValueError("gamma must be 'scale', 'auto' or a positive float")
+    else:
+        g = float(gamma)
+        if g <= 0:
+            raise ValueError('gamma must be positive')
+    lds = _ceil(n, 4)
+    St = np.zeros((max(k, 1), lds), dtype=np.float32)
+    St[:k, :n] = S.T
+    Sd, yd, cd = ctx.upload(St), ctx.upload(y), ctx.upload(classes)
+    K = ctx.empty((n, lds))
+    gam = ctx.empty((1,), F64)
+    kid = _SVC_KERNELS[kernel]
+    ctx.call('cpsd_svc_kernel_matrix', ptr(Sd), lds, 0, ptr(None), k, ptr(None), n, n, kid, g, ptr(gam),
+             ptr(K), lds, 0, 1)
+    npair = ncls * (ncls - 1) // 2
+    coef = ctx.empty((ncls - 1, lds), F64)
+    rho = ctx.empty((npair,), F64)
+    info = ctx.empty((npair, 2), I32)
+    srt = np.sort(counts)
+    m_max = int(srt[-1] + srt[-2])
+    ctx.call('cpsd_svc_fit_ovo', ptr(K), lds, 0, ptr(yd), 0, ptr(None), n, ptr(cd), ncls, float(C),
+             int(bool(balanced)), float(tol), int(max_iter), ptr(coef), lds, ptr(rho), ptr(info), m_max, 1)
+    return dict(St=Sd, y=yd, classes_dev=cd, coef_dev=coef, rho_dev=rho, gamma_dev=gam, n=n, k=k, lds=lds,
+                kernel=kid, classes=classes, coef=coef.cpu().numpy()[:, :n], rho=rho.cpu().numpy(),
+                gamma=float(gam.cpu().numpy()[0]), info=info.cpu().numpy())
+
+
+def svc_predict_ovo(model, S, device=None, return_decision=False):
+    ctx = _ctx(device)
+    S = np.asarray(S, dtype=np.float32)
+    nt, k = S.shape
+    assert k == model['k'], 'feature count differs from fit'
+    ncls = len(model['classes'])
+    npair = ncls * (ncls - 1) // 2
+    Zt = ctx.upload(np.ascontiguousarray(S.T) if k else np.zeros((1, nt), dtype=np.float32))
+    yh = ctx.empty((nt,), I32)
+    dec = ctx.empty((nt, npair), F64)
+    n, lds = model['n'], model['lds']
+    ctx.call('cpsd_svc_predict_ovo', ptr(model['St']), lds, 0, ptr(Zt), nt, 0, ptr(None), k, ptr(None), n, n,
+             ptr(None), nt, ptr(model['y']), 0, ptr(model['classes_dev']), ncls, model['kernel'],
+             ptr(model['gamma_dev']), ptr(model['coef_dev']), lds, ptr(model['rho_dev']), ptr(yh),
+             ptr(dec), k, 1)
+    if return_decision:
+        return yh.cpu().numpy(), dec.cpu().numpy()
+    return yh.cpu().numpy()

@@ -271,6 +271,34 @@ int cpsd_svm_predict_ovr(const float* Xt, int ldx, long long strideX, const doub
                          int n_te_max, const int* classes, int ncls, int* yhat, double* dec,
                          int nfold, cudaStream_t stream);
 
+/* kernel C-SVC with one-vs-one voting (libsvm's algorithm): the reference scripts' literal
+ * decoders SVC(kernel='rbf', class_weight='balanced') (scripts/aligned_decode_svm_ncv.py:313-317)
+ * and SVC(kernel='linear') inside BaggingClassifier (scripts/aligned_decode_svm.py:262-263).
+ * St: feature-major pool scores (k x n, leading dimension lds) per fold; kernel 0 = linear,
+ * 1 = rbf; gamma <= 0 means 'scale' = 1 / (k * var(X)); the per-fold gamma is written to
+ * gamma_out; K: (n x n) float kernel matrix per fold. */
+int cpsd_svc_kernel_matrix(const float* St, int lds, long long strideS, const int* k_dev,
+                           int k_fixed, const int* n_dev, int n_fixed, int n_max, int kernel,
+                           double gamma, double* gamma_out, float* K, int ldk, long long strideK,
+                           int nfold, cudaStream_t stream);
+/* SMO per (fold, class pair), pairs in libsvm's order; y: pool labels (ldy per fold); classes:
+ * sorted label values; balanced != 0: C_c = C * n / (n_classes * count_c) (sklearn
+ * class_weight='balanced'); eps = libsvm's tol; coef: [fold][ncls-1][ldc] in libsvm's sv_coef
+ * layout indexed by pool sample; rho: [fold][npair]; info: [fold][npair][2] = iterations,
+ * status (0 converged, 1 iteration cap, 2 class absent, 3 pair larger than m_max). */
+int cpsd_svc_fit_ovo(const float* K, int ldk, long long strideK, const int* y, int ldy,
+                     const int* n_dev, int n_fixed, const int* classes, int ncls, double C,
+                     int balanced, double eps, int max_iter, double* coef, int ldc, double* rho,
+                     int* info, int m_max, int nfold, cudaStream_t stream);
+/* votes of all pair decisions, first maximum wins (libsvm svm_predict_values); dec (optional):
+ * [fold][n_te_max][npair] */
+int cpsd_svc_predict_ovo(const float* St, int lds, long long strideS, const float* Ste, int ldt,
+                         long long strideT, const int* k_dev, int k_fixed, const int* n_dev,
+                         int n_fixed, int n_max, const int* n_te, int n_te_max, const int* y,
+                         int ldy, const int* classes, int ncls, int kernel, const double* gamma,
+                         const double* coef, int ldc, const double* rho, int* yhat, double* dec,
+                         int k_max, int nfold, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,134 @@
+"""Throughput of the BASELINE.json configurations other than the headline one:
+  1  two patients, pairwise CCA (PCA 0.9 and fixed 30), 5-fold
+  3  latent-size sweep 10..100 x {jointpca, cca, mcca}, 20-fold
+  4  electrode subsampling (grid / Poisson-disk) x 8 targets x 20 folds, pairwise CCA
+  5  per-call latency of transform + predict of a fitted config-2 model, batch 1 and 256
+Data resident in HBM, wall clock around a synchronised run (CUDA work only between the syncs),
+one warm-up run first.  Prints one JSON line per measurement."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+import cross_patient_speech_decoding_b200 as cp  # noqa: E402
+from cross_patient_speech_decoding_b200 import synthetic  # noqa: E402
+from cross_patient_speech_decoding_b200.engine import CVEngine  # noqa: E402
+from cross_patient_speech_decoding_b200.folds import cv_splits  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument('--configs', default='1,3,4,5')
+ap.add_argument('--iters', type=int, default=5, help='CV iterations per measurement')
+ap.add_argument('--dims', default='10,20,30,40,50,60,70,80,90,100')
+args = ap.parse_args()
+todo = set(args.configs.split(','))
+pts = bench.make_data()
+dev = [(torch.from_numpy(np.ascontiguousarray(X)).cuda(), y, ya) for X, y, ya in pts]
+
+
+def folds_for(y, n_splits, iters, seed0):
+    out = []
+    for it in range(iters):
+        np.random.seed(seed0 + it)
+        out += cv_splits(y, n_splits)
+    return out
+
+
+def timed(tag, eng, folds, extra=None):
+    eng.run(folds[:max(1, len(folds) // args.iters)])          # warm-up: workspaces, caches
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res = eng.run(folds)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    acc = float(np.mean(np.concatenate([yp == eng.views[0].y_host[te] for yp, (_, te) in zip(res['y_pred'], folds)])))
+    rec = dict(config=tag, folds=len(folds), folds_per_s=round(len(folds) / dt, 1),
+               ms_per_fold=round(1e3 * dt / len(folds), 3), accuracy=round(acc, 4),
+               k2=int(np.median(res['k2'])))
+    rec.update(extra or {})
+    print(json.dumps(rec), flush=True)
+    return res
+
+
+if '1' in todo:
+    for nc in (0.9, 30):
+        folds = folds_for(pts[0][1], 5, 4 * args.iters, 100)
+        eng = CVEngine(dev[0], dev[1:2], method='cca', n_comp=nc, use_tensor_cores=True, max_batch=148)
+        timed('1: 2 patients, CCA, n_comp=%s, 5-fold' % nc, eng, folds)
+
+if '3' in todo:
+    for d in [int(x) for x in args.dims.split(',')]:
+        for method in ('jointpca', 'cca', 'mcca'):
+            folds = folds_for(pts[0][1], 20, args.iters, 200)
+            kw = dict(method=method, n_comp=d, use_tensor_cores=True, max_batch=148)
+            if method == 'mcca':
+                kw.update(regs=0.5, pca_var=0.8)
+            if method == 'jointpca':
+                kw.update(max_batch=32)
+            eng = CVEngine(dev[0], dev[1:], **kw)
+            timed('3: 8 patients, %s, d=%d, 20-fold' % (method, d), eng, folds)
+
+if '4' in todo:
+    from cross_patient_speech_decoding_b200.processing_utils import device_subsample as ds
+    from cross_patient_speech_decoding_b200.processing_utils.grid_subsampling import sig_channels_in_windows
+    chan_map = np.arange(1, 129).reshape(8, 16)
+    sig = np.arange(1, 129)
+    subs = sig_channels_in_windows(chan_map, sig, (4, 8), (2, 4))[:6]     # 32-channel windows
+    res_dev = [ds.resident(p[0]) for p in pts]
+    t_all, n_all = 0.0, 0
+    for rep in range(2):                      # rep 0 = warm-up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n_all = 0
+        for si, sub in enumerate(subs):
+            cols = np.sort(np.asarray(sub).ravel())
+            for tgt in range(2 if rep == 0 else 8):
+                order = [tgt] + [p for p in range(8) if p != tgt]
+                views = []
+                for p in order:
+                    Xs = ds.gather_channels(res_dev[p], cols)
+                    views.append((Xs, pts[p][1], pts[p][2]))
+                folds = folds_for(pts[tgt][1], 20, 1, 300 + si)
+                eng = CVEngine(views[0], views[1:], method='cca', n_comp=0.9, use_tensor_cores=True, max_batch=148)
+                eng.run(folds)
+                n_all += len(folds)
+        torch.cuda.synchronize()
+        t_all = time.perf_counter() - t0
+    print(json.dumps(dict(config='4: %d grid subsamples x 8 targets x 20 folds, CCA (engine per unit)' % len(subs),
+                          folds=n_all, folds_per_s=round(n_all / t_all, 1), ms_per_fold=round(1e3 * t_all / n_all, 3))), flush=True)
+
+if '5' in todo:
+    from sklearn.pipeline import make_pipeline
+    from cross_patient_speech_decoding_b200.alignment.AlignMCCA import AlignMCCA
+    from cross_patient_speech_decoding_b200.decoders.cross_pt_decoders import crossPtDecoder_mcca
+    from cross_patient_speech_decoding_b200.decomposition.DimRedReshape import DimRedReshape
+    from cross_patient_speech_decoding_b200.decomposition.PCA import PCA
+    from cross_patient_speech_decoding_b200.svm import LinearSVC
+    Xt, yt, yat = pts[0]
+    np.random.seed(0)
+    tr, te = cv_splits(yt, 20)[0]
+    m = crossPtDecoder_mcca(pts[1:], make_pipeline(DimRedReshape(PCA, n_components=0.8), LinearSVC()),
+                            AlignMCCA, n_comp=30, regs=0.5, pca_var=0.8)
+    t0 = time.perf_counter()
+    m.fit(Xt[tr], yt[tr], y_align=yat[tr])
+    fit_ms = 1e3 * (time.perf_counter() - t0)
+    for nb in (1, 256):
+        Xb = np.ascontiguousarray(np.concatenate([Xt] * 2)[:nb])
+        for _ in range(5):
+            m.predict(Xb)
+        ts = []
+        for _ in range(200 if nb == 1 else 50):
+            t0 = time.perf_counter()
+            yp = m.predict(Xb)
+            ts.append(1e3 * (time.perf_counter() - t0))
+        ts = np.sort(ts)
+        print(json.dumps(dict(config='5: fitted config-2 model, predict() latency, host float64 in -> labels out',
+                              batch=nb, p50_ms=round(float(np.percentile(ts, 50)), 3),
+                              p99_ms=round(float(np.percentile(ts, 99)), 3),
+                              trials_per_s=round(nb / (np.median(ts) * 1e-3), 1), fit_ms=round(fit_ms, 1))), flush=True)
