@@ -77,14 +77,14 @@ _SIGS = {
     'cpsd_eig_topk_ws_elems': [c_int, c_int, c_int],
     'cpsd_eig_topk_voff': [c_int, c_int, c_int],
     'cpsd_eig_sym_topk': [_P, c_int, c_ll, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P,
-                          c_int, _P, _P, _P, c_int, c_float, _P],
+                          c_int, _P, _P, _P, c_int, c_float, c_int, _P],
     'cpsd_topk_tc_ws_elems': [c_int, c_int],
     'cpsd_topk_tc_map_bytes': [c_int],
     'cpsd_topk_tc_encode': [_P, c_int, c_ll, c_int, c_int, _P, _P, _P, _P],
     'cpsd_topk_tc_split_k': [_P, c_int, c_ll, c_int, c_int, _P, _P],
     'cpsd_topk_tc_kq': [_P, c_ll, _P, c_ll, c_int, c_int, c_int, _P, _P, _P],
     'cpsd_eig_sym_topk_tc': [_P, c_int, c_ll, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P,
-                             c_int, _P, _P, _P, c_int, c_float, _P, _P, c_int, _P],
+                             c_int, _P, _P, _P, c_int, c_float, _P, _P, c_int, c_int, _P],
     'cpsd_sgemm_batched': [c_int, c_int, c_int, c_int, c_float, _P, c_int, c_ll, _P, c_int, c_ll,
                            _P, c_int, c_ll, c_int, _P],
     'cpsd_chol_solve_f64': [_P, c_int, c_ll, c_int, _P, c_int, c_ll, c_int, _P, c_int, c_ll, _P, c_int,

@@ -184,9 +184,49 @@ k_sgemm(const float* __restrict__ A, int lda, long long strideA, const float* __
 // positive (rank-deficient block); the pivot is then replaced so the factor stays finite.
 // ---------------------------------------------------------------------------------------
 #define CH_LD 129
+// S (m x m, fp64, lower 32x32 tiles only) = Y^T Y with fp64 accumulation; Y: n x m row-major.
+// The Gram of the Cholesky-QR step: the block K Q has the condition number of the leading
+// spectrum (1e4 and more for low-rank-plus-noise data), which an fp32 Gram squares past 1/eps.
+__global__ void __launch_bounds__(256)
+k_gram_cols_f64(const float* __restrict__ Y, int ldy, long long strideY, int n, int m,
+                double* __restrict__ S, long long strideS) {
+  __shared__ float a[32][33], b[32][33];
+  int ti = 0, rem = blockIdx.x;           // lower-triangular tile index -> (ti, tj), tj <= ti
+  while (rem > ti) { rem -= ti + 1; ++ti; }
+  const int tj = rem;
+  const float* Yg = Y + (long long)blockIdx.y * strideY;
+  double* Sg = S + (long long)blockIdx.y * strideS;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int i0 = ti * 32, j0 = tj * 32;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int r0 = 0; r0 < n; r0 += 32) {
+    for (int r = ty; r < 32; r += 8) {
+      const bool ok = r0 + r < n;
+      a[r][tx] = (ok && i0 + tx < m) ? Yg[(long long)(r0 + r) * ldy + i0 + tx] : 0.f;
+      b[r][tx] = (ok && j0 + tx < m) ? Yg[(long long)(r0 + r) * ldy + j0 + tx] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) {
+      const double bv = (double)b[r][tx];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[e] = fma((double)a[r][ty + 8 * e], bv, acc[e]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int i = i0 + ty + 8 * e, j = j0 + tx;
+    if (i < m && j < m) Sg[(long long)i * m + j] = acc[e];
+  }
+}
+
 #define CH_NT 1024
+// TI = float: symmetric fp32 Gram (both triangles averaged); TI = double: lower triangle of an
+// fp64 Gram (k_gram_cols_f64)
+template <typename TI>
 __global__ void __launch_bounds__(CH_NT)
-k_chol_inv(const float* __restrict__ S, int lds, long long strideS, int m,
+k_chol_inv(const TI* __restrict__ S, int lds, long long strideS, int m,
            float* __restrict__ Rinv, int ldr, long long strideR, int* __restrict__ status) {
   // P: strict lower triangle + diagonal = Cholesky factor L; afterwards the strict upper
   // triangle receives X^T, X = L^{-1} (so P's upper triangle is R^{-1} off the diagonal)
@@ -196,15 +236,18 @@ k_chol_inv(const float* __restrict__ S, int lds, long long strideS, int m,
   __shared__ double s_piv;
   __shared__ int s_bad;
   const int prob = blockIdx.x;
-  const float* Sg = S + (long long)prob * strideS;
+  const TI* Sg = S + (long long)prob * strideS;
   const int tid = threadIdx.x;
   const int tx = tid & 31, ty = tid >> 5;
   if (tid == 0) s_bad = 0;
   for (int e = tid; e < m * m; e += CH_NT) {
     const int r = e / m, c = e - r * m;
-    P[r * CH_LD + c] = (c <= r) ? 0.5 * ((double)Sg[(long long)r * lds + c] +
-                                         (double)Sg[(long long)c * lds + r])
-                                : 0.0;
+    double v = 0.0;
+    if (c <= r) {
+      if (sizeof(TI) == 8) v = (double)Sg[(long long)r * lds + c];
+      else v = 0.5 * ((double)Sg[(long long)r * lds + c] + (double)Sg[(long long)c * lds + r]);
+    }
+    P[r * CH_LD + c] = v;
   }
   __syncthreads();
   double dmax = 0.0;
@@ -446,8 +489,24 @@ extern "C" int cpsd_chol_inv(const float* S, int lds, long long strideS, int m, 
   CPSD_CHECK_ARG(m > 0 && m <= 128, "chol_inv: m must be in 1..128");
   if (nprob == 0) return CPSD_OK;
   const size_t smem = 128 * CH_LD * sizeof(double);
-  CPSD_CUDA(cudaFuncSetAttribute(k_chol_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_chol_inv<<<nprob, CH_NT, smem, stream>>>(S, lds, strideS, m, Rinv, ldr, strideR, status);
+  CPSD_CUDA(cudaFuncSetAttribute(k_chol_inv<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_chol_inv<float><<<nprob, CH_NT, smem, stream>>>(S, lds, strideS, m, Rinv, ldr, strideR, status);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
+
+// Rinv = chol(Y^T Y)^{-T} with the Gram accumulated in fp64 (S64: nprob * m * m doubles of
+// workspace): the orthonormalisation step of the subspace iteration.
+static int chol_qr_factor(const float* Y, int ldy, long long strideY, int n, int m, double* S64,
+                          float* Rinv, int ldr, long long strideR, int* status, int nprob,
+                          cudaStream_t stream) {
+  const int nt = (m + 31) / 32;
+  k_gram_cols_f64<<<dim3(nt * (nt + 1) / 2, nprob), 256, 0, stream>>>(Y, ldy, strideY, n, m, S64,
+                                                                      (long long)m * m);
+  CPSD_LAUNCH_CHECK();
+  const size_t smem = 128 * CH_LD * sizeof(double);
+  CPSD_CUDA(cudaFuncSetAttribute(k_chol_inv<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_chol_inv<double><<<nprob, CH_NT, smem, stream>>>(S64, m, (long long)m * m, m, Rinv, ldr, strideR, status);
   CPSD_LAUNCH_CHECK();
   return CPSD_OK;
 }
@@ -468,7 +527,7 @@ extern "C" int cpsd_chol_solve_f64(const double* S, int lds, long long strideS, 
 
 // workspace floats: per problem  Q,Y (2 n_pad m)  +  VV (2 n_pad m)  +  S, Rinv, H, W (4 m m)
 extern "C" long long cpsd_eig_topk_ws_elems(int n_pad, int m, int nprob) {
-  return (long long)nprob * (4LL * n_pad * m + 4LL * m * m);
+  return (long long)nprob * (4LL * n_pad * m + 5LL * m * m);     // S holds doubles
 }
 
 // Leading m (<= 128) eigen-pairs of nprob symmetric PSD matrices K (n_pad x n_pad, leading
@@ -493,7 +552,7 @@ static int eig_sym_topk_impl(float* K, int ld, long long stride, int n_pad, cons
                              int n_fixed, int nprob, int m, int iters, int init, float* ws,
                              float* evals, int ld_e, float* total, float* resid, int* status,
                              int eig_sweeps, float eig_tol, float* tc_ws, const void* map_dev,
-                             int tf32_iters, cudaStream_t stream) {
+                             int tf32_iters, int f64_gram, cudaStream_t stream) {
   CPSD_CHECK_ARG(n_pad > 0 && ld >= n_pad, "eig_sym_topk: bad dims");
   CPSD_CHECK_ARG(m > 0 && m <= 128 && (m % 4) == 0 && m <= n_pad, "eig_sym_topk: m must be a multiple of 4 in 4..128");
   CPSD_CHECK_ARG(ld_e >= m && iters >= 0, "eig_sym_topk: bad ld_e / iters");
@@ -501,8 +560,8 @@ static int eig_sym_topk_impl(float* K, int ld, long long stride, int n_pad, cons
   const long long sQY = 2LL * n_pad * m, sMM = (long long)m * m;
   float* QY = ws;                               // [prob][Q | Y]
   float* VV = QY + (long long)nprob * sQY;      // [prob][V | KV]
-  float* S = VV + (long long)nprob * sQY;
-  float* Rinv = S + (long long)nprob * sMM;
+  double* S = reinterpret_cast<double*>(VV + (long long)nprob * sQY);   // fp64 Gram (8-byte aligned:
+  float* Rinv = reinterpret_cast<float*>(S) + 2LL * nprob * sMM;        //  every offset is even)
   float* H = Rinv + (long long)nprob * sMM;
   float* W = H + (long long)nprob * sMM;
   float* Q = QY;
@@ -530,8 +589,10 @@ static int eig_sym_topk_impl(float* K, int ld, long long stride, int n_pad, cons
                                 stream));
   }
   auto orth = [&](const float* src) -> int {   // Q <- src * chol(src^T src)^{-1}
-    CPSD_TRY(launch_sgemm<1>(src, m, sQY, src, m, sQY, S, m, sMM, m, m, n_pad, 1.f, nprob, stream));
-    CPSD_TRY(cpsd_chol_inv(S, m, sMM, m, Rinv, m, sMM, status, nprob, stream));
+    if (f64_gram) return chol_qr_factor(src, m, sQY, n_pad, m, S, Rinv, m, sMM, status, nprob, stream);
+    float* S32 = reinterpret_cast<float*>(S);
+    CPSD_TRY(launch_sgemm<1>(src, m, sQY, src, m, sQY, S32, m, sMM, m, m, n_pad, 1.f, nprob, stream));
+    CPSD_TRY(cpsd_chol_inv(S32, m, sMM, m, Rinv, m, sMM, status, nprob, stream));
     return CPSD_OK;
   };
   if (init) {
@@ -569,11 +630,16 @@ static int eig_sym_topk_impl(float* K, int ld, long long stride, int n_pad, cons
 extern "C" int cpsd_eig_sym_topk(float* K, int ld, long long stride, int n_pad, const int* n_dev,
                                  int n_fixed, int nprob, int m, int iters, int init, float* ws,
                                  float* evals, int ld_e, float* total, float* resid, int* status,
-                                 int eig_sweeps, float eig_tol, cudaStream_t stream) {
+                                 int eig_sweeps, float eig_tol, int f64_gram, cudaStream_t stream) {
   return eig_sym_topk_impl(K, ld, stride, n_pad, n_dev, n_fixed, nprob, m, iters, init, ws, evals, ld_e,
-                           total, resid, status, eig_sweeps, eig_tol, nullptr, nullptr, 0, stream);
+                           total, resid, status, eig_sweeps, eig_tol, nullptr, nullptr, 0, f64_gram,
+                           stream);
 }
 
+// f64_gram != 0: the Gram of every Cholesky-QR step is accumulated in fp64 (k_gram_cols_f64) --
+// needed when the leading spectrum spans more than ~3e3 (low-rank signal over a noise floor),
+// where an fp32 Gram of K Q is no longer positive definite; costs ~0.5 ms per 138 problems and
+// step, so callers try the fp32 Gram first and switch when status reports a failed pivot.
 // Same solver with K Q on the tensor cores (tcgen05, tc_gram.cu): tc_ws = cpsd_topk_tc_ws_elems()
 // floats, map_dev = the tensor maps written by cpsd_topk_tc_encode for this K / tc_ws; the
 // first tf32_iters iterations of a fresh start use single-pass TF32, the rest 3xTF32.
@@ -581,8 +647,9 @@ extern "C" int cpsd_eig_sym_topk_tc(float* K, int ld, long long stride, int n_pa
                                     int n_fixed, int nprob, int m, int iters, int init, float* ws,
                                     float* evals, int ld_e, float* total, float* resid, int* status,
                                     int eig_sweeps, float eig_tol, float* tc_ws, const void* map_dev,
-                                    int tf32_iters, cudaStream_t stream) {
+                                    int tf32_iters, int f64_gram, cudaStream_t stream) {
   CPSD_CHECK_ARG(tc_ws != nullptr && map_dev != nullptr, "eig_sym_topk_tc: tc_ws / map_dev is NULL");
   return eig_sym_topk_impl(K, ld, stride, n_pad, n_dev, n_fixed, nprob, m, iters, init, ws, evals, ld_e,
-                           total, resid, status, eig_sweeps, eig_tol, tc_ws, map_dev, tf32_iters, stream);
+                           total, resid, status, eig_sweeps, eig_tol, tc_ws, map_dev, tf32_iters,
+                           f64_gram, stream);
 }

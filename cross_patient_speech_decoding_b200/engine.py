@@ -93,7 +93,19 @@ class CVEngine:
                  dcd_epochs=0, max_newton=60, tol_newton=1e-9, tol_dcd=1e-4,
                  eig_sweeps=12, eig_tol=3e-7, use_tensor_cores=False, pool_solver='auto',
                  topk_block=128, topk_iters=8, topk_tol=5e-6, topk_rounds=3, n_lanes=2, lane=0,
-                 topk_tf32_iters=5):
+                 topk_tf32_iters=5, topk_gap_tol=0.05, decoder='linear', class_weight=None, svc_tol=1e-3,
+                 svc_gamma='scale', svc_max_iter=1000000):
+        # decoder: 'linear' = one-vs-rest squared-hinge linear SVM (the north star's dual-CD
+        # decoder); 'svc_rbf' / 'svc_linear' = libsvm-style C-SVC with one-vs-one votes, the
+        # reference scripts' literal SVC(kernel=..., class_weight=...)
+        assert decoder in ('linear', 'svc_rbf', 'svc_linear')
+        assert class_weight in (None, 'balanced')
+        self.decoder = decoder
+        self.class_weight = class_weight
+        self.svc_tol = float(svc_tol)
+        self.svc_gamma = -1.0 if svc_gamma == 'scale' else float(svc_gamma)
+        self.svc_max_iter = int(svc_max_iter)
+        self.topk_gap_tol = float(topk_gap_tol)
         self.ctx = Context.get(device)
         self.lane = int(lane)
         self.stream = _lane_stream(self.ctx.device, self.lane)
@@ -130,7 +142,7 @@ class CVEngine:
         # decoder-stage PCA eigen-solver: 'topk' = block subspace iteration for the leading
         # components (falls back to the full solver when the requested variance is not reached
         # inside the block), 'full' = block Jacobi of the whole Gram, 'auto' = topk when the
-        # pooled matrix is large enough for it to pay
+        # pooled matrix is large enough for it to pay (at least 3 blocks of rows and columns)
         assert pool_solver in ('auto', 'topk', 'full')
         self.pool_solver = pool_solver
         self.topk_block = int(topk_block)
@@ -256,7 +268,8 @@ class CVEngine:
         self.eig_vecs(tag, n_pad, nprob, perm, ptr(None), nc, nc, evecs)
         return evals, evecs
 
-    def eig_topk(self, K, n_pad, n_dev, nprob, m, evals, tag, thr, mode, kcap, k2):
+    def eig_topk(self, K, n_pad, n_dev, nprob, m, evals, tag, thr, mode, kcap, k2, tol=None,
+                 gap_tol=None):
         """Leading eigen-pairs of K (nprob, n_pad, n_pad) by subspace iteration; K keeps its
         leading block.  Fills evals / k2 and returns (V tensor view, ldv, strideV) when every
         problem reached its component count inside the block with converged Ritz pairs, else
@@ -270,8 +283,10 @@ class CVEngine:
         status = self.ws(tag + '_tkst', (nprob,), I32)
         voff = int(ctx.lib.cpsd_eig_topk_voff(n_pad, m, nprob))
         V = ws[voff:voff + nprob * 2 * n_pad * m]
-        info = {'rounds': 0, 'ok': False}
+        info = {'rounds': 0, 'ok': False, 'tag': tag}
         self.stats['topk'] = info
+        self.stats.setdefault('topk_log', []).append(info)
+        del self.stats['topk_log'][:-16]
         tc = self.use_tc and m == 128 and n_pad % 128 == 0
         if tc:
             # K Q on the tensor cores: hi/lo workspace + tensor maps (re-encoded only when the
@@ -289,35 +304,70 @@ class CVEngine:
                 ctx.call('cpsd_topk_tc_encode', ptr(K), n_pad, n_pad * n_pad, n_pad, nprob, ptr(tcw),
                          ctypes.c_void_p(mp), ctypes.c_void_p(stage.data_ptr()))
                 cache[tag] = (key, stage)
-        for rnd in range(self.topk_rounds):
+        tol = self.topk_tol if tol is None else tol
+        prev = None
+        # Gram of the Cholesky-QR steps: fp32 first; a tag whose block once lost rank that way
+        # (leading spectrum spanning > ~3e3) uses the fp64-accumulated Gram from then on
+        f64 = getattr(self, '_tk_f64', None)
+        if f64 is None:
+            f64 = self._tk_f64 = {}
+        # up to topk_rounds rounds; more (at most twice as many) only while every extra round
+        # still shrinks the worst residual 4x -- far cheaper than the full solver it avoids
+        rnd, fresh = 0, 1
+        while rnd < 2 * self.topk_rounds:
             if tc:
                 ctx.call('cpsd_eig_sym_topk_tc', ptr(K), n_pad, n_pad * n_pad, n_pad, _p(n_dev), 0,
-                         nprob, m, self.topk_iters, 1 if rnd == 0 else 0, ptr(ws), ptr(evals),
+                         nprob, m, self.topk_iters, fresh, ptr(ws), ptr(evals),
                          evals.shape[-1], ptr(tot), ptr(resid), ptr(status), self.eig_sweeps + 3,
-                         self.eig_tol, ptr(tcw), ctypes.c_void_p(mp), self.topk_tf32_iters)
+                         self.eig_tol, ptr(tcw), ctypes.c_void_p(mp), self.topk_tf32_iters,
+                         int(f64.get(tag, False)))
             else:
                 ctx.call('cpsd_eig_sym_topk', ptr(K), n_pad, n_pad * n_pad, n_pad, _p(n_dev), 0,
-                         nprob, m, self.topk_iters, 1 if rnd == 0 else 0, ptr(ws), ptr(evals),
+                         nprob, m, self.topk_iters, fresh, ptr(ws), ptr(evals),
                          evals.shape[-1], ptr(tot), ptr(resid), ptr(status), self.eig_sweeps + 3,
-                         self.eig_tol)
+                         self.eig_tol, int(f64.get(tag, False)))
             ctx.call('cpsd_select_k_total', ptr(evals), evals.shape[-1], ptr(None), m, ptr(tot),
                      thr, mode, 1, min(kcap, m), ptr(k2), 1, nprob)
             yield 'sync'
             k2h = k2.cpu().numpy()
             rh = resid.cpu().numpy()
             ev0 = evals[:, 0].cpu().numpy()
-            info['rounds'] = rnd + 1
+            rnd += 1
+            fresh = 0
+            info['rounds'] = rnd
+            info['k2_max'] = int(k2h.max())
+            info['f64_gram'] = bool(f64.get(tag, False))
             if status.cpu().numpy().any():
-                return None                       # rank-deficient block
+                if not f64.get(tag, False):
+                    f64[tag] = True            # start over with the fp64 Gram
+                    rnd, fresh, prev = 0, 1, None
+                    continue
+                info['why'] = 'rank-deficient block'
+                return None
             if mode == 0 and (k2h >= m - 8).any():
-                return None                       # variance threshold not crossed inside the block
+                info['why'] = 'variance threshold not crossed inside the block'
+                return None
             worst = max(float(rh[f, :k2h[f]].max()) / max(float(ev0[f]), 1e-30)
                         for f in range(nprob))
             info['resid'] = worst
-            if worst <= self.topk_tol:
+            # the retained subspace is only as good as residual / (gap at the cut): with a
+            # near-degenerate cut (flat noisy spectra) the block result is left to the full solver
+            evh = evals[:, :m].cpu().numpy()
+            kk = np.clip(k2h, 1, m - 1)
+            ar = np.arange(nprob)
+            gap = evh[ar, kk - 1] - evh[ar, kk]
+            rmax = np.array([rh[f, :k2h[f]].max() if k2h[f] > 0 else 0.0 for f in range(nprob)])
+            gtol = self.topk_gap_tol if gap_tol is None else gap_tol
+            gap_ok = bool((rmax <= gtol * np.maximum(gap, 0.0)).all()) or not np.isfinite(gtol)
+            info['gap_ok'] = gap_ok
+            if worst <= tol and gap_ok:
                 info['ok'] = True
                 self._k2_max = max(int(k2h.max()), 1)
                 return V, m, 2 * n_pad * m
+            if rnd >= self.topk_rounds and (prev is None or worst > 0.25 * prev):
+                info['why'] = 'residual stalled'
+                return None
+            prev = worst
         return None
 
     # ------------------------------------------------------------------ tensor-core projection
@@ -847,7 +897,7 @@ class CVEngine:
         use_topk = (self.pool_solver != 'full' and n_pad > 128 and mode in (0, 3)
                     and (mode == 0 or int(thr) <= m - 8)
                     and (self.pool_solver == 'topk'
-                         or (min(n_pool) - 1 >= 2 * m and F >= 2 * m)))
+                         or (min(n_pool) - 1 >= 3 * m and F >= 3 * m)))
         perm_p = ptr(None)
         if use_topk:
             got = yield from self.eig_topk(Kall, n_pad, npool_dev, B, m, evals, 'pool', thr, mode,
@@ -883,9 +933,25 @@ class CVEngine:
         return evals, k2, St, Ste, V, sweeps, kcap
 
     def _svm_stage(self, pk2, B, St, Ste, k2, kcap, n_pad, n_pool, n_te, o_ypool, ypool_ld,
-                   o_nte, n_te_max):
+                   o_nte, n_te_max, ypool=None):
         ctx = self.ctx
         ncls = len(self.classes)
+        if self.decoder != 'linear':
+            # C-SVC: no descriptors; the largest class pair of the batch sizes the solver's
+            # shared memory
+            valid = np.arange(ypool.shape[1])[None, :] < np.asarray(n_pool)[:, None]
+            ci = np.searchsorted(self.classes, ypool[valid])
+            fo = np.broadcast_to(np.arange(B)[:, None], ypool.shape)[valid]
+            cnt = np.bincount(fo * ncls + ci, minlength=B * ncls).reshape(B, ncls)
+            top = np.sort(cnt, axis=1)
+            m_max = int((top[:, -1] + top[:, -2]).max())
+            npair = ncls * (ncls - 1) // 2
+            state = dict(m_max=m_max, coef=self.ws('svc_coef', (B, ncls - 1, n_pad), torch.float64),
+                         rho=self.ws('svc_rho', (B, npair), torch.float64),
+                         gamma=self.ws('svc_gamma', (B,), torch.float64),
+                         K=self.ws('svc_K', (B, n_pad, n_pad)))
+            info = self.ws('svc_info', (B, npair, 2), I32)
+            return state, info, np.zeros(0, dtype=_lib.SVM_DESC)
         W = self.ws('svm_W', (B, ncls, kcap + 1), torch.float64)
         info = self.ws('svm_info', (B, ncls, 4), I32)
         recs = np.zeros(B * ncls, dtype=_lib.SVM_DESC)
@@ -902,6 +968,37 @@ class CVEngine:
         recs['C'], recs['tol_dcd'], recs['tol_newton'] = self.Csvm, self.tol_dcd, self.tol_newton
         recs['max_newton'], recs['dcd_epochs'] = self.max_newton, self.dcd_epochs
         return W, info, recs
+
+    def _decode(self, pk, d_svm, W, info, B, St, Ste, k2, kcap, n_pad, o_ypool, ypool_ld, o_npool,
+                o_nte, n_te_max):
+        """Fits the decoder of every fold of the batch on its pooled scores and labels the
+        held-out trials; returns the (B, n_te_max) label tensor."""
+        ctx = self.ctx
+        ncls = len(self.classes)
+        yhat = self.ws('yhat', (B, n_te_max), I32)
+        nte_dev = ctypes_int_ptr(pk.iaddr(o_nte))
+        if self.decoder == 'linear':
+            # shared memory of the solver is sized by the largest k2 of the batch, not by its cap
+            ctx.call('cpsd_svm_fit_ovr', pk.daddr(d_svm), B * ncls, min(kcap, self._k2_max), n_pad)
+            ctx.call('cpsd_svm_predict_ovr', ptr(Ste), n_te_max, kcap * n_te_max, ptr(W), kcap + 1,
+                     ncls * (kcap + 1), ptr(k2), 0, nte_dev, n_te_max, ptr(self.classes_dev), ncls,
+                     ptr(yhat), ptr(None), B)
+            return yhat
+        sv = W
+        kid = 1 if self.decoder == 'svc_rbf' else 0
+        npool_dev = ctypes_int_ptr(pk.iaddr(o_npool))
+        ypool_dev = ctypes_int_ptr(pk.iaddr(o_ypool))
+        ctx.call('cpsd_svc_kernel_matrix', ptr(St), n_pad, kcap * n_pad, ptr(k2), 0, npool_dev, 0, n_pad,
+                 kid, self.svc_gamma, ptr(sv['gamma']), ptr(sv['K']), n_pad, n_pad * n_pad, B)
+        ctx.call('cpsd_svc_fit_ovo', ptr(sv['K']), n_pad, n_pad * n_pad, ypool_dev, ypool_ld, npool_dev, 0,
+                 ptr(self.classes_dev), ncls, self.Csvm, int(self.class_weight == 'balanced'),
+                 self.svc_tol, self.svc_max_iter, ptr(sv['coef']), n_pad, ptr(sv['rho']), ptr(info),
+                 sv['m_max'], B)
+        ctx.call('cpsd_svc_predict_ovo', ptr(St), n_pad, kcap * n_pad, ptr(Ste), n_te_max,
+                 kcap * n_te_max, ptr(k2), 0, npool_dev, 0, n_pad, nte_dev, n_te_max, ypool_dev, ypool_ld,
+                 ptr(self.classes_dev), ncls, kid, ptr(sv['gamma']), ptr(sv['coef']), n_pad,
+                 ptr(sv['rho']), ptr(yhat), ptr(None), min(kcap, 1024), B)
+        return yhat
 
     # ------------------------------------------------------------------ MCCA batch
     def _batch_mcca_gen(self, batch, want_details, align_only, pk):
@@ -1265,7 +1362,7 @@ class CVEngine:
             St = self.ws('pool_St', (B, kcap, n_pad))
             k2 = self.ws('pool_k2', (B,), I32)
             W, info, r_svm = self._svm_stage(pk, B, St, None, k2, kcap, n_pad, n_pool, n_te, o_ypool,
-                                             n_pad, o_nte, n_te_max)
+                                             n_pad, o_nte, n_te_max, ypool)
             d_svm = pk.add_descs(r_svm)
         pk.upload()
         self.stats['host_pack_ms'] = self.stats.get('host_pack_ms', 0.0) + \
@@ -1296,8 +1393,13 @@ class CVEngine:
             Vj = None
             mj = self.topk_block
             if nJ_pad > 128 and Q <= mj - 8 and self.pool_solver != 'full':
+                # above 1000 concatenated channels sklearn's PCA itself switches to randomized SVD
+                # (7 power iterations, random start: decomposition/_pca.py 'auto' policy), so
+                # the trailing noise-floor components are not defined to better than that
+                jtol = self.topk_tol if nJ <= 1000 else max(self.topk_tol, 1e-3)
                 got = yield from self.eig_topk(covj, nJ_pad, nj_dev, B, mj, evj, 'joint', float(Q), 3,
-                                               nJ_pad, kj)
+                                               nJ_pad, kj, tol=jtol,
+                                               gap_tol=None if nJ <= 1000 else float('inf'))
                 if got is not None:
                     Vj, ldvj, sVj = got
             if Vj is None:
@@ -1406,14 +1508,8 @@ class CVEngine:
             pk, d_p1, d_p2, B, Zall, pmu, Kall, n_pad, F, n_pool, n_te, o_npool, o_nall, o_ypool,
             n_te_max, want_details)
         self.mark('svm')
-        # shared memory of the solver is sized by the largest k2 of the batch, not by its cap
-        ctx.call('cpsd_svm_fit_ovr', pk.daddr(d_svm), B * len(self.classes),
-                 min(kcap, self._k2_max), n_pad)
-        yhat = self.ws('yhat', (B, n_te_max), I32)
-        ncls = len(self.classes)
-        ctx.call('cpsd_svm_predict_ovr', ptr(Ste), n_te_max, kcap * n_te_max, ptr(W), kcap + 1,
-                 ncls * (kcap + 1), ptr(k2), 0, ctypes_int_ptr(pk.iaddr(o_nte)), n_te_max,
-                 ptr(self.classes_dev), ncls, ptr(yhat), ptr(None), B)
+        yhat = self._decode(pk, d_svm, W, info, B, St_, Ste, k2, kcap, n_pad, o_ypool, n_pad, o_npool,
+                            o_nte, n_te_max)
         self.mark('end')
         yield 'sync'
         yh = yhat.cpu().numpy()

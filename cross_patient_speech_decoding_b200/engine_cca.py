@@ -212,7 +212,7 @@ def batch_cca(eng, batch, want_details):
     St = eng.ws('pool_St', (B, kcap, n_pad))
     k2 = eng.ws('pool_k2', (B,), I32)
     W, info, r_svm = eng._svm_stage(pk, B, St, None, k2, kcap, n_pad, n_pool, n_te, o_ypool, n_pad,
-                                    o_nte, n_te_max)
+                                    o_nte, n_te_max, ypool)
     d_svm = pk.add_descs(r_svm)
     pk.upload()
 
@@ -238,11 +238,8 @@ def batch_cca(eng, batch, want_details):
         n_te_max, want_details)
     ncls = len(eng.classes)
     eng.mark('svm')
-    ctx.call('cpsd_svm_fit_ovr', pk.daddr(d_svm), B * ncls, min(kcap, eng._k2_max), n_pad)
-    yhat = eng.ws('yhat', (B, n_te_max), I32)
-    ctx.call('cpsd_svm_predict_ovr', ptr(Ste), n_te_max, kcap * n_te_max, ptr(W), kcap + 1,
-             ncls * (kcap + 1), ptr(k2), 0, ctypes_int_ptr(pk.iaddr(o_nte)), n_te_max,
-             ptr(eng.classes_dev), ncls, ptr(yhat), ptr(None), B)
+    yhat = eng._decode(pk, d_svm, W, info, B, St_, Ste, k2, kcap, n_pad, o_ypool, n_pad, o_npool, o_nte,
+                       n_te_max)
     eng.mark('end')
     yh = yhat.cpu().numpy()
     k2h = k2.cpu().numpy()

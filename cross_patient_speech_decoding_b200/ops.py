@@ -137,7 +137,7 @@ def lstsq_gram(X, Y, device=None):
 
 
 def eig_topk(A, m=128, iters=8, rounds=1, n=None, max_sweeps=15, tol=3e-7, device=None,
-             tensor_cores=False, tf32_iters=5):
+             tensor_cores=False, tf32_iters=5, f64_gram=False):
     """Leading m eigen-pairs of symmetric PSD matrices A (nprob, n, n) by subspace iteration.
     Returns dict(evals (nprob, m), V (nprob, n, m), total, resid (nprob, m), status)."""
     ctx = _ctx(device)
@@ -164,11 +164,11 @@ def eig_topk(A, m=128, iters=8, rounds=1, n=None, max_sweeps=15, tol=3e-7, devic
         if tensor_cores:
             ctx.call('cpsd_eig_sym_topk_tc', ptr(Ad), n_pad, n_pad * n_pad, n_pad, ptr(nd), 0, nprob,
                      m, iters, 1 if r == 0 else 0, ptr(ws), ptr(evals), n_pad, ptr(tot), ptr(resid),
-                     ptr(st), max_sweeps, tol, ptr(tcw), ctypes.c_void_p(mp), tf32_iters)
+                     ptr(st), max_sweeps, tol, ptr(tcw), ctypes.c_void_p(mp), tf32_iters, int(f64_gram))
         else:
             ctx.call('cpsd_eig_sym_topk', ptr(Ad), n_pad, n_pad * n_pad, n_pad, ptr(nd), 0, nprob,
                      m, iters, 1 if r == 0 else 0, ptr(ws), ptr(evals), n_pad, ptr(tot),
-                     ptr(resid), ptr(st), max_sweeps, tol)
+                     ptr(resid), ptr(st), max_sweeps, tol, int(f64_gram))
     voff = int(ctx.lib.cpsd_eig_topk_voff(n_pad, m, nprob))
     V = ws[voff:voff + nprob * 2 * n_pad * m].view(nprob, 2 * n_pad, m)[:, :nn, :]
     return dict(evals=evals.cpu().numpy()[:, :m], V=V.cpu().numpy(), total=tot.cpu().numpy(),

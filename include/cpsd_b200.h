@@ -170,13 +170,16 @@ int cpsd_select_k_total(const float* evals, int ld_e, const int* n_dev, int n_fi
  * >= n) is zeroed, K is otherwise preserved.  ws: cpsd_eig_topk_ws_elems() floats; the
  * eigenvectors land at ws + cpsd_eig_topk_voff() as (n_pad x m) per problem, row stride m,
  * problem stride 2*n_pad*m.  resid[prob][j] = ||K v_j - theta_j v_j||; status bit 0 = the
- * block lost rank.  init = 0 continues from the Ritz vectors of the previous call. */
+ * block lost rank.  init = 0 continues from the Ritz vectors of the previous call.
+ * f64_gram != 0 accumulates the Gram of every Cholesky-QR step in fp64: needed when the leading
+ * spectrum spans more than ~3e3 (an fp32 Gram of K Q is then no longer positive definite and
+ * status reports it); callers try 0 first. */
 long long cpsd_eig_topk_ws_elems(int n_pad, int m, int nprob);
 long long cpsd_eig_topk_voff(int n_pad, int m, int nprob);
 int cpsd_eig_sym_topk(float* K, int ld, long long stride, int n_pad, const int* n_dev, int n_fixed,
                       int nprob, int m, int iters, int init, float* ws, float* evals, int ld_e,
                       float* total, float* resid, int* status, int eig_sweeps, float eig_tol,
-                      cudaStream_t stream);
+                      int f64_gram, cudaStream_t stream);
 /* same solver with Y = K Q on the tensor cores (tcgen05 kind::tf32 + TMA): single-pass TF32
  * for the first tf32_iters iterations of a fresh start (the iteration is self-correcting),
  * 3xTF32 afterwards.  tc_ws: cpsd_topk_tc_ws_elems() floats; map_dev: cpsd_topk_tc_map_bytes()
@@ -194,7 +197,7 @@ int cpsd_eig_sym_topk_tc(float* K, int ld, long long stride, int n_pad, const in
                          int n_fixed, int nprob, int m, int iters, int init, float* ws, float* evals,
                          int ld_e, float* total, float* resid, int* status, int eig_sweeps,
                          float eig_tol, float* tc_ws, const void* map_dev, int tf32_iters,
-                         cudaStream_t stream);
+                         int f64_gram, cudaStream_t stream);
 /* building blocks of the above, exported for the kernel-level parity tests:
  * C = alpha op(A) B (batched, element strides; trans_a: A stored K x M), and the inverse of
  * the upper Cholesky factor of an m x m (m <= 128) Gram (fp64 in shared memory). */

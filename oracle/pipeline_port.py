@@ -141,7 +141,7 @@ def pool_none(Xtr, ytr, cross, n_comp):
 
 
 def run_fold(target, cross, train, test, method='mcca', n_comp=None, regs=0.5, pca_var=0.8,
-             decoder_var=0.8, C=1.0):
+             decoder_var=0.8, C=1.0, decoder='linear', class_weight=None):
     """One unit of scripts/aligned_decode_svm_ncv.py:344-442 with the pinned decoder
     DimRedReshape(PCA, decoder_var) -> LinearSVC(dual=False) (DimRedReshape.py:36-65).
     Returns (y_pred, k2)."""
@@ -162,5 +162,13 @@ def run_fold(target, cross, train, test, method='mcca', n_comp=None, regs=0.5, p
     else:
         raise ValueError(method)
     pca = PCA(n_components=decoder_var).fit(Xp)
-    svm = LinearSVC(dual=False, C=C, tol=1e-10, max_iter=100000).fit(pca.transform(Xp), yp)
+    if decoder == 'linear':
+        svm = LinearSVC(dual=False, C=C, tol=1e-10, max_iter=100000)
+    else:
+        # the scripts' literal decoder (scripts/aligned_decode_svm_ncv.py:313-317: rbf, balanced;
+        # aligned_decode_svm.py:262: linear) -- sklearn's SVC is libsvm itself
+        from sklearn.svm import SVC
+        svm = SVC(kernel={'svc_rbf': 'rbf', 'svc_linear': 'linear'}[decoder], C=C,
+                  class_weight=class_weight)
+    svm.fit(pca.transform(Xp), yp)
     return svm.predict(pca.transform(Zte)), int(pca.n_components_)

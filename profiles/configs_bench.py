@@ -23,7 +23,7 @@ from cross_patient_speech_decoding_b200.engine import CVEngine  # noqa: E402
 from cross_patient_speech_decoding_b200.folds import cv_splits  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument('--configs', default='1,3,4,5')
+ap.add_argument('--configs', default='1,2s,3,4,5')
 ap.add_argument('--iters', type=int, default=5, help='CV iterations per measurement')
 ap.add_argument('--dims', default='10,20,30,40,50,60,70,80,90,100')
 args = ap.parse_args()
@@ -47,7 +47,7 @@ def timed(tag, eng, folds, extra=None):
     res = eng.run(folds)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    acc = float(np.mean(np.concatenate([yp == eng.views[0].y_host[te] for yp, (_, te) in zip(res['y_pred'], folds)])))
+    acc = float(np.mean(np.concatenate([yp == eng.views[0].y[te] for yp, (_, te) in zip(res['y_pred'], folds)])))
     rec = dict(config=tag, folds=len(folds), folds_per_s=round(len(folds) / dt, 1),
                ms_per_fold=round(1e3 * dt / len(folds), 3), accuracy=round(acc, 4),
                k2=int(np.median(res['k2'])))
@@ -62,6 +62,15 @@ if '1' in todo:
         eng = CVEngine(dev[0], dev[1:2], method='cca', n_comp=nc, use_tensor_cores=True, max_batch=148)
         timed('1: 2 patients, CCA, n_comp=%s, 5-fold' % nc, eng, folds)
 
+if '2s' in todo:
+    for dec, cw in (('svc_rbf', 'balanced'), ('svc_linear', None), ('linear', None)):
+        folds = folds_for(pts[0][1], 20, args.iters, 150)
+        eng = CVEngine(dev[0], dev[1:], method='mcca', n_comp=30, regs=0.5, pca_var=0.8, decoder=dec,
+                       class_weight=cw, use_tensor_cores=True, max_batch=148)
+        eng.profile = True
+        timed('2: 8 patients, MCCA, 20-fold, decoder=%s class_weight=%s' % (dec, cw), eng, folds)
+        print('   stages ms:', {k: round(v, 2) for k, v in eng.collect_marks().items()}, flush=True)
+
 if '3' in todo:
     for d in [int(x) for x in args.dims.split(',')]:
         for method in ('jointpca', 'cca', 'mcca'):
@@ -72,7 +81,12 @@ if '3' in todo:
             if method == 'jointpca':
                 kw.update(max_batch=32)
             eng = CVEngine(dev[0], dev[1:], **kw)
-            timed('3: 8 patients, %s, d=%d, 20-fold' % (method, d), eng, folds)
+            eng.profile = True
+            try:
+                timed('3: 8 patients, %s, d=%d, 20-fold' % (method, d), eng, folds)
+                print('   stages ms:', {k: round(v, 2) for k, v in eng.collect_marks().items()}, flush=True)
+            except ValueError as e:          # mvlearn raises too when n_components exceeds the summed ranks
+                print(json.dumps(dict(config='3: 8 patients, %s, d=%d' % (method, d), error=str(e)[:80])), flush=True)
 
 if '4' in todo:
     from cross_patient_speech_decoding_b200.processing_utils import device_subsample as ds
