@@ -645,6 +645,7 @@ class CVEngine:
             ln._extra_lanes = None                    # no reference cycles: engines must die by
             ln._ws, ln._vs, ln._tc_stage, ln._marks = {}, None, None, []   # refcount
             ln._xc = None
+            ln._jc = None
             ln._tkc_key = None
             ln.packA, ln.packB = HostPack(self.ctx), HostPack(self.ctx)
             ln.packM = [HostPack(self.ctx), HostPack(self.ctx)]
@@ -1216,26 +1217,51 @@ class CVEngine:
             mub = np.zeros((B, P), dtype=np.int64)             # no centring at transform time
             Gj = self.ws('j_G', (B, nJ, nJ), torch.float64)
             sj = self.ws('j_s', (B, nJ))
-            pairs = [(u, v) for u in range(P) for v in range(u, P)]
-            npair = len(pairs)
-            pu = np.array([p_[0] for p_ in pairs], dtype=np.int64)
-            pv = np.array([p_[1] for p_ in pairs], dtype=np.int64)
-            r_jg = np.zeros(B * npair, dtype=_lib.GRAM_TN_DESC)
-            ff = np.repeat(fi, npair)
-            uu, vv = np.tile(pu, B), np.tile(pv, B)
+            # The blocks between cross patients (and their column sums) depend only on the
+            # shared class set, not on the fold: they are computed once per set into a cache
+            # slot and copied into every fold's Gram; per fold only the target's row of blocks
+            # is new (the reference refits everything for every fold).
+            jc = getattr(self, '_jc', None)
+            if jc is None or jc['nJ'] != nJ or jc['cap'] < len(keys_u):
+                cap = max(8, len(keys_u) + 8)
+                jc = self._jc = dict(nJ=nJ, cap=cap, keys={}, G=self.ctx.zeros((cap, nJ, nJ), torch.float64),
+                                     s=self.ctx.zeros((cap, nJ)))
+            if len(jc['keys']) + len(set(keys_u) - set(jc['keys'])) > jc['cap']:
+                jc['keys'].clear()
+            miss_u = [u for u, ku in enumerate(keys_u) if ku not in jc['keys']]
+            for u in miss_u:
+                jc['keys'][keys_u[u]] = len(jc['keys'])
+            jslot = np.array([jc['keys'][ku] for ku in keys_u], dtype=np.int64)[inv]     # per fold
+            first = np.asarray(first).ravel()
+            tp = [(0, v) for v in range(P)]                                  # target row, every fold
+            xp = [(u, v) for u in range(1, P) for v in range(u, P)]          # cross blocks, misses only
+            ff = np.concatenate([np.repeat(fi, len(tp)), np.repeat(first[miss_u], len(xp))]).astype(np.int64)
+            uu = np.concatenate([np.tile([a for a, _ in tp], B), np.tile([a for a, _ in xp], len(miss_u))]).astype(np.int64)
+            vv = np.concatenate([np.tile([b for _, b in tp], B), np.tile([b for _, b in xp], len(miss_u))]).astype(np.int64)
+            n_t = B * len(tp)
+            r_jg = np.zeros(len(ff), dtype=_lib.GRAM_TN_DESC)
             r_jg['A'], r_jg['B'] = cmb[ff, uu], cmb[ff, vv]
             r_jg['segA'], r_jg['segB'] = segb[ff, uu], segb[ff, vv]
-            r_jg['out'] = addr(Gj) + 8 * (nJ * nJ * ff + coff[uu] * nJ + coff[vv])
+            out = addr(Gj) + 8 * (nJ * nJ * ff + coff[uu] * nJ + coff[vv])
+            out[n_t:] = addr(jc['G']) + 8 * (nJ * nJ * jslot[ff[n_t:]] + coff[uu[n_t:]] * nJ + coff[vv[n_t:]])
+            r_jg['out'] = out
             r_jg['nseg'], r_jg['seg_len'] = Ksa[ff], T
             r_jg['p'] = r_jg['lda'] = cdims[uu]
             r_jg['q'] = r_jg['ldb'] = cdims[vv]
             r_jg['ldo'], r_jg['sym'], r_jg['alpha'] = nJ, (uu == vv).astype(np.int32), 1.0
-            r_js = np.zeros(B * P, dtype=_lib.COLSUM_DESC)
-            pf_, pv_ = np.repeat(fi, P), np.tile(np.arange(P, dtype=np.int64), B)
-            r_js['A'], r_js['segA'] = cmb.ravel(), segb.ravel()
-            r_js['out'] = addr(sj) + 4 * (nJ * pf_ + coff[pv_])
-            r_js['nseg'], r_js['seg_len'], r_js['p'], r_js['lda'] = Ksa[pf_], T, cdims[pv_], cdims[pv_]
+            npair_launch = len(ff)
+            # column sums: the target's per fold, the cross patients' per missing set
+            sf = np.concatenate([fi, np.repeat(first[miss_u], P - 1)]).astype(np.int64)
+            sv = np.concatenate([np.zeros(B, dtype=np.int64), np.tile(np.arange(1, P, dtype=np.int64), len(miss_u))])
+            r_js = np.zeros(len(sf), dtype=_lib.COLSUM_DESC)
+            r_js['A'], r_js['segA'] = cmb[sf, sv], segb[sf, sv]
+            so = addr(sj) + 4 * (nJ * sf + coff[sv])
+            so[B:] = addr(jc['s']) + 4 * (nJ * jslot[sf[B:]] + coff[sv[B:]])
+            r_js['out'] = so
+            r_js['nseg'], r_js['seg_len'], r_js['p'], r_js['lda'] = Ksa[sf], T, cdims[sv], cdims[sv]
             r_js['alpha'] = 1.0
+            ncs_launch = len(sf)
+            jslot_dev = torch.from_numpy(jslot).pin_memory().to(ctx.device, non_blocking=True)
             d_cm = pk.add_descs(r_cm)
             d_jg, d_js = pk.add_descs(r_jg), pk.add_descs(r_js)
         else:
@@ -1380,8 +1406,12 @@ class CVEngine:
         if joint:
             # ---- JointPCA fit of every fold
             self.mark('align_scatter_eig')
-            ctx.call('cpsd_colsum', pk.daddr(d_js), B * P, Cm)
-            ctx.call('cpsd_gram_tn_f64', pk.daddr(d_jg), B * npair, Cm, Cm)
+            ctx.call('cpsd_colsum', pk.daddr(d_js), ncs_launch, Cm)
+            ctx.call('cpsd_gram_tn_f64', pk.daddr(d_jg), npair_launch, Cm, Cm)
+            if P > 1:       # cross blocks / sums of every fold from its set's cache slot (device copy)
+                c1 = int(coff[1])
+                Gj[:B, c1:, c1:] = jc['G'][jslot_dev][:, c1:, c1:]
+                sj[:B, c1:] = jc['s'][jslot_dev][:, c1:]
             nrows_dev = self.ws('j_nrows', (B,), I32)
             nrows_dev.copy_(torch.from_numpy((Ksa * T).astype(np.int32)).pin_memory(), non_blocking=True)
             covj = self.ws('j_cov', (B, nJ_pad, nJ_pad))
