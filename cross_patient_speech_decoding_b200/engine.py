@@ -667,60 +667,56 @@ class CVEngine:
         batches = [folds[s:s + size] for s in range(0, len(folds), size)]   # as a full one)
         results = [None] * len(batches)
         self._ensure_ready()
+        # every batch is a generator that yields right before each blocking read-back; the
+        # lanes are advanced round-robin, so while one lane waits for its GPU results the
+        # host packs and queues the other lane's batch on its own stream
         if self.method in ('mcca', 'jointpca'):
-            # every batch is a generator that yields right before each blocking read-back; the
-            # lanes are advanced round-robin, so while one lane waits for its GPU results the
-            # host packs and queues the other lane's batch on its own stream
             with torch.cuda.stream(self.stream):
                 self._tc_proj_ready(int(self.n_comp))  # split X / encode maps before the lanes fork
-            nl = 1 if (self.profile or len(batches) == 1) else min(self.n_lanes, len(batches))
-            lanes = self._lanes(nl)
-            ready = torch.cuda.Event()
-            ready.record(self.stream)
-            for ln in lanes[1:]:
-                ln.stream.wait_event(ready)            # fold-invariant tables live on lane 0's stream
-            todo = [list(range(li, len(batches), nl)) for li in range(nl)]
-            gens = [None] * nl
-            cur = [None] * nl
-            wait = [None] * nl          # event recorded when the lane last yielded
-            live = sum(len(t) for t in todo)
-            while live:
-                progressed = False
-                for li, ln in enumerate(lanes):
-                    if gens[li] is None:
-                        if not todo[li]:
-                            continue
-                        cur[li] = todo[li].pop(0)
-                        with torch.cuda.stream(ln.stream):
-                            gens[li] = ln._mcca_start(batches[cur[li]], return_details)
-                        wait[li] = None
-                        progressed = True
+        nl = 1 if (self.profile or len(batches) == 1) else min(self.n_lanes, len(batches))
+        lanes = self._lanes(nl)
+        ready = torch.cuda.Event()
+        ready.record(self.stream)
+        for ln in lanes[1:]:
+            ln.stream.wait_event(ready)            # fold-invariant tables live on lane 0's stream
+        todo = [list(range(li, len(batches), nl)) for li in range(nl)]
+        gens = [None] * nl
+        cur = [None] * nl
+        wait = [None] * nl          # event recorded when the lane last yielded
+        live = sum(len(t) for t in todo)
+        while live:
+            progressed = False
+            for li, ln in enumerate(lanes):
+                if gens[li] is None:
+                    if not todo[li]:
                         continue
-                    # resume a lane only when the work it queued before yielding has finished:
-                    # its read-back then returns at once and the host never sits in one lane's
-                    # wait while another lane has nothing queued
-                    if wait[li] is not None and nl > 1 and not wait[li].query():
-                        continue
-                    progressed = True
+                    cur[li] = todo[li].pop(0)
                     with torch.cuda.stream(ln.stream):
-                        try:
-                            if next(gens[li]) == 'host':
-                                wait[li] = None      # nothing queued: resumable at once
-                            else:
-                                wait[li] = torch.cuda.Event()
-                                wait[li].record(ln.stream)
-                        except StopIteration as e:
-                            results[cur[li]] = e.value
-                            gens[li] = None
-                            live -= 1
-                if not progressed:
-                    time.sleep(0)
-            for ln in lanes:
-                ln.stream.synchronize()
-        else:
-            with torch.cuda.stream(self.stream):
-                for i, batch in enumerate(batches):
-                    results[i] = self._batch_cca(batch, return_details)
+                        gens[li] = ln._batch_start(batches[cur[li]], return_details)
+                    wait[li] = None
+                    progressed = True
+                    continue
+                # resume a lane only when the work it queued before yielding has finished:
+                # its read-back then returns at once and the host never sits in one lane's
+                # wait while another lane has nothing queued
+                if wait[li] is not None and nl > 1 and not wait[li].query():
+                    continue
+                progressed = True
+                with torch.cuda.stream(ln.stream):
+                    try:
+                        if next(gens[li]) == 'host':
+                            wait[li] = None      # nothing queued: resumable at once
+                        else:
+                            wait[li] = torch.cuda.Event()
+                            wait[li].record(ln.stream)
+                    except StopIteration as e:
+                        results[cur[li]] = e.value
+                        gens[li] = None
+                        live -= 1
+            if not progressed:
+                time.sleep(0)
+        for ln in lanes:
+            ln.stream.synchronize()
         for res in results:
             out['y_pred'] += res['y_pred']
             out['k2'] += res['k2']
@@ -745,10 +741,7 @@ class CVEngine:
         self._ensure_ready()
         for s0 in range(0, len(folds), size):
             batch = folds[s0:s0 + size]
-            if self.method in ('mcca', 'jointpca'):
-                res = yield from self._mcca_start(batch, return_details)
-            else:
-                res = self._batch_cca(batch, return_details)
+            res = yield from self._batch_start(batch, return_details)
             out['y_pred'] += res['y_pred']
             out['k2'] += res['k2']
             out['h2d_bytes'] += res['h2d_bytes']
@@ -764,6 +757,13 @@ class CVEngine:
         pk = self.packM[self._pack_i]
         self._pack_i ^= 1
         return self._batch_mcca_gen(batch, want_details, align_only, pk)
+
+    def _batch_start(self, batch, want_details):
+        """Generator of one batch for this engine's method."""
+        if self.method in ('mcca', 'jointpca'):
+            return self._mcca_start(batch, want_details)
+        from .engine_cca import batch_cca_gen
+        return batch_cca_gen(self, batch, want_details)
 
     def _batch_mcca(self, batch, want_details, align_only=False):
         self._ensure_ready()

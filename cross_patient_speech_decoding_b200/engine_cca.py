@@ -25,6 +25,13 @@ def _drain(g):
 
 
 def batch_cca(eng, batch, want_details):
+    return _drain(batch_cca_gen(eng, batch, want_details))
+
+
+def batch_cca_gen(eng, batch, want_details):
+    """Generator form (same protocol as CVEngine._batch_mcca_gen): yields 'sync' right before
+    every blocking read-back and 'host' after a stretch of pure host packing, so that the lane
+    scheduler of CVEngine.run can keep a second batch in flight."""
     ctx, T, P, Cm = eng.ctx, eng.T, eng.P, eng.Cmax
     B = len(batch)
     nv = P - 1
@@ -68,6 +75,7 @@ def batch_cca(eng, batch, want_details):
     ev_t, evec_t = eng.eig_any(cov, n_padC, ptr(None), tv.C, B, 'ct')
     k_t = eng.ws('c_kt', (B,), I32)
     eng._select_pca_k(ev_t, n_padC, ptr(None), tv.C, k_t, 1, 0, B, eng.n_comp)
+    yield 'sync'
     d_a = k_t.cpu().numpy().astype(np.int32)          # the one mid-batch sync: latent sizes
     d2h = d_a.nbytes
     d_b = eng.cross_k if nv else np.zeros(0, dtype=np.int32)
@@ -215,6 +223,7 @@ def batch_cca(eng, batch, want_details):
                                     o_nte, n_te_max, ypool)
     d_svm = pk.add_descs(r_svm)
     pk.upload()
+    yield 'host'
 
     # ------------------------------------------------------------- launches, stage B
     eng.mark('cca_solve')
@@ -233,7 +242,7 @@ def batch_cca(eng, batch, want_details):
     eng.mark('project_pool')
     ctx.call('cpsd_proj_nn', pk.daddr(d_pp), len(r_pp),
              max(max(eng.views[v].N for v in range(P)), n_te_max), T, dq)
-    evals, k2_, St_, Ste, V, sweeps, kcap = eng._pooled_stage_run(
+    evals, k2_, St_, Ste, V, sweeps, kcap = yield from eng._pooled_stage_run_gen(
         pk, d_p1, d_p2, B, Zall, pmu, Kall, n_pad, F, n_pool, n_te, o_npool, o_nall, o_ypool,
         n_te_max, want_details)
     ncls = len(eng.classes)
@@ -241,6 +250,7 @@ def batch_cca(eng, batch, want_details):
     yhat = eng._decode(pk, d_svm, W, info, B, St_, Ste, k2, kcap, n_pad, o_ypool, n_pad, o_npool, o_nte,
                        n_te_max)
     eng.mark('end')
+    yield 'sync'
     yh = yhat.cpu().numpy()
     k2h = k2.cpu().numpy()
     res = {'y_pred': [yh[f, :n_te[f]].copy() for f in range(B)], 'k2': k2h.tolist(),

@@ -25,6 +25,7 @@ from cross_patient_speech_decoding_b200.folds import cv_splits  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument('--configs', default='1,2s,3,4,5')
 ap.add_argument('--iters', type=int, default=5, help='CV iterations per measurement')
+ap.add_argument('--cca-batch', type=int, default=40)
 ap.add_argument('--dims', default='10,20,30,40,50,60,70,80,90,100')
 args = ap.parse_args()
 todo = set(args.configs.split(','))
@@ -59,7 +60,7 @@ def timed(tag, eng, folds, extra=None):
 if '1' in todo:
     for nc in (0.9, 30):
         folds = folds_for(pts[0][1], 5, 4 * args.iters, 100)
-        eng = CVEngine(dev[0], dev[1:2], method='cca', n_comp=nc, use_tensor_cores=True, max_batch=148)
+        eng = CVEngine(dev[0], dev[1:2], method='cca', n_comp=nc, use_tensor_cores=True, max_batch=args.cca_batch)
         timed('1: 2 patients, CCA, n_comp=%s, 5-fold' % nc, eng, folds)
 
 if '2s' in todo:
@@ -80,6 +81,8 @@ if '3' in todo:
                 kw.update(regs=0.5, pca_var=0.8)
             if method == 'jointpca':
                 kw.update(max_batch=32)
+            if method == 'cca':
+                kw.update(max_batch=args.cca_batch)
             eng = CVEngine(dev[0], dev[1:], **kw)
             eng.profile = True
             try:
