@@ -1554,7 +1554,7 @@ class CVEngine:
         if want_details and joint:
             res['details'] = dict(
                 loadings=L.view(B, P, Cm, Q).cpu().numpy(), evals_joint=evj[:, :Q].cpu().numpy(),
-                pool_evals=evals.cpu().numpy(), svm_info=info.cpu().numpy(), W=W.cpu().numpy(),
+                pool_evals=evals.cpu().numpy(), svm_info=info.cpu().numpy(), W=_w_host(W),
                 n_pool=list(n_pool), shared=[s.copy() for s in shared], lsq_status=stj.cpu().numpy(),
                 bj_sweeps=None if sweeps is None else sweeps.cpu().numpy()[B:2 * B])
         elif want_details:
@@ -1562,7 +1562,7 @@ class CVEngine:
                 loadings=L.view(B, P, Cm, Q).cpu().numpy(), mu=self._slot_means(mu, slot, Cm),
                 evals_mcca=evm[:, :Q].cpu().numpy(), r_eff=r_eff.view(B, P).cpu().numpy(),
                 pool_evals=evals.cpu().numpy(), svm_info=info.cpu().numpy(),
-                W=W.cpu().numpy(), n_pool=list(n_pool), shared=[s.copy() for s in shared],
+                W=_w_host(W), n_pool=list(n_pool), shared=[s.copy() for s in shared],
                 bj_sweeps=None if sweeps is None else sweeps.cpu().numpy()[B:2 * B])
         return res
 
@@ -1570,6 +1570,13 @@ class CVEngine:
     def _batch_cca(self, batch, want_details):
         from .engine_cca import batch_cca
         return batch_cca(self, batch, want_details)
+
+
+def _w_host(W):
+    """Decoder state for the details dict: OvR weights, or the C-SVC's coef / rho / gamma."""
+    if isinstance(W, dict):
+        return {k: W[k].cpu().numpy() for k in ('coef', 'rho', 'gamma')}
+    return W.cpu().numpy()
 
 
 def _drain(g):

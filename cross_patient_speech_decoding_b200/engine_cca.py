@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 from .device import addr, ptr
-from .engine import F32, I32, _ceil, ctypes_int_ptr
+from .engine import _w_host, F32, I32, _ceil, ctypes_int_ptr
 
 
 def _drain(g):
@@ -260,7 +260,7 @@ def batch_cca_gen(eng, batch, want_details):
     if want_details:
         det = dict(d_a=d_a.copy(), d_b=np.array(d_b).copy(), d_out=d_out.copy(),
                    Wt=Wt.cpu().numpy(), mu_t=mu_t.cpu().numpy(), pool_evals=evals.cpu().numpy(),
-                   svm_info=info.cpu().numpy(), W=W.cpu().numpy(), n_pool=list(n_pool),
+                   svm_info=info.cpu().numpy(), W=_w_host(W), n_pool=list(n_pool),
                    ev_t=ev_t.cpu().numpy(),
                    bj_sweeps=None if sweeps is None else sweeps.cpu().numpy()[B:2 * B])
         if aligned and nv:

@@ -15,11 +15,14 @@ ap.add_argument('--folds', type=int, default=107)
 ap.add_argument('--no-tc', action='store_true')
 ap.add_argument('--stages', action='store_true')
 ap.add_argument('--dcd', type=int, default=0)
+ap.add_argument('--decoder', default='linear')
+ap.add_argument('--class-weight', default=None)
 a = ap.parse_args()
 from cross_patient_speech_decoding_b200.engine import CVEngine  # noqa: E402
 pts = bench.make_data()
 eng = CVEngine(pts[0], pts[1:], method='mcca', n_comp=30, regs=0.5, pca_var=0.8,
-               use_tensor_cores=not a.no_tc, max_batch=a.folds, dcd_epochs=a.dcd)
+               use_tensor_cores=not a.no_tc, max_batch=a.folds, dcd_epochs=a.dcd,
+               decoder=a.decoder, class_weight=a.class_weight)
 def mk(seed):
     out = []
     while len(out) < a.folds:
@@ -34,6 +37,11 @@ for s in range(a.steps):
     res = eng.run(fl, return_details=True)
     if a.stages:
         print('stages_ms', {k: round(v, 3) for k, v in eng.collect_marks().items()})
+    if a.decoder != 'linear':
+        si = res['details'][0]['svm_info']
+        print('svc: SMO iterations per pair mean %.0f max %d; not converged %d' % (
+            si[..., 0].mean(), si[..., 0].max(), int((si[..., 1] == 1).sum())))
+        continue
     sw = res['details'][0]['bj_sweeps']
     print('acc', sum(int((p == pts[0][1][te]).sum()) for p, (_, te) in zip(res['y_pred'], fl)) / sum(len(te) for _, te in fl))
     print('k2', res['k2'][:4], 'topk', eng.stats.get('topk'), 'bj_sweeps', None if sw is None else sw[:4],
