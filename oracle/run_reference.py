@@ -23,6 +23,14 @@ def make_decoder(ref, decoder_var=0.8, C=1.0, svm='primal'):
         clf = LinearSVC(dual=False, C=C, tol=1e-10, max_iter=100000)
     elif svm == 'dual_default':
         clf = LinearSVC(dual=True, C=C, random_state=0)
+    elif svm == 'svc_rbf':
+        # the decoder the reference's scripts build themselves
+        # (scripts/aligned_decode_svm_ncv.py:313-317)
+        from sklearn.svm import SVC
+        clf = SVC(kernel='rbf', class_weight='balanced', C=C)
+    elif svm == 'svc_linear':                         # scripts/aligned_decode_svm.py:262
+        from sklearn.svm import SVC
+        clf = SVC(kernel='linear', C=C)
     else:
         raise ValueError(svm)
     return make_pipeline(ref.DimRedReshape(PCA, n_components=decoder_var), clf)
@@ -63,7 +71,10 @@ def run_folds(target, cross, folds, method='mcca', n_comp=None, regs=0.5, pca_va
         out['k2'].append(int(pca.n_components_))
         out['pool_shape'].append((pca.n_samples_, pca.n_features_in_))
         if details:
-            out['svm_w'].append(np.hstack([svc.coef_, svc.intercept_[:, None]]))
+            if hasattr(svc, 'dual_coef_'):
+                out['svm_w'].append(np.asarray(svc.intercept_))
+            else:
+                out['svm_w'].append(np.hstack([svc.coef_, svc.intercept_[:, None]]))
             if method == 'mcca':
                 mc = m.aligner.mcca
                 out['ranks'].append(None if mc.signal_ranks is None else

@@ -42,6 +42,11 @@ CONFIGS = {
                                      dict(p=2, n_trials=70, n_time=60, n_chan=33)]),
     'mcca_p8_20fold': dict(method='mcca', n_comp=30, regs=0.5, pca_var=0.8, n_splits=20, seed=5,
                            patients=[dict(p=i) for i in range(8)], max_folds=6),
+    # the scripts' literal decoder SVC(kernel='rbf', class_weight='balanced')
+    'cca_p3_svc_rbf': dict(method='cca', n_comp=0.9, n_splits=4, seed=8, svm='svc_rbf',
+                           patients=[dict(p=0, n_trials=90, n_time=60, n_chan=48, noise=0.6),
+                                     dict(p=1, n_trials=110, n_time=60, n_chan=64, noise=0.6),
+                                     dict(p=2, n_trials=70, n_time=60, n_chan=33, noise=0.6)]),
     'cca_p2_noisy': dict(method='cca', n_comp=0.9, n_splits=5, seed=6,
                          patients=[dict(p=0, noise=1.0), dict(p=1, noise=1.0)]),
 }
@@ -62,7 +67,7 @@ def generate(name):
     t0 = time.time()
     res = run_reference.run_folds(pts[0], pts[1:], folds, method=cfg['method'],
                                   n_comp=cfg.get('n_comp'), regs=cfg.get('regs', 0.5),
-                                  pca_var=cfg.get('pca_var', 0.8))
+                                  pca_var=cfg.get('pca_var', 0.8), svm=cfg.get('svm', 'primal'))
     dt = time.time() - t0
     nf = len(folds)
     out = dict(n_folds=nf, seconds_per_fold=dt / nf, k2=np.array(res['k2']),

@@ -106,7 +106,8 @@ def test_liblinear_dual_cd_does_not_converge_on_unscaled_scores():
     assert rel > 0.05
 
 
-@pytest.mark.parametrize('name', ['cca_p3_ragged', 'none_p3_ragged', 'mcca_p3_ragged'])
+@pytest.mark.parametrize('name', ['cca_p3_ragged', 'none_p3_ragged', 'mcca_p3_ragged',
+                                  'cca_p3_svc_rbf'])
 def test_cpu_port_reproduces_reference_golden(name):
     """oracle/pipeline_port.py (used on the GPU box, where /root/reference is absent) against
     the outputs the UNMODIFIED reference produced here (tests/golden/make_golden.py)."""
@@ -120,7 +121,9 @@ def test_cpu_port_reproduces_reference_golden(name):
             warnings.simplefilter('ignore')
             yp, k2 = pipeline_port.run_fold(pts[0], pts[1:], tr, te, method=cfg['method'],
                                             n_comp=cfg.get('n_comp'), regs=cfg.get('regs', 0.5),
-                                            pca_var=cfg.get('pca_var', 0.8))
+                                            pca_var=cfg.get('pca_var', 0.8),
+                                            decoder=cfg.get('svm', 'linear').replace('primal', 'linear'),
+                                            class_weight='balanced' if cfg.get('svm') == 'svc_rbf' else None)
         assert k2 == int(g['k2'][f])
         assert np.array_equal(yp, g['y_pred_%d' % f])
 
