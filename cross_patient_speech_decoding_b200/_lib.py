@@ -124,10 +124,10 @@ _SIGS = {
     'cpsd_svm_fit_ovr': [_P, c_int, c_int, c_int, _P],
     'cpsd_svm_predict_ovr': [_P, c_int, c_ll, _P, c_int, c_ll, _P, c_int, _P, c_int, _P, c_int, _P,
                              _P, c_int, _P],
-    'cpsd_svc_kernel_matrix': [_P, c_int, c_ll, _P, c_int, _P, c_int, c_int, c_int, ctypes.c_double, _P, _P,
-                               c_int, c_ll, c_int, _P],
-    'cpsd_svc_fit_ovo': [_P, c_int, c_ll, _P, c_int, _P, c_int, _P, c_int, ctypes.c_double, c_int, ctypes.c_double,
-                         c_int, _P, c_int, _P, _P, c_int, c_int, _P],
+    'cpsd_svc_kernel_matrix': [_P, c_int, c_ll, _P, c_int, _P, c_int, c_int, _P, c_int, _P, c_int, c_int,
+                               ctypes.c_double, _P, _P, _P, _P, _P, c_int, c_ll, c_int, _P],
+    'cpsd_svc_fit_ovo': [_P, c_int, c_ll, _P, _P, _P, c_int, c_int, ctypes.c_double, c_int,
+                         ctypes.c_double, c_int, _P, c_int, _P, _P, c_int, c_int, _P],
     'cpsd_svc_predict_ovo': [_P, c_int, c_ll, _P, c_int, c_ll, _P, c_int, _P, c_int, c_int, _P, c_int,
                              _P, c_int, _P, c_int, c_int, _P, _P, c_int, _P, _P, _P, c_int, c_int, _P],
     'cpsd_cca_solve': [_P, c_int, c_int, _P],

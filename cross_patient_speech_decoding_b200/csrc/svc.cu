@@ -6,8 +6,9 @@
 // selection, float kernel values, double gradients, eps = tol stopping rule, first-maximum vote)
 // as batched kernels:
 //   k_svc_gamma      gamma='scale' = 1 / (n_features * var(X)) per fold
-//   k_svc_kmat       (n x n) kernel matrix per fold (fp64 accumulation, stored as float like
-//                    libsvm's Qfloat cache)
+//   k_svc_perm       class-sorted order of the pool + squared norms
+//   k_svc_kmat       (n x n) kernel matrix per fold in class-sorted order (fp64 accumulation,
+//                    stored as float like libsvm's Qfloat cache; upper tiles, mirrored)
 //   k_svc_smo        one WARP per (fold, class pair) dual problem: members, alpha and the
 //                    gradient live in shared memory, no block barrier inside the SMO loop
 //   k_svc_predict    one CTA per (fold, held-out trial): kernel row, all pair decisions, vote
@@ -48,46 +49,106 @@ __global__ void k_svc_gamma(const float* __restrict__ St, int lds, long long str
   if (threadIdx.x == 0) gamma_out[f] = g;
 }
 
-// 32x32 output tile per CTA, 256 threads x 4 entries; features staged 32 at a time.
+// One CTA per fold: class-sorted order of the pool (stable counting sort by class, warp 0) and
+// the squared norms of the samples (all threads).  perm[pos] = pool index of the sample at
+// sorted position pos; cls_off[c] .. cls_off[c+1] = positions of class c.
+__global__ void k_svc_perm(const float* __restrict__ St, int lds, long long strideS,
+                           const int* __restrict__ k_dev, int k_fixed,
+                           const int* __restrict__ n_dev, int n_fixed, const int* __restrict__ y,
+                           int ldy, const int* __restrict__ classes, int ncls,
+                           int* __restrict__ perm, int ldp, int* __restrict__ cls_off,
+                           double* __restrict__ sqn) {
+  const int f = blockIdx.x;
+  const int k = k_dev ? k_dev[f] : k_fixed;
+  const int n = n_dev ? n_dev[f] : n_fixed;
+  const float* X = St + (long long)f * strideS;
+  const int* yf = y + (long long)f * ldy;
+  for (int t = threadIdx.x; t < n; t += blockDim.x) {
+    double v = 0.0;
+    for (int j = 0; j < k; ++j) {
+      const double x = (double)X[(long long)j * lds + t];
+      v = fma(x, x, v);
+    }
+    sqn[(long long)f * ldp + t] = v;
+  }
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    int pos = 0;
+    for (int c = 0; c < ncls; ++c) {
+      if (lane == 0) cls_off[(long long)f * (ncls + 1) + c] = pos;
+      const int want = classes[c];
+      for (int t0 = 0; t0 < n; t0 += 32) {
+        const int t = t0 + lane;
+        const bool hit = t < n && yf[t] == want;
+        const unsigned msk = __ballot_sync(0xffffffffu, hit);
+        if (hit) perm[(long long)f * ldp + pos + __popc(msk & ((1u << lane) - 1u))] = t;
+        pos += __popc(msk);
+      }
+    }
+    if (lane == 0) cls_off[(long long)f * (ncls + 1) + ncls] = pos;
+  }
+}
+
+// Kernel matrix in class-sorted order, K'[p][q] = k(x_perm[p], x_perm[q]): 32x32 tiles of the
+// upper triangle (mirrored on write), 256 threads x 4 entries, features staged 32 at a time,
+// libsvm's form exp(-gamma (|a|^2 + |b|^2 - 2 a.b)) with the dot product accumulated in fp64.
 __global__ void k_svc_kmat(const float* __restrict__ St, int lds, long long strideS,
                            const int* __restrict__ k_dev, int k_fixed,
                            const int* __restrict__ n_dev, int n_fixed, int kernel,
-                           const double* __restrict__ gamma, float* __restrict__ K, int ldk,
+                           const double* __restrict__ gamma, const int* __restrict__ perm, int ldp,
+                           const double* __restrict__ sqn, float* __restrict__ K, int ldk,
                            long long strideK) {
   __shared__ float a[32][33], b[32][33];
+  __shared__ int pa[32], pb[32];
   const int f = blockIdx.z;
   const int k = k_dev ? k_dev[f] : k_fixed;
   const int n = n_dev ? n_dev[f] : n_fixed;
   const int i0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
-  if (i0 >= n || t0 >= n) return;
+  if (t0 < i0 || i0 >= n || t0 >= n) return;
   const float* X = St + (long long)f * strideS;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // ty 0..7
+  if (threadIdx.x < 32) pa[tx] = i0 + tx < n ? perm[(long long)f * ldp + i0 + tx] : -1;
+  else if (threadIdx.x < 64) pb[tx] = t0 + tx < n ? perm[(long long)f * ldp + t0 + tx] : -1;
+  __syncthreads();
+  const int ia = pa[tx], ib = pb[tx];
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
   for (int j0 = 0; j0 < k; j0 += 32) {
     for (int r = ty; r < 32; r += 8) {
       const int j = j0 + r;
-      a[r][tx] = (j < k && i0 + tx < n) ? X[(long long)j * lds + i0 + tx] : 0.f;
-      b[r][tx] = (j < k && t0 + tx < n) ? X[(long long)j * lds + t0 + tx] : 0.f;
+      a[r][tx] = (j < k && ia >= 0) ? X[(long long)j * lds + ia] : 0.f;
+      b[r][tx] = (j < k && ib >= 0) ? X[(long long)j * lds + ib] : 0.f;
     }
     __syncthreads();
 #pragma unroll 8
     for (int r = 0; r < 32; ++r) {
       const double bv = (double)b[r][tx];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const double av = (double)a[r][ty + 8 * e];
-        if (kernel == 1) { const double d = av - bv; acc[e] = fma(d, d, acc[e]); }
-        else acc[e] = fma(av, bv, acc[e]);
-      }
+      for (int e = 0; e < 4; ++e) acc[e] = fma((double)a[r][ty + 8 * e], bv, acc[e]);
     }
     __syncthreads();
   }
   const double g = gamma[f];
   float* Kf = K + (long long)f * strideK;
+  const double sb = ib >= 0 ? sqn[(long long)f * ldp + ib] : 0.0;
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    const int i = i0 + ty + 8 * e, t = t0 + tx;
-    if (i < n && t < n) Kf[(long long)i * ldk + t] = (float)(kernel == 1 ? exp(-g * acc[e]) : acc[e]);
+    const int r = ty + 8 * e;
+    const int i = i0 + r, t = t0 + tx;
+    float v = 0.f;
+    if (i < n && t < n) {
+      v = kernel == 1 ? (float)exp(-g * (sqn[(long long)f * ldp + pa[r]] + sb - 2.0 * acc[e]))
+                      : (float)acc[e];
+      Kf[(long long)i * ldk + t] = v;
+    }
+    a[r][tx] = v;                       // staged for the mirrored tile
+  }
+  if (t0 == i0) return;
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int r = ty + 8 * e;           // row of the mirrored tile = column of this one
+    const int i = t0 + r, t = i0 + tx;
+    if (i < n && t < n) Kf[(long long)i * ldk + t] = a[tx][r];
   }
 }
 
@@ -121,14 +182,17 @@ __device__ __forceinline__ void pair_of(int p, int ncls, int& a, int& b) {
   b = a + 1 + rem;
 }
 
-// Dual problem of one class pair.  Members of class a (y=+1) first, then class b (y=-1), both in
-// pool order.  Shared memory per warp: alpha[m_max], G[m_max] (double), idx[m_max] (int),
-// qd[m_max] (float), ys[m_max] (signed char).
+// Dual problem of one class pair, one warp.  Members: class a (y=+1) then class b (y=-1), both
+// in pool order = two contiguous ranges of the class-sorted kernel matrix, so a kernel row is
+// two coalesced segments.  Shared memory per warp: alpha[m_max], G[m_max] (double), qi[m_max]
+// (row i of the pair's kernel block, kept from the selection pass for the gradient update),
+// qd[m_max] (diagonal).
+constexpr int SVC_U = 4;                // independent loads in flight per lane
 __global__ void __launch_bounds__(32 * SVC_WARPS)
-k_svc_smo(const float* __restrict__ K, int ldk, long long strideK, const int* __restrict__ y, int ldy,
-          const int* __restrict__ n_dev, int n_fixed, const int* __restrict__ classes, int ncls,
-          double Cpar, int balanced, double eps, int max_iter, double* __restrict__ coef, int ldc,
-          double* __restrict__ rho, int* __restrict__ info, int m_max, int ntask) {
+k_svc_smo(const float* __restrict__ K, int ldk, long long strideK, const int* __restrict__ perm,
+          int ldp, const int* __restrict__ cls_off, const int* __restrict__ n_dev, int n_fixed,
+          int ncls, double Cpar, int balanced, double eps, int max_iter, double* __restrict__ coef,
+          int ldc, double* __restrict__ rho, int* __restrict__ info, int m_max, int ntask) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int task = blockIdx.x * SVC_WARPS + w;
@@ -137,32 +201,19 @@ k_svc_smo(const float* __restrict__ K, int ldk, long long strideK, const int* __
   const int f = task / npair, p = task - f * npair;
   int ca, cb;
   pair_of(p, ncls, ca, cb);
-  const size_t per_warp = (size_t)m_max * (8 + 8 + 4 + 4 + 1) + 16;
+  const size_t per_warp = (size_t)m_max * (8 + 8 + 4 + 4) + 16;
   unsigned char* base = smem_raw + (size_t)w * ((per_warp + 15) & ~(size_t)15);
   double* alpha = (double*)base;
   double* G = alpha + m_max;
-  int* idx = (int*)(G + m_max);
-  float* qd = (float*)(idx + m_max);
-  signed char* ys = (signed char*)(qd + m_max);
+  float* qi = (float*)(G + m_max);
+  float* qd = qi + m_max;
 
   const int n = n_dev ? n_dev[f] : n_fixed;
-  const int* yf = y + (long long)f * ldy;
-  const float* Kf = K + (long long)f * strideK;
-  const int la = classes[ca], lb = classes[cb];
-  // members (ordered compaction, 32 at a time) and the class statistics of the whole pool
-  int ma = 0, mb = 0;
-  for (int pass = 0; pass < 2; ++pass) {
-    const int want = pass == 0 ? la : lb;
-    for (int t0 = 0; t0 < n; t0 += 32) {
-      const int t = t0 + lane;
-      const bool hit = t < n && yf[t] == want;
-      const unsigned msk = __ballot_sync(0xffffffffu, hit);
-      const int pos = (pass == 0 ? ma : ma + mb) + __popc(msk & ((1u << lane) - 1u));
-      if (hit && pos < m_max) { idx[pos] = t; ys[pos] = pass == 0 ? 1 : -1; }
-      if (pass == 0) ma += __popc(msk); else mb += __popc(msk);
-    }
-  }
+  const int* off = cls_off + (long long)f * (ncls + 1);
+  const int offA = off[ca], ma = off[ca + 1] - offA;
+  const int offB = off[cb], mb = off[cb + 1] - offB;
   const int m = ma + mb;
+  const float* Kf = K + (long long)f * strideK;
   int* inf = info + 2 * (long long)task;
   if (ma == 0 || mb == 0) {            // class absent from this pool: no such pair in libsvm
     if (lane == 0) { rho[task] = 0.0; inf[0] = 0; inf[1] = 2; }
@@ -175,19 +226,18 @@ k_svc_smo(const float* __restrict__ K, int ldk, long long strideK, const int* __
   double Cp = Cpar, Cn = Cpar;
   if (balanced) {                       // n_samples / (n_classes_present * count_c), sklearn
     int present = 0;
-    for (int c = 0; c < ncls; ++c) {
-      int cnt = 0;
-      for (int t = lane; t < n; t += 32) cnt += yf[t] == classes[c];
-      cnt = __reduce_add_sync(0xffffffffu, cnt);
-      present += cnt > 0;
-    }
+    for (int c = 0; c < ncls; ++c) present += off[c + 1] > off[c];
     Cp = Cpar * ((double)n / ((double)present * (double)ma));
     Cn = Cpar * ((double)n / ((double)present * (double)mb));
   }
+  // sorted position of local member t, and its label sign
+#define SVC_POS(t) ((t) < ma ? offA + (t) : offB + (t) - ma)
+#define SVC_Y(t) ((t) < ma ? 1 : -1)
   for (int t = lane; t < m; t += 32) {
     alpha[t] = 0.0;
     G[t] = -1.0;
-    qd[t] = Kf[(long long)idx[t] * ldk + idx[t]];
+    const int ps = SVC_POS(t);
+    qd[t] = Kf[(long long)ps * ldk + ps];
   }
   __syncwarp();
 
@@ -197,32 +247,43 @@ k_svc_smo(const float* __restrict__ K, int ldk, long long strideK, const int* __
     Pick pi{-SVC_INF, -1};
     for (int t = lane; t < m; t += 32) {
       const double a = alpha[t], g = G[t];
-      if (ys[t] > 0) { if (a < Cp && -g >= pi.v) { pi.v = -g; pi.i = t; } }
-      else           { if (a > 0.0 && g >= pi.v) { pi.v = g; pi.i = t; } }
+      if (t < ma) { if (a < Cp && -g >= pi.v) { pi.v = -g; pi.i = t; } }
+      else        { if (a > 0.0 && g >= pi.v) { pi.v = g; pi.i = t; } }
     }
     pi = warp_argmax_last(pi);
     const int i = pi.i;
     const double Gmax = pi.v;
     if (i < 0) { status = 0; break; }
-    const float* Ki = Kf + (long long)idx[i] * ldk;
-    const int yi = ys[i];
+    const float* Ki = Kf + (long long)SVC_POS(i) * ldk;
+    const int yi = SVC_Y(i);
     const double qdi = (double)qd[i];
-    // --- j: second-order choice in the "low" set
+    // --- j: second-order choice in the "low" set (row i is gathered once and kept in qi)
     Pick pj{-SVC_INF, -1};               // maximise -obj  (obj <= min, ties to the larger index)
     double Gmax2 = -SVC_INF;
-    for (int t = lane; t < m; t += 32) {
-      const double a = alpha[t], g = G[t];
-      const int yt = ys[t];
-      double gd;
-      bool ok;
-      if (yt > 0) { ok = a > 0.0; gd = Gmax + g; if (ok) Gmax2 = fmax(Gmax2, g); }
-      else        { ok = a < Cn;  gd = Gmax - g; if (ok) Gmax2 = fmax(Gmax2, -g); }
-      if (ok && gd > 0.0) {
-        // QD_i + QD_t - 2 y_i y_t Q_it with Q_it = y_i y_t K_it
-        double quad = qdi + (double)qd[t] - 2.0 * (double)Ki[idx[t]];
-        if (!(quad > 0.0)) quad = SVC_TAU;
-        const double nobj = (gd * gd) / quad;
-        if (nobj >= pj.v) { pj.v = nobj; pj.i = t; }
+    for (int t0 = lane; t0 < m; t0 += 32 * SVC_U) {
+      float kv[SVC_U];
+#pragma unroll
+      for (int u = 0; u < SVC_U; ++u) {
+        const int t = t0 + 32 * u;
+        kv[u] = t < m ? Ki[SVC_POS(t)] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < SVC_U; ++u) {
+        const int t = t0 + 32 * u;
+        if (t >= m) break;
+        qi[t] = kv[u];
+        const double a = alpha[t], g = G[t];
+        double gd;
+        bool ok;
+        if (t < ma) { ok = a > 0.0; gd = Gmax + g; if (ok) Gmax2 = fmax(Gmax2, g); }
+        else        { ok = a < Cn;  gd = Gmax - g; if (ok) Gmax2 = fmax(Gmax2, -g); }
+        if (ok && gd > 0.0) {
+          // QD_i + QD_t - 2 y_i y_t Q_it with Q_it = y_i y_t K_it
+          double quad = qdi + (double)qd[t] - 2.0 * (double)kv[u];
+          if (!(quad > 0.0)) quad = SVC_TAU;
+          const double nobj = (gd * gd) / quad;
+          if (nobj >= pj.v) { pj.v = nobj; pj.i = t; }
+        }
       }
     }
     pj = warp_argmax_last(pj);
@@ -230,11 +291,12 @@ k_svc_smo(const float* __restrict__ K, int ldk, long long strideK, const int* __
     const int j = pj.i;
     if (Gmax + Gmax2 < eps || j < 0) { status = 0; break; }
     ++it;
-    const float* Kj = Kf + (long long)idx[j] * ldk;
-    const int yj = ys[j];
+    __syncwarp();                        // qi complete
+    const float* Kj = Kf + (long long)SVC_POS(j) * ldk;
+    const int yj = SVC_Y(j);
     const double Ci = yi > 0 ? Cp : Cn, Cj = yj > 0 ? Cp : Cn;
     const double ai0 = alpha[i], aj0 = alpha[j], Gi = G[i], Gj = G[j];
-    const double Qij = (double)((float)(yi * yj) * Ki[idx[j]]);
+    const double Qij = (double)((float)(yi * yj) * qi[j]);
     double ai = ai0, aj = aj0;
     if (yi != yj) {
       double quad = qdi + (double)qd[j] + 2.0 * Qij;
@@ -261,11 +323,22 @@ k_svc_smo(const float* __restrict__ K, int ldk, long long strideK, const int* __
     }
     const double dai = ai - ai0, daj = aj - aj0;
     __syncwarp();                        // every lane has read alpha/G of i and j
-    for (int t = lane; t < m; t += 32) {
-      const int yt = ys[t];
-      const float qit = (float)(yi * yt) * Ki[idx[t]];
-      const float qjt = (float)(yj * yt) * Kj[idx[t]];
-      G[t] += (double)qit * dai + (double)qjt * daj;
+    for (int t0 = lane; t0 < m; t0 += 32 * SVC_U) {
+      float kv[SVC_U];
+#pragma unroll
+      for (int u = 0; u < SVC_U; ++u) {
+        const int t = t0 + 32 * u;
+        kv[u] = t < m ? Kj[SVC_POS(t)] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < SVC_U; ++u) {
+        const int t = t0 + 32 * u;
+        if (t >= m) break;
+        const int yt = SVC_Y(t);
+        const float qit = (float)(yi * yt) * qi[t];
+        const float qjt = (float)(yj * yt) * kv[u];
+        G[t] += (double)qit * dai + (double)qjt * daj;
+      }
     }
     if (lane == 0) { alpha[i] = ai; alpha[j] = aj; }
     __syncwarp();
@@ -275,7 +348,7 @@ k_svc_smo(const float* __restrict__ K, int ldk, long long strideK, const int* __
   int nfree = 0;
   for (int t = lane; t < m; t += 32) {
     const double a = alpha[t];
-    const int yt = ys[t];
+    const int yt = SVC_Y(t);
     const double yG = (double)yt * G[t];
     const double Ct = yt > 0 ? Cp : Cn;
     if (a >= Ct)      { if (yt < 0) ub = fmin(ub, yG); else lbv = fmax(lbv, yG); }
@@ -287,14 +360,17 @@ k_svc_smo(const float* __restrict__ K, int ldk, long long strideK, const int* __
   ub = warp_mind(ub);
   lbv = warp_maxd(lbv);
   const double r = nfree > 0 ? sum_free / (double)nfree : 0.5 * (ub + lbv);
-  // coefficients in libsvm's sv_coef layout: a class-a member stores the pair under slot b-1,
-  // a class-b member under slot a
+  // coefficients in libsvm's sv_coef layout, indexed by pool sample: a class-a member stores
+  // the pair under slot b-1, a class-b member under slot a
   double* cf = coef + (long long)f * (ncls - 1) * ldc;
+  const int* pf = perm + (long long)f * ldp;
   for (int t = lane; t < m; t += 32) {
-    const int slot = ys[t] > 0 ? cb - 1 : ca;
-    cf[(long long)slot * ldc + idx[t]] = alpha[t] * (double)ys[t];
+    const int slot = t < ma ? cb - 1 : ca;
+    cf[(long long)slot * ldc + pf[SVC_POS(t)]] = alpha[t] * (double)SVC_Y(t);
   }
   if (lane == 0) { rho[task] = r; inf[0] = it; inf[1] = status; }
+#undef SVC_POS
+#undef SVC_Y
 }
 
 // One CTA per (fold, held-out trial).  dec (optional): [fold][n_te_max][npair] pair decisions.
@@ -372,31 +448,36 @@ __global__ void k_svc_predict(const float* __restrict__ St, int lds, long long s
 }
 
 static size_t smo_smem(int m_max) {
-  const size_t per_warp = (size_t)m_max * (8 + 8 + 4 + 4 + 1) + 16;
+  const size_t per_warp = (size_t)m_max * (8 + 8 + 4 + 4) + 16;
   return SVC_WARPS * ((per_warp + 15) & ~(size_t)15);
 }
 
 }  // namespace
 
 extern "C" int cpsd_svc_kernel_matrix(const float* St, int lds, long long strideS, const int* k_dev,
-                                      int k_fixed, const int* n_dev, int n_fixed, int n_max, int kernel,
-                                      double gamma, double* gamma_out, float* K, int ldk,
-                                      long long strideK, int nfold, cudaStream_t stream) {
-  CPSD_CHECK_ARG(nfold >= 0 && n_max > 0 && ldk >= n_max && (kernel == 0 || kernel == 1),
+                                      int k_fixed, const int* n_dev, int n_fixed, int n_max, const int* y,
+                                      int ldy, const int* classes, int ncls, int kernel, double gamma,
+                                      double* gamma_out, int* perm, int* cls_off, double* sqn, float* K,
+                                      int ldk, long long strideK, int nfold, cudaStream_t stream) {
+  CPSD_CHECK_ARG(nfold >= 0 && n_max > 0 && ldk >= n_max && (kernel == 0 || kernel == 1) && ncls >= 2,
                  "svc_kernel_matrix: bad dims");
   if (nfold == 0) return CPSD_OK;
   k_svc_gamma<<<nfold, 256, 0, stream>>>(St, lds, strideS, k_dev, k_fixed, n_dev, n_fixed, kernel, gamma,
                                          gamma_out);
   CPSD_LAUNCH_CHECK();
+  k_svc_perm<<<nfold, 256, 0, stream>>>(St, lds, strideS, k_dev, k_fixed, n_dev, n_fixed, y, ldy, classes,
+                                        ncls, perm, ldk, cls_off, sqn);
+  CPSD_LAUNCH_CHECK();
   const int tiles = (n_max + 31) / 32;
   k_svc_kmat<<<dim3(tiles, tiles, nfold), 256, 0, stream>>>(St, lds, strideS, k_dev, k_fixed, n_dev, n_fixed,
-                                                             kernel, gamma_out, K, ldk, strideK);
+                                                             kernel, gamma_out, perm, ldk, sqn, K, ldk,
+                                                             strideK);
   CPSD_LAUNCH_CHECK();
   return CPSD_OK;
 }
 
-extern "C" int cpsd_svc_fit_ovo(const float* K, int ldk, long long strideK, const int* y, int ldy,
-                                const int* n_dev, int n_fixed, const int* classes, int ncls, double C,
+extern "C" int cpsd_svc_fit_ovo(const float* K, int ldk, long long strideK, const int* perm,
+                                const int* cls_off, const int* n_dev, int n_fixed, int ncls, double C,
                                 int balanced, double eps, int max_iter, double* coef, int ldc,
                                 double* rho, int* info, int m_max, int nfold, cudaStream_t stream) {
   CPSD_CHECK_ARG(nfold >= 0 && ncls >= 2 && ncls <= 64 && m_max > 0 && C > 0 && eps > 0 && max_iter > 0,
@@ -408,8 +489,8 @@ extern "C" int cpsd_svc_fit_ovo(const float* K, int ldk, long long strideK, cons
   CPSD_CUDA(cudaMemsetAsync(coef, 0, sizeof(double) * (size_t)nfold * (ncls - 1) * ldc, stream));
   const int ntask = nfold * (ncls * (ncls - 1) / 2);
   k_svc_smo<<<(ntask + SVC_WARPS - 1) / SVC_WARPS, 32 * SVC_WARPS, smem, stream>>>(
-      K, ldk, strideK, y, ldy, n_dev, n_fixed, classes, ncls, C, balanced, eps, max_iter, coef, ldc, rho,
-      info, m_max, ntask);
+      K, ldk, strideK, perm, ldk, cls_off, n_dev, n_fixed, ncls, C, balanced, eps, max_iter, coef, ldc,
+      rho, info, m_max, ntask);
   CPSD_LAUNCH_CHECK();
   return CPSD_OK;
 }

@@ -950,7 +950,9 @@ class CVEngine:
             state = dict(m_max=m_max, coef=self.ws('svc_coef', (B, ncls - 1, n_pad), torch.float64),
                          rho=self.ws('svc_rho', (B, npair), torch.float64),
                          gamma=self.ws('svc_gamma', (B,), torch.float64),
-                         K=self.ws('svc_K', (B, n_pad, n_pad)))
+                         K=self.ws('svc_K', (B, n_pad, n_pad)), perm=self.ws('svc_perm', (B, n_pad), I32),
+                         off=self.ws('svc_off', (B, ncls + 1), I32),
+                         sqn=self.ws('svc_sqn', (B, n_pad), torch.float64))
             info = self.ws('svc_info', (B, npair, 2), I32)
             return state, info, np.zeros(0, dtype=_lib.SVM_DESC)
         W = self.ws('svm_W', (B, ncls, kcap + 1), torch.float64)
@@ -990,9 +992,10 @@ class CVEngine:
         npool_dev = ctypes_int_ptr(pk.iaddr(o_npool))
         ypool_dev = ctypes_int_ptr(pk.iaddr(o_ypool))
         ctx.call('cpsd_svc_kernel_matrix', ptr(St), n_pad, kcap * n_pad, ptr(k2), 0, npool_dev, 0, n_pad,
-                 kid, self.svc_gamma, ptr(sv['gamma']), ptr(sv['K']), n_pad, n_pad * n_pad, B)
-        ctx.call('cpsd_svc_fit_ovo', ptr(sv['K']), n_pad, n_pad * n_pad, ypool_dev, ypool_ld, npool_dev, 0,
-                 ptr(self.classes_dev), ncls, self.Csvm, int(self.class_weight == 'balanced'),
+                 ypool_dev, ypool_ld, ptr(self.classes_dev), ncls, kid, self.svc_gamma, ptr(sv['gamma']),
+                 ptr(sv['perm']), ptr(sv['off']), ptr(sv['sqn']), ptr(sv['K']), n_pad, n_pad * n_pad, B)
+        ctx.call('cpsd_svc_fit_ovo', ptr(sv['K']), n_pad, n_pad * n_pad, ptr(sv['perm']), ptr(sv['off']),
+                 npool_dev, 0, ncls, self.Csvm, int(self.class_weight == 'balanced'),
                  self.svc_tol, self.svc_max_iter, ptr(sv['coef']), n_pad, ptr(sv['rho']), ptr(info),
                  sv['m_max'], B)
         ctx.call('cpsd_svc_predict_ovo', ptr(St), n_pad, kcap * n_pad, ptr(Ste), n_te_max,

@@ -436,16 +436,17 @@ def svc_fit_ovo(S, y, C=1.0, kernel='rbf', gamma='scale', balanced=False, tol=1e
     Sd, yd, cd = ctx.upload(St), ctx.upload(y), ctx.upload(classes)
     K = ctx.empty((n, lds))
     gam = ctx.empty((1,), F64)
+    perm, off, sqn = ctx.empty((lds,), I32), ctx.empty((ncls + 1,), I32), ctx.empty((lds,), F64)
     kid = _SVC_KERNELS[kernel]
-    ctx.call('cpsd_svc_kernel_matrix', ptr(Sd), lds, 0, ptr(None), k, ptr(None), n, n, kid, g, ptr(gam),
-             ptr(K), lds, 0, 1)
+    ctx.call('cpsd_svc_kernel_matrix', ptr(Sd), lds, 0, ptr(None), k, ptr(None), n, n, ptr(yd), 0, ptr(cd),
+             ncls, kid, g, ptr(gam), ptr(perm), ptr(off), ptr(sqn), ptr(K), lds, 0, 1)
     npair = ncls * (ncls - 1) // 2
     coef = ctx.empty((ncls - 1, lds), F64)
     rho = ctx.empty((npair,), F64)
     info = ctx.empty((npair, 2), I32)
     srt = np.sort(counts)
     m_max = int(srt[-1] + srt[-2])
-    ctx.call('cpsd_svc_fit_ovo', ptr(K), lds, 0, ptr(yd), 0, ptr(None), n, ptr(cd), ncls, float(C),
+    ctx.call('cpsd_svc_fit_ovo', ptr(K), lds, 0, ptr(perm), ptr(off), ptr(None), n, ncls, float(C),
              int(bool(balanced)), float(tol), int(max_iter), ptr(coef), lds, ptr(rho), ptr(info), m_max, 1)
     return dict(St=Sd, y=yd, classes_dev=cd, coef_dev=coef, rho_dev=rho, gamma_dev=gam, n=n, k=k, lds=lds,
                 kernel=kid, classes=classes, coef=coef.cpu().numpy()[:, :n], rho=rho.cpu().numpy(),

@@ -279,20 +279,25 @@ int cpsd_svm_predict_ovr(const float* Xt, int ldx, long long strideX, const doub
  * and SVC(kernel='linear') inside BaggingClassifier (scripts/aligned_decode_svm.py:262-263).
  * St: feature-major pool scores (k x n, leading dimension lds) per fold; kernel 0 = linear,
  * 1 = rbf; gamma <= 0 means 'scale' = 1 / (k * var(X)); the per-fold gamma is written to
- * gamma_out; K: (n x n) float kernel matrix per fold. */
+ * gamma_out; y: pool labels (ldy per fold), classes: sorted label values; K: (n x n) float kernel
+ * matrix per fold in CLASS-SORTED sample order (perm / cls_off / sqn: [fold][ldk] ints,
+ * [fold][ncls+1] ints, [fold][ldk] doubles, written here), so that a class pair's block is two
+ * contiguous row / column ranges. */
 int cpsd_svc_kernel_matrix(const float* St, int lds, long long strideS, const int* k_dev,
-                           int k_fixed, const int* n_dev, int n_fixed, int n_max, int kernel,
-                           double gamma, double* gamma_out, float* K, int ldk, long long strideK,
+                           int k_fixed, const int* n_dev, int n_fixed, int n_max, const int* y, int ldy,
+                           const int* classes, int ncls, int kernel, double gamma, double* gamma_out,
+                           int* perm, int* cls_off, double* sqn, float* K, int ldk, long long strideK,
                            int nfold, cudaStream_t stream);
-/* SMO per (fold, class pair), pairs in libsvm's order; y: pool labels (ldy per fold); classes:
- * sorted label values; balanced != 0: C_c = C * n / (n_classes * count_c) (sklearn
+/* SMO per (fold, class pair), one warp each, pairs in libsvm's order, on the class-sorted kernel
+ * matrix cpsd_svc_kernel_matrix left in K (perm: [fold][ldk] sorted position -> pool sample,
+ * cls_off: [fold][ncls+1]); balanced != 0: C_c = C * n / (n_classes * count_c) (sklearn
  * class_weight='balanced'); eps = libsvm's tol; coef: [fold][ncls-1][ldc] in libsvm's sv_coef
  * layout indexed by pool sample; rho: [fold][npair]; info: [fold][npair][2] = iterations,
  * status (0 converged, 1 iteration cap, 2 class absent, 3 pair larger than m_max). */
-int cpsd_svc_fit_ovo(const float* K, int ldk, long long strideK, const int* y, int ldy,
-                     const int* n_dev, int n_fixed, const int* classes, int ncls, double C,
-                     int balanced, double eps, int max_iter, double* coef, int ldc, double* rho,
-                     int* info, int m_max, int nfold, cudaStream_t stream);
+int cpsd_svc_fit_ovo(const float* K, int ldk, long long strideK, const int* perm, const int* cls_off,
+                     const int* n_dev, int n_fixed, int ncls, double C, int balanced, double eps,
+                     int max_iter, double* coef, int ldc, double* rho, int* info, int m_max, int nfold,
+                     cudaStream_t stream);
 /* votes of all pair decisions, first maximum wins (libsvm svm_predict_values); dec (optional):
  * [fold][n_te_max][npair] */
 int cpsd_svc_predict_ovo(const float* St, int lds, long long strideS, const float* Ste, int ldt,
