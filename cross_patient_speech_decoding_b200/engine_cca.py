@@ -91,65 +91,84 @@ def batch_cca_gen(eng, batch, want_details):
     pk = eng.packB
     pk.reset()
     eng._o_zero = pk.o_zero = pk.add_ints([0])
-    o_tr = [pk.add_ints(tb['tr'] * T) for tb in tabs]
-    o_te = [pk.add_ints(tb['te'] * T) for tb in tabs]
-    o_allseg = [pk.add_ints(np.arange(eng.views[v].N, dtype=np.int32) * T) for v in range(P)]
-    cross_N = [eng.views[v].N for v in range(1, P)]
-    n_pool = [(nt if eng.tar_in_train else 0) + sum(cross_N) for nt in n_tr]
-    n_te_max = max(n_te)
-    n_pad = _ceil(max(a + b for a, b in zip(n_pool, n_te)), 128)
+    # (all index tables and records below are built column-wise with numpy: no per-fold or
+    # per-pair Python work beyond a few slice assignments)
+    n_tr_a, n_te_a = np.asarray(n_tr, dtype=np.int64), np.asarray(n_te, dtype=np.int64)
+    o_tr = pk.add_ints(np.concatenate([tb['tr'] for tb in tabs]) * T) + \
+        np.concatenate([[0], np.cumsum(n_tr_a)])[:-1]
+    o_te = pk.add_ints(np.concatenate([tb['te'] for tb in tabs]) * T) + \
+        np.concatenate([[0], np.cumsum(n_te_a)])[:-1]
+    Ns = np.array([eng.views[v].N for v in range(P)], dtype=np.int64)
+    o_allseg = pk.add_ints(np.arange(int(Ns.max()), dtype=np.int32) * T)   # prefix serves every view
+    sumN = int(Ns[1:].sum())
+    n_pool_a = (n_tr_a if eng.tar_in_train else 0 * n_tr_a) + sumN
+    n_pool = n_pool_a.tolist()
+    n_te_max = int(n_te_a.max())
+    n_pad = _ceil(int((n_pool_a + n_te_a).max()), 128)
     F = T * dq
-    ypool = np.zeros((B, n_pad), dtype=np.int32)
+    # destination rows inside the pooled matrix: slices of one table of row starts
+    o_rows = pk.add_ints(np.arange(n_pad + n_te_max, dtype=np.int64) * T)
+    row0 = n_tr_a if eng.tar_in_train else 0 * n_tr_a
+    xoff = np.concatenate([[0], np.cumsum(Ns[1:])])[:-1]                 # start of each cross patient
     o_pooldst = np.zeros((B, P), dtype=np.int64)
-    o_tedst = []
+    o_pooldst[:, 0] = o_rows
+    o_pooldst[:, 1:] = o_rows + row0[:, None] + xoff[None, :]
+    o_tedst = o_rows + n_pool_a
+    ypool = np.zeros((B, n_pad), dtype=np.int32)
+    ycross = np.concatenate([eng.views[v].y for v in range(1, P)]).astype(np.int32) if nv else \
+        np.zeros(0, dtype=np.int32)
     for f, tb in enumerate(tabs):
-        row, ys = 0, []
+        r0 = int(row0[f])
         if eng.tar_in_train:
-            o_pooldst[f, 0] = pk.add_ints((row + np.arange(n_tr[f])) * T)
-            ys.append(tv.y[tb['tr']])
-            row += n_tr[f]
-        for v in range(1, P):
-            o_pooldst[f, v] = pk.add_ints((row + np.arange(eng.views[v].N)) * T)
-            ys.append(eng.views[v].y)
-            row += eng.views[v].N
-        ypool[f, :row] = np.concatenate(ys)
-        o_tedst.append(pk.add_ints((row + np.arange(n_te[f])) * T))
+            ypool[f, :r0] = tv.y[tb['tr']]
+        ypool[f, r0:r0 + sumN] = ycross
     o_ypool = pk.add_ints(ypool)
     o_npool = pk.add_ints(n_pool)
-    o_nall = pk.add_ints([a + b for a, b in zip(n_pool, n_te)])
+    o_nall = pk.add_ints(n_pool_a + n_te_a)
     o_nte = pk.add_ints(n_te)
     o_dt = pk.add_ints(d_a)
     o_cdim_t = pk.add_ints([tv.C] * B)
     o_cdim_x = pk.add_ints([eng.views[v].C for v in range(1, P)])
-    # pairwise shared classes
-    pairs = []
-    if aligned:
+    # pairwise shared classes: pair j = f * nv + i, classes ascending
+    npair = 0
+    if aligned and nv:
+        V = len(eng.vocab)
+        present2d = np.zeros((B, V), dtype=bool)
         for f, tb in enumerate(tabs):
-            slot_t = -np.ones(len(eng.vocab), dtype=np.int64)
-            slot_t[tb['present']] = np.arange(len(tb['present']))
+            present2d[f, tb['present']] = True
+        xm = getattr(eng, '_cross_mask', None)
+        if xm is None:
+            xm = np.zeros((nv, V), dtype=bool)
+            rows = np.zeros((nv, V), dtype=np.int64)
             for i in range(nv):
-                sh = np.array(sorted(set(tb['present'].tolist()) & eng.cross_classes[i]),
-                              dtype=np.int64)
-                if len(sh) == 0:
-                    raise ValueError('fold %d shares no alignment class with cross patient %d'
-                                     % (f, i))
-                pairs.append(dict(f=f, i=i, K=len(sh), sh=sh,
-                                  o_a=pk.add_ints(slot_t[sh] * T),
-                                  o_b=pk.add_ints(eng.cm_row[i + 1][sh] * T)))
-        KTmax = max(p['K'] for p in pairs) * T
+                xm[i, sorted(eng.cross_classes[i])] = True
+                rows[i] = np.asarray(eng.cm_row[i + 1], dtype=np.int64)
+            eng._cross_mask, eng._cross_rows = xm, rows
+        sh = (present2d[:, None, :] & xm[None, :, :]).reshape(B * nv, V)
+        Kp = sh.sum(axis=1).astype(np.int64)
+        if (Kp == 0).any():
+            j = int(np.nonzero(Kp == 0)[0][0])
+            raise ValueError('fold %d shares no alignment class with cross patient %d'
+                             % (j // nv, j % nv))
+        npair = B * nv
+        pj, pc = np.nonzero(sh)                                        # pair, class (ascending)
+        pf, pi = pj // nv, pj % nv
+        slot_t = np.cumsum(present2d, axis=1) - 1                      # class -> row of the fold's means
+        starts = np.concatenate([[0], np.cumsum(Kp)])[:-1]
+        o_a = pk.add_ints(slot_t[pf, pc] * T) + starts
+        o_b = pk.add_ints(eng._cross_rows[pi, pc] * T) + starts
+        KTmax = int(Kp.max()) * T
         o_segdst = pk.add_ints(np.arange(KTmax // T, dtype=np.int32) * T)
-    pk.reserve_ints()
+    ib = pk.reserve_ints()
 
     # PCA bases (sklearn sign convention, zero-padded to dmax columns)
     Wt = eng.ws('c_Wt', (B, Cm, dmax))
     Wx = eng.ws('c_Wx', (max(nv, 1), Cm, dmax))
-    npair = len(pairs)
     Zall = eng.ws('pool_Z', (B, n_pad, F))
     Zall.zero_()
-    r_pp = []
-
-    def proj_rec(X, src, dst, mu, W, ldw, f, nseg, C, q):
-        return (addr(X), src, dst, mu, W, addr(Zall, f * n_pad * F), nseg, T, C, q, C, ldw, dq, 0)
+    xC = np.array([eng.views[v].C for v in range(1, P)], dtype=np.int64)
+    xX = np.array([addr(eng.views[v].X) for v in range(1, P)], dtype=np.int64)
+    fi = np.arange(B, dtype=np.int64)
 
     if aligned and nv:
         mA = eng.ws('c_mA', (npair, Cm))
@@ -162,56 +181,88 @@ def batch_cca_gen(eng, batch, want_details):
         rho = eng.ws('c_rho', (npair, dmax))
         cinfo = eng.ws('c_info', (npair, 4), I32)
         Wc = eng.ws('c_Wc', (npair, Cm, dmax))
-        r_m = np.zeros(2 * npair, dtype=_lib.COLSUM_DESC)
-        r_pl = np.zeros(2 * npair, dtype=_lib.PROJ_DESC)
+        jj = np.arange(npair, dtype=np.int64)
+        jf, ji = jj // nv, jj % nv
+        cma = addr(cmT) + 4 * Kmax * T * tv.C * jf
+        cmb = np.array([addr(eng.cm[i + 1]) for i in range(nv)], dtype=np.int64)[ji]
+        sa, sb = ib + 4 * o_a, ib + 4 * o_b
+        zero_a = pk.iaddr(eng._o_zero)
+        segdst = pk.iaddr(o_segdst)
+        inv_kt = (1.0 / (Kp * T)).astype(np.float32)
+        r_m = np.zeros((npair, 2), dtype=_lib.COLSUM_DESC)
+        r_m['A'][:, 0], r_m['A'][:, 1] = cma, cmb
+        r_m['segA'][:, 0], r_m['segA'][:, 1] = sa, sb
+        r_m['out'][:, 0], r_m['out'][:, 1] = addr(mA) + 4 * Cm * jj, addr(mB) + 4 * Cm * jj
+        r_m['nseg'], r_m['seg_len'] = Kp[:, None], T
+        r_m['p'][:, 0] = r_m['lda'][:, 0] = tv.C
+        r_m['p'][:, 1] = r_m['lda'][:, 1] = xC[ji]
+        r_m['alpha'] = inv_kt[:, None]
+        r_m = r_m.ravel()
+        lbase = addr(Lcat) + 4 * KTmax * 2 * dmax * jj
+        r_pl = np.zeros((npair, 2), dtype=_lib.PROJ_DESC)
+        r_pl['X'][:, 0], r_pl['X'][:, 1] = cma, cmb
+        r_pl['seg_src'][:, 0], r_pl['seg_src'][:, 1] = sa, sb
+        r_pl['seg_dst'] = segdst
+        r_pl['mu'][:, 0], r_pl['mu'][:, 1] = addr(mA) + 4 * Cm * jj, addr(mB) + 4 * Cm * jj
+        r_pl['W'][:, 0], r_pl['W'][:, 1] = addr(Wt) + 4 * Cm * dmax * jf, addr(Wx) + 4 * Cm * dmax * ji
+        r_pl['Y'][:, 0], r_pl['Y'][:, 1] = lbase, lbase + 4 * dmax
+        r_pl['nseg'], r_pl['seg_len'] = Kp[:, None], T
+        r_pl['C'][:, 0] = r_pl['ldx'][:, 0] = tv.C
+        r_pl['C'][:, 1] = r_pl['ldx'][:, 1] = xC[ji]
+        r_pl['q'], r_pl['ldw'], r_pl['ldy'] = dmax, dmax, 2 * dmax
+        r_pl = r_pl.ravel()
+        sbase = addr(S) + 4 * 4 * dmax * dmax * jj
         r_s = np.zeros(npair, dtype=_lib.GRAM_TN_DESC)
+        r_s['A'] = r_s['B'] = lbase
+        r_s['segA'] = r_s['segB'] = zero_a
+        r_s['out'], r_s['nseg'], r_s['seg_len'] = sbase, 1, Kp * T
+        r_s['p'] = r_s['q'] = r_s['lda'] = r_s['ldb'] = r_s['ldo'] = 2 * dmax
+        r_s['sym'], r_s['alpha'] = 1, 1.0
         r_c = np.zeros(npair, dtype=_lib.CCA_DESC)
+        r_c['Saa'], r_c['Sbb'], r_c['Sab'] = sbase, sbase + 4 * (dmax * 2 * dmax + dmax), sbase + 4 * dmax
+        r_c['Ma'], r_c['Mb'] = addr(Ma) + 4 * dmax * dmax * jj, addr(Mb) + 4 * dmax * dmax * jj
+        r_c['G'], r_c['rho'] = addr(G) + 4 * dmax * dmax * jj, addr(rho) + 4 * dmax * jj
+        r_c['info'] = addr(cinfo) + 16 * jj
+        r_c['da'], r_c['db'] = d_a[jf], np.asarray(d_b)[ji]
+        r_c['lds'], r_c['ldm'], r_c['ldg'], r_c['rank_tol'] = 2 * dmax, dmax, dmax, 1e-10
+        # Wc = W_b G  (C_b x dmax)
         r_w = np.zeros(npair, dtype=_lib.PROJ_DESC)
-        for j, p in enumerate(pairs):
-            f, i, K = p['f'], p['i'], p['K']
-            xv = eng.views[i + 1]
-            cma = addr(cmT, f * Kmax * T * tv.C)
-            cmb = addr(eng.cm[i + 1])
-            sa, sb = pk.iaddr(p['o_a']), pk.iaddr(p['o_b'])
-            r_m[2 * j] = (cma, sa, addr(mA, j * Cm), K, T, tv.C, tv.C, 1.0 / (K * T), 0)
-            r_m[2 * j + 1] = (cmb, sb, addr(mB, j * Cm), K, T, xv.C, xv.C, 1.0 / (K * T), 0)
-            lbase = addr(Lcat, j * KTmax * 2 * dmax)
-            r_pl[2 * j] = (cma, sa, pk.iaddr(o_segdst), addr(mA, j * Cm), addr(Wt, f * Cm * dmax),
-                           lbase, K, T, tv.C, dmax, tv.C, dmax, 2 * dmax, 0)
-            r_pl[2 * j + 1] = (cmb, sb, pk.iaddr(o_segdst), addr(mB, j * Cm),
-                               addr(Wx, i * Cm * dmax), lbase + 4 * dmax, K, T, xv.C, dmax, xv.C,
-                               dmax, 2 * dmax, 0)
-            sbase = addr(S, j * 4 * dmax * dmax)
-            r_s[j] = (lbase, lbase, pk.iaddr(eng._o_zero), pk.iaddr(eng._o_zero), 0, 0, sbase, 1,
-                      K * T, 2 * dmax, 2 * dmax, 2 * dmax, 2 * dmax, 2 * dmax, 1, 1.0, 0)
-            r_c[j] = (sbase, sbase + 4 * (dmax * 2 * dmax + dmax), sbase + 4 * dmax, 0, 0,
-                      addr(Ma, j * dmax * dmax), addr(Mb, j * dmax * dmax),
-                      addr(G, j * dmax * dmax), addr(rho, j * dmax), addr(cinfo, j * 4),
-                      int(d_a[f]), int(d_b[i]), 2 * dmax, dmax, dmax, 0, 1e-10, 0)
-            # Wc = W_b G  (C_b x dmax)
-            r_w[j] = (addr(Wx, i * Cm * dmax), pk.iaddr(eng._o_zero), pk.iaddr(eng._o_zero), 0,
-                      addr(G, j * dmax * dmax), addr(Wc, j * Cm * dmax), 1, xv.C, dmax, dmax,
-                      dmax, dmax, dmax, 0)
+        r_w['X'] = addr(Wx) + 4 * Cm * dmax * ji
+        r_w['seg_src'] = r_w['seg_dst'] = zero_a
+        r_w['W'], r_w['Y'] = addr(G) + 4 * dmax * dmax * jj, addr(Wc) + 4 * Cm * dmax * jj
+        r_w['nseg'], r_w['seg_len'] = 1, xC[ji]
+        r_w['C'] = r_w['q'] = r_w['ldx'] = r_w['ldw'] = r_w['ldy'] = dmax
         d_m, d_pl = pk.add_descs(r_m), pk.add_descs(r_pl)
         d_s, d_c, d_w = pk.add_descs(r_s), pk.add_descs(r_c), pk.add_descs(r_w)
-    # pooled projection records
-    for f, tb in enumerate(tabs):
-        q = int(d_out[f])
-        if eng.tar_in_train:
-            r_pp.append(proj_rec(tv.X, pk.iaddr(o_tr[f]), pk.iaddr(o_pooldst[f, 0]),
-                                 addr(mu_t, f * Cm), addr(Wt, f * Cm * dmax), dmax, f, n_tr[f],
-                                 tv.C, q))
-        for i in range(nv):
-            xv = eng.views[i + 1]
-            if aligned:
-                W = addr(Wc, (f * nv + i) * Cm * dmax)
-            else:
-                W = addr(Wx, i * Cm * dmax)
-            r_pp.append(proj_rec(xv.X, pk.iaddr(o_allseg[i + 1]), pk.iaddr(o_pooldst[f, i + 1]),
-                                 addr(eng.cross_mu, i * Cm), W, dmax, f, xv.N, xv.C, q))
-        r_pp.append(proj_rec(tv.X, pk.iaddr(o_te[f]), pk.iaddr(o_tedst[f]), addr(mu_t, f * Cm),
-                             addr(Wt, f * Cm * dmax), dmax, f, n_te[f], tv.C, q))
-    r_pp = np.array(r_pp, dtype=_lib.PROJ_DESC)
+    # pooled projection records: per fold [target train] + cross patients + target test
+    nrec = (1 if eng.tar_in_train else 0) + nv + 1
+    r_pp = np.zeros((B, nrec), dtype=_lib.PROJ_DESC)
+    r_pp['Y'] = (addr(Zall) + 4 * n_pad * F * fi)[:, None]
+    r_pp['seg_len'], r_pp['ldw'], r_pp['ldy'] = T, dmax, dq
+    r_pp['q'] = np.asarray(d_out, dtype=np.int64)[:, None]
+    c0 = 0
+    if eng.tar_in_train:
+        r_pp['X'][:, 0], r_pp['seg_src'][:, 0] = addr(tv.X), ib + 4 * o_tr
+        r_pp['seg_dst'][:, 0] = ib + 4 * o_pooldst[:, 0]
+        r_pp['mu'][:, 0], r_pp['W'][:, 0] = addr(mu_t) + 4 * Cm * fi, addr(Wt) + 4 * Cm * dmax * fi
+        r_pp['nseg'][:, 0], r_pp['C'][:, 0], r_pp['ldx'][:, 0] = n_tr_a, tv.C, tv.C
+        c0 = 1
+    if nv:
+        r_pp['X'][:, c0:c0 + nv] = xX[None, :]
+        r_pp['seg_src'][:, c0:c0 + nv] = pk.iaddr(o_allseg)
+        r_pp['seg_dst'][:, c0:c0 + nv] = ib + 4 * o_pooldst[:, 1:]
+        r_pp['mu'][:, c0:c0 + nv] = (addr(eng.cross_mu) + 4 * Cm * np.arange(nv, dtype=np.int64))[None, :]
+        if aligned:
+            r_pp['W'][:, c0:c0 + nv] = addr(Wc) + 4 * Cm * dmax * (fi[:, None] * nv + np.arange(nv)[None, :])
+        else:
+            r_pp['W'][:, c0:c0 + nv] = (addr(Wx) + 4 * Cm * dmax * np.arange(nv, dtype=np.int64))[None, :]
+        r_pp['nseg'][:, c0:c0 + nv] = Ns[None, 1:]
+        r_pp['C'][:, c0:c0 + nv] = r_pp['ldx'][:, c0:c0 + nv] = xC[None, :]
+    r_pp['X'][:, -1], r_pp['seg_src'][:, -1] = addr(tv.X), ib + 4 * o_te
+    r_pp['seg_dst'][:, -1] = ib + 4 * o_tedst
+    r_pp['mu'][:, -1], r_pp['W'][:, -1] = addr(mu_t) + 4 * Cm * fi, addr(Wt) + 4 * Cm * dmax * fi
+    r_pp['nseg'][:, -1], r_pp['C'][:, -1], r_pp['ldx'][:, -1] = n_te_a, tv.C, tv.C
+    r_pp = r_pp.ravel()
     d_pp = pk.add_descs(r_pp)
     r1, r2, pmu, Kall = eng._pooled_stage(pk, B, Zall, n_pad, F, n_pool, n_te, o_npool, o_nall,
                                           o_ypool, n_pad, n_te_max, want_details)

@@ -42,7 +42,7 @@ def folds_for(y, n_splits, iters, seed0):
 
 
 def timed(tag, eng, folds, extra=None):
-    eng.run(folds[:max(1, len(folds) // args.iters)])          # warm-up: workspaces, caches
+    eng.run(folds)          # warm-up with the same batch structure: workspaces of every lane, caches
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     res = eng.run(folds)
