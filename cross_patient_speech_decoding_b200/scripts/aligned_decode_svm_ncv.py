@@ -1,0 +1,179 @@
+"""Batched counterpart of the reference's ``scripts/aligned_decode_svm_ncv.py``.
+
+Same command line (``-pt -pi -po -t -a -m -j -r -tss -pp -c -f -s``), same data-dictionary
+pickle in (``alignment_utils.load_pkl`` / ``decoding_data_from_dict``,
+aligned_decode_svm_ncv.py:268-275), same result pickle out
+(``{'params', 'y_true', 'y_pred', 'wrong_trs', 'accs'}``, :289-296, :443-456) -- but the
+``n_iter x n_folds`` fit/predict units of the two nested loops (:332-442) are generated up
+front (the numpy global RNG is consumed in the reference's order: one shuffled
+StratifiedKFold per iteration, then one stratified ``train_test_split`` per fold when
+``--trial_subsample < 1``) and handed to ``cv_align_decode`` as ONE batch.
+
+The nested Bayesian search (``-cv True``, needs scikit-optimize) is not available.
+Extra options: ``--data_file``, ``--n_iter``, ``--n_folds``, ``--decoder``, ``--seed``.
+"""
+import argparse
+import os
+
+import numpy as np
+
+from .. import cv_align_decode
+from ..alignment import alignment_utils as utils
+from ..folds import cv_splits
+
+
+def init_parser():
+    ap = argparse.ArgumentParser(description='Aligned decoding SVM (batched, B200)')
+    ap.add_argument('-pt', '--patient', type=str, required=True, help='Patient ID')
+    ap.add_argument('-pi', '--p_ind', type=int, default=-1, help='Sequence position index')
+    ap.add_argument('-po', '--pool_train', type=str, default='False')
+    ap.add_argument('-t', '--tar_in_train', type=str, default='True')
+    ap.add_argument('-a', '--cca_align', type=str, default='False')
+    ap.add_argument('-m', '--MCCA_align', type=str, default='False')
+    ap.add_argument('-j', '--joint_dim_red', type=str, default='False')
+    ap.add_argument('-r', '--random_data', type=str, default='False')
+    ap.add_argument('-n', '--no_S23', type=str, default='False')
+    ap.add_argument('-tss', '--trial_subsample', type=float, default=1.0)
+    ap.add_argument('-surr', '--surrogate', type=str, default='False')
+    ap.add_argument('-pp', '--pooled_patients', type=str, default='all')
+    ap.add_argument('-c', '--cluster', type=str, default='True')
+    ap.add_argument('-cv', '--cross_validate', type=str, default='False')
+    ap.add_argument('-f', '--filename', type=str, default='')
+    ap.add_argument('-s', '--suffix', type=str, default='')
+    # not in the reference (its values are constants in the script body)
+    ap.add_argument('--data_file', type=str, default='')
+    ap.add_argument('--n_iter', type=int, default=50)
+    ap.add_argument('--n_folds', type=int, default=20)
+    ap.add_argument('--decoder', type=str, default='svc_rbf',
+                    choices=['svc_rbf', 'svc_linear', 'linear'],
+                    help="svc_rbf = the script's SVC(kernel='rbf', class_weight='balanced')")
+    ap.add_argument('--seed', type=int, default=None, help='np.random.seed before the loops')
+    return ap
+
+
+def str2bool(s):
+    return s.lower() == 'true'
+
+
+def make_units(lab_tar, n_iter, n_folds, tr_subsamp_r):
+    """The (train_idx, test_idx) units of every iteration, drawing from the numpy global RNG in
+    the order of aligned_decode_svm_ncv.py:332-362."""
+    from sklearn.model_selection import train_test_split
+    units = []
+    for _ in range(n_iter):
+        for train_idx, test_idx in cv_splits(lab_tar, n_folds):
+            if tr_subsamp_r < 1:
+                train_idx, _ = train_test_split(train_idx, train_size=tr_subsamp_r,
+                                                stratify=lab_tar[train_idx], shuffle=True)
+            units.append((np.asarray(train_idx), np.asarray(test_idx)))
+    return units
+
+
+def run(inputs):
+    from sklearn.metrics import balanced_accuracy_score
+    cluster = str2bool(inputs['cluster'])
+    if cluster:
+        data_path, out_path = os.path.expanduser('~') + '/data/', os.path.expanduser('~') + '/workspace/'
+    else:
+        data_path, out_path = '../data/', '../acc_data/'
+    pt, p_ind = inputs['patient'], inputs['p_ind']
+    pool_train, tar_in_train = str2bool(inputs['pool_train']), str2bool(inputs['tar_in_train'])
+    cca_align, mcca_align = str2bool(inputs['cca_align']), str2bool(inputs['MCCA_align'])
+    joint_dim_red = str2bool(inputs['joint_dim_red'])
+    if str2bool(inputs['cross_validate']):
+        raise NotImplementedError('nested Bayesian search (-cv True) is not available here')
+    n_iter, n_folds = inputs['n_iter'], inputs['n_folds']
+    if sum([cca_align, mcca_align, joint_dim_red]) > 1:      # the reference's precedence (:218-222)
+        cca_align = mcca_align = False
+    if mcca_align:
+        param_grid = {'n_comp': 30, 'regs': 0.5, 'pca_var': 0.8,
+                      'decoder__dimredreshape__n_components': 0.8}
+    else:
+        param_grid = {'n_comp': 0.9, 'decoder__dimredreshape__n_components': 0.8}
+    algn_type, algn_grouping, lab_type, red_method = 'phon_seq', 'class', 'phon', 'PCA'
+    if inputs['filename']:
+        filename = inputs['filename']
+    else:
+        prefix = out_path + ('outputs/alignment_accs/%s/' % pt if cluster else 'ncv_accs/%s/' % pt)
+        filename = prefix + '%s_%s%s_%s.pkl' % (pt, 'p' if lab_type == 'phon' else 'a',
+                                               'All' if p_ind == -1 else p_ind, inputs['suffix'])
+    data_file = inputs['data_file'] or data_path + (
+        'pt_decoding_data_S62_TME.pkl' if str2bool(inputs['surrogate']) else 'pt_decoding_data_S62.pkl')
+    if inputs.get('seed') is not None:
+        np.random.seed(inputs['seed'])
+    pt_data = utils.load_pkl(data_file)
+    (D_tar, lab_tar, lab_tar_full), pre_data = utils.decoding_data_from_dict(
+        pt_data, pt, p_ind, lab_type=lab_type, algn_type=algn_type)
+    if str2bool(inputs['random_data']):
+        cross = [(np.random.rand(*d[0].shape), d[1], d[2]) for d in pre_data]
+    elif inputs['pooled_patients'] != 'all':
+        pre_pts = pt_data[pt]['pre_pts']
+        cross = [pre_data[pre_pts.index(p)] for p in inputs['pooled_patients'].split(',')]
+    else:
+        cross = pre_data
+    out = {'params': {'pt': pt, 'p_ind': p_ind, 'pool_train': pool_train,
+                      'tar_in_train': tar_in_train, 'cca_align': cca_align,
+                      'joint_dim_red': joint_dim_red, 'n_iter': n_iter, 'n_folds': n_folds,
+                      'hyperparams': param_grid, 'algn_type': algn_type,
+                      'algn_grouping': algn_grouping, 'lab_type': lab_type,
+                      'red_method': red_method}}
+    lab_tar = np.asarray(lab_tar)
+    units = make_units(lab_tar, n_iter, n_folds, inputs['trial_subsample'])
+    dec_kw = dict(decoder=inputs['decoder'],
+                  class_weight='balanced' if inputs['decoder'] == 'svc_rbf' else None,
+                  decoder_var=param_grid['decoder__dimredreshape__n_components'])
+    if pool_train:
+        if joint_dim_red:
+            kw = dict(method='jointpca', n_comp=40)          # JointPCA's default, untouched by set_params
+        elif cca_align:
+            kw = dict(method='cca', n_comp=param_grid['n_comp'])
+        elif mcca_align:
+            kw = dict(method='mcca', n_comp=30, regs=0.5, pca_var=0.8)
+        else:
+            kw = dict(method='none', n_comp=param_grid['n_comp'])
+        res = cv_align_decode((D_tar, lab_tar, lab_tar_full), cross, units,
+                              tar_in_train=tar_in_train, use_tensor_cores=True, max_batch=148,
+                              **kw, **dec_kw)
+        y_pred_units = res['y_pred']
+    else:
+        # single-patient branch (:406-428): DimRedReshape(PCA(0.8)) -> decoder on the raw trials
+        from sklearn.pipeline import make_pipeline
+        from ..decomposition.DimRedReshape import DimRedReshape
+        from ..decomposition.PCA import PCA
+        from ..svm import SVC, LinearSVC
+        y_pred_units = []
+        for tr, te in units:
+            dec = LinearSVC() if inputs['decoder'] == 'linear' else SVC(
+                kernel=inputs['decoder'][4:], class_weight=dec_kw['class_weight'])
+            clf = make_pipeline(DimRedReshape(PCA, n_components=0.8), dec)
+            clf.fit(D_tar[tr], lab_tar[tr])
+            y_pred_units.append(clf.predict(D_tar[te]))
+    y_true_iter, y_pred_iter, wrong_iter, accs = [], [], [], []
+    for j in range(n_iter):
+        yt, yp, wrong = [], [], []
+        for u in range(j * n_folds, (j + 1) * n_folds):
+            te = units[u][1]
+            y_test, y_hat = lab_tar[te], np.asarray(y_pred_units[u])
+            yt.extend(y_test)
+            yp.extend(y_hat)
+            wrong.extend(te[np.where(y_test != y_hat)[0]])
+        y_true_iter.append(yt)
+        y_pred_iter.append(yp)
+        wrong_iter.append(wrong)
+        accs.append(balanced_accuracy_score(yt, yp))
+    out.update(y_true=y_true_iter, y_pred=y_pred_iter, wrong_trs=wrong_iter, accs=accs)
+    d = os.path.dirname(filename)
+    if d:
+        os.makedirs(d, exist_ok=True)
+    utils.save_pkl(out, filename)
+    return out
+
+
+def aligned_decoding(argv=None):
+    args = init_parser().parse_args(argv)
+    return run(dict(vars(args)))
+
+
+if __name__ == '__main__':
+    aligned_decoding()
+    print('########## Done ###########')
