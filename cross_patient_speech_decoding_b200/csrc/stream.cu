@@ -301,6 +301,34 @@ k_region_mean_f64(const double* __restrict__ data, int nelec, int T, const int* 
   }
 }
 
+// r[c] = Pearson correlation of rows a[c][:], b[c][:] (fp64, two-pass like scipy.stats.pearsonr:
+// centre, then normalise) -- alignment/metrics.py:41-68 pt_corr, one CTA per condition.
+__global__ void __launch_bounds__(256)
+k_pearson_rows(const double* __restrict__ a, const double* __restrict__ b, long long len,
+               double* __restrict__ r) {
+  __shared__ double red[40];
+  const double* x = a + (long long)blockIdx.x * len;
+  const double* y = b + (long long)blockIdx.x * len;
+  double sx = 0.0, sy = 0.0;
+  for (long long i = threadIdx.x; i < len; i += blockDim.x) { sx += x[i]; sy += y[i]; }
+  const double mx = block_sum(sx, red) / (double)len;
+  const double my = block_sum(sy, red) / (double)len;
+  double sxx = 0.0, syy = 0.0, sxy = 0.0;
+  for (long long i = threadIdx.x; i < len; i += blockDim.x) {
+    const double dx = x[i] - mx, dy = y[i] - my;
+    sxx = fma(dx, dx, sxx);
+    syy = fma(dy, dy, syy);
+    sxy = fma(dx, dy, sxy);
+  }
+  sxx = block_sum(sxx, red);
+  syy = block_sum(syy, red);
+  sxy = block_sum(sxy, red);
+  if (threadIdx.x == 0) {
+    double v = sxy / (sqrt(sxx) * sqrt(syy));
+    r[blockIdx.x] = fmax(-1.0, fmin(1.0, v));      // scipy clips rounding overshoot the same way
+  }
+}
+
 // ---- JointPCA (alignment/JointPCA.py:165-211) --------------------------------------------
 // G (n x n fp64): Gram of the channel-concatenated class averages, only the blocks u <= v are
 // stored (diagonal blocks completely); s (n, fp32): column sums; nrows: rows of the matrix.
@@ -398,6 +426,15 @@ extern "C" int cpsd_region_mean_f64(const double* data, int ntrials, int nelec, 
   if (ntrials == 0) return CPSD_OK;
   k_region_mean_f64<<<dim3(nreg, ntrials), 128, 0, stream>>>(data, nelec, T, reg_ptr, reg_elec, nreg,
                                                              out);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
+
+extern "C" int cpsd_pearson_rows(const double* a, const double* b, int nrows, long long len, double* r,
+                                 cudaStream_t stream) {
+  CPSD_CHECK_ARG(nrows >= 0 && len >= 2, "pearson_rows: need at least 2 samples per row");
+  if (nrows == 0) return CPSD_OK;
+  k_pearson_rows<<<nrows, 256, 0, stream>>>(a, b, len, r);
   CPSD_LAUNCH_CHECK();
   return CPSD_OK;
 }

@@ -55,9 +55,13 @@ def str2bool(s):
     return s.lower() == 'true'
 
 
-def make_units(lab_tar, n_iter, n_folds, tr_subsamp_r):
+def make_units(lab_tar, n_iter, n_folds, tr_subsamp_r, fit_draws=1):
     """The (train_idx, test_idx) units of every iteration, drawing from the numpy global RNG in
-    the order of aligned_decode_svm_ncv.py:332-362."""
+    the order of aligned_decode_svm_ncv.py:332-442: per iteration one shuffled StratifiedKFold;
+    per fold the optional stratified ``train_test_split`` and then the draw sklearn's
+    ``SVC.fit`` makes for libsvm's seed (``check_random_state(None).randint(INT_MAX)``,
+    sklearn/svm/_base.py) -- ``fit_draws`` of them, so that the folds of iteration j+1 are the
+    ones the reference script would have produced."""
     from sklearn.model_selection import train_test_split
     units = []
     for _ in range(n_iter):
@@ -65,6 +69,8 @@ def make_units(lab_tar, n_iter, n_folds, tr_subsamp_r):
             if tr_subsamp_r < 1:
                 train_idx, _ = train_test_split(train_idx, train_size=tr_subsamp_r,
                                                 stratify=lab_tar[train_idx], shuffle=True)
+            for _d in range(fit_draws):
+                np.random.randint(np.iinfo('i').max)
             units.append((np.asarray(train_idx), np.asarray(test_idx)))
     return units
 

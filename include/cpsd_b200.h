@@ -63,6 +63,10 @@ int cpsd_sum_mats_f64(const double* base, const double* mats, long long mat_stri
  * means of spatial_avg_data (processing_utils/spatial_avg_subsampling.py:74-96) */
 int cpsd_gather_channels(const float* src, int lds, const int* idx, int nidx, float* dst, int ldd,
                          long long nrows, cudaStream_t stream);
+/* alignment/metrics.py:41-68 pt_corr: Pearson r of every condition's flattened (time x feature)
+ * block, a / b: (nrows x len) fp64 */
+int cpsd_pearson_rows(const double* a, const double* b, int nrows, long long len, double* r,
+                      cudaStream_t stream);
 int cpsd_region_mean_f64(const double* data, int ntrials, int nelec, int T, const int* reg_ptr,
                          const int* reg_elec, int nreg, double* out, cudaStream_t stream);
 /* ingest: the reference keeps trials as float64 (pickled numpy); cast once on the device */

@@ -231,3 +231,22 @@ def test_joint_pca_matches_reference_golden(pkg):
         agree += int((yp == g['y_pred_%d' % f]).sum())
         tot += len(te)
     assert agree / tot >= 0.99
+
+
+def test_pt_corr_matches_scipy(pkg):
+    """alignment.metrics.pt_corr / pt_corr_multi against scipy.stats.pearsonr (what the reference
+    calls per condition, alignment/metrics.py:41-68)."""
+    from scipy.stats import pearsonr
+    from cross_patient_speech_decoding_b200.alignment.metrics import pt_corr, pt_corr_multi
+    rng = np.random.default_rng(2)
+    a = rng.standard_normal((7, 30, 6))
+    b = 0.6 * a + 0.8 * rng.standard_normal((7, 30, 6))
+    b[3] = -a[3]
+    r, p = pt_corr(a, b, p_vals=True)
+    ref = [pearsonr(a[c].ravel(), b[c].ravel()) for c in range(7)]
+    assert np.abs(r - np.array([x[0] for x in ref])).max() < 1e-12
+    assert np.allclose(p, np.array([x[1] for x in ref]), rtol=1e-9, atol=1e-300)
+    rs = pt_corr_multi(a, [b, a])
+    assert np.allclose(rs[1], 1.0) and np.abs(rs[0] - r).max() == 0
+    with pytest.raises(ValueError):
+        pt_corr(a, b[:, :10])
