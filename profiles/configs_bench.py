@@ -92,32 +92,26 @@ if '3' in todo:
                 print(json.dumps(dict(config='3: 8 patients, %s, d=%d' % (method, d), error=str(e)[:80])), flush=True)
 
 if '4' in todo:
-    from cross_patient_speech_decoding_b200.processing_utils import device_subsample as ds
     from cross_patient_speech_decoding_b200.processing_utils.grid_subsampling import sig_channels_in_windows
+    from cross_patient_speech_decoding_b200.processing_utils.subsample_decode import subsample_decode
     chan_map = np.arange(1, 129).reshape(8, 16)
     sig = np.arange(1, 129)
-    subs = sig_channels_in_windows(chan_map, sig, (4, 8), (2, 4))[:6]     # 32-channel windows
-    res_dev = [ds.resident(p[0]) for p in pts]
-    t_all, n_all = 0.0, 0
+    subs = [np.sort(np.asarray(s_).ravel()) for s_ in sig_channels_in_windows(chan_map, sig, (4, 8), (2, 4))]
     for rep in range(2):                      # rep 0 = warm-up
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         n_all = 0
-        for si, sub in enumerate(subs):
-            cols = np.sort(np.asarray(sub).ravel())
-            for tgt in range(2 if rep == 0 else 8):
-                order = [tgt] + [p for p in range(8) if p != tgt]
-                views = []
-                for p in order:
-                    Xs = ds.gather_channels(res_dev[p], cols)
-                    views.append((Xs, pts[p][1], pts[p][2]))
-                folds = folds_for(pts[tgt][1], 20, 1, 300 + si)
-                eng = CVEngine(views[0], views[1:], method='cca', n_comp=0.9, use_tensor_cores=True, max_batch=148)
-                eng.run(folds)
-                n_all += len(folds)
+        for tgt in range(2 if rep == 0 else 8):
+            order = [tgt] + [p for p in range(8) if p != tgt]
+            np.random.seed(300 + tgt)
+            out = subsample_decode(pts[order[0]], [pts[p] for p in order[1:]], subs[:6], [subs] * 7,
+                                   n_folds=20, method='cca', n_comp=0.9, use_tensor_cores=True,
+                                   max_batch=148, depth=6)
+            n_all += 20 * len(out['accs'])
         torch.cuda.synchronize()
         t_all = time.perf_counter() - t0
-    print(json.dumps(dict(config='4: %d grid subsamples x 8 targets x 20 folds, CCA (engine per unit)' % len(subs),
+    print(json.dumps(dict(config='4: 6 grid subsamples (32 of 128 channels) x 8 targets x 20 folds, CCA, '
+                                 'subsample_decode (resident patients re-uploaded per target, 6 jobs in flight)',
                           folds=n_all, folds_per_s=round(n_all / t_all, 1), ms_per_fold=round(1e3 * t_all / n_all, 3))), flush=True)
 
 if '5' in todo:

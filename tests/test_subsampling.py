@@ -130,3 +130,42 @@ def test_subsampled_resident_views_match_host_slices(lib_built):
         for x, y in zip(a['y_pred'], b['y_pred']):
             assert np.array_equal(x, y)
         assert b['h2d_bytes'] < a['h2d_bytes']
+
+
+@pytest.mark.gpu
+def test_subsample_decode_matches_per_subsample_port(lib_built):
+    """processing_utils.subsample_decode (streamed jobs, device-side channel gathers, the
+    scripts' RNG order) against the CPU port run on host-sliced copies with the same choices."""
+    from sklearn.model_selection import StratifiedKFold
+    from cross_patient_speech_decoding_b200 import synthetic
+    from cross_patient_speech_decoding_b200.processing_utils.subsample_decode import subsample_decode
+    from oracle import pipeline_port as port
+    pts = [synthetic.make_patient(p, n_trials=n, n_time=20, n_chan=32, noise=0.6)
+           for p, n in enumerate((72, 80, 64))]
+    rng = np.random.default_rng(3)
+    tar_list = [np.sort(rng.choice(32, 12, replace=False)) for _ in range(3)]
+    cross_lists = [[np.sort(rng.choice(32, 12, replace=False)) for _ in range(4)] for _ in range(2)]
+    np.random.seed(9)
+    out = subsample_decode(pts[0], pts[1:], tar_list, cross_lists, n_folds=4, method='cca',
+                           n_comp=0.9, decoder='svc_rbf', class_weight='balanced', depth=2)
+    # replay the reference loop's RNG stream on the host
+    np.random.seed(9)
+    lab = pts[0][1]
+    same = tot = 0
+    for j, sub in enumerate(tar_list):
+        chosen = [int(np.random.choice(len(c))) for c in cross_lists]
+        assert chosen == out['chosen'][j]
+        splits = list(StratifiedKFold(n_splits=4, shuffle=True).split(np.zeros((len(lab), 1)), lab))
+        tar = (pts[0][0][:, :, sub], pts[0][1], pts[0][2])
+        cross = [(pts[p + 1][0][:, :, cross_lists[p][chosen[p]]], pts[p + 1][1], pts[p + 1][2])
+                 for p in range(2)]
+        yp = []
+        for tr, te in splits:
+            ref, _ = port.run_fold(tar, cross, tr, te, method='cca', n_comp=0.9, decoder='svc_rbf',
+                                   class_weight='balanced')     # sklearn's SVC.fit draws its seed here
+            yp.append(ref)
+        yp = np.concatenate(yp)
+        assert np.array_equal(np.concatenate([lab[te] for _, te in splits]), np.array(out['y_true'][j]))
+        same += int((yp == np.array(out['y_pred'][j])).sum())
+        tot += len(yp)
+    assert same / tot >= 0.97, (same, tot)
