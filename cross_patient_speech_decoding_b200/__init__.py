@@ -15,7 +15,11 @@ def cv_align_decode(target, cross, folds, method='mcca', **kw):
     (alignment/alignment_utils.py:127-157).  Returns a dict with ``y_pred`` (one array per
     fold), ``k2`` and the bytes moved host<->device.  ``method``: 'mcca'
     (crossPtDecoder_mcca), 'jointpca' (crossPtDecoder_jointDimRed + JointPCA), 'cca'
-    (crossPtDecoder_sepAlign + AlignCCA) or 'none' (crossPtDecoder_sepDimRed); the decoder is PCA(decoder_var) -> one-vs-rest linear SVM.
+    (crossPtDecoder_sepAlign + AlignCCA) or 'none' (crossPtDecoder_sepDimRed).  The decoder is
+    PCA(decoder_var) followed by ``decoder``: 'linear' (default; one-vs-rest squared-hinge linear
+    SVM, the north star's dual-CD decoder), 'svc_rbf' or 'svc_linear' (libsvm-style C-SVC with
+    one-vs-one votes -- with ``class_weight='balanced'`` the first is the reference scripts' own
+    ``SVC(kernel='rbf', class_weight='balanced')``, scripts/aligned_decode_svm_ncv.py:313-317).
     """
     from .engine import CVEngine
     eng = CVEngine(target, cross, method=method, **kw)

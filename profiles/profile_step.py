@@ -16,13 +16,16 @@ ap.add_argument('--no-tc', action='store_true')
 ap.add_argument('--stages', action='store_true')
 ap.add_argument('--dcd', type=int, default=0)
 ap.add_argument('--decoder', default='linear')
+ap.add_argument('--topk-iters', type=int, default=8)
+ap.add_argument('--tf32-iters', type=int, default=5)
 ap.add_argument('--class-weight', default=None)
 a = ap.parse_args()
 from cross_patient_speech_decoding_b200.engine import CVEngine  # noqa: E402
 pts = bench.make_data()
 eng = CVEngine(pts[0], pts[1:], method='mcca', n_comp=30, regs=0.5, pca_var=0.8,
                use_tensor_cores=not a.no_tc, max_batch=a.folds, dcd_epochs=a.dcd,
-               decoder=a.decoder, class_weight=a.class_weight)
+               decoder=a.decoder, class_weight=a.class_weight, topk_iters=a.topk_iters,
+               topk_tf32_iters=a.tf32_iters)
 def mk(seed):
     out = []
     while len(out) < a.folds:

@@ -1,5 +1,7 @@
-import sys, numpy as np, torch
-sys.path.insert(0, '/root/repo')
+"""Which top-k eigen-problems converge in how many rounds, which need the fp64 Cholesky-QR Gram,
+which fall back to the full solver (and why): engine.stats['topk_log'] per method / latent size."""
+import os, sys, numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 from cross_patient_speech_decoding_b200.engine import CVEngine
 from cross_patient_speech_decoding_b200.folds import cv_splits
