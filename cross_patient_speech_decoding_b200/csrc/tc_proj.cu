@@ -187,7 +187,9 @@ k_proj_tc(const CUtensorMap* __restrict__ xmaps, const CUtensorMap* __restrict__
     uint32_t rj[PT_N];
 #pragma unroll
     for (int i = 0; i < PT_N; ++i) {
-      const int e = lane + 32 * i;
+      // the block has 32 Q elements = Q per lane; slots i >= Q repeat an earlier element of the
+      // same lane (a benign duplicate store) so that the copy-out loop needs no validity test
+      const int e = lane + 32 * (i % Q);
       const int r = e / Q, j = e - r * Q;
       rj[i] = (uint32_t)((quad * 32 + r) << 8) | (uint32_t)j;
     }
@@ -234,9 +236,9 @@ k_proj_tc(const CUtensorMap* __restrict__ xmaps, const CUtensorMap* __restrict__
 #pragma unroll
         for (int i = 0; i < PT_N; ++i) {
           const int r = (int)(rj[i] >> 8), j = (int)(rj[i] & 255u);
-          const int off = (i < Q) ? row_off[r] : -1;
+          const int off = row_off[r];
           offs[i] = (off >= 0) ? off + j : -1;
-          vals[i] = (i < Q) ? stg[r * PT_LDS + j] : 0.f;
+          vals[i] = stg[r * PT_LDS + j];
         }
 #pragma unroll
         for (int i = 0; i < PT_N; ++i)

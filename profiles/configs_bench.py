@@ -25,7 +25,8 @@ from cross_patient_speech_decoding_b200.folds import cv_splits  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument('--configs', default='1,2s,3,4,5')
 ap.add_argument('--iters', type=int, default=5, help='CV iterations per measurement')
-ap.add_argument('--cca-batch', type=int, default=40)
+ap.add_argument('--cca-batch', type=int, default=148)
+ap.add_argument('--dcd', type=int, default=0, help='dual-CD warm-start epochs of the linear SVM')
 ap.add_argument('--dims', default='10,20,30,40,50,60,70,80,90,100')
 args = ap.parse_args()
 todo = set(args.configs.split(','))
@@ -76,7 +77,7 @@ if '3' in todo:
     for d in [int(x) for x in args.dims.split(',')]:
         for method in ('jointpca', 'cca', 'mcca'):
             folds = folds_for(pts[0][1], 20, args.iters, 200)
-            kw = dict(method=method, n_comp=d, use_tensor_cores=True, max_batch=148)
+            kw = dict(method=method, n_comp=d, use_tensor_cores=True, max_batch=148, dcd_epochs=args.dcd)
             if method == 'mcca':
                 kw.update(regs=0.5, pca_var=0.8)
             if method == 'jointpca':
