@@ -311,6 +311,19 @@ int cpsd_svc_predict_ovo(const float* St, int lds, long long strideS, const floa
                          const double* coef, int ldc, const double* rho, int* yhat, double* dec,
                          int k_max, int nfold, cudaStream_t stream);
 
+/* fused per-trial predict of a fitted cross-patient decoder (crossPtDecoder.predict,
+ * decoders/cross_pt_decoders.py:70-71,444: aligner.transform(X, idx=0) -> DimRedReshape/PCA
+ * transform -> one-vs-rest linear decision), one CTA per trial.  X: (n, T, C) fp64 device;
+ * mu: (C) or NULL; A: (C x Q); pmean: (T*Q); P: (T*Q x k2) = components_^T; W: (ncls x (k2+1)),
+ * intercept last (ncls = 1: binary, classes holds 2 labels); dec optional (n x ncls).  Each
+ * trial is split into nsplit time slices (one CTA each; the last to finish reduces in slice
+ * order and decides); ws_part: n * nsplit * roundup(k2, 32) doubles, ws_count: n ints, zero
+ * before the first call. */
+int cpsd_predict_fused(const double* X, int n, int T, int C, const float* mu, const float* A, int Q,
+                       const float* pmean, const float* P, int k2, const double* W,
+                       const int* classes, int ncls, int* yhat, double* dec, int nsplit,
+                       double* ws_part, int* ws_count, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

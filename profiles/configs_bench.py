@@ -140,6 +140,18 @@ if '5' in todo:
             yp = m.predict(Xb)
             ts.append(1e3 * (time.perf_counter() - t0))
         ts = np.sort(ts)
+        from cross_patient_speech_decoding_b200.decoders.fused_predict import FusedPredictor
+        fp = FusedPredictor(m)
+        assert np.mean(fp.predict(Xb) == yp) >= 0.97
+        tf = []
+        for _ in range(300 if nb == 1 else 80):
+            t0 = time.perf_counter()
+            fp.predict(Xb)
+            tf.append(1e3 * (time.perf_counter() - t0))
+        print(json.dumps(dict(config='5: fitted config-2 model, FusedPredictor.predict latency, host float64 in -> labels out',
+                              batch=nb, p50_ms=round(float(np.percentile(tf, 50)), 3),
+                              p99_ms=round(float(np.percentile(tf, 99)), 3),
+                              trials_per_s=round(nb / (np.median(tf) * 1e-3), 1))), flush=True)
         print(json.dumps(dict(config='5: fitted config-2 model, predict() latency, host float64 in -> labels out',
                               batch=nb, p50_ms=round(float(np.percentile(ts, 50)), 3),
                               p99_ms=round(float(np.percentile(ts, 99)), 3),

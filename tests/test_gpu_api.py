@@ -250,3 +250,39 @@ def test_pt_corr_matches_scipy(pkg):
     assert np.allclose(rs[1], 1.0) and np.abs(rs[0] - r).max() == 0
     with pytest.raises(ValueError):
         pt_corr(a, b[:, :10])
+
+
+def test_fused_predictor_matches_class_predict(pkg):
+    """decoders.fused_predict.FusedPredictor (one kernel per call) against the three-stage
+    crossPtDecoder.predict of the same fitted model, for every decoder class."""
+    from sklearn.pipeline import make_pipeline
+    from cross_patient_speech_decoding_b200.alignment.AlignCCA import AlignCCA
+    from cross_patient_speech_decoding_b200.alignment.AlignMCCA import AlignMCCA
+    from cross_patient_speech_decoding_b200.alignment.JointPCA import JointPCA
+    from cross_patient_speech_decoding_b200.decoders.cross_pt_decoders import (
+        crossPtDecoder_jointDimRed, crossPtDecoder_mcca, crossPtDecoder_sepAlign,
+        crossPtDecoder_sepDimRed)
+    from cross_patient_speech_decoding_b200.decoders.fused_predict import FusedPredictor
+    from cross_patient_speech_decoding_b200.decomposition.DimRedReshape import DimRedReshape
+    from cross_patient_speech_decoding_b200.decomposition.PCA import PCA
+    from cross_patient_speech_decoding_b200.svm import LinearSVC
+    pts = _patients(3, n_trials=80)
+    Xt, yt, yat = pts[0]
+    tr, te = np.arange(0, 60), np.arange(60, 80)
+    for cls, kw, fitkw in [
+            (crossPtDecoder_mcca, dict(aligner=AlignMCCA, n_comp=8, regs=0.5, pca_var=0.8), True),
+            (crossPtDecoder_sepAlign, dict(aligner=AlignCCA, n_comp=0.9), True),
+            (crossPtDecoder_sepDimRed, dict(n_comp=0.9), False),
+            (crossPtDecoder_jointDimRed, dict(joint_dr_method=JointPCA, n_comp=10), True)]:
+        m = cls(pts[1:], make_pipeline(DimRedReshape(PCA, n_components=0.8), LinearSVC()), **kw)
+        m.fit(Xt[tr], yt[tr], y_align=yat[tr]) if fitkw else m.fit(Xt[tr], yt[tr])
+        fp = FusedPredictor(m)
+        ref = m.predict(Xt[te])
+        got, dec = fp.predict(Xt[te], return_decision=True)
+        assert got.dtype == ref.dtype and np.mean(got == ref) >= 0.95, (cls.__name__, got, ref)
+        Xp = m.preprocess_test(Xt[te])
+        dref = m.decoder.decision_function(Xp)
+        assert np.abs(dec - dref).max() <= 2e-3 * max(1.0, np.abs(dref).max()), cls.__name__
+        assert np.array_equal(fp.predict(Xt[te][:1]), got[:1])          # batch of one
+    with pytest.raises(ValueError):
+        fp.predict(Xt[te][:, :5])
