@@ -103,7 +103,7 @@ _SIGS = {
     'cpsd_sum_mats_f64': [_P, _P, c_ll, _P, _P, ctypes.c_double, _P, c_ll, c_int, c_int, _P],
     'cpsd_gather_channels': [_P, c_int, _P, c_int, _P, c_int, c_ll, _P],
     'cpsd_predict_fused': [_P, c_int, c_int, c_int, _P, _P, c_int, _P, _P, c_int, _P, _P, c_int, _P, _P,
-                           c_int, _P, _P, _P],
+                           c_int, _P, _P, _P, c_int, _P],
     'cpsd_pearson_rows': [_P, _P, c_int, c_ll, _P, _P],
     'cpsd_region_mean_f64': [_P, c_int, c_int, c_int, _P, _P, c_int, _P, _P],
     'cpsd_cast_f64_f32': [_P, _P, c_ll, _P],

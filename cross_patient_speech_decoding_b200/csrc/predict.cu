@@ -24,7 +24,7 @@ k_predict_fused(const double* __restrict__ X, int T, int C, const float* __restr
                 const float* __restrict__ P, int k2, const double* __restrict__ W,
                 const int* __restrict__ classes, int ncls, int* __restrict__ yhat,
                 double* __restrict__ dec, int rows_per, double* __restrict__ ws_part,
-                int* __restrict__ ws_count) {
+                int* __restrict__ ws_count, float* __restrict__ scores_out, int ld_scores) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_last;
   const int trial = blockIdx.x, slice = blockIdx.y, nsplit = gridDim.y;
@@ -80,8 +80,13 @@ k_predict_fused(const double* __restrict__ X, int T, int C, const float* __restr
     double a = 0.0;
     for (int u = 0; u < nsplit; ++u) a += gall[(long long)u * k2p + j];
     s[j] = a;
+    if (scores_out) scores_out[(long long)j * ld_scores + trial] = (float)a;   // feature-major
   }
   __syncthreads();
+  if (W == nullptr) {                                       // scores only (kernel-SVM decoders)
+    if (threadIdx.x == 0) ws_count[trial] = 0;
+    return;
+  }
   double* dv = s + k2p;                                     // ncls decisions
   for (int c = wid; c < ncls; c += nw) {
     const double* w = W + (long long)c * (k2 + 1);
@@ -112,11 +117,16 @@ k_predict_fused(const double* __restrict__ X, int T, int C, const float* __restr
 // entries); yhat: n labels; dec (optional): (n x ncls) decision values.  nsplit time slices per
 // trial (1..T; more slices = lower latency for few trials); ws_part: n * nsplit * roundup(k2, 32)
 // doubles; ws_count: n ints, zero before the first call (the kernel leaves them zero).
+// scores_out (optional): the PCA scores, feature-major (k2 x ld_scores) fp32 -- with W = NULL the
+// kernel stops there (input of cpsd_svc_predict_ovo for the kernel-SVM decoders).
 extern "C" int cpsd_predict_fused(const double* X, int n, int T, int C, const float* mu, const float* A,
                                   int Q, const float* pmean, const float* P, int k2, const double* W,
                                   const int* classes, int ncls, int* yhat, double* dec, int nsplit,
-                                  double* ws_part, int* ws_count, cudaStream_t stream) {
+                                  double* ws_part, int* ws_count, float* scores_out, int ld_scores,
+                                  cudaStream_t stream) {
   CPSD_CHECK_ARG(n >= 0 && T > 0 && C > 0 && Q > 0 && k2 > 0 && ncls > 0, "predict_fused: bad dims");
+  CPSD_CHECK_ARG(W != nullptr || scores_out != nullptr, "predict_fused: neither W nor scores_out");
+  CPSD_CHECK_ARG(scores_out == nullptr || ld_scores >= n, "predict_fused: ld_scores < n");
   CPSD_CHECK_ARG(nsplit >= 1 && nsplit <= T && nsplit <= 65535 && ws_part && ws_count,
                  "predict_fused: bad nsplit / workspace");
   if (n == 0) return CPSD_OK;
@@ -128,7 +138,8 @@ extern "C" int cpsd_predict_fused(const double* X, int n, int T, int C, const fl
   CPSD_CHECK_ARG(smem <= 227 * 1024, "predict_fused: slice (rows x C) + latent (rows x Q) exceed shared memory");
   CPSD_CUDA(cudaFuncSetAttribute(k_predict_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_predict_fused<<<dim3(n, nsplit), PF_NT, smem, stream>>>(X, T, C, mu, A, Q, pmean, P, k2, W, classes, ncls,
-                                                            yhat, dec, rows_per, ws_part, ws_count);
+                                                            yhat, dec, rows_per, ws_part, ws_count,
+                                                            scores_out, ld_scores);
   CPSD_LAUNCH_CHECK();
   return CPSD_OK;
 }

@@ -4,7 +4,9 @@ path): ``FusedPredictor(model)`` captures the three fitted stages that
 transform ``(X - mu) A``, the ``DimRedReshape`` PCA transform and the one-vs-rest linear
 decision -- as device tensors, and ``predict`` runs them as one kernel
 (``cpsd_predict_fused``): one upload of the trials, one launch, one read-back of the labels.
-The decoder must be ``make_pipeline(DimRedReshape(PCA, ...), LinearSVC())`` from this package."""
+The decoder must be ``make_pipeline(DimRedReshape(PCA, ...), LinearSVC())`` from this package,
+or the same pipeline ending in this package's ``SVC`` (then the kernel stops at the PCA scores
+and ``cpsd_svc_predict_ovo`` casts the one-vs-one votes: two launches)."""
 import numpy as np
 import torch
 
@@ -31,8 +33,9 @@ class FusedPredictor:
     def __init__(self, model, device=None):
         steps = model.decoder.steps
         pca, svm = steps[0][1].transformer, steps[-1][1]
-        if not hasattr(svm, '_W') or len(steps) != 2:
-            raise TypeError('FusedPredictor needs make_pipeline(DimRedReshape(PCA), LinearSVC())')
+        self.svc = getattr(svm, '_model', None)               # svm.SVC: libsvm-style C-SVC, one-vs-one
+        if (not hasattr(svm, '_W') and self.svc is None) or len(steps) != 2:
+            raise TypeError('FusedPredictor needs make_pipeline(DimRedReshape(PCA), LinearSVC() or SVC())')
         mu, A = _target_map(model)
         self.ctx = ctx = Context.get(device)
         self.C, self.Q = (int(v) for v in A.shape)
@@ -46,9 +49,14 @@ class FusedPredictor:
         self.A = ctx.upload(A, np.float32)
         self.pmean = ctx.upload(np.asarray(pca.mean_), np.float32)
         self.P = ctx.upload(np.ascontiguousarray(comps.T), np.float32)
-        self.W = ctx.upload(np.asarray(svm._W), np.float64)
+        if self.svc is None:
+            self.W = ctx.upload(np.asarray(svm._W), np.float64)
+            self.ncls = int(svm._W.shape[0])
+        else:
+            if self.svc['k'] != self.k2:
+                raise ValueError('SVC was fitted on a different number of PCA components')
+            self.W, self.ncls = None, len(self.classes_)
         self.cls = ctx.upload(self.classes_.astype(np.int32), np.int32)
-        self.ncls = int(svm._W.shape[0])
         self._cap = 0
 
     def _buffers(self, n):
@@ -62,6 +70,7 @@ class FusedPredictor:
             k2p = (self.k2 + 31) // 32 * 32
             self._wsp = self.ctx.empty((self._cap * min(self.T, 16) * k2p,), torch.float64)
             self._wsc = self.ctx.zeros((self._cap,), torch.int32)
+            self._sc = self.ctx.empty((self.k2, self._cap)) if self.svc is not None else None
 
     def predict(self, X, return_decision=False):
         X = np.asarray(X, dtype=np.float64)
@@ -75,7 +84,17 @@ class FusedPredictor:
         self._dx[:n].copy_(self._hx[:n], non_blocking=True)
         self.ctx.call('cpsd_predict_fused', ptr(self._dx), n, self.T, self.C, ptr(self.mu), ptr(self.A),
                       self.Q, ptr(self.pmean), ptr(self.P), self.k2, ptr(self.W), ptr(self.cls),
-                      self.ncls, ptr(self._yh), ptr(self._dec), nsplit, ptr(self._wsp), ptr(self._wsc))
+                      self.ncls, ptr(self._yh), ptr(self._dec), nsplit, ptr(self._wsp), ptr(self._wsc),
+                      ptr(self._sc), self._cap)
+        if self.svc is not None:
+            if return_decision:
+                raise ValueError('return_decision is only available with the linear decoder')
+            m = self.svc
+            self.ctx.call('cpsd_svc_predict_ovo', ptr(m['St']), m['lds'], 0, ptr(self._sc), self._cap, 0,
+                          ptr(None), self.k2, ptr(None), m['n'], m['n'], ptr(None), n, ptr(m['y']), 0,
+                          ptr(m['classes_dev']), self.ncls, m['kernel'], ptr(m['gamma_dev']),
+                          ptr(m['coef_dev']), m['lds'], ptr(m['rho_dev']), ptr(self._yh), ptr(None),
+                          self.k2, 1)
         self._hy[:n].copy_(self._yh[:n], non_blocking=True)
         torch.cuda.current_stream(self.ctx.device).synchronize()
         out = self._hy[:n].numpy().astype(self.classes_.dtype)

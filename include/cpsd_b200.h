@@ -318,11 +318,13 @@ int cpsd_svc_predict_ovo(const float* St, int lds, long long strideS, const floa
  * intercept last (ncls = 1: binary, classes holds 2 labels); dec optional (n x ncls).  Each
  * trial is split into nsplit time slices (one CTA each; the last to finish reduces in slice
  * order and decides); ws_part: n * nsplit * roundup(k2, 32) doubles, ws_count: n ints, zero
- * before the first call. */
+ * before the first call.  scores_out (optional): PCA scores, feature-major (k2 x ld_scores) fp32;
+ * with W = NULL the kernel stops there (input of cpsd_svc_predict_ovo for the C-SVC decoders). */
 int cpsd_predict_fused(const double* X, int n, int T, int C, const float* mu, const float* A, int Q,
                        const float* pmean, const float* P, int k2, const double* W,
                        const int* classes, int ncls, int* yhat, double* dec, int nsplit,
-                       double* ws_part, int* ws_count, cudaStream_t stream);
+                       double* ws_part, int* ws_count, float* scores_out, int ld_scores,
+                       cudaStream_t stream);
 
 #ifdef __cplusplus
 }

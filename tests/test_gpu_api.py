@@ -286,3 +286,12 @@ def test_fused_predictor_matches_class_predict(pkg):
         assert np.array_equal(fp.predict(Xt[te][:1]), got[:1])          # batch of one
     with pytest.raises(ValueError):
         fp.predict(Xt[te][:, :5])
+    # the scripts' own decoder behind the fused front end (scores kernel + C-SVC vote kernel)
+    from cross_patient_speech_decoding_b200.svm import SVC
+    m = crossPtDecoder_mcca(pts[1:], make_pipeline(DimRedReshape(PCA, n_components=0.8),
+                                                   SVC(kernel='rbf', class_weight='balanced')),
+                            AlignMCCA, n_comp=8, regs=0.5, pca_var=0.8)
+    m.fit(Xt[tr], yt[tr], y_align=yat[tr])
+    fp = FusedPredictor(m)
+    assert np.mean(fp.predict(Xt[te]) == m.predict(Xt[te])) >= 0.95
+    assert np.array_equal(fp.predict(Xt[te][3:4]), fp.predict(Xt[te])[3:4])
