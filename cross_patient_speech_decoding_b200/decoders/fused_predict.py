@@ -80,7 +80,7 @@ class FusedPredictor:
         self._buffers(n)
         self._hx[:n].copy_(torch.from_numpy(np.ascontiguousarray(X)))
         # few trials: split every trial over several CTAs (time slices) to fill the SMs
-        nsplit = max(1, min(self.T, 16, 296 // n))
+        nsplit = max(1, min(self.T, 16, 592 // n))
         self._dx[:n].copy_(self._hx[:n], non_blocking=True)
         self.ctx.call('cpsd_predict_fused', ptr(self._dx), n, self.T, self.C, ptr(self.mu), ptr(self.A),
                       self.Q, ptr(self.pmean), ptr(self.P), self.k2, ptr(self.W), ptr(self.cls),
