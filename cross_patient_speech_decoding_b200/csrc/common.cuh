@@ -3,6 +3,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+// the public prototypes: every extern "C" definition in csrc/ is compiled against them, so a
+// drift between the header and an implementation is a compile error
+#include "../../include/cpsd_b200.h"
 
 #define CPSD_OK 0
 #define CPSD_ERR_INVALID 1

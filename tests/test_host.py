@@ -120,3 +120,40 @@ def test_product_path_fails_loudly_without_gpu():
     from cross_patient_speech_decoding_b200.device import Context
     with pytest.raises(_lib.CpsdError):
         Context(None)
+
+
+def test_ctypes_signatures_match_header():
+    """Every prototype of include/cpsd_b200.h against the ctypes argtypes the Python layer binds
+    (argument count and class: pointer / int / long long / float / double)."""
+    import ctypes
+    import re
+    from cross_patient_speech_decoding_b200 import _lib
+    hdr = open(os.path.join(ROOT, 'include', 'cpsd_b200.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', ' ', hdr, flags=re.S)
+    protos = re.findall(r'\b(?:int|long long|const char\s*\*|void)\s+(cpsd_\w+)\s*\(([^;{]*?)\)\s*;', hdr, flags=re.S)
+    assert len(protos) >= 60
+
+    def kind(param):
+        p = ' '.join(param.split())
+        if '*' in p or 'cudaStream_t' in p:
+            return ctypes.c_void_p
+        if p.startswith('long long') or p.startswith('const long long'):
+            return ctypes.c_longlong
+        if p.startswith('double'):
+            return ctypes.c_double
+        if p.startswith('float'):
+            return ctypes.c_float
+        assert p.startswith('int') or p.startswith('const int'), p
+        return ctypes.c_int
+
+    checked = 0
+    for name, params in protos:
+        if name not in _lib._SIGS:
+            continue
+        plist = [] if params.strip() in ('', 'void') else [kind(x) for x in params.split(',')]
+        want = list(_lib._SIGS[name])
+        assert len(plist) == len(want), (name, len(plist), len(want))
+        for i, (a, b) in enumerate(zip(plist, want)):
+            assert a is b, (name, i, a, b)
+        checked += 1
+    assert checked >= 55
