@@ -295,3 +295,31 @@ def test_fused_predictor_matches_class_predict(pkg):
     fp = FusedPredictor(m)
     assert np.mean(fp.predict(Xt[te]) == m.predict(Xt[te])) >= 0.95
     assert np.array_equal(fp.predict(Xt[te][3:4]), fp.predict(Xt[te])[3:4])
+
+
+def test_realtime_hooks(pkg):
+    """realtime_sim.reduce_to_latent_space / align_to_target against sklearn PCA and the CPU port
+    of CCA_align (what the reference's hooks call, realtime_datamodule.py:813-894)."""
+    import torch
+    from sklearn.decomposition import PCA as SkPCA
+    from cross_patient_speech_decoding_b200.alignment.AlignCCA import AlignCCA
+    from cross_patient_speech_decoding_b200.realtime_sim import align_to_target, reduce_to_latent_space
+    pts = _patients(2, n_trials=60)
+    Xa, Xb = torch.tensor(pts[0][0]), torch.tensor(pts[1][0])
+    ra, pca_a = reduce_to_latent_space(Xa, n_components=6)
+    ref = SkPCA(n_components=6).fit(pts[0][0].reshape(-1, pts[0][0].shape[-1]))
+    assert tuple(ra.shape) == (60, Xa.shape[1], 6) and ra.dtype == torch.float32
+    want = ref.transform(pts[0][0].reshape(-1, pts[0][0].shape[-1])).reshape(60, -1, 6)
+    assert np.abs(ra.numpy() - want).max() <= 2e-3 * np.abs(want).max()
+    rb2, _ = reduce_to_latent_space(Xa[:5], pca=pca_a)                 # transform-only branch
+    assert np.abs(rb2.numpy() - ra.numpy()[:5]).max() <= 1e-4 * np.abs(want).max()
+    # variance threshold that keeps <= 5 components -> the 30-component re-fit
+    r30, p30 = reduce_to_latent_space(Xa, n_components=0.2)
+    assert p30.n_components_ == 30 and r30.shape[-1] == 30
+    rb, _ = reduce_to_latent_space(Xb, n_components=6)
+    ya, yb = torch.tensor(pts[0][2]), torch.tensor(pts[1][2])
+    out = align_to_target(AlignCCA, ra, rb, ya, yb)
+    chk = AlignCCA()
+    chk.fit(ra.numpy(), rb.numpy(), pts[0][2], pts[1][2])
+    assert tuple(out.shape) == (60, Xb.shape[1], 6)
+    assert np.abs(out.numpy() - chk.transform(rb.numpy())).max() <= 1e-5 * np.abs(out.numpy()).max() + 1e-6
