@@ -323,3 +323,30 @@ def test_realtime_hooks(pkg):
     chk.fit(ra.numpy(), rb.numpy(), pts[0][2], pts[1][2])
     assert tuple(out.shape) == (60, Xb.shape[1], 6)
     assert np.abs(out.numpy() - chk.transform(rb.numpy())).max() <= 1e-5 * np.abs(out.numpy()).max() + 1e-6
+
+
+def test_nested_search_with_sklearn_searchcv(pkg):
+    """The nested-CV pattern of scripts/aligned_decode_svm_ncv.py:388-405 (search with
+    refit=False over the decoder's hyper-parameters, extra fit kwarg y_align, then set_params +
+    fit) with sklearn's own GridSearchCV driving the GPU estimators (BayesSearchCV needs the
+    absent scikit-optimize; the script lists GridSearchCV / RandomizedSearchCV as the
+    alternatives)."""
+    from sklearn.model_selection import GridSearchCV, StratifiedKFold
+    from sklearn.pipeline import make_pipeline
+    from cross_patient_speech_decoding_b200.alignment.AlignCCA import AlignCCA
+    from cross_patient_speech_decoding_b200.decoders.cross_pt_decoders import crossPtDecoder_sepAlign
+    from cross_patient_speech_decoding_b200.decomposition.DimRedReshape import DimRedReshape
+    from cross_patient_speech_decoding_b200.decomposition.PCA import PCA
+    from cross_patient_speech_decoding_b200.svm import SVC
+    pts = _patients(2, n_trials=60)
+    Xt, yt, yat = pts[0]
+    clf = make_pipeline(DimRedReshape(PCA), SVC(kernel='rbf', class_weight='balanced'))
+    model = crossPtDecoder_sepAlign(pts[1:], clf, AlignCCA)
+    grid = {'n_comp': [0.8, 0.9], 'decoder__dimredreshape__n_components': [0.6, 0.8]}
+    search = GridSearchCV(model, grid, cv=StratifiedKFold(2, shuffle=True, random_state=0), refit=False)
+    search.fit(Xt, yt, y_align=yat)
+    assert set(search.best_params_) == set(grid)
+    assert 0.0 <= search.best_score_ <= 1.0 and len(search.cv_results_['params']) == 4
+    model.set_params(**search.best_params_)
+    model.fit(Xt, yt, y_align=yat)
+    assert model.predict(Xt[:5]).shape == (5,)
