@@ -31,7 +31,8 @@ def cv_align_decode(target, cross, folds, method='mcca', **kw):
 def cv_align_decode_stream(jobs, depth=8, method='mcca', device=None, **kw):
     """Pipelined form of ``cv_align_decode`` for many independent jobs (e.g. the 50 CV
     iterations x patient sets of scripts/aligned_decode_svm_ncv.py:332-456): ``jobs`` is an
-    iterable of ``(target, cross, folds)``; results are yielded in order.  Up to ``depth`` jobs
+    iterable of ``(target, cross, folds)`` or ``(target, cross, folds, overrides)`` (a dict of
+    engine keywords for that job only); results are yielded in order.  Up to ``depth`` jobs
     are in flight, each on its own CUDA stream with its own upload, so the host->device copy
     and the latency-bound small solvers of one job overlap the kernels of the others."""
     import collections
@@ -51,7 +52,11 @@ def cv_align_decode_stream(jobs, depth=8, method='mcca', device=None, **kw):
         lane = 8 + (nsub % depth) * 4           # leave room for the engines' extra lanes
         nsub += 1
         with torch.cuda.stream(_lane_stream(dev, lane)):
-            eng = CVEngine(job[0], job[1], method=method, device=dev, lane=lane, **kw)
+            jkw = dict(kw)
+            if len(job) > 3 and job[3]:
+                jkw.update(job[3])                 # per-job engine keywords
+            eng = CVEngine(job[0], job[1], method=jkw.pop('method', method), device=dev, lane=lane,
+                           **jkw)
             gen = eng.run_gen(job[2])
         return [eng, gen, None, False, None]     # engine, generator, result, done, wait event
 
@@ -92,6 +97,34 @@ def cv_align_decode_stream(jobs, depth=8, method='mcca', device=None, **kw):
         if not progressed:
             time.sleep(0)
             cv_align_decode_stream.idle_s += time.perf_counter() - t_iter
+
+
+def search_align_decode(target, cross, candidates, inner_folds, method='mcca', depth=4, device=None,
+                        **kw):
+    """Hyper-parameter search over the align -> reduce -> decode path, batched: every candidate
+    (a dict of engine keywords, e.g. ``{'n_comp': 0.9, 'decoder_var': 0.6}``) is scored on all
+    ``inner_folds`` as one job of ``cv_align_decode_stream``; the patients are uploaded once and
+    shared by all candidates.  The inner loop of the reference's nested CV
+    (scripts/aligned_decode_svm_ncv.py:388-405: a search with ``refit=False`` whose score is the
+    mean per-fold accuracy) without one fit / predict call per (candidate, fold).
+    Returns ``scores`` (mean per-fold accuracy per candidate), ``best_index``, ``best_params``
+    and ``y_pred`` (per candidate, per fold)."""
+    import numpy as np
+
+    from .processing_utils import device_subsample as ds
+    tv = (ds.resident(target[0], device), target[1], target[2])
+    cvs = [(ds.resident(c[0], device), c[1], c[2]) for c in cross]
+    lab = np.asarray(target[1])
+    jobs = ((tv, cvs, inner_folds, dict(c)) for c in candidates)
+    scores, preds = [], []
+    for res in cv_align_decode_stream(jobs, depth=depth, method=method, device=device, **kw):
+        accs = [float(np.mean(yp == lab[te])) for yp, (_, te) in zip(res['y_pred'], inner_folds)]
+        scores.append(float(np.mean(accs)))
+        preds.append(res['y_pred'])
+    scores = np.asarray(scores)
+    best = int(np.argmax(scores)) if len(scores) else -1
+    return dict(scores=scores, best_index=best, best_params=dict(candidates[best]) if best >= 0 else None,
+                y_pred=preds)
 
 
 cv_align_decode_stream.idle_s = 0.0     # host time spent with every in-flight job waiting on the GPU

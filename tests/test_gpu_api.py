@@ -350,3 +350,31 @@ def test_nested_search_with_sklearn_searchcv(pkg):
     model.set_params(**search.best_params_)
     model.fit(Xt, yt, y_align=yat)
     assert model.predict(Xt[:5]).shape == (5,)
+
+
+def test_batched_search_matches_gridsearchcv(pkg):
+    """search_align_decode (all candidates x inner folds streamed through the engine, patients
+    uploaded once) against sklearn's GridSearchCV around the drop-in estimators on the same
+    inner folds: same mean accuracies per candidate, same winner."""
+    from sklearn.model_selection import GridSearchCV, StratifiedKFold
+    from sklearn.pipeline import make_pipeline
+    from cross_patient_speech_decoding_b200.alignment.AlignCCA import AlignCCA
+    from cross_patient_speech_decoding_b200.decoders.cross_pt_decoders import crossPtDecoder_sepAlign
+    from cross_patient_speech_decoding_b200.decomposition.DimRedReshape import DimRedReshape
+    from cross_patient_speech_decoding_b200.decomposition.PCA import PCA
+    from cross_patient_speech_decoding_b200.svm import LinearSVC
+    pts = _patients(3, n_trials=72)
+    Xt, yt, yat = pts[0]
+    cv = StratifiedKFold(3, shuffle=True, random_state=1)
+    folds = list(cv.split(np.zeros((len(yt), 1)), yt))
+    cands = [dict(n_comp=a, decoder_var=b) for a in (0.8, 0.9) for b in (0.6, 0.8)]
+    out = pkg.search_align_decode(pts[0], pts[1:], cands, folds, method='cca', depth=2)
+    model = crossPtDecoder_sepAlign(pts[1:], make_pipeline(DimRedReshape(PCA), LinearSVC()), AlignCCA)
+    grid = {'n_comp': [0.8, 0.9], 'decoder__dimredreshape__n_components': [0.6, 0.8]}
+    gs = GridSearchCV(model, grid, cv=folds, refit=False).fit(Xt, yt, y_align=yat)
+    ref = {(p['n_comp'], p['decoder__dimredreshape__n_components']): s
+           for p, s in zip(gs.cv_results_['params'], gs.cv_results_['mean_test_score'])}
+    got = {(c['n_comp'], c['decoder_var']): s for c, s in zip(cands, out['scores'])}
+    for k in ref:
+        assert abs(ref[k] - got[k]) <= 0.03, (k, ref[k], got[k])
+    assert out['best_params'] == cands[out['best_index']] and len(out['y_pred']) == 4
