@@ -128,10 +128,17 @@ def run(inputs):
     dec_kw = dict(decoder=inputs['decoder'],
                   class_weight='balanced' if inputs['decoder'] == 'svc_rbf' else None,
                   decoder_var=param_grid['decoder__dimredreshape__n_components'])
-    if pool_train:
-        if joint_dim_red:
-            kw = dict(method='jointpca', n_comp=40)          # JointPCA's default, untouched by set_params
-        elif cca_align:
+    def make_clf():
+        from sklearn.pipeline import make_pipeline
+        from ..decomposition.DimRedReshape import DimRedReshape
+        from ..decomposition.PCA import PCA
+        from ..svm import SVC, LinearSVC
+        dec = LinearSVC() if inputs['decoder'] == 'linear' else SVC(
+            kernel=inputs['decoder'][4:], class_weight=dec_kw['class_weight'])
+        return make_pipeline(DimRedReshape(PCA, n_components=dec_kw['decoder_var']), dec)
+
+    if pool_train and not joint_dim_red:
+        if cca_align:
             kw = dict(method='cca', n_comp=param_grid['n_comp'])
         elif mcca_align:
             kw = dict(method='mcca', n_comp=30, regs=0.5, pca_var=0.8)
@@ -141,17 +148,23 @@ def run(inputs):
                               tar_in_train=tar_in_train, use_tensor_cores=True, max_batch=148,
                               **kw, **dec_kw)
         y_pred_units = res['y_pred']
-    else:
-        # single-patient branch (:406-428): DimRedReshape(PCA(0.8)) -> decoder on the raw trials
-        from sklearn.pipeline import make_pipeline
-        from ..decomposition.DimRedReshape import DimRedReshape
-        from ..decomposition.PCA import PCA
-        from ..svm import SVC, LinearSVC
+    elif pool_train:
+        # joint PCA: the script's set_params hands n_comp = 0.9 (a variance fraction) to
+        # JointPCA(n_components=...) (:186-190, :372-375, :416); the batched engine takes a fixed
+        # component count only, so this branch goes fold by fold through the drop-in classes
+        from ..alignment.JointPCA import JointPCA
+        from ..decoders.cross_pt_decoders import crossPtDecoder_jointDimRed
         y_pred_units = []
         for tr, te in units:
-            dec = LinearSVC() if inputs['decoder'] == 'linear' else SVC(
-                kernel=inputs['decoder'][4:], class_weight=dec_kw['class_weight'])
-            clf = make_pipeline(DimRedReshape(PCA, n_components=0.8), dec)
+            model = crossPtDecoder_jointDimRed(cross, make_clf(), JointPCA, n_comp=param_grid['n_comp'],
+                                               tar_in_train=tar_in_train)
+            model.fit(D_tar[tr], lab_tar[tr], y_align=lab_tar_full[tr])
+            y_pred_units.append(model.predict(D_tar[te]))
+    else:
+        # single-patient branch (:406-428): DimRedReshape(PCA(0.8)) -> decoder on the raw trials
+        y_pred_units = []
+        for tr, te in units:
+            clf = make_clf()
             clf.fit(D_tar[tr], lab_tar[tr])
             y_pred_units.append(clf.predict(D_tar[te]))
     y_true_iter, y_pred_iter, wrong_iter, accs = [], [], [], []

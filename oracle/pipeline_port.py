@@ -159,6 +159,14 @@ def run_fold(target, cross, train, test, method='mcca', n_comp=None, regs=0.5, p
         n_comp = 0.9 if n_comp is None else n_comp
         Xp, yp, pt, dim = pool_none(Xtr, yt[train], cross, n_comp)
         Zte = pt.transform(Xte.reshape(-1, Xte.shape[-1]))[:, :dim].reshape(len(test), -1)
+    elif method == 'jointpca':
+        # crossPtDecoder_jointDimRed (cross_pt_decoders.py:288-364) around JointPCA
+        n_comp = 40 if n_comp is None else n_comp
+        Xs = [Xtr] + [c[0] for c in cross]
+        W = joint_pca_fit(Xs, [yat[train]] + [c[2] for c in cross], n_comp)
+        Xp = np.vstack([joint_pca_transform(w, X).reshape(X.shape[0], -1) for w, X in zip(W, Xs)])
+        yp = np.hstack([yt[train]] + [c[1] for c in cross])
+        Zte = joint_pca_transform(W[0], Xte).reshape(len(test), -1)
     else:
         raise ValueError(method)
     pca = PCA(n_components=decoder_var).fit(Xp)

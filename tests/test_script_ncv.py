@@ -77,3 +77,24 @@ def test_script_matches_reference_script_golden(lib_built, tmp_path):
     assert np.abs(np.array(res['accs']) - g['accs']).mean() <= 0.005
     assert abs(np.mean(res['accs']) - g['accs'].mean()) <= 0.005
     assert np.abs(np.array([len(w) for w in res['wrong_trs']]) - g['n_wrong']).max() <= 3
+
+
+@pytest.mark.gpu
+def test_script_joint_branch_matches_port(lib_built, tmp_path):
+    """-j True: the script's set_params hands n_comp = 0.9 (a variance fraction) to JointPCA
+    (aligned_decode_svm_ncv.py:186-190, 372-375, 416); checked fold by fold against the CPU port."""
+    import make_golden_script as mg
+    from cross_patient_speech_decoding_b200.scripts import aligned_decode_svm_ncv as sc
+    from oracle import pipeline_port as port
+    d = mg.data_dict()
+    res = sc.aligned_decoding(['-pt', 'S1', '-pi', '1', '-po', 'True', '-j', 'True', '-c', 'False',
+                               '-f', str(tmp_path / 'out.pkl'), '--data_file', _write_data(tmp_path),
+                               '--seed', '3', '--n_iter', '1', '--n_folds', '3', '--decoder', 'linear'])
+    tar = (d['S1']['X1'], np.asarray(d['S1']['y1']), d['S1']['y_full_phon'])
+    cross = [(d[p]['X1'], np.asarray(d[p]['y1']), d[p]['y_full_phon']) for p in d['S1']['pre_pts']]
+    np.random.seed(3)
+    units = sc.make_units(tar[1], 1, 3, 1.0)
+    ref = np.concatenate([port.run_fold(tar, cross, tr, te, method='jointpca', n_comp=0.9)[0]
+                          for tr, te in units])
+    got = np.array(res['y_pred'][0])
+    assert got.shape == ref.shape and np.mean(got == ref) >= 0.9, float(np.mean(got == ref))
