@@ -988,6 +988,9 @@ class CVEngine:
                      ptr(yhat), ptr(None), B)
             return yhat
         sv = W
+        if self._k2_max > 1024:
+            raise NotImplementedError('C-SVC decoders support at most 1024 decoder-PCA components '
+                                      '(this batch keeps %d)' % self._k2_max)
         kid = 1 if self.decoder == 'svc_rbf' else 0
         npool_dev = ctypes_int_ptr(pk.iaddr(o_npool))
         ypool_dev = ctypes_int_ptr(pk.iaddr(o_ypool))
