@@ -164,3 +164,28 @@ def test_joint_pca_port_matches_reference_golden():
         assert np.abs(W[v] - Wref).max() <= 1e-8 * np.abs(Wref).max()
         Z = port.joint_pca_transform(W[v], p[0][:4])
         assert np.abs(Z - g['Z_full_%d' % v]).max() <= 1e-8 * np.abs(g['Z_full_%d' % v]).max()
+
+
+@pytest.mark.parametrize('kernel,balanced,ncls', [('rbf', True, 4), ('rbf', False, 2), ('linear', False, 3)])
+def test_svc_smo_restatement_matches_libsvm(kernel, balanced, ncls):
+    """oracle/svc_smo.py (the algorithm csrc/svc.cu follows) against sklearn.svm.SVC = libsvm,
+    the class the reference scripts instantiate (scripts/aligned_decode_svm_ncv.py:313-317)."""
+    from sklearn.svm import SVC
+    from oracle import svc_smo
+    rng = np.random.default_rng(5)
+    y = rng.integers(0, ncls, 150) + 1
+    cent = rng.standard_normal((ncls + 1, 6)) * 0.9
+    X = cent[y] + rng.standard_normal((150, 6))
+    Z = cent[rng.integers(1, ncls + 1, 60)] + rng.standard_normal((60, 6))
+    ref = SVC(kernel=kernel, class_weight='balanced' if balanced else None, tol=1e-6,
+              decision_function_shape='ovo').fit(X, y)
+    m = svc_smo.fit_ovo(X, y, kernel=kernel, balanced=balanced, tol=1e-6)
+    if kernel == 'rbf':
+        assert abs(m['gamma'] - ref._gamma) <= 1e-12 * ref._gamma
+    d_ref = ref.decision_function(Z)
+    d = svc_smo.decision_ovo(m, Z)
+    d = -d[:, 0] if ncls == 2 else d                  # sklearn flips the binary sign
+    assert np.abs(d - d_ref).max() <= 2e-4 * max(1.0, np.abs(d_ref).max())
+    assert np.array_equal(svc_smo.predict_ovo(m, Z), ref.predict(Z))
+    rho = np.array([p['rho'] for p in m['pairs']])
+    assert np.abs((-rho if ncls > 2 else rho) - ref.intercept_).max() < 1e-4
