@@ -189,3 +189,28 @@ def test_svc_smo_restatement_matches_libsvm(kernel, balanced, ncls):
     assert np.array_equal(svc_smo.predict_ovo(m, Z), ref.predict(Z))
     rho = np.array([p['rho'] for p in m['pairs']])
     assert np.abs((-rho if ncls > 2 else rho) - ref.intercept_).max() < 1e-4
+
+
+@pytest.mark.skipif(not reference_path.available(), reason='reference tree not present')
+def test_port_jointpca_and_svc_match_reference_classes_live():
+    """With /root/reference importable: crossPtDecoder_jointDimRed + JointPCA with a variance
+    fraction (what the script's set_params produces) and the scripts' own SVC decoder, against
+    the port's run_fold on the same fold."""
+    from sklearn.decomposition import PCA
+    from sklearn.pipeline import make_pipeline
+    from sklearn.svm import SVC
+    from cross_patient_speech_decoding_b200 import synthetic
+    ref = reference_path.load()
+    pts = [synthetic.make_patient(p, n_trials=60, n_time=20, n_chan=12, noise=0.8) for p in range(3)]
+    Xt, yt, yat = pts[0]
+    tr, te = np.arange(0, 45), np.arange(45, 60)
+    clf = make_pipeline(ref.DimRedReshape(PCA, n_components=0.8), SVC(kernel='rbf', class_weight='balanced'))
+    m = ref.decoders.crossPtDecoder_jointDimRed(pts[1:], clf, ref.JointPCA, n_comp=0.9)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        m.fit(Xt[tr], yt[tr], y_align=yat[tr])
+        want = m.predict(Xt[te])
+        got, k2 = pipeline_port.run_fold(pts[0], pts[1:], tr, te, method='jointpca', n_comp=0.9,
+                                         decoder='svc_rbf', class_weight='balanced')
+    assert k2 == clf.steps[0][1].transformer.n_components_
+    assert np.array_equal(got, want)
