@@ -134,6 +134,11 @@ _SIGS = {
     'cpsd_svc_predict_ovo': [_P, c_int, c_ll, _P, c_int, c_ll, _P, c_int, _P, c_int, c_int, _P, c_int,
                              _P, c_int, _P, c_int, c_int, _P, _P, c_int, _P, _P, _P, c_int, c_int, _P],
     'cpsd_cca_solve': [_P, c_int, c_int, _P],
+    'cpsd_cca_solve_f64_ws_elems': [c_int, c_int],
+    'cpsd_cca_solve_f64': [_P, c_int, c_int, _P, _P],
+    'cpsd_eig_sym_f64_ws_elems': [c_int, c_int],
+    'cpsd_eig_sym_f64': [_P, c_int, c_ll, _P, c_int, c_int, _P, c_int, _P, c_int, c_ll, c_int, _P,
+                         c_int, _P, _P],
     'cpsd_pca_basis': [_P, c_int, c_ll, _P, _P, c_int, c_int, _P, c_int, c_int, c_int, _P],
     'cpsd_split_tf32': [_P, _P, _P, c_ll, _P],
     'cpsd_tmap_encode_f32': [_P, _P, c_ll, c_int, c_ll, c_int],
@@ -147,7 +152,8 @@ _SIGS = {
 _RESTYPES = {'cpsd_last_error': ctypes.c_char_p, 'cpsd_launch_count': c_ll,
              'cpsd_bj_rlog_elems': c_ll, 'cpsd_eig_topk_ws_elems': c_ll,
              'cpsd_eig_topk_voff': c_ll, 'cpsd_topk_tc_ws_elems': c_ll,
-             'cpsd_gram_tn_split_ws_elems': c_ll,
+             'cpsd_gram_tn_split_ws_elems': c_ll, 'cpsd_cca_solve_f64_ws_elems': c_ll,
+             'cpsd_eig_sym_f64_ws_elems': c_ll,
              'cpsd_reset_launch_count': None}
 
 EXPORTED_SYMBOLS = sorted(_SIGS)

@@ -55,7 +55,7 @@ def _cca_from_latents(L_a, L_b):
     da, db = L_a.shape[1], L_b.shape[1]
     L = np.ascontiguousarray(np.hstack([L_a, L_b]))
     mu = ops.colmean(L)
-    S = ops.gram_tn(L, muA=mu)                       # centred scatter of [L_a | L_b]
+    S = ops.gram_tn(L, muA=mu, f64=True)             # centred scatter of [L_a | L_b], fp64
     out = ops.cca_solve(S[:da, :da], S[da:, da:], S[:da, da:])
     swp = ops.cca_solve(S[da:, da:], S[:da, :da], S[da:, :da])   # roles swapped: a -> b map
     return (out['Ma'].astype(np.float64), out['Mb'].astype(np.float64),

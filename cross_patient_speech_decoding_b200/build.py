@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libcpsd_b200.so')
-SOURCES = ['api.cu', 'jacobi.cu', 'gemm.cu', 'stream.cu', 'svm.cu', 'cca.cu', 'tc_gram.cu', 'subspace.cu', 'tc_proj.cu', 'svc.cu', 'predict.cu']
+SOURCES = ['api.cu', 'jacobi.cu', 'gemm.cu', 'stream.cu', 'svm.cu', 'cca.cu', 'tc_gram.cu', 'subspace.cu', 'tc_proj.cu', 'svc.cu', 'predict.cu', 'solve64.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 EXTRA = os.environ.get('CPSD_NVCC_FLAGS', '').split()
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',

@@ -369,7 +369,7 @@ extern "C" int cpsd_colsum(const cpsd_colsum_desc* descs_dev, int nprob, int p_m
 extern "C" int cpsd_proj_nn(const cpsd_proj_desc* descs_dev, int nprob, int nseg_max, int seg_len,
                             int q_max, cudaStream_t stream) {
   CPSD_CHECK_ARG(nprob >= 0 && nseg_max >= 0 && seg_len > 0, "proj_nn: bad dims");
-  CPSD_CHECK_ARG(q_max > 0 && q_max <= 128, "proj_nn: q must be in 1..128");
+  CPSD_CHECK_ARG(q_max > 0 && q_max <= 256, "proj_nn: q must be in 1..256");
   if (nprob == 0 || nseg_max == 0) return CPSD_OK;
   CPSD_CHECK_ARG(nprob <= 65535, "proj_nn: nprob > 65535");
   const int bps = (seg_len + PJ_ROWS - 1) / PJ_ROWS;
@@ -378,8 +378,10 @@ extern "C" int cpsd_proj_nn(const cpsd_proj_desc* descs_dev, int nprob, int nseg
     k_proj_nn<2><<<grid, 256, 0, stream>>>(descs_dev, bps);
   else if (q_max <= 64)
     k_proj_nn<4><<<grid, 256, 0, stream>>>(descs_dev, bps);
-  else
+  else if (q_max <= 128)
     k_proj_nn<8><<<grid, 256, 0, stream>>>(descs_dev, bps);
+  else
+    k_proj_nn<16><<<grid, 256, 0, stream>>>(descs_dev, bps);
   CPSD_LAUNCH_CHECK();
   return CPSD_OK;
 }

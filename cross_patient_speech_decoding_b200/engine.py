@@ -52,6 +52,14 @@ class View:
             # processing_utils.device_subsample): no upload
             assert X.dim() == 3, 'features must be (trials, time, channels)'
             self.N, self.T, self.C = (int(v) for v in X.shape)
+            # the producer (device_subsample.resident / gather_channels, or the caller's own
+            # kernels) ran on another stream than this engine's lane: wait for it
+            cur = torch.cuda.current_stream(X.device)
+            ev = getattr(X, '_cpsd_ready', None)
+            if ev is not None:
+                cur.wait_event(ev)
+            else:
+                cur.wait_stream(torch.cuda.default_stream(X.device))
             Xc = X.contiguous()
             if Xc.dtype == torch.float64:
                 self.X = ctx.empty((self.N * self.T, self.C))
@@ -254,10 +262,21 @@ class CVEngine:
         if nprob == 0:
             return evals, evecs
         if A.dtype == torch.float64:
-            assert n_pad <= 128
-            self.ctx.call('cpsd_eig_sym_small_f64', ptr(A), n_pad, n_pad * n_pad, _p(n_dev),
-                          n_fixed, nprob, ptr(evals), n_pad, ptr(evecs if vecs else None), n_pad,
-                          n_pad * n_pad, self.eig_sweeps + 6, 1e-10, ptr(None))
+            if n_pad <= 128:
+                self.ctx.call('cpsd_eig_sym_small_f64', ptr(A), n_pad, n_pad * n_pad, _p(n_dev),
+                              n_fixed, nprob, ptr(evals), n_pad, ptr(evecs if vecs else None), n_pad,
+                              n_pad * n_pad, self.eig_sweeps + 6, 1e-10, ptr(None))
+                return evals, evecs
+            # 128 < n <= 256 (patients with more than 128 electrodes): fp64 one-sided Jacobi on an
+            # L2-resident workspace (csrc/solve64.cu)
+            assert n_pad <= 256
+            w64 = self.ws(tag + '_e64', (int(self.ctx.lib.cpsd_eig_sym_f64_ws_elems(nprob, n_pad)),),
+                          torch.float64)
+            if vecs:
+                evecs.zero_()
+            self.ctx.call('cpsd_eig_sym_f64', ptr(A), n_pad, n_pad * n_pad, _p(n_dev), n_fixed, nprob,
+                          ptr(evals), n_pad, ptr(evecs if vecs else None), n_pad, n_pad * n_pad, 40,
+                          ptr(w64), n_pad, ptr(None))
             return evals, evecs
         if n_pad <= 128:
             self.eig_small(A, n_dev, n_fixed, nprob, n_pad, evals, evecs, n_pad)
@@ -466,7 +485,7 @@ class CVEngine:
     def scatter(self, name, nprob, n_pad):
         """Workspace + kernel name for a batch of scatter matrices that feed an eigen-solver:
         fp64 accumulation and the fp64-matrix solver whenever the tile solver applies."""
-        if n_pad <= 128:
+        if n_pad <= 256:
             return self.ws(name, (nprob, n_pad, n_pad), torch.float64), 'cpsd_gram_tn_f64'
         return self.ws(name, (nprob, n_pad, n_pad)), 'cpsd_gram_tn'
 
@@ -644,6 +663,7 @@ class CVEngine:
             ln = copy.copy(self)
             ln._extra_lanes = None                    # no reference cycles: engines must die by
             ln._ws, ln._vs, ln._tc_stage, ln._marks = {}, None, None, []   # refcount
+            ln._sched = {}          # block-Jacobi schedules are uploaded on the lane's own stream
             ln._xc = None
             ln._jc = None
             ln._tkc_key = None
@@ -1143,7 +1163,13 @@ class CVEngine:
         t_pack = time.perf_counter()
         downdate = (not joint) and use_rank and getattr(self, 'tg', None) is not None and n_padC == 128
         if downdate:
-            use_te = int(n_te_a.sum()) <= int(n_tr_a.sum())
+            # 'all trials minus held-out trials' equals the train-set Gram only when train and
+            # test partition the target's trials exactly (plain K-fold units); subsampled train
+            # sets, fit-only calls and inner folds of a nested search sum the train list instead
+            hits = np.zeros((B, tv.N), dtype=np.int32)
+            np.add.at(hits, (np.nonzero(mtr)[0], TR[mtr]), 1)
+            np.add.at(hits, (np.nonzero(mte)[0], TE[mte]), 1)
+            use_te = bool((hits == 1).all()) and int(n_te_a.sum()) <= int(n_tr_a.sum())
             La, Lm = (TE, mte) if use_te else (TR, mtr)
             o_lptr = pk.add_ints(np.concatenate([[0], np.cumsum(Lm.sum(axis=1))]))
             o_list = pk.add_ints(La[Lm])

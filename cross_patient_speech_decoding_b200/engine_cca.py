@@ -174,7 +174,12 @@ def batch_cca_gen(eng, batch, want_details):
         mA = eng.ws('c_mA', (npair, Cm))
         mB = eng.ws('c_mB', (npair, Cm))
         Lcat = eng.ws('c_L', (npair, KTmax, 2 * dmax))
-        S = eng.ws('c_S', (npair, 2 * dmax, 2 * dmax))
+        # scatter of [L_a | L_b] accumulated in fp64 and solved in fp64 (csrc/solve64.cu): the
+        # Gram form squares the latents' condition number, fp32 moved the b->a map by up to 5e-3
+        # on noisy configurations with ~100 latent dimensions
+        S = eng.ws('c_S', (npair, 2 * dmax, 2 * dmax), torch.float64)
+        cca_ws = eng.ws('c_cca_ws', (int(ctx.lib.cpsd_cca_solve_f64_ws_elems(npair, dmax)),),
+                        torch.float64)
         Ma = eng.ws('c_Ma', (npair, dmax, dmax))
         Mb = eng.ws('c_Mb', (npair, dmax, dmax))
         G = eng.ws('c_G', (npair, dmax, dmax))
@@ -211,7 +216,7 @@ def batch_cca_gen(eng, batch, want_details):
         r_pl['C'][:, 1] = r_pl['ldx'][:, 1] = xC[ji]
         r_pl['q'], r_pl['ldw'], r_pl['ldy'] = dmax, dmax, 2 * dmax
         r_pl = r_pl.ravel()
-        sbase = addr(S) + 4 * 4 * dmax * dmax * jj
+        sbase = addr(S) + 8 * 4 * dmax * dmax * jj
         r_s = np.zeros(npair, dtype=_lib.GRAM_TN_DESC)
         r_s['A'] = r_s['B'] = lbase
         r_s['segA'] = r_s['segB'] = zero_a
@@ -219,12 +224,12 @@ def batch_cca_gen(eng, batch, want_details):
         r_s['p'] = r_s['q'] = r_s['lda'] = r_s['ldb'] = r_s['ldo'] = 2 * dmax
         r_s['sym'], r_s['alpha'] = 1, 1.0
         r_c = np.zeros(npair, dtype=_lib.CCA_DESC)
-        r_c['Saa'], r_c['Sbb'], r_c['Sab'] = sbase, sbase + 4 * (dmax * 2 * dmax + dmax), sbase + 4 * dmax
+        r_c['Saa'], r_c['Sbb'], r_c['Sab'] = sbase, sbase + 8 * (dmax * 2 * dmax + dmax), sbase + 8 * dmax
         r_c['Ma'], r_c['Mb'] = addr(Ma) + 4 * dmax * dmax * jj, addr(Mb) + 4 * dmax * dmax * jj
         r_c['G'], r_c['rho'] = addr(G) + 4 * dmax * dmax * jj, addr(rho) + 4 * dmax * jj
         r_c['info'] = addr(cinfo) + 16 * jj
         r_c['da'], r_c['db'] = d_a[jf], np.asarray(d_b)[ji]
-        r_c['lds'], r_c['ldm'], r_c['ldg'], r_c['rank_tol'] = 2 * dmax, dmax, dmax, 1e-10
+        r_c['lds'], r_c['ldm'], r_c['ldg'], r_c['rank_tol'] = 2 * dmax, dmax, dmax, 1e-13
         # Wc = W_b G  (C_b x dmax)
         r_w = np.zeros(npair, dtype=_lib.PROJ_DESC)
         r_w['X'] = addr(Wx) + 4 * Cm * dmax * ji
@@ -287,8 +292,8 @@ def batch_cca_gen(eng, batch, want_details):
     if aligned and nv:
         ctx.call('cpsd_colsum', pk.daddr(d_m), 2 * npair, Cm)
         ctx.call('cpsd_proj_nn', pk.daddr(d_pl), 2 * npair, KTmax // T, T, dmax)
-        ctx.call('cpsd_gram_tn', pk.daddr(d_s), npair, 2 * dmax, 2 * dmax)
-        ctx.call('cpsd_cca_solve', pk.daddr(d_c), npair, dmax)
+        ctx.call('cpsd_gram_tn_f64', pk.daddr(d_s), npair, 2 * dmax, 2 * dmax)
+        ctx.call('cpsd_cca_solve_f64', pk.daddr(d_c), npair, dmax, ptr(cca_ws))
         ctx.call('cpsd_proj_nn', pk.daddr(d_w), npair, 1, Cm, dmax)
     eng.mark('project_pool')
     ctx.call('cpsd_proj_nn', pk.daddr(d_pp), len(r_pp),
@@ -304,6 +309,14 @@ def batch_cca_gen(eng, batch, want_details):
     yield 'sync'
     yh = yhat.cpu().numpy()
     k2h = k2.cpu().numpy()
+    if aligned and nv:
+        bad = cinfo.view(npair, 4)[:, 1].cpu().numpy()
+        if bad.any():
+            j = int(np.nonzero(bad)[0][0])
+            raise np.linalg.LinAlgError(
+                'CCA: rank-deficient class-averaged latents (fold %d, cross patient %d); the '
+                'reference truncates to matrix_rank (AlignCCA.py:263-265), which the Gram-form '
+                'solver does not reproduce' % (j // nv, j % nv))
     res = {'y_pred': [yh[f, :n_te[f]].copy() for f in range(B)], 'k2': k2h.tolist(),
            'h2d_bytes': eng.packA.h2d_bytes + pk.h2d_bytes,
            'd2h_bytes': yh.nbytes + k2h.nbytes + d2h}

@@ -40,6 +40,18 @@ def eig_sym(A, n=None, max_sweeps=15, tol=3e-7, device=None, return_sweeps=False
     nprob, nn, _ = A.shape
     ns = np.full(nprob, nn, dtype=np.int32) if n is None else np.asarray(n, dtype=np.int32)
     n_pad = 128 if nn <= 128 else _ceil(nn, 128)
+    if f64 and n_pad > 128:
+        assert n_pad <= 256, 'fp64 eigen-solver: n <= 256'
+        Ad, nd = ctx.upload(np.ascontiguousarray(A)), ctx.upload(ns)
+        evals, evecs = ctx.empty((nprob, nn)), ctx.zeros((nprob, nn, nn))
+        sw = ctx.zeros((nprob,), I32)
+        ws = ctx.empty((int(ctx.lib.cpsd_eig_sym_f64_ws_elems(nprob, nn)),), F64)
+        ctx.call('cpsd_eig_sym_f64', ptr(Ad), nn, nn * nn, ptr(nd), 0, nprob, ptr(evals), nn, ptr(evecs),
+                 nn, nn * nn, 40, ptr(ws), nn, ptr(sw))
+        ev, V, sweeps = evals.cpu().numpy(), evecs.cpu().numpy(), sw.cpu().numpy()
+        if single:
+            ev, V, sweeps = ev[0], V[0], sweeps[0]
+        return (ev, V, sweeps) if return_sweeps else (ev, V)
     Ap = np.zeros((nprob, n_pad, n_pad), dtype=A.dtype)
     Ap[:, :nn, :nn] = A
     Ad = ctx.upload(Ap)
@@ -304,6 +316,57 @@ def project(X, W, mu=None, device=None):
     return Y.reshape(lead + (q,))
 
 
+def project_pool_tc(Xs, L, mu, dst, n_rows, device=None):
+    """The tensor-core pooled projection on its own (csrc/tc_proj.cu, ``k_proj_tc``):
+    Z[f][dst[f, v, trial]][t][:] = (X_v[trial][t][:] - mu[f, v]) @ L[f, v].
+    Xs: list of P arrays (N_v, T, C_v) with C_v <= 128 and C_v % 4 == 0; L: (B, P, Cmax, Q) with
+    Q <= 32; mu: (B, P, Cmax) or None; dst: (B, P, Nmax) int destination trial rows (-1 = skip).
+    Returns Z (B, n_rows, T * Q) float32 (rows no trial maps to stay zero)."""
+    ctx = _ctx(device)
+    P = len(Xs)
+    L = np.ascontiguousarray(L, dtype=np.float32)
+    B, P2, Cm, Q = L.shape
+    assert P2 == P
+    T = Xs[0].shape[1]
+    Nmax = int(dst.shape[2])
+    maps_h = torch.zeros((2 * P, 128), dtype=torch.uint8).pin_memory()
+    keep = []
+    for i, X in enumerate(Xs):
+        X = np.ascontiguousarray(X, dtype=np.float32)
+        N, T_, C = X.shape
+        assert T_ == T and C <= Cm
+        Xd = ctx.upload(X.reshape(N * T, C))
+        hi, lo = ctx.empty(Xd.shape), ctx.empty(Xd.shape)
+        ctx.call('cpsd_split_tf32', ptr(Xd), ptr(hi), ptr(lo), Xd.numel())
+        for u, t in enumerate((hi, lo)):
+            _lib.check(ctx.lib.cpsd_tmap_encode_f32(ctypes.c_void_p(maps_h[2 * i + u].data_ptr()), ptr(t),
+                                                    N * T, C, C, 128), 'tmap_encode')
+        keep += [Xd, hi, lo]
+    xmaps = maps_h.to(ctx.device, non_blocking=True)
+    nprob = B * P
+    lthi, ltlo, mul = ctx.zeros((nprob, 32, 128)), ctx.zeros((nprob, 32, 128)), ctx.zeros((nprob, 32))
+    mh = torch.zeros((2, 128), dtype=torch.uint8).pin_memory()
+    for u, t in enumerate((lthi, ltlo)):
+        _lib.check(ctx.lib.cpsd_tmap_encode_f32(ctypes.c_void_p(mh[u].data_ptr()), ptr(t), nprob * 32,
+                                                128, 128, 32), 'tmap_encode')
+    ltmaps = mh.to(ctx.device, non_blocking=True)
+    Ld = ctx.upload(L)
+    mud = ctx.upload(np.ascontiguousarray(mu, dtype=np.float32)) if mu is not None else None
+    cdim = ctx.upload(np.tile(np.array([X.shape[2] for X in Xs], dtype=np.int32), B))
+    ctx.call('cpsd_proj_tc_prep', ptr(Ld), Q, Cm * Q, ptr(mud), ptr(None), Cm, ptr(cdim), Q, ptr(lthi),
+             ptr(ltlo), ptr(mul), nprob)
+    dst_d = ctx.upload(np.ascontiguousarray(dst, dtype=np.int32))
+    Z = ctx.zeros((B, n_rows, T * Q))
+    ntr = np.array([X.shape[0] for X in Xs], dtype=np.int32)
+    nch = np.array([X.shape[2] for X in Xs], dtype=np.int32)
+    sms = torch.cuda.get_device_properties(ctx.device).multi_processor_count
+    ctx.call('cpsd_proj_tc', ptr(xmaps), ptr(ltmaps), P, B, T, Q, ctypes.c_void_p(ntr.ctypes.data),
+             ctypes.c_void_p(nch.ctypes.data), Nmax, ptr(dst_d), ptr(mul), ptr(Z), n_rows * T * Q, sms)
+    out = Z.cpu().numpy()
+    del keep
+    return out
+
+
 def class_mean(X, ids, device=None):
     """Mean over trials of each class.  X: (N, ...) ; ids: (N,) ints.  Classes in sorted id
     order.  Returns (classes, means (n_classes, ...))."""
@@ -328,8 +391,41 @@ def class_mean(X, ids, device=None):
     return classes, out.cpu().numpy().reshape((len(classes),) + X.shape[1:])
 
 
-def cca_solve(Saa, Sbb, Sab, device=None):
-    """CCA from scatter matrices.  Returns dict(Ma, Mb, G (db x da, b->a), rho, info)."""
+def cca_solve(Saa, Sbb, Sab, device=None, check_rank=True):
+    """CCA from scatter matrices (fp64 solve).  Returns dict(Ma, Mb, G (db x da, b->a), rho, info).
+    Raises LinAlgError when a scatter matrix is numerically rank deficient (the reference
+    truncates to ``matrix_rank`` there, AlignCCA.py:263-265; the Gram form cannot)."""
+    ctx = _ctx(device)
+    da, db = Saa.shape[0], Sbb.shape[0]
+    dmax = _ceil(max(da, db), 4)
+    S = np.zeros((2 * dmax, 2 * dmax), dtype=np.float64)
+    S[:da, :da] = Saa
+    S[dmax:dmax + db, dmax:dmax + db] = Sbb
+    S[:da, dmax:dmax + db] = Sab
+    Sd = ctx.upload(S)
+    Ma, Mb, G = ctx.zeros((dmax, dmax)), ctx.zeros((dmax, dmax)), ctx.zeros((dmax, dmax))
+    rho, info = ctx.zeros((dmax,)), ctx.zeros((4,), I32)
+    rec = np.zeros(1, dtype=_lib.CCA_DESC)
+    base = addr(Sd)
+    rec[0] = (base, base + 8 * (dmax * 2 * dmax + dmax), base + 8 * dmax, 0, 0, addr(Ma), addr(Mb),
+              addr(G), addr(rho), addr(info), da, db, 2 * dmax, dmax, dmax, 0, 1e-13, 0)
+    pk = HostPack(ctx)
+    pk.reserve_ints()
+    d = pk.add_descs(rec)
+    pk.upload()
+    ws = ctx.empty((int(ctx.lib.cpsd_cca_solve_f64_ws_elems(1, dmax)),), F64)
+    ctx.call('cpsd_cca_solve_f64', pk.daddr(d), 1, dmax, ptr(ws))
+    inf = info.cpu().numpy()
+    if check_rank and inf[1] == 1:
+        raise np.linalg.LinAlgError('CCA: rank-deficient latent dynamics (fewer independent samples '
+                                    'than latent dimensions, or duplicated dimensions)')
+    dd = int(inf[0])
+    return dict(Ma=Ma.cpu().numpy()[:da, :dd], Mb=Mb.cpu().numpy()[:db, :dd],
+                G=G.cpu().numpy()[:db, :da], rho=rho.cpu().numpy()[:dd], info=inf)
+
+
+def cca_solve_f32(Saa, Sbb, Sab, device=None):
+    """The fp32 shared-memory solver (kept for comparison; d <= 116)."""
     ctx = _ctx(device)
     da, db = Saa.shape[0], Sbb.shape[0]
     dmax = _ceil(max(da, db), 4)

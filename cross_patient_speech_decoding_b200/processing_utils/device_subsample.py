@@ -11,23 +11,39 @@ from ..device import Context, ptr
 I32 = torch.int32
 
 
+def _mark_ready(t):
+    """Tags a freshly produced CUDA tensor with an event on the producing stream; the engine's
+    lane stream waits on it before its first kernel reads the tensor (engine.View)."""
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(t.device))
+    t._cpsd_ready = ev
+    return t
+
+
 def resident(X, device=None):
     """Host (trials, time, channels) array -> fp32 CUDA tensor (uploaded once)."""
     ctx = Context.get(device)
     X = np.ascontiguousarray(X)
     t = torch.from_numpy(X)
-    raw = t.pin_memory().to(ctx.device, non_blocking=True)
+    t = t.pin_memory()
+    raw = t.to(ctx.device, non_blocking=True)
     if raw.dtype == torch.float64:
         out = ctx.empty(tuple(X.shape))
         ctx.call('cpsd_cast_f64_f32', ptr(raw), ptr(out), raw.numel())
-        return out
-    return raw.to(torch.float32)
+        out._cpsd_src = (t, raw)         # pinned source + raw copy stay alive with the tensor
+        return _mark_ready(out)
+    out = raw.to(torch.float32)
+    out._cpsd_src = (t, raw)
+    return _mark_ready(out)
 
 
 def gather_channels(X_dev, idx, device=None):
     """X_dev (trials, time, channels) fp32 CUDA tensor -> X_dev[:, :, idx] (new CUDA tensor)."""
     ctx = Context.get(device if device is not None else X_dev.device)
     assert X_dev.is_cuda and X_dev.dtype == torch.float32 and X_dev.dim() == 3
+    ev = getattr(X_dev, '_cpsd_ready', None)
+    if ev is not None:          # the source may still be uploading on another stream
+        torch.cuda.current_stream(X_dev.device).wait_event(ev)
     X_dev = X_dev.contiguous()
     idx = np.ascontiguousarray(idx, dtype=np.int32)
     assert idx.ndim == 1 and idx.size > 0 and idx.min() >= 0 and idx.max() < X_dev.shape[2]
@@ -36,7 +52,8 @@ def gather_channels(X_dev, idx, device=None):
     out = ctx.empty((N, T, idx.size))
     ctx.call('cpsd_gather_channels', ptr(X_dev), C, ptr(idx_d), int(idx.size), ptr(out), int(idx.size),
              N * T)
-    return out
+    out._cpsd_src = (X_dev, idx_d)
+    return _mark_ready(out)
 
 
 def spatial_average(data, avgIdxs, device=None):

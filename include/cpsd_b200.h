@@ -223,6 +223,26 @@ int cpsd_pca_basis(const float* evecs, int ldv, long long strideV, const int* k_
 /* CCA_align in Gram form: Cholesky whitening + one-sided Jacobi SVD (AlignCCA.py:235-285),
  * and the b->a map M_b pinv(M_a) of AlignCCA.transform (AlignCCA.py:93) */
 int cpsd_cca_solve(const cpsd_cca_desc* descs, int nprob, int dmax, cudaStream_t stream);
+/* the same in fp64 (the default of the engine and of AlignCCA): the records' Saa / Sbb / Sab
+ * point to DOUBLES (row stride lds in doubles, e.g. from cpsd_gram_tn_f64); Cholesky factors,
+ * whitened cross-scatter, its SVD and every back-substitution in fp64; dmax <= 256 (operands
+ * in shared memory while they fit, else in the L2-resident workspace `ws` of
+ * cpsd_cca_solve_f64_ws_elems doubles); outputs fp32 as above; info[1] = 1 flags a scatter
+ * matrix whose smallest Cholesky pivot fell below rank_tol (rank-deficient latents: the
+ * reference truncates to matrix_rank at AlignCCA.py:263-265, here the caller is told) */
+long long cpsd_cca_solve_f64_ws_elems(int nprob, int dmax);
+int cpsd_cca_solve_f64(const cpsd_cca_desc* descs, int nprob, int dmax, double* ws,
+                       cudaStream_t stream);
+/* symmetric eigen-decomposition in fp64 for 128 < n <= n_cap <= 256 (one-sided Jacobi on an
+ * L2-resident workspace of cpsd_eig_sym_f64_ws_elems doubles): channel covariances / scatter
+ * matrices of patients with more than 128 electrodes (sklearn PCA reached from
+ * decoders/cross_pt_decoders.py:234-241; AlignMCCA.n_components_var AlignMCCA.py:156-174).
+ * Positive semi-definite input; eigenvalues descending (fp32), eigenvectors as sorted columns
+ * (fp32; may be NULL) */
+long long cpsd_eig_sym_f64_ws_elems(int nprob, int n_cap);
+int cpsd_eig_sym_f64(const double* A, int lda, long long strideA, const int* n_dev, int n_fixed,
+                     int nprob, float* evals, int ld_e, float* evecs, int ldv, long long strideV,
+                     int max_sweeps, double* ws, int n_cap, int* sweeps_out, cudaStream_t stream);
 
 /* ---- MCCA assembly (mvlearn.embed.MCCA as called at AlignMCCA.py:152-153) ---------- */
 int cpsd_mcca_mask(const float* evecs, int ldv, long long strideV, const float* evals, int ld_e,

@@ -90,6 +90,26 @@ def cca_fit(Xa, Xb, ya, yb):
     return cca_directions(La.reshape(-1, La.shape[-1]), Lb.reshape(-1, Lb.shape[-1]))
 
 
+def trial_subselect(Xa, Xb, sa, sb):
+    """AlignCCA.py:205-232 (shared_trial_subselect): per shared class, in np.intersect1d order,
+    one np.random.permutation of patient A's trials of the class, then one of patient B's; the
+    first min(count) of each are kept (numpy's GLOBAL RNG, as in the reference)."""
+    La, Lb = [], []
+    for c in np.intersect1d(sa, sb):
+        ia = np.random.permutation(np.where(sa == c)[0])
+        ib = np.random.permutation(np.where(sb == c)[0])
+        m = min(len(ia), len(ib))
+        La.append(Xa[ia[:m]])
+        Lb.append(Xb[ib[:m]])
+    return np.vstack(La), np.vstack(Lb)
+
+
+def cca_fit_trial(Xa, Xb, ya, yb):
+    """AlignCCA.fit with type='trial' (AlignCCA.py:43-61, 186-232)."""
+    La, Lb = trial_subselect(Xa, Xb, labels_as_str(ya), labels_as_str(yb))
+    return cca_directions(La.reshape(-1, La.shape[-1]), Lb.reshape(-1, Lb.shape[-1]))
+
+
 # ----------------------------------------------------------------------- JointPCA.py
 def joint_pca_fit(Xs, labs, n_components):
     """JointPCA.py:165-211 (get_joint_PCA_transforms): PCA of the channel-concatenated class

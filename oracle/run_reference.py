@@ -42,7 +42,7 @@ def run_folds(target, cross, folds, method='mcca', n_comp=None, regs=0.5, pca_va
     ref = reference_path.load()
     Xt, yt, yat = target
     out = dict(y_pred=[], y_true=[], k2=[], d_a=[], d_b=[], rho=[], ranks=[], evals_mcca=[],
-               loadings=[], means=[], Ma=[], Mb=[], svm_w=[], pool_shape=[])
+               loadings=[], means=[], Ma=[], Mb=[], svm_w=[], pool_shape=[], W_joint=[])
     for tr, te in folds:
         clf = make_decoder(ref, decoder_var, C, svm)
         if method == 'mcca':
@@ -54,6 +54,12 @@ def run_folds(target, cross, folds, method='mcca', n_comp=None, regs=0.5, pca_va
             m = ref.decoders.crossPtDecoder_sepAlign(cross, clf, ref.AlignCCA,
                                                      n_comp=0.9 if n_comp is None else n_comp,
                                                      tar_in_train=tar_in_train)
+        elif method == 'jointpca':
+            import functools
+            jp = functools.partial(ref.JointPCA, dim_red=functools.partial(PCA, svd_solver='full'))
+            m = ref.decoders.crossPtDecoder_jointDimRed(cross, clf, jp,
+                                                        n_comp=40 if n_comp is None else n_comp,
+                                                        tar_in_train=tar_in_train)
         elif method == 'none':
             m = ref.decoders.crossPtDecoder_sepDimRed(cross, clf,
                                                       n_comp=0.9 if n_comp is None else n_comp,
@@ -87,6 +93,8 @@ def run_folds(target, cross, folds, method='mcca', n_comp=None, regs=0.5, pca_va
                 out['rho'].append([np.asarray(a.canon_corrs) for a in m.algns])
                 out['Ma'].append([np.asarray(a.M_a) for a in m.algns])
                 out['Mb'].append([np.asarray(a.M_b) for a in m.algns])
+            elif method == 'jointpca':
+                out['W_joint'].append([np.asarray(w) for w in m.joint_dr.transforms])
             else:
                 out['d_a'].append(int(m.common_dim))
     return out

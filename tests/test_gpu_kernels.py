@@ -175,7 +175,8 @@ def _cca_ref(La, Lb):
     return Ma, Mb, np.clip(S[:d], 0, 1), La, Lb
 
 
-@pytest.mark.parametrize('da,db', [(13, 13), (20, 14), (9, 26), (60, 60), (100, 97), (1, 1)])
+@pytest.mark.parametrize('da,db', [(13, 13), (20, 14), (9, 26), (60, 60), (100, 97), (1, 1), (116, 116),
+                                   (130, 101), (88, 150), (201, 180)])
 def test_cca_solve(ops, da, db):
     rng = np.random.default_rng(da * 100 + db)
     n = 900
@@ -185,15 +186,51 @@ def test_cca_solve(ops, da, db):
     Ma, Mb, rho, Lac, Lbc = _cca_ref(La, Lb)
     out = ops.cca_solve(Lac.T @ Lac, Lbc.T @ Lbc, Lac.T @ Lbc)
     assert out['info'][0] == min(da, db)
-    assert np.abs(out['rho'] - rho).max() < 1e-4
+    assert out['info'][1] == 0
+    assert np.abs(out['rho'] - rho).max() < 2e-6        # fp64 solve, fp32 output
     # canonical variates: correlations of the projected data equal rho, variates are white
     Pa, Pb = Lac @ out['Ma'], Lbc @ out['Mb']
-    assert np.abs(Pa.T @ Pa - np.eye(len(rho))).max() < 2e-3
-    assert np.abs(np.diag(Pa.T @ Pb) - rho).max() < 2e-4
+    assert np.abs(Pa.T @ Pa - np.eye(len(rho))).max() < 1e-4
+    assert np.abs(np.diag(Pa.T @ Pb) - rho).max() < 1e-4
     # b -> a map equals M_b pinv(M_a) of the reference
     Gref = Mb @ np.linalg.pinv(Ma)
-    num = np.abs(Lbc @ out['G'] - Lbc @ Gref).max()
-    assert num <= 2e-3 * np.abs(Lbc @ Gref).max()
+    assert np.abs(out['G'] - Gref).max() <= 2e-5 * np.abs(Gref).max()
+
+
+@pytest.mark.parametrize('da,db', [(30, 30), (100, 97)])
+def test_cca_solve_fp64_beats_fp32_on_ill_conditioned_latents(ops, da, db):
+    """Latents whose variances span 1e5 (PCA scores down to the noise floor): the fp64 solver keeps
+    the b->a map at fp32-output accuracy where the fp32 shared-memory solver loses digits."""
+    rng = np.random.default_rng(da)
+    n = 2000
+    sc = np.logspace(0, -2.5, max(da, db))
+    Zs = rng.standard_normal((n, max(da, db)))
+    La = (Zs[:, :da] + 0.5 * rng.standard_normal((n, da))) * sc[:da]
+    Lb = (Zs[:, :db] @ np.linalg.qr(rng.standard_normal((db, db)))[0] + 0.5 * rng.standard_normal((n, db))) * sc[:db]
+    Ma, Mb, rho, Lac, Lbc = _cca_ref(La, Lb)
+    Gref = Mb @ np.linalg.pinv(Ma)
+    S = (Lac.T @ Lac, Lbc.T @ Lbc, Lac.T @ Lbc)
+    e64 = np.abs(Lbc @ ops.cca_solve(*S)['G'] - Lbc @ Gref).max() / np.abs(Lbc @ Gref).max()
+    e32 = np.abs(Lbc @ ops.cca_solve_f32(*S)['G'] - Lbc @ Gref).max() / np.abs(Lbc @ Gref).max()
+    assert e64 < 1e-5, e64
+    assert e64 < e32
+
+
+@pytest.mark.parametrize('n', [129, 150, 201, 256])
+def test_eig_sym_f64_above_128(ops, n):
+    """fp64 one-sided Jacobi eigen-solver for 128 < n <= 256 (patients with more than 128
+    channels) against numpy.linalg.eigh: spectrum, orthonormality, residual, sorted order."""
+    rng = np.random.default_rng(n)
+    X = rng.standard_normal((3 * n, n)) * np.logspace(0, -2, n)
+    A = np.stack([X.T @ X, _rand_sym(rng, n)])
+    ev, V, sw = ops.eig_sym(A, f64=True, return_sweeps=True)
+    assert (sw < 40).all(), sw
+    for i in range(2):
+        ref = np.linalg.eigvalsh(A[i])[::-1]
+        scale = np.abs(ref).max()
+        assert np.abs(ev[i] - ref).max() <= 2e-7 * scale
+        assert np.abs(V[i].T @ V[i] - np.eye(n)).max() < 2e-6
+        assert np.abs(A[i] @ V[i] - V[i] * ev[i]).max() <= 2e-6 * scale
 
 
 def test_svm_matches_liblinear_primal(ops):
@@ -383,3 +420,52 @@ def test_select_k_total(ops):
     # mode 0: k = #{cumulative ratio <= thr} + 1
     assert ops.select_k(ev, 0.82, 0, total=[10.0])[0] == 3    # ratios .5 .8 .9 .95 of the given total
     assert ops.select_k(ev, 0.82, 0)[0] == 2                  # ratios .526 .842 ... of their own sum
+
+
+@pytest.mark.parametrize('shape', [
+    dict(n=(20, 31, 9), c=(128, 96, 64), t=25, q=30, b=3),
+    dict(n=(40, 17), c=(128, 128), t=200, q=32, b=5),
+    dict(n=(12, 14, 5, 8), c=(36, 4, 100, 128), t=7, q=7, b=2),
+])
+def test_proj_tc_direct(ops, shape):
+    """k_proj_tc (tcgen05 3xTF32 pooled projection) on its own against fp64 (X - mu) L: ragged
+    trial counts, channel counts below 128, odd time axis, destination tables with skipped
+    trials and per-fold permutations."""
+    rng = np.random.default_rng(3)
+    P, B, T, Q = len(shape['n']), shape['b'], shape['t'], shape['q']
+    Cm = max(shape['c'])
+    Xs = [rng.standard_normal((n, T, c)) * rng.uniform(0.5, 3.0, c) + rng.standard_normal(c)
+          for n, c in zip(shape['n'], shape['c'])]
+    L = rng.standard_normal((B, P, Cm, Q))
+    mu = rng.standard_normal((B, P, Cm))
+    for v, c in enumerate(shape['c']):
+        L[:, v, c:, :] = 0.0
+    Nmax = max(shape['n'])
+    ntot = sum(shape['n'])
+    dst = -np.ones((B, P, Nmax), dtype=np.int32)
+    for f in range(B):
+        perm = rng.permutation(ntot)
+        o = 0
+        for v, n in enumerate(shape['n']):
+            dst[f, v, :n] = perm[o:o + n]
+            o += n
+        dst[f, 0, f % shape['n'][0]] = -1           # one skipped trial per fold
+    Z = ops.project_pool_tc(Xs, L, mu, dst, ntot)
+    Z = Z.reshape(B, ntot, T, Q)
+    worst = 0.0
+    for f in range(B):
+        used = np.zeros(ntot, dtype=bool)
+        for v, n in enumerate(shape['n']):
+            c = shape['c'][v]
+            ref = (Xs[v].astype(np.float32).astype(np.float64) -
+                   mu[f, v, :c].astype(np.float32).astype(np.float64)) @ \
+                L[f, v, :c].astype(np.float32).astype(np.float64)
+            for tr in range(n):
+                d = dst[f, v, tr]
+                if d < 0:
+                    continue
+                used[d] = True
+                err = np.abs(Z[f, d] - ref[tr]).max() / np.abs(ref).max()
+                worst = max(worst, err)
+        assert not Z[f, ~used].any()                 # rows nobody maps to stay untouched
+    assert worst < 2e-5, worst      # 3xTF32 (one TF32 pass would be ~1e-3)

@@ -65,12 +65,14 @@ def test_golden_fold_indices_reproducible():
         pts = [(None, None, None)]
         # only labels are needed: regenerate patient 0 cheaply
         from cross_patient_speech_decoding_b200 import synthetic
-        kw = dict(cfg['patients'][0])
+        kw = dict(cfg['patients'][cfg.get('target', 0)])
         kw.update(n_time=2, n_chan=2)
         _, y, _ = synthetic.make_patient(**kw)
         from cross_patient_speech_decoding_b200.folds import cv_splits
         np.random.seed(cfg['seed'])
-        folds = cv_splits(y, cfg['n_splits'])
+        folds = []
+        for _ in range(cfg.get('n_iter', 1)):
+            folds += cv_splits(y, cfg['n_splits'])
         for f in range(int(g['n_folds'])):
             assert np.array_equal(folds[f][0], g['train_%d' % f])
             assert np.array_equal(folds[f][1], g['test_%d' % f])
