@@ -100,7 +100,7 @@ def cv_align_decode_stream(jobs, depth=8, method='mcca', device=None, **kw):
 
 
 def search_align_decode(target, cross, candidates, inner_folds, method='mcca', depth=4, device=None,
-                        **kw):
+                        shard=True, **kw):
     """Hyper-parameter search over the align -> reduce -> decode path, batched: every candidate
     (a dict of engine keywords, e.g. ``{'n_comp': 0.9, 'decoder_var': 0.6}``) is scored on all
     ``inner_folds`` as one job of ``cv_align_decode_stream``; the patients are uploaded once and
@@ -108,23 +108,35 @@ def search_align_decode(target, cross, candidates, inner_folds, method='mcca', d
     (scripts/aligned_decode_svm_ncv.py:388-405: a search with ``refit=False`` whose score is the
     mean per-fold accuracy) without one fit / predict call per (candidate, fold).
     Returns ``scores`` (mean per-fold accuracy per candidate), ``best_index``, ``best_params``
-    and ``y_pred`` (per candidate, per fold)."""
+    and ``y_pred`` (per candidate, per fold).  Under torch.distributed the candidates are dealt
+    to the ranks (one all_gather of the predicted labels at the end) unless ``shard=False`` (a
+    search nested inside an outer loop that is itself sharded)."""
     import numpy as np
 
+    from . import sharding
     from .processing_utils import device_subsample as ds
-    tv = (ds.resident(target[0], device), target[1], target[2])
-    cvs = [(ds.resident(c[0], device), c[1], c[2]) for c in cross]
+    rank, world, _ = sharding.init_from_env() if shard else (0, 1, 0)
+    mine = sharding.shard_units(len(candidates), 1, rank, world)   # candidates dealt to the ranks
     lab = np.asarray(target[1])
-    jobs = ((tv, cvs, inner_folds, dict(c)) for c in candidates)
-    scores, preds = [], []
-    for res in cv_align_decode_stream(jobs, depth=depth, method=method, device=device, **kw):
-        accs = [float(np.mean(yp == lab[te])) for yp, (_, te) in zip(res['y_pred'], inner_folds)]
+    preds = []
+    if mine:
+        tv = (ds.resident(target[0], device), target[1], target[2])
+        cvs = [(ds.resident(c[0], device), c[1], c[2]) for c in cross]
+        jobs = ((tv, cvs, inner_folds, dict(candidates[c])) for c in mine)
+        for res in cv_align_decode_stream(jobs, depth=depth, method=method, device=device, **kw):
+            preds.append(np.concatenate(res['y_pred']) if res['y_pred'] else np.zeros(0, dtype=np.int32))
+    allp = sharding.gather_predictions(mine, preds, enabled=shard)
+    cuts = np.cumsum([len(te) for _, te in inner_folds])[:-1]
+    scores, per_fold = [], []
+    for c in range(len(candidates)):
+        yps = np.split(np.asarray(allp[c]), cuts)
+        accs = [float(np.mean(yp == lab[te])) for yp, (_, te) in zip(yps, inner_folds)]
         scores.append(float(np.mean(accs)))
-        preds.append(res['y_pred'])
+        per_fold.append(yps)
     scores = np.asarray(scores)
     best = int(np.argmax(scores)) if len(scores) else -1
     return dict(scores=scores, best_index=best, best_params=dict(candidates[best]) if best >= 0 else None,
-                y_pred=preds)
+                y_pred=per_fold)
 
 
 cv_align_decode_stream.idle_s = 0.0     # host time spent with every in-flight job waiting on the GPU

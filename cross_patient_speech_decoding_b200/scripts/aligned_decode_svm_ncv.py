@@ -11,6 +11,13 @@ StratifiedKFold per iteration, then one stratified ``train_test_split`` per fold
 
 The nested Bayesian search (``-cv True``, needs scikit-optimize) is not available.
 Extra options: ``--data_file``, ``--n_iter``, ``--n_folds``, ``--decoder``, ``--seed``.
+
+Multi-GPU: launched under ``torchrun --nproc-per-node N -m
+cross_patient_speech_decoding_b200.scripts.aligned_decode_svm_ncv ...`` every rank generates
+the same unit list (same RNG stream), runs the CV iterations ``sharding.shard_units`` gives it
+on its own GPU with no data-path communication, and one all_gather of the predicted labels
+(``sharding.gather_predictions``) gives every rank the full result; rank 0 writes the pickle,
+which is identical to the single-GPU one.
 """
 import argparse
 import os
@@ -18,6 +25,7 @@ import os
 import numpy as np
 
 from .. import cv_align_decode
+from .. import sharding
 from ..alignment import alignment_utils as utils
 from ..folds import cv_splits
 
@@ -75,8 +83,12 @@ def make_units(lab_tar, n_iter, n_folds, tr_subsamp_r, fit_draws=1):
     return units
 
 
-def run(inputs):
+def run(inputs, run_units=None):
+    """``run_units(target, cross, units, **kw) -> {'y_pred': [...]}`` defaults to
+    ``cv_align_decode`` (tests inject a CPU stand-in to exercise the sharding on gloo)."""
     from sklearn.metrics import balanced_accuracy_score
+    rank, world, _ = sharding.init_from_env()
+    run_units = run_units or cv_align_decode
     cluster = str2bool(inputs['cluster'])
     if cluster:
         data_path, out_path = os.path.expanduser('~') + '/data/', os.path.expanduser('~') + '/workspace/'
@@ -125,6 +137,8 @@ def run(inputs):
                       'red_method': red_method}}
     lab_tar = np.asarray(lab_tar)
     units = make_units(lab_tar, n_iter, n_folds, inputs['trial_subsample'])
+    mine = sharding.shard_units(len(units), n_folds, rank, world)    # whole iterations per rank
+    my_units = [units[u] for u in mine]
     dec_kw = dict(decoder=inputs['decoder'],
                   class_weight='balanced' if inputs['decoder'] == 'svc_rbf' else None,
                   decoder_var=param_grid['decoder__dimredreshape__n_components'])
@@ -144,29 +158,32 @@ def run(inputs):
             kw = dict(method='mcca', n_comp=30, regs=0.5, pca_var=0.8)
         else:
             kw = dict(method='none', n_comp=param_grid['n_comp'])
-        res = cv_align_decode((D_tar, lab_tar, lab_tar_full), cross, units,
-                              tar_in_train=tar_in_train, use_tensor_cores=True, max_batch=148,
-                              **kw, **dec_kw)
-        y_pred_units = res['y_pred']
+        res = run_units((D_tar, lab_tar, lab_tar_full), cross, my_units,
+                        tar_in_train=tar_in_train, use_tensor_cores=True, max_batch=148,
+                        **kw, **dec_kw) if my_units else {'y_pred': []}
+        y_pred_mine = res['y_pred']
     elif pool_train:
         # joint PCA: the script's set_params hands n_comp = 0.9 (a variance fraction) to
         # JointPCA(n_components=...) (:186-190, :372-375, :416); the batched engine takes a fixed
         # component count only, so this branch goes fold by fold through the drop-in classes
         from ..alignment.JointPCA import JointPCA
         from ..decoders.cross_pt_decoders import crossPtDecoder_jointDimRed
-        y_pred_units = []
-        for tr, te in units:
+        y_pred_mine = []
+        for tr, te in my_units:
             model = crossPtDecoder_jointDimRed(cross, make_clf(), JointPCA, n_comp=param_grid['n_comp'],
                                                tar_in_train=tar_in_train)
             model.fit(D_tar[tr], lab_tar[tr], y_align=lab_tar_full[tr])
-            y_pred_units.append(model.predict(D_tar[te]))
+            y_pred_mine.append(model.predict(D_tar[te]))
     else:
         # single-patient branch (:406-428): DimRedReshape(PCA(0.8)) -> decoder on the raw trials
-        y_pred_units = []
-        for tr, te in units:
+        y_pred_mine = []
+        for tr, te in my_units:
             clf = make_clf()
             clf.fit(D_tar[tr], lab_tar[tr])
-            y_pred_units.append(clf.predict(D_tar[te]))
+            y_pred_mine.append(clf.predict(D_tar[te]))
+    # the one collective: every rank receives the labels of all units
+    allp = sharding.gather_predictions(mine, y_pred_mine)
+    y_pred_units = [allp[u] for u in range(len(units))]
     y_true_iter, y_pred_iter, wrong_iter, accs = [], [], [], []
     for j in range(n_iter):
         yt, yp, wrong = [], [], []
@@ -181,10 +198,11 @@ def run(inputs):
         wrong_iter.append(wrong)
         accs.append(balanced_accuracy_score(yt, yp))
     out.update(y_true=y_true_iter, y_pred=y_pred_iter, wrong_trs=wrong_iter, accs=accs)
-    d = os.path.dirname(filename)
-    if d:
-        os.makedirs(d, exist_ok=True)
-    utils.save_pkl(out, filename)
+    if rank == 0:
+        d = os.path.dirname(filename)
+        if d:
+            os.makedirs(d, exist_ok=True)
+        utils.save_pkl(out, filename)
     return out
 
 

@@ -191,7 +191,8 @@ def run_fold(target, cross, train, test, method='mcca', n_comp=None, regs=0.5, p
         raise ValueError(method)
     pca = PCA(n_components=decoder_var).fit(Xp)
     if decoder == 'linear':
-        svm = LinearSVC(dual=False, C=C, tol=1e-10, max_iter=100000)
+        from oracle.svm_exact import oracle_linear_svc
+        svm = oracle_linear_svc(C)     # liblinear primal, certified / re-solved per class
     else:
         # the scripts' literal decoder (scripts/aligned_decode_svm_ncv.py:313-317: rbf, balanced;
         # aligned_decode_svm.py:262: linear) -- sklearn's SVC is libsvm itself

@@ -4,8 +4,9 @@ Runs the reference's own classes (imported from /root/reference through
 oracle/reference_path.py) over a list of CV folds, the way the loop body of
 scripts/aligned_decode_svm_ncv.py:344-442 does, with the pinned decoder
 ``make_pipeline(DimRedReshape(PCA, n_components=decoder_var),
-LinearSVC(dual=False, C, tol=1e-10, max_iter=100000))``  (see oracle/svm_exact.py for
-why the primal liblinear solver is the one that defines the converged optimum).
+CertifiedLinearSVC(dual=False, C, tol=1e-10, max_iter=100000))``  (see oracle/svm_exact.py for
+why the primal liblinear solver, certified per class by its gradient and re-solved where it
+stalled, is what defines the converged optimum).
 Returns per-fold predictions plus the intermediate quantities the parity tests compare.
 """
 import warnings
@@ -20,7 +21,8 @@ from oracle import reference_path
 
 def make_decoder(ref, decoder_var=0.8, C=1.0, svm='primal'):
     if svm == 'primal':
-        clf = LinearSVC(dual=False, C=C, tol=1e-10, max_iter=100000)
+        from oracle.svm_exact import oracle_linear_svc
+        clf = oracle_linear_svc(C)     # liblinear primal, certified / re-solved per class
     elif svm == 'dual_default':
         clf = LinearSVC(dual=True, C=C, random_state=0)
     elif svm == 'svc_rbf':
@@ -75,6 +77,7 @@ def run_folds(target, cross, folds, method='mcca', n_comp=None, regs=0.5, pca_va
         pca = clf.steps[0][1].transformer
         svc = clf.steps[1][1]
         out['k2'].append(int(pca.n_components_))
+        out.setdefault('svm_refit', []).append(len(getattr(svc, 'refit_', [])))
         out['pool_shape'].append((pca.n_samples_, pca.n_features_in_))
         if details:
             if hasattr(svc, 'dual_coef_'):

@@ -104,7 +104,8 @@ def generate(name):
     nf = len(folds)
     heavy = cfg.get('heavy', nf)          # folds that keep their matrices
     out = dict(n_folds=nf, seconds_per_fold=dt / nf, k2=np.array(res['k2']),
-               pool_shape=np.array(res['pool_shape']), heavy=heavy)
+               pool_shape=np.array(res['pool_shape']), heavy=heavy,
+               svm_refit=np.array(res.get('svm_refit', [0] * nf)))   # classes liblinear left unconverged
     for f in range(nf):
         out['train_%d' % f] = folds[f][0].astype(np.int16)
         out['test_%d' % f] = folds[f][1].astype(np.int16)
@@ -135,8 +136,8 @@ def generate(name):
             out['d_a_%d' % f] = res['d_a'][f]
     np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
     acc = np.mean(np.concatenate(res['y_pred']) == np.concatenate(res['y_true']))
-    print('%s: %d folds, %.2f s/fold, acc %.3f, k2 %s' % (name, nf, dt / nf, acc, res['k2']),
-          flush=True)
+    print('%s: %d folds, %.2f s/fold, acc %.3f, k2 %s, classes re-solved after a liblinear stall: %s'
+          % (name, nf, dt / nf, acc, res['k2'], res.get('svm_refit')), flush=True)
 
 
 if __name__ == '__main__':

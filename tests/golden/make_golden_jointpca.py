@@ -25,7 +25,7 @@ from decoders.cross_pt_decoders import crossPtDecoder_jointDimRed  # noqa: E402 
 from decomposition.DimRedReshape import DimRedReshape  # noqa: E402  (reference)
 from sklearn.decomposition import PCA  # noqa: E402
 from sklearn.pipeline import make_pipeline  # noqa: E402
-from sklearn.svm import LinearSVC  # noqa: E402
+from oracle.svm_exact import oracle_linear_svc  # noqa: E402
 
 N_COMP = 12
 
@@ -48,7 +48,7 @@ def main():
     Xt, yt, yat = pts[0]
     for f, (tr, te) in enumerate(folds):
         clf = make_pipeline(DimRedReshape(PCA, n_components=0.8),
-                            LinearSVC(dual=False, C=1.0, tol=1e-10, max_iter=100000))
+                            oracle_linear_svc(1.0))
         model = crossPtDecoder_jointDimRed(pts[1:], clf, functools.partial(JointPCA, dim_red=full),
                                            n_comp=N_COMP)
         model.fit(Xt[tr], yt[tr], y_align=yat[tr])
