@@ -98,7 +98,7 @@ class CVEngine:
 
     def __init__(self, target, cross, method='mcca', n_comp=None, regs=0.5, pca_var=0.8,
                  decoder_var=0.8, C=1.0, tar_in_train=True, device=None, max_batch=32,
-                 dcd_epochs=0, max_newton=60, tol_newton=1e-9, tol_dcd=1e-4,
+                 dcd_epochs=0, max_newton=400, tol_newton=1e-9, tol_dcd=1e-4,
                  eig_sweeps=12, eig_tol=3e-7, use_tensor_cores=False, pool_solver='auto',
                  topk_block=128, topk_iters=8, topk_tol=5e-6, topk_rounds=3, n_lanes=2, lane=0,
                  topk_tf32_iters=5, topk_gap_tol=0.05, decoder='linear', class_weight=None, svc_tol=1e-3,
@@ -1027,6 +1027,19 @@ class CVEngine:
                  ptr(sv['rho']), ptr(yhat), ptr(None), min(kcap, 1024), B)
         return yhat
 
+    def _check_decoder(self, info, B):
+        """Linear decoder: counts the one-vs-rest problems whose Newton iteration hit max_newton
+        (stats['svm_unconverged']) and warns like sklearn does for liblinear."""
+        if self.decoder != 'linear':
+            return
+        bad = int((info.view(B, -1, 4)[:, :, 3] != 0).sum().item())
+        self.stats['svm_unconverged'] = self.stats.get('svm_unconverged', 0) + bad
+        if bad:
+            import warnings
+            from sklearn.exceptions import ConvergenceWarning
+            warnings.warn('linear SVM: %d one-vs-rest problem(s) did not reach the optimum in %d '
+                          'Newton steps' % (bad, self.max_newton), ConvergenceWarning)
+
     # ------------------------------------------------------------------ MCCA batch
     def _batch_mcca_gen(self, batch, want_details, align_only, pk):
         """Generator: runs the host packing + table upload, yields once, then launches."""
@@ -1577,6 +1590,7 @@ class CVEngine:
         yh = yhat.cpu().numpy()
         k2h = k2.cpu().numpy()
         st = status.cpu().numpy()
+        self._check_decoder(info, B)
         if st.any():
             raise ValueError('MCCA: n_components=%d exceeds the total signal rank in fold(s) %s'
                              % (Q, np.nonzero(st)[0].tolist()))

@@ -309,6 +309,7 @@ def batch_cca_gen(eng, batch, want_details):
     yield 'sync'
     yh = yhat.cpu().numpy()
     k2h = k2.cpu().numpy()
+    eng._check_decoder(info, B)
     if aligned and nv:
         bad = cinfo.view(npair, 4)[:, 1].cpu().numpy()
         if bad.any():

@@ -451,7 +451,7 @@ def cca_solve_f32(Saa, Sbb, Sab, device=None):
                 G=G.cpu().numpy()[:db, :da], rho=rho.cpu().numpy()[:dd], info=inf)
 
 
-def svm_fit_ovr(S, y, C=1.0, dcd_epochs=0, max_newton=60, tol_newton=1e-9, tol_dcd=1e-4,
+def svm_fit_ovr(S, y, C=1.0, dcd_epochs=0, max_newton=400, tol_newton=1e-9, tol_dcd=1e-4,
                 device=None):
     """One-vs-rest L2-regularised squared-hinge linear SVM.  S: (n, k) features, y: (n,) ints.
     Returns (classes, W (n_classes, k+1) float64 with the bias last, info (n_classes, 4))."""

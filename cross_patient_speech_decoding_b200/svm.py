@@ -10,7 +10,7 @@ from . import ops
 
 
 class LinearSVC(BaseEstimator, ClassifierMixin):
-    def __init__(self, C=1.0, tol=1e-4, dcd_epochs=2, max_newton=60, tol_newton=1e-9):
+    def __init__(self, C=1.0, tol=1e-4, dcd_epochs=2, max_newton=400, tol_newton=1e-9):
         self.C = C
         self.tol = tol
         self.dcd_epochs = dcd_epochs
