@@ -102,6 +102,7 @@ _SIGS = {
     'cpsd_copy_rows': [_P, c_int, c_ll, _P, c_int, c_ll, _P, c_int, c_int, c_int, c_int, c_int, _P],
     'cpsd_sum_mats_f64': [_P, _P, c_ll, _P, _P, ctypes.c_double, _P, c_ll, c_int, c_int, _P],
     'cpsd_gather_channels': [_P, c_int, _P, c_int, _P, c_int, c_ll, _P],
+    'cpsd_gather_trials': [_P, c_ll, _P, c_int, _P, _P],
     'cpsd_predict_fused': [_P, c_int, c_int, c_int, _P, _P, c_int, _P, _P, c_int, _P, _P, c_int, _P, _P,
                            c_int, _P, _P, _P, c_int, _P],
     'cpsd_pearson_rows': [_P, _P, c_int, c_ll, _P, _P],

@@ -415,6 +415,42 @@ extern "C" int cpsd_gather_channels(const float* src, int lds, const int* idx, i
   return CPSD_OK;
 }
 
+// Trial subsampling on resident trials (scripts/aligned_decode_cross_patient_subsample.py:
+// 303-312 index the trial axis with np.random.choice): dst[i] = src[idx[i]], rows of TC floats.
+namespace {
+__global__ void __launch_bounds__(256)
+k_gather_trials(const float* __restrict__ src, long long TC, const int* __restrict__ idx,
+                float* __restrict__ dst, int vec) {
+  const long long row = blockIdx.y;
+  const float* s = src + (long long)idx[row] * TC;
+  float* d = dst + row * TC;
+  if (vec) {
+    const float4* s4 = reinterpret_cast<const float4*>(s);
+    float4* d4 = reinterpret_cast<float4*>(d);
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < TC / 4;
+         e += (long long)gridDim.x * blockDim.x)
+      d4[e] = s4[e];
+  } else {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < TC;
+         e += (long long)gridDim.x * blockDim.x)
+      d[e] = s[e];
+  }
+}
+}  // namespace
+
+extern "C" int cpsd_gather_trials(const float* src, long long TC, const int* idx, int n, float* dst,
+                                  cudaStream_t stream) {
+  CPSD_CHECK_ARG(TC > 0 && n >= 0 && n <= 65535, "gather_trials: bad dims");
+  if (n == 0) return CPSD_OK;
+  const int vec = (TC % 4 == 0) && ((((uintptr_t)src) & 15) == 0) && ((((uintptr_t)dst) & 15) == 0);
+  long long per = vec ? TC / 4 : TC;
+  int bx = (int)((per + 255) / 256);
+  if (bx > 32) bx = 32;
+  k_gather_trials<<<dim3(bx, n), 256, 0, stream>>>(src, TC, idx, dst, vec);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
+
 // spatial_avg_data (processing_utils/spatial_avg_subsampling.py:74-96): block means of the
 // electrode grid.  data (trials x nelec x T) fp64, regions as CSR (reg_ptr, reg_elec = flat
 // electrode index x * grid_y + y), out (trials x T x nreg) fp64.

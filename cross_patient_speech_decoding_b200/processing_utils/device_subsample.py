@@ -56,6 +56,25 @@ def gather_channels(X_dev, idx, device=None):
     return _mark_ready(out)
 
 
+def gather_trials(X_dev, idx, device=None):
+    """X_dev (trials, time, channels) fp32 CUDA tensor -> X_dev[idx] (new CUDA tensor): the
+    ``x[samp_idx]`` of scripts/aligned_decode_cross_patient_subsample.py:309-311 on the device."""
+    ctx = Context.get(device if device is not None else X_dev.device)
+    assert X_dev.is_cuda and X_dev.dtype == torch.float32 and X_dev.dim() == 3
+    ev = getattr(X_dev, '_cpsd_ready', None)
+    if ev is not None:
+        torch.cuda.current_stream(X_dev.device).wait_event(ev)
+    X_dev = X_dev.contiguous()
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    assert idx.ndim == 1 and idx.size > 0 and idx.min() >= 0 and idx.max() < X_dev.shape[0]
+    idx_d = ctx.upload(idx, np.int32)
+    N, T, C = (int(v) for v in X_dev.shape)
+    out = ctx.empty((idx.size, T, C))
+    ctx.call('cpsd_gather_trials', ptr(X_dev), T * C, ptr(idx_d), int(idx.size), ptr(out))
+    out._cpsd_src = (X_dev, idx_d)
+    return _mark_ready(out)
+
+
 def spatial_average(data, avgIdxs, device=None):
     """spatial_avg_data: data (trials, grid_x, grid_y, time) host float array, avgIdxs list of
     (n_i, 2) grid index arrays -> (trials, time, regions) float64 numpy array."""

@@ -9,8 +9,11 @@ front (the numpy global RNG is consumed in the reference's order: one shuffled
 StratifiedKFold per iteration, then one stratified ``train_test_split`` per fold when
 ``--trial_subsample < 1``) and handed to ``cv_align_decode`` as ONE batch.
 
-The nested Bayesian search (``-cv True``, needs scikit-optimize) is not available.
-Extra options: ``--data_file``, ``--n_iter``, ``--n_folds``, ``--decoder``, ``--seed``.
+``-cv True`` (the nested ``BayesSearchCV`` of :388-405; scikit-optimize is absent) runs
+``search.bayes_search_align_decode`` per outer fold: a Gaussian-process / expected-improvement
+proposal loop whose candidates x inner folds go to the GPU as one batch per round.
+Extra options: ``--data_file``, ``--n_iter``, ``--n_folds``, ``--decoder``, ``--seed``,
+``--search_iter``, ``--search_points``.
 
 Multi-GPU: launched under ``torchrun --nproc-per-node N -m
 cross_patient_speech_decoding_b200.scripts.aligned_decode_svm_ncv ...`` every rank generates
@@ -56,6 +59,8 @@ def init_parser():
                     choices=['svc_rbf', 'svc_linear', 'linear'],
                     help="svc_rbf = the script's SVC(kernel='rbf', class_weight='balanced')")
     ap.add_argument('--seed', type=int, default=None, help='np.random.seed before the loops')
+    ap.add_argument('--search_iter', type=int, default=25, help='BayesSearchCV n_iter (-cv True)')
+    ap.add_argument('--search_points', type=int, default=5, help='BayesSearchCV n_points (-cv True)')
     return ap
 
 
@@ -98,12 +103,24 @@ def run(inputs, run_units=None):
     pool_train, tar_in_train = str2bool(inputs['pool_train']), str2bool(inputs['tar_in_train'])
     cca_align, mcca_align = str2bool(inputs['cca_align']), str2bool(inputs['MCCA_align'])
     joint_dim_red = str2bool(inputs['joint_dim_red'])
-    if str2bool(inputs['cross_validate']):
-        raise NotImplementedError('nested Bayesian search (-cv True) is not available here')
+    do_cv = str2bool(inputs['cross_validate'])
     n_iter, n_folds = inputs['n_iter'], inputs['n_folds']
     if sum([cca_align, mcca_align, joint_dim_red]) > 1:      # the reference's precedence (:218-222)
         cca_align = mcca_align = False
-    if mcca_align:
+    if do_cv:
+        # search spaces of aligned_decode_svm_ncv.py:149-176.  The reference's MCCA grid also lists
+        # three 'decoder__baggingclassifier__*' keys, but its checked-in decoder pipeline has no
+        # BaggingClassifier step (:299-317), so set_params would reject them: they are left out.
+        if mcca_align:
+            param_grid = {'n_comp': (10, 50), 'pca_var': (0.1, 0.95, 'uniform'),
+                          'decoder__dimredreshape__n_components': (0.1, 0.95, 'uniform')}
+        else:
+            param_grid = {'n_comp': (0.1, 0.95, 'uniform'),
+                          'decoder__dimredreshape__n_components': (0.1, 0.95, 'uniform')}
+        if not pool_train or joint_dim_red:
+            raise NotImplementedError('-cv True is batched for the pooled CCA / MCCA / unaligned '
+                                      'decoders (the search of aligned_decode_svm_ncv.py:388-394)')
+    elif mcca_align:
         param_grid = {'n_comp': 30, 'regs': 0.5, 'pca_var': 0.8,
                       'decoder__dimredreshape__n_components': 0.8}
     else:
@@ -140,8 +157,11 @@ def run(inputs, run_units=None):
     mine = sharding.shard_units(len(units), n_folds, rank, world)    # whole iterations per rank
     my_units = [units[u] for u in mine]
     dec_kw = dict(decoder=inputs['decoder'],
-                  class_weight='balanced' if inputs['decoder'] == 'svc_rbf' else None,
-                  decoder_var=param_grid['decoder__dimredreshape__n_components'])
+                  class_weight='balanced' if inputs['decoder'] == 'svc_rbf' else None)
+    if not do_cv:
+        dec_kw['decoder_var'] = param_grid['decoder__dimredreshape__n_components']
+    # one search seed per unit, drawn up front: a sharded run gives every rank the same searches
+    search_seeds = [int(np.random.randint(2 ** 31 - 1)) for _ in units] if do_cv else None
     def make_clf():
         from sklearn.pipeline import make_pipeline
         from ..decomposition.DimRedReshape import DimRedReshape
@@ -151,7 +171,30 @@ def run(inputs, run_units=None):
             kernel=inputs['decoder'][4:], class_weight=dec_kw['class_weight'])
         return make_pipeline(DimRedReshape(PCA, n_components=dec_kw['decoder_var']), dec)
 
-    if pool_train and not joint_dim_red:
+    if do_cv:
+        # nested search per outer fold (:388-405): 25 candidates in rounds of 5, each scored on
+        # n_folds inner folds of the outer-train trials, then one fit / predict with the winner
+        from .. import cv_align_decode_stream
+        from ..search import bayes_search_align_decode, engine_keywords
+        method = 'cca' if cca_align else ('mcca' if mcca_align else 'none')
+        base_kw = dict(dec_kw, tar_in_train=tar_in_train, use_tensor_cores=True)
+        if mcca_align:
+            base_kw['regs'] = 0.5
+        best = []
+        for u in mine:
+            tr, _ = units[u]
+            bs = bayes_search_align_decode((D_tar[tr], lab_tar[tr], lab_tar_full[tr]), cross, param_grid,
+                                           n_folds=n_folds, n_iter=inputs.get('search_iter', 25),
+                                           n_points=inputs.get('search_points', 5), method=method,
+                                           random_state=search_seeds[u], shard=False, max_batch=148,
+                                           **base_kw)
+            best.append(bs['best_params_'])
+        jobs = (((D_tar, lab_tar, lab_tar_full), cross, [units[u]], engine_keywords(b))
+                for u, b in zip(mine, best))
+        y_pred_mine = [r['y_pred'][0] for r in cv_align_decode_stream(jobs, depth=8, method=method,
+                                                                     max_batch=8, **base_kw)]
+        out['params']['best_params'] = sharding.gather_objects(mine, best)
+    elif pool_train and not joint_dim_red:
         if cca_align:
             kw = dict(method='cca', n_comp=param_grid['n_comp'])
         elif mcca_align:

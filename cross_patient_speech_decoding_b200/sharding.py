@@ -102,3 +102,15 @@ def gather_predictions(unit_ids, preds, device=None, enabled=True):
         rec[i, 2:2 + len(p)] = p
     rows = gather_records(rec, device=dev)
     return {int(r[0]): r[2:2 + int(r[1])].copy() for r in rows}
+
+
+def gather_objects(unit_ids, objs):
+    """Small picklable per-unit objects (e.g. the winning parameter dict of a nested search) from
+    all ranks, as a list ordered by unit id (every rank gets it)."""
+    rank, world = rank_world()
+    pairs = list(zip([int(u) for u in unit_ids], objs))
+    if world > 1:
+        allp = [None] * world
+        dist.all_gather_object(allp, pairs)
+        pairs = [p for part in allp for p in part]
+    return [o for _, o in sorted(pairs, key=lambda t: t[0])]

@@ -63,6 +63,10 @@ int cpsd_sum_mats_f64(const double* base, const double* mats, long long mat_stri
  * means of spatial_avg_data (processing_utils/spatial_avg_subsampling.py:74-96) */
 int cpsd_gather_channels(const float* src, int lds, const int* idx, int nidx, float* dst, int ldd,
                          long long nrows, cudaStream_t stream);
+/* dst[i] = src[idx[i]] over the trial axis (rows of TC = time x channels floats): the random
+ * trial subsets of scripts/aligned_decode_cross_patient_subsample.py:303-312 on resident data */
+int cpsd_gather_trials(const float* src, long long TC, const int* idx, int n, float* dst,
+                       cudaStream_t stream);
 /* alignment/metrics.py:41-68 pt_corr: Pearson r of every condition's flattened (time x feature)
  * block, a / b: (nrows x len) fp64 */
 int cpsd_pearson_rows(const double* a, const double* b, int nrows, long long len, double* r,

@@ -159,3 +159,45 @@ def test_ctypes_signatures_match_header():
             assert a is b, (name, i, a, b)
         checked += 1
     assert checked >= 55
+
+
+def test_bayes_search_space_and_proposals():
+    """search.BayesSearch (the BayesSearchCV stand-in of scripts/aligned_decode_svm_ncv.py:388-394):
+    skopt's space notation, reproducible proposals under a seed, no repeated candidates, and a
+    better optimum than the random start on a smooth objective."""
+    from cross_patient_speech_decoding_b200.search import BayesSearch, Dimension, engine_keywords
+    assert Dimension((10, 50)).kind == 'int' and Dimension((0.1, 0.95, 'uniform')).kind == 'real'
+    assert Dimension((1e-3, 1e5, 'log-uniform')).kind == 'log'
+    g = Dimension(np.arange(0.1, 1, 0.1))
+    assert g.kind == 'grid' and g.from_unit(0.0) == pytest.approx(0.1) and g.from_unit(1.0) == pytest.approx(0.9)
+    d = Dimension((1e-3, 1e5, 'log-uniform'))
+    assert d.from_unit(d.to_unit(3.7)) == pytest.approx(3.7)
+    space = {'n_comp': (10, 50), 'pca_var': (0.1, 0.95, 'uniform'),
+             'decoder__dimredreshape__n_components': (0.1, 0.95, 'uniform')}
+
+    def score(p):     # smooth, maximum 1.0 at (32, 0.7, 0.4)
+        return 1.0 - ((p['n_comp'] - 32) / 40.0) ** 2 - (p['pca_var'] - 0.7) ** 2 - \
+            (p['decoder__dimredreshape__n_components'] - 0.4) ** 2
+
+    def run(seed):
+        opt = BayesSearch(space, n_initial_points=10, random_state=seed)
+        hist = []
+        for _ in range(5):
+            c = opt.ask(5)
+            assert all(isinstance(p['n_comp'], int) and 10 <= p['n_comp'] <= 50 for p in c)
+            assert all(0.1 <= p['pca_var'] <= 0.95 for p in c)
+            opt.tell(c, [score(p) for p in c])
+            hist += c
+        return opt, hist
+
+    a, ha = run(3)
+    b, hb = run(3)
+    assert ha == hb                                             # reproducible
+    keys = {tuple(sorted(p.items())) for p in ha}
+    assert len(keys) == 25                                      # no candidate proposed twice
+    assert max(a.y[10:]) > max(a.y[:10])                        # the surrogate rounds improve on the random start
+    assert max(a.y) > 0.97
+    assert engine_keywords(ha[0]) == {'n_comp': ha[0]['n_comp'], 'pca_var': ha[0]['pca_var'],
+                                      'decoder_var': ha[0]['decoder__dimredreshape__n_components']}
+    with pytest.raises(ValueError):
+        engine_keywords({'decoder__baggingclassifier__n_estimators': 10})

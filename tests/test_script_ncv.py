@@ -98,3 +98,34 @@ def test_script_joint_branch_matches_port(lib_built, tmp_path):
                           for tr, te in units])
     got = np.array(res['y_pred'][0])
     assert got.shape == ref.shape and np.mean(got == ref) >= 0.9, float(np.mean(got == ref))
+
+
+@pytest.mark.gpu
+def test_script_nested_bayes_search(lib_built, tmp_path):
+    """-cv True (aligned_decode_svm_ncv.py:388-405): per outer fold a Bayesian search over the
+    script's space scored on inner folds of the outer-train trials, then one fit / predict with the
+    winner.  Checked for consistency: winners lie in the space, and the outer predictions equal a
+    plain cv_align_decode call with each unit's winning parameters."""
+    import make_golden_script as mg
+    from cross_patient_speech_decoding_b200 import cv_align_decode
+    from cross_patient_speech_decoding_b200.scripts import aligned_decode_svm_ncv as sc
+    from cross_patient_speech_decoding_b200.search import engine_keywords
+    res = sc.aligned_decoding(['-pt', 'S1', '-pi', '1', '-po', 'True', '-a', 'True', '-c', 'False',
+                               '-cv', 'True', '-f', str(tmp_path / 'out.pkl'), '--data_file',
+                               _write_data(tmp_path), '--seed', '5', '--n_iter', '1', '--n_folds', '3',
+                               '--decoder', 'linear', '--search_iter', '6', '--search_points', '3'])
+    best = res['params']['best_params']
+    assert len(best) == 3
+    for b in best:
+        assert set(b) == {'n_comp', 'decoder__dimredreshape__n_components'}
+        assert 0.1 <= b['n_comp'] <= 0.95 and 0.1 <= b['decoder__dimredreshape__n_components'] <= 0.95
+    d = mg.data_dict()
+    tar = (d['S1']['X1'], np.asarray(d['S1']['y1']), d['S1']['y_full_phon'])
+    cross = [(d[p]['X1'], np.asarray(d[p]['y1']), d[p]['y_full_phon']) for p in d['S1']['pre_pts']]
+    np.random.seed(5)
+    units = sc.make_units(tar[1], 1, 3, 1.0)
+    got = np.array(res['y_pred'][0])
+    want = np.concatenate([cv_align_decode(tar, cross, [u], method='cca', decoder='linear',
+                                           **engine_keywords(b))['y_pred'][0] for u, b in zip(units, best)])
+    assert np.array_equal(got, want)
+    assert 0.0 <= res['accs'][0] <= 1.0

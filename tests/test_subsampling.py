@@ -169,3 +169,55 @@ def test_subsample_decode_matches_per_subsample_port(lib_built):
         same += int((yp == np.array(out['y_pred'][j])).sum())
         tot += len(yp)
     assert same / tot >= 0.97, (same, tot)
+
+
+@pytest.mark.gpu
+def test_trial_count_sweep_matches_port(lib_built):
+    """processing_utils.trial_subsample_decode (the batched loops of
+    scripts/aligned_decode_cross_patient_subsample.py:290-381: per (k, iteration) a random k-trial
+    subset of every cross patient, a shuffled split, one decoder per fold) against the CPU port fed
+    with the same np.random stream: identical trial picks and folds, labels and the accuracy matrix."""
+    from sklearn.metrics import balanced_accuracy_score
+    from sklearn.model_selection import StratifiedKFold
+    from cross_patient_speech_decoding_b200 import synthetic
+    from cross_patient_speech_decoding_b200.processing_utils import device_subsample as ds
+    from cross_patient_speech_decoding_b200.processing_utils.trial_subsample_decode import (
+        trial_counts, trial_subsample_decode)
+    from oracle import pipeline_port as port
+    pts = [synthetic.make_patient(p, n_trials=n, n_time=20, n_chan=24, noise=0.5)
+           for p, n in enumerate((72, 90, 50))]
+    assert list(trial_counts(pts[1:], 25)) == [5, 30, 55]       # arange(5, ceil(median(90, 50)) + 1, 25)
+    # the device row gather itself
+    Xd = ds.resident(pts[1][0])
+    idx = np.array([7, 0, 89, 33, 12])
+    assert np.array_equal(ds.gather_trials(Xd, idx).cpu().numpy(), pts[1][0].astype(np.float32)[idx])
+    k_list, n_iter, n_folds = [20, 60], 2, 3
+    np.random.seed(21)
+    out = trial_subsample_decode(pts[0], pts[1:], k_list=k_list, n_iter=n_iter, n_folds=n_folds,
+                                 method='cca', n_comp=0.9, decoder='svc_rbf', class_weight='balanced', depth=3)
+    np.random.seed(21)
+    lab = pts[0][1]
+    same = tot = 0
+    for ki, k in enumerate(k_list):
+        for it in range(n_iter):
+            cross = []
+            for X, y, ya in pts[1:]:
+                if X.shape[0] < k:
+                    cross.append((X, y, ya))
+                else:
+                    s = np.random.choice(X.shape[0], k, replace=False)
+                    cross.append((X[s], y[s], ya[s]))
+            splits = list(StratifiedKFold(n_splits=n_folds, shuffle=True).split(np.zeros((len(lab), 1)), lab))
+            yp = np.concatenate([port.run_fold(pts[0], cross, tr, te, method='cca', n_comp=0.9,
+                                               decoder='svc_rbf', class_weight='balanced')[0]
+                                 for tr, te in splits])        # SVC.fit draws libsvm's seed per fold
+            yt = np.concatenate([lab[te] for _, te in splits])
+            j = ki * n_iter + it
+            assert np.array_equal(yt, np.array(out['y_true'][j]))
+            got = np.array(out['y_pred'][j])
+            same += int((got == yp).sum())
+            tot += len(yp)
+            assert abs(out['acc_mat'][ki, it] - balanced_accuracy_score(yt, got)) < 1e-12
+        assert out['trial_vec'][ki] == sum(min(k, p[0].shape[0]) if p[0].shape[0] >= k else p[0].shape[0]
+                                           for p in pts[1:])
+    assert same / tot >= 0.97, (same, tot)
