@@ -22,8 +22,9 @@ def cv_align_decode(target, cross, folds, method='mcca', **kw):
     ``SVC(kernel='rbf', class_weight='balanced')``, scripts/aligned_decode_svm_ncv.py:313-317).
     """
     from .engine import CVEngine
+    bag_seeds = kw.pop('bag_seeds', None)      # bagging decoders: per-fold estimator seeds
     eng = CVEngine(target, cross, method=method, **kw)
-    out = eng.run(folds)
+    out = eng.run(folds, bag_seeds=bag_seeds)
     out['h2d_bytes'] += sum(v.h2d_bytes for v in eng.views)
     return out
 
@@ -55,9 +56,10 @@ def cv_align_decode_stream(jobs, depth=8, method='mcca', device=None, **kw):
             jkw = dict(kw)
             if len(job) > 3 and job[3]:
                 jkw.update(job[3])                 # per-job engine keywords
+            seeds = jkw.pop('bag_seeds', None)
             eng = CVEngine(job[0], job[1], method=jkw.pop('method', method), device=dev, lane=lane,
                            **jkw)
-            gen = eng.run_gen(job[2])
+            gen = eng.run_gen(job[2], bag_seeds=seeds)
         return [eng, gen, None, False, None]     # engine, generator, result, done, wait event
 
     import time

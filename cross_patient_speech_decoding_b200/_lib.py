@@ -103,6 +103,7 @@ _SIGS = {
     'cpsd_sum_mats_f64': [_P, _P, c_ll, _P, _P, ctypes.c_double, _P, c_ll, c_int, c_int, _P],
     'cpsd_gather_channels': [_P, c_int, _P, c_int, _P, c_int, c_ll, _P],
     'cpsd_gather_trials': [_P, c_ll, _P, c_int, _P, _P],
+    'cpsd_mask_cols': [_P, c_int, c_ll, c_int, c_int, _P, c_int, c_int, _P],
     'cpsd_predict_fused': [_P, c_int, c_int, c_int, _P, _P, c_int, _P, _P, c_int, _P, _P, c_int, _P, _P,
                            c_int, _P, _P, _P, c_int, _P],
     'cpsd_pearson_rows': [_P, _P, c_int, c_ll, _P, _P],
@@ -134,6 +135,9 @@ _SIGS = {
                          ctypes.c_double, c_int, _P, c_int, _P, _P, c_int, c_int, _P],
     'cpsd_svc_predict_ovo': [_P, c_int, c_ll, _P, c_int, c_ll, _P, c_int, _P, c_int, c_int, _P, c_int,
                              _P, c_int, _P, c_int, c_int, _P, _P, c_int, _P, _P, _P, c_int, c_int, _P],
+    'cpsd_bag_gather': [_P, c_int, c_ll, _P, c_int, c_ll, _P, c_int, _P, c_int, _P, _P, _P, c_int, c_int,
+                        _P, c_int, _P, c_int, _P, _P, _P, _P, c_int, _P],
+    'cpsd_bag_vote': [_P, c_int, _P, c_int, _P, c_int, _P, c_int, _P],
     'cpsd_cca_solve': [_P, c_int, c_int, _P],
     'cpsd_cca_solve_f64_ws_elems': [c_int, c_int],
     'cpsd_cca_solve_f64': [_P, c_int, c_int, _P, _P],

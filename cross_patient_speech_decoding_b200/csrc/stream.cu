@@ -415,6 +415,32 @@ extern "C" int cpsd_gather_channels(const float* src, int lds, const int* idx, i
   return CPSD_OK;
 }
 
+// Zeroes the columns j >= k[p / group] of problem p's (rows x cols) matrix: the read-in matrices
+// of a JointPCA whose component count is a variance fraction (JointPCA(n_components=0.9),
+// scripts/aligned_decode_svm_ncv.py:186-190) are computed at a fixed width and cut per fold.
+namespace {
+__global__ void k_mask_cols(float* __restrict__ M, int ld, long long stride, int rows, int cols,
+                            const int* __restrict__ k_dev, int group) {
+  const int p = blockIdx.x;
+  const int k = k_dev[p / group];
+  float* Mp = M + (long long)p * stride;
+  for (int e = threadIdx.x; e < rows * cols; e += blockDim.x) {
+    const int r = e / cols, j = e - r * cols;
+    if (j >= k) Mp[(long long)r * ld + j] = 0.f;
+  }
+}
+}  // namespace
+
+extern "C" int cpsd_mask_cols(float* M, int ld, long long stride, int rows, int cols, const int* k_dev,
+                              int group, int nprob, cudaStream_t stream) {
+  CPSD_CHECK_ARG(nprob >= 0 && rows > 0 && cols > 0 && ld >= cols && group > 0 && k_dev != nullptr,
+                 "mask_cols: bad dims");
+  if (nprob == 0) return CPSD_OK;
+  k_mask_cols<<<nprob, 256, 0, stream>>>(M, ld, stride, rows, cols, k_dev, group);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
+
 // Trial subsampling on resident trials (scripts/aligned_decode_cross_patient_subsample.py:
 // 303-312 index the trial axis with np.random.choice): dst[i] = src[idx[i]], rows of TC floats.
 namespace {

@@ -514,3 +514,86 @@ extern "C" int cpsd_svc_predict_ovo(const float* St, int lds, long long strideS,
   CPSD_LAUNCH_CHECK();
   return CPSD_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// Bagging (sklearn BaggingClassifier(estimator=SVC(kernel='linear'), n_estimators=10), the
+// decoder of the reference's scripts/aligned_decode_svm.py:262-265): every fold becomes
+// n_est bootstrap problems that run as extra folds of the C-SVC kernels above.
+//   k_bag_gather: problem p = fold * n_est + e gets the resampled training scores
+//                 St_b[p][j][t] = St[fold][j][idx[p][t]], labels y_b[p][t] = y[fold][idx[p][t]],
+//                 a copy of the fold's test scores and of its sizes.
+//   k_bag_vote  : label = classes[argmax_c #{e : estimator e voted c}] (first maximum, as
+//                 numpy argmax over BaggingClassifier.predict_proba's vote counts).
+// ---------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256)
+k_bag_gather(const float* __restrict__ St, int lds, long long strideS, const float* __restrict__ Ste,
+             int ldt, long long strideT, const int* __restrict__ y, int ldy,
+             const int* __restrict__ idx, int ldi, const int* __restrict__ k_dev,
+             const int* __restrict__ n_dev, const int* __restrict__ nte_dev, int n_est, int kb,
+             float* __restrict__ St_b, int lds_b, float* __restrict__ Ste_b, int ldt_b,
+             int* __restrict__ y_b, int* __restrict__ k_b, int* __restrict__ n_b,
+             int* __restrict__ nte_b) {
+  const int p = blockIdx.x, f = p / n_est;
+  const int k = min(k_dev[f], kb), n = n_dev[f], nte = nte_dev[f];
+  const int* ix = idx + (long long)p * ldi;
+  const float* S = St + (long long)f * strideS;
+  float* Sb = St_b + (long long)p * kb * lds_b;
+  for (int e = threadIdx.x; e < kb * lds_b; e += blockDim.x) {
+    const int j = e / lds_b, t = e - j * lds_b;
+    Sb[e] = (j < k && t < n) ? S[(long long)j * lds + ix[t]] : 0.f;
+  }
+  const int* yf = y + (long long)f * ldy;
+  for (int t = threadIdx.x; t < lds_b; t += blockDim.x) y_b[(long long)p * lds_b + t] = (t < n) ? yf[ix[t]] : 0;
+  const float* Z = Ste + (long long)f * strideT;
+  float* Zb = Ste_b + (long long)p * kb * ldt_b;
+  for (int e = threadIdx.x; e < kb * ldt_b; e += blockDim.x) {
+    const int j = e / ldt_b, s = e - j * ldt_b;
+    Zb[e] = (j < k && s < nte) ? Z[(long long)j * ldt + s] : 0.f;
+  }
+  if (threadIdx.x == 0) { k_b[p] = k; n_b[p] = n; nte_b[p] = nte; }
+}
+
+__global__ void k_bag_vote(const int* __restrict__ yhat_b, int n_est, const int* __restrict__ classes,
+                           int ncls, const int* __restrict__ nte_dev, int n_te_max,
+                           int* __restrict__ yhat) {
+  const int f = blockIdx.x;
+  const int nte = nte_dev[f];
+  for (int s = threadIdx.x; s < n_te_max; s += blockDim.x) {
+    if (s >= nte) { yhat[(long long)f * n_te_max + s] = -1; continue; }
+    int best = -1, bv = -1;
+    for (int c = 0; c < ncls; ++c) {
+      int v = 0;
+      for (int e = 0; e < n_est; ++e)
+        v += (yhat_b[((long long)f * n_est + e) * n_te_max + s] == classes[c]);
+      if (v > bv) { bv = v; best = c; }
+    }
+    yhat[(long long)f * n_te_max + s] = classes[best];
+  }
+}
+}  // namespace
+
+extern "C" int cpsd_bag_gather(const float* St, int lds, long long strideS, const float* Ste, int ldt,
+                               long long strideT, const int* y, int ldy, const int* idx, int ldi,
+                               const int* k_dev, const int* n_dev, const int* nte_dev, int n_est, int kb,
+                               float* St_b, int lds_b, float* Ste_b, int ldt_b, int* y_b, int* k_b,
+                               int* n_b, int* nte_b, int nfold, cudaStream_t stream) {
+  CPSD_CHECK_ARG(nfold >= 0 && n_est > 0 && kb > 0 && lds_b > 0 && ldt_b > 0 && ldi >= 1,
+                 "bag_gather: bad dims");
+  if (nfold == 0) return CPSD_OK;
+  k_bag_gather<<<nfold * n_est, 256, 0, stream>>>(St, lds, strideS, Ste, ldt, strideT, y, ldy, idx, ldi,
+                                                  k_dev, n_dev, nte_dev, n_est, kb, St_b, lds_b, Ste_b,
+                                                  ldt_b, y_b, k_b, n_b, nte_b);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
+
+extern "C" int cpsd_bag_vote(const int* yhat_b, int n_est, const int* classes, int ncls,
+                             const int* nte_dev, int n_te_max, int* yhat, int nfold,
+                             cudaStream_t stream) {
+  CPSD_CHECK_ARG(nfold >= 0 && n_est > 0 && ncls > 0 && n_te_max > 0, "bag_vote: bad dims");
+  if (nfold == 0) return CPSD_OK;
+  k_bag_vote<<<nfold, 128, 0, stream>>>(yhat_b, n_est, classes, ncls, nte_dev, n_te_max, yhat);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}

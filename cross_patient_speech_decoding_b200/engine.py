@@ -93,6 +93,11 @@ class View:
         self.h2d_bytes = host.numel() * host.element_size()
 
 
+class _Batch(list):
+    """The folds of one engine batch plus what travels with them (bagging seeds)."""
+    bag_seeds = None
+
+
 class CVEngine:
     """See module docstring.  ``method``: 'mcca' | 'cca' | 'none'."""
 
@@ -102,11 +107,14 @@ class CVEngine:
                  eig_sweeps=12, eig_tol=3e-7, use_tensor_cores=False, pool_solver='auto',
                  topk_block=128, topk_iters=8, topk_tol=5e-6, topk_rounds=3, n_lanes=2, lane=0,
                  topk_tf32_iters=5, topk_gap_tol=0.05, decoder='linear', class_weight=None, svc_tol=1e-3,
-                 svc_gamma='scale', svc_max_iter=1000000):
+                 svc_gamma='scale', svc_max_iter=1000000, joint_cap=None, n_estimators=10):
         # decoder: 'linear' = one-vs-rest squared-hinge linear SVM (the north star's dual-CD
         # decoder); 'svc_rbf' / 'svc_linear' = libsvm-style C-SVC with one-vs-one votes, the
         # reference scripts' literal SVC(kernel=..., class_weight=...)
-        assert decoder in ('linear', 'svc_rbf', 'svc_linear')
+        # 'bag_svc_linear' / 'bag_svc_rbf': sklearn BaggingClassifier(estimator=SVC(kernel=...),
+        # n_estimators) around the C-SVC -- scripts/aligned_decode_svm.py:262-265 -- as n_estimators
+        # extra C-SVC problems per fold
+        assert decoder in ('linear', 'svc_rbf', 'svc_linear', 'bag_svc_linear', 'bag_svc_rbf')
         assert class_weight in (None, 'balanced')
         self.decoder = decoder
         self.class_weight = class_weight
@@ -123,6 +131,9 @@ class CVEngine:
                        use_tensor_cores, pool_solver, topk_block, topk_iters, topk_tol, topk_rounds,
                        n_lanes)
             self.topk_tf32_iters = int(topk_tf32_iters)
+        if joint_cap is not None:
+            self._joint_qcap = int(joint_cap)
+        self.n_estimators = int(n_estimators)
 
     def _init(self, target, cross, method, n_comp, regs, pca_var, decoder_var, C, tar_in_train,
               max_batch, dcd_epochs, max_newton, tol_newton, tol_dcd, eig_sweeps, eig_tol,
@@ -157,7 +168,15 @@ class CVEngine:
         self.topk_iters = int(topk_iters)
         self.topk_tol = float(topk_tol)
         self.topk_rounds = int(topk_rounds)
-        if method in ('mcca', 'jointpca'):
+        # JointPCA(n_components=0.9) -- what the script's set_params hands to the class
+        # (scripts/aligned_decode_svm_ncv.py:186-190): a variance fraction, i.e. a component count
+        # that depends on the fold.  The batch is laid out for `_joint_qcap` columns (sized from a
+        # fit on all trials, see _ensure_ready) and every fold's read-in matrices are cut at its own
+        # count; the surplus columns of the pooled matrix are zero and change nothing downstream.
+        self.joint_var = (method == 'jointpca' and isinstance(n_comp, (float, np.floating))
+                          and 0 < n_comp < 1)
+        self._joint_qcap = None
+        if method == 'mcca' or (method == 'jointpca' and not self.joint_var):
             assert isinstance(n_comp, (int, np.integer)) and n_comp >= 1
         views = [target] + list(cross)
         ids, self.vocab = class_ids([v[2] if v[2] is not None else v[1] for v in views])
@@ -545,6 +564,13 @@ class CVEngine:
             with torch.cuda.stream(self.stream):
                 self.cross_rank = self._rank_dev.cpu().numpy().astype(np.int32)
             self._keep = None
+        if self.joint_var and self._joint_qcap is None:
+            self._joint_qcap = 32
+            tv = self.views[0]
+            res = self._batch_mcca([(np.arange(tv.N), np.zeros(0, dtype=np.int64))], False,
+                                   align_only=True)
+            k_all = int(res['k'][0])
+            self._joint_qcap = min(120, _ceil(k_all + max(4, k_all // 4), 4))
 
     def _ranks_full(self, vs):
         """AlignMCCA.n_components_var on all trials of the given views (AlignMCCA.py:146-150)."""
@@ -677,14 +703,32 @@ class CVEngine:
         lanes = [self] + extra
         return lanes[:n]
 
-    def run(self, folds, return_details=False):
+    def _bag_seeds(self, folds, bag_seeds):
+        """Bagging decoders: the per-fold estimator seeds BaggingClassifier.fit draws
+        (``random_state.randint(MAX_INT, size=n_estimators)``, sklearn/ensemble/_bagging.py); given
+        by the caller (who replays the script's RNG stream) or drawn here from numpy's global RNG,
+        one draw of n_estimators seeds per fold in fold order."""
+        if not self.decoder.startswith('bag_'):
+            return None
+        if bag_seeds is None:
+            bag_seeds = [np.random.randint(np.iinfo(np.int32).max, size=self.n_estimators)
+                         for _ in folds]
+        bag_seeds = np.asarray(bag_seeds, dtype=np.int64).reshape(len(folds), self.n_estimators)
+        return bag_seeds
+
+    def run(self, folds, return_details=False, bag_seeds=None):
         """folds: list of (train_idx, test_idx) into the target's trials.  Returns a dict with
         ``y_pred`` (list of arrays, one per fold) and per-fold diagnostics."""
         out = {'y_pred': [], 'k2': [], 'h2d_bytes': 0, 'd2h_bytes': 0}
         details = []
         nb = max(1, -(-len(folds) // self.max_batch))
         size = -(-len(folds) // nb)          # balanced batches (a short tail batch costs as much
-        batches = [folds[s:s + size] for s in range(0, len(folds), size)]   # as a full one)
+        seeds = self._bag_seeds(folds, bag_seeds)                           # as a full one)
+        batches = []
+        for s0 in range(0, len(folds), size):
+            b = _Batch(folds[s0:s0 + size])
+            b.bag_seeds = None if seeds is None else seeds[s0:s0 + size]
+            batches.append(b)
         results = [None] * len(batches)
         self._ensure_ready()
         # every batch is a generator that yields right before each blocking read-back; the
@@ -748,7 +792,7 @@ class CVEngine:
             out['details'] = details
         return out
 
-    def run_gen(self, folds, return_details=False):
+    def run_gen(self, folds, return_details=False, bag_seeds=None):
         """Generator form of run() on this engine's own stream only (no extra lanes): yields
         before every blocking read-back, returns the result dict.  The caller advances it with
         this engine's stream current (cv_align_decode_stream keeps several jobs in flight)."""
@@ -759,8 +803,10 @@ class CVEngine:
         if self.method == 'mcca' and self.cross_rank is None:
             yield 'sync'                     # constructor work still in flight
         self._ensure_ready()
+        seeds = self._bag_seeds(folds, bag_seeds)
         for s0 in range(0, len(folds), size):
-            batch = folds[s0:s0 + size]
+            batch = _Batch(folds[s0:s0 + size])
+            batch.bag_seeds = None if seeds is None else seeds[s0:s0 + size]
             res = yield from self._batch_start(batch, return_details)
             out['y_pred'] += res['y_pred']
             out['k2'] += res['k2']
@@ -954,9 +1000,15 @@ class CVEngine:
         return evals, k2, St, Ste, V, sweeps, kcap
 
     def _svm_stage(self, pk2, B, St, Ste, k2, kcap, n_pad, n_pool, n_te, o_ypool, ypool_ld,
-                   o_nte, n_te_max, ypool=None):
+                   o_nte, n_te_max, ypool=None, batch=None):
         ctx = self.ctx
         ncls = len(self.classes)
+        if self.decoder.startswith('bag_'):
+            # everything is sized after the decoder PCA (the bootstrap index streams depend on its
+            # component count): see _decode_bagged
+            state = dict(bag=True, ypool=ypool, n_pool=list(n_pool),
+                         seeds=getattr(batch, 'bag_seeds', None))
+            return state, self.ws('svc_info', (B, 1, 2), I32), np.zeros(0, dtype=_lib.SVM_DESC)
         if self.decoder != 'linear':
             # C-SVC: no descriptors; the largest class pair of the batch sizes the solver's
             # shared memory
@@ -1008,6 +1060,9 @@ class CVEngine:
                      ptr(yhat), ptr(None), B)
             return yhat
         sv = W
+        if sv.get('bag'):
+            return self._decode_bagged(pk, sv, B, St, Ste, k2, kcap, n_pad, o_ypool, ypool_ld, o_npool,
+                                       o_nte, n_te_max, yhat)
         if self._k2_max > 1024:
             raise NotImplementedError('C-SVC decoders support at most 1024 decoder-PCA components '
                                       '(this batch keeps %d)' % self._k2_max)
@@ -1040,13 +1095,83 @@ class CVEngine:
             warnings.warn('linear SVM: %d one-vs-rest problem(s) did not reach the optimum in %d '
                           'Newton steps' % (bad, self.max_newton), ConvergenceWarning)
 
+    def _decode_bagged(self, pk, sv, B, St, Ste, k2, kcap, n_pad, o_ypool, ypool_ld, o_npool, o_nte,
+                       n_te_max, yhat):
+        """BaggingClassifier(estimator=SVC(kernel), n_estimators) per fold
+        (scripts/aligned_decode_svm.py:262-265): the bootstrap sample of estimator e of fold f is
+        sklearn's own index stream for seed[f][e] (``_generate_bagging_indices``: the feature draw
+        -- all features, a permutation -- comes first, so the stream depends on the decoder-PCA
+        component count); the resampled problems run as B * n_estimators folds of the C-SVC
+        kernels, their labels are combined by majority vote."""
+        from sklearn.ensemble._bagging import _generate_bagging_indices
+        ctx = self.ctx
+        ncls = len(self.classes)
+        E = self.n_estimators
+        k2h = k2.cpu().numpy()
+        n_pool, ypool, seeds = sv['n_pool'], sv['ypool'], sv['seeds']
+        idx = np.zeros((B * E, n_pad), dtype=np.int32)
+        for f in range(B):
+            kf, nf = int(k2h[f]), int(n_pool[f])
+            for e in range(E):
+                _, si = _generate_bagging_indices(int(seeds[f][e]), False, True, kf, nf, kf, nf)
+                idx[f * E + e, :nf] = si
+        fe = np.repeat(np.arange(B), E)
+        yb = ypool[fe[:, None], idx]
+        valid = np.arange(n_pad)[None, :] < np.asarray(n_pool)[fe][:, None]
+        ci = np.searchsorted(self.classes, yb[valid])
+        po = np.broadcast_to(np.arange(B * E)[:, None], yb.shape)[valid]
+        cnt = np.bincount(po * ncls + ci, minlength=B * E * ncls).reshape(B * E, ncls)
+        top = np.sort(cnt, axis=1)
+        m_max = int((top[:, -1] + top[:, -2]).max())
+        kb = _ceil(max(int(k2h.max()), 1), 4)
+        if kb > 1024:
+            raise NotImplementedError('C-SVC decoders support at most 1024 decoder-PCA components')
+        BE = B * E
+        idx_d = ctx.upload(idx, np.int32)
+        St_b = self.ws('bag_St', (BE, kb, n_pad))
+        Ste_b = self.ws('bag_Ste', (BE, kb, n_te_max))
+        y_b = self.ws('bag_y', (BE, n_pad), I32)
+        k_b, n_b, nte_b = (self.ws('bag_' + t, (BE,), I32) for t in ('k', 'n', 'nte'))
+        yhat_b = self.ws('bag_yhat', (BE, n_te_max), I32)
+        npair = ncls * (ncls - 1) // 2
+        coef = self.ws('svc_coef', (BE, ncls - 1, n_pad), torch.float64)
+        rho = self.ws('svc_rho', (BE, npair), torch.float64)
+        gam = self.ws('svc_gamma', (BE,), torch.float64)
+        K = self.ws('svc_K', (BE, n_pad, n_pad))
+        perm = self.ws('svc_perm', (BE, n_pad), I32)
+        off = self.ws('svc_off', (BE, ncls + 1), I32)
+        sqn = self.ws('svc_sqn', (BE, n_pad), torch.float64)
+        info = self.ws('bag_info', (BE, npair, 2), I32)
+        npool_dev = ctypes_int_ptr(pk.iaddr(o_npool))
+        nte_dev = ctypes_int_ptr(pk.iaddr(o_nte))
+        ypool_dev = ctypes_int_ptr(pk.iaddr(o_ypool))
+        kid = 1 if self.decoder.endswith('rbf') else 0
+        ctx.call('cpsd_bag_gather', ptr(St), n_pad, kcap * n_pad, ptr(Ste), n_te_max, kcap * n_te_max,
+                 ypool_dev, ypool_ld, ptr(idx_d), n_pad, ptr(k2), npool_dev, nte_dev, E, kb, ptr(St_b),
+                 n_pad, ptr(Ste_b), n_te_max, ptr(y_b), ptr(k_b), ptr(n_b), ptr(nte_b), B)
+        ctx.call('cpsd_svc_kernel_matrix', ptr(St_b), n_pad, kb * n_pad, ptr(k_b), 0, ptr(n_b), 0, n_pad,
+                 ptr(y_b), n_pad, ptr(self.classes_dev), ncls, kid, self.svc_gamma, ptr(gam), ptr(perm),
+                 ptr(off), ptr(sqn), ptr(K), n_pad, n_pad * n_pad, BE)
+        ctx.call('cpsd_svc_fit_ovo', ptr(K), n_pad, n_pad * n_pad, ptr(perm), ptr(off), ptr(n_b), 0, ncls,
+                 self.Csvm, int(self.class_weight == 'balanced'), self.svc_tol, self.svc_max_iter,
+                 ptr(coef), n_pad, ptr(rho), ptr(info), m_max, BE)
+        ctx.call('cpsd_svc_predict_ovo', ptr(St_b), n_pad, kb * n_pad, ptr(Ste_b), n_te_max,
+                 kb * n_te_max, ptr(k_b), 0, ptr(n_b), 0, n_pad, ptr(nte_b), n_te_max, ptr(y_b), n_pad,
+                 ptr(self.classes_dev), ncls, kid, ptr(gam), ptr(coef), n_pad, ptr(rho), ptr(yhat_b),
+                 ptr(None), kb, BE)
+        ctx.call('cpsd_bag_vote', ptr(yhat_b), E, ptr(self.classes_dev), ncls, nte_dev, n_te_max,
+                 ptr(yhat), B)
+        self._bag_keep = idx_d
+        return yhat
+
     # ------------------------------------------------------------------ MCCA batch
     def _batch_mcca_gen(self, batch, want_details, align_only, pk):
         """Generator: runs the host packing + table upload, yields once, then launches."""
         ctx, T, P, Cm = self.ctx, self.T, self.P, self.Cmax
         B = len(batch)
-        Q = int(self.n_comp)
         joint = self.method == 'jointpca'
+        jvar = joint and self.joint_var
+        Q = int(self._joint_qcap) if jvar else int(self.n_comp)
         use_rank = (0 < self.pca_var < 1) and not joint
         R = Q if use_rank else Cm      # pca_var == 1: no rank reduction (mvlearn _mcca_gevp)
         tv = self.views[0]
@@ -1433,7 +1558,7 @@ class CVEngine:
             St = self.ws('pool_St', (B, kcap, n_pad))
             k2 = self.ws('pool_k2', (B,), I32)
             W, info, r_svm = self._svm_stage(pk, B, St, None, k2, kcap, n_pad, n_pool, n_te, o_ypool,
-                                             n_pad, o_nte, n_te_max, ypool)
+                                             n_pad, o_nte, n_te_max, ypool, batch=batch)
             d_svm = pk.add_descs(r_svm)
         pk.upload()
         self.stats['host_pack_ms'] = self.stats.get('host_pack_ms', 0.0) + \
@@ -1472,7 +1597,8 @@ class CVEngine:
                 # (7 power iterations, random start: decomposition/_pca.py 'auto' policy), so
                 # the trailing noise-floor components are not defined to better than that
                 jtol = self.topk_tol if nJ <= 1000 else max(self.topk_tol, 1e-3)
-                got = yield from self.eig_topk(covj, nJ_pad, nj_dev, B, mj, evj, 'joint', float(Q), 3,
+                jthr, jmode = (float(self.n_comp), 0) if jvar else (float(Q), 3)
+                got = yield from self.eig_topk(covj, nJ_pad, nj_dev, B, mj, evj, 'joint', jthr, jmode,
                                                nJ_pad, kj, tol=jtol,
                                                gap_tol=None if nJ <= 1000 else float('inf'))
                 if got is not None:
@@ -1480,6 +1606,9 @@ class CVEngine:
             if Vj is None:
                 evj, Vj = self.eig_any(covj, nJ_pad, nj_dev, 0, B, 'jointf', ncols=_ceil(Q, 64))
                 ldvj, sVj = nJ_pad, nJ_pad * nJ_pad
+                if jvar:
+                    ctx.call('cpsd_select_k', ptr(evj), nJ_pad, nj_dev, 0, float(self.n_comp), 0, 1,
+                             1 << 30, ptr(kj), 1, B)
             rhs = self.ws('j_rhs', (B * P, Cm, Q), torch.float64)
             coff_dev = self.ws('j_coff', (P + 1,), I32)
             coff_dev.copy_(torch.from_numpy(coff.astype(np.int32)).pin_memory(), non_blocking=True)
@@ -1494,10 +1623,13 @@ class CVEngine:
                 ctx.call('cpsd_chol_solve_f64', ptr(Gj, int(coff[v]) * nJ + int(coff[v])), nJ, nJ * nJ, C,
                          ptr(rhs, v * Cm * Q), Q, P * Cm * Q, Q, ptr(L, v * Cm * Q), Q, P * Cm * Q,
                          ptr(stj, v), B)
+            if jvar:       # every fold keeps its own component count
+                ctx.call('cpsd_mask_cols', ptr(L), Q, Cm * Q, Cm, Q, ptr(kj), P, B * P)
             if align_only:
                 torch.cuda.synchronize(self.ctx.device)
                 return dict(loadings=L.view(B, P, Cm, Q).cpu().numpy(), shared=[s_.copy() for s_ in shared],
-                            evals=evj[:, :Q].cpu().numpy(), status=stj.cpu().numpy())
+                            evals=evj[:, :Q].cpu().numpy(), status=stj.cpu().numpy(),
+                            k=kj.cpu().numpy() if jvar else np.full(B, Q))
         else:
             # signal ranks (cross ranks are fold-invariant and come with the int table)
             ctx.call('cpsd_copy_rows', ctypes_int_ptr(pk.iaddr(o_rank)), B * P, 0, ptr(rank_dev),
@@ -1591,6 +1723,11 @@ class CVEngine:
         k2h = k2.cpu().numpy()
         st = status.cpu().numpy()
         self._check_decoder(info, B)
+        if jvar:
+            kjh = kj.cpu().numpy()
+            if (kjh > Q).any():
+                raise RuntimeError('JointPCA: a fold keeps %d components, above the batch layout of %d '
+                                   'columns; pass joint_cap=%d' % (int(kjh.max()), Q, int(kjh.max()) + 4))
         if st.any():
             raise ValueError('MCCA: n_components=%d exceeds the total signal rank in fold(s) %s'
                              % (Q, np.nonzero(st)[0].tolist()))
@@ -1602,6 +1739,7 @@ class CVEngine:
                 loadings=L.view(B, P, Cm, Q).cpu().numpy(), evals_joint=evj[:, :Q].cpu().numpy(),
                 pool_evals=evals.cpu().numpy(), svm_info=info.cpu().numpy(), W=_w_host(W),
                 n_pool=list(n_pool), shared=[s.copy() for s in shared], lsq_status=stj.cpu().numpy(),
+                k_joint=kj.cpu().numpy() if jvar else np.full(B, Q),
                 bj_sweeps=None if sweeps is None else sweeps.cpu().numpy()[B:2 * B])
         elif want_details:
             res['details'] = dict(
@@ -1621,6 +1759,8 @@ class CVEngine:
 def _w_host(W):
     """Decoder state for the details dict: OvR weights, or the C-SVC's coef / rho / gamma."""
     if isinstance(W, dict):
+        if W.get('bag'):
+            return {}
         return {k: W[k].cpu().numpy() for k in ('coef', 'rho', 'gamma')}
     return W.cpu().numpy()
 

@@ -276,7 +276,7 @@ def batch_cca_gen(eng, batch, want_details):
     St = eng.ws('pool_St', (B, kcap, n_pad))
     k2 = eng.ws('pool_k2', (B,), I32)
     W, info, r_svm = eng._svm_stage(pk, B, St, None, k2, kcap, n_pad, n_pool, n_te, o_ypool, n_pad,
-                                    o_nte, n_te_max, ypool)
+                                    o_nte, n_te_max, ypool, batch=batch)
     d_svm = pk.add_descs(r_svm)
     pk.upload()
     yield 'host'

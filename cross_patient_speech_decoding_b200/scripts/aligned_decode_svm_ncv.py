@@ -207,16 +207,12 @@ def run(inputs, run_units=None):
         y_pred_mine = res['y_pred']
     elif pool_train:
         # joint PCA: the script's set_params hands n_comp = 0.9 (a variance fraction) to
-        # JointPCA(n_components=...) (:186-190, :372-375, :416); the batched engine takes a fixed
-        # component count only, so this branch goes fold by fold through the drop-in classes
-        from ..alignment.JointPCA import JointPCA
-        from ..decoders.cross_pt_decoders import crossPtDecoder_jointDimRed
-        y_pred_mine = []
-        for tr, te in my_units:
-            model = crossPtDecoder_jointDimRed(cross, make_clf(), JointPCA, n_comp=param_grid['n_comp'],
-                                               tar_in_train=tar_in_train)
-            model.fit(D_tar[tr], lab_tar[tr], y_align=lab_tar_full[tr])
-            y_pred_mine.append(model.predict(D_tar[te]))
+        # JointPCA(n_components=...) (:186-190, :372-375, :416); the batched engine sizes the batch
+        # from a fit on all trials and cuts every fold at its own component count
+        res = run_units((D_tar, lab_tar, lab_tar_full), cross, my_units, method='jointpca',
+                        n_comp=param_grid['n_comp'], tar_in_train=tar_in_train, use_tensor_cores=True,
+                        max_batch=148, **dec_kw) if my_units else {'y_pred': []}
+        y_pred_mine = res['y_pred']
     else:
         # single-patient branch (:406-428): DimRedReshape(PCA(0.8)) -> decoder on the raw trials
         y_pred_mine = []

@@ -63,6 +63,11 @@ int cpsd_sum_mats_f64(const double* base, const double* mats, long long mat_stri
  * means of spatial_avg_data (processing_utils/spatial_avg_subsampling.py:74-96) */
 int cpsd_gather_channels(const float* src, int lds, const int* idx, int nidx, float* dst, int ldd,
                          long long nrows, cudaStream_t stream);
+/* zero the columns j >= k_dev[p / group] of every problem's (rows x cols) matrix: JointPCA read-in
+ * matrices when n_components is a variance fraction (alignment/JointPCA.py:199 with the script's
+ * n_comp = 0.9, scripts/aligned_decode_svm_ncv.py:186-190) */
+int cpsd_mask_cols(float* M, int ld, long long stride, int rows, int cols, const int* k_dev, int group,
+                   int nprob, cudaStream_t stream);
 /* dst[i] = src[idx[i]] over the trial axis (rows of TC = time x channels floats): the random
  * trial subsets of scripts/aligned_decode_cross_patient_subsample.py:303-312 on resident data */
 int cpsd_gather_trials(const float* src, long long TC, const int* idx, int n, float* dst,
@@ -334,6 +339,19 @@ int cpsd_svc_predict_ovo(const float* St, int lds, long long strideS, const floa
                          int ldy, const int* classes, int ncls, int kernel, const double* gamma,
                          const double* coef, int ldc, const double* rho, int* yhat, double* dec,
                          int k_max, int nfold, cudaStream_t stream);
+/* Bagging around the C-SVC (BaggingClassifier(estimator=SVC(kernel='linear'), n_estimators=10),
+ * scripts/aligned_decode_svm.py:262-265): cpsd_bag_gather makes n_est bootstrap problems per fold
+ * (resampled training scores and labels from the index table idx[fold * n_est + e][t], the fold's
+ * test scores and sizes copied) that run through cpsd_svc_kernel_matrix / fit / predict as
+ * nfold * n_est folds; cpsd_bag_vote takes the majority vote of the estimators' labels (first
+ * maximum in class order, numpy argmax over BaggingClassifier.predict_proba's vote counts) */
+int cpsd_bag_gather(const float* St, int lds, long long strideS, const float* Ste, int ldt,
+                    long long strideT, const int* y, int ldy, const int* idx, int ldi,
+                    const int* k_dev, const int* n_dev, const int* nte_dev, int n_est, int kb,
+                    float* St_b, int lds_b, float* Ste_b, int ldt_b, int* y_b, int* k_b, int* n_b,
+                    int* nte_b, int nfold, cudaStream_t stream);
+int cpsd_bag_vote(const int* yhat_b, int n_est, const int* classes, int ncls, const int* nte_dev,
+                  int n_te_max, int* yhat, int nfold, cudaStream_t stream);
 
 /* fused per-trial predict of a fitted cross-patient decoder (crossPtDecoder.predict,
  * decoders/cross_pt_decoders.py:70-71,444: aligner.transform(X, idx=0) -> DimRedReshape/PCA

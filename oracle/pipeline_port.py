@@ -161,7 +161,8 @@ def pool_none(Xtr, ytr, cross, n_comp):
 
 
 def run_fold(target, cross, train, test, method='mcca', n_comp=None, regs=0.5, pca_var=0.8,
-             decoder_var=0.8, C=1.0, decoder='linear', class_weight=None):
+             decoder_var=0.8, C=1.0, decoder='linear', class_weight=None, bag_random_state=None,
+             n_estimators=10):
     """One unit of scripts/aligned_decode_svm_ncv.py:344-442 with the pinned decoder
     DimRedReshape(PCA, decoder_var) -> LinearSVC(dual=False) (DimRedReshape.py:36-65).
     Returns (y_pred, k2)."""
@@ -193,6 +194,13 @@ def run_fold(target, cross, train, test, method='mcca', n_comp=None, regs=0.5, p
     if decoder == 'linear':
         from oracle.svm_exact import oracle_linear_svc
         svm = oracle_linear_svc(C)     # liblinear primal, certified / re-solved per class
+    elif decoder.startswith('bag_'):
+        # scripts/aligned_decode_svm.py:262-265: BaggingClassifier(estimator=SVC(kernel='linear'),
+        # n_estimators=10); random_state=None there (seeds from numpy's global RNG at fit time)
+        from sklearn.ensemble import BaggingClassifier
+        from sklearn.svm import SVC
+        svm = BaggingClassifier(estimator=SVC(kernel=decoder.split('_')[-1], C=C, class_weight=class_weight),
+                                n_estimators=n_estimators, random_state=bag_random_state)
     else:
         # the scripts' literal decoder (scripts/aligned_decode_svm_ncv.py:313-317: rbf, balanced;
         # aligned_decode_svm.py:262: linear) -- sklearn's SVC is libsvm itself
