@@ -1099,11 +1099,11 @@ class CVEngine:
                        n_te_max, yhat):
         """BaggingClassifier(estimator=SVC(kernel), n_estimators) per fold
         (scripts/aligned_decode_svm.py:262-265): the bootstrap sample of estimator e of fold f is
-        sklearn's own index stream for seed[f][e] (``_generate_bagging_indices``: the feature draw
-        -- all features, a permutation -- comes first, so the stream depends on the decoder-PCA
+        sklearn's index stream for seed[f][e] (``_generate_bagging_indices``: the feature draw --
+        all features, a permutation -- comes first, so the stream depends on the decoder-PCA
         component count); the resampled problems run as B * n_estimators folds of the C-SVC
         kernels, their labels are combined by majority vote."""
-        from sklearn.ensemble._bagging import _generate_bagging_indices
+        from sklearn.utils.random import sample_without_replacement
         ctx = self.ctx
         ncls = len(self.classes)
         E = self.n_estimators
@@ -1113,8 +1113,12 @@ class CVEngine:
         for f in range(B):
             kf, nf = int(k2h[f]), int(n_pool[f])
             for e in range(E):
-                _, si = _generate_bagging_indices(int(seeds[f][e]), False, True, kf, nf, kf, nf)
-                idx[f * E + e, :nf] = si
+                # sklearn/ensemble/_bagging.py::_generate_bagging_indices with bootstrap_features=
+                # False, bootstrap=True, max_features = all, max_samples = all: the feature draw (a
+                # permutation of all features, irrelevant to the kernels) consumes the stream first
+                rs = np.random.RandomState(int(seeds[f][e]))
+                sample_without_replacement(kf, kf, random_state=rs)
+                idx[f * E + e, :nf] = rs.randint(0, nf, nf)
         fe = np.repeat(np.arange(B), E)
         yb = ypool[fe[:, None], idx]
         valid = np.arange(n_pad)[None, :] < np.asarray(n_pool)[fe][:, None]
