@@ -196,6 +196,169 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def measure_tf32_peak(dev):
+    """TF32 dense matmul throughput of this GPU, measured the way MEASURED_PEAKS.json measured
+    bf16 (torch.matmul 8192^3, best of 5, CUDA events): the denominator SURVEY 8(d) asks for the
+    Gram kernels.  Library call, outside every timed region."""
+    import torch
+    try:
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        n = 8192
+        a = torch.randn((n, n), device=dev, dtype=torch.float32)
+        b = torch.randn((n, n), device=dev, dtype=torch.float32)
+        torch.matmul(a, b)
+        best = 1e30
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            best = min(best, e0.elapsed_time(e1))
+        torch.backends.cuda.matmul.allow_tf32 = old
+        del a, b
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    except Exception:
+        return None
+
+
+def load_traffic():
+    """profiles/traffic.json: {kernel: {'dram_bytes': read + write of one ncu --set full capture,
+    'folds': folds of that launch, 'source': file}} written by profiles/summarize.py."""
+    try:
+        return json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
+    except Exception:
+        return {}
+
+
+def scaled_traffic(traffic, kernel, nfolds, also=None):
+    tot = 0.0
+    for k in (kernel, also):
+        if k is None:
+            continue
+        t = traffic.get(k)
+        if not t:
+            return None
+        tot += float(t['dram_bytes']) / float(t['folds']) * nfolds
+    return tot
+
+
+def predict_latency(pts):
+    """BASELINE configs[4]: per-call latency of the fitted config-2 model from host float64 trials
+    to labels (decoders.fused_predict.FusedPredictor: one upload, one kernel, one read-back), batch
+    1 and 256, wall clock per call, p50 / p99."""
+    try:
+        from sklearn.pipeline import make_pipeline
+        from cross_patient_speech_decoding_b200.alignment.AlignMCCA import AlignMCCA
+        from cross_patient_speech_decoding_b200.decoders.cross_pt_decoders import crossPtDecoder_mcca
+        from cross_patient_speech_decoding_b200.decoders.fused_predict import FusedPredictor
+        from cross_patient_speech_decoding_b200.decomposition.DimRedReshape import DimRedReshape
+        from cross_patient_speech_decoding_b200.decomposition.PCA import PCA
+        from cross_patient_speech_decoding_b200.svm import LinearSVC
+        Xt, yt, yat = pts[0]
+        tr, te = step_folds(yt, 0)[0]
+        m = crossPtDecoder_mcca(pts[1:], make_pipeline(DimRedReshape(PCA, n_components=0.8), LinearSVC()),
+                                AlignMCCA, n_comp=30, regs=0.5, pca_var=0.8)
+        m.fit(Xt[tr], yt[tr], y_align=yat[tr])
+        fp = FusedPredictor(m)
+        out = {'api': 'decoders.fused_predict.FusedPredictor.predict (host float64 trials -> labels)'}
+        for nb in (1, 256):
+            Xb = np.ascontiguousarray(np.concatenate([Xt] * 2)[:nb])
+            for _ in range(10):
+                fp.predict(Xb)
+            ts = []
+            for _ in range(300 if nb == 1 else 60):
+                t0 = time.perf_counter()
+                fp.predict(Xb)
+                ts.append(1e3 * (time.perf_counter() - t0))
+            out['batch%d' % nb] = {'p50_ms': round(float(np.percentile(ts, 50)), 4),
+                                   'p99_ms': round(float(np.percentile(ts, 99)), 4),
+                                   'trials_per_s': round(nb / (np.median(ts) * 1e-3), 1)}
+        return out
+    except Exception as e:                                   # the probe never breaks the headline line
+        return {'error': str(e)[:120]}
+
+
+def run_other_config(args, rank, world, local, pts):
+    """BASELINE configs[2] / configs[3] through the PRODUCT API, sharded over the ranks the way the
+    scripts are (whole CV iterations / subsamples per rank, one all_gather of the labels)."""
+    import torch
+    import torch.distributed as dist
+    from cross_patient_speech_decoding_b200 import cv_align_decode, sharding
+    dev = torch.device('cuda', local)
+
+    def timed(fn):
+        fn(True)                                            # warm-up with the same structure
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        n = fn(False)
+        torch.cuda.synchronize(dev)
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return n, float(dt.item())
+
+    lines = []
+    y0 = pts[0][1]
+    if args.config == 'sweep':
+        n_iter = args.steps * world                          # weak scaling: `steps` iterations per GPU
+        for method in args.methods.split(','):
+            for d in [int(x) for x in args.dims.split(',')]:
+                units = []
+                for it in range(n_iter):
+                    units += step_folds(y0, 5000 + it)
+                mine = sharding.shard_units(len(units), N_FOLDS, rank, world)
+                kw = dict(method=method, n_comp=d, use_tensor_cores=True, max_batch=args.batch)
+                if method == 'mcca':
+                    kw.update(regs=0.5, pca_var=0.8)
+
+                def go(warm, kw=kw, units=units, mine=mine):
+                    mu = [units[u] for u in (mine[:2 * N_FOLDS] if warm else mine)]
+                    res = cv_align_decode(pts[0], pts[1:], mu, **kw)
+                    sharding.gather_predictions(mine[:len(mu)], res['y_pred'])
+                    return len(units)
+                try:
+                    n, dt = timed(go)
+                    lines.append({'workload': 'config3 sweep: 8 patients, %s, n_comp=%d, 20-fold' % (method, d),
+                                  'folds': n, 'value': n / dt})
+                except ValueError as e:                      # MCCA n_components above the summed ranks
+                    lines.append({'workload': 'config3 sweep: %s n_comp=%d' % (method, d), 'error': str(e)[:80]})
+    else:
+        from cross_patient_speech_decoding_b200.processing_utils.grid_subsampling import sig_channels_in_windows
+        from cross_patient_speech_decoding_b200.processing_utils.subsample_decode import subsample_decode
+        chan_map, sig = np.arange(1, 129).reshape(8, 16), np.arange(1, 129)
+        subs = [np.sort(np.asarray(s_).ravel()) for s_ in sig_channels_in_windows(chan_map, sig, (4, 8), (2, 4))]
+        nsub = args.steps * world                            # subsamples per target, dealt to the ranks
+
+        def go(warm):
+            tot = 0
+            for tgt in range(1 if warm else N_PATIENTS):
+                order = [tgt] + [p for p in range(N_PATIENTS) if p != tgt]
+                np.random.seed(300 + tgt)
+                pick = [subs[i % len(subs)] for i in range(2 * world if warm else nsub)]
+                out = subsample_decode(pts[order[0]], [pts[p] for p in order[1:]], pick, [subs] * 7,
+                                       n_folds=N_FOLDS, method='cca', n_comp=0.9, use_tensor_cores=True,
+                                       max_batch=args.batch, depth=6)
+                tot += N_FOLDS * len(out['accs'])
+            return tot
+        n, dt = timed(go)
+        lines.append({'workload': 'config4 electrode subsampling: %d grid subsamples (32 of 128 channels) x 8 '
+                                  'targets x 20 folds, pairwise CCA, host patients uploaded per target' % nsub,
+                      'folds': n, 'value': n / dt})
+    if rank == 0:
+        for ln in lines:
+            out = {'metric': METRIC, 'unit': 'folds/s', 'n_gpus': world, 'steps': args.steps,
+                   'warmup': 1, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                   'dtype': 'f32', 'data': 'synthetic', 'config': {'workload': ln.pop('workload')},
+                   'timing': 'wall clock between device synchronisations, max over ranks, product API '
+                             '(host arrays in, labels out)'}
+            out.update(ln)
+            print(json.dumps(out), flush=True)
+
+
 # ------------------------------------------------------------------------------------ ours
 def main():
     ap = argparse.ArgumentParser()
@@ -208,6 +371,13 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=None)
     ap.add_argument('--e2e-depth', type=int, default=8, help='steps in flight in the e2e measurement')
     ap.add_argument('--batch', type=int, default=148, help='max folds per engine batch')
+    ap.add_argument('--config', default='headline', choices=['headline', 'sweep', 'subsample'],
+                    help='headline = BASELINE configs[1] (the driver\'s run); sweep = configs[2] (latent-size '
+                         'sweep x methods); subsample = configs[3] (electrode subsampling); the last two run '
+                         'through the product API sharded over the ranks')
+    ap.add_argument('--dims', default='10,30,60,100', help='--config sweep: latent sizes')
+    ap.add_argument('--methods', default='jointpca,cca,mcca', help='--config sweep: alignment methods')
+    ap.add_argument('--no-latency', action='store_true', help='skip the config-5 predict latency probe')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -216,6 +386,20 @@ def main():
         run_reference(args, rank)
         return
 
+    # cpu_baseline: rank 0, N = 1 only, before any GPU work is queued (at N > 1 the other ranks
+    # would spin in a barrier on the same host cores and contaminate it; the driver's own
+    # --impl reference arm covers every N)
+    cpu_line = None
+    if rank == 0 and world == 1 and args.config == 'headline' and args.cpu_folds > 0:
+        pts_cpu = make_data()
+        cpu_sample(pts_cpu, 1, 12345)            # warm-up (imports, BLAS threads)
+        cpu_val, cpu_dt, cpu_acc = cpu_sample(pts_cpu, args.cpu_folds, 0)
+        cpu_line = {'value': cpu_val, 'unit': 'folds/s', 'cores': blas_threads(), 'kind': 'port',
+                    'accuracy': cpu_acc,
+                    'sample': '%d folds of the same 8-patient 20-fold workload, oracle/pipeline_port.py '
+                              '(numpy/scipy/sklearn float64), %.1f s, timed before any GPU work'
+                              % (args.cpu_folds, cpu_dt)}
+        del pts_cpu
     import torch
     import torch.distributed as dist
     import __graft_entry__
@@ -230,6 +414,12 @@ def main():
 
     pts = make_data()
     y0 = pts[0][1]
+    if args.config != 'headline':
+        run_other_config(args, rank, world, local, pts)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     kw = dict(method='mcca', n_comp=30, regs=0.5, pca_var=0.8, decoder_var=0.8,
               use_tensor_cores=not args.no_tc, max_batch=args.batch)
     eng = CVEngine(pts[0], pts[1:], device='cuda:%d' % local, **kw)
@@ -349,6 +539,8 @@ def main():
     eng.profile = False
     stages = {k: v * N_FOLDS / nprof for k, v in stages_batch.items()}
     pk, pk_kind = peaks()
+    tf32_peak = measure_tf32_peak(dev)
+    traffic = load_traffic()
     n_all = 1152
     F = 200 * 30
     stage_total = sum(stages_batch.values()) or 1.0
@@ -363,29 +555,41 @@ def main():
                 else 'k_gram_nt (pooled Gram, fp32 SIMT)',
                 'bound': 'tensor', 'achieved': gram_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
                 'frac': gram_tf / peak_tf,
-                # dram__bytes_read + write of one `ncu --set full` capture (profiles/
-                # ncu_r1_k_gram_tc.txt: 7.48 GB per 107-fold launch), scaled to this launch
-                'traffic': 7.478e9 / 107 * nprof,
-                'peak_source': '%s bf16_tflops_sustained (TF32 dense is nominally half of it; '
-                               '3xTF32 issues 3 MMAs per algorithmic product)' % pk_kind,
+                # dram__bytes_read + write per fold from the committed ncu capture
+                # (profiles/traffic.json, written by profiles/summarize.py), times this launch's folds
+                'traffic': scaled_traffic(traffic, 'k_gram_tc', nprof, also='k_split_tf32_batched'),
+                'peak_source': '%s bf16_tflops_sustained (MEASURED_PEAKS.json)' % pk_kind,
+                # the pipe this kernel runs on: TF32 dense peak measured in this run (torch.matmul,
+                # allow_tf32, 8192^3, best of 5); 3xTF32 issues 3 MMAs per algorithmic product and only
+                # the 45 upper tiles of the 9 x 9 tile grid are computed
+                'tf32_dense_tflops_measured': tf32_peak,
+                'frac_of_tf32_peak': (gram_tf / tf32_peak) if tf32_peak else None,
+                'executed_tf32_tflops': gram_tf * 3.0 * 45.0 / 81.0,
+                'executed_frac_of_tf32_peak': (gram_tf * 3.0 * 45.0 / 81.0 / tf32_peak) if tf32_peak else None,
                 'algorithmic_flops_per_launch': gram_flops, 'launch_ms': gram_ms,
                 'share_of_step': gram_ms / stage_total}
+    proj_traffic = scaled_traffic(traffic, 'k_proj_tc', nprof)
+    # compulsory traffic of the launch: X hi/lo once + every pooled matrix written once
+    proj_real = proj_traffic if proj_traffic else (2 * sum(p[0].size for p in pts) * 4 + nprof * n_all * F * 4)
     roofline_hbm = {'kernel': 'k_proj_tc_prep + k_proj_tc (project all trials of all patients into the '
                               'pooled matrices, tcgen05 3xTF32 + TMA)',
-                    'traffic': 3.209e9 / 107 * nprof,
-                    'note': 'achieved counts SURVEY 8(d) algorithmic bytes (every fold reads every '
-                            'patient once and writes its pooled matrix); the kernel shares each X '
-                            'tile between all folds of the batch, so its real DRAM traffic '
-                            '(`traffic`, ncu) is ~5x lower',
-                    'bound': 'hbm', 'achieved': proj_bytes / (proj_ms * 1e-3) / 1e9,
+                    'traffic': proj_traffic,
+                    'bound': 'hbm', 'achieved': proj_real / (proj_ms * 1e-3) / 1e9,
                     'peak': pk['hbm_gbs'], 'unit': 'GB/s',
-                    'frac': proj_bytes / (proj_ms * 1e-3) / 1e9 / pk['hbm_gbs'],
-                    'algorithmic_bytes_per_launch': proj_bytes, 'launch_ms': proj_ms,
-                    'share_of_step': proj_ms / stage_total}
+                    'frac': proj_real / (proj_ms * 1e-3) / 1e9 / pk['hbm_gbs'],
+                    'note': 'achieved = the DRAM bytes the kernel really moves (ncu dram read + write of '
+                            'the committed capture, scaled to this launch; X hi/lo once + the pooled '
+                            'matrices once) / its CUDA-event time.  SURVEY 8(d) counts every fold '
+                            're-reading every patient (`survey_bytes_per_launch`, `survey_gbs`): the '
+                            'kernel shares each X tile between all folds of the batch instead',
+                    'survey_bytes_per_launch': proj_bytes,
+                    'survey_gbs': proj_bytes / (proj_ms * 1e-3) / 1e9,
+                    'launch_ms': proj_ms, 'share_of_step': proj_ms / stage_total}
 
+    latency = None
+    if rank == 0 and world == 1 and not args.no_latency:
+        latency = predict_latency(pts)
     if rank == 0:
-        cpu_sample(pts, 1, 12345)            # warm-up (imports, BLAS threads)
-        cpu_val, cpu_dt, cpu_acc = cpu_sample(pts, args.cpu_folds, 0)
         line = {
             'metric': METRIC, 'value': value, 'unit': 'folds/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_max / args.steps,
@@ -422,11 +626,10 @@ def main():
             % (eng.stats.get('view_solves', 0), eng.stats.get('view_problems', 0)),
             'accuracy_mean': float(np.mean(acc_all)),
             'host_pack_ms_per_step': round(host_pack_timed / args.steps, 3),
-            'cpu_baseline': {'value': cpu_val, 'unit': 'folds/s', 'cores': blas_threads(),
-                             'kind': 'port', 'accuracy': cpu_acc,
-                             'sample': '%d folds of the same 8-patient 20-fold workload, '
-                                       'oracle/pipeline_port.py (numpy/scipy/sklearn float64), '
-                                       '%.1f s' % (args.cpu_folds, cpu_dt)},
+            'cpu_baseline': cpu_line or {'value': None, 'unit': 'folds/s', 'cores': blas_threads(),
+                                         'kind': 'port', 'sample': 'measured at N = 1 only (rank 0)'},
+            'predict_latency': latency,
+            'svm_unconverged': int(eng.stats.get('svm_unconverged', 0)),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
