@@ -25,9 +25,11 @@ namespace {
 using namespace tc;
 
 constexpr int PT_BM = 128;                 // rows per tile
-constexpr int PT_N = 32;                   // latent columns (padded)
+constexpr int PT_N = 32;                   // latent columns per MMA (wider latents run as chunks of 32)
 constexpr int PT_BK = 32;                  // fp32 per 128-byte swizzle row
-constexpr int PT_KB = 4;                   // k-blocks: channels <= 128
+constexpr int PT_KB = 4;                   // k-blocks per resident X panel: 128 channels
+constexpr int PT_MAXC = 256;               // channels per patient: two panels, the second adds to Y
+constexpr int PT_MAXQ = 128;               // latent columns: four chunks
 constexpr int PT_A_TILE = PT_BM * PT_BK * 4;          // 16 KB
 constexpr int PT_B_TILE = PT_N * PT_BK * 4;           // 4 KB
 constexpr int PT_A_BYTES = PT_KB * 2 * PT_A_TILE;     // 128 KB
@@ -41,12 +43,14 @@ constexpr uint32_t PT_TMEM_COLS = 64;      // two 32-column accumulator stages
 
 struct ProjTcParams {
   int P, B, T, Q;
+  int nq;                // latent chunks of 32 columns (Q <= 32: 1)
+  int ltc;               // columns of the L^T arrays (128 or 256)
   int n_max;             // trials per patient in the destination table (row stride)
   int fg, ngroups;       // folds per group, groups per tile
   int ntile_total;
   int tile_prefix[PT_MAXP + 1];
   int nrows[PT_MAXP];    // N_v * T
-  int kblocks[PT_MAXP];  // ceil(C_v / 32)
+  int kblocks[PT_MAXP];  // ceil(C_v / 32), up to 8
   long long strideY;     // floats between the pooled matrices of consecutive folds
 };
 
@@ -110,27 +114,32 @@ k_proj_tc(const CUtensorMap* __restrict__ xmaps, const CUtensorMap* __restrict__
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t it_a = 0, it_b = 0;
-      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it_a) {
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         int v, tile, f0, f1;
         decode(item, v, tile, f0, f1);
-        const int kbn = prm.kblocks[v];
         const CUtensorMap* mh = xmaps + 2 * v;
         const CUtensorMap* ml = mh + 1;
-        mbar_wait(a_empty, (it_a & 1u) ^ 1u);
-        mbar_expect_tx(a_full, (uint32_t)(kbn * 2 * PT_A_TILE));
-        for (int kb = 0; kb < kbn; ++kb) {
-          tma_load_2d(sA + (kb * 2) * PT_A_TILE, mh, kb * PT_BK, tile * PT_BM, a_full);
-          tma_load_2d(sA + (kb * 2 + 1) * PT_A_TILE, ml, kb * PT_BK, tile * PT_BM, a_full);
-        }
-        for (int f = f0; f < f1; ++f, ++it_b) {
-          const int s = it_b & 1;
-          mbar_wait(&b_empty[s], ((it_b >> 1) & 1u) ^ 1u);
-          mbar_expect_tx(&b_full[s], (uint32_t)(kbn * 2 * PT_B_TILE));
-          uint8_t* st = sB + s * PT_B_STAGE;
-          const int brow = (f * prm.P + v) * PT_N;
+        // channel panels of <= 128 channels: the X panel stays in shared memory while the
+        // loadings of every (fold, latent chunk) of the group stream past it
+        for (int kb0 = 0; kb0 < prm.kblocks[v]; kb0 += PT_KB, ++it_a) {
+          const int kbn = min(PT_KB, prm.kblocks[v] - kb0);
+          mbar_wait(a_empty, (it_a & 1u) ^ 1u);
+          mbar_expect_tx(a_full, (uint32_t)(kbn * 2 * PT_A_TILE));
           for (int kb = 0; kb < kbn; ++kb) {
-            tma_load_2d(st + (kb * 2) * PT_B_TILE, ltmaps, kb * PT_BK, brow, &b_full[s]);
-            tma_load_2d(st + (kb * 2 + 1) * PT_B_TILE, ltmaps + 1, kb * PT_BK, brow, &b_full[s]);
+            tma_load_2d(sA + (kb * 2) * PT_A_TILE, mh, (kb0 + kb) * PT_BK, tile * PT_BM, a_full);
+            tma_load_2d(sA + (kb * 2 + 1) * PT_A_TILE, ml, (kb0 + kb) * PT_BK, tile * PT_BM, a_full);
+          }
+          for (int vf = f0 * prm.nq; vf < f1 * prm.nq; ++vf, ++it_b) {
+            const int f = vf / prm.nq, qc = vf - f * prm.nq;
+            const int s = it_b & 1;
+            mbar_wait(&b_empty[s], ((it_b >> 1) & 1u) ^ 1u);
+            mbar_expect_tx(&b_full[s], (uint32_t)(kbn * 2 * PT_B_TILE));
+            uint8_t* st = sB + s * PT_B_STAGE;
+            const int brow = ((f * prm.P + v) * prm.nq + qc) * PT_N;
+            for (int kb = 0; kb < kbn; ++kb) {
+              tma_load_2d(st + (kb * 2) * PT_B_TILE, ltmaps, (kb0 + kb) * PT_BK, brow, &b_full[s]);
+              tma_load_2d(st + (kb * 2 + 1) * PT_B_TILE, ltmaps + 1, (kb0 + kb) * PT_BK, brow, &b_full[s]);
+            }
           }
         }
       }
@@ -140,12 +149,13 @@ k_proj_tc(const CUtensorMap* __restrict__ xmaps, const CUtensorMap* __restrict__
     if (lane == 0) {
       const uint32_t idesc = idesc_tf32(PT_BM, PT_N);
       uint32_t it_a = 0, it_b = 0;
-      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it_a) {
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         int v, tile, f0, f1;
         decode(item, v, tile, f0, f1);
-        const int kbn = prm.kblocks[v];
+        for (int kb0 = 0; kb0 < prm.kblocks[v]; kb0 += PT_KB, ++it_a) {
+        const int kbn = min(PT_KB, prm.kblocks[v] - kb0);
         mbar_wait(a_full, it_a & 1u);
-        for (int f = f0; f < f1; ++f, ++it_b) {
+        for (int vf = f0 * prm.nq; vf < f1 * prm.nq; ++vf, ++it_b) {
           const int s = it_b & 1;
           const uint32_t ph = (it_b >> 1) & 1u;
           mbar_wait(&b_full[s], ph);
@@ -174,7 +184,8 @@ k_proj_tc(const CUtensorMap* __restrict__ xmaps, const CUtensorMap* __restrict__
           umma_commit(&b_empty[s]);
           umma_commit(&t_full[s]);
         }
-        umma_commit(a_empty);          // X tile free once every fold's MMAs retired
+        umma_commit(a_empty);          // X panel free once every fold's MMAs retired
+        }
       }
     }
   } else {
@@ -189,8 +200,9 @@ k_proj_tc(const CUtensorMap* __restrict__ xmaps, const CUtensorMap* __restrict__
     for (int i = 0; i < PT_N; ++i) {
       // the block has 32 Q elements = Q per lane; slots i >= Q repeat an earlier element of the
       // same lane (a benign duplicate store) so that the copy-out loop needs no validity test
-      const int e = lane + 32 * (i % Q);
-      const int r = e / Q, j = e - r * Q;
+      const int Qc = Q < PT_N ? Q : PT_N;
+      const int e = lane + 32 * (i % Qc);
+      const int r = e / Qc, j = e - r * Qc;
       rj[i] = (uint32_t)((quad * 32 + r) << 8) | (uint32_t)j;
     }
     uint32_t it_b = 0;
@@ -204,19 +216,14 @@ k_proj_tc(const CUtensorMap* __restrict__ xmaps, const CUtensorMap* __restrict__
         my_tr = R / prm.T;
         my_t = R - my_tr * prm.T;
       }
-      const int* drow = dst_row + ((long long)f0 * prm.P + v) * prm.n_max;
-      int d_next = (my_tr >= 0) ? drow[my_tr] : -1;
-      // mu L of the fold: lane j keeps column j, broadcast by shuffle in the epilogue
-      float ml_next = muL[(long long)(f0 * prm.P + v) * PT_N + lane];
-      for (int f = f0; f < f1; ++f, ++it_b) {
+      for (int kb0 = 0; kb0 < prm.kblocks[v]; kb0 += PT_KB) {
+      const bool first = kb0 == 0;       // later channel panels add to what the first one wrote
+      for (int vf = f0 * prm.nq; vf < f1 * prm.nq; ++vf, ++it_b) {
+        const int f = vf / prm.nq, qc = vf - f * prm.nq;
         const int s = it_b & 1;
-        const int d = d_next;
-        const float ml_mine = ml_next;
-        if (f + 1 < f1) {        // destination / mu L of the next fold: in flight during this one
-          drow += (long long)prm.P * prm.n_max;
-          d_next = (my_tr >= 0) ? drow[my_tr] : -1;
-          ml_next = muL[(long long)((f + 1) * prm.P + v) * PT_N + lane];
-        }
+        const int d = (my_tr >= 0) ? dst_row[((long long)f * prm.P + v) * prm.n_max + my_tr] : -1;
+        // mu L of the (fold, chunk): lane j keeps column j, broadcast by shuffle below
+        const float ml_mine = first ? muL[((long long)(f * prm.P + v) * prm.nq + qc) * PT_N + lane] : 0.f;
         mbar_wait(&t_full[s], (it_b >> 1) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint32_t vv[32];
@@ -230,20 +237,43 @@ k_proj_tc(const CUtensorMap* __restrict__ xmaps, const CUtensorMap* __restrict__
         row_off[r_own] = (d >= 0) ? (d * prm.T + my_t) * Q : -1;
         __syncwarp();
         float* Yf = Y + (long long)f * prm.strideY;
-        // all shared-memory reads first (independent), then the predicated global stores
-        int offs[PT_N];
-        float vals[PT_N];
+        if (prm.nq == 1) {
+          // all shared-memory reads first (independent), then the predicated global stores
+          int offs[PT_N];
+          float vals[PT_N];
 #pragma unroll
-        for (int i = 0; i < PT_N; ++i) {
-          const int r = (int)(rj[i] >> 8), j = (int)(rj[i] & 255u);
-          const int off = row_off[r];
-          offs[i] = (off >= 0) ? off + j : -1;
-          vals[i] = stg[r * PT_LDS + j];
+          for (int i = 0; i < PT_N; ++i) {
+            const int r = (int)(rj[i] >> 8), j = (int)(rj[i] & 255u);
+            const int off = row_off[r];
+            offs[i] = (off >= 0) ? off + j : -1;
+            vals[i] = stg[r * PT_LDS + j];
+          }
+          if (first) {
+#pragma unroll
+            for (int i = 0; i < PT_N; ++i)
+              if (offs[i] >= 0) Yf[offs[i]] = vals[i];
+          } else {
+            // (no duplicate slots here: an element is added exactly once)
+#pragma unroll
+            for (int i = 0; i < PT_N; ++i)
+              if (i < Q && offs[i] >= 0) Yf[offs[i]] += vals[i];
+          }
+        } else {
+          // wide latents: this chunk is 32 consecutive floats (128 bytes) of every output row
+          const int col = qc * PT_N + lane;
+          if (col < Q) {
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+              const int off = row_off[quad * 32 + r];
+              if (off >= 0) {
+                const float val = stg[(quad * 32 + r) * PT_LDS + lane];
+                if (first) Yf[off + col] = val; else Yf[off + col] += val;
+              }
+            }
+          }
         }
-#pragma unroll
-        for (int i = 0; i < PT_N; ++i)
-          if (offs[i] >= 0) Yf[offs[i]] = vals[i];
         __syncwarp();
+      }
       }
     }
   }
@@ -257,33 +287,53 @@ k_proj_tc(const CUtensorMap* __restrict__ xmaps, const CUtensorMap* __restrict__
   }
 }
 
-// Per problem p = fold * P + view: L^T split into tf32 hi / lo (32 x 128, zero padded) and the
-// row vector mu L.  mu of problem p lives at mu_base + slot[p] * ld_mu.
+// Per problem p = fold * P + view and latent chunk qc: 32 rows of L^T (latent columns qc*32 ..
+// qc*32+31) split into tf32 hi / lo, each row ltc floats (channels, zero padded), and the row
+// vector mu L of the chunk.  mu of problem p lives at mu_base + slot[p] * ld_mu.
 __global__ void __launch_bounds__(128)
 k_proj_tc_prep(const float* __restrict__ L, int ldl, long long strideL, const float* __restrict__ mu_base,
-               const int* __restrict__ slot, int ld_mu, const int* __restrict__ cdim, int Q,
-               float* __restrict__ LtHi, float* __restrict__ LtLo, float* __restrict__ muL) {
-  const int p = blockIdx.x;
-  const int C = min(cdim[p], PT_KB * PT_BK);
+               const int* __restrict__ slot, int ld_mu, const int* __restrict__ cdim, int Q, int nq,
+               int ltc, float* __restrict__ LtHi, float* __restrict__ LtLo, float* __restrict__ muL) {
+  const int p = blockIdx.x, qc = blockIdx.y;
+  const int C = min(cdim[p], ltc);
   const float* Lp = L + (long long)p * strideL;
   const float* mu = mu_base ? mu_base + (long long)(slot ? slot[p] : p) * ld_mu : nullptr;
-  float* hi = LtHi + (long long)p * PT_N * (PT_KB * PT_BK);
-  float* lo = LtLo + (long long)p * PT_N * (PT_KB * PT_BK);
-  for (int e = threadIdx.x; e < PT_N * PT_KB * PT_BK; e += blockDim.x) {
-    const int j = e / (PT_KB * PT_BK), c = e - j * (PT_KB * PT_BK);
+  const long long blk = (long long)p * nq + qc;
+  float* hi = LtHi + blk * PT_N * ltc;
+  float* lo = LtLo + blk * PT_N * ltc;
+  for (int e = threadIdx.x; e < PT_N * ltc; e += blockDim.x) {
+    const int j = e / ltc, c = e - j * ltc;
+    const int col = qc * PT_N + j;
     float x = 0.f;
-    if (j < Q && c < C) x = Lp[(long long)c * ldl + j];
+    if (col < Q && c < C) x = Lp[(long long)c * ldl + col];
     float h, l;
     split_tf32(x, h, l);
     hi[e] = h;
     lo[e] = l;
   }
   if (threadIdx.x < PT_N) {
-    const int j = threadIdx.x;
+    const int col = qc * PT_N + threadIdx.x;
     double a = 0.0;
-    if (mu && j < Q)
-      for (int c = 0; c < C; ++c) a = fma((double)mu[c], (double)Lp[(long long)c * ldl + j], a);
-    muL[(long long)p * PT_N + j] = (float)a;
+    if (mu && col < Q)
+      for (int c = 0; c < C; ++c) a = fma((double)mu[c], (double)Lp[(long long)c * ldl + col], a);
+    muL[blk * PT_N + threadIdx.x] = (float)a;
+  }
+}
+
+// hi / lo split of a (rows x cols) matrix (row stride lds) into arrays with row stride ldd >= cols
+// (ldd a multiple of 4 floats so that TMA can address rows; the padding columns are zeroed)
+__global__ void __launch_bounds__(256)
+k_split_2d(const float* __restrict__ src, long long lds, long long rows, int cols,
+           float* __restrict__ hi, float* __restrict__ lo, int ldd) {
+  const long long total = rows * ldd;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const long long r = e / ldd;
+    const int c = (int)(e - r * ldd);
+    float h = 0.f, l = 0.f;
+    if (c < cols) split_tf32(src[r * lds + c], h, l);
+    hi[e] = h;
+    lo[e] = l;
   }
 }
 
@@ -357,33 +407,52 @@ extern "C" int cpsd_split_tf32(const float* src, float* hi, float* lo, long long
   return CPSD_OK;
 }
 
+extern "C" int cpsd_split_tf32_2d(const float* src, long long lds, long long rows, int cols, float* hi,
+                                  float* lo, int ldd, cudaStream_t stream) {
+  CPSD_CHECK_ARG(rows >= 0 && cols > 0 && lds >= cols && ldd >= cols && (ldd & 3) == 0,
+                 "split_tf32_2d: bad dims (ldd % 4)");
+  if (rows == 0) return CPSD_OK;
+  long long nb = (rows * ldd + 255) / 256;
+  if (nb > 148 * 16) nb = 148 * 16;
+  k_split_2d<<<(int)nb, 256, 0, stream>>>(src, lds, rows, cols, hi, lo, ldd);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
+
 extern "C" int cpsd_proj_tc_prep(const float* L, int ldl, long long strideL, const float* mu_base,
-                                 const int* slot, int ld_mu, const int* cdim, int Q, float* LtHi,
-                                 float* LtLo, float* muL, int nprob, cudaStream_t stream) {
-  CPSD_CHECK_ARG(nprob >= 0 && Q > 0 && Q <= PT_N, "proj_tc_prep: Q must be in 1..32");
+                                 const int* slot, int ld_mu, const int* cdim, int Q, int ltc,
+                                 float* LtHi, float* LtLo, float* muL, int nprob,
+                                 cudaStream_t stream) {
+  CPSD_CHECK_ARG(nprob >= 0 && Q > 0 && Q <= PT_MAXQ, "proj_tc_prep: Q must be in 1..128");
+  CPSD_CHECK_ARG(ltc == 128 || ltc == 256, "proj_tc_prep: ltc must be 128 or 256");
   if (nprob == 0) return CPSD_OK;
-  k_proj_tc_prep<<<nprob, 128, 0, stream>>>(L, ldl, strideL, mu_base, slot, ld_mu, cdim, Q, LtHi, LtLo,
-                                            muL);
+  const int nq = (Q + PT_N - 1) / PT_N;
+  k_proj_tc_prep<<<dim3(nprob, nq), 128, 0, stream>>>(L, ldl, strideL, mu_base, slot, ld_mu, cdim, Q, nq,
+                                                      ltc, LtHi, LtLo, muL);
   CPSD_LAUNCH_CHECK();
   return CPSD_OK;
 }
 
 // xmaps_dev: 2*P tensor maps (hi, lo per patient; box 128 rows), ltmaps_dev: 2 maps over the
-// LtHi / LtLo arrays (box 32 rows).  n_trials[v], n_chan[v]: patient shapes (channels <= 128,
-// multiple of 4).  dst_row: [B][P][n_max] destination trial row in fold f's pooled matrix (or
-// -1).  Y: pooled matrices, fold stride strideY floats, row stride Q*T (trial) / Q (time bin).
+// LtHi / LtLo arrays (box 32 rows, ltc columns).  n_trials[v], n_chan[v]: patient shapes
+// (channels <= 256; the hi / lo arrays may have a padded row stride, cpsd_split_tf32_2d).
+// dst_row: [B][P][n_max] destination trial row in fold f's pooled matrix (or -1).  Y: pooled
+// matrices, fold stride strideY floats, row stride Q*T (trial) / Q (time bin); Q <= 128.
 extern "C" int cpsd_proj_tc(const void* xmaps_dev, const void* ltmaps_dev, int P, int B, int T, int Q,
-                            const int* n_trials_host, const int* n_chan_host, int n_max,
+                            int ltc, const int* n_trials_host, const int* n_chan_host, int n_max,
                             const int* dst_row, const float* muL, float* Y, long long strideY,
                             int num_sms, cudaStream_t stream) {
   CPSD_CHECK_ARG(P > 0 && P <= PT_MAXP && B > 0 && T > 0, "proj_tc: bad dims");
-  CPSD_CHECK_ARG(Q > 0 && Q <= PT_N, "proj_tc: Q must be in 1..32");
+  CPSD_CHECK_ARG(Q > 0 && Q <= PT_MAXQ, "proj_tc: Q must be in 1..128");
+  CPSD_CHECK_ARG(ltc == 128 || ltc == 256, "proj_tc: ltc must be 128 or 256");
   ProjTcParams prm;
   prm.P = P; prm.B = B; prm.T = T; prm.Q = Q; prm.n_max = n_max; prm.strideY = strideY;
+  prm.nq = (Q + PT_N - 1) / PT_N;
+  prm.ltc = ltc;
   int tot = 0;
   for (int v = 0; v < P; ++v) {
-    CPSD_CHECK_ARG(n_chan_host[v] > 0 && n_chan_host[v] <= PT_KB * PT_BK && (n_chan_host[v] & 3) == 0,
-                   "proj_tc: channels must be a multiple of 4 and <= 128");
+    CPSD_CHECK_ARG(n_chan_host[v] > 0 && n_chan_host[v] <= ltc && n_chan_host[v] <= PT_MAXC,
+                   "proj_tc: channels must be <= 256 (and <= ltc)");
     CPSD_CHECK_ARG(n_trials_host[v] <= n_max, "proj_tc: n_trials > n_max");
     prm.tile_prefix[v] = tot;
     prm.nrows[v] = n_trials_host[v] * T;

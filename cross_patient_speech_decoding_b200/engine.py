@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .device import Context, HostPack, addr, ptr
+from .device import Context, HostPack, LaneContext, addr, ptr
 from .folds import class_ids
 
 F32 = torch.float32
@@ -122,9 +122,10 @@ class CVEngine:
         self.svc_gamma = -1.0 if svc_gamma == 'scale' else float(svc_gamma)
         self.svc_max_iter = int(svc_max_iter)
         self.topk_gap_tol = float(topk_gap_tol)
-        self.ctx = Context.get(device)
+        base = Context.get(device)
         self.lane = int(lane)
-        self.stream = _lane_stream(self.ctx.device, self.lane)
+        self.stream = _lane_stream(base.device, self.lane)
+        self.ctx = LaneContext(base, self.stream)       # every launch of this engine goes to its lane
         with torch.cuda.stream(self.stream):     # uploads + fold-invariant work on the lane's stream
             self._init(target, cross, method, n_comp, regs, pca_var, decoder_var, C, tar_in_train,
                        max_batch, dcd_epochs, max_newton, tol_newton, tol_dcd, eig_sweeps, eig_tol,
@@ -410,48 +411,53 @@ class CVEngine:
 
     # ------------------------------------------------------------------ tensor-core projection
     def _tc_proj_ready(self, Q):
-        """Tensor-core pooled projection (csrc/tc_proj.cu): available for <= 32 latent columns,
-        <= 128 channels (multiples of 4) and <= 16 patients.  Splits every patient into tf32
-        hi / lo once and encodes the TMA tensor maps."""
-        if not self.use_tc or Q > 32 or self.P > 16:
+        """Tensor-core pooled projection (csrc/tc_proj.cu): any channel count <= 256 (two resident
+        panels above 128), <= 128 latent columns (chunks of 32) and <= 16 patients.  Splits every
+        patient into tf32 hi / lo once (row stride padded to a multiple of 4 floats, which is what
+        lets odd channel counts through TMA) and encodes the TMA tensor maps."""
+        if not self.use_tc or Q > 128 or self.P > 16:
             return False
-        if any(v.C > 128 or v.C % 4 for v in self.views):
+        if any(v.C > 256 for v in self.views):
             return False
         if getattr(self, '_tcp', None) is None:
             ctx = self.ctx
             maps_h = torch.zeros((2 * self.P, 128), dtype=torch.uint8).pin_memory()
             keep = []
             for i, vw in enumerate(self.views):
-                hi, lo = ctx.empty(vw.X.shape), ctx.empty(vw.X.shape)
-                ctx.call('cpsd_split_tf32', ptr(vw.X), ptr(hi), ptr(lo), vw.X.numel())
+                ldd = _ceil(vw.C, 4)
+                rows = vw.N * vw.T
+                hi, lo = ctx.empty((rows, ldd)), ctx.empty((rows, ldd))
+                ctx.call('cpsd_split_tf32_2d', ptr(vw.X), vw.C, rows, vw.C, ptr(hi), ptr(lo), ldd)
                 for u, t in enumerate((hi, lo)):
                     _lib.check(ctx.lib.cpsd_tmap_encode_f32(
-                        ctypes.c_void_p(maps_h[2 * i + u].data_ptr()), ptr(t), vw.N * vw.T, vw.C,
-                        vw.C, 128), 'tmap_encode')
+                        ctypes.c_void_p(maps_h[2 * i + u].data_ptr()), ptr(t), rows, vw.C, ldd, 128),
+                        'tmap_encode')
                 keep += [hi, lo]
             self._tcp = dict(xmaps=maps_h.to(ctx.device, non_blocking=True), xmaps_host=maps_h,
-                             split=keep, cap=0,
+                             split=keep, cap=0, nq=0, ltc=128 if self.Cmax <= 128 else 256,
                              ntr=np.array([v.N for v in self.views], dtype=np.int32),
                              nch=np.array([v.C for v in self.views], dtype=np.int32),
                              sms=torch.cuda.get_device_properties(ctx.device).multi_processor_count)
         return True
 
-    def _tc_proj_ws(self, nprob):
-        """L^T hi / lo (nprob, 32, 128), mu L (nprob, 32) and their tensor maps."""
+    def _tc_proj_ws(self, nprob, Q):
+        """L^T hi / lo (nprob * nq, 32, ltc), mu L (nprob * nq, 32) and their tensor maps."""
         tcp = self._tcp
-        if tcp['cap'] < nprob:
+        nq = -(-Q // 32)
+        if tcp['cap'] < nprob or tcp['nq'] != nq:
             ctx = self.ctx
             cap = max(nprob, self.max_batch * self.P)
-            tcp['lthi'] = ctx.zeros((cap, 32, 128))
-            tcp['ltlo'] = ctx.zeros((cap, 32, 128))
-            tcp['mul'] = ctx.zeros((cap, 32))
+            ltc = tcp['ltc']
+            tcp['lthi'] = ctx.zeros((cap * nq, 32, ltc))
+            tcp['ltlo'] = ctx.zeros((cap * nq, 32, ltc))
+            tcp['mul'] = ctx.zeros((cap * nq, 32))
             mh = torch.zeros((2, 128), dtype=torch.uint8).pin_memory()
             for u, t in enumerate((tcp['lthi'], tcp['ltlo'])):
                 _lib.check(ctx.lib.cpsd_tmap_encode_f32(ctypes.c_void_p(mh[u].data_ptr()), ptr(t),
-                                                        cap * 32, 128, 128, 32), 'tmap_encode')
+                                                        cap * nq * 32, ltc, ltc, 32), 'tmap_encode')
             tcp['ltmaps'] = mh.to(ctx.device, non_blocking=True)
             tcp['ltmaps_host'] = mh               # pinned source stays alive until the copy ran
-            tcp['cap'] = cap
+            tcp['cap'], tcp['nq'] = cap, nq
         return tcp
 
     def _view_slots(self, B, n_pad, Cm):
@@ -697,8 +703,9 @@ class CVEngine:
             ln.packM = [HostPack(self.ctx), HostPack(self.ctx)]
             ln._pack_i = 0
             if getattr(self, '_tcp', None) is not None:
-                ln._tcp = dict(self._tcp, cap=0)      # shares the X split + maps, own L^T buffers
+                ln._tcp = dict(self._tcp, cap=0, nq=0)   # shares the X split + maps, own L^T buffers
             ln.stream = _lane_stream(self.ctx.device, self.lane + 1 + len(extra))
+            ln.ctx = LaneContext(self.ctx.base, ln.stream)
             extra.append(ln)
         lanes = [self] + extra
         return lanes[:n]
@@ -734,9 +741,8 @@ class CVEngine:
         # every batch is a generator that yields right before each blocking read-back; the
         # lanes are advanced round-robin, so while one lane waits for its GPU results the
         # host packs and queues the other lane's batch on its own stream
-        if self.method in ('mcca', 'jointpca'):
-            with torch.cuda.stream(self.stream):
-                self._tc_proj_ready(int(self.n_comp))  # split X / encode maps before the lanes fork
+        with torch.cuda.stream(self.stream):
+            self._tc_proj_ready(1)                     # split X / encode maps before the lanes fork
         nl = 1 if (self.profile or len(batches) == 1) else min(self.n_lanes, len(batches))
         lanes = self._lanes(nl)
         ready = torch.cuda.Event()
@@ -1704,11 +1710,12 @@ class CVEngine:
         # project every trial of every view into the pooled (trial x time*Q) matrix
         self.mark('project_pool')
         if tc_proj:
-            tcp = self._tc_proj_ws(B * P)
+            tcp = self._tc_proj_ws(B * P, Q)
             ctx.call('cpsd_proj_tc_prep', ptr(L), Q, Cm * Q, ptr(None) if joint else ptr(mu),
                      ptr(None) if joint else ctypes_int_ptr(pk.iaddr(o_slot)),
-                     Cm, cdim_dev, Q, ptr(tcp['lthi']), ptr(tcp['ltlo']), ptr(tcp['mul']), B * P)
-            ctx.call('cpsd_proj_tc', ptr(tcp['xmaps']), ptr(tcp['ltmaps']), P, B, T, Q,
+                     Cm, cdim_dev, Q, tcp['ltc'], ptr(tcp['lthi']), ptr(tcp['ltlo']), ptr(tcp['mul']),
+                     B * P)
+            ctx.call('cpsd_proj_tc', ptr(tcp['xmaps']), ptr(tcp['ltmaps']), P, B, T, Q, tcp['ltc'],
                      ctypes.c_void_p(tcp['ntr'].ctypes.data), ctypes.c_void_p(tcp['nch'].ctypes.data),
                      Nmax, ctypes_int_ptr(pk.iaddr(o_dst)), ptr(tcp['mul']), ptr(Zall), n_pad * F,
                      tcp['sms'])

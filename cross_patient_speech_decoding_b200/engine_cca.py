@@ -8,6 +8,8 @@ of the class-averaged latents restricted to the classes both share (AlignCCA.py:
 235-285), the map  G = M_b pinv(M_a)  composed with the cross patient's PCA basis; then
 every trial is projected straight into the pooled matrix.
 """
+import ctypes
+
 import numpy as np
 import torch
 
@@ -159,13 +161,31 @@ def batch_cca_gen(eng, batch, want_details):
         o_b = pk.add_ints(eng._cross_rows[pi, pc] * T) + starts
         KTmax = int(Kp.max()) * T
         o_segdst = pk.add_ints(np.arange(KTmax // T, dtype=np.int32) * T)
-    ib = pk.reserve_ints()
-
     # PCA bases (sklearn sign convention, zero-padded to dmax columns)
     Wt = eng.ws('c_Wt', (B, Cm, dmax))
     Wx = eng.ws('c_Wx', (max(nv, 1), Cm, dmax))
     Zall = eng.ws('pool_Z', (B, n_pad, F))
-    Zall.zero_()
+    # pooled projection on the tensor cores (csrc/tc_proj.cu) when the shapes allow it: every
+    # (fold, patient) gets its (channels x dq) map and mean, every trial a destination row
+    tc_proj = eng._tc_proj_ready(dq)
+    if tc_proj:
+        Nmax = int(Ns.max())
+        dst = -np.ones((B, P, Nmax), dtype=np.int32)
+        for f, tb in enumerate(tabs):
+            if eng.tar_in_train:
+                dst[f, 0, tb['tr']] = np.arange(len(tb['tr']))
+            dst[f, 0, tb['te']] = n_pool[f] + np.arange(len(tb['te']))
+        for i in range(nv):
+            dst[:, 1 + i, :Ns[1 + i]] = (row0[:, None] + xoff[i] + np.arange(Ns[1 + i])[None, :])
+        o_dst = pk.add_ints(dst)
+        slot = np.empty((B, P), dtype=np.int32)           # row of the mean vector in [mu_t ; cross_mu]
+        slot[:, 0] = np.arange(B)
+        slot[:, 1:] = B + np.arange(nv)[None, :]
+        o_slot = pk.add_ints(slot)
+        o_cdim_all = pk.add_ints(np.tile(np.array([eng.views[v].C for v in range(P)], dtype=np.int32), B))
+    else:
+        Zall.zero_()
+    ib = pk.reserve_ints()
     xC = np.array([eng.views[v].C for v in range(1, P)], dtype=np.int64)
     xX = np.array([addr(eng.views[v].X) for v in range(1, P)], dtype=np.int64)
     fi = np.arange(B, dtype=np.int64)
@@ -296,8 +316,29 @@ def batch_cca_gen(eng, batch, want_details):
         ctx.call('cpsd_cca_solve_f64', pk.daddr(d_c), npair, dmax, ptr(cca_ws))
         ctx.call('cpsd_proj_nn', pk.daddr(d_w), npair, 1, Cm, dmax)
     eng.mark('project_pool')
-    ctx.call('cpsd_proj_nn', pk.daddr(d_pp), len(r_pp),
-             max(max(eng.views[v].N for v in range(P)), n_te_max), T, dq)
+    if tc_proj:
+        # L[(f, v)] = target basis / aligned cross map, all with row stride dmax (first dq columns)
+        Lall = eng.ws('c_Lall', (B, P, Cm, dmax))
+        Lall[:, 0].copy_(Wt)
+        if nv:
+            if aligned:
+                Lall[:, 1:].copy_(Wc.view(B, nv, Cm, dmax))
+            else:
+                Lall[:, 1:].copy_(Wx[:nv].unsqueeze(0).expand(B, nv, Cm, dmax))
+        mu_all = eng.ws('c_muall', (B + max(nv, 1), Cm))
+        mu_all[:B].copy_(mu_t)
+        if nv:
+            mu_all[B:B + nv].copy_(eng.cross_mu[:nv])
+        tcp = eng._tc_proj_ws(B * P, dq)
+        ctx.call('cpsd_proj_tc_prep', ptr(Lall), dmax, Cm * dmax, ptr(mu_all),
+                 ctypes_int_ptr(pk.iaddr(o_slot)), Cm, ctypes_int_ptr(pk.iaddr(o_cdim_all)), dq, tcp['ltc'],
+                 ptr(tcp['lthi']), ptr(tcp['ltlo']), ptr(tcp['mul']), B * P)
+        ctx.call('cpsd_proj_tc', ptr(tcp['xmaps']), ptr(tcp['ltmaps']), P, B, T, dq, tcp['ltc'],
+                 ctypes.c_void_p(tcp['ntr'].ctypes.data), ctypes.c_void_p(tcp['nch'].ctypes.data),
+                 Nmax, ctypes_int_ptr(pk.iaddr(o_dst)), ptr(tcp['mul']), ptr(Zall), n_pad * F, tcp['sms'])
+    else:
+        ctx.call('cpsd_proj_nn', pk.daddr(d_pp), len(r_pp),
+                 max(max(eng.views[v].N for v in range(P)), n_te_max), T, dq)
     evals, k2_, St_, Ste, V, sweeps, kcap = yield from eng._pooled_stage_run_gen(
         pk, d_p1, d_p2, B, Zall, pmu, Kall, n_pad, F, n_pool, n_te, o_npool, o_nall, o_ypool,
         n_te_max, want_details)

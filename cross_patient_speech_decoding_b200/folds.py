@@ -75,10 +75,27 @@ def cv_splits(y, n_splits, shuffle=True, random_state=None):
 
 
 # ----------------------------------------------------------------------------- labels
+_L2S_CACHE = {}
+
+
 def label2str(labels):
-    """Reference alignment_utils.py:64-99: 2-D rows are joined digit strings, 1-D are str."""
+    """Reference alignment_utils.py:64-99: 2-D rows are joined digit strings, 1-D are str.
+    (2-D integer labels are joined column-wise with numpy string ops and memoised on their bytes:
+    a streamed job re-submits the same label arrays for every CV iteration.)"""
     labels = np.asarray(labels)
     if labels.ndim > 1:
+        if labels.dtype.kind in 'iu' and labels.ndim == 2:
+            key = (labels.shape, labels.dtype.str, labels.tobytes())
+            out = _L2S_CACHE.get(key)
+            if out is None:
+                cols = labels.astype(str)
+                out = cols[:, 0]
+                for j in range(1, cols.shape[1]):
+                    out = np.char.add(out, cols[:, j])
+                if len(_L2S_CACHE) > 256:
+                    _L2S_CACHE.clear()
+                _L2S_CACHE[key] = out
+            return out.copy()
         return np.array([''.join(str(x) for x in row) for row in labels])
     return labels.astype(str)
 

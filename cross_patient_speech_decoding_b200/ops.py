@@ -319,8 +319,8 @@ def project(X, W, mu=None, device=None):
 def project_pool_tc(Xs, L, mu, dst, n_rows, device=None):
     """The tensor-core pooled projection on its own (csrc/tc_proj.cu, ``k_proj_tc``):
     Z[f][dst[f, v, trial]][t][:] = (X_v[trial][t][:] - mu[f, v]) @ L[f, v].
-    Xs: list of P arrays (N_v, T, C_v) with C_v <= 128 and C_v % 4 == 0; L: (B, P, Cmax, Q) with
-    Q <= 32; mu: (B, P, Cmax) or None; dst: (B, P, Nmax) int destination trial rows (-1 = skip).
+    Xs: list of P arrays (N_v, T, C_v) with C_v <= 256 (any parity); L: (B, P, Cmax, Q) with
+    Q <= 128; mu: (B, P, Cmax) or None; dst: (B, P, Nmax) int destination trial rows (-1 = skip).
     Returns Z (B, n_rows, T * Q) float32 (rows no trial maps to stay zero)."""
     ctx = _ctx(device)
     P = len(Xs)
@@ -336,31 +336,35 @@ def project_pool_tc(Xs, L, mu, dst, n_rows, device=None):
         N, T_, C = X.shape
         assert T_ == T and C <= Cm
         Xd = ctx.upload(X.reshape(N * T, C))
-        hi, lo = ctx.empty(Xd.shape), ctx.empty(Xd.shape)
-        ctx.call('cpsd_split_tf32', ptr(Xd), ptr(hi), ptr(lo), Xd.numel())
+        ldd = _ceil(C, 4)
+        hi, lo = ctx.empty((N * T, ldd)), ctx.empty((N * T, ldd))
+        ctx.call('cpsd_split_tf32_2d', ptr(Xd), C, N * T, C, ptr(hi), ptr(lo), ldd)
         for u, t in enumerate((hi, lo)):
             _lib.check(ctx.lib.cpsd_tmap_encode_f32(ctypes.c_void_p(maps_h[2 * i + u].data_ptr()), ptr(t),
-                                                    N * T, C, C, 128), 'tmap_encode')
+                                                    N * T, C, ldd, 128), 'tmap_encode')
         keep += [Xd, hi, lo]
     xmaps = maps_h.to(ctx.device, non_blocking=True)
     nprob = B * P
-    lthi, ltlo, mul = ctx.zeros((nprob, 32, 128)), ctx.zeros((nprob, 32, 128)), ctx.zeros((nprob, 32))
+    nq = -(-Q // 32)
+    ltc = 128 if Cm <= 128 else 256
+    lthi, ltlo = ctx.zeros((nprob * nq, 32, ltc)), ctx.zeros((nprob * nq, 32, ltc))
+    mul = ctx.zeros((nprob * nq, 32))
     mh = torch.zeros((2, 128), dtype=torch.uint8).pin_memory()
     for u, t in enumerate((lthi, ltlo)):
-        _lib.check(ctx.lib.cpsd_tmap_encode_f32(ctypes.c_void_p(mh[u].data_ptr()), ptr(t), nprob * 32,
-                                                128, 128, 32), 'tmap_encode')
+        _lib.check(ctx.lib.cpsd_tmap_encode_f32(ctypes.c_void_p(mh[u].data_ptr()), ptr(t), nprob * nq * 32,
+                                                ltc, ltc, 32), 'tmap_encode')
     ltmaps = mh.to(ctx.device, non_blocking=True)
     Ld = ctx.upload(L)
     mud = ctx.upload(np.ascontiguousarray(mu, dtype=np.float32)) if mu is not None else None
     cdim = ctx.upload(np.tile(np.array([X.shape[2] for X in Xs], dtype=np.int32), B))
-    ctx.call('cpsd_proj_tc_prep', ptr(Ld), Q, Cm * Q, ptr(mud), ptr(None), Cm, ptr(cdim), Q, ptr(lthi),
+    ctx.call('cpsd_proj_tc_prep', ptr(Ld), Q, Cm * Q, ptr(mud), ptr(None), Cm, ptr(cdim), Q, ltc, ptr(lthi),
              ptr(ltlo), ptr(mul), nprob)
     dst_d = ctx.upload(np.ascontiguousarray(dst, dtype=np.int32))
     Z = ctx.zeros((B, n_rows, T * Q))
     ntr = np.array([X.shape[0] for X in Xs], dtype=np.int32)
     nch = np.array([X.shape[2] for X in Xs], dtype=np.int32)
     sms = torch.cuda.get_device_properties(ctx.device).multi_processor_count
-    ctx.call('cpsd_proj_tc', ptr(xmaps), ptr(ltmaps), P, B, T, Q, ctypes.c_void_p(ntr.ctypes.data),
+    ctx.call('cpsd_proj_tc', ptr(xmaps), ptr(ltmaps), P, B, T, Q, ltc, ctypes.c_void_p(ntr.ctypes.data),
              ctypes.c_void_p(nch.ctypes.data), Nmax, ptr(dst_d), ptr(mul), ptr(Z), n_rows * T * Q, sms)
     out = Z.cpu().numpy()
     del keep

@@ -111,15 +111,21 @@ int cpsd_proj_nn(const cpsd_proj_desc* descs, int nprob, int nseg_max, int seg_l
  * streams the loadings of every fold past it.  Needs the tf32 hi/lo split of every patient
  * (cpsd_split_tf32, once), tensor maps (cpsd_tmap_encode_f32: host-encoded, copied to the
  * device by the caller; X maps with box_rows = 128, L^T maps with box_rows = 32) and the
- * per-problem L^T hi/lo + mu L prepared by cpsd_proj_tc_prep.  Channels <= 128 (multiple of
- * 4), latent size <= 32. */
+ * per-problem L^T hi/lo + mu L prepared by cpsd_proj_tc_prep.  Any channel count <= 256 (the
+ * hi / lo arrays get a row stride padded to a multiple of 4 floats by cpsd_split_tf32_2d; TMA
+ * zero-fills the box beyond the last channel; more than 128 channels run as two resident panels,
+ * the second adding to the first's output) and any latent size <= 128 (chunks of 32 columns;
+ * the L^T arrays hold ceil(Q / 32) blocks of 32 rows x ltc columns per problem, ltc = 128 or
+ * 256 >= the widest patient). */
 int cpsd_split_tf32(const float* src, float* hi, float* lo, long long n, cudaStream_t stream);
 int cpsd_tmap_encode_f32(void* map_out_host, const float* base, long long rows, int cols,
                          long long ld, int box_rows);
+int cpsd_split_tf32_2d(const float* src, long long lds, long long rows, int cols, float* hi,
+                       float* lo, int ldd, cudaStream_t stream);
 int cpsd_proj_tc_prep(const float* L, int ldl, long long strideL, const float* mu_base,
-                      const int* slot, int ld_mu, const int* cdim, int Q, float* LtHi, float* LtLo,
-                      float* muL, int nprob, cudaStream_t stream);
-int cpsd_proj_tc(const void* xmaps_dev, const void* ltmaps_dev, int P, int B, int T, int Q,
+                      const int* slot, int ld_mu, const int* cdim, int Q, int ltc, float* LtHi,
+                      float* LtLo, float* muL, int nprob, cudaStream_t stream);
+int cpsd_proj_tc(const void* xmaps_dev, const void* ltmaps_dev, int P, int B, int T, int Q, int ltc,
                  const int* n_trials_host, const int* n_chan_host, int n_max, const int* dst_row,
                  const float* muL, float* Y, long long strideY, int num_sms, cudaStream_t stream);
 /* A B^T over the long feature axis: Gram of the pooled matrix for the decoder-stage PCA

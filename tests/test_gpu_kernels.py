@@ -426,6 +426,12 @@ def test_select_k_total(ops):
     dict(n=(20, 31, 9), c=(128, 96, 64), t=25, q=30, b=3),
     dict(n=(40, 17), c=(128, 128), t=200, q=32, b=5),
     dict(n=(12, 14, 5, 8), c=(36, 4, 100, 128), t=7, q=7, b=2),
+    dict(n=(11, 9, 14), c=(63, 111, 74), t=13, q=30, b=3),          # odd channel counts (padded row stride)
+    dict(n=(10, 12, 7), c=(149, 201, 111), t=19, q=30, b=3),        # more than 128 channels: two panels
+    dict(n=(9, 13), c=(256, 171), t=16, q=12, b=2),
+    dict(n=(14, 10), c=(128, 96), t=11, q=60, b=3),                 # wide latents: chunks of 32
+    dict(n=(8, 12, 6), c=(201, 144, 63), t=9, q=100, b=2),          # both
+    dict(n=(7, 9), c=(200, 128), t=5, q=128, b=2),
 ])
 def test_proj_tc_direct(ops, shape):
     """k_proj_tc (tcgen05 3xTF32 pooled projection) on its own against fp64 (X - mu) L: ragged
