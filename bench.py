@@ -16,6 +16,11 @@ Prints ONE JSON line (rank 0).  `value` = folds/s with the patient data resident
 import argparse
 import json
 import os
+
+# more hardware work queues than the default 8: the streamed e2e path keeps 14+ CUDA streams busy and
+# streams that alias onto one queue serialise (measured: 981 folds/s with 2 queues, 1681 with 8, 1774
+# with 32).  Must be set before the CUDA context exists.
+os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')
 import subprocess
 import sys
 import threading
@@ -369,7 +374,10 @@ def main():
     ap.add_argument('--no-tc', action='store_true', help='fp32 SIMT pooled Gram instead of tcgen05')
     ap.add_argument('--cpu-folds', type=int, default=2, help='folds in the cpu_baseline sample')
     ap.add_argument('--e2e-steps', type=int, default=None)
-    ap.add_argument('--e2e-depth', type=int, default=8, help='steps in flight in the e2e measurement')
+    ap.add_argument('--e2e-depth', type=int, default=14, help='steps in flight in the e2e measurement')
+    ap.add_argument('--e2e-group', type=int, default=7,
+                    help='steps sharing one engine batch in the e2e measurement (replicas: every step still '
+                         'uploads its own inputs; 7 x 20 folds = one 140-fold batch)')
     ap.add_argument('--batch', type=int, default=148, help='max folds per engine batch')
     ap.add_argument('--config', default='headline', choices=['headline', 'sweep', 'subsample'],
                     help='headline = BASELINE configs[1] (the driver\'s run); sweep = configs[2] (latent-size '
@@ -498,7 +506,7 @@ def main():
             yield host_pts[0], host_pts[1:], step_folds(y0, seed0 + s)
 
     for _ in cv_align_decode_stream(jobs(args.e2e_depth + 2, 77), depth=args.e2e_depth, device='cuda:%d' % local,
-                                    **kw_e2e):
+                                    group=args.e2e_group, **kw_e2e):
         pass
     sync_all()
     t0 = time.perf_counter()
@@ -506,7 +514,7 @@ def main():
     e2e_ok = e2e_tot = 0
     for s, r in enumerate(cv_align_decode_stream(jobs(e2e_steps, 500 + rank * 1000),
                                                  depth=args.e2e_depth, device='cuda:%d' % local,
-                                                 **kw_e2e)):
+                                                 group=args.e2e_group, **kw_e2e)):
         e2e_h2d += r['h2d_bytes']
         e2e_d2h += r['d2h_bytes']
     sync_all()
@@ -611,7 +619,8 @@ def main():
                     'd2h_bytes_per_step': e2e_d2h // max(e2e_steps, 1), 'steps': e2e_steps,
                     'api': 'cross_patient_speech_decoding_b200.cv_align_decode_stream (host float64 '
                            'arrays in pinned memory -> predictions; every step uploads its own '
-                           'inputs; %d steps in flight)' % args.e2e_depth,
+                           'inputs; %d steps in flight, %d steps per engine batch)'
+                           % (args.e2e_depth, args.e2e_group),
                     'blocking_value': e2e_blocking,
                     'blocking_api': 'cv_align_decode, one blocking call per step'},
             'gpu_launches': launches,

@@ -29,73 +29,150 @@ def cv_align_decode(target, cross, folds, method='mcca', **kw):
     return out
 
 
-def cv_align_decode_stream(jobs, depth=8, method='mcca', device=None, **kw):
+def _same_labels(a, b):
+    import numpy as np
+    if a is b:
+        return True
+    if a is None or b is None:
+        return False
+    a, b = np.asarray(a), np.asarray(b)
+    return a.shape == b.shape and bool((a == b).all())
+
+
+def _groupable(job, first):
+    """A job can share an engine with ``first`` when it has no per-job overrides, host inputs and
+    the same patient shapes and labels (e.g. the CV iterations of one data set)."""
+    import torch
+    if len(job) > 3 and job[3]:
+        return False
+    pa, pb = [job[0]] + list(job[1]), [first[0]] + list(first[1])
+    if len(pa) != len(pb):
+        return False
+    for a, b in zip(pa, pb):
+        if isinstance(a[0], torch.Tensor) and a[0].is_cuda:
+            return False
+        if tuple(a[0].shape) != tuple(b[0].shape):
+            return False
+        if not _same_labels(a[1], b[1]) or not _same_labels(a[2], b[2]):
+            return False
+    return True
+
+
+def cv_align_decode_stream(jobs, depth=8, method='mcca', device=None, group=None, **kw):
     """Pipelined form of ``cv_align_decode`` for many independent jobs (e.g. the 50 CV
     iterations x patient sets of scripts/aligned_decode_svm_ncv.py:332-456): ``jobs`` is an
     iterable of ``(target, cross, folds)`` or ``(target, cross, folds, overrides)`` (a dict of
     engine keywords for that job only); results are yielded in order.  Up to ``depth`` jobs
     are in flight, each on its own CUDA stream with its own upload, so the host->device copy
-    and the latency-bound small solvers of one job overlap the kernels of the others."""
-    import collections
+    and the latency-bound small solvers of one job overlap the kernels of the others.
 
+    ``group`` (MCCA with tensor cores; default ``max(1, depth // 2)``, at most 8): consecutive
+    jobs with the same patient shapes and labels and no overrides -- each still uploading its
+    own inputs -- become REPLICAS of one engine, so their folds share the solver launches of
+    one batch (a 20-fold job alone occupies a sixth of the GPU in the tile eigen-solvers; eight
+    of them in one batch run at the resident-data rate)."""
+    import collections
+    import time
+
+    import numpy as np
     import torch
 
     from .engine import CVEngine, _lane_stream
     from .device import Context
     dev = Context.get(device).device
+    if group is None:
+        group = min(8, max(1, depth // 2)) if (method == 'mcca' and kw.get('use_tensor_cores')) else 1
+    if method != 'mcca' or not kw.get('use_tensor_cores') or kw.get('decoder', 'linear').startswith('bag_'):
+        group = 1
+    slots = depth if group <= 1 else max(1, depth // group)      # engines in flight
     pending = collections.deque()
     it = iter(jobs)
     nsub = 0
     done = False
+    held = []                   # a job read ahead that did not fit the group being formed
 
-    def submit(job):
+    def next_job():
+        if held:
+            return held.pop()
+        return next(it)
+
+    def submit(members):
         nonlocal nsub
-        lane = 8 + (nsub % depth) * 4           # leave room for the engines' extra lanes
+        lane = 8 + (nsub % slots) * 4              # leave room for the engines' extra lanes
         nsub += 1
+        first = members[0]
         with torch.cuda.stream(_lane_stream(dev, lane)):
             jkw = dict(kw)
-            if len(job) > 3 and job[3]:
-                jkw.update(job[3])                 # per-job engine keywords
+            if len(first) > 3 and first[3]:
+                jkw.update(first[3])               # per-job engine keywords (ungrouped jobs only)
             seeds = jkw.pop('bag_seeds', None)
-            eng = CVEngine(job[0], job[1], method=jkw.pop('method', method), device=dev, lane=lane,
-                           **jkw)
-            gen = eng.run_gen(job[2], bag_seeds=seeds)
-        return [eng, gen, None, False, None]     # engine, generator, result, done, wait event
+            reps = [(m[0], m[1]) for m in members[1:]]
+            if reps:                                # the group is one batch (<= 148 folds, see below)
+                jkw['max_batch'] = max(jkw.get('max_batch', 32), sum(len(m[2]) for m in members))
+            eng = CVEngine(first[0], first[1], method=jkw.pop('method', method), device=dev, lane=lane,
+                           replicas=reps or None, **jkw)
+            folds, rep = [], []
+            for r, m in enumerate(members):
+                folds += list(m[2])
+                rep += [r] * len(m[2])
+            gen = eng.run_gen(folds, bag_seeds=seeds, rep=rep if reps else None)
+        return dict(eng=eng, gen=gen, res=None, done=False, wait=None, counts=[len(m[2]) for m in members])
 
-    import time
+    def split(ent):
+        out, eng = ent['res'], ent['eng']
+        n = len(ent['counts'])
+        res, o = [], 0
+        for r, c in enumerate(ent['counts']):
+            res.append({'y_pred': out['y_pred'][o:o + c], 'k2': out['k2'][o:o + c],
+                        'h2d_bytes': out['h2d_bytes'] // n + sum(v.h2d_bytes for v in eng.rviews[r]),
+                        'd2h_bytes': out['d2h_bytes'] // n})
+            o += c
+        return res
+
     while True:
         t_iter = time.perf_counter()
-        while not done and len(pending) < depth:
+        while not done and len(pending) < slots:
             try:
-                job = next(it)
+                members = [next_job()]
             except StopIteration:
                 done = True
                 break
-            pending.append(submit(job))
+            while group > 1 and len(members) < group and _groupable(members[0], members[0]):
+                try:
+                    nxt = next_job()
+                except StopIteration:
+                    done = True
+                    break
+                # one batch per group: at most 148 folds (one tile-solver problem per SM)
+                if _groupable(nxt, members[0]) and sum(len(m[2]) for m in members) + len(nxt[2]) <= 148:
+                    members.append(nxt)
+                else:
+                    held.append(nxt)
+                    break
+            pending.append(submit(members))
         if not pending:
             return
         progressed = False
         for ent in pending:
-            if ent[3]:
+            if ent['done']:
                 continue
             # resume a job only when the GPU work it queued before yielding has finished
-            if ent[4] is not None and len(pending) > 1 and not ent[4].query():
+            if ent['wait'] is not None and len(pending) > 1 and not ent['wait'].query():
                 continue
             progressed = True
-            with torch.cuda.stream(ent[0].stream):
+            with torch.cuda.stream(ent['eng'].stream):
                 try:
-                    if next(ent[1]) == 'host':
-                        ent[4] = None               # pure host step: resumable at once
+                    if next(ent['gen']) == 'host':
+                        ent['wait'] = None               # pure host step: resumable at once
                     else:
-                        ent[4] = torch.cuda.Event()
-                        ent[4].record(ent[0].stream)
+                        ent['wait'] = torch.cuda.Event()
+                        ent['wait'].record(ent['eng'].stream)
                 except StopIteration as e:
-                    out = e.value
-                    out['h2d_bytes'] += sum(v.h2d_bytes for v in ent[0].views)
-                    ent[2], ent[3] = out, True
-        while pending and pending[0][3]:
+                    ent['res'], ent['done'] = e.value, True
+        while pending and pending[0]['done']:
             progressed = True
-            yield pending.popleft()[2]
+            for r in split(pending.popleft()):
+                yield r
         if not progressed:
             time.sleep(0)
             cv_align_decode_stream.idle_s += time.perf_counter() - t_iter

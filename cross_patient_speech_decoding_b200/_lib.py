@@ -147,6 +147,8 @@ _SIGS = {
     'cpsd_pca_basis': [_P, c_int, c_ll, _P, _P, c_int, c_int, _P, c_int, c_int, c_int, _P],
     'cpsd_split_tf32': [_P, _P, _P, c_ll, _P],
     'cpsd_tmap_encode_f32': [_P, _P, c_ll, c_int, c_ll, c_int],
+    'cpsd_proj_tc_rep': [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int, _P, _P, _P,
+                         c_ll, c_int, _P],
     'cpsd_split_tf32_2d': [_P, c_ll, c_ll, c_int, _P, _P, c_int, _P],
     'cpsd_proj_tc_prep': [_P, c_int, c_ll, _P, _P, c_int, _P, c_int, c_int, _P, _P, _P, c_int, _P],
     'cpsd_proj_tc': [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P, _P, c_ll, c_int,

@@ -38,11 +38,15 @@ constexpr int PT_B_STAGES = 2;
 constexpr int PT_LDS = 33;                 // staging row stride (floats)
 constexpr int PT_STAGING = PT_BM * PT_LDS * 4;
 constexpr int PT_THREADS = 192;
-constexpr int PT_MAXP = 16;
+constexpr int PT_MAXP = 128;               // (replica, patient) pairs of one launch
 constexpr uint32_t PT_TMEM_COLS = 64;      // two 32-column accumulator stages
 
 struct ProjTcParams {
-  int P, B, T, Q;
+  int P, B, T, Q;        // P = patients per replica (row stride of the L / destination tables)
+  int PV;                // virtual patients = replicas x P: virtual patient vv = replica * P + v is
+                         // multiplied with the loadings of the folds [fbeg[vv], fbeg[vv] + fcnt[vv])
+  int fbeg[PT_MAXP];
+  int fcnt[PT_MAXP];
   int nq;                // latent chunks of 32 columns (Q <= 32: 1)
   int ltc;               // columns of the L^T arrays (128 or 256)
   int n_max;             // trials per patient in the destination table (row stride)
@@ -101,13 +105,15 @@ k_proj_tc(const CUtensorMap* __restrict__ xmaps, const CUtensorMap* __restrict__
   const uint32_t tmem_base = *tmem_slot;
 
   // item -> (patient v, tile inside the patient, fold group)
-  auto decode = [&](int item, int& v, int& tile, int& f0, int& f1) {
+  // vv: virtual patient (indexes the X maps / shapes); v = vv % P indexes the per-fold tables
+  auto decode = [&](int item, int& vv, int& v, int& tile, int& f0, int& f1) {
     const int tg = item / prm.ngroups, g = item - tg * prm.ngroups;
-    v = 0;
-    while (v + 1 < prm.P && tg >= prm.tile_prefix[v + 1]) ++v;
-    tile = tg - prm.tile_prefix[v];
-    f0 = g * prm.fg;
-    f1 = min(prm.B, f0 + prm.fg);
+    vv = 0;
+    while (vv + 1 < prm.PV && tg >= prm.tile_prefix[vv + 1]) ++vv;
+    v = vv % prm.P;
+    tile = tg - prm.tile_prefix[vv];
+    f0 = prm.fbeg[vv] + g * prm.fg;
+    f1 = min(prm.fbeg[vv] + prm.fcnt[vv], f0 + prm.fg);     // empty when this group lies past the range
   };
 
   if (warp == 0) {
@@ -115,14 +121,15 @@ k_proj_tc(const CUtensorMap* __restrict__ xmaps, const CUtensorMap* __restrict__
     if (lane == 0) {
       uint32_t it_a = 0, it_b = 0;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        int v, tile, f0, f1;
-        decode(item, v, tile, f0, f1);
-        const CUtensorMap* mh = xmaps + 2 * v;
+        int vv, v, tile, f0, f1;
+        decode(item, vv, v, tile, f0, f1);
+        if (f0 >= f1) continue;
+        const CUtensorMap* mh = xmaps + 2 * vv;
         const CUtensorMap* ml = mh + 1;
         // channel panels of <= 128 channels: the X panel stays in shared memory while the
         // loadings of every (fold, latent chunk) of the group stream past it
-        for (int kb0 = 0; kb0 < prm.kblocks[v]; kb0 += PT_KB, ++it_a) {
-          const int kbn = min(PT_KB, prm.kblocks[v] - kb0);
+        for (int kb0 = 0; kb0 < prm.kblocks[vv]; kb0 += PT_KB, ++it_a) {
+          const int kbn = min(PT_KB, prm.kblocks[vv] - kb0);
           mbar_wait(a_empty, (it_a & 1u) ^ 1u);
           mbar_expect_tx(a_full, (uint32_t)(kbn * 2 * PT_A_TILE));
           for (int kb = 0; kb < kbn; ++kb) {
@@ -150,10 +157,11 @@ k_proj_tc(const CUtensorMap* __restrict__ xmaps, const CUtensorMap* __restrict__
       const uint32_t idesc = idesc_tf32(PT_BM, PT_N);
       uint32_t it_a = 0, it_b = 0;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        int v, tile, f0, f1;
-        decode(item, v, tile, f0, f1);
-        for (int kb0 = 0; kb0 < prm.kblocks[v]; kb0 += PT_KB, ++it_a) {
-        const int kbn = min(PT_KB, prm.kblocks[v] - kb0);
+        int vv, v, tile, f0, f1;
+        decode(item, vv, v, tile, f0, f1);
+        if (f0 >= f1) continue;
+        for (int kb0 = 0; kb0 < prm.kblocks[vv]; kb0 += PT_KB, ++it_a) {
+        const int kbn = min(PT_KB, prm.kblocks[vv] - kb0);
         mbar_wait(a_full, it_a & 1u);
         for (int vf = f0 * prm.nq; vf < f1 * prm.nq; ++vf, ++it_b) {
           const int s = it_b & 1;
@@ -207,16 +215,17 @@ k_proj_tc(const CUtensorMap* __restrict__ xmaps, const CUtensorMap* __restrict__
     }
     uint32_t it_b = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-      int v, tile, f0, f1;
-      decode(item, v, tile, f0, f1);
+      int vv, v, tile, f0, f1;
+      decode(item, vv, v, tile, f0, f1);
+      if (f0 >= f1) continue;
       // this thread's row of the tile: trial and time bin (item-invariant)
       const int R = tile * PT_BM + r_own;
       int my_tr = -1, my_t = 0;
-      if (R < prm.nrows[v]) {
+      if (R < prm.nrows[vv]) {
         my_tr = R / prm.T;
         my_t = R - my_tr * prm.T;
       }
-      for (int kb0 = 0; kb0 < prm.kblocks[v]; kb0 += PT_KB) {
+      for (int kb0 = 0; kb0 < prm.kblocks[vv]; kb0 += PT_KB) {
       const bool first = kb0 == 0;       // later channel panels add to what the first one wrote
       for (int vf = f0 * prm.nq; vf < f1 * prm.nq; ++vf, ++it_b) {
         const int f = vf / prm.nq, qc = vf - f * prm.nq;
@@ -438,37 +447,46 @@ extern "C" int cpsd_proj_tc_prep(const float* L, int ldl, long long strideL, con
 // (channels <= 256; the hi / lo arrays may have a padded row stride, cpsd_split_tf32_2d).
 // dst_row: [B][P][n_max] destination trial row in fold f's pooled matrix (or -1).  Y: pooled
 // matrices, fold stride strideY floats, row stride Q*T (trial) / Q (time bin); Q <= 128.
-extern "C" int cpsd_proj_tc(const void* xmaps_dev, const void* ltmaps_dev, int P, int B, int T, int Q,
-                            int ltc, const int* n_trials_host, const int* n_chan_host, int n_max,
-                            const int* dst_row, const float* muL, float* Y, long long strideY,
-                            int num_sms, cudaStream_t stream) {
-  CPSD_CHECK_ARG(P > 0 && P <= PT_MAXP && B > 0 && T > 0, "proj_tc: bad dims");
+extern "C" int cpsd_proj_tc_rep(const void* xmaps_dev, const void* ltmaps_dev, int P, int n_rep, int B,
+                                int T, int Q, int ltc, const int* n_trials_host, const int* n_chan_host,
+                                const int* fold_beg_host, const int* fold_cnt_host, int n_max,
+                                const int* dst_row, const float* muL, float* Y, long long strideY,
+                                int num_sms, cudaStream_t stream) {
+  CPSD_CHECK_ARG(P > 0 && n_rep > 0 && P * n_rep <= PT_MAXP && B > 0 && T > 0,
+                 "proj_tc: bad dims (patients x replicas <= 128)");
   CPSD_CHECK_ARG(Q > 0 && Q <= PT_MAXQ, "proj_tc: Q must be in 1..128");
   CPSD_CHECK_ARG(ltc == 128 || ltc == 256, "proj_tc: ltc must be 128 or 256");
   ProjTcParams prm;
   prm.P = P; prm.B = B; prm.T = T; prm.Q = Q; prm.n_max = n_max; prm.strideY = strideY;
+  prm.PV = P * n_rep;
   prm.nq = (Q + PT_N - 1) / PT_N;
   prm.ltc = ltc;
-  int tot = 0;
-  for (int v = 0; v < P; ++v) {
-    CPSD_CHECK_ARG(n_chan_host[v] > 0 && n_chan_host[v] <= ltc && n_chan_host[v] <= PT_MAXC,
+  int tot = 0, fmax = 0;
+  for (int vv = 0; vv < prm.PV; ++vv) {
+    CPSD_CHECK_ARG(n_chan_host[vv] > 0 && n_chan_host[vv] <= ltc && n_chan_host[vv] <= PT_MAXC,
                    "proj_tc: channels must be <= 256 (and <= ltc)");
-    CPSD_CHECK_ARG(n_trials_host[v] <= n_max, "proj_tc: n_trials > n_max");
-    prm.tile_prefix[v] = tot;
-    prm.nrows[v] = n_trials_host[v] * T;
-    prm.kblocks[v] = (n_chan_host[v] + PT_BK - 1) / PT_BK;
-    tot += (prm.nrows[v] + PT_BM - 1) / PT_BM;
+    CPSD_CHECK_ARG(n_trials_host[vv] <= n_max, "proj_tc: n_trials > n_max");
+    const int r = vv / P;
+    prm.fbeg[vv] = fold_beg_host ? fold_beg_host[r] : 0;
+    prm.fcnt[vv] = fold_cnt_host ? fold_cnt_host[r] : B;
+    CPSD_CHECK_ARG(prm.fbeg[vv] >= 0 && prm.fcnt[vv] >= 0 && prm.fbeg[vv] + prm.fcnt[vv] <= B,
+                   "proj_tc: fold range outside the batch");
+    if (prm.fcnt[vv] > fmax) fmax = prm.fcnt[vv];
+    prm.tile_prefix[vv] = tot;
+    prm.nrows[vv] = n_trials_host[vv] * T;
+    prm.kblocks[vv] = (n_chan_host[vv] + PT_BK - 1) / PT_BK;
+    tot += (prm.nrows[vv] + PT_BM - 1) / PT_BM;
   }
-  for (int v = P; v < PT_MAXP; ++v) { prm.nrows[v] = 0; prm.kblocks[v] = 0; }
-  for (int v = P; v <= PT_MAXP; ++v) prm.tile_prefix[v] = tot;
+  for (int vv = prm.PV; vv < PT_MAXP; ++vv) { prm.nrows[vv] = 0; prm.kblocks[vv] = 0; prm.fbeg[vv] = 0; prm.fcnt[vv] = 0; }
+  for (int vv = prm.PV; vv <= PT_MAXP; ++vv) prm.tile_prefix[vv] = tot;
   prm.ntile_total = tot;
-  if (tot == 0) return CPSD_OK;
+  if (tot == 0 || fmax == 0) return CPSD_OK;
   if (num_sms <= 0) num_sms = 148;
   // fold groups: enough items to balance the persistent grid, few enough to amortise the X tile
   int ngroups = 1;
-  while (ngroups * 2 <= B && (long long)tot * ngroups < 8LL * num_sms) ngroups *= 2;
-  prm.fg = (B + ngroups - 1) / ngroups;
-  prm.ngroups = (B + prm.fg - 1) / prm.fg;
+  while (ngroups * 2 <= fmax && (long long)tot * ngroups < 8LL * num_sms) ngroups *= 2;
+  prm.fg = (fmax + ngroups - 1) / ngroups;
+  prm.ngroups = (fmax + prm.fg - 1) / prm.fg;
   const long long nitems = (long long)tot * prm.ngroups;
   const int grid = (int)(nitems < num_sms ? nitems : num_sms);
   const size_t smem = 1024 + PT_A_BYTES + PT_B_STAGES * PT_B_STAGE + PT_STAGING + 2 * PT_BM * 4 + 128;
@@ -478,4 +496,12 @@ extern "C" int cpsd_proj_tc(const void* xmaps_dev, const void* ltmaps_dev, int P
                                                 dst_row, muL, Y);
   CPSD_LAUNCH_CHECK();
   return CPSD_OK;
+}
+
+extern "C" int cpsd_proj_tc(const void* xmaps_dev, const void* ltmaps_dev, int P, int B, int T, int Q,
+                            int ltc, const int* n_trials_host, const int* n_chan_host, int n_max,
+                            const int* dst_row, const float* muL, float* Y, long long strideY,
+                            int num_sms, cudaStream_t stream) {
+  return cpsd_proj_tc_rep(xmaps_dev, ltmaps_dev, P, 1, B, T, Q, ltc, n_trials_host, n_chan_host, nullptr,
+                          nullptr, n_max, dst_row, muL, Y, strideY, num_sms, stream);
 }

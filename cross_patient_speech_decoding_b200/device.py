@@ -4,11 +4,13 @@ All arithmetic on the product path happens in the kernels of ``libcpsd_b200.so``
 module fails loudly when CUDA or the library is unavailable (there is no CPU fallback).
 """
 import ctypes
-
-import numpy as np
-import torch
-
 import os
+
+# see bench.py: streams that alias onto one hardware queue serialise; set before CUDA initialises
+os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
 
 from . import _lib
 

@@ -94,8 +94,9 @@ class View:
 
 
 class _Batch(list):
-    """The folds of one engine batch plus what travels with them (bagging seeds)."""
+    """The folds of one engine batch plus what travels with them (bagging seeds, replica ids)."""
     bag_seeds = None
+    rep = None
 
 
 class CVEngine:
@@ -107,7 +108,8 @@ class CVEngine:
                  eig_sweeps=12, eig_tol=3e-7, use_tensor_cores=False, pool_solver='auto',
                  topk_block=128, topk_iters=8, topk_tol=5e-6, topk_rounds=3, n_lanes=2, lane=0,
                  topk_tf32_iters=5, topk_gap_tol=0.05, decoder='linear', class_weight=None, svc_tol=1e-3,
-                 svc_gamma='scale', svc_max_iter=1000000, joint_cap=None, n_estimators=10):
+                 svc_gamma='scale', svc_max_iter=1000000, joint_cap=None, n_estimators=10,
+                 replicas=None):
         # decoder: 'linear' = one-vs-rest squared-hinge linear SVM (the north star's dual-CD
         # decoder); 'svc_rbf' / 'svc_linear' = libsvm-style C-SVC with one-vs-one votes, the
         # reference scripts' literal SVC(kernel=..., class_weight=...)
@@ -122,6 +124,12 @@ class CVEngine:
         self.svc_gamma = -1.0 if svc_gamma == 'scale' else float(svc_gamma)
         self.svc_max_iter = int(svc_max_iter)
         self.topk_gap_tol = float(topk_gap_tol)
+        # replicas: further (target, cross) data sets with the SAME shapes and labels as the primary
+        # one (independent jobs, e.g. the CV iterations of a streamed run, each with its own
+        # upload): their folds share this engine's batches -- run(folds, rep=...) says which
+        # replica a fold reads -- so the latency-bound solver launches are amortised over all of
+        # them.  MCCA with the tensor-core projection only.
+        self._replicas = list(replicas or [])
         base = Context.get(device)
         self.lane = int(lane)
         self.stream = _lane_stream(base.device, self.lane)
@@ -182,6 +190,16 @@ class CVEngine:
         views = [target] + list(cross)
         ids, self.vocab = class_ids([v[2] if v[2] is not None else v[1] for v in views])
         self.views = [View(self.ctx, v[0], v[1], v[2], i) for v, i in zip(views, ids)]
+        self.rviews = [self.views]
+        for rt, rc in self._replicas:
+            rv = [rt] + list(rc)
+            assert method == 'mcca' and len(rv) == len(views), 'replicas: MCCA, same patient count'
+            vs_r = [View(self.ctx, v[0], v[1], v[2], i) for v, i in zip(rv, ids)]
+            for a, b in zip(vs_r, self.views):
+                assert (a.N, a.T, a.C) == (b.N, b.T, b.C), 'replicas must have the primary job\'s shapes'
+            self.rviews.append(vs_r)
+        self.J = len(self.rviews)
+        self._replicas = None                      # the host arrays are not kept alive by the engine
         self.P = len(self.views)
         self.T = self.views[0].T
         assert all(v.T == self.T for v in self.views), 'all patients need the same time axis'
@@ -415,15 +433,16 @@ class CVEngine:
         panels above 128), <= 128 latent columns (chunks of 32) and <= 16 patients.  Splits every
         patient into tf32 hi / lo once (row stride padded to a multiple of 4 floats, which is what
         lets odd channel counts through TMA) and encodes the TMA tensor maps."""
-        if not self.use_tc or Q > 128 or self.P > 16:
+        if not self.use_tc or Q > 128 or self.P * self.J > 128:
             return False
         if any(v.C > 256 for v in self.views):
             return False
         if getattr(self, '_tcp', None) is None:
             ctx = self.ctx
-            maps_h = torch.zeros((2 * self.P, 128), dtype=torch.uint8).pin_memory()
+            allv = [vw for rv in self.rviews for vw in rv]        # (replica, patient) order
+            maps_h = torch.zeros((2 * len(allv), 128), dtype=torch.uint8).pin_memory()
             keep = []
-            for i, vw in enumerate(self.views):
+            for i, vw in enumerate(allv):
                 ldd = _ceil(vw.C, 4)
                 rows = vw.N * vw.T
                 hi, lo = ctx.empty((rows, ldd)), ctx.empty((rows, ldd))
@@ -435,8 +454,8 @@ class CVEngine:
                 keep += [hi, lo]
             self._tcp = dict(xmaps=maps_h.to(ctx.device, non_blocking=True), xmaps_host=maps_h,
                              split=keep, cap=0, nq=0, ltc=128 if self.Cmax <= 128 else 256,
-                             ntr=np.array([v.N for v in self.views], dtype=np.int32),
-                             nch=np.array([v.C for v in self.views], dtype=np.int32),
+                             ntr=np.array([v.N for v in allv], dtype=np.int32),
+                             nch=np.array([v.C for v in allv], dtype=np.int32),
                              sms=torch.cuda.get_device_properties(ctx.device).multi_processor_count)
         return True
 
@@ -534,28 +553,30 @@ class CVEngine:
             counts = np.bincount(vw.cls, minlength=len(self.vocab))[present]
             mptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
             offs.append((pk.add_ints(mptr), pk.add_ints(order.astype(np.int32)), len(present)))
-            self.cm[v] = ctx.empty((len(present) * T, vw.C))
+            self.cm[v] = ctx.empty((self.J, len(present) * T, vw.C))     # one slab per replica
         if self.P > 1:
+            J = self.J
+            recs = np.zeros((self.P - 1, J), dtype=_lib.CLASS_MEAN_DESC)
             pk.reserve_ints()
             for i, v in enumerate(range(1, self.P)):
-                vw = self.views[v]
                 o_ptr, o_mem, ns = offs[i]
-                recs[i] = (addr(vw.X), pk.iaddr(o_ptr), pk.iaddr(o_mem), addr(self.cm[v]), ns,
-                           T * vw.C, 0, 0)
-            d_off = pk.add_descs(recs)
+                for j in range(J):
+                    vw = self.rviews[j][v]
+                    recs[i, j] = (addr(vw.X), pk.iaddr(o_ptr), pk.iaddr(o_mem), addr(self.cm[v][j]), ns,
+                                  T * vw.C, 0, 0)
+            d_off = pk.add_descs(recs.ravel())
             pk.upload()
-            ns_max = max(o[2] for o in offs)
             for i, v in enumerate(range(1, self.P)):
-                # one launch per view: TC differs between views
+                # one launch per view (TC differs between views), all replicas of the view in it
                 ctx.call('cpsd_class_mean',
-                         ctypes_off(pk.daddr(d_off), i * _lib.CLASS_MEAN_DESC.itemsize), 1,
+                         ctypes_off(pk.daddr(d_off), i * J * _lib.CLASS_MEAN_DESC.itemsize), J,
                          offs[i][2], T * self.views[v].C)
         self.cross_classes = [set(np.unique(self.views[v].cls).tolist())
                               for v in range(1, self.P)]
         if self.method == 'mcca':
             # the ranks stay on the device until the first batch needs them on the host
             # (_ensure_ready): constructing an engine does not block on its own uploads
-            self._rank_dev = self._ranks_full(range(1, self.P))
+            self._rank_dev = self._ranks_full(range(1, self.P))     # (replica, view) order
             self.cross_rank = None
             self._target_trial_grams()
             self._keep = [pk]                # staging of the kernels still in flight
@@ -568,7 +589,7 @@ class CVEngine:
         """Blocking tail of the constructor: signal ranks of the cross patients -> host."""
         if self.method == 'mcca' and self.cross_rank is None:
             with torch.cuda.stream(self.stream):
-                self.cross_rank = self._rank_dev.cpu().numpy().astype(np.int32)
+                self.cross_rank = self._rank_dev.cpu().numpy().astype(np.int32).reshape(self.J, self.P - 1)
             self._keep = None
         if self.joint_var and self._joint_qcap is None:
             self._joint_qcap = 32
@@ -582,60 +603,68 @@ class CVEngine:
         """AlignMCCA.n_components_var on all trials of the given views (AlignMCCA.py:146-150)."""
         vs = list(vs)
         if not (0 < self.pca_var < 1) or not vs:
-            return torch.full((len(vs),), int(self.n_comp), dtype=I32, device=self.ctx.device)
+            return torch.full((getattr(self, 'J', 1) * len(vs),), int(self.n_comp), dtype=I32,
+                              device=self.ctx.device)
         ctx, T, Cm = self.ctx, self.T, self.Cmax
         n_pad = _ceil(Cm, 128) if Cm > 128 else 128
         pk = HostPack(ctx)
-        G, gram = self.scatter('rk_G', len(vs), n_pad)
+        J = getattr(self, 'J', 1)
+        nprob = J * len(vs)                       # problem (j, i) = replica j, view vs[i]
+        G, gram = self.scatter('rk_G', nprob, n_pad)
         G.zero_()
         seg = [pk.add_ints(np.arange(self.views[v].N, dtype=np.int32) * T) for v in vs]
-        cdim = pk.add_ints([self.views[v].C for v in vs])
+        cdim = pk.add_ints([self.views[v].C for v in vs] * J)
         pk.reserve_ints()
-        recs = np.zeros(len(vs), dtype=_lib.GRAM_TN_DESC)
-        for i, v in enumerate(vs):
-            vw = self.views[v]
-            recs[i] = (addr(vw.X), addr(vw.X), pk.iaddr(seg[i]), pk.iaddr(seg[i]), 0, 0,
-                       addr(G, i * n_pad * n_pad), vw.N, T, vw.C, vw.C, vw.C, vw.C, n_pad, 1,
-                       1.0, 0)
+        recs = np.zeros(nprob, dtype=_lib.GRAM_TN_DESC)
+        for j in range(J):
+            for i, v in enumerate(vs):
+                vw = self.rviews[j][v]
+                q = j * len(vs) + i
+                recs[q] = (addr(vw.X), addr(vw.X), pk.iaddr(seg[i]), pk.iaddr(seg[i]), 0, 0,
+                           addr(G, q * n_pad * n_pad), vw.N, T, vw.C, vw.C, vw.C, vw.C, n_pad, 1,
+                           1.0, 0)
         d = pk.add_descs(recs)
         pk.upload()
-        self.gram_scatter(gram, pk.daddr(d), len(vs), Cm, Cm, G, 3)
+        self.gram_scatter(gram, pk.daddr(d), nprob, Cm, Cm, G, 3)
         cd = ctypes_int_ptr(pk.iaddr(cdim))
-        evals, _ = self.eig_any(G, n_pad, cd, 0, len(vs), 'rk', vecs=False)
-        k = self.ws('rk_k', (len(vs),), I32)
+        evals, _ = self.eig_any(G, n_pad, cd, 0, nprob, 'rk', vecs=False)
+        k = self.ws('rk_k', (nprob,), I32)
         ctx.call('cpsd_select_k', ptr(evals), n_pad, cd, 0, float(self.pca_var), 1, 0, 1 << 30,
-                 ptr(k), 1, len(vs))
+                 ptr(k), 1, nprob)
         self._keep_rk = pk
         return k.clone()
 
     def _target_trial_grams(self):
-        """Uncentred per-trial scatter matrices X_t^T X_t of the target (fp64) and their sum:
-        the train-set Gram of every fold follows by subtracting the held-out trials."""
+        """Uncentred per-trial scatter matrices X_t^T X_t of the target (fp64), for every replica,
+        followed by MINUS their sum per replica: the train-set Gram of a fold is
+        -( -G_all + sum of the held-out trials' matrices ), one cpsd_sum_mats_f64 list per fold
+        (rows: [replica * N + trial] ..., then [J * N + replica])."""
         self.tg = None
         tv = self.views[0]
         if not (0 < self.pca_var < 1) or tv.C > 128:
             return
-        ctx, T = self.ctx, self.T
+        ctx, T, J, N = self.ctx, self.T, self.J, tv.N
         pk = HostPack(ctx)
-        seg = pk.add_ints(np.arange(tv.N, dtype=np.int32) * T)
+        seg = pk.add_ints(np.arange(N, dtype=np.int32) * T)
+        o_ptr = pk.add_ints(np.arange(J + 1, dtype=np.int32) * N)
+        o_all = pk.add_ints(np.arange(J * N, dtype=np.int32))
         pk.reserve_ints()
-        G = ctx.zeros((tv.N, 128, 128), torch.float64)
-        recs = np.zeros(tv.N, dtype=_lib.GRAM_TN_DESC)
-        recs['A'] = recs['B'] = addr(tv.X)
-        recs['segA'] = recs['segB'] = pk.iaddr(seg) + 4 * np.arange(tv.N, dtype=np.int64)
-        recs['out'] = addr(G) + 8 * 128 * 128 * np.arange(tv.N, dtype=np.int64)
+        G = ctx.zeros((J * N + J, 128, 128), torch.float64)
+        recs = np.zeros(J * N, dtype=_lib.GRAM_TN_DESC)
+        tn = np.tile(np.arange(N, dtype=np.int64), J)
+        recs['A'] = recs['B'] = np.repeat(np.array([addr(self.rviews[j][0].X) for j in range(J)],
+                                                   dtype=np.int64), N)
+        recs['segA'] = recs['segB'] = pk.iaddr(seg) + 4 * tn
+        recs['out'] = addr(G) + 8 * 128 * 128 * np.arange(J * N, dtype=np.int64)
         recs['nseg'], recs['seg_len'] = 1, T
         recs['p'] = recs['q'] = recs['lda'] = recs['ldb'] = tv.C
         recs['ldo'], recs['sym'], recs['alpha'] = 128, 1, 1.0
         d = pk.add_descs(recs)
         pk.upload()
-        ctx.call('cpsd_gram_tn_f64', pk.daddr(d), tv.N, tv.C, tv.C)
-        allp = ctx.upload(np.array([0, tv.N], dtype=np.int32))
-        alll = ctx.upload(np.arange(tv.N, dtype=np.int32))
-        Gall = ctx.zeros((128, 128), torch.float64)
-        ctx.call('cpsd_sum_mats_f64', ptr(None), ptr(G), 128 * 128, ptr(allp), ptr(alll), 1.0,
-                 ptr(Gall), 128 * 128, 128 * 128, 1)
-        self.tg = dict(trial=G, all=Gall)
+        ctx.call('cpsd_gram_tn_f64', pk.daddr(d), J * N, tv.C, tv.C)
+        ctx.call('cpsd_sum_mats_f64', ptr(None), ptr(G), 128 * 128, ctypes_int_ptr(pk.iaddr(o_ptr)),
+                 ctypes_int_ptr(pk.iaddr(o_all)), -1.0, ptr(G, J * N * 128 * 128), 128 * 128, 128 * 128, J)
+        self.tg = dict(trial=G, keep=pk)
 
     def _cross_pca(self):
         """sklearn PCA(n_comp) of every cross patient's (trials*time, channels) matrix
@@ -723,7 +752,7 @@ class CVEngine:
         bag_seeds = np.asarray(bag_seeds, dtype=np.int64).reshape(len(folds), self.n_estimators)
         return bag_seeds
 
-    def run(self, folds, return_details=False, bag_seeds=None):
+    def run(self, folds, return_details=False, bag_seeds=None, rep=None):
         """folds: list of (train_idx, test_idx) into the target's trials.  Returns a dict with
         ``y_pred`` (list of arrays, one per fold) and per-fold diagnostics."""
         out = {'y_pred': [], 'k2': [], 'h2d_bytes': 0, 'd2h_bytes': 0}
@@ -732,9 +761,11 @@ class CVEngine:
         size = -(-len(folds) // nb)          # balanced batches (a short tail batch costs as much
         seeds = self._bag_seeds(folds, bag_seeds)                           # as a full one)
         batches = []
+        rep = self._check_rep(rep, len(folds))
         for s0 in range(0, len(folds), size):
             b = _Batch(folds[s0:s0 + size])
             b.bag_seeds = None if seeds is None else seeds[s0:s0 + size]
+            b.rep = None if rep is None else rep[s0:s0 + size]
             batches.append(b)
         results = [None] * len(batches)
         self._ensure_ready()
@@ -798,7 +829,17 @@ class CVEngine:
             out['details'] = details
         return out
 
-    def run_gen(self, folds, return_details=False, bag_seeds=None):
+    def _check_rep(self, rep, n):
+        """Replica index of every fold: ascending (the folds of one replica are contiguous)."""
+        if rep is None:
+            assert self.J == 1 or n == 0, 'an engine with replicas needs rep= for its folds'
+            return None
+        rep = np.asarray(rep, dtype=np.int64)
+        assert rep.shape == (n,) and (n == 0 or (rep.min() >= 0 and rep.max() < self.J))
+        assert (np.diff(rep) >= 0).all(), 'folds must be grouped by replica'
+        return rep
+
+    def run_gen(self, folds, return_details=False, bag_seeds=None, rep=None):
         """Generator form of run() on this engine's own stream only (no extra lanes): yields
         before every blocking read-back, returns the result dict.  The caller advances it with
         this engine's stream current (cv_align_decode_stream keeps several jobs in flight)."""
@@ -810,9 +851,11 @@ class CVEngine:
             yield 'sync'                     # constructor work still in flight
         self._ensure_ready()
         seeds = self._bag_seeds(folds, bag_seeds)
+        rep = self._check_rep(rep, len(folds))
         for s0 in range(0, len(folds), size):
             batch = _Batch(folds[s0:s0 + size])
             batch.bag_seeds = None if seeds is None else seeds[s0:s0 + size]
+            batch.rep = None if rep is None else rep[s0:s0 + size]
             res = yield from self._batch_start(batch, return_details)
             out['y_pred'] += res['y_pred']
             out['k2'] += res['k2']
@@ -868,12 +911,12 @@ class CVEngine:
                              o_tr=pk.add_ints(tr * self.T), o_te=pk.add_ints(np.asarray(te) * self.T)))
         return tabs
 
-    def _class_means_target(self, pk, tabs, B, Kmax):
+    def _class_means_target(self, pk, tabs, B, Kmax, xaddr=None):
         tv, T = self.views[0], self.T
         cmT = self.ws('cmT', (B, Kmax * T, tv.C))
         recs = np.zeros(B, dtype=_lib.CLASS_MEAN_DESC)
         ib = pk.iaddr(0)
-        recs['X'] = addr(tv.X)
+        recs['X'] = addr(tv.X) if xaddr is None else xaddr
         if not isinstance(tabs, dict):       # list of per-fold tables (CCA / none batches)
             tabs = dict(o_ptr=[tb['o_ptr'] for tb in tabs], o_mem=[tb['o_mem'] for tb in tabs],
                         Kp=[len(tb['present']) for tb in tabs])
@@ -1185,6 +1228,11 @@ class CVEngine:
         use_rank = (0 < self.pca_var < 1) and not joint
         R = Q if use_rank else Cm      # pca_var == 1: no rank reduction (mvlearn _mcca_gevp)
         tv = self.views[0]
+        J = self.J
+        rep = getattr(batch, 'rep', None)
+        rep = np.zeros(B, dtype=np.int64) if rep is None else np.asarray(rep, dtype=np.int64)
+        assert J == 1 or not (joint or align_only), 'replicas: MCCA decode batches only'
+        xaddr0 = np.array([addr(self.rviews[j][0].X) for j in range(J)], dtype=np.int64)[rep]   # target X per fold
         launches0 = ctx.launches()
         t_pack = time.perf_counter()
         pk.reset()
@@ -1231,10 +1279,13 @@ class CVEngine:
         Ksa = shared2d.sum(axis=1).astype(np.int64)
         if Ksa.min() == 0:
             raise ValueError('no alignment class is shared by all patients in some fold')
-        uniq, first, inv = np.unique(shared2d, axis=0, return_index=True, return_inverse=True)
+        # folds with the same (replica, shared class set) share everything that depends on it
+        uniq, first, inv = np.unique(np.column_stack([rep, shared2d.astype(np.int64)]), axis=0,
+                                     return_index=True, return_inverse=True)
         inv = np.asarray(inv).ravel()
-        shared_u = [np.nonzero(u)[0].astype(np.int64) for u in uniq]
-        keys_u = [sh.tobytes() for sh in shared_u]
+        rep_u = uniq[:, 0]
+        shared_u = [np.nonzero(u)[0].astype(np.int64) for u in uniq[:, 1:]]
+        keys_u = [(int(r), sh.tobytes()) for r, sh in zip(rep_u, shared_u)]
         shared = [shared_u[u] for u in inv]
         Kmax, Ks = int(Kp.max()), Ksa.tolist()
         KTmax = int(Ksa.max()) * T
@@ -1259,7 +1310,7 @@ class CVEngine:
             o_nj = pk.add_ints(np.full(B, nJ, dtype=np.int32))
         else:
             ranks = np.zeros((B, P), dtype=np.int32)
-            ranks[:, 1:] = self.cross_rank[None, :]
+            ranks[:, 1:] = self.cross_rank[rep]
             o_rank = pk.add_ints(ranks)
             # slot of every (fold, view) problem; solve list = targets + cache misses
             n_padC = 128 if Cm <= 128 else _ceil(Cm, 128)
@@ -1271,7 +1322,7 @@ class CVEngine:
                 pending = {}
                 if P > 1:
                     rows_u = np.zeros((len(shared_u), P - 1), dtype=np.int64)
-                    for u, ku in enumerate(keys_u):
+                    for u, ku in enumerate(keys_u):      # ku = (replica, class set)
                         for v in range(1, P):
                             key = (v, ku)
                             sl = vs['keys'].get(key)
@@ -1318,9 +1369,15 @@ class CVEngine:
             np.add.at(hits, (np.nonzero(mtr)[0], TR[mtr]), 1)
             np.add.at(hits, (np.nonzero(mte)[0], TE[mte]), 1)
             use_te = bool((hits == 1).all()) and int(n_te_a.sum()) <= int(n_tr_a.sum())
+            # rows of self.tg['trial']: replica * N + trial, then J * N + replica = minus the sum of
+            # the replica's trials; a fold's Gram is -(listed rows) (held-out form) or +(train rows)
             La, Lm = (TE, mte) if use_te else (TR, mtr)
-            o_lptr = pk.add_ints(np.concatenate([[0], np.cumsum(Lm.sum(axis=1))]))
-            o_list = pk.add_ints(La[Lm])
+            Lf = np.where(Lm, La + rep[:, None] * tv.N, -1)
+            if use_te:
+                Lf = np.concatenate([(J * tv.N + rep)[:, None], Lf], axis=1)
+            Lk = Lf >= 0
+            o_lptr = pk.add_ints(np.concatenate([[0], np.cumsum(Lk.sum(axis=1))]))
+            o_list = pk.add_ints(Lf[Lk])
         # pooled layout
         n_tr, n_te = n_tr_a.tolist(), n_te_a.tolist()
         cross_N = [self.views[v].N for v in range(1, P)]
@@ -1329,6 +1386,7 @@ class CVEngine:
         n_pad = _ceil(max(a + b for a, b in zip(n_pool, n_te)), 128)
         F = T * Q
         tc_proj = (not align_only) and self._tc_proj_ready(Q)
+        assert J == 1 or tc_proj, 'replicas need the tensor-core projection (use_tensor_cores=True)'
         ycross = getattr(self, '_ycross', None)
         if ycross is None:
             ycross = self._ycross = (np.concatenate([self.views[v].y for v in range(1, P)])
@@ -1380,13 +1438,13 @@ class CVEngine:
         ib = pk.iaddr(0)
 
         # ---- descriptors, stage A (filled column-wise: one numpy op per field)
-        cmT, r_cm = self._class_means_target(pk, tabs, B, Kmax)
+        cmT, r_cm = self._class_means_target(pk, tabs, B, Kmax, xaddr=xaddr0)
         fi = np.arange(B, dtype=np.int64)
         # base address of the class-mean array of every (fold, view)
         cmb = np.empty((B, P), dtype=np.int64)
         cmb[:, 0] = addr(cmT) + 4 * Kmax * T * tv.C * fi
         for v in range(1, P):
-            cmb[:, v] = addr(self.cm[v])
+            cmb[:, v] = addr(self.cm[v]) + 4 * self.cm[v][0].numel() * rep
         segb = ib + 4 * o_seg                       # (B, P) segment-table addresses
         Ksa = np.asarray(Ks, dtype=np.int64)
         o_tr = ib + 4 * o_trv
@@ -1452,7 +1510,7 @@ class CVEngine:
             esz = cov.element_size()
             mub = addr(mu) + 4 * Cm * slot               # (B, P) mean vectors (slots)
             r_gt = np.zeros(B, dtype=_lib.GRAM_TN_DESC)
-            r_gt['A'] = r_gt['B'] = addr(tv.X)
+            r_gt['A'] = r_gt['B'] = xaddr0
             r_gt['segA'] = r_gt['segB'] = o_tr
             r_gt['out'] = addr(Gt) + Gt.element_size() * n_padC * n_padC * fi
             r_gt['nseg'], r_gt['seg_len'] = n_tr, T
@@ -1535,7 +1593,7 @@ class CVEngine:
             # size of the reduced GEVP: the target's rank is only known on the device (<= R), the
             # cross patients' ranks are fold-invariant and known here
             if use_rank:
-                n_m_max = R + int(np.minimum(self.cross_rank, R).sum())
+                n_m_max = R + int(np.minimum(self.cross_rank, R).sum(axis=1).max())
             else:
                 n_m_max = sum(min(R, vw.C) for vw in self.views)
             n_padM = 128 if n_m_max <= 128 else _ceil(n_m_max, 128)
@@ -1650,7 +1708,7 @@ class CVEngine:
                 Gt.zero_()
             if use_rank:
                 if downdate:     # train-set Gram = all-trials Gram - held-out trials (or sum of train)
-                    ctx.call('cpsd_sum_mats_f64', ptr(self.tg['all']) if use_te else ptr(None),
+                    ctx.call('cpsd_sum_mats_f64', ptr(None),
                              ptr(self.tg['trial']), 128 * 128, ctypes_int_ptr(pk.iaddr(o_lptr)),
                              ctypes_int_ptr(pk.iaddr(o_list)), -1.0 if use_te else 1.0, ptr(Gt),
                              128 * 128, 128 * 128, B)
@@ -1715,8 +1773,11 @@ class CVEngine:
                      ptr(None) if joint else ctypes_int_ptr(pk.iaddr(o_slot)),
                      Cm, cdim_dev, Q, tcp['ltc'], ptr(tcp['lthi']), ptr(tcp['ltlo']), ptr(tcp['mul']),
                      B * P)
-            ctx.call('cpsd_proj_tc', ptr(tcp['xmaps']), ptr(tcp['ltmaps']), P, B, T, Q, tcp['ltc'],
+            fbeg = np.searchsorted(rep, np.arange(J)).astype(np.int32)      # fold range of every replica
+            fcnt = (np.searchsorted(rep, np.arange(J), side='right') - fbeg).astype(np.int32)
+            ctx.call('cpsd_proj_tc_rep', ptr(tcp['xmaps']), ptr(tcp['ltmaps']), P, J, B, T, Q, tcp['ltc'],
                      ctypes.c_void_p(tcp['ntr'].ctypes.data), ctypes.c_void_p(tcp['nch'].ctypes.data),
+                     ctypes.c_void_p(fbeg.ctypes.data), ctypes.c_void_p(fcnt.ctypes.data),
                      Nmax, ctypes_int_ptr(pk.iaddr(o_dst)), ptr(tcp['mul']), ptr(Zall), n_pad * F,
                      tcp['sms'])
         else:

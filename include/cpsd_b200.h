@@ -128,6 +128,15 @@ int cpsd_proj_tc_prep(const float* L, int ldl, long long strideL, const float* m
 int cpsd_proj_tc(const void* xmaps_dev, const void* ltmaps_dev, int P, int B, int T, int Q, int ltc,
                  const int* n_trials_host, const int* n_chan_host, int n_max, const int* dst_row,
                  const float* muL, float* Y, long long strideY, int num_sms, cudaStream_t stream);
+/* the same for several REPLICAS of the patient set in one launch (independent jobs with the same
+ * shapes whose folds share a batch, cv_align_decode_stream): xmaps / n_trials / n_chan hold
+ * n_rep * P entries (replica-major); replica r is multiplied with the folds
+ * [fold_beg_host[r], fold_beg_host[r] + fold_cnt_host[r]) of the batch */
+int cpsd_proj_tc_rep(const void* xmaps_dev, const void* ltmaps_dev, int P, int n_rep, int B, int T,
+                     int Q, int ltc, const int* n_trials_host, const int* n_chan_host,
+                     const int* fold_beg_host, const int* fold_cnt_host, int n_max,
+                     const int* dst_row, const float* muL, float* Y, long long strideY, int num_sms,
+                     cudaStream_t stream);
 /* A B^T over the long feature axis: Gram of the pooled matrix for the decoder-stage PCA
  * (decomposition/DimRedReshape.py:47-49 -> sklearn PCA full SVD). */
 int cpsd_gram_nt(const cpsd_gram_nt_desc* descs, int nprob, int m_max, int n_max,

@@ -22,16 +22,17 @@ def jobs(n, s0):
         yield host_pts[0], host_pts[1:], bench.step_folds(y0, s0 + s)
 
 
-for depth in [int(a) for a in sys.argv[1:]] or [8, 12, 16, 24]:
-    for _ in cp.cv_align_decode_stream(jobs(depth + 2, 77), depth=depth, **kw):
+for spec in sys.argv[1:] or ['8:1', '14:7', '21:7']:
+    depth, group = (int(x) for x in spec.split(':'))
+    for _ in cp.cv_align_decode_stream(jobs(depth + 2, 77), depth=depth, group=group, **kw):
         pass
     torch.cuda.synchronize()
-    n = 48
+    n = 56
     cp.cv_align_decode_stream.idle_s = 0.0
     t0 = time.perf_counter()
-    for _ in cp.cv_align_decode_stream(jobs(n, 500), depth=depth, **kw):
+    for _ in cp.cv_align_decode_stream(jobs(n, 500), depth=depth, group=group, **kw):
         pass
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    print('depth %2d: %.2f ms per 20-fold job, %.0f folds/s, scheduler idle %.0f %%'
-          % (depth, 1e3 * dt / n, 20 * n / dt, 100 * cp.cv_align_decode_stream.idle_s / dt), flush=True)
+    print('depth %2d group %d: %.2f ms per 20-fold job, %.0f folds/s, scheduler idle %.0f %%'
+          % (depth, group, 1e3 * dt / n, 20 * n / dt, 100 * cp.cv_align_decode_stream.idle_s / dt), flush=True)
