@@ -374,7 +374,7 @@ def main():
     ap.add_argument('--no-tc', action='store_true', help='fp32 SIMT pooled Gram instead of tcgen05')
     ap.add_argument('--cpu-folds', type=int, default=2, help='folds in the cpu_baseline sample')
     ap.add_argument('--e2e-steps', type=int, default=None)
-    ap.add_argument('--e2e-depth', type=int, default=14, help='steps in flight in the e2e measurement')
+    ap.add_argument('--e2e-depth', type=int, default=21, help='steps in flight in the e2e measurement')
     ap.add_argument('--e2e-group', type=int, default=7,
                     help='steps sharing one engine batch in the e2e measurement (replicas: every step still '
                          'uploads its own inputs; 7 x 20 folds = one 140-fold batch)')

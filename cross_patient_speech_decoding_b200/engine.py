@@ -43,7 +43,7 @@ def _lane_stream(device, i):
 class View:
     """One patient resident on the device."""
 
-    def __init__(self, ctx, X, y, y_align, cls_ids):
+    def __init__(self, ctx, X, y, y_align, cls_ids, upload_stream=None):
         # X: numpy array or (pinned) CPU torch tensor, float64 (the reference's dtype) or
         # float32.  float64 is copied as is and cast on the device, so the host never touches
         # the 29 M samples per patient.
@@ -81,12 +81,33 @@ class View:
         self.N, self.T, self.C = (int(v) for v in host.shape)
         if not host.is_pinned():
             host = host.pin_memory()
-        raw = host.to(ctx.device, non_blocking=True)
-        if raw.dtype == torch.float64:
-            self.X = ctx.empty((self.N * self.T, self.C))
-            ctx.call('cpsd_cast_f64_f32', ptr(raw), ptr(self.X), raw.numel())
+        if upload_stream is not None:
+            # all uploads of a streamed run go through ONE stream, in submission order: the first
+            # job's data is complete (and its kernels start) while the later jobs still copy --
+            # uploads issued on every job's own stream share the link and all finish late
+            # (buffers come from the lane's own allocator pool; the upload stream only borrows them
+            # between two events, so no cross-stream allocator bookkeeping is needed)
+            lane = torch.cuda.current_stream(ctx.device)
+            raw = torch.empty(host.shape, dtype=host.dtype, device=ctx.device)
+            f64 = raw.dtype == torch.float64
+            self.X = ctx.empty((self.N * self.T, self.C)) if f64 else raw.view(self.N * self.T, self.C)
+            ev0 = torch.cuda.Event()
+            ev0.record(lane)
+            upload_stream.wait_event(ev0)
+            with torch.cuda.stream(upload_stream):    # DMA only: kernels would queue behind the busy SMs
+                raw.copy_(host, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(upload_stream)
+            lane.wait_event(ev)
+            if f64:
+                ctx.call('cpsd_cast_f64_f32', ptr(raw), ptr(self.X), raw.numel())
         else:
-            self.X = raw.view(self.N * self.T, self.C)
+            raw = host.to(ctx.device, non_blocking=True)
+            if raw.dtype == torch.float64:
+                self.X = ctx.empty((self.N * self.T, self.C))
+                ctx.call('cpsd_cast_f64_f32', ptr(raw), ptr(self.X), raw.numel())
+            else:
+                self.X = raw.view(self.N * self.T, self.C)
         self._host = host                                     # keep staging alive until done
         self.y = np.asarray(y).astype(np.int64)
         self.cls = np.asarray(cls_ids, dtype=np.int32)        # alignment class id per trial
@@ -109,7 +130,7 @@ class CVEngine:
                  topk_block=128, topk_iters=8, topk_tol=5e-6, topk_rounds=3, n_lanes=2, lane=0,
                  topk_tf32_iters=5, topk_gap_tol=0.05, decoder='linear', class_weight=None, svc_tol=1e-3,
                  svc_gamma='scale', svc_max_iter=1000000, joint_cap=None, n_estimators=10,
-                 replicas=None):
+                 replicas=None, upload_stream=None):
         # decoder: 'linear' = one-vs-rest squared-hinge linear SVM (the north star's dual-CD
         # decoder); 'svc_rbf' / 'svc_linear' = libsvm-style C-SVC with one-vs-one votes, the
         # reference scripts' literal SVC(kernel=..., class_weight=...)
@@ -130,6 +151,7 @@ class CVEngine:
         # replica a fold reads -- so the latency-bound solver launches are amortised over all of
         # them.  MCCA with the tensor-core projection only.
         self._replicas = list(replicas or [])
+        self._upload_stream = upload_stream
         base = Context.get(device)
         self.lane = int(lane)
         self.stream = _lane_stream(base.device, self.lane)
@@ -189,12 +211,13 @@ class CVEngine:
             assert isinstance(n_comp, (int, np.integer)) and n_comp >= 1
         views = [target] + list(cross)
         ids, self.vocab = class_ids([v[2] if v[2] is not None else v[1] for v in views])
-        self.views = [View(self.ctx, v[0], v[1], v[2], i) for v, i in zip(views, ids)]
+        us = self._upload_stream
+        self.views = [View(self.ctx, v[0], v[1], v[2], i, us) for v, i in zip(views, ids)]
         self.rviews = [self.views]
         for rt, rc in self._replicas:
             rv = [rt] + list(rc)
             assert method == 'mcca' and len(rv) == len(views), 'replicas: MCCA, same patient count'
-            vs_r = [View(self.ctx, v[0], v[1], v[2], i) for v, i in zip(rv, ids)]
+            vs_r = [View(self.ctx, v[0], v[1], v[2], i, us) for v, i in zip(rv, ids)]
             for a, b in zip(vs_r, self.views):
                 assert (a.N, a.T, a.C) == (b.N, b.T, b.C), 'replicas must have the primary job\'s shapes'
             self.rviews.append(vs_r)
