@@ -126,7 +126,10 @@ def lstsq_gram(X, Y, device=None):
     Y = np.ascontiguousarray(Y, dtype=np.float32)
     rows, C = X.shape
     q = Y.shape[1]
-    assert Y.shape[0] == rows and C <= 128
+    assert Y.shape[0] == rows
+    if C > 128:
+        raise ValueError('lstsq_gram: at most 128 columns (channels per patient) -- the normal equations are '
+                         'solved by a shared-memory Cholesky; the reference (JointPCA.py:203-206) has no limit')
     Xd, Yd = ctx.upload(X), ctx.upload(Y)
     pk = HostPack(ctx)
     o = pk.add_ints([0])
