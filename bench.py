@@ -379,6 +379,7 @@ def main():
                     help='steps sharing one engine batch in the e2e measurement (replicas: every step still '
                          'uploads its own inputs; 7 x 20 folds = one 140-fold batch)')
     ap.add_argument('--batch', type=int, default=148, help='max folds per engine batch')
+    ap.add_argument('--lanes', type=int, default=2, help='execution lanes (batches in flight) of the engine')
     ap.add_argument('--config', default='headline', choices=['headline', 'sweep', 'subsample'],
                     help='headline = BASELINE configs[1] (the driver\'s run); sweep = configs[2] (latent-size '
                          'sweep x methods); subsample = configs[3] (electrode subsampling); the last two run '
@@ -429,7 +430,7 @@ def main():
             dist.destroy_process_group()
         return
     kw = dict(method='mcca', n_comp=30, regs=0.5, pca_var=0.8, decoder_var=0.8,
-              use_tensor_cores=not args.no_tc, max_batch=args.batch)
+              use_tensor_cores=not args.no_tc, max_batch=args.batch, n_lanes=args.lanes)
     eng = CVEngine(pts[0], pts[1:], device='cuda:%d' % local, **kw)
     dev = eng.ctx.device
 
@@ -457,9 +458,9 @@ def main():
     # size every workspace for a full engine batch before anything is timed
     # (two full batches: both execution lanes allocate their workspaces)
     big = []
-    while len(big) < 2 * args.batch:
+    while len(big) < args.lanes * args.batch:
         big += step_folds(y0, 20_000 + len(big))
-    eng.run(big[:2 * args.batch])
+    eng.run(big[:args.lanes * args.batch])
     if args.warmup:
         run_steps([10_000 + rank * 1000 + w for w in range(args.warmup)])
     sync_all()
@@ -499,7 +500,7 @@ def main():
     e2e_steps = args.e2e_steps or max(args.steps, 12)
     host_pts = [(torch.from_numpy(np.ascontiguousarray(X)).pin_memory(), y, ya)
                 for X, y, ya in pts]
-    kw_e2e = dict(kw, max_batch=N_FOLDS)
+    kw_e2e = dict(kw, max_batch=N_FOLDS, n_lanes=2)
 
     def jobs(n, seed0):
         for s in range(n):
@@ -611,7 +612,7 @@ def main():
                                     'stages; 3xTF32 tcgen05 projection and pooled Gram; top-k '
                                     'subspace iteration (TF32 then 3xTF32 tcgen05) for the decoder '
                                     'PCA; fp64 Newton SVM',
-                       'lanes': 2,
+                       'lanes': args.lanes,
                        'l2': 'working set per step ~2 GB (20 pooled 1152x6000 matrices + Grams) '
                              '>> 126 MB L2, no explicit flush'},
             'e2e': {'value': e2e_val, 'unit': 'folds/s',

@@ -11,6 +11,7 @@ once by the kernels of libcpsd_b200.so.  Patient data stays resident in HBM; per
 the host only uploads fold index tables + descriptor records and downloads predictions.
 """
 import ctypes
+import os
 import time
 
 import numpy as np
@@ -114,6 +115,10 @@ class View:
         self.h2d_bytes = host.numel() * host.element_size()
 
 
+class _TopkRetry(Exception):
+    """A speculatively used top-k round failed its acceptance test: run the batch again."""
+
+
 class _Batch(list):
     """The folds of one engine batch plus what travels with them (bagging seeds, replica ids)."""
     bag_seeds = None
@@ -130,7 +135,7 @@ class CVEngine:
                  topk_block=128, topk_iters=8, topk_tol=5e-6, topk_rounds=3, n_lanes=2, lane=0,
                  topk_tf32_iters=5, topk_gap_tol=0.05, decoder='linear', class_weight=None, svc_tol=1e-3,
                  svc_gamma='scale', svc_max_iter=1000000, joint_cap=None, n_estimators=10,
-                 replicas=None, upload_stream=None):
+                 replicas=None, upload_stream=None, speculative_topk=True):
         # decoder: 'linear' = one-vs-rest squared-hinge linear SVM (the north star's dual-CD
         # decoder); 'svc_rbf' / 'svc_linear' = libsvm-style C-SVC with one-vs-one votes, the
         # reference scripts' literal SVC(kernel=..., class_weight=...)
@@ -152,6 +157,11 @@ class CVEngine:
         # them.  MCCA with the tensor-core projection only.
         self._replicas = list(replicas or [])
         self._upload_stream = upload_stream
+        # decoder-PCA top-k solver: launch the rest of the batch on the first round's result and
+        # verify its acceptance test with the batch's final read-back (one host sync per batch
+        # instead of two; a batch whose first round is not accepted is run again the slow way)
+        self.speculative_topk = bool(speculative_topk) and os.environ.get('CPSD_SPECULATIVE_TOPK', '1') != '0'
+        self._spec = False
         base = Context.get(device)
         self.lane = int(lane)
         self.stream = _lane_stream(base.device, self.lane)
@@ -385,6 +395,18 @@ class CVEngine:
                          ctypes.c_void_p(mp), ctypes.c_void_p(stage.data_ptr()))
                 cache[tag] = (key, stage)
         tol = self.topk_tol if tol is None else tol
+        gtol_ = self.topk_gap_tol if gap_tol is None else gap_tol
+        if self._spec and tag == 'pool':
+            f64s = getattr(self, '_tk_f64', None) or {}
+            self._topk_round(tc, K, n_pad, n_dev, nprob, m, 1, ws, evals, tot, resid, status,
+                             tcw if tc else None, mp if tc else None, int(f64s.get(tag, False)))
+            ctx.call('cpsd_select_k_total', ptr(evals), evals.shape[-1], ptr(None), m, ptr(tot),
+                     thr, mode, 1, min(kcap, m), ptr(k2), 1, nprob)
+            info.update(rounds=1, speculative=True, f64_gram=bool(f64s.get(tag, False)))
+            self._spec_check = dict(k2=k2, resid=resid, evals=evals, status=status, m=m, mode=mode,
+                                    tol=tol, gtol=gtol_, nprob=nprob, info=info)
+            self._k2_max = max(m - 8, 1)          # upper bound: sizes shared memory only
+            return V, m, 2 * n_pad * m
         prev = None
         # Gram of the Cholesky-QR steps: fp32 first; a tag whose block once lost rank that way
         # (leading spectrum spanning > ~3e3) uses the fp64-accumulated Gram from then on
@@ -395,17 +417,8 @@ class CVEngine:
         # still shrinks the worst residual 4x -- far cheaper than the full solver it avoids
         rnd, fresh = 0, 1
         while rnd < 2 * self.topk_rounds:
-            if tc:
-                ctx.call('cpsd_eig_sym_topk_tc', ptr(K), n_pad, n_pad * n_pad, n_pad, _p(n_dev), 0,
-                         nprob, m, self.topk_iters, fresh, ptr(ws), ptr(evals),
-                         evals.shape[-1], ptr(tot), ptr(resid), ptr(status), self.eig_sweeps + 3,
-                         self.eig_tol, ptr(tcw), ctypes.c_void_p(mp), self.topk_tf32_iters,
-                         int(f64.get(tag, False)))
-            else:
-                ctx.call('cpsd_eig_sym_topk', ptr(K), n_pad, n_pad * n_pad, n_pad, _p(n_dev), 0,
-                         nprob, m, self.topk_iters, fresh, ptr(ws), ptr(evals),
-                         evals.shape[-1], ptr(tot), ptr(resid), ptr(status), self.eig_sweeps + 3,
-                         self.eig_tol, int(f64.get(tag, False)))
+            self._topk_round(tc, K, n_pad, n_dev, nprob, m, fresh, ws, evals, tot, resid, status,
+                             tcw if tc else None, mp if tc else None, int(f64.get(tag, False)))
             ctx.call('cpsd_select_k_total', ptr(evals), evals.shape[-1], ptr(None), m, ptr(tot),
                      thr, mode, 1, min(kcap, m), ptr(k2), 1, nprob)
             yield 'sync'
@@ -449,6 +462,48 @@ class CVEngine:
                 return None
             prev = worst
         return None
+
+    def _topk_round(self, tc, K, n_pad, n_dev, nprob, m, fresh, ws, evals, tot, resid, status, tcw,
+                    mp, f64_gram):
+        """One round (topk_iters subspace iterations + Rayleigh-Ritz + residuals) of the top-k solver."""
+        ctx = self.ctx
+        if tc:
+            ctx.call('cpsd_eig_sym_topk_tc', ptr(K), n_pad, n_pad * n_pad, n_pad, _p(n_dev), 0,
+                     nprob, m, self.topk_iters, fresh, ptr(ws), ptr(evals),
+                     evals.shape[-1], ptr(tot), ptr(resid), ptr(status), self.eig_sweeps + 3,
+                     self.eig_tol, ptr(tcw), ctypes.c_void_p(mp), self.topk_tf32_iters, f64_gram)
+        else:
+            ctx.call('cpsd_eig_sym_topk', ptr(K), n_pad, n_pad * n_pad, n_pad, _p(n_dev), 0,
+                     nprob, m, self.topk_iters, fresh, ptr(ws), ptr(evals),
+                     evals.shape[-1], ptr(tot), ptr(resid), ptr(status), self.eig_sweeps + 3,
+                     self.eig_tol, f64_gram)
+
+    def _verify_spec(self):
+        """Acceptance test of a speculatively used top-k round (same criteria as eig_topk), run on
+        the batch's final read-back.  Raises _TopkRetry when the round would not have been accepted."""
+        chk = self.__dict__.pop('_spec_check', None)
+        if chk is None:
+            return
+        m, nprob, info = chk['m'], chk['nprob'], chk['info']
+        k2h = chk['k2'].cpu().numpy()
+        rh = chk['resid'].cpu().numpy()
+        evh = chk['evals'][:, :m].cpu().numpy()
+        ok = not chk['status'].cpu().numpy().any()
+        if ok and chk['mode'] == 0 and (k2h >= m - 8).any():
+            ok = False
+        if ok:
+            rmax = np.array([rh[f, :k2h[f]].max() if k2h[f] > 0 else 0.0 for f in range(nprob)])
+            worst = float((rmax / np.maximum(evh[:, 0], 1e-30)).max())
+            kk = np.clip(k2h, 1, m - 1)
+            ar = np.arange(nprob)
+            gap = evh[ar, kk - 1] - evh[ar, kk]
+            gap_ok = bool((rmax <= chk['gtol'] * np.maximum(gap, 0.0)).all()) or not np.isfinite(chk['gtol'])
+            info.update(resid=worst, gap_ok=gap_ok, k2_max=int(k2h.max()))
+            ok = worst <= chk['tol'] and gap_ok
+        info['ok'] = ok
+        if not ok:
+            raise _TopkRetry()
+        self._k2_max = max(int(k2h.max()), 1)
 
     # ------------------------------------------------------------------ tensor-core projection
     def _tc_proj_ready(self, Q):
@@ -896,12 +951,24 @@ class CVEngine:
         self._pack_i ^= 1
         return self._batch_mcca_gen(batch, want_details, align_only, pk)
 
-    def _batch_start(self, batch, want_details):
-        """Generator of one batch for this engine's method."""
+    def _batch_once(self, batch, want_details):
         if self.method in ('mcca', 'jointpca'):
             return self._mcca_start(batch, want_details)
         from .engine_cca import batch_cca_gen
         return batch_cca_gen(self, batch, want_details)
+
+    def _batch_start(self, batch, want_details):
+        """Generator of one batch for this engine's method: speculative first (see
+        speculative_topk), again without speculation when the top-k round was not acceptable."""
+        self._spec = self.speculative_topk and self.decoder == 'linear'
+        self._spec_check = None
+        try:
+            res = yield from self._batch_once(batch, want_details)
+        except _TopkRetry:
+            self._spec = False
+            self.stats['topk_retries'] = self.stats.get('topk_retries', 0) + 1
+            res = yield from self._batch_once(batch, want_details)
+        return res
 
     def _batch_mcca(self, batch, want_details, align_only=False):
         self._ensure_ready()
@@ -1814,6 +1881,7 @@ class CVEngine:
                             o_nte, n_te_max)
         self.mark('end')
         yield 'sync'
+        self._verify_spec()
         yh = yhat.cpu().numpy()
         k2h = k2.cpu().numpy()
         st = status.cpu().numpy()

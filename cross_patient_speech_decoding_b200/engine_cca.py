@@ -348,6 +348,7 @@ def batch_cca_gen(eng, batch, want_details):
                        n_te_max)
     eng.mark('end')
     yield 'sync'
+    eng._verify_spec()
     yh = yhat.cpu().numpy()
     k2h = k2.cpu().numpy()
     eng._check_decoder(info, B)
