@@ -36,6 +36,10 @@ N_FOLDS = 20
 METRIC = 'CV align+decode folds/sec (MCCA->PCA->SVM)'
 WORKLOAD = ('mcca_8patients_144x200x128_20fold: MCCA(n_comp=30, regs=0.5, pca_var=0.8) -> '
             'PCA(0.8) -> OvR linear SVM, 20 folds per step')
+# identical in both arms (the driver compares it)
+CONFIG = {'workload': WORKLOAD, 'folds_per_step_per_gpu': N_FOLDS,
+          'l2': 'inputs larger than L2: working set per step ~2 GB (20 pooled 1152x6000 matrices + Grams) '
+                '>> 126 MB L2, no explicit flush'}
 
 
 def peaks():
@@ -189,8 +193,9 @@ def run_reference(args, rank):
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / max(n, 1),
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic', 'impl': 'reference',
-            'config': {'workload': WORKLOAD, 'step': '1 fold of the 20-fold workload (bounded '
-                       'sample)', 'host': 'numpy/scipy/scikit-learn float64'},
+            'config': CONFIG,
+            'reference_config': {'step': '1 fold of the 20-fold workload (bounded sample)',
+                                 'host': 'numpy/scipy/scikit-learn float64'},
             'cpu_baseline': {'value': val, 'unit': 'folds/s', 'cores': cores, 'kind': 'port',
                              'sample': '%d single-fold steps of the 8-patient 20-fold MCCA workload '
                                        '(oracle/pipeline_port.py; /root/reference is absent on the '
@@ -604,17 +609,15 @@ def main():
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_max / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'folds_per_step_per_gpu': N_FOLDS,
-                       'engine_batch_folds': args.batch,
-                       'parallelism': 'folds sharded over %d GPU(s), one NCCL all_gather of '
-                                      'accuracies' % world,
-                       'precision': 'fp32 storage; fp64 scatter + eigen-solver for the alignment PCA '
-                                    'stages; 3xTF32 tcgen05 projection and pooled Gram; top-k '
-                                    'subspace iteration (TF32 then 3xTF32 tcgen05) for the decoder '
-                                    'PCA; fp64 Newton SVM',
-                       'lanes': args.lanes,
-                       'l2': 'working set per step ~2 GB (20 pooled 1152x6000 matrices + Grams) '
-                             '>> 126 MB L2, no explicit flush'},
+            'config': CONFIG,
+            'engine_config': {'engine_batch_folds': args.batch,
+                              'parallelism': 'folds sharded over %d GPU(s), one NCCL all_gather of '
+                                             'accuracies' % world,
+                              'precision': 'fp32 storage; fp64 scatter + eigen-solver for the alignment '
+                                           'PCA stages; 3xTF32 tcgen05 projection and pooled Gram; top-k '
+                                           'subspace iteration (TF32 then 3xTF32 tcgen05) for the decoder '
+                                           'PCA; fp64 Newton SVM',
+                              'lanes': args.lanes},
             'e2e': {'value': e2e_val, 'unit': 'folds/s',
                     'h2d_bytes_per_step': e2e_h2d // max(e2e_steps, 1),
                     'd2h_bytes_per_step': e2e_d2h // max(e2e_steps, 1), 'steps': e2e_steps,
