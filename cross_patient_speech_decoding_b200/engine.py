@@ -960,12 +960,15 @@ class CVEngine:
     def _batch_start(self, batch, want_details):
         """Generator of one batch for this engine's method: speculative first (see
         speculative_topk), again without speculation when the top-k round was not acceptable."""
-        self._spec = self.speculative_topk and self.decoder == 'linear'
+        self._spec = (self.speculative_topk and self.decoder == 'linear'
+                      and not getattr(self, '_spec_failed', False))
         self._spec_check = None
         try:
             res = yield from self._batch_once(batch, want_details)
         except _TopkRetry:
+            # this workload needs more than one round: no more speculation on this lane
             self._spec = False
+            self._spec_failed = True
             self.stats['topk_retries'] = self.stats.get('topk_retries', 0) + 1
             res = yield from self._batch_once(batch, want_details)
         return res
@@ -1100,16 +1103,27 @@ class CVEngine:
         Ste = self.ws('pool_Ste', (B, kcap, n_te_max))
         yhat = self.ws('yhat', (B, n_te_max), I32)
         m = self.topk_block
+        # 'auto': the top-k iteration first (it converges in one round whenever the retained
+        # components are a small, well separated part of the spectrum -- also on small pools: 2-patient
+        # CCA 1980 -> 3160 folds/s), the full block-Jacobi solver when it is not accepted; an engine
+        # whose SMALL pools (n_pad <= 512) needed more than two rounds (flat noisy spectra) goes
+        # straight to the full solver from then on
+        slow = getattr(self, '_topk_slow', None)
+        if slow is None:
+            slow = self._topk_slow = {}
         use_topk = (self.pool_solver != 'full' and n_pad > 128 and mode in (0, 3)
                     and (mode == 0 or int(thr) <= m - 8)
                     and (self.pool_solver == 'topk'
-                         or (min(n_pool) - 1 >= 3 * m and F >= 3 * m)))
+                         or (not slow.get('pool') and min(n_pool) - 1 >= m and F >= m)))
         perm_p = ptr(None)
         if use_topk:
             got = yield from self.eig_topk(Kall, n_pad, npool_dev, B, m, evals, 'pool', thr, mode,
                                            kcap, k2)
             if got is not None:
                 V, ldv, sV = got
+            # (only where the full solver is the cheaper alternative: small pools)
+            if n_pad <= 512 and (got is None or self.stats['topk'].get('rounds', 1) > 2):
+                slow['pool'] = True
             self.mark('pool_eigvecs')
         if V is None:
             V = self.ws('pool_V', (B, n_pad, n_pad))
