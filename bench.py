@@ -603,6 +603,14 @@ def main():
     latency = None
     if rank == 0 and world == 1 and not args.no_latency:
         latency = predict_latency(pts)
+    # whole-step roofline against SURVEY 8(d)'s per-fold work without reuse: 30 GF of tensor-shaped
+    # work and 0.29 GB of streaming traffic per fold
+    step_roofline = {'tensor_gflop_per_fold': 30.0, 'hbm_gb_per_fold': 0.29,
+                     'tflops': 30.0e9 * value / 1e12, 'frac_of_bf16_sustained': 30.0e9 * value / 1e12 / peak_tf,
+                     'frac_of_tf32_measured': (30.0e9 * value / 1e12 / tf32_peak) if tf32_peak else None,
+                     'gbs': 0.29 * value, 'frac_of_hbm': 0.29 * value / pk['hbm_gbs'],
+                     'note': 'the step is a chain of latency-bound small solvers (tile Jacobi, Cholesky-QR, '
+                             'Newton SVM) around two dense kernels; see stages_ms_per_step'}
     if rank == 0:
         line = {
             'metric': METRIC, 'value': value, 'unit': 'folds/s', 'n_gpus': world,
@@ -630,7 +638,7 @@ def main():
             'gpu_launches': launches,
             'h2d_bytes_per_step': h2d // args.steps, 'd2h_bytes_per_step': d2h // args.steps,
             'clocks': clk.summary(),
-            'roofline': roofline, 'roofline_hbm': roofline_hbm,
+            'roofline': roofline, 'roofline_hbm': roofline_hbm, 'step_roofline': step_roofline,
             'stages_ms_per_step': {k: round(v, 3) for k, v in stages.items()},
             'stages_batch_folds': nprof,
             'reuse': eng.stats.get('view_solves', 0) and

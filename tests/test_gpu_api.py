@@ -427,3 +427,39 @@ def test_batched_search_matches_gridsearchcv(pkg):
     for k in ref:
         assert abs(ref[k] - got[k]) <= 0.03, (k, ref[k], got[k])
     assert out['best_params'] == cands[out['best_index']] and len(out['y_pred']) == 4
+
+
+def test_fused_predictor_matches_oracle_port(pkg):
+    """BASELINE config 5 (per-trial aligned projection + decode): FusedPredictor on models fitted
+    by the drop-in classes against the float64 CPU port of the reference path -- >= 99 % of 120
+    held-out labels per decoder class, at batch size 1 (one trial per call) and in one batch."""
+    from sklearn.pipeline import make_pipeline
+    from cross_patient_speech_decoding_b200.alignment.AlignCCA import AlignCCA
+    from cross_patient_speech_decoding_b200.alignment.AlignMCCA import AlignMCCA
+    from cross_patient_speech_decoding_b200.decoders.cross_pt_decoders import (
+        crossPtDecoder_mcca, crossPtDecoder_sepAlign)
+    from cross_patient_speech_decoding_b200.decoders.fused_predict import FusedPredictor
+    from cross_patient_speech_decoding_b200.decomposition.DimRedReshape import DimRedReshape
+    from cross_patient_speech_decoding_b200.decomposition.PCA import PCA
+    from cross_patient_speech_decoding_b200.folds import cv_splits
+    from cross_patient_speech_decoding_b200.svm import LinearSVC
+    from oracle import pipeline_port as port
+    pts = _patients(3, n_trials=120)
+    Xt, yt, yat = pts[0]
+    np.random.seed(12)
+    folds = cv_splits(yt, 4)
+    for cls, kw, method, nc in [
+            (crossPtDecoder_mcca, dict(aligner=AlignMCCA, n_comp=8, regs=0.5, pca_var=0.8), 'mcca', 8),
+            (crossPtDecoder_sepAlign, dict(aligner=AlignCCA, n_comp=0.9), 'cca', 0.9)]:
+        same = tot = 0
+        for tr, te in folds:
+            m = cls(pts[1:], make_pipeline(DimRedReshape(PCA, n_components=0.8), LinearSVC()), **kw)
+            m.fit(Xt[tr], yt[tr], y_align=yat[tr])
+            fp = FusedPredictor(m)
+            ref, _ = port.run_fold(pts[0], pts[1:], tr, te, method=method, n_comp=nc)
+            batch = fp.predict(Xt[te])
+            one = np.concatenate([fp.predict(Xt[i:i + 1]) for i in te[:6]])
+            assert np.array_equal(one, batch[:6])                # batch 1 == batched
+            same += int((batch == ref).sum())
+            tot += len(te)
+        assert tot >= 100 and same / tot >= 0.99, (method, same, tot)

@@ -97,7 +97,7 @@ def test_script_joint_branch_matches_port(lib_built, tmp_path):
     ref = np.concatenate([port.run_fold(tar, cross, tr, te, method='jointpca', n_comp=0.9)[0]
                           for tr, te in units])
     got = np.array(res['y_pred'][0])
-    assert got.shape == ref.shape and np.mean(got == ref) >= 0.9, float(np.mean(got == ref))
+    assert got.shape == ref.shape and np.mean(got == ref) >= 0.97, float(np.mean(got == ref))
 
 
 @pytest.mark.gpu
