@@ -415,6 +415,60 @@ extern "C" int cpsd_gather_channels(const float* src, int lds, const int* idx, i
   return CPSD_OK;
 }
 
+// Per-trial column sums in fp64 (sums[t][c] = sum over the T rows of trial t of X[t*T + r][c]) and
+// the covariance of a trial subset from per-trial statistics: with G = sum of the subset's
+// per-trial Grams X_t^T X_t and s = sum of its column sums over n = (#trials * T) rows,
+//     cov = (G - s s^T / n) / (n - 1),   mu = s / n
+// -- sklearn PCA's centred covariance (decoders/cross_pt_decoders.py:234-241 -> PCA.fit) of every
+// CV fold's train trials without another pass over the data: the per-trial statistics are
+// computed once per target, a fold is a list of trials (cpsd_sum_mats_f64).
+namespace {
+__global__ void __launch_bounds__(256)
+k_trial_colsum_f64(const float* __restrict__ X, int T, int C, int ldx, double* __restrict__ sums, int lds) {
+  const int t = blockIdx.x;
+  const float* Xt = X + (long long)t * T * ldx;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double a = 0.0;
+    for (int r = 0; r < T; ++r) a += (double)Xt[(long long)r * ldx + c];
+    sums[(long long)t * lds + c] = a;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_cov_from_sums(double* __restrict__ G, int ldg, long long strideG, const double* __restrict__ s, int lds,
+                const int* __restrict__ nrows, int C, float* __restrict__ mu, int ldmu) {
+  const int p = blockIdx.x;
+  const double n = (double)nrows[p];
+  double* Gp = G + (long long)p * strideG;
+  const double* sp = s + (long long)p * lds;
+  for (int e = threadIdx.x; e < C * C; e += blockDim.x) {
+    const int i = e / C, j = e - i * C;
+    Gp[(long long)i * ldg + j] = (Gp[(long long)i * ldg + j] - sp[i] * sp[j] / n) / (n - 1.0);
+  }
+  if (mu)
+    for (int c = threadIdx.x; c < C; c += blockDim.x) mu[(long long)p * ldmu + c] = (float)(sp[c] / n);
+}
+}  // namespace
+
+extern "C" int cpsd_trial_colsum_f64(const float* X, int n_trials, int T, int C, int ldx, double* sums,
+                                     int lds, cudaStream_t stream) {
+  CPSD_CHECK_ARG(n_trials >= 0 && T > 0 && C > 0 && ldx >= C && lds >= C, "trial_colsum_f64: bad dims");
+  if (n_trials == 0) return CPSD_OK;
+  k_trial_colsum_f64<<<n_trials, 256, 0, stream>>>(X, T, C, ldx, sums, lds);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
+
+extern "C" int cpsd_cov_from_sums(double* G, int ldg, long long strideG, const double* s, int lds,
+                                  const int* nrows_dev, int C, float* mu, int ldmu, int nprob,
+                                  cudaStream_t stream) {
+  CPSD_CHECK_ARG(nprob >= 0 && C > 0 && ldg >= C && lds >= C && nrows_dev != nullptr, "cov_from_sums: bad dims");
+  if (nprob == 0) return CPSD_OK;
+  k_cov_from_sums<<<nprob, 256, 0, stream>>>(G, ldg, strideG, s, lds, nrows_dev, C, mu, ldmu);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
+
 // Zeroes the columns j >= k[p / group] of problem p's (rows x cols) matrix: the read-in matrices
 // of a JointPCA whose component count is a variance fraction (JointPCA(n_components=0.9),
 // scripts/aligned_decode_svm_ncv.py:186-190) are computed at a fixed width and cut per fold.

@@ -659,6 +659,8 @@ class CVEngine:
             self._target_trial_grams()
             self._keep = [pk]                # staging of the kernels still in flight
         else:
+            if self.method in ('cca', 'none') and self.Cmax <= 128 and self.J == 1:
+                self._target_trial_grams(with_sums=True)       # per-fold PCA covariance by downdate
             if self.P > 1 and self.method != 'jointpca':
                 self._cross_pca()
             torch.cuda.current_stream(self.ctx.device).synchronize()
@@ -712,14 +714,14 @@ class CVEngine:
         self._keep_rk = pk
         return k.clone()
 
-    def _target_trial_grams(self):
+    def _target_trial_grams(self, with_sums=False):
         """Uncentred per-trial scatter matrices X_t^T X_t of the target (fp64), for every replica,
         followed by MINUS their sum per replica: the train-set Gram of a fold is
         -( -G_all + sum of the held-out trials' matrices ), one cpsd_sum_mats_f64 list per fold
         (rows: [replica * N + trial] ..., then [J * N + replica])."""
         self.tg = None
         tv = self.views[0]
-        if not (0 < self.pca_var < 1) or tv.C > 128:
+        if tv.C > 128 or (not with_sums and not (0 < self.pca_var < 1)):
             return
         ctx, T, J, N = self.ctx, self.T, self.J, tv.N
         pk = HostPack(ctx)
@@ -743,6 +745,15 @@ class CVEngine:
         ctx.call('cpsd_sum_mats_f64', ptr(None), ptr(G), 128 * 128, ctypes_int_ptr(pk.iaddr(o_ptr)),
                  ctypes_int_ptr(pk.iaddr(o_all)), -1.0, ptr(G, J * N * 128 * 128), 128 * 128, 128 * 128, J)
         self.tg = dict(trial=G, keep=pk)
+        if with_sums:
+            # per-trial column sums (fp64), then MINUS their total, in the same row order as G
+            S = ctx.zeros((J * N + J, 128), torch.float64)
+            for j in range(J):
+                ctx.call('cpsd_trial_colsum_f64', ptr(self.rviews[j][0].X), N, T, tv.C, tv.C,
+                         ptr(S, j * N * 128), 128)
+            ctx.call('cpsd_sum_mats_f64', ptr(None), ptr(S), 128, ctypes_int_ptr(pk.iaddr(o_ptr)),
+                     ctypes_int_ptr(pk.iaddr(o_all)), -1.0, ptr(S, J * N * 128), 128, 128, J)
+            self.tg['sums'] = S
 
     def _cross_pca(self):
         """sklearn PCA(n_comp) of every cross patient's (trials*time, channels) matrix

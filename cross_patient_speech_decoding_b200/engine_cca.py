@@ -50,6 +50,21 @@ def batch_cca_gen(eng, batch, want_details):
     n_tr = [len(tb['tr']) for tb in tabs]
     n_te = [len(tb['te']) for tb in tabs]
     Kmax = max(len(tb['present']) for tb in tabs)
+    # covariance of every fold's train trials from the per-trial Grams / column sums of the target
+    # (CVEngine._target_trial_grams): rows [trial] ..., then [N] = minus the total -- a fold that
+    # partitions the trials lists its held-out trials plus the total (sign -1), any other fold its
+    # train trials (sign +1)
+    tg = getattr(eng, 'tg', None)
+    downdate = tg is not None and 'sums' in tg and n_padC == 128 and eng.J == 1
+    if downdate:
+        N0 = tv.N
+        part = all(len(tb['tr']) + len(tb['te']) == N0 and
+                   len(np.union1d(tb['tr'], tb['te'])) == N0 for tb in tabs)
+        use_te = part and sum(n_te) <= sum(n_tr)
+        lists = [np.concatenate([[N0], tb['te']]) if use_te else tb['tr'] for tb in tabs]
+        o_lptr = pk.add_ints(np.concatenate([[0], np.cumsum([len(l) for l in lists])]))
+        o_list = pk.add_ints(np.concatenate(lists))
+        o_nrows = pk.add_ints(np.asarray(n_tr) * T)
     pk.reserve_ints()
     mu_t = eng.ws('c_mu_t', (B, Cm))
     cov, gram_c = eng.scatter('c_cov', B, n_padC)
@@ -70,8 +85,18 @@ def batch_cca_gen(eng, batch, want_details):
         d_cm = pk.add_descs(r_cm)
     pk.upload()
     eng.mark('align_scatter_eig')
-    ctx.call('cpsd_colsum', pk.daddr(d_mu), B, tv.C)
-    ctx.call(gram_c, pk.daddr(d_cov), B, tv.C, tv.C)
+    if downdate:
+        sgn = -1.0 if use_te else 1.0
+        lp, ll = ctypes_int_ptr(pk.iaddr(o_lptr)), ctypes_int_ptr(pk.iaddr(o_list))
+        ssum = eng.ws('c_ssum', (B, 128), torch.float64)
+        ctx.call('cpsd_sum_mats_f64', ptr(None), ptr(tg['trial']), 128 * 128, lp, ll, sgn, ptr(cov),
+                 128 * 128, 128 * 128, B)
+        ctx.call('cpsd_sum_mats_f64', ptr(None), ptr(tg['sums']), 128, lp, ll, sgn, ptr(ssum), 128, 128, B)
+        ctx.call('cpsd_cov_from_sums', ptr(cov), 128, 128 * 128, ptr(ssum), 128,
+                 ctypes_int_ptr(pk.iaddr(o_nrows)), tv.C, ptr(mu_t), Cm, B)
+    else:
+        ctx.call('cpsd_colsum', pk.daddr(d_mu), B, tv.C)
+        ctx.call(gram_c, pk.daddr(d_cov), B, tv.C, tv.C)
     if aligned:
         ctx.call('cpsd_class_mean', pk.daddr(d_cm), B, Kmax, T * tv.C)
     ev_t, evec_t = eng.eig_any(cov, n_padC, ptr(None), tv.C, B, 'ct')
