@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get('CPSD_LIB') or os.path.join(_HERE, 'libcpsd_b200.so')
 c_int = ctypes.c_int
 c_ll = ctypes.c_longlong
 c_float = ctypes.c_float
+c_double = ctypes.c_double
 c_void_p = ctypes.c_void_p
 
 # numpy mirrors of csrc/descs.h (all fields naturally aligned, no implicit padding)
@@ -65,6 +66,11 @@ _SIGS = {
                            c_float, _P, _P],
     'cpsd_eig_sym_small_f64': [_P, c_int, c_ll, _P, c_int, c_int, _P, c_int, _P, c_int, c_ll, c_int,
                                c_float, _P, _P],
+    'cpsd_eig_sym_small_f64_warm': [_P, c_int, c_ll, _P, c_int, _P, c_int, _P, _P, c_int, _P, c_int, c_ll,
+                                    _P, c_int, c_ll, _P, c_int, c_float, _P, _P],
+    'cpsd_dgemm_batched': [c_int, c_int, c_int, c_int, c_double, _P, c_int, c_ll, _P, _P, c_int, c_ll, _P,
+                           c_double, _P, c_int, c_ll, _P, _P, c_int, c_ll, _P, c_int, _P],
+    'cpsd_cast_f32_f64_idx': [_P, c_ll, _P, _P, c_ll, c_ll, c_int, _P],
     'cpsd_bj_schedule': [c_int, _P],
     'cpsd_eig_sym_block': [_P, c_int, c_ll, c_int, _P, c_int, c_int, _P, _P, _P, _P, _P, _P,
                            c_int, c_int, c_float, _P, _P],
@@ -102,7 +108,7 @@ _SIGS = {
     'cpsd_copy_rows': [_P, c_int, c_ll, _P, c_int, c_ll, _P, c_int, c_int, c_int, c_int, c_int, _P],
     'cpsd_sum_mats_f64': [_P, _P, c_ll, _P, _P, ctypes.c_double, _P, c_ll, c_int, c_int, _P],
     'cpsd_trial_colsum_f64': [_P, c_int, c_int, c_int, c_int, _P, c_int, _P],
-    'cpsd_cov_from_sums': [_P, c_int, c_ll, _P, c_int, _P, c_int, _P, c_int, c_int, _P],
+    'cpsd_cov_from_sums': [_P, c_int, c_ll, _P, c_int, _P, c_int, _P, c_int, _P, c_int, _P],
     'cpsd_gather_channels': [_P, c_int, _P, c_int, _P, c_int, c_ll, _P],
     'cpsd_gather_trials': [_P, c_ll, _P, c_int, _P, _P],
     'cpsd_mask_cols': [_P, c_int, c_ll, c_int, c_int, _P, c_int, c_int, _P],

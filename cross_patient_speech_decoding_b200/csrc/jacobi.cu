@@ -39,6 +39,17 @@ struct StepBuf {
   float df[TS / 2];
 };
 
+// optional arguments of the n <= 128 tile solver (all null = plain batched solve)
+struct EigWarm {
+  const int* sel;        // problem of CTA b (null: b)
+  const int* out_idx;    // output slot of a problem (null: the problem index)
+  const float* V0;       // initial eigenvector accumulators (null: identity)
+  int ldv0;
+  long long strideV0;
+  const int* v0_idx;     // which V0 a problem starts from (< 0: identity; null: V0[0])
+  int zero_pad;          // also write zeros to the eigenvector block outside n x n (ldv >= 128)
+};
+
 template <typename T> struct RotView;
 template <> struct RotView<double> {
   static __device__ __forceinline__ double c(const StepBuf* sb, int k) { return sb->c[k]; }
@@ -417,7 +428,8 @@ template <typename T>
 __global__ void __launch_bounds__(ET_NT, 1)
 k_eig_tile(const T* __restrict__ A, int lda, long long strideA, const int* __restrict__ n_dev,
            int n_fixed, float* __restrict__ evals, int ld_e, float* __restrict__ evecs, int ldv,
-           long long strideV, int max_sweeps, float tol, int* __restrict__ sweeps_out) {
+           long long strideV, int max_sweeps, float tol, int* __restrict__ sweeps_out,
+           EigWarm warm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* As = reinterpret_cast<T*>(smem_raw);                  // upper triangle, rows of LDS_SYM
   float* Vs = reinterpret_cast<float*>(As + TS * LDS_SYM);
@@ -425,12 +437,22 @@ k_eig_tile(const T* __restrict__ A, int lda, long long strideA, const int* __res
   int* redmax = reinterpret_cast<int*>(sb + 2);
   int* rank = redmax + 1;  // TS ints
 
-  const int prob = blockIdx.x;
+  // warm.sel: CTA b works on problem sel[b]; warm.out_idx: its results go to slot out_idx[prob];
+  // warm.V0 / v0_idx: the eigenvector accumulator starts from V0[v0_idx[prob]] (the caller has
+  // rotated A into that basis, A' = V0^T A V0, so that A' is nearly diagonal and the sweeps
+  // converge in about half as many passes) instead of the identity
+  const int prob = warm.sel ? warm.sel[blockIdx.x] : blockIdx.x;
+  const int oslot = warm.out_idx ? warm.out_idx[prob] : prob;
   int n = n_dev ? n_dev[prob] : n_fixed;
   if (n > TS) n = TS;
   if (n < 0) n = 0;
   const int m = (n + 1) & ~1;
   const T* Ag = A + (long long)prob * strideA;
+  const float* V0 = nullptr;
+  if (warm.V0 && evecs) {
+    const int vi = warm.v0_idx ? warm.v0_idx[prob] : 0;
+    if (vi >= 0) V0 = warm.V0 + (long long)vi * warm.strideV0;
+  }
 
   // upper triangle of the symmetrised input (inputs are Grams computed tile-wise; the average
   // removes last-ulp asymmetry), identity eigenvectors
@@ -441,7 +463,9 @@ k_eig_tile(const T* __restrict__ A, int lda, long long strideA, const int* __res
       if (c < n) v = (T)0.5 * (Ag[(long long)r * lda + c] + Ag[(long long)c * lda + r]);
       As[r * LDS_SYM + c] = v;
     }
-    Vs[e] = (r == c) ? 1.f : 0.f;
+    float v0 = (r == c) ? 1.f : 0.f;
+    if (V0 && r < n && c < n) v0 = V0[(long long)r * warm.ldv0 + c];
+    Vs[e] = v0;
   }
   __syncthreads();
 
@@ -467,16 +491,22 @@ k_eig_tile(const T* __restrict__ A, int lda, long long strideA, const int* __res
     rank[i] = r;
   }
   __syncthreads();
-  float* ev = evals + (long long)prob * ld_e;
+  float* ev = evals + (long long)oslot * ld_e;
   for (int i = threadIdx.x; i < ld_e; i += ET_NT) {
     if (i >= n) ev[i] = 0.f;
   }
   for (int i = threadIdx.x; i < n; i += ET_NT) ev[rank[i]] = (float)As[i * LDS_SYM + i];
   if (evecs) {
-    float* Vg = evecs + (long long)prob * strideV;
+    float* Vg = evecs + (long long)oslot * strideV;
     for (int e = threadIdx.x; e < n * n; e += ET_NT) {
       const int r = e / n, c = e - r * n;
       Vg[(long long)r * ldv + rank[c]] = Vs[r * TS + c];
+    }
+    if (warm.zero_pad && n < TS) {
+      for (int e = threadIdx.x; e < TS * TS; e += ET_NT) {
+        const int r = e >> 7, c = e & (TS - 1);
+        if (r >= n || c >= n) Vg[(long long)r * ldv + c] = 0.f;
+      }
     }
   }
 }
@@ -1091,7 +1121,7 @@ extern "C" int cpsd_eig_sym_small(const float* A, int lda, long long strideA, co
   CPSD_CUDA(cudaFuncSetAttribute(k_eig_tile<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
   k_eig_tile<float><<<nprob, ET_NT, smem, stream>>>(A, lda, strideA, n_dev, n_fixed, evals, ld_e, evecs,
-                                                 ldv, strideV, max_sweeps, tol, sweeps_out);
+                                                 ldv, strideV, max_sweeps, tol, sweeps_out, EigWarm{});
   CPSD_LAUNCH_CHECK();
   return CPSD_OK;
 }
@@ -1108,7 +1138,35 @@ extern "C" int cpsd_eig_sym_small_f64(const double* A, int lda, long long stride
   CPSD_CUDA(cudaFuncSetAttribute(k_eig_tile<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
   k_eig_tile<double><<<nprob, ET_NT, smem, stream>>>(A, lda, strideA, n_dev, n_fixed, evals, ld_e,
-                                                  evecs, ldv, strideV, max_sweeps, tol, sweeps_out);
+                                                  evecs, ldv, strideV, max_sweeps, tol, sweeps_out,
+                                                  EigWarm{});
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
+
+// Same solver on a selected subset of a batch, optionally warm-started: CTA b solves problem
+// sel[b] (sel null: b) of A, writes eigenvalues / sorted eigenvectors to slot out_idx[problem]
+// (null: the problem index) and starts its eigenvector accumulator from V0[v0_idx[problem]]
+// (entry < 0: identity); the eigenvector block is zero outside n x n.  The caller passes A already rotated into that basis (V0^T A V0, see
+// cpsd_dgemm_batched): the per-fold scatter matrices of a cross-validation differ from their
+// all-trials version by a few percent, so in its eigenbasis they are nearly diagonal.
+extern "C" int cpsd_eig_sym_small_f64_warm(const double* A, int lda, long long strideA, const int* n_dev,
+                                           int n_fixed, const int* sel, int nsel, const int* out_idx,
+                                           float* evals, int ld_e, float* evecs, int ldv,
+                                           long long strideV, const float* V0, int ldv0,
+                                           long long strideV0, const int* v0_idx, int max_sweeps,
+                                           float tol, int* sweeps_out, cudaStream_t stream) {
+  CPSD_CHECK_ARG(nsel >= 0 && lda >= 0 && ld_e >= 0, "eig_sym_small_f64_warm: bad dims");
+  CPSD_CHECK_ARG(n_fixed <= TS, "eig_sym_small_f64_warm: n > 128");
+  CPSD_CHECK_ARG(V0 == nullptr || ldv0 > 0, "eig_sym_small_f64_warm: bad V0 stride");
+  CPSD_CHECK_ARG(evecs == nullptr || ldv >= TS, "eig_sym_small_f64_warm: ldv < 128");
+  if (nsel == 0) return CPSD_OK;
+  const size_t smem = tile_smem_bytes(sizeof(double));
+  CPSD_CUDA(cudaFuncSetAttribute(k_eig_tile<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+  EigWarm w{sel, out_idx, V0, ldv0, strideV0, v0_idx, 1};
+  k_eig_tile<double><<<nsel, ET_NT, smem, stream>>>(A, lda, strideA, n_dev, n_fixed, evals, ld_e,
+                                                 evecs, ldv, strideV, max_sweeps, tol, sweeps_out, w);
   CPSD_LAUNCH_CHECK();
   return CPSD_OK;
 }

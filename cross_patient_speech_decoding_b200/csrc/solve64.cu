@@ -425,7 +425,121 @@ k_eig_sym_f64(const double* __restrict__ A, int lda, long long strideA, const in
 
 int s64_grid(int nprob) { return nprob < 296 ? nprob : 296; }
 
+// ---------------------------------------------------------------------------------------
+// Batched fp64 GEMM on index lists: C[ci[p]] = alpha * op(A[ai[p]]) * B[bi[p]] + beta * D[di[p]]
+// (null list: p).  64 x 64 output tile per CTA, 4 x 4 per thread, k in slabs of 16.  Used for the
+// basis changes of the warm-started eigen-solves (V0^T A V0, fold-invariant bases, a few hundred
+// 128^3 products per batch) and the fp64 re-orthonormalisation of those bases.
+// ---------------------------------------------------------------------------------------
+#define DG_T 64
+#define DG_K 16
+struct DgemmArgs {
+  const double* A; int lda; long long sA; const int* ai;
+  const double* B; int ldb; long long sB; const int* bi;
+  const double* D; int ldd; long long sD; const int* di;
+  double* C; int ldc; long long sC; const int* ci;
+  int m, n, k, transA;
+  double alpha, beta;
+};
+
+__global__ void __launch_bounds__(256)
+k_dgemm_batched(DgemmArgs a) {
+  __shared__ double As[DG_K][DG_T + 1];
+  __shared__ double Bs[DG_K][DG_T];
+  const int p = blockIdx.z;
+  const double* A = a.A + (long long)(a.ai ? a.ai[p] : p) * a.sA;
+  const double* B = a.B + (long long)(a.bi ? a.bi[p] : p) * a.sB;
+  double* C = a.C + (long long)(a.ci ? a.ci[p] : p) * a.sC;
+  const int r0 = blockIdx.y * DG_T, c0 = blockIdx.x * DG_T;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  double acc[4][4] = {};
+  for (int k0 = 0; k0 < a.k; k0 += DG_K) {
+    for (int e = threadIdx.x; e < DG_K * DG_T; e += 256) {
+      int kk, r;
+      if (a.transA) { kk = e / DG_T; r = e - kk * DG_T; }     // A is k x m: rows contiguous in r
+      else { r = e / DG_K; kk = e - r * DG_K; }               // A is m x k: rows contiguous in kk
+      const int gr = r0 + r, gk = k0 + kk;
+      double v = 0.0;
+      if (gr < a.m && gk < a.k) v = a.transA ? A[(long long)gk * a.lda + gr] : A[(long long)gr * a.lda + gk];
+      As[kk][r] = v;
+    }
+    for (int e = threadIdx.x; e < DG_K * DG_T; e += 256) {
+      const int kk = e / DG_T, c = e - kk * DG_T;
+      const int gk = k0 + kk, gc = c0 + c;
+      Bs[kk][c] = (gk < a.k && gc < a.n) ? B[(long long)gk * a.ldb + gc] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < DG_K; ++kk) {
+      double av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = As[kk][ty + 16 * i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = Bs[kk][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const double* D = a.D ? a.D + (long long)(a.di ? a.di[p] : p) * a.sD : nullptr;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gr = r0 + ty + 16 * i;
+    if (gr >= a.m) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gc = c0 + tx + 16 * j;
+      if (gc >= a.n) continue;
+      double v = a.alpha * acc[i][j];
+      if (D) v += a.beta * D[(long long)gr * a.ldd + gc];
+      C[(long long)gr * a.ldc + gc] = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_cast_f32_f64_idx(const float* __restrict__ src, long long strideS, const int* __restrict__ idx,
+                   double* __restrict__ dst, long long strideD, long long elems) {
+  const int p = blockIdx.y;
+  const float* s = src + (long long)(idx ? idx[p] : p) * strideS;
+  double* d = dst + (long long)p * strideD;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < elems;
+       e += (long long)gridDim.x * blockDim.x)
+    d[e] = (double)s[e];
+}
+
 }  // namespace
+
+extern "C" int cpsd_dgemm_batched(int transA, int m, int n, int k, double alpha, const double* A,
+                                  int lda, long long strideA, const int* a_idx, const double* B,
+                                  int ldb, long long strideB, const int* b_idx, double beta,
+                                  const double* D, int ldd, long long strideD, const int* d_idx,
+                                  double* C, int ldc, long long strideC, const int* c_idx, int nprob,
+                                  cudaStream_t stream) {
+  CPSD_CHECK_ARG(m >= 0 && n >= 0 && k >= 0 && nprob >= 0, "dgemm_batched: bad dims");
+  CPSD_CHECK_ARG(lda > 0 && ldb >= n && ldc >= n, "dgemm_batched: bad leading dimension");
+  CPSD_CHECK_ARG(nprob <= 65535, "dgemm_batched: more than 65535 problems");
+  if (m == 0 || n == 0 || nprob == 0) return CPSD_OK;
+  DgemmArgs a{A, lda, strideA, a_idx, B, ldb, strideB, b_idx, D, ldd, strideD, d_idx,
+              C, ldc, strideC, c_idx, m, n, k, transA, alpha, beta};
+  k_dgemm_batched<<<dim3((n + DG_T - 1) / DG_T, (m + DG_T - 1) / DG_T, nprob), 256, 0, stream>>>(a);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
+
+extern "C" int cpsd_cast_f32_f64_idx(const float* src, long long strideS, const int* idx, double* dst,
+                                     long long strideD, long long elems, int nprob,
+                                     cudaStream_t stream) {
+  CPSD_CHECK_ARG(elems >= 0 && nprob >= 0 && nprob <= 65535, "cast_f32_f64_idx: bad dims");
+  if (elems == 0 || nprob == 0) return CPSD_OK;
+  long long bx = (elems + 255) / 256;
+  if (bx > 64) bx = 64;
+  k_cast_f32_f64_idx<<<dim3((int)bx, nprob), 256, 0, stream>>>(src, strideS, idx, dst, strideD, elems);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
 
 extern "C" long long cpsd_cca_solve_f64_ws_elems(int nprob, int dmax) {
   return (long long)s64_grid(nprob > 0 ? nprob : 1) * 4 * dmax * (dmax + 1);

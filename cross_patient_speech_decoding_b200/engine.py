@@ -161,6 +161,9 @@ class CVEngine:
         # verify its acceptance test with the batch's final read-back (one host sync per batch
         # instead of two; a batch whose first round is not accepted is run again the slow way)
         self.speculative_topk = bool(speculative_topk) and os.environ.get('CPSD_SPECULATIVE_TOPK', '1') != '0'
+        # warm-started tile eigen-solves (CPSD_WARM_START=0: every solve starts from the identity)
+        self.warm_start = os.environ.get('CPSD_WARM_START', '1') != '0'
+        self._runs_done = 0
         self._spec = False
         base = Context.get(device)
         self.lane = int(lane)
@@ -357,6 +360,49 @@ class CVEngine:
         nc = n_pad if ncols is None else ncols
         self.eig_vecs(tag, n_pad, nprob, perm, ptr(None), nc, nc, evecs)
         return evals, evecs
+
+    # ------------------------------------------------------------------ warm-started tile solves
+    def eig_warm(self, A, n_dev, n_fixed, nsel, evals, evecs, sel=None, out_idx=None, V0=None,
+                 v0_idx=None):
+        """fp64 tile solve (n <= 128) of the problems ``sel`` (device int list, None = 0..nsel-1) of
+        A (nprob, 128, 128); results go to slot ``out_idx[problem]`` of evals (.., 128) / evecs
+        (.., 128, 128); the eigenvector accumulator starts from ``V0[v0_idx[problem]]`` (the caller
+        has rotated A into that basis, see ``rotate_sym``)."""
+        if nsel == 0:
+            return
+        self.ctx.call('cpsd_eig_sym_small_f64_warm', ptr(A), 128, 128 * 128, _p(n_dev), n_fixed,
+                      _p(sel), nsel, _p(out_idx), ptr(evals), evals.shape[-1], ptr(evecs), 128,
+                      128 * 128, ptr(V0), 128, 128 * 128, _p(v0_idx), self.eig_sweeps + 6, 1e-10,
+                      ptr(None))
+
+    def rotate_sym(self, A, Q, nsel, tag, sel=None, base=None):
+        """A[sel[i]] <- Q[base[i]]^T A[sel[i]] Q[base[i]] in fp64 (A, Q: (.., 128, 128); sel / base:
+        device int lists, None = i)."""
+        if nsel == 0:
+            return
+        W = self.ws(tag + '_rotw', (nsel, 128, 128), torch.float64)
+        st = 128 * 128
+        self.ctx.call('cpsd_dgemm_batched', 0, 128, 128, 128, 1.0, ptr(A), 128, st, _p(sel), ptr(Q), 128,
+                      st, _p(base), 0.0, ptr(None), 128, 0, _p(None), ptr(W), 128, st, _p(None), nsel)
+        self.ctx.call('cpsd_dgemm_batched', 1, 128, 128, 128, 1.0, ptr(Q), 128, st, _p(base), ptr(W), 128,
+                      st, _p(None), 0.0, ptr(None), 128, 0, _p(None), ptr(A), 128, st, _p(sel), nsel)
+
+    def ortho_bases(self, evecs, slots, nb, Q, Qf, b0):
+        """Q[b0 + i] = fp64 re-orthonormalised copy of the fp32 eigenvector matrix evecs[slots[i]]
+        (one Newton-Schulz step Q (3 I - Q^T Q) / 2: orthogonal to ~1e-12, so that a rotation by it
+        is an exact similarity), Qf its fp32 rounding (the solver's starting accumulator)."""
+        if nb == 0:
+            return
+        st = 128 * 128
+        Qd = self.ws('ob_qd', (nb, 128, 128), torch.float64)
+        G = self.ws('ob_g', (nb, 128, 128), torch.float64)
+        self.ctx.call('cpsd_cast_f32_f64_idx', ptr(evecs), st, _p(slots), ptr(Qd), st, st, nb)
+        self.ctx.call('cpsd_dgemm_batched', 1, 128, 128, 128, 1.0, ptr(Qd), 128, st, _p(None), ptr(Qd),
+                      128, st, _p(None), 0.0, ptr(None), 128, 0, _p(None), ptr(G), 128, st, _p(None), nb)
+        self.ctx.call('cpsd_dgemm_batched', 0, 128, 128, 128, -0.5, ptr(Qd), 128, st, _p(None), ptr(G),
+                      128, st, _p(None), 1.5, ptr(Qd), 128, st, _p(None), ptr(Q, b0 * st), 128, st,
+                      _p(None), nb)
+        self.ctx.call('cpsd_cast_f64_f32', ptr(Q, b0 * st), ptr(Qf, b0 * st), nb * st)
 
     def eig_topk(self, K, n_pad, n_dev, nprob, m, evals, tag, thr, mode, kcap, k2, tol=None,
                  gap_tol=None):
@@ -572,6 +618,48 @@ class CVEngine:
                       evec=self.ctx.zeros((cap, n_pad, n_pad)))
             self._vs = vs
         return vs
+
+    def _view_bases(self):
+        """Warm-start bases of the per-view scatter eigenproblems: for every (replica, patient) the
+        eigenvectors of the first problem solved for it, as fp64 (rotation) and fp32 (starting
+        accumulator) matrices; ``tab[replica * P + patient]`` = base index or -1."""
+        vb = getattr(self, '_vb', None)
+        if vb is None:
+            cap = self.J * self.P
+            vb = self._vb = dict(cap=cap, n=0, tab=-np.ones(cap, dtype=np.int32),
+                                 Q=self.ctx.zeros((cap, 128, 128), torch.float64),
+                                 Qf=self.ctx.zeros((cap, 128, 128)))
+        return vb
+
+    def _tg_rotate(self):
+        """Second use of a resident engine: moves the target's per-trial Grams (and column sums)
+        into the eigenbasis of their all-trials sum, once.  Every fold's train-set Gram / covariance
+        assembled from them is then nearly diagonal: the signal-rank solve needs the eigenvalues
+        only, the PCA solve of the CCA path starts its eigenvector accumulator from that basis."""
+        tg = getattr(self, 'tg', None)
+        if tg is None or tg.get('rot') or not self.warm_start:
+            return
+        ctx, J, N = self.ctx, self.J, self.views[0].N
+        st = 128 * 128
+        G = tg['trial']
+        nrow = J * N + J
+        A = (-G[J * N:]).contiguous()                       # the all-trials Grams (stored negated)
+        ev = ctx.empty((J, 128))
+        evec = ctx.empty((J, 128, 128))
+        self.eig_warm(A, ptr(None), self.views[0].C, J, ev, evec)
+        Q = ctx.zeros((J, 128, 128), torch.float64)
+        Qf = ctx.zeros((J, 128, 128))
+        self.ortho_bases(evec, None, J, Q, Qf, 0)
+        base = np.concatenate([np.repeat(np.arange(J), N), np.arange(J)]).astype(np.int32)
+        base_dev = ctx.upload(base)
+        self.rotate_sym(G, Q, nrow, 'tg', base=base_dev)
+        if 'sums' in tg:
+            S = tg['sums']
+            tg['sums0'] = S.clone()
+            ctx.call('cpsd_dgemm_batched', 0, 1, 128, 128, 1.0, ptr(tg['sums0']), 128, 128, _p(None),
+                     ptr(Q), 128, st, ptr(base_dev), 0.0, ptr(None), 128, 0, _p(None), ptr(S), 128, 128,
+                     _p(None), nrow)
+        tg.update(rot=True, Q=Q, Qf=Qf, base_dev=base_dev)
 
     def _xcache(self, R, XR):
         """Reduced coordinates Zx (K*T x (P-1)R) of the cross patients' condition averages and
@@ -815,6 +903,7 @@ class CVEngine:
             ln._ws, ln._vs, ln._tc_stage, ln._marks = {}, None, None, []   # refcount
             ln._sched = {}          # block-Jacobi schedules are uploaded on the lane's own stream
             ln._xc = None
+            ln._vb = None
             ln._jc = None
             ln._tkc_key = None
             ln.packA, ln.packB = HostPack(self.ctx), HostPack(self.ctx)
@@ -863,6 +952,9 @@ class CVEngine:
         # host packs and queues the other lane's batch on its own stream
         with torch.cuda.stream(self.stream):
             self._tc_proj_ready(1)                     # split X / encode maps before the lanes fork
+            if self._runs_done or len(batches) > 1:
+                self._tg_rotate()
+        self._runs_done += 1
         nl = 1 if (self.profile or len(batches) == 1) else min(self.n_lanes, len(batches))
         lanes = self._lanes(nl)
         ready = torch.cuda.Event()
@@ -939,6 +1031,9 @@ class CVEngine:
         if self.method == 'mcca' and self.cross_rank is None:
             yield 'sync'                     # constructor work still in flight
         self._ensure_ready()
+        if self._runs_done or nb > 1:
+            self._tg_rotate()
+        self._runs_done += 1
         seeds = self._bag_seeds(folds, bag_seeds)
         rep = self._check_rep(rep, len(folds))
         for s0 in range(0, len(folds), size):
@@ -1453,6 +1548,31 @@ class CVEngine:
                 vs['next'] = vs['res']
             o_slot = pk.add_ints(slot)
             o_cds = pk.add_ints([self.views[v].C for _, v, _ in solve])
+            # warm-start plan of the view solves: the first scatter matrix solved for a (replica,
+            # patient) pair is solved cold and its eigenvectors become the pair's basis; every
+            # other problem of the pair is rotated into that basis and starts from it
+            wplan = None
+            if self.warm_start and n_padC == 128:
+                vb = self._view_bases()
+                s_f = np.array([t[0] for t in solve], dtype=np.int64)
+                code = rep[s_f] * P + np.array([t[1] for t in solve], dtype=np.int64)
+                tab = vb['tab']
+                base_of = tab[code].copy()
+                miss = np.nonzero(base_of < 0)[0]
+                cold = np.zeros(0, dtype=np.int64)
+                if len(miss):
+                    uc, first_miss = np.unique(code[miss], return_index=True)
+                    cold = miss[first_miss]
+                    tab = tab.copy()
+                    tab[uc] = vb['n'] + np.arange(len(uc), dtype=np.int32)
+                    base_of = tab[code].copy()
+                    base_of[cold] = -1
+                warm_i = np.nonzero(base_of >= 0)[0]
+                s_slot = np.array([t[2] for t in solve], dtype=np.int32)
+                wplan = dict(ncold=len(cold), nwarm=len(warm_i), tab=tab,
+                             o_selc=pk.add_ints(cold), o_cslot=pk.add_ints(s_slot[cold]),
+                             o_selw=pk.add_ints(warm_i), o_basew=pk.add_ints(base_of[warm_i]),
+                             o_v0=pk.add_ints(base_of), o_out=pk.add_ints(s_slot))
             # cross-block cache slot of every fold (one slot per shared class set)
             XR = (P - 1) * R
             xc = self._xcache(R, XR)
@@ -1838,11 +1958,28 @@ class CVEngine:
             self.gram_scatter(gram_c, pk.daddr(d_cov), nS, Cm, Cm, cov, 3)
             nM, s0 = nS - B, vs['next']
             ncol = min(n_padC, R)
-            self.eig_any(cov[:B], n_padC, ctypes_int_ptr(pk.iaddr(o_cds)), 0, B, 'mv', ncols=ncol,
-                         out=(vs['ev'][:B], vs['evec'][:B]))
-            if nM:
-                self.eig_any(cov[B:], n_padC, ctypes_int_ptr(pk.iaddr(o_cds + B)), 0, nM, 'mvx',
-                             ncols=ncol, out=(vs['ev'][s0:s0 + nM], vs['evec'][s0:s0 + nM]))
+            if wplan is not None and cov.dtype == torch.float64:
+                ip = lambda o: ctypes_int_ptr(pk.iaddr(o))
+                n_dev = ip(o_cds)
+                if wplan['ncold']:
+                    self.eig_warm(cov, n_dev, 0, wplan['ncold'], vs['ev'], vs['evec'],
+                                  sel=ip(wplan['o_selc']), out_idx=ip(wplan['o_out']))
+                    self.ortho_bases(vs['evec'], ip(wplan['o_cslot']), wplan['ncold'], vb['Q'], vb['Qf'],
+                                     vb['n'])
+                    vb['n'] += wplan['ncold']
+                    vb['tab'] = wplan['tab']
+                if wplan['nwarm']:
+                    self.rotate_sym(cov, vb['Q'], wplan['nwarm'], 'mv', sel=ip(wplan['o_selw']),
+                                    base=ip(wplan['o_basew']))
+                    self.eig_warm(cov, n_dev, 0, wplan['nwarm'], vs['ev'], vs['evec'],
+                                  sel=ip(wplan['o_selw']), out_idx=ip(wplan['o_out']), V0=vb['Qf'],
+                                  v0_idx=ip(wplan['o_v0']))
+            else:
+                self.eig_any(cov[:B], n_padC, ctypes_int_ptr(pk.iaddr(o_cds)), 0, B, 'mv', ncols=ncol,
+                             out=(vs['ev'][:B], vs['evec'][:B]))
+                if nM:
+                    self.eig_any(cov[B:], n_padC, ctypes_int_ptr(pk.iaddr(o_cds + B)), 0, nM, 'mvx',
+                                 ncols=ncol, out=(vs['ev'][s0:s0 + nM], vs['evec'][s0:s0 + nM]))
             vs['keys'].update(pending)
             vs['next'] += nM
             self.stats['view_solves'] = self.stats.get('view_solves', 0) + nS

@@ -56,6 +56,7 @@ def batch_cca_gen(eng, batch, want_details):
     # train trials (sign +1)
     tg = getattr(eng, 'tg', None)
     downdate = tg is not None and 'sums' in tg and n_padC == 128 and eng.J == 1
+    rotated = downdate and bool(tg.get('rot'))
     if downdate:
         N0 = tv.N
         part = all(len(tb['tr']) + len(tb['te']) == N0 and
@@ -92,14 +93,22 @@ def batch_cca_gen(eng, batch, want_details):
         ctx.call('cpsd_sum_mats_f64', ptr(None), ptr(tg['trial']), 128 * 128, lp, ll, sgn, ptr(cov),
                  128 * 128, 128 * 128, B)
         ctx.call('cpsd_sum_mats_f64', ptr(None), ptr(tg['sums']), 128, lp, ll, sgn, ptr(ssum), 128, 128, B)
+        smu = None
+        if rotated:        # statistics live in the all-trials eigenbasis; the means do not
+            smu = eng.ws('c_ssum0', (B, 128), torch.float64)
+            ctx.call('cpsd_sum_mats_f64', ptr(None), ptr(tg['sums0']), 128, lp, ll, sgn, ptr(smu), 128, 128, B)
         ctx.call('cpsd_cov_from_sums', ptr(cov), 128, 128 * 128, ptr(ssum), 128,
-                 ctypes_int_ptr(pk.iaddr(o_nrows)), tv.C, ptr(mu_t), Cm, B)
+                 ctypes_int_ptr(pk.iaddr(o_nrows)), tv.C, ptr(mu_t), Cm, ptr(smu), B)
     else:
         ctx.call('cpsd_colsum', pk.daddr(d_mu), B, tv.C)
         ctx.call(gram_c, pk.daddr(d_cov), B, tv.C, tv.C)
     if aligned:
         ctx.call('cpsd_class_mean', pk.daddr(d_cm), B, Kmax, T * tv.C)
-    ev_t, evec_t = eng.eig_any(cov, n_padC, ptr(None), tv.C, B, 'ct')
+    if rotated:            # nearly diagonal already: start the accumulator from that basis
+        ev_t, evec_t = eng.ws('ct_ev', (B, n_padC)), eng.ws('ct_evec', (B, n_padC, n_padC))
+        eng.eig_warm(cov, ptr(None), tv.C, B, ev_t, evec_t, V0=tg['Qf'])
+    else:
+        ev_t, evec_t = eng.eig_any(cov, n_padC, ptr(None), tv.C, B, 'ct')
     k_t = eng.ws('c_kt', (B,), I32)
     eng._select_pca_k(ev_t, n_padC, ptr(None), tv.C, k_t, 1, 0, B, eng.n_comp)
     yield 'sync'

@@ -27,6 +27,74 @@ def _ivoid(address):
     return ctypes.c_void_p(address)
 
 
+def dgemm_batched(A, B, trans_a=False, alpha=1.0, beta=0.0, D=None, a_idx=None, b_idx=None,
+                  device=None):
+    """C[p] = alpha * op(A[a_idx[p]]) * B[b_idx[p]] + beta * D[p] in fp64 (host arrays in / out)."""
+    ctx = _ctx(device)
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    B = np.ascontiguousarray(B, dtype=np.float64)
+    nprob = len(a_idx) if a_idx is not None else (len(b_idx) if b_idx is not None else A.shape[0])
+    m, k = (A.shape[2], A.shape[1]) if trans_a else (A.shape[1], A.shape[2])
+    n = B.shape[2]
+    assert B.shape[1] == k
+    Ad, Bd = ctx.upload(A), ctx.upload(B)
+    Dd = None if D is None else ctx.upload(np.ascontiguousarray(D, dtype=np.float64))
+    ai = None if a_idx is None else ctx.upload(np.asarray(a_idx, dtype=np.int32))
+    bi = None if b_idx is None else ctx.upload(np.asarray(b_idx, dtype=np.int32))
+    C = ctx.empty((nprob, m, n), F64)
+    ctx.call('cpsd_dgemm_batched', int(trans_a), m, n, k, float(alpha), ptr(Ad), A.shape[2],
+             A.shape[1] * A.shape[2], ptr(ai), ptr(Bd), n, k * n, ptr(bi), float(beta), ptr(Dd), n, m * n,
+             ptr(None), ptr(C), n, m * n, ptr(None), nprob)
+    return C.cpu().numpy()
+
+
+def eig_sym_warm(A, V0, v0_idx=None, n=None, sel=None, out_idx=None, n_out=None, device=None):
+    """Warm-started fp64 tile solve (n <= 128): rotates A[p] into the basis V0[v0_idx[p]] (fp32
+    eigenvector matrices of nearby problems, re-orthonormalised in fp64 on the device), solves from
+    that starting accumulator and returns (evals, evecs, sweeps) like ``eig_sym(f64=True)``;
+    ``v0_idx[p] < 0`` = cold solve of that problem."""
+    ctx = _ctx(device)
+    A = np.asarray(A, dtype=np.float64)
+    nprob, nn, _ = A.shape
+    assert nn <= 128
+    ns = np.full(nprob, nn, dtype=np.int32) if n is None else np.asarray(n, dtype=np.int32)
+    Ap = np.zeros((nprob, 128, 128))
+    Ap[:, :nn, :nn] = A
+    V0 = np.asarray(V0, dtype=np.float32)
+    nb = V0.shape[0]
+    V0p = np.zeros((nb, 128, 128), dtype=np.float32)
+    V0p[:, :nn, :nn] = V0
+    vi = np.zeros(nprob, dtype=np.int32) if v0_idx is None else np.asarray(v0_idx, dtype=np.int32)
+    Ad, nd, V0d, vid = ctx.upload(Ap), ctx.upload(ns), ctx.upload(V0p), ctx.upload(vi)
+    st = 128 * 128
+    # fp64 re-orthonormalisation of the bases (one Newton-Schulz step)
+    Qd, G, Q, Qf = (ctx.empty((nb, 128, 128), F64), ctx.empty((nb, 128, 128), F64),
+                    ctx.empty((nb, 128, 128), F64), ctx.empty((nb, 128, 128)))
+    ctx.call('cpsd_cast_f32_f64_idx', ptr(V0d), st, ptr(None), ptr(Qd), st, st, nb)
+    ctx.call('cpsd_dgemm_batched', 1, 128, 128, 128, 1.0, ptr(Qd), 128, st, ptr(None), ptr(Qd), 128, st,
+             ptr(None), 0.0, ptr(None), 128, 0, ptr(None), ptr(G), 128, st, ptr(None), nb)
+    ctx.call('cpsd_dgemm_batched', 0, 128, 128, 128, -0.5, ptr(Qd), 128, st, ptr(None), ptr(G), 128, st,
+             ptr(None), 1.5, ptr(Qd), 128, st, ptr(None), ptr(Q), 128, st, ptr(None), nb)
+    ctx.call('cpsd_cast_f64_f32', ptr(Q), ptr(Qf), nb * st)
+    warm = np.nonzero(vi >= 0)[0].astype(np.int32)
+    if len(warm):
+        wd, bd = ctx.upload(warm), ctx.upload(vi[warm])
+        W = ctx.empty((len(warm), 128, 128), F64)
+        ctx.call('cpsd_dgemm_batched', 0, 128, 128, 128, 1.0, ptr(Ad), 128, st, ptr(wd), ptr(Q), 128, st,
+                 ptr(bd), 0.0, ptr(None), 128, 0, ptr(None), ptr(W), 128, st, ptr(None), len(warm))
+        ctx.call('cpsd_dgemm_batched', 1, 128, 128, 128, 1.0, ptr(Q), 128, st, ptr(bd), ptr(W), 128, st,
+                 ptr(None), 0.0, ptr(None), 128, 0, ptr(None), ptr(Ad), 128, st, ptr(wd), len(warm))
+    sl = None if sel is None else ctx.upload(np.asarray(sel, dtype=np.int32))
+    oi = None if out_idx is None else ctx.upload(np.asarray(out_idx, dtype=np.int32))
+    nsel = nprob if sel is None else len(sel)
+    n_out = nprob if n_out is None else n_out
+    evals, evecs = ctx.zeros((n_out, 128)), ctx.zeros((n_out, 128, 128))
+    sw = ctx.zeros((nprob,), I32)
+    ctx.call('cpsd_eig_sym_small_f64_warm', ptr(Ad), 128, st, ptr(nd), 0, ptr(sl), nsel, ptr(oi),
+             ptr(evals), 128, ptr(evecs), 128, st, ptr(Qf), 128, st, ptr(vid), 18, 1e-10, ptr(sw))
+    return evals.cpu().numpy()[:, :nn], evecs.cpu().numpy()[:, :nn, :nn], sw.cpu().numpy()
+
+
 def eig_sym(A, n=None, max_sweeps=15, tol=3e-7, device=None, return_sweeps=False, f64=False,
             tensor_cores=False):
     """Eigen-decomposition of a batch of symmetric matrices.  A: (nprob, n, n) or (n, n).

@@ -59,13 +59,13 @@ int cpsd_sum_mats_f64(const double* base, const double* mats, long long mat_stri
                       const int* list_ptr, const int* list, double sign, double* out,
                       long long out_stride, int elems, int nprob, cudaStream_t stream);
 /* per-trial column sums (fp64) and the centred covariance of a trial subset from per-trial
- * statistics, cov = (G - s s^T / n) / (n - 1), mu = s / n: sklearn PCA's covariance of a fold's
+ * statistics, cov = (G - s s^T / n) / (n - 1), mu = s_mu / n (s_mu NULL: s): sklearn PCA's covariance of a fold's
  * train trials (decoders/cross_pt_decoders.py:234-241 -> PCA.fit) without re-reading the trials */
 int cpsd_trial_colsum_f64(const float* X, int n_trials, int T, int C, int ldx, double* sums, int lds,
                           cudaStream_t stream);
 int cpsd_cov_from_sums(double* G, int ldg, long long strideG, const double* s, int lds,
-                       const int* nrows_dev, int C, float* mu, int ldmu, int nprob,
-                       cudaStream_t stream);
+                       const int* nrows_dev, int C, float* mu, int ldmu, const double* s_mu,
+                       int nprob, cudaStream_t stream);
 /* electrode subsampling of resident trials: dst = src[:, idx] (the channel lists of
  * processing_utils/grid_subsampling.py:8-61 and poisson_disk_sampling.py:9-77) and the block
  * means of spatial_avg_data (processing_utils/spatial_avg_subsampling.py:74-96) */
@@ -175,6 +175,25 @@ int cpsd_eig_sym_small_f64(const double* A, int lda, long long strideA, const in
                            int n_fixed, int nprob, float* evals, int ld_e, float* evecs, int ldv,
                            long long strideV, int max_sweeps, float tol, int* sweeps_out,
                            cudaStream_t stream);
+/* the same solver on a subset (sel) of a batch, results to slot out_idx[problem], eigenvector
+ * accumulator started from V0[v0_idx[problem]] (the caller rotates A into that basis first):
+ * the per-fold scatter matrices of a cross-validation (cross_pt_decoders.py:234-241,
+ * AlignMCCA.py:140-174 refit them from scratch every fold) are nearly diagonal in the
+ * eigenbasis of their all-trials version, which halves the number of sweeps */
+int cpsd_eig_sym_small_f64_warm(const double* A, int lda, long long strideA, const int* n_dev,
+                                int n_fixed, const int* sel, int nsel, const int* out_idx,
+                                float* evals, int ld_e, float* evecs, int ldv, long long strideV,
+                                const float* V0, int ldv0, long long strideV0, const int* v0_idx,
+                                int max_sweeps, float tol, int* sweeps_out, cudaStream_t stream);
+/* C[ci[p]] = alpha * op(A[ai[p]]) * B[bi[p]] + beta * D[di[p]] in fp64 (null list: p; D may be
+ * NULL): the basis changes V0^T A V0 of the warm-started solves */
+int cpsd_dgemm_batched(int transA, int m, int n, int k, double alpha, const double* A, int lda,
+                       long long strideA, const int* a_idx, const double* B, int ldb,
+                       long long strideB, const int* b_idx, double beta, const double* D, int ldd,
+                       long long strideD, const int* d_idx, double* C, int ldc, long long strideC,
+                       const int* c_idx, int nprob, cudaStream_t stream);
+int cpsd_cast_f32_f64_idx(const float* src, long long strideS, const int* idx, double* dst,
+                          long long strideD, long long elems, int nprob, cudaStream_t stream);
 /* block two-sided Jacobi for n > 128 (n_pad multiple of 128): pooled-Gram PCA, large GEVPs.
  * Every round's 128x128 tile rotations are kept in a rotation log (Rlog,
  * cpsd_bj_rlog_elems() floats); cpsd_bj_eigvecs replays them on the identity columns of the

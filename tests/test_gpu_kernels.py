@@ -313,6 +313,55 @@ def test_eig_f64_resolves_noise_level_directions(ops):
     assert np.abs(V.T @ V - np.eye(n)).max() < 2e-5
 
 
+@pytest.mark.parametrize('trans_a', [False, True])
+@pytest.mark.parametrize('shape', [(128, 128, 128), (1, 128, 128), (70, 33, 129), (5, 3, 2)])
+def test_dgemm_batched(ops, shape, trans_a):
+    m, n, k = shape
+    rng = np.random.default_rng(m + n + k)
+    A = rng.standard_normal((4, k, m) if trans_a else (4, m, k))
+    B = rng.standard_normal((3, k, n))
+    D = rng.standard_normal((6, m, n))
+    ai, bi = [3, 0, 0, 2, 1, 3], [2, 2, 0, 1, 0, 1]
+    C = ops.dgemm_batched(A, B, trans_a=trans_a, alpha=-0.5, beta=1.5, D=D, a_idx=ai, b_idx=bi)
+    for p in range(6):
+        a = A[ai[p]].T if trans_a else A[ai[p]]
+        ref = -0.5 * a @ B[bi[p]] + 1.5 * D[p]
+        assert np.abs(C[p] - ref).max() <= 1e-13 * (np.abs(ref).max() + 1)
+
+
+@pytest.mark.parametrize('n', [128, 111, 37])
+def test_eig_warm_start_same_pairs_fewer_sweeps(ops, n):
+    """Fold-like perturbations of one scatter matrix, solved cold and warm-started from the
+    eigenvectors of the unperturbed matrix: same eigenpairs (to the fp32 accumulator's accuracy),
+    clearly fewer sweeps; a problem flagged cold inside the warm launch matches the cold solver;
+    sel / out_idx route a subset of the batch to chosen output slots."""
+    rng = np.random.default_rng(n)
+    X = rng.standard_normal((140, 40, 12)) @ rng.standard_normal((12, n)) + 0.3 * rng.standard_normal((140, 40, n))
+    G = np.einsum('ntc,ntd->ncd', X, X)
+    A = np.stack([G.sum(0) - G[rng.permutation(140)[:7]].sum(0) for _ in range(6)])
+    _, V0 = ops.eig_sym(G.sum(0), f64=True)
+    ev_c, V_c, sw_c = ops.eig_sym(A, f64=True, return_sweeps=True)
+    vi = np.array([0, 0, 0, -1, 0, 0])
+    ev_w, V_w, sw_w = ops.eig_sym_warm(A, V0[None], v0_idx=vi)
+    for i in range(6):
+        w, U = np.linalg.eigh(A[i])
+        w, U = w[::-1], U[:, ::-1]
+        assert np.abs(ev_w[i] - w).max() <= 1e-6 * w[0]
+        assert np.abs(V_w[i].T @ V_w[i] - np.eye(n)).max() < 2e-5
+        assert np.abs(A[i] @ V_w[i] - V_w[i] * w).max() <= 2e-5 * w[0]
+        gaps = np.minimum(np.abs(np.diff(w, prepend=np.inf)), np.abs(np.diff(w, append=-np.inf)))
+        ok = gaps > 1e-3 * w[0]                     # well-separated pairs: same vectors up to sign
+        assert np.abs(np.abs(np.sum(U * V_w[i], axis=0)) - 1)[ok].max() < 1e-5
+    assert np.abs(ev_w[3] - ev_c[3]).max() <= 1e-6 * ev_c[3, 0]
+    assert sw_w[vi >= 0].max() < sw_c[:6].min(), (sw_w, sw_c)
+    # subset + output slots
+    ev_s, V_s, _ = ops.eig_sym_warm(A, V0[None], v0_idx=np.zeros(6), sel=[4, 1], out_idx=[9, 2, 9, 9, 0, 9],
+                                    n_out=3)
+    assert np.abs(ev_s[0] - ev_w[4]).max() <= 1e-6 * ev_w[4, 0]
+    assert np.abs(ev_s[2] - ev_w[1]).max() <= 1e-6 * ev_w[1, 0]
+    assert np.abs(ev_s[1]).max() == 0
+
+
 def test_gram_tn_f64_accumulation(ops):
     import torch
     from cross_patient_speech_decoding_b200 import _lib
