@@ -95,6 +95,8 @@ _SIGS = {
                            _P, c_int, c_ll, c_int, _P],
     'cpsd_chol_solve_f64': [_P, c_int, c_ll, c_int, _P, c_int, c_ll, c_int, _P, c_int, c_ll, _P, c_int,
                             _P],
+    'cpsd_chol_solve_f64_ws': [_P, c_int, c_ll, c_int, _P, c_int, c_ll, c_int, _P, c_int, c_ll, _P, _P,
+                               c_int, _P],
     'cpsd_chol_inv': [_P, c_int, c_ll, c_int, _P, c_int, c_ll, _P, c_int, _P],
     'cpsd_gram_tn': [_P, c_int, c_int, c_int, _P],
     'cpsd_gram_tn_f64': [_P, c_int, c_int, c_int, _P],

@@ -308,9 +308,13 @@ k_chol_inv(const TI* __restrict__ S, int lds, long long strideS, int m,
 __global__ void __launch_bounds__(CH_NT)
 k_chol_solve_f64(const double* __restrict__ S, int lds, long long strideS, int m,
                  double* __restrict__ B, int ldb, long long strideB, int q,
-                 float* __restrict__ W, int ldw, long long strideW, int* __restrict__ status) {
+                 float* __restrict__ W, int ldw, long long strideW, int* __restrict__ status,
+                 double* __restrict__ ws) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* P = reinterpret_cast<double*>(smem_raw);          // m x CH_LD, lower factor
+  // lower factor, m rows of ldp doubles: shared memory for m <= 128, else this problem's
+  // slice of the caller's workspace (L2-resident; patients with more than 128 electrodes)
+  const int ldp = ws ? m + 1 : CH_LD;
+  double* P = ws ? ws + (long long)blockIdx.x * m * (m + 1) : reinterpret_cast<double*>(smem_raw);
   __shared__ double s_piv;
   __shared__ int s_bad;
   const int prob = blockIdx.x;
@@ -322,15 +326,15 @@ k_chol_solve_f64(const double* __restrict__ S, int lds, long long strideS, int m
   if (tid == 0) s_bad = 0;
   for (int e = tid; e < m * m; e += CH_NT) {
     const int r = e / m, c = e - r * m;
-    P[r * CH_LD + c] = (c <= r) ? 0.5 * (Sg[(long long)r * lds + c] + Sg[(long long)c * lds + r]) : 0.0;
+    P[r * ldp + c] = (c <= r) ? 0.5 * (Sg[(long long)r * lds + c] + Sg[(long long)c * lds + r]) : 0.0;
   }
   __syncthreads();
   double dmax = 0.0;
-  for (int i = 0; i < m; ++i) dmax = fmax(dmax, P[i * CH_LD + i]);
+  for (int i = 0; i < m; ++i) dmax = fmax(dmax, P[i * ldp + i]);
   const double floor_piv = dmax * 1e-14 + 1e-290;
   for (int j = 0; j < m; ++j) {
     if (tid == 0) {
-      double d = P[j * CH_LD + j];
+      double d = P[j * ldp + j];
       if (!(d > floor_piv)) {
         s_bad = 1;
         d = floor_piv;
@@ -340,11 +344,11 @@ k_chol_solve_f64(const double* __restrict__ S, int lds, long long strideS, int m
     __syncthreads();
     const double ljj = s_piv;
     const double inv = 1.0 / ljj;
-    for (int i = j + tid; i < m; i += CH_NT) P[i * CH_LD + j] = (i == j) ? ljj : P[i * CH_LD + j] * inv;
+    for (int i = j + tid; i < m; i += CH_NT) P[i * ldp + j] = (i == j) ? ljj : P[i * ldp + j] * inv;
     __syncthreads();
     for (int i = j + 1 + ty; i < m; i += 32) {
-      const double lij = P[i * CH_LD + j];
-      for (int k = j + 1 + tx; k <= i; k += 32) P[i * CH_LD + k] -= lij * P[k * CH_LD + j];
+      const double lij = P[i * ldp + j];
+      for (int k = j + 1 + tx; k <= i; k += 32) P[i * ldp + k] -= lij * P[k * ldp + j];
     }
     __syncthreads();
   }
@@ -352,13 +356,13 @@ k_chol_solve_f64(const double* __restrict__ S, int lds, long long strideS, int m
   for (int c = tid; c < q; c += CH_NT) {
     for (int i = 0; i < m; ++i) {
       double acc = Bg[(long long)i * ldb + c];
-      for (int k = 0; k < i; ++k) acc -= P[i * CH_LD + k] * Bg[(long long)k * ldb + c];
-      Bg[(long long)i * ldb + c] = acc / P[i * CH_LD + i];
+      for (int k = 0; k < i; ++k) acc -= P[i * ldp + k] * Bg[(long long)k * ldb + c];
+      Bg[(long long)i * ldb + c] = acc / P[i * ldp + i];
     }
     for (int i = m - 1; i >= 0; --i) {
       double acc = Bg[(long long)i * ldb + c];
-      for (int k = i + 1; k < m; ++k) acc -= P[k * CH_LD + i] * Bg[(long long)k * ldb + c];
-      acc /= P[i * CH_LD + i];
+      for (int k = i + 1; k < m; ++k) acc -= P[k * ldp + i] * Bg[(long long)k * ldb + c];
+      acc /= P[i * ldp + i];
       Bg[(long long)i * ldb + c] = acc;
       Wg[(long long)i * ldw + c] = (float)acc;
     }
@@ -514,13 +518,27 @@ static int chol_qr_factor(const float* Y, int ldy, long long strideY, int n, int
 extern "C" int cpsd_chol_solve_f64(const double* S, int lds, long long strideS, int m, double* B,
                                    int ldb, long long strideB, int q, float* W, int ldw,
                                    long long strideW, int* status, int nprob, cudaStream_t stream) {
-  CPSD_CHECK_ARG(m > 0 && m <= 128 && q > 0, "chol_solve_f64: m must be in 1..128");
+  CPSD_CHECK_ARG(m > 0 && m <= 128 && q > 0, "chol_solve_f64: m must be in 1..128 (wider: cpsd_chol_solve_f64_ws)");
   if (nprob == 0) return CPSD_OK;
   const size_t smem = 128 * CH_LD * sizeof(double);
   CPSD_CUDA(cudaFuncSetAttribute(k_chol_solve_f64, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
   k_chol_solve_f64<<<nprob, CH_NT, smem, stream>>>(S, lds, strideS, m, B, ldb, strideB, q, W, ldw,
-                                                   strideW, status);
+                                                   strideW, status, nullptr);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
+}
+
+// Any m: the Cholesky factor lives in the caller's workspace (nprob * m * (m + 1) doubles)
+// instead of shared memory -- the read-in matrices of patients with more than 128 electrodes.
+extern "C" int cpsd_chol_solve_f64_ws(const double* S, int lds, long long strideS, int m, double* B,
+                                      int ldb, long long strideB, int q, float* W, int ldw,
+                                      long long strideW, int* status, double* ws, int nprob,
+                                      cudaStream_t stream) {
+  CPSD_CHECK_ARG(m > 0 && q > 0 && ws != nullptr, "chol_solve_f64_ws: bad dims / workspace");
+  if (nprob == 0) return CPSD_OK;
+  k_chol_solve_f64<<<nprob, CH_NT, 0, stream>>>(S, lds, strideS, m, B, ldb, strideB, q, W, ldw,
+                                                strideW, status, ws);
   CPSD_LAUNCH_CHECK();
   return CPSD_OK;
 }

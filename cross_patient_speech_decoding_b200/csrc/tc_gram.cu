@@ -45,7 +45,10 @@ struct TcProb {
 // growing linearly with K, 1e-4 at K=6000).  So TMEM only accumulates CHUNK k-blocks
 // (48 MMAs); the epilogue warps drain each partial tile into round-to-nearest fp32 register
 // accumulators while the MMA warp fills the other TMEM stage.
-constexpr int CHUNK = 4;
+#ifndef GRAM_EXP_CHUNK
+#define GRAM_EXP_CHUNK 4
+#endif
+constexpr int CHUNK = GRAM_EXP_CHUNK;
 constexpr int ACC_STAGES = 2;
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -66,7 +69,11 @@ k_gram_tc(const CUtensorMap* __restrict__ maps, const TcProb* __restrict__ probs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef GRAM_EXP_NOB
+  const bool diag = true;
+#else
   const bool diag = (tm == tn);
+#endif
   const CUtensorMap* map_hi = maps + 2 * prob;
   const CUtensorMap* map_lo = maps + 2 * prob + 1;
   const int nkb = (k_total + BK - 1) / BK;
@@ -182,6 +189,9 @@ k_gram_tc(const CUtensorMap* __restrict__ maps, const TcProb* __restrict__ probs
             : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
+#ifdef GRAM_EXP_NOEPI
+        if (c == 0)
+#endif
         for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(v[j]);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -1923,6 +1923,12 @@ class CVEngine:
             stj.zero_()
             for v in range(P):           # S_p W_p = rhs_p with S_p = G's diagonal block of patient p
                 C = int(cdims[v])
+                if C > 128:          # factor in an L2-resident workspace instead of shared memory
+                    cw = self.ws('j_cholws', (B * C * (C + 1),), torch.float64)
+                    ctx.call('cpsd_chol_solve_f64_ws', ptr(Gj, int(coff[v]) * nJ + int(coff[v])), nJ,
+                             nJ * nJ, C, ptr(rhs, v * Cm * Q), Q, P * Cm * Q, Q, ptr(L, v * Cm * Q), Q,
+                             P * Cm * Q, ptr(stj, v), ptr(cw), B)
+                    continue
                 ctx.call('cpsd_chol_solve_f64', ptr(Gj, int(coff[v]) * nJ + int(coff[v])), nJ, nJ * nJ, C,
                          ptr(rhs, v * Cm * Q), Q, P * Cm * Q, Q, ptr(L, v * Cm * Q), Q, P * Cm * Q,
                          ptr(stj, v), B)

@@ -267,6 +267,10 @@ int cpsd_chol_inv(const float* S, int lds, long long strideS, int m, float* Rinv
 int cpsd_chol_solve_f64(const double* S, int lds, long long strideS, int m, double* B, int ldb,
                         long long strideB, int q, float* W, int ldw, long long strideW,
                         int* status, int nprob, cudaStream_t stream);
+/* any m: the factor lives in ws (nprob * m * (m + 1) doubles) instead of shared memory */
+int cpsd_chol_solve_f64_ws(const double* S, int lds, long long strideS, int m, double* B, int ldb,
+                           long long strideB, int q, float* W, int ldw, long long strideW,
+                           int* status, double* ws, int nprob, cudaStream_t stream);
 /* PCA components with sklearn's svd_flip sign convention, zero padded to dmax columns */
 int cpsd_pca_basis(const float* evecs, int ldv, long long strideV, const int* k_dev,
                    const int* cdim, int c_fixed, int dmax, float* W, int ldw, int Cmax, int nprob,
