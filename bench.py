@@ -558,20 +558,24 @@ def main():
     n_all = 1152
     F = 200 * 30
     stage_total = sum(stages_batch.values()) or 1.0
+    # k_gram_tc alone: the engine's profile mode records an event between the hi/lo split and the
+    # MMA kernel (cpsd_gram_nt_tc_probe), so 'pool_split' / 'pool_gram' are the two kernels' own times
     gram_ms = stages_batch.get('pool_gram', float('nan'))
+    split_ms = stages_batch.get('pool_split', 0.0)
     gram_flops = 2.0 * n_all * n_all * F * nprof              # algorithmic, per launch (nprof folds)
     gram_tf = gram_flops / (gram_ms * 1e-3) / 1e12
+    split_bytes = 3.0 * n_all * F * 4 * nprof                 # read the pooled matrix once, write hi and lo
     peak_tf = pk.get('bf16_tflops_sustained', pk.get('bf16_tflops'))
     proj_ms = stages_batch.get('project_pool', float('nan'))
     proj_bytes = nprof * (sum(p[0].size for p in pts) * 4 + n_all * F * 4)   # read X once, write pooled
-    roofline = {'kernel': 'k_split_tf32_batched + k_gram_tc (pooled Gram of the centred matrix, tcgen05 '
-                          'kind::tf32, 3xTF32)' if not args.no_tc
+    roofline = {'kernel': 'k_gram_tc (pooled Gram of the centred matrix, tcgen05 kind::tf32, 3xTF32 on the '
+                          'hi/lo operands k_split_tf32_batched writes: see roofline_split)' if not args.no_tc
                 else 'k_gram_nt (pooled Gram, fp32 SIMT)',
                 'bound': 'tensor', 'achieved': gram_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
                 'frac': gram_tf / peak_tf,
                 # dram__bytes_read + write per fold from the committed ncu capture
                 # (profiles/traffic.json, written by profiles/summarize.py), times this launch's folds
-                'traffic': scaled_traffic(traffic, 'k_gram_tc', nprof, also='k_split_tf32_batched'),
+                'traffic': scaled_traffic(traffic, 'k_gram_tc', nprof),
                 'peak_source': '%s bf16_tflops_sustained (MEASURED_PEAKS.json)' % pk_kind,
                 # the pipe this kernel runs on: TF32 dense peak measured in this run (torch.matmul,
                 # allow_tf32, 8192^3, best of 5); 3xTF32 issues 3 MMAs per algorithmic product and only
@@ -581,7 +585,16 @@ def main():
                 'executed_tf32_tflops': gram_tf * 3.0 * 45.0 / 81.0,
                 'executed_frac_of_tf32_peak': (gram_tf * 3.0 * 45.0 / 81.0 / tf32_peak) if tf32_peak else None,
                 'algorithmic_flops_per_launch': gram_flops, 'launch_ms': gram_ms,
+                'launch_ms_with_split': gram_ms + split_ms,
+                'achieved_with_split': gram_flops / ((gram_ms + split_ms) * 1e-3) / 1e12,
                 'share_of_step': gram_ms / stage_total}
+    roofline_split = {'kernel': 'k_split_tf32_batched (centre + split the pooled matrix into tf32 hi / lo)',
+                      'bound': 'hbm', 'achieved': split_bytes / (split_ms * 1e-3) / 1e9 if split_ms else None,
+                      'peak': pk['hbm_gbs'], 'unit': 'GB/s',
+                      'frac': split_bytes / (split_ms * 1e-3) / 1e9 / pk['hbm_gbs'] if split_ms else None,
+                      'traffic': scaled_traffic(traffic, 'k_split_tf32_batched', nprof),
+                      'algorithmic_bytes_per_launch': split_bytes, 'launch_ms': split_ms,
+                      'share_of_step': split_ms / stage_total}
     proj_traffic = scaled_traffic(traffic, 'k_proj_tc', nprof)
     # compulsory traffic of the launch: X hi/lo once + every pooled matrix written once
     proj_real = proj_traffic if proj_traffic else (2 * sum(p[0].size for p in pts) * 4 + nprof * n_all * F * 4)
@@ -638,7 +651,8 @@ def main():
             'gpu_launches': launches,
             'h2d_bytes_per_step': h2d // args.steps, 'd2h_bytes_per_step': d2h // args.steps,
             'clocks': clk.summary(),
-            'roofline': roofline, 'roofline_hbm': roofline_hbm, 'step_roofline': step_roofline,
+            'roofline': roofline, 'roofline_hbm': roofline_hbm, 'roofline_split': roofline_split,
+            'step_roofline': step_roofline,
             'stages_ms_per_step': {k: round(v, 3) for k, v in stages.items()},
             'stages_batch_folds': nprof,
             'reuse': eng.stats.get('view_solves', 0) and

@@ -71,6 +71,7 @@ _SIGS = {
     'cpsd_dgemm_batched': [c_int, c_int, c_int, c_int, c_double, _P, c_int, c_ll, _P, _P, c_int, c_ll, _P,
                            c_double, _P, c_int, c_ll, _P, _P, c_int, c_ll, _P, c_int, _P],
     'cpsd_cast_f32_f64_idx': [_P, c_ll, _P, _P, c_ll, c_ll, c_int, _P],
+    'cpsd_gram_nt_tc_probe': [_P],
     'cpsd_bj_schedule': [c_int, _P],
     'cpsd_eig_sym_block': [_P, c_int, c_ll, c_int, _P, c_int, c_int, _P, _P, _P, _P, _P, _P,
                            c_int, c_int, c_float, _P, _P],

@@ -469,6 +469,15 @@ EncodeFn get_encode() {
 
 }  // namespace
 
+// Profiling hook: an event recorded between the hi/lo split and the MMA kernel of the next
+// cpsd_gram_nt_tc* calls (NULL: off), so that the two kernels can be timed separately with CUDA
+// events outside a profiler.  Not thread-safe: set by the one profiling caller only.
+static cudaEvent_t g_probe_event = nullptr;
+extern "C" int cpsd_gram_nt_tc_probe(void* event) {
+  g_probe_event = reinterpret_cast<cudaEvent_t>(event);
+  return CPSD_OK;
+}
+
 // Symmetric Gram of row-major fp32 matrices on the tensor cores.
 //   descs_host : HOST array of records (A == B, sym = 1, k % 4 == 0, lda % 4 == 0 required)
 //   split_ws   : device workspace, >= 2 * sum_p m_p * lda_p floats (hi / lo copies)
@@ -539,6 +548,7 @@ static int gram_nt_tc_impl(const cpsd_gram_nt_desc* descs_host, int nprob, int m
     int by = rows_max < 64 ? rows_max : 64;
     k_split_tf32_batched<<<dim3(bx, by, nprob), 256, 0, stream>>>(probs_d, k_total);
     CPSD_LAUNCH_CHECK();
+    if (g_probe_event) CPSD_CUDA(cudaEventRecord(g_probe_event, stream));
   }
   const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024 + 128;
   CPSD_CUDA(cudaFuncSetAttribute(k_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -1160,13 +1160,25 @@ class CVEngine:
             self._tc_stage = torch.empty((nbytes + 64,), dtype=torch.uint8).pin_memory()
         recs = np.ascontiguousarray(recs_host)
         a = (maps.data_ptr() + 63) & ~63
-        if mu is not None:
-            ctx.call('cpsd_gram_nt_tc_centered', ctypes.c_void_p(recs.ctypes.data), nprob, nmax, nmax,
-                     ptr(split), split.numel(), ctypes.c_void_p(a),
-                     ctypes.c_void_p(self._tc_stage.data_ptr()), ptr(mu), ldmu)
-            return
-        ctx.call('cpsd_gram_nt_tc', ctypes.c_void_p(recs.ctypes.data), nprob, nmax, nmax, ptr(split),
-                 split.numel(), ctypes.c_void_p(a), ctypes.c_void_p(self._tc_stage.data_ptr()))
+        mid = None
+        if getattr(self, 'profile', False) and self._marks and self._marks[-1][0] == 'pool_gram':
+            # stage timers: the hi/lo split (HBM-bound) and the MMA kernel (tensor-bound) separately
+            mid = torch.cuda.Event(enable_timing=True)
+            mid.record(torch.cuda.current_stream(ctx.device))      # creates the handle
+            ctx.lib.cpsd_gram_nt_tc_probe(ctypes.c_void_p(mid.cuda_event))
+            self._marks[-1] = ('pool_split', self._marks[-1][1])
+        try:
+            if mu is not None:
+                ctx.call('cpsd_gram_nt_tc_centered', ctypes.c_void_p(recs.ctypes.data), nprob, nmax, nmax,
+                         ptr(split), split.numel(), ctypes.c_void_p(a),
+                         ctypes.c_void_p(self._tc_stage.data_ptr()), ptr(mu), ldmu)
+            else:
+                ctx.call('cpsd_gram_nt_tc', ctypes.c_void_p(recs.ctypes.data), nprob, nmax, nmax, ptr(split),
+                         split.numel(), ctypes.c_void_p(a), ctypes.c_void_p(self._tc_stage.data_ptr()))
+        finally:
+            if mid is not None:
+                ctx.lib.cpsd_gram_nt_tc_probe(ctypes.c_void_p(0))
+                self._marks.append(('pool_gram', mid))
 
     def _pooled_stage_run(self, *args):
         """Blocking form of _pooled_stage_run_gen (CCA / none batches)."""

@@ -161,6 +161,9 @@ int cpsd_gram_nt_tc(const cpsd_gram_nt_desc* descs_host, int nprob, int m_max, i
 int cpsd_gram_nt_tc_centered(const cpsd_gram_nt_desc* descs_host, int nprob, int m_max, int n_max,
                              float* split_ws, long long split_ws_elems, void* map_ws,
                              void* stage_host, const float* mu, int ldmu, cudaStream_t stream);
+/* profiling hook: CUDA event (cudaEvent_t) recorded between the hi/lo split and the MMA kernel of
+ * the following cpsd_gram_nt_tc* calls; NULL switches it off */
+int cpsd_gram_nt_tc_probe(void* event);
 int cpsd_gram_nt_tc_ws_bytes(int nprob);
 
 /* ---- small solvers ---------------------------------------------------------------
