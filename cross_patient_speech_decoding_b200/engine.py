@@ -163,11 +163,13 @@ class CVEngine:
         self.speculative_topk = bool(speculative_topk) and os.environ.get('CPSD_SPECULATIVE_TOPK', '1') != '0'
         # warm-started tile eigen-solves (CPSD_WARM_START=0: every solve starts from the identity)
         self.warm_start = os.environ.get('CPSD_WARM_START', '1') != '0'
+        self.side_streams = os.environ.get('CPSD_SIDE_STREAMS', '1') != '0'
         self._runs_done = 0
         self._spec = False
         base = Context.get(device)
         self.lane = int(lane)
         self.stream = _lane_stream(base.device, self.lane)
+        self.lane_idx = self.lane
         self.ctx = LaneContext(base, self.stream)       # every launch of this engine goes to its lane
         with torch.cuda.stream(self.stream):     # uploads + fold-invariant work on the lane's stream
             self._init(target, cross, method, n_comp, regs, pca_var, decoder_var, C, tar_in_train,
@@ -912,6 +914,7 @@ class CVEngine:
             if getattr(self, '_tcp', None) is not None:
                 ln._tcp = dict(self._tcp, cap=0, nq=0)   # shares the X split + maps, own L^T buffers
             ln.stream = _lane_stream(self.ctx.device, self.lane + 1 + len(extra))
+            ln.lane_idx = self.lane + 1 + len(extra)
             ln.ctx = LaneContext(self.ctx.base, ln.stream)
             extra.append(ln)
         lanes = [self] + extra
@@ -1959,7 +1962,29 @@ class CVEngine:
             if Cm < n_padC:
                 cov.zero_()
                 Gt.zero_()
-            if use_rank:
+            rank_done = None
+            if use_rank and downdate and self.side_streams and not self.profile and B <= 64:
+                # small batches (one job per call: 20 problems per launch) leave most SMs idle, and
+                # the signal-rank solve is independent of the view solves until cpsd_mcca_mask_idx:
+                # it runs on the lane's side stream (same workspaces, explicit stream handle only).
+                # Full batches fill the SMs with one launch: nothing to overlap (measured)
+                ev_t = self.ws('mrk_ev', (B, n_padC))
+                sd = _lane_stream(ctx.device, 16 + self.lane_idx)
+                sx = LaneContext(ctx.base, sd)
+                fork = torch.cuda.Event()
+                fork.record(ctx.torch_stream)
+                sd.wait_event(fork)
+                sx.call('cpsd_sum_mats_f64', ptr(None), ptr(self.tg['trial']), 128 * 128,
+                        ctypes_int_ptr(pk.iaddr(o_lptr)), ctypes_int_ptr(pk.iaddr(o_list)),
+                        -1.0 if use_te else 1.0, ptr(Gt), 128 * 128, 128 * 128, B)
+                sx.call('cpsd_eig_sym_small_f64', ptr(Gt), n_padC, n_padC * n_padC, ptr(None), tv.C, B,
+                        ptr(ev_t), n_padC, ptr(None), n_padC, n_padC * n_padC, self.eig_sweeps + 6, 1e-10,
+                        ptr(None))
+                sx.call('cpsd_select_k', ptr(ev_t), n_padC, ptr(None), tv.C, float(self.pca_var), 1,
+                        0, 1 << 30, ptr(rank_dev), P, B)
+                rank_done = torch.cuda.Event()
+                rank_done.record(sd)
+            elif use_rank:
                 if downdate:     # train-set Gram = all-trials Gram - held-out trials (or sum of train)
                     ctx.call('cpsd_sum_mats_f64', ptr(None),
                              ptr(self.tg['trial']), 128 * 128, ctypes_int_ptr(pk.iaddr(o_lptr)),
@@ -2002,6 +2027,8 @@ class CVEngine:
             vs['next'] += nM
             self.stats['view_solves'] = self.stats.get('view_solves', 0) + nS
             self.stats['view_problems'] = self.stats.get('view_problems', 0) + B * P
+            if rank_done is not None:
+                ctx.torch_stream.wait_event(rank_done)
             ctx.call('cpsd_mcca_mask_idx', ptr(vs['evec']), n_padC, n_padC * n_padC, ptr(vs['ev']),
                      n_padC, ptr(rank_dev) if use_rank else ptr(None), cdim_dev,
                      ctypes_int_ptr(pk.iaddr(o_slot)), R, Cm, ptr(Vr), ptr(d2), ptr(r_eff), B * P)
