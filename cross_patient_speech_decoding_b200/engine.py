@@ -621,6 +621,12 @@ class CVEngine:
             self._vs = vs
         return vs
 
+    def _sm_count(self):
+        n = getattr(self, '_sms', None)
+        if n is None:
+            n = self._sms = torch.cuda.get_device_properties(self.ctx.device).multi_processor_count
+        return n
+
     def _view_bases(self):
         """Warm-start bases of the per-view scatter eigenproblems: for every (replica, patient) the
         eigenvectors of the first problem solved for it, as fp64 (rotation) and fp32 (starting
@@ -2004,14 +2010,21 @@ class CVEngine:
             if wplan is not None and cov.dtype == torch.float64:
                 ip = lambda o: ctypes_int_ptr(pk.iaddr(o))
                 n_dev = ip(o_cds)
-                if wplan['ncold']:
+                # a batch whose problems fit one wave of SMs and needs new bases anyway solves
+                # everything cold in ONE launch (cold + warm would be two dependent launches of
+                # which the second only halves its own latency); the bases serve later batches
+                one_wave = wplan['ncold'] > 0 and nS <= self._sm_count()
+                if one_wave:
+                    self.eig_warm(cov, n_dev, 0, nS, vs['ev'], vs['evec'], out_idx=ip(wplan['o_out']))
+                elif wplan['ncold']:
                     self.eig_warm(cov, n_dev, 0, wplan['ncold'], vs['ev'], vs['evec'],
                                   sel=ip(wplan['o_selc']), out_idx=ip(wplan['o_out']))
+                if wplan['ncold']:
                     self.ortho_bases(vs['evec'], ip(wplan['o_cslot']), wplan['ncold'], vb['Q'], vb['Qf'],
                                      vb['n'])
                     vb['n'] += wplan['ncold']
                     vb['tab'] = wplan['tab']
-                if wplan['nwarm']:
+                if wplan['nwarm'] and not one_wave:
                     self.rotate_sym(cov, vb['Q'], wplan['nwarm'], 'mv', sel=ip(wplan['o_selw']),
                                     base=ip(wplan['o_basew']))
                     self.eig_warm(cov, n_dev, 0, wplan['nwarm'], vs['ev'], vs['evec'],
