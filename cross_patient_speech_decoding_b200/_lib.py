@@ -111,7 +111,7 @@ _SIGS = {
     'cpsd_copy_rows': [_P, c_int, c_ll, _P, c_int, c_ll, _P, c_int, c_int, c_int, c_int, c_int, _P],
     'cpsd_sum_mats_f64': [_P, _P, c_ll, _P, _P, ctypes.c_double, _P, c_ll, c_int, c_int, _P],
     'cpsd_trial_colsum_f64': [_P, c_int, c_int, c_int, c_int, _P, c_int, _P],
-    'cpsd_cov_from_sums': [_P, c_int, c_ll, _P, c_int, _P, c_int, _P, c_int, _P, c_int, _P],
+    'cpsd_cov_from_sums': [_P, c_int, c_ll, _P, c_int, _P, c_int, _P, c_int, _P, c_int, c_int, _P],
     'cpsd_gather_channels': [_P, c_int, _P, c_int, _P, c_int, c_ll, _P],
     'cpsd_gather_trials': [_P, c_ll, _P, c_int, _P, _P],
     'cpsd_mask_cols': [_P, c_int, c_ll, c_int, c_int, _P, c_int, c_int, _P],

@@ -419,6 +419,7 @@ extern "C" int cpsd_gather_channels(const float* src, int lds, const int* idx, i
 // the covariance of a trial subset from per-trial statistics: with G = sum of the subset's
 // per-trial Grams X_t^T X_t and s = sum of its column sums over n = (#trials * T) rows,
 //     cov = (G - s s^T / n) / (n - 1),   mu = s_mu / n
+// (normalize == 0: the centred scatter G - s s^T / n itself, as the MCCA view solves take it)
 // (s_mu = s unless G and s were moved to another basis: the means stay in channel coordinates)
 // -- sklearn PCA's centred covariance (decoders/cross_pt_decoders.py:234-241 -> PCA.fit) of every
 // CV fold's train trials without another pass over the data: the per-trial statistics are
@@ -438,14 +439,15 @@ k_trial_colsum_f64(const float* __restrict__ X, int T, int C, int ldx, double* _
 __global__ void __launch_bounds__(256)
 k_cov_from_sums(double* __restrict__ G, int ldg, long long strideG, const double* __restrict__ s, int lds,
                 const int* __restrict__ nrows, int C, float* __restrict__ mu, int ldmu,
-                const double* __restrict__ s_mu) {
+                const double* __restrict__ s_mu, int normalize) {
   const int p = blockIdx.x;
   const double n = (double)nrows[p];
   double* Gp = G + (long long)p * strideG;
   const double* sp = s + (long long)p * lds;
   for (int e = threadIdx.x; e < C * C; e += blockDim.x) {
     const int i = e / C, j = e - i * C;
-    Gp[(long long)i * ldg + j] = (Gp[(long long)i * ldg + j] - sp[i] * sp[j] / n) / (n - 1.0);
+    const double v = Gp[(long long)i * ldg + j] - sp[i] * sp[j] / n;
+    Gp[(long long)i * ldg + j] = normalize ? v / (n - 1.0) : v;
   }
   if (mu) {
     const double* sm = s_mu ? s_mu + (long long)p * lds : sp;
@@ -465,10 +467,10 @@ extern "C" int cpsd_trial_colsum_f64(const float* X, int n_trials, int T, int C,
 
 extern "C" int cpsd_cov_from_sums(double* G, int ldg, long long strideG, const double* s, int lds,
                                   const int* nrows_dev, int C, float* mu, int ldmu,
-                                  const double* s_mu, int nprob, cudaStream_t stream) {
+                                  const double* s_mu, int normalize, int nprob, cudaStream_t stream) {
   CPSD_CHECK_ARG(nprob >= 0 && C > 0 && ldg >= C && lds >= C && nrows_dev != nullptr, "cov_from_sums: bad dims");
   if (nprob == 0) return CPSD_OK;
-  k_cov_from_sums<<<nprob, 256, 0, stream>>>(G, ldg, strideG, s, lds, nrows_dev, C, mu, ldmu, s_mu);
+  k_cov_from_sums<<<nprob, 256, 0, stream>>>(G, ldg, strideG, s, lds, nrows_dev, C, mu, ldmu, s_mu, normalize);
   CPSD_LAUNCH_CHECK();
   return CPSD_OK;
 }

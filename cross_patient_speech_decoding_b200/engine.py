@@ -753,6 +753,7 @@ class CVEngine:
             self._rank_dev = self._ranks_full(range(1, self.P))     # (replica, view) order
             self.cross_rank = None
             self._target_trial_grams()
+            self._cross_class_stats()
             self._keep = [pk]                # staging of the kernels still in flight
         else:
             if self.method in ('cca', 'none') and self.Cmax <= 128 and self.J == 1:
@@ -774,6 +775,45 @@ class CVEngine:
                                    align_only=True)
             k_all = int(res['k'][0])
             self._joint_qcap = min(120, _ceil(k_all + max(4, k_all // 4), 4))
+
+    def _cross_class_stats(self):
+        """Per-class Gram matrices M_k^T M_k and column sums (fp64) of every cross patient's
+        condition averages (M_k: the T rows of class k), for every replica.  The centred scatter of
+        the averages restricted to ANY shared class set -- what AlignMCCA.py:140-154 feeds to the
+        per-view SVD, one set per distinct loss of classes among the target's train trials -- is then
+        sum_k G_k - s s^T / n with s = sum_k s_k: a list sum instead of a pass over the averages per
+        (patient, class set).  Rows of the two tables: ccs_off[v] + replica * n_classes_v + class slot."""
+        self.ccs = None
+        if self.P < 2 or self.Cmax > 128 or not self.warm_start:
+            return
+        ctx, T, J = self.ctx, self.T, self.J
+        ncl = [0] + [self.cm[v].shape[1] // T for v in range(1, self.P)]
+        off = np.concatenate([[0, 0], np.cumsum([J * n for n in ncl[1:]])]).astype(np.int64)
+        tot = int(off[-1])
+        G = ctx.zeros((tot, 128, 128), torch.float64)
+        S = ctx.zeros((tot, 128), torch.float64)
+        pk = HostPack(ctx)
+        o_zero = pk.add_ints([0])
+        pk.reserve_ints()
+        recs = np.zeros(tot, dtype=_lib.GRAM_TN_DESC)
+        r = 0
+        for v in range(1, self.P):
+            C, n = self.views[v].C, ncl[v]
+            for j in range(J):
+                a = addr(self.cm[v][j]) + 4 * T * C * np.arange(n, dtype=np.int64)
+                sl = slice(r, r + n)
+                recs['A'][sl] = recs['B'][sl] = a
+                recs['p'][sl] = recs['q'][sl] = recs['lda'][sl] = recs['ldb'][sl] = C
+                ctx.call('cpsd_trial_colsum_f64', ptr(self.cm[v][j]), n, T, C, C, ptr(S, r * 128), 128)
+                r += n
+        recs['segA'] = recs['segB'] = pk.iaddr(o_zero)
+        recs['out'] = addr(G) + 8 * 128 * 128 * np.arange(tot, dtype=np.int64)
+        recs['nseg'], recs['seg_len'] = 1, T
+        recs['ldo'], recs['sym'], recs['alpha'] = 128, 1, 1.0
+        d = pk.add_descs(recs)
+        pk.upload()
+        ctx.call('cpsd_gram_tn_f64', pk.daddr(d), tot, self.Cmax, self.Cmax)
+        self.ccs = dict(G=G, S=S, off=off, ncl=ncl, keep=pk)
 
     def _ranks_full(self, vs):
         """AlignMCCA.n_components_var on all trials of the given views (AlignMCCA.py:146-150)."""
@@ -1550,6 +1590,7 @@ class CVEngine:
             slot[:, 0] = fold_of
             for attempt in range(2):
                 solve = [(f, 0, f) for f in range(B)]
+                solve_u = []                 # shared-class-set index of every cross problem
                 pending = {}
                 if P > 1:
                     rows_u = np.zeros((len(shared_u), P - 1), dtype=np.int64)
@@ -1561,6 +1602,7 @@ class CVEngine:
                                 sl = vs['next'] + len(pending)
                                 pending[key] = sl
                                 solve.append((int(first[u]), v, sl))
+                                solve_u.append(u)
                             rows_u[u, v - 1] = sl
                     slot[:, 1:] = rows_u[inv]
                 if vs['next'] + len(pending) <= vs['cap']:
@@ -1569,6 +1611,17 @@ class CVEngine:
                 vs['next'] = vs['res']
             o_slot = pk.add_ints(slot)
             o_cds = pk.add_ints([self.views[v].C for _, v, _ in solve])
+            # cross problems: centred scatter from the per-class statistics (_cross_class_stats)
+            xplan = None
+            ccs = getattr(self, 'ccs', None)
+            if ccs is not None and n_padC == 128 and len(solve) > B:
+                lists, nrw = [], []
+                for (f, v, sl), u in zip(solve[B:], solve_u):
+                    rows = self.cm_row[v][shared_u[u]]
+                    lists.append(ccs['off'][v] + int(rep_u[u]) * ccs['ncl'][v] + rows)
+                    nrw.append(len(rows) * T)
+                xplan = dict(o_lptr=pk.add_ints(np.concatenate([[0], np.cumsum([len(l) for l in lists])])),
+                             o_list=pk.add_ints(np.concatenate(lists)), o_nrows=pk.add_ints(nrw))
             # warm-start plan of the view solves: the first scatter matrix solved for a (replica,
             # patient) pair is solved cold and its eigenvectors become the pair's basis; every
             # other problem of the pair is rotated into that basis and starts from it
@@ -2003,9 +2056,22 @@ class CVEngine:
                          0, 1 << 30, ptr(rank_dev), P, B)
             # per-view centred scatter of the condition averages + eigen-decomposition, for the
             # target of every fold and for the cross-patient problems not solved before
-            ctx.call('cpsd_colsum', pk.daddr(d_mu), nS, Cm)
-            self.gram_scatter(gram_c, pk.daddr(d_cov), nS, Cm, Cm, cov, 3)
             nM, s0 = nS - B, vs['next']
+            if xplan is not None and cov.dtype == torch.float64:
+                # targets: one pass over each fold's condition averages; cross patients: list sums
+                ctx.call('cpsd_colsum', pk.daddr(d_mu), B, Cm)
+                self.gram_scatter(gram_c, pk.daddr(d_cov), B, Cm, Cm, cov, 3)
+                lp, ll = ctypes_int_ptr(pk.iaddr(xplan['o_lptr'])), ctypes_int_ptr(pk.iaddr(xplan['o_list']))
+                xs_ = self.ws('m_xsum', (nM, 128), torch.float64)
+                ctx.call('cpsd_sum_mats_f64', ptr(None), ptr(ccs['G']), 128 * 128, lp, ll, 1.0,
+                         ptr(cov, B * 128 * 128), 128 * 128, 128 * 128, nM)
+                ctx.call('cpsd_sum_mats_f64', ptr(None), ptr(ccs['S']), 128, lp, ll, 1.0, ptr(xs_), 128, 128, nM)
+                ctx.call('cpsd_cov_from_sums', ptr(cov, B * 128 * 128), 128, 128 * 128, ptr(xs_), 128,
+                         ctypes_int_ptr(pk.iaddr(xplan['o_nrows'])), Cm, ptr(mu, s0 * Cm), Cm, ptr(None),
+                         0, nM)
+            else:
+                ctx.call('cpsd_colsum', pk.daddr(d_mu), nS, Cm)
+                self.gram_scatter(gram_c, pk.daddr(d_cov), nS, Cm, Cm, cov, 3)
             ncol = min(n_padC, R)
             if wplan is not None and cov.dtype == torch.float64:
                 ip = lambda o: ctypes_int_ptr(pk.iaddr(o))

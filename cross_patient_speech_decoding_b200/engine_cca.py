@@ -98,7 +98,7 @@ def batch_cca_gen(eng, batch, want_details):
             smu = eng.ws('c_ssum0', (B, 128), torch.float64)
             ctx.call('cpsd_sum_mats_f64', ptr(None), ptr(tg['sums0']), 128, lp, ll, sgn, ptr(smu), 128, 128, B)
         ctx.call('cpsd_cov_from_sums', ptr(cov), 128, 128 * 128, ptr(ssum), 128,
-                 ctypes_int_ptr(pk.iaddr(o_nrows)), tv.C, ptr(mu_t), Cm, ptr(smu), B)
+                 ctypes_int_ptr(pk.iaddr(o_nrows)), tv.C, ptr(mu_t), Cm, ptr(smu), 1, B)
     else:
         ctx.call('cpsd_colsum', pk.daddr(d_mu), B, tv.C)
         ctx.call(gram_c, pk.daddr(d_cov), B, tv.C, tv.C)

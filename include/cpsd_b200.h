@@ -59,13 +59,13 @@ int cpsd_sum_mats_f64(const double* base, const double* mats, long long mat_stri
                       const int* list_ptr, const int* list, double sign, double* out,
                       long long out_stride, int elems, int nprob, cudaStream_t stream);
 /* per-trial column sums (fp64) and the centred covariance of a trial subset from per-trial
- * statistics, cov = (G - s s^T / n) / (n - 1), mu = s_mu / n (s_mu NULL: s): sklearn PCA's covariance of a fold's
+ * statistics, cov = (G - s s^T / n) / (n - 1), mu = s_mu / n (s_mu NULL: s; normalize 0: the centred scatter without the 1 / (n - 1)): sklearn PCA's covariance of a fold's
  * train trials (decoders/cross_pt_decoders.py:234-241 -> PCA.fit) without re-reading the trials */
 int cpsd_trial_colsum_f64(const float* X, int n_trials, int T, int C, int ldx, double* sums, int lds,
                           cudaStream_t stream);
 int cpsd_cov_from_sums(double* G, int ldg, long long strideG, const double* s, int lds,
                        const int* nrows_dev, int C, float* mu, int ldmu, const double* s_mu,
-                       int nprob, cudaStream_t stream);
+                       int normalize, int nprob, cudaStream_t stream);
 /* electrode subsampling of resident trials: dst = src[:, idx] (the channel lists of
  * processing_utils/grid_subsampling.py:8-61 and poisson_disk_sampling.py:9-77) and the block
  * means of spatial_avg_data (processing_utils/spatial_avg_subsampling.py:74-96) */
