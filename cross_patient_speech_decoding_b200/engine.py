@@ -804,8 +804,9 @@ class CVEngine:
                 sl = slice(r, r + n)
                 recs['A'][sl] = recs['B'][sl] = a
                 recs['p'][sl] = recs['q'][sl] = recs['lda'][sl] = recs['ldb'][sl] = C
-                ctx.call('cpsd_trial_colsum_f64', ptr(self.cm[v][j]), n, T, C, C, ptr(S, r * 128), 128)
                 r += n
+            # (the replicas' slabs of a patient are contiguous: one launch per patient)
+            ctx.call('cpsd_trial_colsum_f64', ptr(self.cm[v]), J * n, T, C, C, ptr(S, int(off[v]) * 128), 128)
         recs['segA'] = recs['segB'] = pk.iaddr(o_zero)
         recs['out'] = addr(G) + 8 * 128 * 128 * np.arange(tot, dtype=np.int64)
         recs['nseg'], recs['seg_len'] = 1, T

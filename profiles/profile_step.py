@@ -34,6 +34,7 @@ def mk(seed):
 
 
 eng.run(mk(1000))
+eng.run(mk(1500))        # second use: trial statistics move to the all-trials eigenbasis (once)
 for s in range(a.steps):
     eng.profile = a.stages
     fl = mk(2000 if a.same else 2000 + 100 * s)
