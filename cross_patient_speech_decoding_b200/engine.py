@@ -1675,9 +1675,8 @@ class CVEngine:
             # 'all trials minus held-out trials' equals the train-set Gram only when train and
             # test partition the target's trials exactly (plain K-fold units); subsampled train
             # sets, fit-only calls and inner folds of a nested search sum the train list instead
-            hits = np.zeros((B, tv.N), dtype=np.int32)
-            np.add.at(hits, (np.nonzero(mtr)[0], TR[mtr]), 1)
-            np.add.at(hits, (np.nonzero(mte)[0], TE[mte]), 1)
+            flat = np.concatenate([np.nonzero(mtr)[0] * tv.N + TR[mtr], np.nonzero(mte)[0] * tv.N + TE[mte]])
+            hits = np.bincount(flat, minlength=B * tv.N).reshape(B, tv.N)
             use_te = bool((hits == 1).all()) and int(n_te_a.sum()) <= int(n_tr_a.sum())
             # rows of self.tg['trial']: replica * N + trial, then J * N + replica = minus the sum of
             # the replica's trials; a fold's Gram is -(listed rows) (held-out form) or +(train rows)

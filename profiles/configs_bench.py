@@ -70,8 +70,9 @@ if '2s' in todo:
         folds = folds_for(pts[0][1], 20, args.iters, 150)
         eng = CVEngine(dev[0], dev[1:], method='mcca', n_comp=30, regs=0.5, pca_var=0.8, decoder=dec,
                        class_weight=cw, use_tensor_cores=True, max_batch=148)
-        eng.profile = True
         timed('2: 8 patients, MCCA, 20-fold, decoder=%s class_weight=%s' % (dec, cw), eng, folds)
+        eng.profile = True
+        eng.run(folds)
         print('   stages ms:', {k: round(v, 2) for k, v in eng.collect_marks().items()}, flush=True)
 
 if '3' in todo:
@@ -81,14 +82,13 @@ if '3' in todo:
             kw = dict(method=method, n_comp=d, use_tensor_cores=True, max_batch=148, dcd_epochs=args.dcd)
             if method == 'mcca':
                 kw.update(regs=0.5, pca_var=0.8)
-            if method == 'jointpca':
-                kw.update(max_batch=32)
             if method == 'cca':
                 kw.update(max_batch=args.cca_batch)
             eng = CVEngine(dev[0], dev[1:], **kw)
-            eng.profile = True
             try:
                 timed('3: 8 patients, %s, d=%d, 20-fold' % (method, d), eng, folds)
+                eng.profile = True               # stage timers: a separate single-lane run
+                eng.run(folds)
                 print('   stages ms:', {k: round(v, 2) for k, v in eng.collect_marks().items()}, flush=True)
             except ValueError as e:          # mvlearn raises too when n_components exceeds the summed ranks
                 print(json.dumps(dict(config='3: 8 patients, %s, d=%d' % (method, d), error=str(e)[:80])), flush=True)
