@@ -25,7 +25,7 @@ namespace {
 
 #define SV_NT 256
 #ifndef SV_MINB
-#define SV_MINB 3
+#define SV_MINB 4
 #endif
 #define SV_INEXACT_ITS 12
 
