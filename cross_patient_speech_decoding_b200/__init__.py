@@ -73,6 +73,7 @@ def cv_align_decode_stream(jobs, depth=8, method='mcca', device=None, group=None
     of them in one batch run at the resident-data rate)."""
     import collections
     import time
+    from . import engine as _engine
 
     import numpy as np
     import torch
@@ -181,7 +182,7 @@ def cv_align_decode_stream(jobs, depth=8, method='mcca', device=None, group=None
             for r in split(pending.popleft()):
                 yield r
         if not progressed:
-            time.sleep(0)
+            time.sleep(_engine._IDLE_SLEEP)
             cv_align_decode_stream.idle_s += time.perf_counter() - t_iter
 
 

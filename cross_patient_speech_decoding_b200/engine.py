@@ -30,6 +30,8 @@ def _ceil(a, b):
 
 
 _LANE_STREAMS = {}
+# idle wait of the lane schedulers between polls of their CUDA events (seconds; 0 = yield only)
+_IDLE_SLEEP = float(os.environ.get('CPSD_IDLE_SLEEP', '0'))
 
 
 def _lane_stream(device, i):
@@ -1046,7 +1048,7 @@ class CVEngine:
                         gens[li] = None
                         live -= 1
             if not progressed:
-                time.sleep(0)
+                time.sleep(_IDLE_SLEEP)
         for ln in lanes:
             ln.stream.synchronize()
         for res in results:

@@ -17,8 +17,9 @@ from cross_patient_speech_decoding_b200 import cv_align_decode_stream  # noqa: E
 pts = bench.make_data()
 y0 = pts[0][1]
 host_pts = [(torch.from_numpy(np.ascontiguousarray(X)).pin_memory(), y, ya) for X, y, ya in pts]
-kw = dict(method='mcca', n_comp=30, regs=0.5, pca_var=0.8, decoder_var=0.8, use_tensor_cores=True, max_batch=20)
-depth = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+kw = dict(method='mcca', n_comp=30, regs=0.5, pca_var=0.8, decoder_var=0.8, use_tensor_cores=True, max_batch=148)
+depth = int(sys.argv[1]) if len(sys.argv) > 1 else 21
+group = int(sys.argv[2]) if len(sys.argv) > 2 else 7
 
 
 def jobs(n, s0):
@@ -26,14 +27,14 @@ def jobs(n, s0):
         yield host_pts[0], host_pts[1:], bench.step_folds(y0, s0 + s)
 
 
-for _ in cv_align_decode_stream(jobs(depth + 2, 77), depth=depth, **kw):
+for _ in cv_align_decode_stream(jobs(2 * depth, 77), depth=depth, group=group, **kw):
     pass
 torch.cuda.synchronize()
-n = 32
+n = 84
 t0 = time.perf_counter()
 pr = cProfile.Profile()
 pr.enable()
-for _ in cv_align_decode_stream(jobs(n, 500), depth=depth, **kw):
+for _ in cv_align_decode_stream(jobs(n, 500), depth=depth, group=group, **kw):
     pass
 torch.cuda.synchronize()
 pr.disable()
