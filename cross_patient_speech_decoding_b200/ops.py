@@ -186,18 +186,16 @@ def chol_inv(S, device=None):
 
 
 def lstsq_gram(X, Y, device=None):
-    """Least-squares solution W = argmin |X W - Y| for a full-column-rank X (rows x C, C <= 128)
-    through the normal equations in fp64: X^T X and X^T Y are accumulated in fp64 on the GPU and
-    solved by a shared-memory Cholesky.  Returns (W (C, q) float64, status)."""
+    """Least-squares solution W = argmin |X W - Y| for a full-column-rank X (rows x C) through the
+    normal equations in fp64: X^T X and X^T Y are accumulated in fp64 on the GPU and solved by a
+    Cholesky factorisation (in shared memory up to 128 columns, in an L2-resident workspace above:
+    patients with more than 128 electrodes).  Returns (W (C, q) float64, status)."""
     ctx = _ctx(device)
     X = np.ascontiguousarray(X, dtype=np.float32)
     Y = np.ascontiguousarray(Y, dtype=np.float32)
     rows, C = X.shape
     q = Y.shape[1]
     assert Y.shape[0] == rows
-    if C > 128:
-        raise ValueError('lstsq_gram: at most 128 columns (channels per patient) -- the normal equations are '
-                         'solved by a shared-memory Cholesky; the reference (JointPCA.py:203-206) has no limit')
     Xd, Yd = ctx.upload(X), ctx.upload(Y)
     pk = HostPack(ctx)
     o = pk.add_ints([0])
@@ -214,8 +212,13 @@ def lstsq_gram(X, Y, device=None):
     ctx.call('cpsd_gram_tn_f64', pk.daddr(d), 2, C, max(C, q))
     W = ctx.zeros((C, q))
     st = ctx.zeros((1,), I32)
-    ctx.call('cpsd_chol_solve_f64', ptr(S), C, C * C, C, ptr(Bm), q, C * q, q, ptr(W), q, C * q,
-             ptr(st), 1)
+    if C > 128:
+        cw = ctx.empty((C * (C + 1),), F64)
+        ctx.call('cpsd_chol_solve_f64_ws', ptr(S), C, C * C, C, ptr(Bm), q, C * q, q, ptr(W), q, C * q,
+                 ptr(st), ptr(cw), 1)
+    else:
+        ctx.call('cpsd_chol_solve_f64', ptr(S), C, C * C, C, ptr(Bm), q, C * q, q, ptr(W), q, C * q,
+                 ptr(st), 1)
     return W.cpu().numpy().astype(np.float64), int(st.cpu().numpy()[0])
 
 

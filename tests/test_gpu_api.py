@@ -238,6 +238,33 @@ def test_cv_align_decode_public_api(pkg):
     assert out['h2d_bytes'] > 0 and out['d2h_bytes'] > 0
 
 
+def test_joint_pca_class_with_more_than_128_electrodes(pkg):
+    """JointPCA read-in matrices of a patient with 150 electrodes (the real recordings reach 201):
+    the normal equations factor in the workspace-backed Cholesky; against the float64 port of
+    JointPCA.get_joint_PCA_transforms (pinv(X_p) @ latent)."""
+    from cross_patient_speech_decoding_b200 import ops, synthetic
+    from cross_patient_speech_decoding_b200.alignment.JointPCA import JointPCA
+    from oracle import pipeline_port as port
+    pts = [synthetic.make_patient(p, n_trials=n, n_time=30, n_chan=c) for p, n, c in ((0, 80, 150), (1, 90, 40))]
+    Xs, yal = [p[0] for p in pts], [p[2] for p in pts]
+    jp = JointPCA(n_components=8)
+    Z = jp.fit_transform(Xs, yal)
+    Wref = port.joint_pca_fit(Xs, yal, 8)
+    for v in range(2):
+        W = jp.transforms[v]
+        sgn = np.sign(np.sum(W * Wref[v], axis=0))
+        assert np.abs(W * sgn - Wref[v]).max() <= 5e-3 * np.abs(Wref[v]).max()
+        assert Z[v].shape == Xs[v].shape[:-1] + (8,)
+    # the solver alone, 201 columns
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((900, 201))
+    Y = rng.standard_normal((900, 7))
+    W, st = ops.lstsq_gram(X, Y)
+    ref = np.linalg.lstsq(X.astype(np.float32).astype(np.float64), Y.astype(np.float32).astype(np.float64),
+                          rcond=None)[0]
+    assert st == 0 and np.abs(W - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
 def test_joint_pca_matches_reference_golden(pkg):
     """alignment.JointPCA.JointPCA (GPU) against the reference class's stored output: read-in
     matrices, transformed trials, API errors; and crossPtDecoder_jointDimRed end to end."""
