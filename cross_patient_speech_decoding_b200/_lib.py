@@ -138,6 +138,7 @@ _SIGS = {
     'cpsd_scores_test': [_P, c_int, c_ll, _P, c_int, c_ll, _P, _P, c_int, _P, _P, c_int, c_int,
                          _P, c_int, c_ll, c_int, c_int, _P],
     'cpsd_svm_fit_ovr': [_P, c_int, c_int, c_int, _P],
+    'cpsd_svm_fit_ovr_ex': [_P, c_int, c_int, c_int, c_int, _P],
     'cpsd_svm_predict_ovr': [_P, c_int, c_ll, _P, c_int, c_ll, _P, c_int, _P, c_int, _P, c_int, _P,
                              _P, c_int, _P],
     'cpsd_svc_kernel_matrix': [_P, c_int, c_ll, _P, c_int, _P, c_int, c_int, _P, c_int, _P, c_int, c_int,

@@ -25,7 +25,7 @@ namespace {
 
 #define SV_NT 256
 #ifndef SV_MINB
-#define SV_MINB 4
+#define SV_MINB 5
 #endif
 #define SV_INEXACT_ITS 12
 
@@ -35,13 +35,18 @@ struct SvmSmem {
   float* yv; int* perm; double* red;
 };
 
-__device__ __forceinline__ SvmSmem carve(unsigned char* base, int kp_max, int n_max) {
+// dcd == 0: no task of the launch runs the dual-CD phase, so its per-sample arrays (alpha, QD,
+// permutation: 20 bytes per sample) are not carved -- 32 KB instead of 50 KB per task at
+// n = 1152, which is what lets five tasks share an SM.
+__device__ __forceinline__ SvmSmem carve(unsigned char* base, int kp_max, int n_max, int dcd) {
   SvmSmem s;
   double* dp = reinterpret_cast<double*>(base);
   s.red = dp; dp += 40;
   s.w = dp; dp += kp_max; s.g = dp; dp += kp_max; s.d = dp; dp += kp_max; s.r = dp; dp += kp_max;
   s.zz = dp; dp += kp_max; s.p = dp; dp += kp_max; s.hp = dp; dp += kp_max; s.dg = dp; dp += kp_max;
-  s.z = dp; dp += n_max; s.q = dp; dp += n_max; s.alpha = dp; dp += n_max; s.qd = dp; dp += n_max;
+  s.z = dp; dp += n_max; s.q = dp; dp += n_max;
+  s.alpha = dp; s.qd = dp;
+  if (dcd) { dp += n_max; s.qd = dp; dp += n_max; }
   s.yv = reinterpret_cast<float*>(dp);
   s.perm = reinterpret_cast<int*>(s.yv + n_max);
   return s;
@@ -81,10 +86,11 @@ __device__ __forceinline__ double bdot(const double* a, const double* b, int n, 
 }
 
 __global__ void __launch_bounds__(SV_NT, SV_MINB)
-k_svm_fit(const cpsd_svm_desc* __restrict__ descs, int kp_max, int n_max) {
+k_svm_fit(const cpsd_svm_desc* __restrict__ descs, int kp_max, int n_max, int dcd) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const cpsd_svm_desc t = descs[blockIdx.x];
-  SvmSmem s = carve(smem_raw, kp_max, n_max);
+  cpsd_svm_desc t = descs[blockIdx.x];
+  if (!dcd) t.dcd_epochs = 0;                 // (the host checked: no task asked for the phase)
+  SvmSmem s = carve(smem_raw, kp_max, n_max, dcd);
   const int n = min(t.n, n_max);
   int k = t.k_dev ? t.k_dev[0] : t.k;
   if (k > kp_max - 1) k = kp_max - 1;
@@ -97,7 +103,7 @@ k_svm_fit(const cpsd_svm_desc* __restrict__ descs, int kp_max, int n_max) {
 
   for (int i = threadIdx.x; i < n; i += SV_NT) {
     s.yv[i] = (t.y[i] == t.cls) ? 1.f : -1.f;
-    s.alpha[i] = 0.0;
+    if (dcd) s.alpha[i] = 0.0;
   }
   for (int j = threadIdx.x; j < kp; j += SV_NT) s.w[j] = 0.0;
   __syncthreads();
@@ -352,20 +358,29 @@ __global__ void k_svm_predict(const float* __restrict__ Xt, int ldx, long long s
 
 }  // namespace
 
-static size_t svm_smem_bytes(int kp_max, int n_max) {
-  return (40 + 8 * (size_t)kp_max + 4 * (size_t)n_max) * sizeof(double) + 2 * (size_t)n_max * 4 + 16;
+static size_t svm_smem_bytes(int kp_max, int n_max, int dcd) {
+  return (40 + 8 * (size_t)kp_max + (dcd ? 4 : 2) * (size_t)n_max) * sizeof(double) +
+         (dcd ? 2 : 1) * (size_t)n_max * 4 + 16;
+}
+
+// dcd_epochs_max: the largest dcd_epochs of any task of the launch (0: Newton only -- the
+// dual-CD work arrays are left out of shared memory and more tasks share an SM).
+extern "C" int cpsd_svm_fit_ovr_ex(const cpsd_svm_desc* descs_dev, int ntask, int k_max, int n_max,
+                                   int dcd_epochs_max, cudaStream_t stream) {
+  CPSD_CHECK_ARG(ntask >= 0 && k_max >= 0 && n_max > 0, "svm_fit_ovr: bad dims");
+  if (ntask == 0) return CPSD_OK;
+  const int dcd = dcd_epochs_max > 0;
+  const size_t smem = svm_smem_bytes(k_max + 1, n_max, dcd);
+  CPSD_CHECK_ARG(smem <= 227 * 1024, "svm_fit_ovr: n_max/k_max exceed the shared-memory budget");
+  CPSD_CUDA(cudaFuncSetAttribute(k_svm_fit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_svm_fit<<<ntask, SV_NT, smem, stream>>>(descs_dev, k_max + 1, n_max, dcd);
+  CPSD_LAUNCH_CHECK();
+  return CPSD_OK;
 }
 
 extern "C" int cpsd_svm_fit_ovr(const cpsd_svm_desc* descs_dev, int ntask, int k_max, int n_max,
                                 cudaStream_t stream) {
-  CPSD_CHECK_ARG(ntask >= 0 && k_max >= 0 && n_max > 0, "svm_fit_ovr: bad dims");
-  if (ntask == 0) return CPSD_OK;
-  const size_t smem = svm_smem_bytes(k_max + 1, n_max);
-  CPSD_CHECK_ARG(smem <= 227 * 1024, "svm_fit_ovr: n_max/k_max exceed the shared-memory budget");
-  CPSD_CUDA(cudaFuncSetAttribute(k_svm_fit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_svm_fit<<<ntask, SV_NT, smem, stream>>>(descs_dev, k_max + 1, n_max);
-  CPSD_LAUNCH_CHECK();
-  return CPSD_OK;
+  return cpsd_svm_fit_ovr_ex(descs_dev, ntask, k_max, n_max, 1, stream);
 }
 
 extern "C" int cpsd_svm_predict_ovr(const float* Xt, int ldx, long long strideX, const double* W,

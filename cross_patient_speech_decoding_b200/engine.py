@@ -1377,7 +1377,8 @@ class CVEngine:
         nte_dev = ctypes_int_ptr(pk.iaddr(o_nte))
         if self.decoder == 'linear':
             # shared memory of the solver is sized by the largest k2 of the batch, not by its cap
-            ctx.call('cpsd_svm_fit_ovr', pk.daddr(d_svm), B * ncls, min(kcap, self._k2_max), n_pad)
+            ctx.call('cpsd_svm_fit_ovr_ex', pk.daddr(d_svm), B * ncls, min(kcap, self._k2_max), n_pad,
+                     int(self.dcd_epochs))
             ctx.call('cpsd_svm_predict_ovr', ptr(Ste), n_te_max, kcap * n_te_max, ptr(W), kcap + 1,
                      ncls * (kcap + 1), ptr(k2), 0, nte_dev, n_te_max, ptr(self.classes_dev), ncls,
                      ptr(yhat), ptr(None), B)

@@ -553,7 +553,7 @@ def svm_fit_ovr(S, y, C=1.0, dcd_epochs=0, max_newton=400, tol_newton=1e-9, tol_
     pk.reserve_ints()
     d = pk.add_descs(rec)
     pk.upload()
-    ctx.call('cpsd_svm_fit_ovr', pk.daddr(d), len(classes), k, lds)
+    ctx.call('cpsd_svm_fit_ovr_ex', pk.daddr(d), len(classes), k, lds, int(dcd_epochs))
     return classes, W.cpu().numpy(), info.cpu().numpy()
 
 

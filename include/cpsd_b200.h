@@ -351,6 +351,9 @@ int cpsd_scores_test(const float* Kte, int ldk, long long strideK, const float* 
  * decoders/cross_pt_decoders.py:46-59 */
 int cpsd_svm_fit_ovr(const cpsd_svm_desc* descs, int ntask, int k_max, int n_max,
                      cudaStream_t stream);
+/* same; dcd_epochs_max = the largest dcd_epochs of any task (0: Newton only, smaller footprint) */
+int cpsd_svm_fit_ovr_ex(const cpsd_svm_desc* descs, int ntask, int k_max, int n_max,
+                        int dcd_epochs_max, cudaStream_t stream);
 int cpsd_svm_predict_ovr(const float* Xt, int ldx, long long strideX, const double* W, int ldw,
                          long long strideW, const int* k_dev, int k_fixed, const int* n_te,
                          int n_te_max, const int* classes, int ncls, int* yhat, double* dec,
