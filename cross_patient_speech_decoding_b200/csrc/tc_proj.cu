@@ -213,6 +213,11 @@ k_proj_tc(const CUtensorMap* __restrict__ xmaps, const CUtensorMap* __restrict__
       const int r = e / Qc, j = e - r * Qc;
       rj[i] = (uint32_t)((quad * 32 + r) << 8) | (uint32_t)j;
     }
+    // staging index of the same elements (fast copy-out below)
+    int sidx[PT_N];
+#pragma unroll
+    for (int i = 0; i < PT_N; ++i) sidx[i] = (int)(rj[i] >> 8) * PT_LDS + (int)(rj[i] & 255u);
+    const int Qc_ = Q < PT_N ? Q : PT_N;
     uint32_t it_b = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
       int vv, v, tile, f0, f1;
@@ -231,8 +236,15 @@ k_proj_tc(const CUtensorMap* __restrict__ xmaps, const CUtensorMap* __restrict__
         const int f = vf / prm.nq, qc = vf - f * prm.nq;
         const int s = it_b & 1;
         const int d = (my_tr >= 0) ? dst_row[((long long)f * prm.P + v) * prm.n_max + my_tr] : -1;
-        // mu L of the (fold, chunk): lane j keeps column j, broadcast by shuffle below
-        const float ml_mine = first ? muL[((long long)(f * prm.P + v) * prm.nq + qc) * PT_N + lane] : 0.f;
+        // mu L of the (fold, chunk): 32 floats, the same for every lane (broadcast 16-byte loads,
+        // issued before the wait for the accumulator)
+        float4 ml4[PT_N / 4];
+        {
+          const float4* mp = reinterpret_cast<const float4*>(
+              muL + ((long long)(f * prm.P + v) * prm.nq + qc) * PT_N);
+#pragma unroll
+          for (int j = 0; j < PT_N / 4; ++j) ml4[j] = first ? __ldg(mp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         mbar_wait(&t_full[s], (it_b >> 1) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint32_t vv[32];
@@ -241,12 +253,27 @@ k_proj_tc(const CUtensorMap* __restrict__ xmaps, const CUtensorMap* __restrict__
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_empty[s]);
 #pragma unroll
-        for (int j = 0; j < PT_N; ++j)
-          stg[r_own * PT_LDS + j] = __uint_as_float(vv[j]) - __shfl_sync(0xffffffffu, ml_mine, j);
-        row_off[r_own] = (d >= 0) ? (d * prm.T + my_t) * Q : -1;
+        for (int j = 0; j < PT_N / 4; ++j) {
+          stg[r_own * PT_LDS + 4 * j + 0] = __uint_as_float(vv[4 * j + 0]) - ml4[j].x;
+          stg[r_own * PT_LDS + 4 * j + 1] = __uint_as_float(vv[4 * j + 1]) - ml4[j].y;
+          stg[r_own * PT_LDS + 4 * j + 2] = __uint_as_float(vv[4 * j + 2]) - ml4[j].z;
+          stg[r_own * PT_LDS + 4 * j + 3] = __uint_as_float(vv[4 * j + 3]) - ml4[j].w;
+        }
+        const int my_off = (d >= 0) ? (d * prm.T + my_t) * Q : -1;
+        row_off[r_own] = my_off;
+        // fast copy-out: the warp's 32 rows are consecutive time bins of ONE kept trial, i.e. one
+        // contiguous block of 32 Q floats that starts at lane 0's row -- element e = lane + 32 i
+        // goes to base + e, no per-element row lookup or predicate (5 of 6 blocks with T = 200)
+        const int base0 = __shfl_sync(0xffffffffu, my_off, 0);
+        const bool contiguous = __all_sync(0xffffffffu, my_off >= 0 && my_off == base0 + lane * Q);
         __syncwarp();
         float* Yf = Y + (long long)f * prm.strideY;
-        if (prm.nq == 1) {
+        if (prm.nq == 1 && first && contiguous) {
+          float* Yb = Yf + base0 + lane;
+#pragma unroll
+          for (int i = 0; i < PT_N; ++i)
+            if (i < Qc_) Yb[32 * i] = stg[sidx[i]];
+        } else if (prm.nq == 1) {
           // all shared-memory reads first (independent), then the predicated global stores
           int offs[PT_N];
           float vals[PT_N];
