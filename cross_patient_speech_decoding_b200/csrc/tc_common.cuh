@@ -44,6 +44,29 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                    smem_u32(bar))
                : "memory");
 }
+// Whole-warp forms: every lane of a CONVERGED warp executes them with the same (warp-uniform)
+// operands and one elected lane issues.  Issued from inside an `if (lane == 0)` region instead,
+// ptxas must assume divergent operands and wraps every tcgen05.mma in an elect / broadcast /
+// branch loop of ~100 cycles -- more than the 17..68 cycles the MMA itself occupies the tensor
+// pipe, so the kernels were bound by instruction issue (ncu source view, profiles/README.md).
+__device__ __forceinline__ void umma_tf32_w(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_c),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_w(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(
+          smem_u32(bar))
+      : "memory");
+}
 // K-major operand, 128-byte swizzle: 8-row groups are 1024 B apart (SBO), LBO unused.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   uint64_t d = 0;

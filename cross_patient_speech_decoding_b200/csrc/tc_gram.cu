@@ -124,7 +124,8 @@ k_gram_tc(const CUtensorMap* __restrict__ maps, const TcProb* __restrict__ probs
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // (the whole warp runs the loop converged; one elected lane issues, see umma_tf32_w)
+    {
       // instruction descriptor: D=f32, A=B=tf32, both K-major, N=128, M=128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
                              ((uint32_t)(BM >> 4) << 24);
@@ -148,14 +149,14 @@ k_gram_tc(const CUtensorMap* __restrict__ maps, const TcProb* __restrict__ probs
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k) {
             const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);   // 32 bytes per K=8 step
-            umma_tf32(tacc, a_lo + adv, b_hi + adv, idesc, (kb != c * CHUNK || k != 0) ? 1u : 0u);
-            umma_tf32(tacc, a_hi + adv, b_lo + adv, idesc, 1u);
-            umma_tf32(tacc, a_hi + adv, b_hi + adv, idesc, 1u);
+            umma_tf32_w(tacc, a_lo + adv, b_hi + adv, idesc, (kb != c * CHUNK || k != 0) ? 1u : 0u);
+            umma_tf32_w(tacc, a_hi + adv, b_lo + adv, idesc, 1u);
+            umma_tf32_w(tacc, a_hi + adv, b_hi + adv, idesc, 1u);
           }
-          umma_commit(&empty[stage]);        // frees the smem stage when the MMAs retire
+          umma_commit_w(&empty[stage]);        // frees the smem stage when the MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[as]);         // partial accumulator complete
+        umma_commit_w(&tmem_full[as]);         // partial accumulator complete
       }
     }
   } else {
@@ -296,7 +297,7 @@ k_gemm_tc_nt(const CUtensorMap* __restrict__ maps, float* __restrict__ C, int ld
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // whole warp, converged; one elected lane issues (umma_tf32_w)
       const uint32_t idesc = idesc_tf32(BM, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -316,7 +317,7 @@ k_gemm_tc_nt(const CUtensorMap* __restrict__ maps, float* __restrict__ C, int ld
 #pragma unroll
             for (int k = 0; k < BK / 8; ++k) {
               const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
-              umma_tf32(tacc, a + adv, b + adv, idesc, (kb != c * chunk || k != 0) ? 1u : 0u);
+              umma_tf32_w(tacc, a + adv, b + adv, idesc, (kb != c * chunk || k != 0) ? 1u : 0u);
             }
           } else {
             const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + TILE_BYTES);
@@ -325,15 +326,15 @@ k_gemm_tc_nt(const CUtensorMap* __restrict__ maps, float* __restrict__ C, int ld
 #pragma unroll
             for (int k = 0; k < BK / 8; ++k) {
               const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
-              umma_tf32(tacc, a_lo + adv, b_hi + adv, idesc, (kb != c * chunk || k != 0) ? 1u : 0u);
-              umma_tf32(tacc, a_hi + adv, b_lo + adv, idesc, 1u);
-              umma_tf32(tacc, a_hi + adv, b_hi + adv, idesc, 1u);
+              umma_tf32_w(tacc, a_lo + adv, b_hi + adv, idesc, (kb != c * chunk || k != 0) ? 1u : 0u);
+              umma_tf32_w(tacc, a_hi + adv, b_lo + adv, idesc, 1u);
+              umma_tf32_w(tacc, a_hi + adv, b_hi + adv, idesc, 1u);
             }
           }
-          umma_commit(&empty[stage]);
+          umma_commit_w(&empty[stage]);
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[as]);
+        umma_commit_w(&tmem_full[as]);
       }
     }
   } else {

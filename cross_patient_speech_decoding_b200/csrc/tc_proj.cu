@@ -153,7 +153,8 @@ k_proj_tc(const CUtensorMap* __restrict__ xmaps, const CUtensorMap* __restrict__
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // (whole warp, converged; one elected lane issues: see umma_tf32_w)
+    {
       const uint32_t idesc = idesc_tf32(PT_BM, PT_N);
       uint32_t it_a = 0, it_b = 0;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
@@ -181,18 +182,18 @@ k_proj_tc(const CUtensorMap* __restrict__ xmaps, const CUtensorMap* __restrict__
             for (int k = 0; k < PT_BK / 8; ++k) {
               const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
 #ifdef PT_EXPERIMENT_1TERM
-              umma_tf32(tacc, a_hi + adv, b_hi + adv, idesc, (kb != 0 || k != 0) ? 1u : 0u);
+              umma_tf32_w(tacc, a_hi + adv, b_hi + adv, idesc, (kb != 0 || k != 0) ? 1u : 0u);
 #else
-              umma_tf32(tacc, a_lo + adv, b_hi + adv, idesc, (kb != 0 || k != 0) ? 1u : 0u);
-              umma_tf32(tacc, a_hi + adv, b_lo + adv, idesc, 1u);
-              umma_tf32(tacc, a_hi + adv, b_hi + adv, idesc, 1u);
+              umma_tf32_w(tacc, a_lo + adv, b_hi + adv, idesc, (kb != 0 || k != 0) ? 1u : 0u);
+              umma_tf32_w(tacc, a_hi + adv, b_lo + adv, idesc, 1u);
+              umma_tf32_w(tacc, a_hi + adv, b_hi + adv, idesc, 1u);
 #endif
             }
           }
-          umma_commit(&b_empty[s]);
-          umma_commit(&t_full[s]);
+          umma_commit_w(&b_empty[s]);
+          umma_commit_w(&t_full[s]);
         }
-        umma_commit(a_empty);          // X panel free once every fold's MMAs retired
+        umma_commit_w(a_empty);          // X panel free once every fold's MMAs retired
         }
       }
     }
