@@ -14,7 +14,7 @@
 // Structure (one CTA per upper-triangular output tile, 192 threads):
 //   warp 0   : TMA producer   cp.async.bulk.tensor.2d -> 128B-swizzled smem ring (3 stages
 //              of {A_hi, A_lo, B_hi, B_lo}, 128 rows x 32 fp32 each)
-//   warp 1   : TMEM allocator + single-thread tcgen05.mma.kind::tf32 issuer (M=128, N=128,
+//   warp 1   : TMEM allocator + tcgen05.mma.kind::tf32 issuer, elected lane of the converged warp (M=128, N=128,
 //              K=8), tcgen05.commit releases smem stages / signals the epilogue
 //   warps 2-5: epilogue  tcgen05.ld (32 lanes x 32 columns per warp) of each partial
 //              accumulator -> fp32 register accumulators -> global, plus the mirrored tile
