@@ -233,7 +233,7 @@ k_chol_inv(const TI* __restrict__ S, int lds, long long strideS, int m,
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* P = reinterpret_cast<double*>(smem_raw);          // m x CH_LD
   __shared__ double xd[128];                                // diagonal of X = 1 / diag(L)
-  __shared__ double s_piv;
+  __shared__ double s_piv, s_inv;
   __shared__ int s_bad;
   const int prob = blockIdx.x;
   const TI* Sg = S + (long long)prob * strideS;
@@ -262,10 +262,11 @@ k_chol_inv(const TI* __restrict__ S, int lds, long long strideS, int m,
         d = floor_piv;
       }
       s_piv = sqrt(d);
-    }
+      s_inv = 1.0 / s_piv;       // one fp64 division per column, not one per thread (32 warps
+    }                            // queueing on the fp64 pipe for the same quotient)
     __syncthreads();
     const double ljj = s_piv;
-    const double inv = 1.0 / ljj;
+    const double inv = s_inv;
     for (int i = j + tid; i < m; i += CH_NT) P[i * CH_LD + j] = (i == j) ? ljj : P[i * CH_LD + j] * inv;
     __syncthreads();
     // trailing update of the lower triangle: L[i][k] -= L[i][j] L[k][j], j < k <= i < m
@@ -277,10 +278,11 @@ k_chol_inv(const TI* __restrict__ S, int lds, long long strideS, int m,
   }
   // X = L^{-1} (lower), right-looking: row k is final once scaled by 1/l_kk, then it is
   // eliminated from every row below.  X[i][c] (c < i) lives at P[c][i].
+  for (int k = tid; k < m; k += CH_NT) xd[k] = 1.0 / P[k * CH_LD + k];   // all reciprocal pivots at once
+  __syncthreads();
   for (int k = 0; k < m; ++k) {
-    const double inv = 1.0 / P[k * CH_LD + k];
+    const double inv = xd[k];
     for (int c = tid; c < k; c += CH_NT) P[c * CH_LD + k] *= inv;
-    if (tid == 0) xd[k] = inv;
     __syncthreads();
     for (int i = k + 1 + ty; i < m; i += 32) {
       const double lik = P[i * CH_LD + k];
