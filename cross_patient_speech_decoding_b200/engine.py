@@ -1634,18 +1634,7 @@ class CVEngine:
                 vb = self._view_bases()
                 s_f = np.array([t[0] for t in solve], dtype=np.int64)
                 code = rep[s_f] * P + np.array([t[1] for t in solve], dtype=np.int64)
-                tab = vb['tab']
-                base_of = tab[code].copy()
-                miss = np.nonzero(base_of < 0)[0]
-                cold = np.zeros(0, dtype=np.int64)
-                if len(miss):
-                    uc, first_miss = np.unique(code[miss], return_index=True)
-                    cold = miss[first_miss]
-                    tab = tab.copy()
-                    tab[uc] = vb['n'] + np.arange(len(uc), dtype=np.int32)
-                    base_of = tab[code].copy()
-                    base_of[cold] = -1
-                warm_i = np.nonzero(base_of >= 0)[0]
+                cold, warm_i, base_of, tab = plan_view_solves(code, vb['tab'], vb['n'])
                 s_slot = np.array([t[2] for t in solve], dtype=np.int32)
                 wplan = dict(ncold=len(cold), nwarm=len(warm_i), tab=tab,
                              o_selc=pk.add_ints(cold), o_cslot=pk.add_ints(s_slot[cold]),
@@ -2206,6 +2195,29 @@ class CVEngine:
     def _batch_cca(self, batch, want_details):
         from .engine_cca import batch_cca
         return batch_cca(self, batch, want_details)
+
+
+def plan_view_solves(code, tab, n_bases):
+    """Warm-start plan of a batch of per-view eigenproblems.  ``code[i]`` = (replica, patient) pair
+    of problem i, ``tab[pair]`` = index of the pair's basis or -1, ``n_bases`` = bases stored so far.
+    The first problem of every pair without a basis is solved cold and becomes the pair's basis
+    (bases are numbered in ascending pair order from ``n_bases``); all other problems are warm.
+    Returns (cold problem indices, warm problem indices ascending, base_of[i] = basis of problem i
+    or -1 for a cold one, the updated table -- a copy, committed by the caller once the cold
+    solves are queued)."""
+    code = np.asarray(code, dtype=np.int64)
+    base_of = tab[code].astype(np.int32)
+    miss = np.nonzero(base_of < 0)[0]
+    cold = np.zeros(0, dtype=np.int64)
+    if len(miss):
+        uc, first_miss = np.unique(code[miss], return_index=True)
+        cold = miss[first_miss]
+        tab = tab.copy()
+        tab[uc] = n_bases + np.arange(len(uc), dtype=np.int32)
+        base_of = tab[code].astype(np.int32)
+        base_of[cold] = -1
+    warm_i = np.nonzero(base_of >= 0)[0]
+    return cold, warm_i, base_of, tab
 
 
 def _w_host(W):

@@ -201,3 +201,30 @@ def test_bayes_search_space_and_proposals():
                                       'decoder_var': ha[0]['decoder__dimredreshape__n_components']}
     with pytest.raises(ValueError):
         engine_keywords({'decoder__baggingclassifier__n_estimators': 10})
+
+
+def test_warm_start_plan_of_view_solves():
+    """Host logic of the warm-started view solves (engine.plan_view_solves): the first problem of
+    every (replica, patient) pair without a basis is cold and founds the pair's basis, everything
+    else is warm from its pair's basis; bases persist across batches."""
+    from cross_patient_speech_decoding_b200.engine import plan_view_solves
+    P = 3
+    tab = -np.ones(2 * P, dtype=np.int32)
+    # batch 1: replica 0 targets (pair 0) x3, replica 1 target (pair 3), cross problems of pairs 1, 2, 1, 4
+    code = np.array([0, 0, 0, 3, 1, 2, 1, 4])
+    cold, warm, base_of, tab1 = plan_view_solves(code, tab, 0)
+    assert sorted(cold.tolist()) == [0, 3, 4, 5, 7]            # first problem of pairs 0, 3, 1, 2, 4
+    assert warm.tolist() == [1, 2, 6]
+    assert (tab == -1).all()                                    # the caller's table is not touched
+    assert tab1.tolist() == [0, 1, 2, 3, 4, -1]                 # bases numbered in pair order
+    assert base_of.tolist() == [-1, 0, 0, -1, -1, -1, 1, -1]
+    # the base founded by a cold problem has the index its pair got
+    assert [int(tab1[code[i]]) for i in cold] == [0, 1, 2, 3, 4]   # cold problem i founds base n_bases + i
+    # batch 2: everything known except pair 5
+    code2 = np.array([0, 3, 5, 5, 2])
+    cold2, warm2, base2, tab2 = plan_view_solves(code2, tab1, 5)
+    assert cold2.tolist() == [2] and warm2.tolist() == [0, 1, 3, 4]
+    assert tab2.tolist() == [0, 1, 2, 3, 4, 5] and base2.tolist() == [0, 3, -1, 5, 2]
+    # nothing new: no copy needed, nothing cold
+    cold3, warm3, base3, tab3 = plan_view_solves(code2, tab2, 6)
+    assert len(cold3) == 0 and warm3.tolist() == [0, 1, 2, 3, 4] and tab3 is tab2
